@@ -1,0 +1,42 @@
+// Library-level entry points: status strings, diagnostics and the avec_gemm dispatcher.
+#include "common.cuh"
+
+static thread_local int g_last_cuda_error = 0;
+static thread_local long long g_launches = 0;
+
+void avec_set_last_cuda_error(int e) { g_last_cuda_error = e; }
+void avec_count_launch() { ++g_launches; }
+
+int avec_gemm_simt(const avec_gemm_args* a, cudaStream_t st);
+int avec_gemm_tc(const avec_gemm_args* a, cudaStream_t st);       // gemm_tc.cu
+bool avec_gemm_tc_supported(const avec_gemm_args* a);             // gemm_tc.cu
+
+extern "C" const char* avec_strerror(int status) {
+    switch (status) {
+    case AVEC_OK: return "ok";
+    case AVEC_ERR_INVALID: return "invalid argument or unsupported shape";
+    case AVEC_ERR_LAUNCH: return "CUDA launch failed (see avec_last_cuda_error)";
+    case AVEC_ERR_UNSUPPORTED: return "combination not implemented";
+    case AVEC_ERR_DRIVER: return "CUDA driver entry point unavailable or tensor-map encode failed";
+    default: return "unknown avec status";
+    }
+}
+extern "C" int avec_last_cuda_error(void) { return g_last_cuda_error; }
+extern "C" int avec_version(void) { return 100; }
+extern "C" long long avec_launch_count(void) { return g_launches; }
+extern "C" void avec_reset_launch_count(void) { g_launches = 0; }
+
+extern "C" int avec_gemm(const avec_gemm_args* a, avec_stream_t stream) {
+    AVEC_CHECK_ARG(a && a->A && a->B && a->out && a->M > 0 && a->N > 0 && a->K > 0);
+    AVEC_CHECK_ARG(a->epi >= AVEC_EPI_LINEAR && a->epi <= AVEC_EPI_RELU);
+    AVEC_CHECK_ARG(a->epi != AVEC_EPI_ACCUM || a->out_dtype == AVEC_F32);
+    AVEC_CHECK_ARG((a->epi != AVEC_EPI_RESIDUAL && a->epi != AVEC_EPI_DSWISH) || a->aux);
+    cudaStream_t st = as_stream(stream);
+    if (a->impl == AVEC_IMPL_SIMT) return avec_gemm_simt(a, st);
+    if (a->impl == AVEC_IMPL_TCGEN05) {
+        if (!avec_gemm_tc_supported(a)) return AVEC_ERR_UNSUPPORTED;
+        return avec_gemm_tc(a, st);
+    }
+    if (avec_gemm_tc_supported(a)) return avec_gemm_tc(a, st);
+    return avec_gemm_simt(a, st);
+}

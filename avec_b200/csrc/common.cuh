@@ -1,0 +1,130 @@
+// Shared device/host helpers for the avec_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include "../../include/avec_b200.h"
+
+#define AVEC_CHECK_ARG(cond) do { if (!(cond)) return AVEC_ERR_INVALID; } while (0)
+#define AVEC_LAUNCH_CHECK() do { avec_count_launch(); cudaError_t e__ = cudaGetLastError(); if (e__ != cudaSuccess) { avec_set_last_cuda_error((int)e__); return AVEC_ERR_LAUNCH; } } while (0)
+
+void avec_set_last_cuda_error(int e);
+void avec_count_launch();
+
+static inline cudaStream_t as_stream(avec_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline long long cdivll(long long a, long long b) { return (a + b - 1) / b; }
+
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ float ldf(const float* p) { return *p; }
+__device__ __forceinline__ float ldf(const bf16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void stf(float* p, float v) { *p = v; }
+__device__ __forceinline__ void stf(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+// runtime-dtype element access (used by epilogues where templating every combination is not worth it)
+__device__ __forceinline__ float ld_any(const void* p, int dtype, size_t idx) {
+    return dtype == AVEC_F32 ? reinterpret_cast<const float*>(p)[idx]
+                             : __bfloat162float(reinterpret_cast<const bf16*>(p)[idx]);
+}
+__device__ __forceinline__ void st_any(void* p, int dtype, size_t idx, float v) {
+    if (dtype == AVEC_F32) reinterpret_cast<float*>(p)[idx] = v;
+    else reinterpret_cast<bf16*>(p)[idx] = __float2bfloat16_rn(v);
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float swishf_(float x) { return x * sigmoidf_(x); }
+// d/dx [x*sigmoid(x)] = s * (1 + x*(1-s))
+__device__ __forceinline__ float dswishf_(float x) { float s = sigmoidf_(x); return s * (1.0f + x * (1.0f - s)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// dispatch a runtime dtype code onto a template parameter
+#define AVEC_DISPATCH_DTYPE(code, T, ...)                                   \
+    do {                                                                    \
+        if ((code) == AVEC_F32) { using T = float; __VA_ARGS__; }           \
+        else if ((code) == AVEC_BF16) { using T = bf16; __VA_ARGS__; }      \
+        else return AVEC_ERR_INVALID;                                       \
+    } while (0)
+
+// ---- GEMM epilogue shared by the SIMT kernel and the tcgen05 kernel ------------------------------
+struct EpiParams {
+    int M, N;
+    int kind;
+    float alpha;
+    const float* bias;
+    void* out; int out_dtype; long long ldo;
+    void* out2; int out2_dtype; long long ldo2;
+    const void* aux; int aux_dtype; long long ldaux;
+    float* colstats;
+};
+
+static inline EpiParams make_epi(const avec_gemm_args* a) {
+    EpiParams p;
+    p.M = a->M; p.N = a->N; p.kind = a->epi; p.alpha = a->alpha; p.bias = a->bias;
+    p.out = a->out; p.out_dtype = a->out_dtype; p.ldo = a->ldo;
+    p.out2 = a->out2; p.out2_dtype = a->out2_dtype; p.ldo2 = a->ldo2;
+    p.aux = a->aux; p.aux_dtype = a->aux_dtype; p.ldaux = a->ldaux;
+    p.colstats = a->colstats;
+    return p;
+}
+
+// Apply the epilogue to one accumulator element (acc already holds the K-sum).  Returns v = acc + bias so that the
+// caller can accumulate BatchNorm column statistics from exactly what was normalised.
+__device__ __forceinline__ float epilogue_elem(const EpiParams& p, int row, int c, float acc) {
+    float v = acc + (p.bias ? p.bias[c] : 0.0f);
+    const size_t o = (size_t)row * p.ldo + c;
+    switch (p.kind) {
+    case AVEC_EPI_LINEAR:
+        st_any(p.out, p.out_dtype, o, p.alpha * v);
+        break;
+    case AVEC_EPI_SWISH:
+        if (p.out2) st_any(p.out2, p.out2_dtype, (size_t)row * p.ldo2 + c, v);
+        st_any(p.out, p.out_dtype, o, swishf_(v));
+        break;
+    case AVEC_EPI_RESIDUAL:
+        st_any(p.out, p.out_dtype, o, ld_any(p.aux, p.aux_dtype, (size_t)row * p.ldaux + c) + p.alpha * v);
+        break;
+    case AVEC_EPI_DSWISH:
+        st_any(p.out, p.out_dtype, o, p.alpha * v * dswishf_(ld_any(p.aux, p.aux_dtype, (size_t)row * p.ldaux + c)));
+        break;
+    case AVEC_EPI_ACCUM:
+        atomicAdd(reinterpret_cast<float*>(p.out) + o, p.alpha * v);
+        break;
+    case AVEC_EPI_RELU: {
+        float r = p.alpha * v;
+        if (p.aux) r += ld_any(p.aux, p.aux_dtype, (size_t)row * p.ldaux + c);
+        st_any(p.out, p.out_dtype, o, fmaxf(r, 0.0f));
+        break;
+    }
+    default: break;
+    }
+    return v;
+}
+
+// ---- convolution geometry helpers ------------------------------------------------------------------
+struct ConvGeom {
+    int N, Ti, Hi, Wi, C;
+    int To, Ho, Wo, Co;
+    int KT, KH, KW;
+    int st, sh, sw;
+    int pt, ph, pw;
+};
+static inline ConvGeom make_geom(const avec_conv_geom& g) {
+    ConvGeom c;
+    c.N = g.N; c.Ti = g.Ti; c.Hi = g.Hi; c.Wi = g.Wi; c.C = g.C;
+    c.To = g.To; c.Ho = g.Ho; c.Wo = g.Wo; c.Co = g.Co;
+    c.KT = g.KT; c.KH = g.KH; c.KW = g.KW;
+    c.st = g.st; c.sh = g.sh; c.sw = g.sw;
+    c.pt = g.pt; c.ph = g.ph; c.pw = g.pw;
+    return c;
+}

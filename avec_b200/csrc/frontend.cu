@@ -1,0 +1,82 @@
+// Audio front-end: framing + Hann window + 512-point FFT + power spectrum + mel filterbank + log, one kernel.
+// Follows torchaudio.transforms.Spectrogram(n_fft=512, win_length=400, hop_length=160, center=True, pad_mode="reflect",
+// power=2, hann periodic, window zero-padded to n_fft on both sides) -> MelScale(80 mels, htk, norm=None) ->
+// log(x + 1e-9), as called by AudioPreprocessing.forward (reference nnet/preprocessing.py:57-85).
+// cuFFT-free: one warp = one frame, radix-2 DIT in shared memory; HBM traffic = 4 B/sample in, 320 B/frame out.
+#include "common.cuh"
+
+namespace {
+
+constexpr int NFFT = 512, WIN = 400, HOP = 160, NBIN = 257, NMEL = 80;
+constexpr int WOFF = (NFFT - WIN) / 2;  // 56
+constexpr int FR_PER_CTA = 4;
+
+__device__ __forceinline__ int bitrev9(int x) { return (int)(__brev((unsigned)x) >> 23); }
+
+__global__ void __launch_bounds__(FR_PER_CTA * 32) stft_mel_log_kernel(const float* __restrict__ wave, const float* __restrict__ fb,
+                                                                     float* __restrict__ out, int L, int F, int layout) {
+    __shared__ float2 tw[NFFT / 2];
+    __shared__ float win[WIN];
+    __shared__ float2 buf[FR_PER_CTA][NFFT];
+    __shared__ float pw[FR_PER_CTA][NBIN + 3];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b = blockIdx.y;
+    for (int k = tid; k < NFFT / 2; k += blockDim.x) {
+        float s, c;
+        sincospif(-2.0f * (float)k / (float)NFFT, &s, &c);
+        tw[k] = make_float2(c, s);
+    }
+    for (int n = tid; n < WIN; n += blockDim.x) win[n] = 0.5f - 0.5f * cospif(2.0f * (float)n / (float)WIN);
+    __syncthreads();
+    const int f = blockIdx.x * FR_PER_CTA + warp;
+    if (f >= F) return;  // no block-level barrier below
+    const float* x = wave + (size_t)b * L;
+    float2* xb = buf[warp];
+    // load (reflect padding of 256 on both sides), window, bit-reversed placement
+    for (int n = lane; n < NFFT; n += 32) {
+        float v = 0.0f;
+        if (n >= WOFF && n < WOFF + WIN) {
+            int idx = f * HOP + n - NFFT / 2;
+            if (idx < 0) idx = -idx;
+            if (idx >= L) idx = 2 * (L - 1) - idx;
+            idx = max(0, min(L - 1, idx));
+            v = x[idx] * win[n - WOFF];
+        }
+        xb[bitrev9(n)] = make_float2(v, 0.0f);
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int len = 2; len <= NFFT; len <<= 1) {
+        const int half = len >> 1, step = NFFT / len;
+        for (int j = lane; j < NFFT / 2; j += 32) {
+            int grp = j / half, pos = j % half;
+            int i0 = grp * len + pos, i1 = i0 + half;
+            float2 w = tw[pos * step];
+            float2 a = xb[i0], c = xb[i1];
+            float2 t = make_float2(w.x * c.x - w.y * c.y, w.x * c.y + w.y * c.x);
+            xb[i0] = make_float2(a.x + t.x, a.y + t.y);
+            xb[i1] = make_float2(a.x - t.x, a.y - t.y);
+        }
+        __syncwarp();
+    }
+    for (int k = lane; k < NBIN; k += 32) { float2 v = xb[k]; pw[warp][k] = v.x * v.x + v.y * v.y; }
+    __syncwarp();
+    for (int m = lane; m < NMEL; m += 32) {
+        float acc = 0.0f;
+        for (int k = 0; k < NBIN; ++k) acc = fmaf(pw[warp][k], __ldg(fb + k * NMEL + m), acc);
+        float v = logf(acc + 1e-9f);
+        if (layout == 0) out[((size_t)b * F + f) * NMEL + m] = v;
+        else out[((size_t)b * NMEL + m) * F + f] = v;
+    }
+}
+
+}  // namespace
+
+extern "C" int avec_stft_mel_log(const float* wave, const float* fb, float* out, int B, int L, int F, int layout,
+                                 avec_stream_t stream) {
+    AVEC_CHECK_ARG(wave && fb && out && B > 0 && B <= 65535 && L > NFFT / 2 && F == L / HOP + 1 && (layout == 0 || layout == 1));
+    dim3 grid(cdiv(F, FR_PER_CTA), B);
+    stft_mel_log_kernel<<<grid, FR_PER_CTA * 32, 0, as_stream(stream)>>>(wave, fb, out, L, F, layout);
+    AVEC_LAUNCH_CHECK();
+    return AVEC_OK;
+}

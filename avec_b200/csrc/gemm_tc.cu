@@ -1,0 +1,458 @@
+// tcgen05 / TMEM GEMM and implicit-GEMM convolution for sm_100a (bf16 operands, fp32 accumulate in tensor memory).
+//
+// One CTA computes one 128 x BN output tile (BN = multiple of 16, <= 256, chosen per problem so that awkward widths
+// such as 180 / 360 / 720 / 1080 waste few columns).  Warp roles:
+//   warps 0-3  producers: gather 128-byte row slices (64 bf16) of both operands from HBM/L2 into the canonical
+//              128B-swizzled shared-memory layout UMMA expects (K-major: smem row = matrix row, MN-major: smem row =
+//              reduction index), zero-filling out-of-range rows / taps / tails; then, once the main loop is done, the
+//              same four warps are the epilogue (tcgen05.ld of their TMEM lane quarter -> fused epilogue -> HBM);
+//   warp 4     lane 0 issues tcgen05.mma (UMMA 128 x BN x 16, kind::f16) over a STAGES-deep mbarrier ring and commits
+//              stage-free / accumulator-ready barriers; the warp also owns the TMEM allocation.
+// The gather producers are what let ONE kernel serve: plain linears with any leading dimension (D = 180 rows are not
+// 16-byte aligned, which rules out a TMA descriptor), transposed operands of dgrad / wgrad (MN-major descriptors, no
+// transposed copies in HBM), and the ResNet / strided convolutions as implicit GEMMs (im2col never materialised).
+#include "common.cuh"
+#include <cstring>
+#include <cstdint>
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BKE = 64;                  // reduction elements per k-block (one 128-byte swizzle row)
+constexpr int PRODUCER_THREADS = 128;
+constexpr int TC_THREADS = 160;
+
+enum OperandKind {
+    OP_PLAIN_K = 0,    // element (row, k) at base[row*ld + k]               -> K-major tile
+    OP_PLAIN_MN = 1,   // element (row, k) at base[k*ld + row]               -> MN-major tile
+    OP_CONV_FWD = 2,   // A: row = output site, k = (tap, ci)                 -> K-major
+    OP_CONV_DGRAD = 3, // A: row = input site, k = (tap, co), gather from dY  -> K-major
+    OP_CONV_WGRAD_X = 4 // B: row = (tap, ci), k = output site, gather from X  -> MN-major
+};
+
+struct TcParams {
+    int M, N, K;
+    int BN;
+    int stages;
+    int num_kb, kb_per_split;
+    int a_kind, b_kind;
+    const bf16* A; long long a_ld; int a_align;
+    const bf16* B; long long b_ld; int b_align;
+    ConvGeom g;
+    int cpb;  // 64-channel blocks per filter tap
+    EpiParams ep;
+    int out_transposed;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor, SWIZZLE_128B, Blackwell version bits (cute::UMMA::SmemDescriptor layout)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;  // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+    return d;
+}
+// instruction descriptor for kind::f16: BF16 x BF16 -> F32, M = 128
+__device__ __forceinline__ uint32_t make_idesc(int n, int a_mn, int b_mn) {
+    uint32_t d = 0;
+    d |= 1u << 4;                       // D format F32
+    d |= 1u << 7;                       // A format BF16
+    d |= 1u << 10;                      // B format BF16
+    d |= (uint32_t)(a_mn & 1) << 15;    // A major (0 = K, 1 = MN)
+    d |= (uint32_t)(b_mn & 1) << 16;    // B major
+    d |= (uint32_t)(n >> 3) << 17;      // N / 8
+    d |= (uint32_t)(BM >> 4) << 24;     // M / 16
+    return d;
+}
+
+// ---------------------------------------------------------------- gather producer
+// load 8 consecutive bf16 (one 16-byte smem chunk); nv = number of valid elements (0..8), the rest are zeros
+__device__ __forceinline__ uint4 load_chunk(const bf16* p, int nv, int align) {
+    uint4 r = make_uint4(0u, 0u, 0u, 0u);
+    if (nv <= 0) return r;
+    if (nv >= 8) {
+        if (align >= 16) return __ldg(reinterpret_cast<const uint4*>(p));
+        if (align >= 8) {
+            uint2 a = __ldg(reinterpret_cast<const uint2*>(p)), b = __ldg(reinterpret_cast<const uint2*>(p) + 1);
+            return make_uint4(a.x, a.y, b.x, b.y);
+        }
+        if (align >= 4) {
+            const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
+            return make_uint4(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3));
+        }
+    }
+    const unsigned short* q = reinterpret_cast<const unsigned short*>(p);
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        if (i < nv) w[i >> 1] |= (uint32_t)__ldg(q + i) << ((i & 1) * 16);
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+struct RowInfo { int n, t, h, w; };
+
+// Fill `rows` smem rows (128 B each, 128B-swizzled, tile base 1024-aligned) of one operand tile for k-block kb.
+// `tile0` = first matrix row (K-major kinds) or first MN index (MN-major kinds) of this CTA's tile.
+__device__ __forceinline__ void fill_operand(uint8_t* tile, int rows, int kind, const bf16* __restrict__ base, long long ld, int align,
+                                             int R, int K, int tile0, int kb, const TcParams& p, const RowInfo* __restrict__ rinfo, int pt) {
+    const int chunk = pt & 7;
+    const int r_first = pt >> 3;  // 0..15
+    // filter tap of this k-block (conv kinds)
+    int kt = 0, kh = 0, kw = 0, cb = 0;
+    if (kind == OP_CONV_FWD || kind == OP_CONV_DGRAD) {
+        int tap = kb / p.cpb; cb = kb % p.cpb;
+        kw = tap % p.g.KW; tap /= p.g.KW; kh = tap % p.g.KH; kt = tap / p.g.KH;
+    }
+    for (int r0 = 0; r0 < rows; r0 += 128) {
+        uint4 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = r0 + r_first + 16 * i;
+            v[i] = make_uint4(0u, 0u, 0u, 0u);
+            if (r >= rows) continue;
+            const bf16* src = nullptr;
+            int nv = 0;
+            if (kind == OP_PLAIN_K) {
+                const int row = tile0 + r, k = kb * BKE + chunk * 8;
+                if (row < R) { src = base + (long long)row * ld + k; nv = K - k; }
+            } else if (kind == OP_PLAIN_MN) {
+                // smem row = (group g = r / 64, reduction index kk = r % 64); 128 bytes = MN indices tile0 + 64 g + [0, 64)
+                const int g = r >> 6, kk = kb * BKE + (r & 63), mn = tile0 + g * 64 + chunk * 8;
+                if (kk < K) { src = base + (long long)kk * ld + mn; nv = R - mn; }
+            } else if (kind == OP_CONV_FWD) {
+                const RowInfo ri = rinfo[r];
+                const int ti = ri.t + kt, hi = ri.h + kh, wi = ri.w + kw;
+                if (ri.n >= 0 && (unsigned)ti < (unsigned)p.g.Ti && (unsigned)hi < (unsigned)p.g.Hi && (unsigned)wi < (unsigned)p.g.Wi) {
+                    src = base + ((((long long)ri.n * p.g.Ti + ti) * p.g.Hi + hi) * p.g.Wi + wi) * p.g.C + cb * BKE + chunk * 8;
+                    nv = 8;
+                }
+            } else if (kind == OP_CONV_DGRAD) {
+                const RowInfo ri = rinfo[r];
+                const int a = ri.t - kt, b = ri.h - kh, c = ri.w - kw;
+                if (ri.n >= 0 && a >= 0 && b >= 0 && c >= 0 && a % p.g.st == 0 && b % p.g.sh == 0 && c % p.g.sw == 0) {
+                    const int to = a / p.g.st, ho = b / p.g.sh, wo = c / p.g.sw;
+                    if (to < p.g.To && ho < p.g.Ho && wo < p.g.Wo) {
+                        src = base + ((((long long)ri.n * p.g.To + to) * p.g.Ho + ho) * p.g.Wo + wo) * p.g.Co + cb * BKE + chunk * 8;
+                        nv = 8;
+                    }
+                }
+            } else {  // OP_CONV_WGRAD_X: group g -> (tap, ci block); smem row kk -> output site
+                const int g = r >> 6;
+                const int G = tile0 / 64 + g;
+                const long long site = (long long)kb * BKE + (r & 63);
+                if (site < K && G * 64 < R) {
+                    int tap = G / p.cpb; const int cbl = G % p.cpb;
+                    const int fw = tap % p.g.KW; tap /= p.g.KW; const int fh = tap % p.g.KH; const int ft = tap / p.g.KH;
+                    long long s = site;
+                    const int wo = (int)(s % p.g.Wo); s /= p.g.Wo;
+                    const int ho = (int)(s % p.g.Ho); s /= p.g.Ho;
+                    const int to = (int)(s % p.g.To); const int n = (int)(s / p.g.To);
+                    const int ti = to * p.g.st + ft - p.g.pt, hi = ho * p.g.sh + fh - p.g.ph, wi = wo * p.g.sw + fw - p.g.pw;
+                    if ((unsigned)ti < (unsigned)p.g.Ti && (unsigned)hi < (unsigned)p.g.Hi && (unsigned)wi < (unsigned)p.g.Wi) {
+                        src = base + ((((long long)n * p.g.Ti + ti) * p.g.Hi + hi) * p.g.Wi + wi) * p.g.C + cbl * BKE + chunk * 8;
+                        nv = 8;
+                    }
+                }
+            }
+            if (src) v[i] = load_chunk(src, nv, align);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = r0 + r_first + 16 * i;
+            if (r < rows) *reinterpret_cast<uint4*>(tile + (size_t)r * 128 + ((chunk ^ (r & 7)) << 4)) = v[i];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int BN = p.BN;
+    const int a_bytes = BM * 128;
+    const int b_rows = (p.b_kind == OP_PLAIN_K) ? BN : ((BN + 63) / 64) * 64;
+    const int b_bytes = ((b_rows * 128 + 1023) / 1024) * 1024;
+    const int stage_bytes = a_bytes + b_bytes;
+    uint8_t* ctrl = smem + (size_t)p.stages * stage_bytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);
+    uint64_t* empty_bar = full_bar + 8;
+    uint64_t* accum_bar = empty_bar + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+    RowInfo* rinfo = reinterpret_cast<RowInfo*>(ctrl + 256);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int kb_begin = blockIdx.z * p.kb_per_split;
+    const int kb_end = min(p.num_kb, kb_begin + p.kb_per_split);
+    const int nkb = kb_end - kb_begin;
+
+    // TMEM columns: power of two >= 32 covering BN
+    uint32_t ncols = 32;
+    while ((int)ncols < BN) ncols <<= 1;
+
+    if (tid == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], PRODUCER_THREADS); mbar_init(&empty_bar[s], 1); }
+        mbar_init(accum_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 4) tmem_alloc(tmem_slot, ncols);
+    // per-row site decode for the conv gathers (A operand rows are fixed for the whole tile)
+    if (tid < BM && (p.a_kind == OP_CONV_FWD || p.a_kind == OP_CONV_DGRAD)) {
+        RowInfo ri; ri.n = -1; ri.t = ri.h = ri.w = 0;
+        long long m = (long long)m0 + tid;
+        if (m < p.M) {
+            if (p.a_kind == OP_CONV_FWD) {
+                int wo = (int)(m % p.g.Wo); m /= p.g.Wo; int ho = (int)(m % p.g.Ho); m /= p.g.Ho; int to = (int)(m % p.g.To);
+                ri.n = (int)(m / p.g.To);
+                ri.t = to * p.g.st - p.g.pt; ri.h = ho * p.g.sh - p.g.ph; ri.w = wo * p.g.sw - p.g.pw;
+            } else {
+                int wi = (int)(m % p.g.Wi); m /= p.g.Wi; int hi = (int)(m % p.g.Hi); m /= p.g.Hi; int ti = (int)(m % p.g.Ti);
+                ri.n = (int)(m / p.g.Ti);
+                ri.t = ti + p.g.pt; ri.h = hi + p.g.ph; ri.w = wi + p.g.pw;
+            }
+        }
+        rinfo[tid] = ri;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        // ===================== producers =====================
+        const bool a_mn = p.a_kind == OP_PLAIN_MN;
+        for (int i = 0; i < nkb; ++i) {
+            const int s = i % p.stages;
+            const uint32_t ph = (uint32_t)((i / p.stages) & 1);
+            mbar_wait(&empty_bar[s], ph ^ 1u);
+            uint8_t* a_tile = smem + (size_t)s * stage_bytes;
+            uint8_t* b_tile = a_tile + a_bytes;
+            const int kb = kb_begin + i;
+            fill_operand(a_tile, BM, p.a_kind, p.A, p.a_ld, p.a_align, p.M, p.K, a_mn ? m0 : m0, kb, p, rinfo, tid);
+            fill_operand(b_tile, b_rows, p.b_kind, p.B, p.b_ld, p.b_align, p.N, p.K, n0, kb, p, rinfo, tid);
+            fence_proxy_async();
+            mbar_arrive(&full_bar[s]);
+        }
+        // ===================== epilogue =====================
+        mbar_wait(accum_bar, 0u);
+        tc_fence_after();
+        const int row = m0 + warp * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        EpiParams ep = p.ep;
+        if (blockIdx.z > 0) ep.bias = nullptr;
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+            float v[16];
+            tmem_ld16(lane_addr + (uint32_t)c0, v);
+            float s1[16], s2[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const int c = n0 + c0 + j;
+                float val = 0.0f;
+                if (row < p.M && c < p.N) {
+                    if (p.out_transposed) {
+                        // only LINEAR / ACCUM make sense transposed (weight gradients): out[c][row]
+                        float vv = v[j] + (ep.bias ? ep.bias[c] : 0.0f);
+                        size_t o = (size_t)c * ep.ldo + row;
+                        if (ep.kind == AVEC_EPI_ACCUM) atomicAdd(reinterpret_cast<float*>(ep.out) + o, ep.alpha * vv);
+                        else st_any(ep.out, ep.out_dtype, o, ep.alpha * vv);
+                        val = vv;
+                    } else {
+                        val = epilogue_elem(ep, row, c, v[j]);
+                    }
+                }
+                s1[j] = val; s2[j] = val * val;
+            }
+            if (ep.colstats) {
+                // column sums over this warp's 32 rows: butterfly reduce, then one atomic per column per warp
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { s1[j] = warp_sum(s1[j]); s2[j] = warp_sum(s2[j]); }
+                if (lane < 16) {
+                    const int c = n0 + c0 + lane;
+                    float a = 0.0f, b = 0.0f;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) if (j == lane) { a = s1[j]; b = s2[j]; }
+                    if (c < p.N) { atomicAdd(ep.colstats + c, a); atomicAdd(ep.colstats + p.N + c, b); }
+                }
+            }
+        }
+        tc_fence_before();
+    } else {
+        // ===================== MMA issuer =====================
+        const int a_mn = p.a_kind == OP_PLAIN_MN ? 1 : 0;
+        const int b_mn = (p.b_kind == OP_PLAIN_MN || p.b_kind == OP_CONV_WGRAD_X) ? 1 : 0;
+        const uint32_t idesc = make_idesc(BN, a_mn, b_mn);
+        for (int i = 0; i < nkb; ++i) {
+            const int s = i % p.stages;
+            const uint32_t ph = (uint32_t)((i / p.stages) & 1);
+            mbar_wait(&full_bar[s], ph);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
+                const uint32_t b_addr = a_addr + a_bytes;
+#pragma unroll
+                for (int k = 0; k < BKE / 16; ++k) {
+                    // K-major: advance 32 bytes inside the 128-byte swizzle row; SBO = 1024 (8 rows).
+                    // MN-major: advance 16 reduction rows = 2048 bytes; LBO = 8192 (next 64-wide MN group), SBO = 1024.
+                    const uint64_t adesc = a_mn ? make_smem_desc(a_addr + k * 2048, 8192, 1024) : make_smem_desc(a_addr + k * 32, 16, 1024);
+                    const uint64_t bdesc = b_mn ? make_smem_desc(b_addr + k * 2048, 8192, 1024) : make_smem_desc(b_addr + k * 32, 16, 1024);
+                    umma_f16(tmem_base, adesc, bdesc, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[s]);
+                if (i == nkb - 1) umma_commit(accum_bar);
+            }
+            __syncwarp();
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_base, ncols); }
+}
+
+int pick_bn(int N) {
+    int ntiles = cdiv(N, 256);
+    int bn = cdiv(cdiv(N, ntiles), 16) * 16;
+    return bn < 16 ? 16 : bn;
+}
+int ptr_align(const void* p, long long ld_elems) {
+    uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    long long ldb = ld_elems * 2;
+    int al = 16;
+    while (al > 2 && ((a % al) != 0 || (ldb % al) != 0)) al >>= 1;
+    return al;
+}
+
+}  // namespace
+
+bool avec_gemm_tc_supported(const avec_gemm_args* a) {
+    if (a->ab_dtype != AVEC_BF16) return false;
+    const avec_conv_geom& g = a->g;
+    switch (a->mode) {
+    case AVEC_GEMM_PLAIN: {
+        bool ak = a->sak == 1, am = a->sam == 1;
+        bool bk = a->sbk == 1, bm = a->sbn == 1;
+        if (!(ak || am) || !(bk || bm)) return false;
+        // tiny problems are not worth a 128-row tile
+        if ((long long)a->M * a->N * a->K < (1LL << 18)) return false;
+        return true;
+    }
+    case AVEC_GEMM_CONV_FWD: return g.C % 64 == 0;
+    case AVEC_GEMM_CONV_DGRAD: return g.Co % 64 == 0;
+    case AVEC_GEMM_CONV_WGRAD: return g.C % 64 == 0;
+    default: return false;
+    }
+}
+
+int avec_gemm_tc(const avec_gemm_args* a, cudaStream_t st) {
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    p.M = a->M; p.N = a->N; p.K = a->K;
+    p.A = reinterpret_cast<const bf16*>(a->A);
+    p.B = reinterpret_cast<const bf16*>(a->B);
+    p.g = make_geom(a->g);
+    p.ep = make_epi(a);
+    p.out_transposed = 0;
+    const int taps = p.g.KT * p.g.KH * p.g.KW;
+    switch (a->mode) {
+    case AVEC_GEMM_PLAIN:
+        if (a->sak == 1) { p.a_kind = OP_PLAIN_K; p.a_ld = a->sam; } else { p.a_kind = OP_PLAIN_MN; p.a_ld = a->sak; }
+        if (a->sbk == 1) { p.b_kind = OP_PLAIN_K; p.b_ld = a->sbn; } else { p.b_kind = OP_PLAIN_MN; p.b_ld = a->sbk; }
+        p.num_kb = cdiv(a->K, BKE);
+        break;
+    case AVEC_GEMM_CONV_FWD:
+        AVEC_CHECK_ARG(a->K == taps * p.g.C && a->N == p.g.Co);
+        p.a_kind = OP_CONV_FWD; p.a_ld = p.g.C;
+        p.b_kind = OP_PLAIN_K; p.b_ld = a->K;
+        p.cpb = p.g.C / 64; p.num_kb = taps * p.cpb;
+        break;
+    case AVEC_GEMM_CONV_DGRAD:
+        AVEC_CHECK_ARG(a->K == taps * p.g.Co && a->N == p.g.C);
+        p.a_kind = OP_CONV_DGRAD; p.a_ld = p.g.Co;
+        p.b_kind = OP_PLAIN_K; p.b_ld = a->K;
+        p.cpb = p.g.Co / 64; p.num_kb = taps * p.cpb;
+        break;
+    case AVEC_GEMM_CONV_WGRAD:
+        AVEC_CHECK_ARG(a->M == p.g.Co && a->N == taps * p.g.C);
+        p.a_kind = OP_PLAIN_MN; p.a_ld = p.g.Co;
+        p.b_kind = OP_CONV_WGRAD_X; p.b_ld = p.g.C;
+        p.cpb = p.g.C / 64; p.num_kb = cdiv(a->K, BKE);
+        break;
+    default: return AVEC_ERR_INVALID;
+    }
+    p.a_align = ptr_align(p.A, p.a_ld);
+    p.b_align = ptr_align(p.B, p.b_ld);
+    p.BN = pick_bn(a->N);
+    if (p.b_kind == OP_CONV_WGRAD_X) p.BN = a->N >= 256 ? 256 : (a->N >= 192 ? 192 : (a->N >= 128 ? 128 : 64));
+    int split = (a->epi == AVEC_EPI_ACCUM && a->split_k > 1) ? a->split_k : 1;
+    if (split > p.num_kb) split = p.num_kb;
+    p.kb_per_split = cdiv(p.num_kb, split);
+    split = cdiv(p.num_kb, p.kb_per_split);
+    const int b_rows = (p.b_kind == OP_PLAIN_K) ? p.BN : cdiv(p.BN, 64) * 64;
+    const int stage_bytes = BM * 128 + cdiv(b_rows * 128, 1024) * 1024;
+    p.stages = stage_bytes <= 32 * 1024 ? 3 : (stage_bytes <= 40 * 1024 ? 4 : 4);
+    if (p.stages > p.kb_per_split) p.stages = p.kb_per_split < 2 ? 2 : p.kb_per_split;
+    size_t smem = (size_t)p.stages * stage_bytes + 256 + BM * sizeof(RowInfo) + 1024;
+    if (smem > 227 * 1024) return AVEC_ERR_UNSUPPORTED;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return AVEC_ERR_LAUNCH;
+        attr_set = true;
+    }
+    dim3 grid(cdiv(a->M, BM), cdiv(a->N, p.BN), split);
+    if (grid.y > 65535u || grid.z > 65535u) return AVEC_ERR_INVALID;
+    gemm_tc_kernel<<<grid, TC_THREADS, smem, st>>>(p);
+    AVEC_LAUNCH_CHECK();
+    return AVEC_OK;
+}

@@ -1,0 +1,616 @@
+// LayerNorm (+ patch pooling), BatchNorm (channels-last), softmax, column reductions and the small elementwise glue of
+// the ConformerBlock / ResNet paths.  All of these are HBM-bound: coalesced channel-contiguous accesses, fp32 math,
+// one pass over the data per kernel, per-channel reductions pre-reduced in shared memory before the global atomics.
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------------------------
+// LayerNorm forward: one warp per output token; the row lives in registers (C <= 32*LN_VPT).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int LN_VPT = 16;
+
+template <typename T>
+__global__ void __launch_bounds__(256) layernorm_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, T* __restrict__ y,
+                                                            float* __restrict__ mean, float* __restrict__ rstd, int B,
+                                                            int Tn, int Tp, int C, int P, float eps) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= B * Tp) return;
+    const int b = warp / Tp, tp = warp % Tp;
+    float out[LN_VPT];
+#pragma unroll
+    for (int u = 0; u < LN_VPT; ++u) out[u] = 0.0f;
+    for (int p = 0; p < P; ++p) {
+        int t = tp * P + p;
+        if (t >= Tn) break;
+        const T* xr = x + ((size_t)b * Tn + t) * C;
+        float v[LN_VPT];
+        float s = 0.0f;
+#pragma unroll
+        for (int u = 0; u < LN_VPT; ++u) { int c = lane + u * 32; v[u] = c < C ? ldf(xr + c) : 0.0f; s += v[u]; }
+        s = warp_sum(s);
+        const float mu = s / C;
+        float q = 0.0f;
+#pragma unroll
+        for (int u = 0; u < LN_VPT; ++u) { int c = lane + u * 32; float dv = c < C ? v[u] - mu : 0.0f; q += dv * dv; }
+        q = warp_sum(q);
+        const float rs = rsqrtf(q / C + eps);
+        if (lane == 0) { mean[(size_t)b * Tn + t] = mu; rstd[(size_t)b * Tn + t] = rs; }
+#pragma unroll
+        for (int u = 0; u < LN_VPT; ++u) {
+            int c = lane + u * 32;
+            if (c < C) out[u] += (v[u] - mu) * rs * gamma[c] + beta[c];
+        }
+    }
+    const float invP = 1.0f / P;
+    T* yr = y + ((size_t)b * Tp + tp) * C;
+#pragma unroll
+    for (int u = 0; u < LN_VPT; ++u) { int c = lane + u * 32; if (c < C) stf(yr + c, out[u] * invP); }
+}
+
+// LayerNorm backward: warps stride over input rows; dgamma/dbeta partials live in registers, are reduced across the
+// block's warps in shared memory and then added atomically to the fp32 gradient buffers.
+template <typename T>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                            const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                            const float* __restrict__ rstd, const T* __restrict__ dres,
+                                                            int res_stride, T* __restrict__ dx, float* __restrict__ dgamma,
+                                                            float* __restrict__ dbeta, int B, int Tn, int Tp, int C, int P) {
+    extern __shared__ float red[];  // [2][C]
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const long long rows = (long long)B * Tn;
+    const int Tr = res_stride > 0 ? (Tn - 1) / res_stride + 1 : 0;
+    float dg[LN_VPT], db[LN_VPT];
+#pragma unroll
+    for (int u = 0; u < LN_VPT; ++u) { dg[u] = 0.0f; db[u] = 0.0f; }
+    const float invP = 1.0f / P;
+    for (long long row = (long long)blockIdx.x * wpb + wib; row < rows; row += (long long)gridDim.x * wpb) {
+        const int b = (int)(row / Tn), t = (int)(row % Tn);
+        const T* xr = x + row * C;
+        const T* dyr = dy + ((size_t)b * Tp + t / P) * C;
+        const float mu = mean[row], rs = rstd[row];
+        float g[LN_VPT], xh[LN_VPT];
+        float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+        for (int u = 0; u < LN_VPT; ++u) {
+            int c = lane + u * 32;
+            g[u] = 0.0f; xh[u] = 0.0f;
+            if (c < C) {
+                float d = ldf(dyr + c) * invP;
+                xh[u] = (ldf(xr + c) - mu) * rs;
+                dg[u] += d * xh[u];
+                db[u] += d;
+                g[u] = d * gamma[c];
+                s1 += g[u];
+                s2 += g[u] * xh[u];
+            }
+        }
+        s1 = warp_sum(s1) / C;
+        s2 = warp_sum(s2) / C;
+        const bool has_res = dres != nullptr && (t % res_stride) == 0;
+        const T* rr = has_res ? dres + ((size_t)b * Tr + t / res_stride) * C : nullptr;
+        T* dxr = dx + row * C;
+#pragma unroll
+        for (int u = 0; u < LN_VPT; ++u) {
+            int c = lane + u * 32;
+            if (c < C) {
+                float v = rs * (g[u] - s1 - xh[u] * s2);
+                if (has_res) v += ldf(rr + c);
+                stf(dxr + c, v);
+            }
+        }
+    }
+    for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) red[c] = 0.0f;
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < LN_VPT; ++u) {
+        int c = lane + u * 32;
+        if (c < C) { atomicAdd(&red[c], dg[u]); atomicAdd(&red[C + c], db[u]); }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        if (dgamma) atomicAdd(dgamma + c, red[c]);
+        if (dbeta) atomicAdd(dbeta + c, red[C + c]);
+    }
+}
+
+template <typename T>
+__global__ void upsample_add_kernel(const T* __restrict__ x, const T* __restrict__ o, T* __restrict__ y, int Tn, int Tp, int C,
+                                    int P, long long total) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % C);
+        long long row = i / C;
+        int t = (int)(row % Tn);
+        long long b = row / Tn;
+        stf(y + i, ldf(x + i) + ldf(o + (b * Tp + t / P) * C + c));
+    }
+}
+
+template <typename T>
+__global__ void pool_sum_kernel(const T* __restrict__ dy, T* __restrict__ dout, int Tn, int Tp, int C, int P, long long total) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % C);
+        long long row = i / C;
+        int tp = (int)(row % Tp);
+        long long b = row / Tp;
+        float s = 0.0f;
+        for (int p = 0; p < P; ++p) {
+            int t = tp * P + p;
+            if (t < Tn) s += ldf(dy + (b * Tn + t) * C + c);
+        }
+        stf(dout + i, s);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Row softmax (C <= 32*SM_VPT), warp per row.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int SM_VPT = 16;
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) softmax_fwd_kernel(const TI* __restrict__ x, TO* __restrict__ y, long long rows, int C) {
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    float v[SM_VPT];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int u = 0; u < SM_VPT; ++u) { int c = lane + u * 32; v[u] = c < C ? ldf(x + row * C + c) : -INFINITY; mx = fmaxf(mx, v[u]); }
+    mx = warp_max(mx);
+    float s = 0.0f;
+#pragma unroll
+    for (int u = 0; u < SM_VPT; ++u) { int c = lane + u * 32; v[u] = c < C ? __expf(v[u] - mx) : 0.0f; s += v[u]; }
+    s = warp_sum(s);
+    const float inv = 1.0f / s;
+#pragma unroll
+    for (int u = 0; u < SM_VPT; ++u) { int c = lane + u * 32; if (c < C) stf(y + row * C + c, v[u] * inv); }
+}
+
+template <typename T, typename TO>
+__global__ void __launch_bounds__(256) softmax_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y,
+                                                          const float* __restrict__ dadd, TO* __restrict__ dx, long long rows, int C) {
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    float d[SM_VPT], p[SM_VPT];
+    float s = 0.0f;
+#pragma unroll
+    for (int u = 0; u < SM_VPT; ++u) {
+        int c = lane + u * 32;
+        d[u] = c < C ? ldf(dy + row * C + c) : 0.0f;
+        p[u] = c < C ? ldf(y + row * C + c) : 0.0f;
+        s += d[u] * p[u];
+    }
+    s = warp_sum(s);
+#pragma unroll
+    for (int u = 0; u < SM_VPT; ++u) {
+        int c = lane + u * 32;
+        if (c < C) {
+            float v = p[u] * (d[u] - s);
+            if (dadd) v += dadd[row * C + c];
+            stf(dx + row * C + c, v);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Column reductions over [rows, C] (C contiguous): thread x owns one channel, thread y strides rows.
+// F(row, c) returns up to two values to be summed per channel.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int CR_X = 32, CR_Y = 16;
+
+template <typename F>
+__global__ void __launch_bounds__(CR_X* CR_Y) colreduce_kernel(F f, long long rows, int C, long long rows_per_block,
+                                                               float* __restrict__ out0, float* __restrict__ out1, float alpha) {
+    __shared__ float s0[CR_Y][CR_X + 1];
+    __shared__ float s1[CR_Y][CR_X + 1];
+    const int c = blockIdx.x * CR_X + threadIdx.x;
+    const long long r0 = (long long)blockIdx.y * rows_per_block;
+    const long long r1 = min(rows, r0 + rows_per_block);
+    float a0 = 0.0f, a1 = 0.0f;
+    if (c < C) {
+        for (long long r = r0 + threadIdx.y; r < r1; r += CR_Y) { float v0, v1; f(r, c, v0, v1); a0 += v0; a1 += v1; }
+    }
+    s0[threadIdx.y][threadIdx.x] = a0;
+    s1[threadIdx.y][threadIdx.x] = a1;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+        float t0 = 0.0f, t1 = 0.0f;
+#pragma unroll
+        for (int y = 0; y < CR_Y; ++y) { t0 += s0[y][threadIdx.x]; t1 += s1[y][threadIdx.x]; }
+        atomicAdd(out0 + c, alpha * t0);
+        if (out1) atomicAdd(out1 + c, alpha * t1);
+    }
+}
+
+template <typename F>
+int launch_colreduce(const F& f, long long rows, int C, float* out0, float* out1, float alpha, cudaStream_t st) {
+    int gx = cdiv(C, CR_X);
+    long long want = cdivll(148 * 8, gx);
+    long long nchunk = min(want, cdivll(rows, CR_Y * 4));
+    if (nchunk < 1) nchunk = 1;
+    if (nchunk > 65535) nchunk = 65535;
+    long long rpb = cdivll(rows, nchunk);
+    nchunk = cdivll(rows, rpb);
+    dim3 grid(gx, (unsigned)nchunk), block(CR_X, CR_Y);
+    colreduce_kernel<F><<<grid, block, 0, st>>>(f, rows, C, rpb, out0, out1, alpha);
+    return 0;
+}
+
+template <typename T>
+struct ColsumF {
+    const T* x; long long ldx;
+    __device__ __forceinline__ void operator()(long long r, int c, float& v0, float& v1) const { v0 = ldf(x + r * ldx + c); v1 = 0.0f; }
+};
+template <typename T>
+struct StatsF {
+    const T* x; int C;
+    __device__ __forceinline__ void operator()(long long r, int c, float& v0, float& v1) const { float v = ldf(x + r * C + c); v0 = v; v1 = v * v; }
+};
+
+__device__ __forceinline__ float act_fwd(float z, int act) { return act == AVEC_ACT_RELU ? fmaxf(z, 0.0f) : (act == AVEC_ACT_SWISH ? swishf_(z) : z); }
+__device__ __forceinline__ float act_bwd(float z, int act) { return act == AVEC_ACT_RELU ? (z > 0.0f ? 1.0f : 0.0f) : (act == AVEC_ACT_SWISH ? dswishf_(z) : 1.0f); }
+
+template <typename T>
+struct BnBwdF {
+    const T* dy; const T* u; const T* res; const float* scale; const float* shift; const float* mean; const float* rstd; int C; int act;
+    __device__ __forceinline__ void operator()(long long r, int c, float& v0, float& v1) const {
+        size_t i = (size_t)r * C + c;
+        float uu = ldf(u + i);
+        float z = scale[c] * uu + shift[c];
+        if (res) z += ldf(res + i);
+        float dz = ldf(dy + i) * act_bwd(z, act);
+        v0 = dz;
+        v1 = dz * (uu - mean[c]) * rstd[c];
+    }
+};
+
+__global__ void zero_kernel(float* p, int n) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = 0.0f; }
+
+__global__ void bn_finalize_kernel(const float* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean,
+                                   float* __restrict__ rstd, float* __restrict__ rmean, float* __restrict__ rvar,
+                                   float inv_count, float unbias, int C, float eps, float momentum) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float mu = stats[c] * inv_count;
+    float var = fmaxf(stats[C + c] * inv_count - mu * mu, 0.0f);
+    float rs = rsqrtf(var + eps);
+    float g = gamma ? gamma[c] : 1.0f, b = beta ? beta[c] : 0.0f;
+    scale[c] = g * rs;
+    shift[c] = b - mu * g * rs;
+    if (mean) mean[c] = mu;
+    if (rstd) rstd[c] = rs;
+    if (rmean) rmean[c] = (1.0f - momentum) * rmean[c] + momentum * mu;
+    if (rvar) rvar[c] = (1.0f - momentum) * rvar[c] + momentum * var * unbias;
+}
+
+__global__ void bn_eval_affine_kernel(const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ rmean,
+                                      const float* __restrict__ rvar, float* __restrict__ scale, float* __restrict__ shift, int C, float eps) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float rs = rsqrtf(rvar[c] + eps);
+    float g = gamma ? gamma[c] : 1.0f, b = beta ? beta[c] : 0.0f;
+    scale[c] = g * rs;
+    shift[c] = b - rmean[c] * g * rs;
+}
+
+template <typename T>
+__global__ void bn_apply_kernel(const T* __restrict__ u, const float* __restrict__ scale, const float* __restrict__ shift,
+                                const T* __restrict__ res, T* __restrict__ y, long long total, int C, int act) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % C);
+        float z = scale[c] * ldf(u + i) + shift[c];
+        if (res) z += ldf(res + i);
+        stf(y + i, act_fwd(z, act));
+    }
+}
+
+template <typename T>
+__global__ void bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ u, const float* __restrict__ scale,
+                                    const float* __restrict__ shift, const T* __restrict__ res, const float* __restrict__ mean,
+                                    const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ sums,
+                                    T* __restrict__ du, T* __restrict__ dres, long long total, int C, int act, float inv_count) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % C);
+        float uu = ldf(u + i);
+        float z = scale[c] * uu + shift[c];
+        if (res) z += ldf(res + i);
+        float dz = ldf(dy + i) * act_bwd(z, act);
+        float xh = (uu - mean[c]) * rstd[c];
+        float g = gamma ? gamma[c] : 1.0f;
+        stf(du + i, g * rstd[c] * (dz - sums[c] * inv_count - xh * sums[C + c] * inv_count));
+        if (dres) stf(dres + i, dz);
+    }
+}
+
+// BN + ReLU + MaxPool 3x3 / stride 2 / zero pad 1 (post-ReLU values are >= 0, so the zero padding never wins a strict max)
+template <typename T>
+__global__ void bn_relu_maxpool_fwd_kernel(const T* __restrict__ u, const float* __restrict__ scale, const float* __restrict__ shift,
+                                           T* __restrict__ y, uint8_t* __restrict__ idx, int Hi, int Wi, int C, int Ho, int Wo, long long total) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % C);
+        long long t = i / C;
+        int wo = (int)(t % Wo); t /= Wo;
+        int ho = (int)(t % Ho);
+        long long n = t / Ho;
+        float best = 0.0f;  // the zero padding / ReLU floor
+        int bi = 255;
+        const float sc = scale[c], sh = shift[c];
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+            int hi = ho * 2 + kh - 1;
+            if ((unsigned)hi >= (unsigned)Hi) continue;
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                int wi = wo * 2 + kw - 1;
+                if ((unsigned)wi >= (unsigned)Wi) continue;
+                float z = sc * ldf(u + ((n * Hi + hi) * Wi + wi) * C + c) + sh;
+                if (z > best) { best = z; bi = kh * 3 + kw; }
+            }
+        }
+        stf(y + i, best);
+        idx[i] = (uint8_t)bi;
+    }
+}
+
+// gather-form backward: input site (hi,wi) receives dy of every window whose saved argmax is this site (z > 0 there)
+template <typename T>
+__global__ void bn_relu_maxpool_bwd_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ idx, T* __restrict__ dz, int Hi,
+                                           int Wi, int C, int Ho, int Wo, long long total) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % C);
+        long long t = i / C;
+        int wi = (int)(t % Wi); t /= Wi;
+        int hi = (int)(t % Hi);
+        long long n = t / Hi;
+        float acc = 0.0f;
+        // windows ho with ho*2+kh-1 == hi  ->  kh = hi+1-2*ho in [0,3)
+        for (int kh = 0; kh < 3; ++kh) {
+            int a = hi + 1 - kh;
+            if (a < 0 || (a & 1)) continue;
+            int ho = a >> 1;
+            if (ho >= Ho) continue;
+            for (int kw = 0; kw < 3; ++kw) {
+                int b = wi + 1 - kw;
+                if (b < 0 || (b & 1)) continue;
+                int wo = b >> 1;
+                if (wo >= Wo) continue;
+                size_t o = ((size_t)(n * Ho + ho) * Wo + wo) * C + c;
+                if (idx[o] == kh * 3 + kw) acc += ldf(dy + o);
+            }
+        }
+        stf(dz + i, acc);
+    }
+}
+
+template <typename T>
+__global__ void avgpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int HW, int C, long long total) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % C);
+        long long n = i / C;
+        float s = 0.0f;
+        for (int p = 0; p < HW; ++p) s += ldf(x + (n * HW + p) * C + c);
+        stf(y + i, s / HW);
+    }
+}
+template <typename T>
+__global__ void avgpool_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int HW, int C, long long total) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % C);
+        long long n = i / ((long long)C * HW);
+        stf(dx + i, ldf(dy + n * C + c) / HW);
+    }
+}
+
+template <typename TI, typename TO>
+__global__ void convert_kernel(const TI* __restrict__ src, long long lds, TO* __restrict__ dst, long long ldd, int C, long long total) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % C);
+        long long r = i / C;
+        stf(dst + r * ldd + c, ldf(src + r * lds + c));
+    }
+}
+
+inline int ew_blocks(long long total, int threads = 256) {
+    long long b = cdivll(total, threads);
+    long long cap = 148LL * 16;
+    return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+
+}  // namespace
+
+extern "C" int avec_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int B,
+                                  int T, int C, int P, float eps, int dtype, avec_stream_t stream) {
+    AVEC_CHECK_ARG(x && gamma && beta && y && mean && rstd && B > 0 && T > 0 && P >= 1 && C > 0 && C <= 32 * LN_VPT);
+    const int Tp = cdiv(T, P);
+    const long long warps = (long long)B * Tp;
+    const int blocks = (int)cdivll(warps * 32, 256);
+    AVEC_DISPATCH_DTYPE(dtype, Tt, (layernorm_fwd_kernel<Tt><<<blocks, 256, 0, as_stream(stream)>>>(
+        (const Tt*)x, gamma, beta, (Tt*)y, mean, rstd, B, T, Tp, C, P, eps)));
+    AVEC_LAUNCH_CHECK();
+    return AVEC_OK;
+}
+
+extern "C" int avec_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                                  const void* dres, int res_stride, void* dx, float* dgamma, float* dbeta, int B, int T, int C,
+                                  int P, int dtype, avec_stream_t stream) {
+    AVEC_CHECK_ARG(dy && x && gamma && mean && rstd && dx && B > 0 && T > 0 && P >= 1 && C > 0 && C <= 32 * LN_VPT);
+    AVEC_CHECK_ARG(!dres || res_stride >= 1);
+    const int Tp = cdiv(T, P);
+    const long long rows = (long long)B * T;
+    int blocks = (int)std::min<long long>(cdivll(rows, 8), 148LL * 4);
+    size_t smem = 2 * (size_t)C * sizeof(float);
+    AVEC_DISPATCH_DTYPE(dtype, Tt, (layernorm_bwd_kernel<Tt><<<blocks, 256, smem, as_stream(stream)>>>(
+        (const Tt*)dy, (const Tt*)x, gamma, mean, rstd, (const Tt*)dres, dres ? res_stride : 0, (Tt*)dx, dgamma, dbeta, B, T, Tp, C, P)));
+    AVEC_LAUNCH_CHECK();
+    return AVEC_OK;
+}
+
+extern "C" int avec_upsample_add(const void* x, const void* o, void* y, int B, int T, int Tp, int C, int P, int dtype,
+                                 avec_stream_t stream) {
+    AVEC_CHECK_ARG(x && o && y && B > 0 && T > 0 && P >= 1 && Tp == cdiv(T, P));
+    long long total = (long long)B * T * C;
+    AVEC_DISPATCH_DTYPE(dtype, Tt, (upsample_add_kernel<Tt><<<ew_blocks(total), 256, 0, as_stream(stream)>>>(
+        (const Tt*)x, (const Tt*)o, (Tt*)y, T, Tp, C, P, total)));
+    AVEC_LAUNCH_CHECK();
+    return AVEC_OK;
+}
+
+extern "C" int avec_pool_sum(const void* dy, void* dout, int B, int T, int Tp, int C, int P, int dtype, avec_stream_t stream) {
+    AVEC_CHECK_ARG(dy && dout && B > 0 && T > 0 && P >= 1 && Tp == cdiv(T, P));
+    long long total = (long long)B * Tp * C;
+    AVEC_DISPATCH_DTYPE(dtype, Tt, (pool_sum_kernel<Tt><<<ew_blocks(total), 256, 0, as_stream(stream)>>>(
+        (const Tt*)dy, (Tt*)dout, T, Tp, C, P, total)));
+    AVEC_LAUNCH_CHECK();
+    return AVEC_OK;
+}
+
+extern "C" int avec_softmax_fwd(const void* x, int x_dtype, void* y, int y_dtype, long long rows, int C, avec_stream_t stream) {
+    AVEC_CHECK_ARG(x && y && rows > 0 && C > 0 && C <= 32 * SM_VPT);
+    const int blocks = (int)cdivll(rows * 32, 256);
+    cudaStream_t st = as_stream(stream);
+    if (x_dtype == AVEC_F32 && y_dtype == AVEC_F32) softmax_fwd_kernel<float, float><<<blocks, 256, 0, st>>>((const float*)x, (float*)y, rows, C);
+    else if (x_dtype == AVEC_F32 && y_dtype == AVEC_BF16) softmax_fwd_kernel<float, bf16><<<blocks, 256, 0, st>>>((const float*)x, (bf16*)y, rows, C);
+    else if (x_dtype == AVEC_BF16 && y_dtype == AVEC_BF16) softmax_fwd_kernel<bf16, bf16><<<blocks, 256, 0, st>>>((const bf16*)x, (bf16*)y, rows, C);
+    else if (x_dtype == AVEC_BF16 && y_dtype == AVEC_F32) softmax_fwd_kernel<bf16, float><<<blocks, 256, 0, st>>>((const bf16*)x, (float*)y, rows, C);
+    else return AVEC_ERR_INVALID;
+    AVEC_LAUNCH_CHECK();
+    return AVEC_OK;
+}
+
+extern "C" int avec_softmax_bwd(const void* dy, const void* y, int dtype, const float* dadd, void* dx, int dx_dtype, long long rows,
+                                int C, avec_stream_t stream) {
+    AVEC_CHECK_ARG(dy && y && dx && rows > 0 && C > 0 && C <= 32 * SM_VPT);
+    const int blocks = (int)cdivll(rows * 32, 256);
+    cudaStream_t st = as_stream(stream);
+    if (dtype == AVEC_F32 && dx_dtype == AVEC_F32) softmax_bwd_kernel<float, float><<<blocks, 256, 0, st>>>((const float*)dy, (const float*)y, dadd, (float*)dx, rows, C);
+    else if (dtype == AVEC_BF16 && dx_dtype == AVEC_BF16) softmax_bwd_kernel<bf16, bf16><<<blocks, 256, 0, st>>>((const bf16*)dy, (const bf16*)y, dadd, (bf16*)dx, rows, C);
+    else if (dtype == AVEC_BF16 && dx_dtype == AVEC_F32) softmax_bwd_kernel<bf16, float><<<blocks, 256, 0, st>>>((const bf16*)dy, (const bf16*)y, dadd, (float*)dx, rows, C);
+    else if (dtype == AVEC_F32 && dx_dtype == AVEC_BF16) softmax_bwd_kernel<float, bf16><<<blocks, 256, 0, st>>>((const float*)dy, (const float*)y, dadd, (bf16*)dx, rows, C);
+    else return AVEC_ERR_INVALID;
+    AVEC_LAUNCH_CHECK();
+    return AVEC_OK;
+}
+
+extern "C" int avec_colsum(const void* x, int dtype, long long rows, int C, long long ldx, float alpha, float* out, int accumulate,
+                           avec_stream_t stream) {
+    AVEC_CHECK_ARG(x && out && rows > 0 && C > 0 && ldx >= C);
+    cudaStream_t st = as_stream(stream);
+    if (!accumulate) { zero_kernel<<<cdiv(C, 256), 256, 0, st>>>(out, C); avec_count_launch(); }
+    AVEC_DISPATCH_DTYPE(dtype, Tt, { ColsumF<Tt> f{(const Tt*)x, ldx}; launch_colreduce(f, rows, C, out, nullptr, alpha, st); });
+    AVEC_LAUNCH_CHECK();
+    return AVEC_OK;
+}
+
+extern "C" int avec_bn_stats(const void* u, int dtype, long long rows, int C, float* stats, avec_stream_t stream) {
+    AVEC_CHECK_ARG(u && stats && rows > 0 && C > 0);
+    cudaStream_t st = as_stream(stream);
+    AVEC_DISPATCH_DTYPE(dtype, Tt, { StatsF<Tt> f{(const Tt*)u, C}; launch_colreduce(f, rows, C, stats, stats + C, 1.0f, st); });
+    AVEC_LAUNCH_CHECK();
+    return AVEC_OK;
+}
+
+extern "C" int avec_bn_finalize(const float* stats, const float* gamma, const float* beta, float* scale, float* shift, float* mean,
+                                float* rstd, float* running_mean, float* running_var, long long count, int C, float eps,
+                                float momentum, avec_stream_t stream) {
+    AVEC_CHECK_ARG(stats && scale && shift && count > 0 && C > 0);
+    float unbias = count > 1 ? (float)((double)count / (double)(count - 1)) : 1.0f;
+    bn_finalize_kernel<<<cdiv(C, 128), 128, 0, as_stream(stream)>>>(stats, gamma, beta, scale, shift, mean, rstd, running_mean,
+                                                                   running_var, (float)(1.0 / (double)count), unbias, C, eps, momentum);
+    AVEC_LAUNCH_CHECK();
+    return AVEC_OK;
+}
+
+extern "C" int avec_bn_eval_affine(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                                   float* scale, float* shift, int C, float eps, avec_stream_t stream) {
+    AVEC_CHECK_ARG(running_mean && running_var && scale && shift && C > 0);
+    bn_eval_affine_kernel<<<cdiv(C, 128), 128, 0, as_stream(stream)>>>(gamma, beta, running_mean, running_var, scale, shift, C, eps);
+    AVEC_LAUNCH_CHECK();
+    return AVEC_OK;
+}
+
+extern "C" int avec_bn_apply(const void* u, const float* scale, const float* shift, const void* res, void* y, long long rows, int C,
+                             int act, int dtype, avec_stream_t stream) {
+    AVEC_CHECK_ARG(u && scale && shift && y && rows > 0 && C > 0);
+    long long total = rows * C;
+    AVEC_DISPATCH_DTYPE(dtype, Tt, (bn_apply_kernel<Tt><<<ew_blocks(total), 256, 0, as_stream(stream)>>>(
+        (const Tt*)u, scale, shift, (const Tt*)res, (Tt*)y, total, C, act)));
+    AVEC_LAUNCH_CHECK();
+    return AVEC_OK;
+}
+
+extern "C" int avec_bn_bwd_reduce(const void* dy, const void* u, const float* scale, const float* shift, const void* res,
+                                  const float* mean, const float* rstd, float* sums, long long rows, int C, int act, int dtype,
+                                  avec_stream_t stream) {
+    AVEC_CHECK_ARG(dy && u && scale && shift && mean && rstd && sums && rows > 0 && C > 0);
+    cudaStream_t st = as_stream(stream);
+    AVEC_DISPATCH_DTYPE(dtype, Tt, {
+        BnBwdF<Tt> f{(const Tt*)dy, (const Tt*)u, (const Tt*)res, scale, shift, mean, rstd, C, act};
+        launch_colreduce(f, rows, C, sums, sums + C, 1.0f, st);
+    });
+    AVEC_LAUNCH_CHECK();
+    return AVEC_OK;
+}
+
+extern "C" int avec_bn_bwd_apply(const void* dy, const void* u, const float* scale, const float* shift, const void* res,
+                                 const float* mean, const float* rstd, const float* gamma, const float* sums, void* du, void* dres,
+                                 long long rows, int C, int act, int dtype, avec_stream_t stream) {
+    AVEC_CHECK_ARG(dy && u && scale && shift && mean && rstd && sums && du && rows > 0 && C > 0);
+    long long total = rows * C;
+    AVEC_DISPATCH_DTYPE(dtype, Tt, (bn_bwd_apply_kernel<Tt><<<ew_blocks(total), 256, 0, as_stream(stream)>>>(
+        (const Tt*)dy, (const Tt*)u, scale, shift, (const Tt*)res, mean, rstd, gamma, sums, (Tt*)du, (Tt*)dres, total, C, act,
+        (float)(1.0 / (double)rows))));
+    AVEC_LAUNCH_CHECK();
+    return AVEC_OK;
+}
+
+extern "C" int avec_bn_relu_maxpool_fwd(const void* u, const float* scale, const float* shift, void* y, uint8_t* idx, int N, int Hi,
+                                        int Wi, int C, int Ho, int Wo, int dtype, avec_stream_t stream) {
+    AVEC_CHECK_ARG(u && scale && shift && y && idx && N > 0 && Ho == (Hi - 1) / 2 + 1 && Wo == (Wi - 1) / 2 + 1);
+    long long total = (long long)N * Ho * Wo * C;
+    AVEC_DISPATCH_DTYPE(dtype, Tt, (bn_relu_maxpool_fwd_kernel<Tt><<<ew_blocks(total), 256, 0, as_stream(stream)>>>(
+        (const Tt*)u, scale, shift, (Tt*)y, idx, Hi, Wi, C, Ho, Wo, total)));
+    AVEC_LAUNCH_CHECK();
+    return AVEC_OK;
+}
+
+extern "C" int avec_bn_relu_maxpool_bwd(const void* dy, const uint8_t* idx, void* dz, int N, int Hi, int Wi, int C, int Ho, int Wo,
+                                        int dtype, avec_stream_t stream) {
+    AVEC_CHECK_ARG(dy && idx && dz && N > 0);
+    long long total = (long long)N * Hi * Wi * C;
+    AVEC_DISPATCH_DTYPE(dtype, Tt, (bn_relu_maxpool_bwd_kernel<Tt><<<ew_blocks(total), 256, 0, as_stream(stream)>>>(
+        (const Tt*)dy, idx, (Tt*)dz, Hi, Wi, C, Ho, Wo, total)));
+    AVEC_LAUNCH_CHECK();
+    return AVEC_OK;
+}
+
+extern "C" int avec_avgpool_fwd(const void* x, void* y, int N, int HW, int C, int dtype, avec_stream_t stream) {
+    AVEC_CHECK_ARG(x && y && N > 0 && HW > 0 && C > 0);
+    long long total = (long long)N * C;
+    AVEC_DISPATCH_DTYPE(dtype, Tt, (avgpool_fwd_kernel<Tt><<<ew_blocks(total), 256, 0, as_stream(stream)>>>((const Tt*)x, (Tt*)y, HW, C, total)));
+    AVEC_LAUNCH_CHECK();
+    return AVEC_OK;
+}
+extern "C" int avec_avgpool_bwd(const void* dy, void* dx, int N, int HW, int C, int dtype, avec_stream_t stream) {
+    AVEC_CHECK_ARG(dy && dx && N > 0 && HW > 0 && C > 0);
+    long long total = (long long)N * HW * C;
+    AVEC_DISPATCH_DTYPE(dtype, Tt, (avgpool_bwd_kernel<Tt><<<ew_blocks(total), 256, 0, as_stream(stream)>>>((const Tt*)dy, (Tt*)dx, HW, C, total)));
+    AVEC_LAUNCH_CHECK();
+    return AVEC_OK;
+}
+
+extern "C" int avec_convert(const void* src, int src_dtype, long long lds, void* dst, int dst_dtype, long long ldd, long long rows,
+                            int C, avec_stream_t stream) {
+    AVEC_CHECK_ARG(src && dst && rows > 0 && C > 0);
+    long long total = rows * C;
+    cudaStream_t st = as_stream(stream);
+    int blocks = ew_blocks(total);
+    if (src_dtype == AVEC_F32 && dst_dtype == AVEC_BF16) convert_kernel<float, bf16><<<blocks, 256, 0, st>>>((const float*)src, lds, (bf16*)dst, ldd, C, total);
+    else if (src_dtype == AVEC_BF16 && dst_dtype == AVEC_F32) convert_kernel<bf16, float><<<blocks, 256, 0, st>>>((const bf16*)src, lds, (float*)dst, ldd, C, total);
+    else if (src_dtype == AVEC_F32 && dst_dtype == AVEC_F32) convert_kernel<float, float><<<blocks, 256, 0, st>>>((const float*)src, lds, (float*)dst, ldd, C, total);
+    else if (src_dtype == AVEC_BF16 && dst_dtype == AVEC_BF16) convert_kernel<bf16, bf16><<<blocks, 256, 0, st>>>((const bf16*)src, lds, (bf16*)dst, ldd, C, total);
+    else return AVEC_ERR_INVALID;
+    AVEC_LAUNCH_CHECK();
+    return AVEC_OK;
+}

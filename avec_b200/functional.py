@@ -1,0 +1,488 @@
+"""Module-level autograd Functions of the hot path.  Each Function is one reference nn.Module.forward with a
+hand-written backward; every arithmetic step is a kernel of libavec_b200.so (ops.py) - PyTorch only owns the tensors.
+
+Reference modules mirrored (file:line in /root/reference):
+  FFNFn        FeedForwardModule + the half-step residual      nnet/modules.py:257-289, nnet/blocks.py:292,301
+  AttentionFn  AttentionModule + RelPos(Patch)1dMultiHeadAttention  nnet/modules.py:291-339, nnet/attentions.py:215-382
+  ConvModuleFn ConvolutionModule + conv_res                     nnet/modules.py:341-385, nnet/blocks.py:273-298
+  LayerNormFn  block norm                                        nnet/blocks.py:267,304
+  InterCTCFn   InterCTCResModule                                 nnet/modules.py:387-400
+  LinearFn / MLPFn  layers.Linear, FusionModule                  nnet/layers.py:29-76, nnet/modules.py:402-426
+  AudioStemFn  AudioPreprocessing + Conv2d/BN2d/Swish stem       nnet/preprocessing.py:57-85, nnet/networks.py:359-368
+  VideoStemFn  Conv3d/BN3d/ReLU + MaxPool3d                      nnet/networks.py:459-471
+  ResBlockFn   ResNetBlock                                       nnet/blocks.py:29-91
+  AvgPoolFn    GlobalAvgPool2d                                   nnet/networks.py:129-132
+"""
+import torch
+from torch.autograd import Function
+
+from . import _lib as L
+from . import ops
+
+# ------------------------------------------------------------------------------------------------------------- config
+_COMPUTE_DTYPE = torch.bfloat16
+
+
+def set_compute_dtype(dt):
+    """torch.bfloat16 (production: tcgen05 tensor cores) or torch.float32 (parity mode: exact fp32 accumulation)."""
+    global _COMPUTE_DTYPE
+    assert dt in (torch.bfloat16, torch.float32)
+    _COMPUTE_DTYPE = dt
+    new_step()
+
+
+def compute_dtype():
+    return _COMPUTE_DTYPE
+
+
+# weight cache: compute-dtype, kernel-layout copies of the fp32 master parameters, valid for one forward+backward
+_wcache = {}
+
+
+def new_step():
+    _wcache.clear()
+
+
+def wc(param, tag="plain", fn=None):
+    """compute-dtype copy of a parameter in the layout a kernel wants (fn: fp32 tensor -> 2-d fp32 view/tensor)."""
+    key = (id(param), tag, _COMPUTE_DTYPE)
+    hit = _wcache.get(key)
+    if hit is not None and hit[0] == param._version:
+        return hit[1]
+    src = param.detach()
+    src = fn(src) if fn is not None else src.reshape(src.shape[0], -1)
+    out = ops.convert(src, _COMPUTE_DTYPE)
+    _wcache[key] = (param._version, out)
+    return out
+
+
+def wc_cat(params, tag):
+    key = (tuple(id(p) for p in params), tag, _COMPUTE_DTYPE)
+    ver = tuple(p._version for p in params)
+    hit = _wcache.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    src = torch.cat([p.detach().reshape(p.shape[0], -1) for p in params], dim=0)
+    out = ops.convert(src, _COMPUTE_DTYPE) if src.dim() == 2 and src.shape[1] > 1 else src
+    _wcache[key] = (ver, out)
+    return out
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# --------------------------------------------------------------------------------------------------------------- FFN
+class FFNFn(Function):
+    """y = x + 0.5 * (W2 swish(W1 LN(x) + b1) + b2)"""
+
+    @staticmethod
+    def forward(ctx, x, ln_w, ln_b, w1, b1, w2, b2):
+        B, T, D = x.shape
+        x = _c(x)
+        xn, mean, rstd = ops.layernorm_fwd(x, ln_w, ln_b)
+        h, pre = ops.linear_fwd(xn.view(B * T, D), wc(w1), b1, L.EPI_SWISH, want_pre=True)
+        y = ops.linear_fwd(h, wc(w2), b2, L.EPI_RESIDUAL, alpha=0.5, aux=x.view(B * T, D))
+        ctx.save_for_backward(x, ln_w, mean, rstd, xn, pre, h, w1, w2)
+        return y.view(B, T, D)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, ln_w, mean, rstd, xn, pre, h, w1, w2 = ctx.saved_tensors
+        B, T, D = x.shape
+        dy = _c(dy)
+        dy2 = dy.view(B * T, D)
+        dpre = ops.linear_dgrad(dy2, wc(w2), L.EPI_DSWISH, alpha=0.5, aux=pre)
+        dw2 = ops.linear_wgrad(dy2, h, alpha=0.5)
+        db2 = ops.colsum(dy2, 0.5)
+        dxn = ops.linear_dgrad(dpre, wc(w1))
+        dw1 = ops.linear_wgrad(dpre, xn.view(B * T, D))
+        db1 = ops.colsum(dpre)
+        dx, dg, db = ops.layernorm_bwd(dxn.view(B, T, D), x, ln_w, mean, rstd, dres=dy, res_stride=1)
+        return dx, dg, db, dw1, db1, dw2, db2
+
+
+# --------------------------------------------------------------------------------------------------------- attention
+class AttentionFn(Function):
+    """y = x + upsample_P( Wo attn( pool_P(LN(x)) ) + bo )   with relative-position scores (P = 1: regular RelPos1d)."""
+
+    @staticmethod
+    def forward(ctx, x, ln_w, ln_b, wq, bq, wk, bk, wv, bv, wo, bo, wp, bp, pe, klen, H, P):
+        B, T, D = x.shape
+        d = D // H
+        x = _c(x)
+        xp, mean, rstd = ops.layernorm_fwd(x, ln_w, ln_b, P=P)
+        Tp = xp.shape[1]
+        wqkv = wc_cat((wq, wk, wv), "qkv")
+        bqkv = wc_cat((bq, bk, bv), "bqkv").reshape(-1)
+        qkv = ops.linear_fwd(xp.view(B * Tp, D), wqkv, bqkv)
+        e = ops.linear_fwd(pe, wc(wp), bp)
+        if P > 1:
+            klen_p = torch.div(klen, P, rounding_mode="floor").to(torch.int32) if klen is not None else None
+            qlen = T // P
+        else:
+            klen_p, qlen = klen, Tp
+        o, probs = ops.relpos_attn_fwd(qkv, e, klen_p, qlen, B, Tp, H, d)
+        if P == 1:
+            y = ops.linear_fwd(o, wc(wo), bo, L.EPI_RESIDUAL, aux=x.view(B * T, D)).view(B, T, D)
+        else:
+            proj = ops.linear_fwd(o, wc(wo), bo)
+            y = ops.upsample_add(x, proj.view(B, Tp, D), P)
+        ctx.save_for_backward(x, ln_w, mean, rstd, xp, qkv, e, probs, o, pe, wq, wk, wv, wo, wp)
+        ctx.H, ctx.P = H, P
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, ln_w, mean, rstd, xp, qkv, e, probs, o, pe, wq, wk, wv, wo, wp = ctx.saved_tensors
+        H, P = ctx.H, ctx.P
+        B, T, D = x.shape
+        Tp = xp.shape[1]
+        d = D // H
+        dy = _c(dy)
+        dproj = dy.view(B * T, D) if P == 1 else ops.pool_sum(dy, P).view(B * Tp, D)
+        do = ops.linear_dgrad(dproj, wc(wo))
+        dwo = ops.linear_wgrad(dproj, o)
+        dbo = ops.colsum(dproj)
+        dqkv, de = ops.relpos_attn_bwd(do, qkv, e, probs, B, Tp, H, d)
+        dwp = ops.linear_wgrad(ops.convert(de, x.dtype), pe)
+        dbp = ops.colsum(de)
+        wqkv = wc_cat((wq, wk, wv), "qkv")
+        dxp = ops.linear_dgrad(dqkv, wqkv)
+        dwqkv = ops.linear_wgrad(dqkv, xp.view(B * Tp, D))
+        dbqkv = ops.colsum(dqkv)
+        dx, dg, db = ops.layernorm_bwd(dxp.view(B, Tp, D), x, ln_w, mean, rstd, P=P, dres=dy, res_stride=1)
+        return (dx, dg, db, dwqkv[:D], dbqkv[:D], dwqkv[D:2 * D], dbqkv[D:2 * D], dwqkv[2 * D:], dbqkv[2 * D:], dwo, dbo,
+                dwp, dbp, None, None, None, None)
+
+
+# ------------------------------------------------------------------------------------------------------- conv module
+class ConvModuleFn(Function):
+    """y = res(x) + W3 swish(BN(dwconv_k15,s(GLU(W1 LN(x) + b1)))) + b3,  res = identity | Conv1d(k=1, stride s)"""
+
+    @staticmethod
+    def forward(ctx, x, ln_w, ln_b, w1, b1, wd, bd, bn_w, bn_b, rm, rv, w3, b3, wr, br, stride, training, momentum):
+        B, T, D = x.shape
+        De = w3.shape[0]
+        ks = wd.shape[-1]
+        x = _c(x)
+        xn, mean, rstd = ops.layernorm_fwd(x, ln_w, ln_b)
+        pre = ops.linear_fwd(xn.view(B * T, D), wc(w1), b1).view(B, T, 2 * De)
+        wdw = wd.detach().reshape(De, ks)
+        u, stats = ops.glu_dwconv_fwd(pre, wdw, bd, stride, ks, want_stats=training)
+        To = u.shape[1]
+        u2 = u.view(B * To, De)
+        if training:
+            bnbuf = ops.bn_finalize(stats, bn_w, bn_b, B * To, rm, rv, 1e-5, momentum)
+        else:
+            bnbuf = ops.bn_eval_affine(bn_w, bn_b, rm, rv, 1e-5)
+        v = ops.bn_apply(u2, bnbuf[0], bnbuf[1], L.ACT_SWISH)
+        if wr is None:
+            xs = None
+            aux = x.view(B * T, D)
+        else:
+            xs = _c(x[:, ::stride]).view(B * To, D) if stride > 1 else x.view(B * T, D)
+            aux = ops.linear_fwd(xs, wc(wr), br)
+        y = ops.linear_fwd(v, wc(w3), b3, L.EPI_RESIDUAL, aux=aux).view(B, To, De)
+        ctx.save_for_backward(x, ln_w, mean, rstd, xn, pre, u, bnbuf, v, xs, w1, wd, bn_w, w3, wr)
+        ctx.stride, ctx.training = stride, training
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, ln_w, mean, rstd, xn, pre, u, bnbuf, v, xs, w1, wd, bn_w, w3, wr = ctx.saved_tensors
+        if not ctx.training:
+            raise RuntimeError("avec_b200: ConvModule backward needs training-mode BatchNorm statistics")
+        stride = ctx.stride
+        B, T, D = x.shape
+        To, De = u.shape[1], u.shape[2]
+        ks = wd.shape[-1]
+        dy = _c(dy)
+        dy2 = dy.view(B * To, De)
+        dv = ops.linear_dgrad(dy2, wc(w3))
+        dw3 = ops.linear_wgrad(dy2, v)
+        db3 = ops.colsum(dy2)
+        du, _, dgamma, dbeta = ops.bn_bwd(dv, u.view(B * To, De), bnbuf, bn_w, L.ACT_SWISH)
+        dpre, dwd, dbd = ops.glu_dwconv_bwd(du.view(B, To, De), pre, wd.detach().reshape(De, ks), stride, ks)
+        dpre2 = dpre.view(B * T, 2 * De)
+        dxn = ops.linear_dgrad(dpre2, wc(w1))
+        dw1 = ops.linear_wgrad(dpre2, xn.view(B * T, D))
+        db1 = ops.colsum(dpre2)
+        if wr is None:
+            dres, dwr, dbr = dy, None, None
+        else:
+            dres = ops.linear_dgrad(dy2, wc(wr)).view(B, To, D)
+            dwr = ops.linear_wgrad(dy2, xs).view(wr.shape)
+            dbr = db3.clone()
+        dx, dg, db = ops.layernorm_bwd(dxn.view(B, T, D), x, ln_w, mean, rstd, dres=dres, res_stride=stride)
+        return (dx, dg, db, dw1.view(w1.shape), db1, dwd.view(wd.shape), dbd, dgamma, dbeta, None, None, dw3.view(w3.shape), db3,
+                dwr, dbr, None, None, None)
+
+
+class LayerNormFn(Function):
+    @staticmethod
+    def forward(ctx, x, w, b):
+        x = _c(x)
+        y, mean, rstd = ops.layernorm_fwd(x, w, b)
+        ctx.save_for_backward(x, w, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w, mean, rstd = ctx.saved_tensors
+        dx, dg, db = ops.layernorm_bwd(_c(dy), x, w, mean, rstd)
+        return dx, dg, db
+
+
+# ----------------------------------------------------------------------------------------------------------- InterCTC
+class InterCTCFn(Function):
+    """logits = W1 x + b1 (fp32);  y = x + W2 softmax(logits) + b2"""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2):
+        B, T, D = x.shape
+        x = _c(x)
+        x2 = x.view(B * T, D)
+        logits = ops.linear_fwd(x2, wc(w1), b1, out_dtype=torch.float32)
+        p = ops.softmax_fwd(logits, x.dtype)
+        y = ops.linear_fwd(p, wc(w2), b2, L.EPI_RESIDUAL, aux=x2)
+        ctx.save_for_backward(x, p, w1, w2)
+        return y.view(B, T, D), logits.view(B, T, -1)
+
+    @staticmethod
+    def backward(ctx, dy, dlogits):
+        x, p, w1, w2 = ctx.saved_tensors
+        B, T, D = x.shape
+        x2 = x.view(B * T, D)
+        dy2 = _c(dy).view(B * T, D)
+        dp = ops.linear_dgrad(dy2, wc(w2))
+        dw2 = ops.linear_wgrad(dy2, p)
+        db2 = ops.colsum(dy2)
+        dadd = _c(dlogits.float()).view(B * T, -1) if dlogits is not None else None
+        dl = ops.softmax_bwd(dp, p, dadd, out_dtype=x.dtype)
+        dx = ops.linear_dgrad(dl, wc(w1), L.EPI_RESIDUAL, aux=dy2)
+        dw1 = ops.linear_wgrad(dl, x2)
+        db1 = ops.colsum(dl)
+        return dx.view(B, T, D), dw1, db1, dw2, db2
+
+
+# ------------------------------------------------------------------------------------------------------------- Linear
+class LinearFn(Function):
+    """y = x W^T + b on the last dim.  wl = optional (tag, to_kernel_layout, grad_to_param_layout) for permuted weights."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, out_fp32, wl):
+        shp = x.shape
+        x2 = _c(x).view(-1, shp[-1])
+        wk = wc(w, wl[0], wl[1]) if wl is not None else wc(w)
+        y = ops.linear_fwd(x2, wk, b, out_dtype=torch.float32 if out_fp32 else None)
+        ctx.save_for_backward(x2, w)
+        ctx.shp, ctx.wl, ctx.has_b = shp, wl, b is not None
+        return y.view(*shp[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w = ctx.saved_tensors
+        wl = ctx.wl
+        wk = wc(w, wl[0], wl[1]) if wl is not None else wc(w)
+        dy2 = _c(dy).view(-1, w.shape[0])
+        if dy2.dtype != x2.dtype:
+            dy2 = ops.convert(dy2, x2.dtype)
+        dx = ops.linear_dgrad(dy2, wk).view(ctx.shp)
+        dw = ops.linear_wgrad(dy2, x2)
+        if wl is not None:
+            dw = wl[2](dw)
+        db = ops.colsum(dy2) if ctx.has_b else None
+        return dx, dw.view(w.shape), db, None, None
+
+
+class MLPFn(Function):
+    """y = W2 swish(W1 x + b1) + b2   (FusionModule body)"""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2):
+        shp = x.shape
+        x2 = _c(x).view(-1, shp[-1])
+        h, pre = ops.linear_fwd(x2, wc(w1), b1, L.EPI_SWISH, want_pre=True)
+        y = ops.linear_fwd(h, wc(w2), b2)
+        ctx.save_for_backward(x2, pre, h, w1, w2)
+        ctx.shp = shp
+        return y.view(*shp[:-1], w2.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, pre, h, w1, w2 = ctx.saved_tensors
+        dy2 = _c(dy).view(-1, w2.shape[0])
+        dpre = ops.linear_dgrad(dy2, wc(w2), L.EPI_DSWISH, alpha=1.0, aux=pre)
+        dw2 = ops.linear_wgrad(dy2, h)
+        db2 = ops.colsum(dy2)
+        dx = ops.linear_dgrad(dpre, wc(w1)).view(ctx.shp)
+        dw1 = ops.linear_wgrad(dpre, x2)
+        db1 = ops.colsum(dpre)
+        return dx, dw1, db1, dw2, db2
+
+
+# --------------------------------------------------------------------------------------------------------- front-ends
+def _bn_buf(stats, w, b, rm, rv, count, training, momentum):
+    if training:
+        return ops.bn_finalize(stats, w, b, count, rm, rv, 1e-5, momentum)
+    return ops.bn_eval_affine(w, b, rm, rv, 1e-5)
+
+
+class AudioStemFn(Function):
+    """wave [B,L] -> log-mel [B,F,80] -> Conv2d(1->C, k3, s2, same) + BN2d + Swish -> [B, F', 40*C] (feature = f*C + c)"""
+
+    @staticmethod
+    def forward(ctx, wave, fb, cw, cb, bn_w, bn_b, rm, rv, training, momentum):
+        B = wave.shape[0]
+        mel = ops.stft_mel_log(_c(wave.float()), fb, layout=0)
+        F = mel.shape[1]
+        melc = ops.convert(mel, compute_dtype())
+        Co = cw.shape[0]
+        g = ops.make_geom(B, 1, F, 80, 1, Co, (1, 3, 3), (1, 2, 2), (0, 1, 1))
+        wp = wc(cw, "stem2d", lambda w: w[:, 0].transpose(1, 2).reshape(w.shape[0], 9))
+        sites = ops.geom_sites(g)
+        stats = torch.zeros((2 * Co,), device=wave.device, dtype=torch.float32) if training else None
+        u = ops.conv_fwd(melc, wp, g, bias=cb, colstats=stats)
+        bnbuf = _bn_buf(stats, bn_w, bn_b, rm, rv, sites, training, momentum)
+        v = ops.bn_apply(u, bnbuf[0], bnbuf[1], L.ACT_SWISH)
+        ctx.save_for_backward(melc, u, bnbuf, bn_w, cw)
+        ctx.g, ctx.training = g, training
+        return v.view(B, g.Ho, g.Wo * Co)
+
+    @staticmethod
+    def backward(ctx, dv):
+        melc, u, bnbuf, bn_w, cw = ctx.saved_tensors
+        if not ctx.training:
+            raise RuntimeError("avec_b200: stem backward needs training-mode BatchNorm statistics")
+        g = ctx.g
+        Co = cw.shape[0]
+        dv2 = _c(dv).view(-1, Co)
+        du, _, dgamma, dbeta = ops.bn_bwd(dv2, u, bnbuf, bn_w, L.ACT_SWISH)
+        dwp = ops.conv_wgrad(du, melc, g)
+        dcw = dwp.view(Co, 3, 3).transpose(1, 2).reshape(cw.shape)
+        dcb = ops.colsum(du)
+        return None, None, dcw, dcb, dgamma, dbeta, None, None, None, None
+
+
+class VideoStemFn(Function):
+    """video [B,T,H,W,1] -> Conv3d(1->64,(5,7,7),s(1,2,2),same)+BN3d+ReLU -> MaxPool3d((1,3,3),s(1,2,2),same) -> [B*T,H/4,W/4,64]"""
+
+    @staticmethod
+    def forward(ctx, video, cw, cb, bn_w, bn_b, rm, rv, training, momentum):
+        B, T, H, W = video.shape[0], video.shape[1], video.shape[2], video.shape[3]
+        xc = ops.convert(_c(video.float()).view(B * T * H, W), compute_dtype()).view(B, T, H, W, 1)
+        Co = cw.shape[0]
+        kt, kh, kw = cw.shape[2], cw.shape[3], cw.shape[4]
+        g = ops.make_geom(B, T, H, W, 1, Co, (kt, kh, kw), (1, 2, 2), ((kt - 1) // 2, (kh - 1) // 2, (kw - 1) // 2))
+        wp = wc(cw, "stem3d", lambda w: w.reshape(w.shape[0], -1))
+        sites = ops.geom_sites(g)
+        stats = torch.zeros((2 * Co,), device=video.device, dtype=torch.float32) if training else None
+        u = ops.conv_fwd(xc, wp, g, bias=cb, colstats=stats)
+        bnbuf = _bn_buf(stats, bn_w, bn_b, rm, rv, sites, training, momentum)
+        y, idx = ops.bn_relu_maxpool_fwd(u, bnbuf[0], bnbuf[1], B * T, g.Ho, g.Wo, Co)
+        ctx.save_for_backward(xc, u, bnbuf, bn_w, cw, idx)
+        ctx.g, ctx.training = g, training
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xc, u, bnbuf, bn_w, cw, idx = ctx.saved_tensors
+        if not ctx.training:
+            raise RuntimeError("avec_b200: stem backward needs training-mode BatchNorm statistics")
+        g = ctx.g
+        Co = cw.shape[0]
+        dz = ops.bn_relu_maxpool_bwd(_c(dy), idx, g.N * g.To, g.Ho, g.Wo, Co)
+        du, _, dgamma, dbeta = ops.bn_bwd(dz, u, bnbuf, bn_w, L.ACT_NONE)
+        dcw = ops.conv_wgrad(du, xc, g).view(cw.shape)
+        dcb = ops.colsum(du)
+        return None, dcw, dcb, dgamma, dbeta, None, None, None, None
+
+
+def _pack_fwd(w):   # (Co, Ci, kh, kw) -> [Co, taps*Ci]
+    return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)
+
+
+def _pack_dgrad(w):  # (Co, Ci, kh, kw) -> [Ci, taps*Co]
+    return w.permute(1, 2, 3, 0).reshape(w.shape[1], -1)
+
+
+def _unpack_wgrad(dw, w):  # [Co, taps*Ci] -> (Co, Ci, kh, kw)
+    Co, Ci, kh, kw = w.shape
+    return dw.view(Co, kh, kw, Ci).permute(0, 3, 1, 2).contiguous()
+
+
+class ResBlockFn(Function):
+    """ResNet BasicBlock on channels-last images: relu(bn2(conv2(relu(bn1(conv1(x))))) + shortcut(x))"""
+
+    @staticmethod
+    def forward(ctx, x, w1, g1w, g1b, rm1, rv1, w2, g2w, g2b, rm2, rv2, wr, grw, grb, rmr, rvr, stride, training, momentum):
+        N, H, W, Ci = x.shape
+        Co = w1.shape[0]
+        x = _c(x)
+        dev = x.device
+
+        def st():
+            return torch.zeros((2 * Co,), device=dev, dtype=torch.float32) if training else None
+
+        ga = ops.make_geom(N, 1, H, W, Ci, Co, (1, 3, 3), (1, stride, stride), (0, 1, 1))
+        s1 = st()
+        u1 = ops.conv_fwd(x, wc(w1, "cf", _pack_fwd), ga, colstats=s1)
+        sites = ops.geom_sites(ga)
+        bn1 = _bn_buf(s1, g1w, g1b, rm1, rv1, sites, training, momentum)
+        a1 = ops.bn_apply(u1, bn1[0], bn1[1], L.ACT_RELU)
+        gb = ops.make_geom(N, 1, ga.Ho, ga.Wo, Co, Co, (1, 3, 3), (1, 1, 1), (0, 1, 1))
+        s2 = st()
+        u2 = ops.conv_fwd(a1, wc(w2, "cf", _pack_fwd), gb, colstats=s2)
+        bn2 = _bn_buf(s2, g2w, g2b, rm2, rv2, sites, training, momentum)
+        if wr is not None:
+            gr = ops.make_geom(N, 1, H, W, Ci, Co, (1, 1, 1), (1, stride, stride), (0, 0, 0))
+            sr = st()
+            ur = ops.conv_fwd(x, wc(wr, "cf", _pack_fwd), gr, colstats=sr)
+            bnr = _bn_buf(sr, grw, grb, rmr, rvr, sites, training, momentum)
+            r = ops.bn_apply(ur, bnr[0], bnr[1], L.ACT_NONE)
+        else:
+            gr, ur, bnr = None, None, None
+            r = x.view(sites, Co)
+        y = ops.bn_apply(u2, bn2[0], bn2[1], L.ACT_RELU, res=r)
+        ctx.save_for_backward(x, u1, bn1, a1, u2, bn2, ur, bnr, r, w1, g1w, w2, g2w, wr, grw)
+        ctx.geoms, ctx.training = (ga, gb, gr), training
+        return y.view(N, ga.Ho, ga.Wo, Co)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, u1, bn1, a1, u2, bn2, ur, bnr, r, w1, g1w, w2, g2w, wr, grw = ctx.saved_tensors
+        if not ctx.training:
+            raise RuntimeError("avec_b200: ResNet backward needs training-mode BatchNorm statistics")
+        ga, gb, gr = ctx.geoms
+        Co = w1.shape[0]
+        dy2 = _c(dy).view(-1, Co)
+        du2, dres, dg2, db2 = ops.bn_bwd(dy2, u2, bn2, g2w, L.ACT_RELU, res=r, want_dres=True)
+        da1 = ops.conv_dgrad(du2, wc(w2, "cd", _pack_dgrad), gb)
+        dw2 = _unpack_wgrad(ops.conv_wgrad(du2, a1, gb), w2)
+        du1, _, dg1, db1 = ops.bn_bwd(da1, u1, bn1, g1w, L.ACT_RELU)
+        dw1 = _unpack_wgrad(ops.conv_wgrad(du1, x, ga), w1)
+        if wr is not None:
+            dur, _, dgr, dbr = ops.bn_bwd(dres, ur, bnr, grw, L.ACT_NONE)
+            dxr = ops.conv_dgrad(dur, wc(wr, "cd", _pack_dgrad), gr)
+            dwr = _unpack_wgrad(ops.conv_wgrad(dur, x, gr), wr)
+            dx = ops.conv_dgrad(du1, wc(w1, "cd", _pack_dgrad), ga, epi=L.EPI_RESIDUAL, aux=dxr)
+        else:
+            dwr = dgr = dbr = None
+            dx = ops.conv_dgrad(du1, wc(w1, "cd", _pack_dgrad), ga, epi=L.EPI_RESIDUAL, aux=dres)
+        return (dx.view(x.shape), dw1, dg1, db1, None, None, dw2, dg2, db2, None, None, dwr, dgr, dbr, None, None, None, None, None)
+
+
+class AvgPoolFn(Function):
+    """[N, H, W, C] -> [N, C]"""
+
+    @staticmethod
+    def forward(ctx, x):
+        N, H, W, Cn = x.shape
+        ctx.shp = x.shape
+        return ops.avgpool_fwd(_c(x), N, H * W, Cn)
+
+    @staticmethod
+    def backward(ctx, dy):
+        N, H, W, Cn = ctx.shp
+        return ops.avgpool_bwd(_c(dy), N, H * W, Cn).view(ctx.shp)

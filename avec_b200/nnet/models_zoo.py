@@ -1,0 +1,93 @@
+"""Zoo models with the reference's constructor arguments and forward(inputs) -> dict convention
+(reference nnet/models_zoo.py:64-182).  Only the encoder hot path is re-implemented; `Model` here is a light nn.Module
+base (compile / forward / losses) - the reference's training runtime (nnet/model.py fit/evaluate/save/...) is out of
+scope and keeps working by patching these encoders into it (avec_b200.patch_reference)."""
+import torch
+import torch.nn as nn
+
+from .. import functional as AF
+from . import networks
+from .layers import check_dropout
+from .losses import CTCLoss
+
+
+class Model(nn.Module):
+    def __init__(self, name="model"):
+        super().__init__()
+        self.name = name
+        self.compiled = False
+        self.losses = None
+        self.loss_weights = None
+
+    def compile(self, losses=None, loss_weights=None, optimizer=None, metrics=None, decoders=None):
+        self.losses = losses if losses is not None else CTCLoss()
+        self.loss_weights = loss_weights
+        self.optimizer, self.metrics, self.decoders = optimizer, metrics, decoders
+        self.compiled = True
+
+    def num_params(self):
+        return sum(p.numel() for p in self.parameters())
+
+    def _prepare(self):
+        check_dropout(self)
+        AF.new_step()
+
+    def compute_loss(self, outputs, targets):
+        """sum_k w_k * CTC(outputs[k]) with weights mapped to the outputs by position for lists (model.py:217) or by
+        key for dicts - the reference's forward_model loss bookkeeping (model.py:275-287)."""
+        keys = list(outputs.keys())
+        w = self.loss_weights
+        if w is None:
+            w = [1.0] * len(keys)
+        if isinstance(w, dict):
+            w = [w[k] for k in keys]
+        loss_fn = self.losses if self.losses is not None else CTCLoss()
+        total = 0.0
+        for k, wk in zip(keys, w):
+            total = total + wk * loss_fn(targets, outputs[k])
+        return total
+
+
+class AudioEfficientConformerInterCTC(Model):
+    def __init__(self, vocab_size=256, att_type="patch", interctc_blocks=[3, 6, 10, 13]):
+        super().__init__(name="Audio Efficient Conformer Inter CTC")
+        self.encoder = networks.AudioEfficientConformerEncoder(vocab_size=vocab_size, att_type=att_type, interctc_blocks=interctc_blocks)
+
+    def forward(self, inputs):
+        self._prepare()
+        x, lengths = inputs
+        x, lengths, interctc_outputs = self.encoder(x, lengths)
+        outputs = {"outputs": [x, lengths]}
+        outputs.update(interctc_outputs)
+        return outputs
+
+
+class VisualEfficientConformerInterCTC(Model):
+    def __init__(self, vocab_size=256, interctc_blocks=[3, 6, 9], test_augments=None):
+        super().__init__(name="Visual Efficient Conformer Inter CTC")
+        self.encoder = networks.VisualEfficientConformerEncoder(vocab_size=vocab_size, interctc_blocks=interctc_blocks)
+        assert test_augments is None, "flip TTA is an evaluation-time feature outside the hot path"
+
+    def forward(self, inputs):
+        self._prepare()
+        video, video_lengths = inputs
+        x, lengths, interctc_outputs = self.encoder(video, video_lengths)
+        outputs = {"outputs": [x, lengths]}
+        outputs.update(interctc_outputs)
+        return outputs
+
+
+class AudioVisualEfficientConformerInterCTC(Model):
+    def __init__(self, vocab_size=256, v_interctc_blocks=[3, 6], a_interctc_blocks=[8, 11], f_interctc_blocks=[2]):
+        super().__init__(name="Audio-Visual Efficient Conformer Inter CTC")
+        self.encoder = networks.AudioVisualEfficientConformerEncoder(
+            vocab_size=vocab_size, v_interctc_blocks=v_interctc_blocks, a_interctc_blocks=a_interctc_blocks,
+            f_interctc_blocks=f_interctc_blocks)
+
+    def forward(self, inputs):
+        self._prepare()
+        video, video_len, audio, audio_len = inputs
+        x, lengths, interctc_outputs = self.encoder(video, video_len, audio, audio_len)
+        outputs = {"outputs": [x, lengths]}
+        outputs.update(interctc_outputs)
+        return outputs

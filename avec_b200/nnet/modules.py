@@ -1,0 +1,161 @@
+"""ConformerBlock sub-modules with the reference's constructor arguments, attribute names and state_dict keys
+(reference nnet/modules.py:257-426, nnet/attentions.py:215-382, nnet/embeddings.py:101-158).  forward() dispatches to
+the fused autograd Functions in avec_b200.functional (hand-written sm_100a kernels)."""
+import torch
+import torch.nn as nn
+
+from .. import functional as AF
+from .layers import Linear, Conv1d, Placeholder, Dropout, Swish
+
+_pe_cache = {}
+
+
+def rel_pos_table(T, D, device, dtype):
+    """rows r = 0..2T-2 hold the sinusoid of relative position T-1-r (even channels sin, odd cos); the slice
+    pos_encoding[max_len-T : max_len-1+T] of RelativeSinusoidalPositionalEncoding (embeddings.py:117-152)."""
+    key = (T, D, str(device), dtype)
+    t = _pe_cache.get(key)
+    if t is None:
+        pos = torch.arange(T - 1, -T, -1, dtype=torch.float).unsqueeze(1)
+        angles = pos / 10000 ** (2 * torch.arange(0, D // 2, dtype=torch.float).unsqueeze(0) / D)
+        pe = torch.zeros(2 * T - 1, D)
+        pe[:, 0::2] = angles.sin()
+        pe[:, 1::2] = angles.cos()
+        t = pe.to(device=device, dtype=dtype).contiguous()
+        _pe_cache[key] = t
+    return t
+
+
+class FeedForwardModule(nn.Module):
+    def __init__(self, dim_model, dim_ffn, drop_rate, act_fun="Swish", inner_dropout=True):
+        super().__init__()
+        assert act_fun == "Swish"
+        self.layers = nn.Sequential(
+            nn.LayerNorm(dim_model, eps=1e-6),
+            Linear(dim_model, dim_ffn),
+            Swish(),
+            Dropout(p=drop_rate) if inner_dropout else Placeholder("Identity"),
+            Linear(dim_ffn, dim_model),
+            Dropout(p=drop_rate),
+        )
+
+    def forward_residual(self, x):
+        """x + 1/2 * FFN(x): the half-step residual of ConformerBlock.forward (blocks.py:292,301) is fused in."""
+        l = self.layers
+        return AF.FFNFn.apply(x, l[0].weight, l[0].bias, l[1].weight, l[1].bias, l[4].weight, l[4].bias)
+
+
+class RelPos1dMultiHeadAttention(nn.Module):
+    """Parameter holder of the relative-position attention (attentions.py:215-232); P = patch size (1 = regular)."""
+
+    patch_size = 1
+
+    def __init__(self, dim_model, num_heads, num_pos_embeddings=10000, attn_drop_rate=0.0, weight_init="default",
+                 bias_init="default", output_proj=True, causal=False):
+        super().__init__()
+        assert not causal and output_proj and attn_drop_rate == 0.0
+        self.num_heads = num_heads
+        self.dim_model = dim_model
+        self.dim_head = dim_model // num_heads
+        self.max_len = num_pos_embeddings
+        self.query_layer = Linear(dim_model, dim_model)
+        self.key_layer = Linear(dim_model, dim_model)
+        self.value_layer = Linear(dim_model, dim_model)
+        self.output_layer = Linear(dim_model, dim_model)
+        self.pos_layer = Linear(dim_model, dim_model)
+
+
+class RelPosPatch1dMultiHeadAttention(RelPos1dMultiHeadAttention):
+    def __init__(self, dim_model, num_heads, patch_size, num_pos_embeddings=10000, attn_drop_rate=0.0,
+                 weight_init="default", bias_init="default", output_proj=True):
+        super().__init__(dim_model, num_heads, num_pos_embeddings, attn_drop_rate, weight_init, bias_init, output_proj)
+        self.patch_size = patch_size
+
+
+att_dict = {
+    "RelPos1dMultiHeadAttention": RelPos1dMultiHeadAttention,
+    "RelPosPatch1dMultiHeadAttention": RelPosPatch1dMultiHeadAttention,
+}
+
+
+class AttentionModule(nn.Module):
+    def __init__(self, dim_model, att_params, drop_rate, residual=False):
+        super().__init__()
+        if att_params["class"] not in att_dict:
+            raise NotImplementedError(f"avec_b200: attention class {att_params['class']} is not implemented yet")
+        self.norm = nn.LayerNorm(dim_model, eps=1e-6)
+        self.attention = att_dict[att_params["class"]](dim_model=dim_model, **att_params["params"])
+        self.dropout = Dropout(drop_rate)
+        self.residual = residual
+
+    def forward_residual(self, x, klen):
+        """x + MHSA(LN(x)) with key-padding lengths klen (int32 [B] on device, or None)."""
+        a = self.attention
+        B, T, D = x.shape
+        P = a.patch_size
+        Tp = -(-T // P)
+        pe = rel_pos_table(Tp, D, x.device, x.dtype)
+        return AF.AttentionFn.apply(
+            x, self.norm.weight, self.norm.bias,
+            a.query_layer.weight, a.query_layer.bias, a.key_layer.weight, a.key_layer.bias,
+            a.value_layer.weight, a.value_layer.bias, a.output_layer.weight, a.output_layer.bias,
+            a.pos_layer.weight, a.pos_layer.bias, pe, klen, a.num_heads, P)
+
+
+class ConvolutionModule(nn.Module):
+    def __init__(self, dim_model, dim_expand, drop_rate, stride, act_fun="Swish", conv_params=None, channels_last=True,
+                 batch_norm=True):
+        super().__init__()
+        assert act_fun == "Swish" and batch_norm and conv_params["class"] == "Conv1d"
+        k = conv_params["params"]["kernel_size"]
+        assert conv_params["params"].get("padding", "same") == "same" and k <= 15
+        self.layers = nn.Sequential(
+            nn.LayerNorm(dim_model, eps=1e-6),
+            Conv1d(dim_model, 2 * dim_expand, kernel_size=1),
+            Placeholder("GLU"),
+            Conv1d(dim_expand, dim_expand, kernel_size=k, stride=stride, groups=dim_expand),
+            nn.BatchNorm1d(dim_expand),
+            Swish(),
+            Conv1d(dim_expand, dim_expand, kernel_size=1),
+            Dropout(p=drop_rate),
+        )
+        self.stride = stride
+
+    def forward_residual(self, x, conv_res):
+        """conv_res(x) + ConvModule(x) (blocks.py:298); conv_res is nn.Identity or a k=1 strided Conv1d."""
+        l = self.layers
+        bn = l[4]
+        training = self.training
+        if training and bn.track_running_stats:
+            bn.num_batches_tracked.add_(1)
+        has_res = not isinstance(conv_res, nn.Identity)
+        return AF.ConvModuleFn.apply(
+            x, l[0].weight, l[0].bias, l[1].weight, l[1].bias, l[3].weight, l[3].bias,
+            bn.weight, bn.bias, bn.running_mean, bn.running_var, l[6].weight, l[6].bias,
+            conv_res.weight if has_res else None, conv_res.bias if has_res else None,
+            self.stride, training, bn.momentum)
+
+
+class InterCTCResModule(nn.Module):
+    def __init__(self, dim_model, vocab_size):
+        super().__init__()
+        self.proj_1 = Linear(dim_model, vocab_size)
+        self.proj_2 = Linear(vocab_size, dim_model)
+
+    def forward(self, x):
+        return AF.InterCTCFn.apply(x, self.proj_1.weight, self.proj_1.bias, self.proj_2.weight, self.proj_2.bias)
+
+
+class FusionModule(nn.Module):
+    def __init__(self, a_dim_model=360, v_dim_model=360, f_dim_model=360, ff_ratio=4):
+        super().__init__()
+        self.layers = nn.Sequential(
+            Linear(a_dim_model + v_dim_model, ff_ratio * f_dim_model),
+            Swish(),
+            Linear(ff_ratio * f_dim_model, f_dim_model),
+        )
+
+    def forward(self, audio, video):
+        x = torch.cat([audio, video], dim=-1)
+        l = self.layers
+        return AF.MLPFn.apply(x, l[0].weight, l[0].bias, l[2].weight, l[2].bias)

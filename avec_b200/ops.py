@@ -1,0 +1,388 @@
+"""Tensor-level wrappers over the C ABI: they take torch CUDA tensors, allocate outputs with torch (device memory and
+streams are the only things PyTorch provides here) and launch the sm_100a kernels on the current stream."""
+import torch
+
+from . import _lib as L
+
+_DT = {torch.float32: L.F32, torch.bfloat16: L.BF16}
+
+# global knob: which GEMM engine avec_gemm uses (AUTO = tcgen05 whenever the operands are bf16 and the shape qualifies)
+GEMM_IMPL = L.IMPL_AUTO
+
+
+def set_gemm_impl(name):
+    global GEMM_IMPL
+    GEMM_IMPL = {"auto": L.IMPL_AUTO, "simt": L.IMPL_SIMT, "tcgen05": L.IMPL_TCGEN05}[name]
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _dt(t):
+    return _DT[t.dtype]
+
+
+def _cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("avec_b200 ops need CUDA tensors: the hot path has no CPU fallback")
+
+
+def launch_count():
+    return L.load().avec_launch_count()
+
+
+def reset_launch_count():
+    L.load().avec_reset_launch_count()
+
+
+# --------------------------------------------------------------------------------------------------------------- GEMM
+def _gemm(args):
+    L.check(L.load().avec_gemm(args, _stream()), "avec_gemm")
+
+
+def _epi(args, epi, alpha, bias, out, out2=None, aux=None, colstats=None):
+    args.epi = epi
+    args.alpha = alpha
+    args.bias = _p(bias)
+    args.out = out.data_ptr()
+    args.out_dtype = _dt(out)
+    args.ldo = out.stride(0) if out.dim() == 2 else out.shape[-1]
+    if out2 is not None:
+        args.out2, args.out2_dtype, args.ldo2 = out2.data_ptr(), _dt(out2), out2.stride(0)
+    if aux is not None:
+        args.aux, args.aux_dtype, args.ldaux = aux.data_ptr(), _dt(aux), aux.stride(0)
+    args.colstats = _p(colstats)
+
+
+def _split_for(M, N, K):
+    tiles = -(-M // 128) * -(-N // 192)
+    kb = -(-K // 64)
+    return max(1, min(kb, 296 // max(1, tiles), 512))
+
+
+def linear_fwd(x, w, bias=None, epi=L.EPI_LINEAR, alpha=1.0, aux=None, out_dtype=None, want_pre=False, colstats=None):
+    """out[M,N] = epi(x[M,K] @ w[N,K]^T + bias).  x, w same dtype, row-major (w may have a padded leading dim)."""
+    _cuda(x, w)
+    M, K = x.shape
+    N = w.shape[0]
+    out = torch.empty((M, N), device=x.device, dtype=out_dtype or x.dtype)
+    pre = torch.empty((M, N), device=x.device, dtype=x.dtype) if want_pre else None
+    a = L.GemmArgs()
+    a.mode, a.impl, a.M, a.N, a.K = L.GEMM_PLAIN, GEMM_IMPL, M, N, K
+    a.A, a.sam, a.sak = x.data_ptr(), x.stride(0), 1
+    a.B, a.sbn, a.sbk = w.data_ptr(), w.stride(0), 1
+    a.ab_dtype = _dt(x)
+    _epi(a, epi, alpha, bias, out, pre, aux, colstats)
+    _gemm(a)
+    return (out, pre) if want_pre else out
+
+
+def linear_dgrad(dy, w, epi=L.EPI_LINEAR, alpha=1.0, aux=None, out_dtype=None):
+    """dx[M,K] = epi(dy[M,N] @ w[N,K])  (B operand read transposed in place: MN-major descriptor, no copy)."""
+    _cuda(dy, w)
+    M, N = dy.shape
+    K = w.shape[1]
+    out = torch.empty((M, K), device=dy.device, dtype=out_dtype or dy.dtype)
+    a = L.GemmArgs()
+    a.mode, a.impl, a.M, a.N, a.K = L.GEMM_PLAIN, GEMM_IMPL, M, K, N
+    a.A, a.sam, a.sak = dy.data_ptr(), dy.stride(0), 1
+    a.B, a.sbn, a.sbk = w.data_ptr(), 1, w.stride(0)
+    a.ab_dtype = _dt(dy)
+    _epi(a, epi, alpha, None, out, None, aux)
+    _gemm(a)
+    return out
+
+
+def linear_wgrad(dy, x, alpha=1.0):
+    """dw[N,K] (fp32) = alpha * dy[M,N]^T @ x[M,K], split-K over the M tokens with atomic fp32 accumulation."""
+    _cuda(dy, x)
+    M, N = dy.shape
+    K = x.shape[1]
+    dw = torch.zeros((N, K), device=dy.device, dtype=torch.float32)
+    a = L.GemmArgs()
+    a.mode, a.impl, a.M, a.N, a.K = L.GEMM_PLAIN, GEMM_IMPL, N, K, M
+    a.A, a.sam, a.sak = dy.data_ptr(), 1, dy.stride(0)
+    a.B, a.sbn, a.sbk = x.data_ptr(), 1, x.stride(0)
+    a.ab_dtype = _dt(dy)
+    _epi(a, L.EPI_ACCUM, alpha, None, dw)
+    a.split_k = _split_for(N, K, M)
+    _gemm(a)
+    return dw
+
+
+def colsum(x, alpha=1.0):
+    _cuda(x)
+    rows, Cn = x.shape
+    out = torch.zeros((Cn,), device=x.device, dtype=torch.float32)
+    L.check(L.load().avec_colsum(x.data_ptr(), _dt(x), rows, Cn, x.stride(0), alpha, out.data_ptr(), 1, _stream()), "avec_colsum")
+    return out
+
+
+def make_geom(N, Ti, Hi, Wi, Cin, Cout, k, s, p):
+    g = L.ConvGeom()
+    g.N, g.Ti, g.Hi, g.Wi, g.C, g.Co = N, Ti, Hi, Wi, Cin, Cout
+    g.KT, g.KH, g.KW = k
+    g.st, g.sh, g.sw = s
+    g.pt, g.ph, g.pw = p
+    g.To = (Ti + (k[0] - 1) - k[0]) // s[0] + 1   # "same" pre-padding: total pad = k-1  (layers.py:250-258)
+    g.Ho = (Hi + (k[1] - 1) - k[1]) // s[1] + 1
+    g.Wo = (Wi + (k[2] - 1) - k[2]) // s[2] + 1
+    return g
+
+
+def geom_sites(g, out=True):
+    return g.N * g.To * g.Ho * g.Wo if out else g.N * g.Ti * g.Hi * g.Wi
+
+
+def conv_fwd(x, wp, g, bias=None, epi=L.EPI_LINEAR, colstats=None, aux=None):
+    """x [N,Ti,Hi,Wi,C] channels-last, wp [Co, taps*C] -> y [sites_out, Co]."""
+    _cuda(x, wp)
+    M = geom_sites(g, True)
+    out = torch.empty((M, g.Co), device=x.device, dtype=x.dtype)
+    a = L.GemmArgs()
+    a.mode, a.impl, a.M, a.N, a.K = L.GEMM_CONV_FWD, GEMM_IMPL, M, g.Co, wp.shape[1]
+    a.A, a.B, a.ab_dtype, a.g = x.data_ptr(), wp.data_ptr(), _dt(x), g
+    _epi(a, epi, 1.0, bias, out, None, aux, colstats)
+    _gemm(a)
+    return out
+
+
+def conv_dgrad(dy, wd, g, epi=L.EPI_LINEAR, aux=None):
+    """dy [sites_out, Co], wd [C, taps*Co] -> dx [sites_in, C] (optionally + aux: merging two gradient branches)."""
+    _cuda(dy, wd)
+    M = geom_sites(g, False)
+    out = torch.empty((M, g.C), device=dy.device, dtype=dy.dtype)
+    a = L.GemmArgs()
+    a.mode, a.impl, a.M, a.N, a.K = L.GEMM_CONV_DGRAD, GEMM_IMPL, M, g.C, wd.shape[1]
+    a.A, a.B, a.ab_dtype, a.g = dy.data_ptr(), wd.data_ptr(), _dt(dy), g
+    _epi(a, epi, 1.0, None, out, None, aux)
+    _gemm(a)
+    return out
+
+
+def conv_wgrad(dy, x, g):
+    """dw [Co, taps*C] fp32 = sum over output sites of dy[site, co] * x[shift(site, tap), ci]."""
+    _cuda(dy, x)
+    taps = g.KT * g.KH * g.KW
+    sites = geom_sites(g, True)
+    dw = torch.zeros((g.Co, taps * g.C), device=dy.device, dtype=torch.float32)
+    a = L.GemmArgs()
+    a.mode, a.impl, a.M, a.N, a.K = L.GEMM_CONV_WGRAD, GEMM_IMPL, g.Co, taps * g.C, sites
+    a.A, a.B, a.ab_dtype, a.g = dy.data_ptr(), x.data_ptr(), _dt(dy), g
+    _epi(a, L.EPI_ACCUM, 1.0, None, dw)
+    a.split_k = _split_for(g.Co, taps * g.C, sites)
+    _gemm(a)
+    return dw
+
+
+# ------------------------------------------------------------------------------------------------------ normalisations
+def layernorm_fwd(x, gamma, beta, P=1, eps=1e-6):
+    """x [B,T,C] -> y [B,ceil(T/P),C] (mean over P consecutive LayerNorm'ed frames), mean/rstd [B*T] fp32."""
+    _cuda(x)
+    B, T, Cn = x.shape
+    Tp = -(-T // P)
+    y = torch.empty((B, Tp, Cn), device=x.device, dtype=x.dtype)
+    mean = torch.empty((B * T,), device=x.device, dtype=torch.float32)
+    rstd = torch.empty_like(mean)
+    L.check(L.load().avec_layernorm_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), mean.data_ptr(),
+                                        rstd.data_ptr(), B, T, Cn, P, eps, _dt(x), _stream()), "avec_layernorm_fwd")
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, x, gamma, mean, rstd, P=1, dres=None, res_stride=1):
+    """returns dx [B,T,C], dgamma, dbeta (fp32).  dx += dres[b, t/res_stride] on frames t % res_stride == 0."""
+    B, T, Cn = x.shape
+    dx = torch.empty_like(x)
+    dg = torch.zeros((Cn,), device=x.device, dtype=torch.float32)
+    db = torch.zeros_like(dg)
+    L.check(L.load().avec_layernorm_bwd(dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                        _p(dres), res_stride, dx.data_ptr(), dg.data_ptr(), db.data_ptr(), B, T, Cn, P,
+                                        _dt(x), _stream()), "avec_layernorm_bwd")
+    return dx, dg, db
+
+
+def upsample_add(x, o, P):
+    B, T, Cn = x.shape
+    y = torch.empty_like(x)
+    L.check(L.load().avec_upsample_add(x.data_ptr(), o.data_ptr(), y.data_ptr(), B, T, o.shape[1], Cn, P, _dt(x), _stream()),
+            "avec_upsample_add")
+    return y
+
+
+def pool_sum(dy, P):
+    B, T, Cn = dy.shape
+    Tp = -(-T // P)
+    out = torch.empty((B, Tp, Cn), device=dy.device, dtype=dy.dtype)
+    L.check(L.load().avec_pool_sum(dy.data_ptr(), out.data_ptr(), B, T, Tp, Cn, P, _dt(dy), _stream()), "avec_pool_sum")
+    return out
+
+
+def softmax_fwd(x, out_dtype):
+    rows, Cn = x.shape
+    y = torch.empty((rows, Cn), device=x.device, dtype=out_dtype)
+    L.check(L.load().avec_softmax_fwd(x.data_ptr(), _dt(x), y.data_ptr(), _dt(y), rows, Cn, _stream()), "avec_softmax_fwd")
+    return y
+
+
+def softmax_bwd(dy, y, dadd=None, out_dtype=None):
+    rows, Cn = y.shape
+    dx = torch.empty((rows, Cn), device=y.device, dtype=out_dtype or y.dtype)
+    L.check(L.load().avec_softmax_bwd(dy.data_ptr(), y.data_ptr(), _dt(y), _p(dadd), dx.data_ptr(), _dt(dx), rows, Cn,
+                                      _stream()), "avec_softmax_bwd")
+    return dx
+
+
+def bn_stats(u2d):
+    rows, Cn = u2d.shape
+    stats = torch.zeros((2 * Cn,), device=u2d.device, dtype=torch.float32)
+    L.check(L.load().avec_bn_stats(u2d.data_ptr(), _dt(u2d), rows, Cn, stats.data_ptr(), _stream()), "avec_bn_stats")
+    return stats
+
+
+def bn_finalize(stats, gamma, beta, count, running_mean=None, running_var=None, eps=1e-5, momentum=0.1):
+    Cn = stats.numel() // 2
+    buf = torch.empty((4, Cn), device=stats.device, dtype=torch.float32)  # scale, shift, mean, rstd
+    L.check(L.load().avec_bn_finalize(stats.data_ptr(), _p(gamma), _p(beta), buf[0].data_ptr(), buf[1].data_ptr(),
+                                      buf[2].data_ptr(), buf[3].data_ptr(), _p(running_mean), _p(running_var), count, Cn,
+                                      eps, momentum, _stream()), "avec_bn_finalize")
+    return buf
+
+
+def bn_eval_affine(gamma, beta, running_mean, running_var, eps=1e-5):
+    Cn = running_mean.numel()
+    buf = torch.empty((2, Cn), device=running_mean.device, dtype=torch.float32)
+    L.check(L.load().avec_bn_eval_affine(_p(gamma), _p(beta), running_mean.data_ptr(), running_var.data_ptr(),
+                                         buf[0].data_ptr(), buf[1].data_ptr(), Cn, eps, _stream()), "avec_bn_eval_affine")
+    return buf
+
+
+def bn_apply(u2d, scale, shift, act, res=None):
+    rows, Cn = u2d.shape
+    y = torch.empty_like(u2d)
+    L.check(L.load().avec_bn_apply(u2d.data_ptr(), scale.data_ptr(), shift.data_ptr(), _p(res), y.data_ptr(), rows, Cn, act,
+                                   _dt(u2d), _stream()), "avec_bn_apply")
+    return y
+
+
+def bn_bwd(dy2d, u2d, bnbuf, gamma, act, res=None, want_dres=False):
+    """BatchNorm (+activation, + residual add before it) backward with batch statistics.
+    returns du, dres (or None), dgamma, dbeta."""
+    rows, Cn = u2d.shape
+    sums = torch.zeros((2 * Cn,), device=u2d.device, dtype=torch.float32)
+    lib = L.load()
+    L.check(lib.avec_bn_bwd_reduce(dy2d.data_ptr(), u2d.data_ptr(), bnbuf[0].data_ptr(), bnbuf[1].data_ptr(), _p(res),
+                                   bnbuf[2].data_ptr(), bnbuf[3].data_ptr(), sums.data_ptr(), rows, Cn, act, _dt(u2d),
+                                   _stream()), "avec_bn_bwd_reduce")
+    du = torch.empty_like(u2d)
+    dres = torch.empty_like(u2d) if want_dres else None
+    L.check(lib.avec_bn_bwd_apply(dy2d.data_ptr(), u2d.data_ptr(), bnbuf[0].data_ptr(), bnbuf[1].data_ptr(), _p(res),
+                                  bnbuf[2].data_ptr(), bnbuf[3].data_ptr(), _p(gamma), sums.data_ptr(), du.data_ptr(),
+                                  _p(dres), rows, Cn, act, _dt(u2d), _stream()), "avec_bn_bwd_apply")
+    return du, dres, sums[Cn:], sums[:Cn]
+
+
+# ----------------------------------------------------------------------------------------------------------- attention
+def relpos_attn_fwd(qkv, e, klen, qlen, B, T, H, d):
+    D = H * d
+    o = torch.empty((B * T, D), device=qkv.device, dtype=qkv.dtype)
+    probs = torch.empty((B, H, T, T), device=qkv.device, dtype=torch.float32)
+    L.check(L.load().avec_relpos_attn_fwd(qkv.data_ptr(), e.data_ptr(), _p(klen), qlen, o.data_ptr(), probs.data_ptr(), B, T,
+                                          H, d, _dt(qkv), _stream()), "avec_relpos_attn_fwd")
+    return o, probs
+
+
+def relpos_attn_bwd(do, qkv, e, probs, B, T, H, d):
+    D = H * d
+    dqkv = torch.empty_like(qkv)
+    de = torch.zeros((2 * T - 1, D), device=qkv.device, dtype=torch.float32)
+    ws = torch.empty_like(probs)
+    L.check(L.load().avec_relpos_attn_bwd(do.data_ptr(), qkv.data_ptr(), e.data_ptr(), probs.data_ptr(), ws.data_ptr(),
+                                          dqkv.data_ptr(), de.data_ptr(), B, T, H, d, _dt(qkv), _stream()),
+            "avec_relpos_attn_bwd")
+    return dqkv, de
+
+
+# --------------------------------------------------------------------------------------------------------- conv module
+def glu_dwconv_fwd(pre, w, bias, stride, ksize=15, want_stats=True):
+    B, T, C2 = pre.shape
+    Cn = C2 // 2
+    pad = (ksize - 1) // 2
+    To = (T + 2 * pad - ksize) // stride + 1
+    u = torch.empty((B, To, Cn), device=pre.device, dtype=pre.dtype)
+    stats = torch.zeros((2 * Cn,), device=pre.device, dtype=torch.float32) if want_stats else None
+    L.check(L.load().avec_glu_dwconv_fwd(pre.data_ptr(), w.data_ptr(), _p(bias), u.data_ptr(), _p(stats), B, T, To, Cn, ksize,
+                                         stride, pad, _dt(pre), _stream()), "avec_glu_dwconv_fwd")
+    return u, stats
+
+
+def glu_dwconv_bwd(du, pre, w, stride, ksize=15):
+    B, T, C2 = pre.shape
+    Cn = C2 // 2
+    pad = (ksize - 1) // 2
+    To = du.shape[1]
+    dpre = torch.empty_like(pre)
+    dw = torch.zeros((Cn, ksize), device=pre.device, dtype=torch.float32)
+    db = torch.zeros((Cn,), device=pre.device, dtype=torch.float32)
+    L.check(L.load().avec_glu_dwconv_bwd(du.data_ptr(), pre.data_ptr(), w.data_ptr(), dpre.data_ptr(), dw.data_ptr(),
+                                         db.data_ptr(), B, T, To, Cn, ksize, stride, pad, _dt(pre), _stream()),
+            "avec_glu_dwconv_bwd")
+    return dpre, dw, db
+
+
+# ---------------------------------------------------------------------------------------------------------- front-ends
+def stft_mel_log(wave, fb, layout=0):
+    _cuda(wave, fb)
+    B, Ln = wave.shape
+    F = Ln // 160 + 1
+    out = torch.empty((B, F, 80) if layout == 0 else (B, 80, F), device=wave.device, dtype=torch.float32)
+    L.check(L.load().avec_stft_mel_log(wave.data_ptr(), fb.data_ptr(), out.data_ptr(), B, Ln, F, layout, _stream()),
+            "avec_stft_mel_log")
+    return out
+
+
+def bn_relu_maxpool_fwd(u, scale, shift, N, Hi, Wi, Cn):
+    Ho, Wo = (Hi - 1) // 2 + 1, (Wi - 1) // 2 + 1
+    y = torch.empty((N, Ho, Wo, Cn), device=u.device, dtype=u.dtype)
+    idx = torch.empty((N, Ho, Wo, Cn), device=u.device, dtype=torch.uint8)
+    L.check(L.load().avec_bn_relu_maxpool_fwd(u.data_ptr(), scale.data_ptr(), shift.data_ptr(), y.data_ptr(), idx.data_ptr(), N,
+                                              Hi, Wi, Cn, Ho, Wo, _dt(u), _stream()), "avec_bn_relu_maxpool_fwd")
+    return y, idx
+
+
+def bn_relu_maxpool_bwd(dy, idx, N, Hi, Wi, Cn):
+    Ho, Wo = idx.shape[1], idx.shape[2]
+    dz = torch.empty((N * Hi * Wi, Cn), device=dy.device, dtype=dy.dtype)
+    L.check(L.load().avec_bn_relu_maxpool_bwd(dy.data_ptr(), idx.data_ptr(), dz.data_ptr(), N, Hi, Wi, Cn, Ho, Wo, _dt(dy),
+                                              _stream()), "avec_bn_relu_maxpool_bwd")
+    return dz
+
+
+def avgpool_fwd(x, N, HW, Cn):
+    y = torch.empty((N, Cn), device=x.device, dtype=x.dtype)
+    L.check(L.load().avec_avgpool_fwd(x.data_ptr(), y.data_ptr(), N, HW, Cn, _dt(x), _stream()), "avec_avgpool_fwd")
+    return y
+
+
+def avgpool_bwd(dy, N, HW, Cn):
+    dx = torch.empty((N * HW, Cn), device=dy.device, dtype=dy.dtype)
+    L.check(L.load().avec_avgpool_bwd(dy.data_ptr(), dx.data_ptr(), N, HW, Cn, _dt(dy), _stream()), "avec_avgpool_bwd")
+    return dx
+
+
+def convert(src, dtype):
+    """dtype cast through the library's own kernel (2-d, possibly strided rows)."""
+    if src.dtype == dtype and src.is_contiguous():
+        return src
+    s2 = src.reshape(-1, src.shape[-1]) if src.dim() != 2 else src
+    if s2.stride(-1) != 1:
+        s2 = s2.contiguous()
+    dst = torch.empty(s2.shape, device=src.device, dtype=dtype)
+    L.check(L.load().avec_convert(s2.data_ptr(), _dt(s2), s2.stride(0), dst.data_ptr(), _dt(dst), dst.stride(0), s2.shape[0],
+                                  s2.shape[1], _stream()), "avec_convert")
+    return dst.reshape(src.shape)

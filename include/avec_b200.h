@@ -1,0 +1,210 @@
+/*
+ * avec_b200.h — C ABI of the B200-native (sm_100a) hot path of AVEC's Efficient-Conformer encoder.
+ *
+ * The reference (burchim/AVEC) is pure Python on PyTorch: every entry point below replaces a *sequence of ATen calls*
+ * issued by a reference nn.Module.forward (and its autograd backward), cited per function as nnet/<file>.py:<lines>.
+ * Conventions:
+ *   - device pointers only, caller owns every buffer (no allocation, no host sync, no global state besides a
+ *     thread-local "last CUDA error" for diagnostics); all launches go to the caller's stream;
+ *   - activations are channels-last, row-major: tokens [rows, C]; images [N, H, W, C]; videos [N, T, H, W, C];
+ *   - `dtype` arguments select the activation element type (AVEC_F32 parity mode / AVEC_BF16 production mode);
+ *     parameters of normalisations, biases, statistics and all gradients of parameters are fp32;
+ *   - return 0 on success, negative avec_status otherwise (avec_strerror()).
+ */
+#ifndef AVEC_B200_H
+#define AVEC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* avec_stream_t; /* cudaStream_t */
+
+enum avec_status {
+    AVEC_OK = 0,
+    AVEC_ERR_INVALID = -1,     /* bad argument / unsupported shape */
+    AVEC_ERR_LAUNCH = -2,      /* cudaGetLastError() != success after a launch (see avec_last_cuda_error) */
+    AVEC_ERR_UNSUPPORTED = -3, /* combination not implemented by this build */
+    AVEC_ERR_DRIVER = -4       /* driver entry point (tensor-map encode) unavailable or failed */
+};
+
+enum avec_dtype { AVEC_F32 = 0, AVEC_BF16 = 1 };
+
+const char* avec_strerror(int status);
+int avec_last_cuda_error(void);
+int avec_version(void);
+/* number of kernels launched by this library on the calling thread since the last reset (bench.py's gpu_launches) */
+long long avec_launch_count(void);
+void avec_reset_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * GEMM / implicit-GEMM convolution:   out = epilogue( sum_k A(m,k) * B(n,k) )
+ * Replaces F.linear / addmm (nnet/layers.py:29-76), the k=1 Conv1d of the ConvModule (nnet/modules.py:372-381),
+ * conv2d/conv3d of the front-ends (nnet/networks.py:359-368, 459-471; nnet/blocks.py:64-91) and all their autograd
+ * backward GEMMs (dgrad / wgrad).
+ * ------------------------------------------------------------------------------------------------------------------ */
+enum avec_gemm_mode {
+    AVEC_GEMM_PLAIN = 0,      /* A(m,k) = A[m*sam + k*sak],  B(n,k) = B[n*sbn + k*sbk]                                  */
+    AVEC_GEMM_CONV_FWD = 1,   /* A = im2col(X): m = output site, k = (tap, ci);  B(n=co, k) = W[co][tap][ci]            */
+    AVEC_GEMM_CONV_DGRAD = 2, /* A = col2im gather of dY: m = input site, k = (tap, co);  B(n=ci,k) = Wd[ci][tap][co]    */
+    AVEC_GEMM_CONV_WGRAD = 3  /* A(m=co,k=site) = dY[site][co];  B(n=(tap,ci), k=site) = X[shift(site,tap)][ci]          */
+};
+
+enum avec_epilogue {
+    AVEC_EPI_LINEAR = 0,   /* out = alpha * (acc + bias)                                                              */
+    AVEC_EPI_SWISH = 1,    /* pre = acc + bias; out2 = pre (if given); out = pre * sigmoid(pre)                       */
+    AVEC_EPI_RESIDUAL = 2, /* out = aux + alpha * (acc + bias)                                                        */
+    AVEC_EPI_DSWISH = 3,   /* out = alpha * acc * swish'(aux)            (backward through Swish, aux = saved pre)     */
+    AVEC_EPI_ACCUM = 4,    /* out(fp32) += alpha * acc   (atomic; split-K partial sums of weight gradients)            */
+    AVEC_EPI_RELU = 5      /* out = max(0, alpha * (acc + bias) + aux?)                                               */
+};
+
+enum avec_gemm_impl { AVEC_IMPL_AUTO = 0, AVEC_IMPL_SIMT = 1, AVEC_IMPL_TCGEN05 = 2 };
+
+/* N-d convolution geometry (2-d and 1-d convolutions set the unused extents to 1). X is [N, Ti, Hi, Wi, C],
+ * Y is [N, To, Ho, Wo, Co], W is [Co][KT][KH][KW][C] (tap-major, channel-minor). */
+typedef struct avec_conv_geom {
+    int N, Ti, Hi, Wi, C;
+    int To, Ho, Wo, Co;
+    int KT, KH, KW;
+    int st, sh, sw; /* strides */
+    int pt, ph, pw; /* leading zero padding ("same": (k-1)/2, nnet/layers.py:250-258) */
+} avec_conv_geom;
+
+typedef struct avec_gemm_args {
+    int mode; /* avec_gemm_mode */
+    int impl; /* avec_gemm_impl */
+    int M, N, K;
+    const void* A;
+    long long sam, sak; /* element strides (PLAIN) */
+    const void* B;
+    long long sbn, sbk;
+    int ab_dtype; /* element type of A and B */
+    avec_conv_geom g;
+    int epi;
+    float alpha;
+    const float* bias; /* [N] or NULL */
+    void* out;
+    int out_dtype;
+    long long ldo;
+    void* out2;
+    int out2_dtype;
+    long long ldo2;
+    const void* aux;
+    int aux_dtype;
+    long long ldaux;
+    float* colstats; /* optional [2*N]: += sum_m v, += sum_m v^2 of v = acc + bias (BatchNorm batch statistics) */
+    int split_k;     /* ACCUM epilogue: number of K slices (0/1 = none) */
+} avec_gemm_args;
+
+int avec_gemm(const avec_gemm_args* args, avec_stream_t stream);
+
+/* out[n] (+)= alpha * sum_m x[m][n]      — bias gradients (autograd of the bias add in addmm / conv) */
+int avec_colsum(const void* x, int dtype, long long rows, int C, long long ldx, float alpha, float* out, int accumulate,
+                avec_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * LayerNorm (eps 1e-6) with the patch-attention average pooling folded in.
+ * fwd: y[b,t'] = 1/P * sum_{p<P, t'P+p<T} LN(x[b,t'P+p])     (P = 1: plain LayerNorm)
+ * Replaces nn.LayerNorm (nnet/modules.py:278,302,373; nnet/blocks.py:267,304) + MultiHeadAttention.pad +
+ * AvgPool1d of RelPosPatch1dMultiHeadAttention.forwardQKV (nnet/attentions.py:351-371).
+ * bwd: dx = LNbwd(expand(dy)/P) + (dres ? gather(dres, res_stride) : 0);  dgamma/dbeta accumulate (atomic) into fp32.
+ * ------------------------------------------------------------------------------------------------------------------ */
+int avec_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int B,
+                       int T, int C, int P, float eps, int dtype, avec_stream_t stream);
+int avec_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                       const void* dres, int res_stride, void* dx, float* dgamma, float* dbeta, int B, int T, int C,
+                       int P, int dtype, avec_stream_t stream);
+
+/* y[b,t] = x[b,t] + o[b, t / P]      (nearest upsample + slice + residual add, nnet/attentions.py:377-380, blocks.py:295) */
+int avec_upsample_add(const void* x, const void* o, void* y, int B, int T, int Tp, int C, int P, int dtype,
+                      avec_stream_t stream);
+/* do[b,t'] = sum_{p<P, t'P+p<T} dy[b, t'P+p]   (its backward) */
+int avec_pool_sum(const void* dy, void* dout, int B, int T, int Tp, int C, int P, int dtype, avec_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Relative-position multi-head self-attention core (nnet/attentions.py:280-323 incl. rel_to_abs 258-276):
+ *   S[i,j] = (q_i . k_j + q_i . e_{T-1+j-i}) / sqrt(d);  S += -1e9 where masked;  P = softmax_j(S);  o_i = sum_j P k v_j
+ * qkv is [B*T, 3*D] (q | k | v, each D = H*d wide), e is [2T-1, D] (pos_layer(R), computed once, not B times),
+ * klen[b] = number of unmasked keys of item b, qlen = number of query rows that are not fully masked (rows >= qlen see
+ * every key masked, as happens for the zero-padded last patch, nnet/attentions.py:140-171,355-363).
+ * probs [B,H,T,T] fp32 is saved for the backward.  bwd: dqkv [B*T,3D]; de [2T-1, D] fp32, accumulated atomically;
+ * ds_ws is a caller-provided [B,H,T,T] fp32 scratch (dS).
+ * ------------------------------------------------------------------------------------------------------------------ */
+int avec_relpos_attn_fwd(const void* qkv, const void* e, const int* klen, int qlen, void* o, float* probs, int B, int T,
+                         int H, int d, int dtype, avec_stream_t stream);
+int avec_relpos_attn_bwd(const void* d_o, const void* qkv, const void* e, const float* probs, float* ds_ws, void* dqkv,
+                         float* de, int B, int T, int H, int d, int dtype, avec_stream_t stream);
+
+/* row softmax / its backward (InterCTCResModule, nnet/modules.py:397-398).  dadd (optional, fp32) is added to dx. */
+int avec_softmax_fwd(const void* x, int x_dtype, void* y, int y_dtype, long long rows, int C, avec_stream_t stream);
+int avec_softmax_bwd(const void* dy, const void* y, int dtype, const float* dadd, void* dx, int dx_dtype, long long rows,
+                     int C, avec_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * ConvolutionModule middle section (nnet/modules.py:374-379): GLU -> depthwise Conv1d(k, stride s, "same") [-> BN stats]
+ *   pre [B,T,2C] (value | gate) -> u [B,To,C];  stats[0:C] += sum u, stats[C:2C] += sum u^2   (stats may be NULL)
+ * bwd: given du [B,To,C]: dpre [B,T,2C], dw [C,k] and db [C] (fp32, atomic accumulate).
+ * ------------------------------------------------------------------------------------------------------------------ */
+int avec_glu_dwconv_fwd(const void* pre, const float* w, const float* bias, void* u, float* stats, int B, int T, int To,
+                        int C, int ksize, int stride, int pad, int dtype, avec_stream_t stream);
+int avec_glu_dwconv_bwd(const void* du, const void* pre, const float* w, void* dpre, float* dw, float* db, int B, int T,
+                        int To, int C, int ksize, int stride, int pad, int dtype, avec_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * BatchNorm over channels-last rows (BatchNorm1d/2d/3d of nnet/normalizations.py:42-170; eps 1e-5, momentum 0.1).
+ * finalize: from stats (sum, sumsq over `count` rows) -> scale/shift (gamma*rstd, beta-mean*gamma*rstd), saved mean /
+ *   rstd, and the running-stat update (unbiased variance) when running_mean != NULL.  In eval mode call
+ *   avec_bn_eval_affine instead.
+ * apply: y = act(scale*u + shift (+ res))                act: 0 none, 1 ReLU, 2 Swish
+ * bwd_reduce: sums[0:C] += sum dz, sums[C:2C] += sum dz*xhat,  dz = dy * act'(.)
+ * bwd_apply: du = gamma*rstd*(dz - sums0/count - xhat*sums1/count);  dres = dz (optional)
+ * ------------------------------------------------------------------------------------------------------------------ */
+enum avec_act { AVEC_ACT_NONE = 0, AVEC_ACT_RELU = 1, AVEC_ACT_SWISH = 2 };
+int avec_bn_finalize(const float* stats, const float* gamma, const float* beta, float* scale, float* shift, float* mean,
+                     float* rstd, float* running_mean, float* running_var, long long count, int C, float eps,
+                     float momentum, avec_stream_t stream);
+int avec_bn_eval_affine(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                        float* scale, float* shift, int C, float eps, avec_stream_t stream);
+int avec_bn_stats(const void* u, int dtype, long long rows, int C, float* stats, avec_stream_t stream);
+int avec_bn_apply(const void* u, const float* scale, const float* shift, const void* res, void* y, long long rows, int C,
+                  int act, int dtype, avec_stream_t stream);
+int avec_bn_bwd_reduce(const void* dy, const void* u, const float* scale, const float* shift, const void* res,
+                       const float* mean, const float* rstd, float* sums, long long rows, int C, int act, int dtype,
+                       avec_stream_t stream);
+int avec_bn_bwd_apply(const void* dy, const void* u, const float* scale, const float* shift, const void* res,
+                      const float* mean, const float* rstd, const float* gamma, const float* sums, void* du, void* dres,
+                      long long rows, int C, int act, int dtype, avec_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Audio front-end: torchaudio Spectrogram(512, 400, 160, hann, center, reflect, power 2) -> MelScale(80, htk) ->
+ * log(x + 1e-9)  (nnet/preprocessing.py:57-85).  wave [B, L] fp32 -> out fp32; layout 0: [B, F, 80] (frames-major,
+ * what the fused stem consumes), layout 1: [B, 80, F] (the reference module's output).  fb is the [257, 80] filterbank.
+ * ------------------------------------------------------------------------------------------------------------------ */
+int avec_stft_mel_log(const float* wave, const float* fb, float* out, int B, int L, int F, int layout,
+                      avec_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Visual front-end helpers (nnet/networks.py:459-472): BN3d + ReLU + MaxPool3d((1,3,3), s (1,2,2), zero "same" pad)
+ * fused: u [N,Hi,Wi,C] -> y [N,Ho,Wo,C], argmax index (0..8, uint8) saved for the backward.
+ * bwd: dz [N,Hi,Wi,C] = relu'(.) * scatter(dy)  (gather form, deterministic).
+ * ------------------------------------------------------------------------------------------------------------------ */
+int avec_bn_relu_maxpool_fwd(const void* u, const float* scale, const float* shift, void* y, uint8_t* idx, int N, int Hi,
+                             int Wi, int C, int Ho, int Wo, int dtype, avec_stream_t stream);
+int avec_bn_relu_maxpool_bwd(const void* dy, const uint8_t* idx, void* dz, int N, int Hi, int Wi, int C, int Ho, int Wo,
+                             int dtype, avec_stream_t stream);
+/* GlobalAvgPool2d (nnet/networks.py:129-132): x [N, HW, C] -> y [N, C]; bwd broadcasts dy / HW */
+int avec_avgpool_fwd(const void* x, void* y, int N, int HW, int C, int dtype, avec_stream_t stream);
+int avec_avgpool_bwd(const void* dy, void* dx, int N, int HW, int C, int dtype, avec_stream_t stream);
+
+/* dtype conversion / strided copy helper: dst[r][c] = (T)src[r][c] */
+int avec_convert(const void* src, int src_dtype, long long lds, void* dst, int dst_dtype, long long ldd, long long rows,
+                 int C, avec_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AVEC_B200_H */
