@@ -1,0 +1,106 @@
+"""GPU parity of avec_gemm: SIMT fp32 against torch fp32, tcgen05 bf16 against fp32 math on the same bf16-rounded
+operands (so the only difference is accumulation order: tolerance 2e-3 relative to the output scale)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from avec_b200 import ops, _lib as L
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _close(got, want, tol):
+    scale = want.float().abs().max().item() + 1e-6
+    err = (got.float() - want.float()).abs().max().item()
+    assert err <= tol * scale, f"max err {err:.3e} vs scale {scale:.3e} (tol {tol})"
+
+
+def _rand(*shape, dtype=torch.float32, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return torch.randn(*shape, generator=g).to(DEV).to(dtype)
+
+
+SHAPES = [(300, 180, 720), (257, 720, 180), (128, 256, 1024), (1000, 360, 1440), (70, 540, 180), (513, 256, 7200), (64, 256, 512)]
+
+
+@pytest.mark.parametrize("impl,dtype,tol", [("simt", torch.float32, 1e-5), ("simt", torch.bfloat16, 1e-2), ("tcgen05", torch.bfloat16, 1e-2)])
+@pytest.mark.parametrize("M,K,N", SHAPES)
+def test_linear_fwd_dgrad_wgrad(impl, dtype, tol, M, K, N):
+    ops.set_gemm_impl(impl)
+    try:
+        x, w, b = _rand(M, K, dtype=dtype, seed=1), _rand(N, K, dtype=dtype, seed=2) / K ** 0.5, _rand(N, seed=3)
+        dy = _rand(M, N, dtype=dtype, seed=4)
+        xf, wf, dyf = x.float(), w.float(), dy.float()
+        y = ops.linear_fwd(x, w, b)
+        _close(y, xf @ wf.t() + b, tol)
+        h, pre = ops.linear_fwd(x, w, b, L.EPI_SWISH, want_pre=True)
+        _close(pre, xf @ wf.t() + b, tol)
+        _close(h, F.silu(xf @ wf.t() + b), tol)
+        aux = _rand(M, N, dtype=dtype, seed=5)
+        r = ops.linear_fwd(x, w, b, L.EPI_RESIDUAL, alpha=0.5, aux=aux)
+        _close(r, aux.float() + 0.5 * (xf @ wf.t() + b), tol)
+        dx = ops.linear_dgrad(dy, w)
+        _close(dx, dyf @ wf, tol)
+        dw = ops.linear_wgrad(dy, x, alpha=0.5)
+        _close(dw, 0.5 * dyf.t() @ xf, tol if dtype == torch.bfloat16 else 1e-4)
+        pre2 = _rand(M, K, dtype=dtype, seed=6)
+        dpre = ops.linear_dgrad(dy, w, L.EPI_DSWISH, alpha=0.5, aux=pre2)
+        s = torch.sigmoid(pre2.float())
+        _close(dpre, 0.5 * (dyf @ wf) * (s * (1 + pre2.float() * (1 - s))), tol)
+        cs = ops.colsum(dy, 0.5)
+        _close(cs, 0.5 * dyf.sum(0), 1e-4 if dtype == torch.float32 else 1e-3)
+    finally:
+        ops.set_gemm_impl("auto")
+
+
+CONVS = [  # N, H, W, Cin, Cout, k, stride
+    (3, 8, 8, 64, 64, 3, 1), (2, 11, 11, 64, 128, 3, 2), (3, 6, 6, 128, 256, 3, 2), (5, 3, 3, 512, 512, 3, 1),
+    (2, 11, 11, 64, 128, 1, 2), (4, 22, 22, 64, 64, 3, 1),
+]
+
+
+@pytest.mark.parametrize("impl,dtype,tol", [("simt", torch.float32, 1e-5), ("tcgen05", torch.bfloat16, 1e-2)])
+@pytest.mark.parametrize("N,H,W,Ci,Co,k,s", CONVS)
+def test_conv2d_fwd_dgrad_wgrad(impl, dtype, tol, N, H, W, Ci, Co, k, s):
+    ops.set_gemm_impl(impl)
+    try:
+        x = _rand(N, H, W, Ci, dtype=dtype, seed=1)
+        w = (_rand(Co, Ci, k, k, seed=2) / (Ci * k * k) ** 0.5).to(dtype)
+        p = (k - 1) // 2
+        g = ops.make_geom(N, 1, H, W, Ci, Co, (1, k, k), (1, s, s), (0, p, p))
+        wp = w.permute(0, 2, 3, 1).reshape(Co, -1).contiguous()
+        wd = w.permute(1, 2, 3, 0).reshape(Ci, -1).contiguous()
+        xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+        wr = w.float().requires_grad_(True)
+        yr = F.conv2d(F.pad(xr, (p, k // 2, p, k // 2)), wr, None, stride=s)
+        stats = torch.zeros(2 * Co, device=DEV)
+        y = ops.conv_fwd(x, wp, g, colstats=stats)
+        yr_cl = yr.permute(0, 2, 3, 1).reshape(-1, Co)
+        _close(y, yr_cl, tol)
+        _close(stats[:Co], yr_cl.sum(0), 1e-2 if dtype == torch.bfloat16 else 1e-4)
+        _close(stats[Co:], (yr_cl ** 2).sum(0), 1e-2 if dtype == torch.bfloat16 else 1e-4)
+        dy = _rand(*y.shape, dtype=dtype, seed=3)
+        yr.backward(dy.float().view(N, g.Ho, g.Wo, Co).permute(0, 3, 1, 2))
+        dx = ops.conv_dgrad(dy, wd, g)
+        _close(dx, xr.grad.permute(0, 2, 3, 1).reshape(-1, Ci), tol)
+        dw = ops.conv_wgrad(dy, x, g)
+        _close(dw, wr.grad.permute(0, 2, 3, 1).reshape(Co, -1), tol if dtype == torch.bfloat16 else 1e-4)
+    finally:
+        ops.set_gemm_impl("auto")
+
+
+def test_conv3d_stem_simt_fp32():
+    ops.set_gemm_impl("simt")
+    try:
+        B, T, H, W, Co = 1, 4, 16, 16, 64
+        x = _rand(B, T, H, W, 1, seed=1)
+        w = _rand(Co, 1, 5, 7, 7, seed=2) / 245 ** 0.5
+        b = _rand(Co, seed=3)
+        g = ops.make_geom(B, T, H, W, 1, Co, (5, 7, 7), (1, 2, 2), (2, 3, 3))
+        y = ops.conv_fwd(x, w.reshape(Co, -1).contiguous(), g, bias=b)
+        xr = x.view(B, 1, T, H, W)
+        yr = F.conv3d(F.pad(xr, (3, 3, 3, 3, 2, 2)), w, b, stride=(1, 2, 2))
+        _close(y, yr.permute(0, 2, 3, 4, 1).reshape(-1, Co), 1e-5)
+    finally:
+        ops.set_gemm_impl("auto")

@@ -1,0 +1,172 @@
+"""GPU parity of the non-GEMM kernels against plain torch fp32 on the same inputs (oracle/restate.py for the composite
+ones).  Tolerances: fp32 path rtol 1e-3 / atol 1e-4 (BASELINE north_star), typically met with 10x margin."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import seeded
+from avec_b200 import ops, _lib as L
+from common import check_close
+from conftest import load_golden
+from oracle import restate
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+RT, AT = 1e-3, 1e-4
+
+
+def _r(name, shape, scale=1.0):
+    return seeded.randn(name, shape, 5, scale).to(DEV)
+
+
+@pytest.mark.parametrize("B,T,C,P", [(3, 20, 180, 3), (2, 21, 180, 3), (2, 17, 256, 1), (4, 9, 360, 1), (2, 201, 180, 3)])
+def test_layernorm_pool_fwd_bwd(B, T, C, P):
+    x = _r("x", (B, T, C)).requires_grad_(True)
+    w, b = (1 + 0.1 * _r("w", (C,))).requires_grad_(True), (0.1 * _r("b", (C,))).requires_grad_(True)
+    h = F.layer_norm(x, (C,), w, b, 1e-6)
+    pad = (P - T % P) % P
+    hp = F.pad(h, (0, 0, 0, pad)).view(B, (T + pad) // P, P, C).mean(2)
+    y, mean, rstd = ops.layernorm_fwd(x.detach(), w.detach(), b.detach(), P=P)
+    check_close("y", y, hp, RT, AT)
+    dy = _r("dy", tuple(hp.shape))
+    dres = _r("dres", (B, T, C))
+    (hp * dy).sum().backward()
+    dx, dg, db = ops.layernorm_bwd(dy, x.detach(), w.detach(), mean, rstd, P=P, dres=dres, res_stride=1)
+    check_close("dx", dx, x.grad + dres, RT, AT)
+    check_close("dgamma", dg, w.grad, RT, 1e-3)
+    check_close("dbeta", db, b.grad, RT, 1e-3)
+    # strided residual gradient (downsampling block): dres rows land on even frames only
+    Tr = (T - 1) // 2 + 1
+    dres2 = _r("dres2", (B, Tr, C))
+    dx2, _, _ = ops.layernorm_bwd(dy, x.detach(), w.detach(), mean, rstd, P=P, dres=dres2, res_stride=2)
+    exp = x.grad.clone()
+    exp[:, ::2] += dres2
+    check_close("dx strided res", dx2, exp, RT, AT)
+
+
+def test_upsample_add_pool_sum():
+    B, T, C, P = 2, 20, 180, 3
+    x, o = _r("x", (B, T, C)), _r("o", (B, 7, C))
+    y = ops.upsample_add(x, o, P)
+    check_close("upsample_add", y, x + o.repeat_interleave(P, 1)[:, :T], 1e-6, 1e-6)
+    dy = _r("dy", (B, T, C))
+    d = ops.pool_sum(dy, P)
+    check_close("pool_sum", d, F.pad(dy, (0, 0, 0, 1)).view(B, 7, 3, C).sum(2), 1e-5, 1e-5)
+
+
+def test_softmax_fwd_bwd():
+    x = _r("x", (37, 256), 3.0).requires_grad_(True)
+    y = ops.softmax_fwd(x.detach(), torch.float32)
+    yr = x.softmax(-1)
+    check_close("softmax", y, yr, RT, 1e-6)
+    dy, dadd = _r("dy", (37, 256)), _r("dadd", (37, 256))
+    (yr * dy).sum().backward()
+    dx = ops.softmax_bwd(dy, y, dadd)
+    check_close("softmax bwd", dx, x.grad + dadd, RT, 1e-5)
+
+
+@pytest.mark.parametrize("rows,C,act", [(1000, 180, L.ACT_SWISH), (777, 64, L.ACT_RELU), (300, 256, L.ACT_NONE)])
+def test_batchnorm_train_fwd_bwd(rows, C, act):
+    u = (_r("u", (rows, C)) * 1.5 + 0.3).requires_grad_(True)
+    res = _r("res", (rows, C)).requires_grad_(True) if act == L.ACT_RELU else None
+    g, b = (1 + 0.1 * _r("g", (C,))).requires_grad_(True), (0.1 * _r("b", (C,))).requires_grad_(True)
+    rm, rv = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+    rm0, rv0 = rm.clone(), rv.clone()
+    z = F.batch_norm(u, rm0, rv0, g, b, True, 0.1, 1e-5)
+    if res is not None:
+        z = z + res
+    yr = {L.ACT_SWISH: F.silu, L.ACT_RELU: F.relu, L.ACT_NONE: lambda t: t}[act](z)
+    stats = ops.bn_stats(u.detach())
+    buf = ops.bn_finalize(stats, g.detach(), b.detach(), rows, rm, rv)
+    y = ops.bn_apply(u.detach(), buf[0], buf[1], act, res=res.detach() if res is not None else None)
+    check_close("bn y", y, yr, RT, AT)
+    check_close("running_mean", rm, rm0, RT, 1e-5)
+    check_close("running_var", rv, rv0, RT, 1e-5)
+    dy = _r("dy", (rows, C))
+    (yr * dy).sum().backward()
+    du, dres, dg, db = ops.bn_bwd(dy, u.detach(), buf, g.detach(), act, res=res.detach() if res is not None else None, want_dres=res is not None)
+    check_close("du", du, u.grad, RT, AT)
+    check_close("dgamma", dg, g.grad, RT, 1e-3)
+    check_close("dbeta", db, b.grad, RT, 1e-3)
+    if res is not None:
+        check_close("dres", dres, res.grad, RT, AT)
+
+
+@pytest.mark.parametrize("B,T,C,stride", [(2, 20, 180, 1), (3, 21, 256, 2), (2, 201, 180, 1), (2, 101, 360, 2), (1, 5, 64, 1)])
+def test_glu_dwconv_fwd_bwd(B, T, C, stride):
+    pre = _r("pre", (B, T, 2 * C)).requires_grad_(True)
+    w = (_r("w", (C, 1, 15)) / 4).requires_grad_(True)
+    b = (0.1 * _r("b", (C,))).requires_grad_(True)
+    gl = F.glu(pre, dim=-1).transpose(1, 2)
+    ur = F.conv1d(F.pad(gl, (7, 7)), w, b, stride=stride, groups=C).transpose(1, 2)
+    u, stats = ops.glu_dwconv_fwd(pre.detach(), w.detach().view(C, 15), b.detach(), stride)
+    check_close("u", u, ur, RT, AT)
+    check_close("sum", stats[:C], ur.sum((0, 1)), RT, 1e-3)
+    check_close("sumsq", stats[C:], (ur ** 2).sum((0, 1)), RT, 1e-3)
+    du = _r("du", tuple(ur.shape))
+    (ur * du).sum().backward()
+    dpre, dw, db = ops.glu_dwconv_bwd(du, pre.detach(), w.detach().view(C, 15), stride)
+    check_close("dpre", dpre, pre.grad, RT, AT)
+    check_close("dw", dw, w.grad.view(C, 15), RT, 1e-3)
+    check_close("db", db, b.grad, RT, 1e-3)
+
+
+@pytest.mark.parametrize("B,T,H,d,ragged,qlen_short", [(3, 7, 4, 45, True, True), (2, 17, 4, 64, True, False), (2, 51, 4, 90, False, False),
+                                                      (2, 101, 4, 64, True, False), (1, 67, 4, 45, True, True)])
+def test_relpos_attention_core(B, T, H, d, ragged, qlen_short):
+    D = H * d
+    qkv = _r("qkv", (B * T, 3 * D), 0.5).requires_grad_(True)
+    e = _r("e", (2 * T - 1, D), 0.5).requires_grad_(True)
+    klen = torch.tensor([T] + [max(1, T - 2 - i) for i in range(B - 1)], device=DEV, dtype=torch.int32) if ragged else None
+    qlen = T - 1 if qlen_short else T
+    q, k, v = [t.view(B, T, H, d).transpose(1, 2) for t in qkv.view(B, T, 3, D).unbind(2)]
+    eh = e.view(2 * T - 1, H, d).transpose(0, 1)
+    idx = (T - 1) + torch.arange(T, device=DEV)[None, :] - torch.arange(T, device=DEV)[:, None]
+    s = (q @ k.transpose(2, 3) + (q @ eh.transpose(1, 2)).gather(3, idx.expand(B, H, T, T))) / d ** 0.5
+    keep = torch.ones(B, 1, T, T, device=DEV)
+    if klen is not None:
+        keep = keep * (torch.arange(T, device=DEV)[None, None, None, :] < klen[:, None, None, None]).float()
+    keep = keep * (torch.arange(T, device=DEV)[None, None, :, None] < qlen).float()
+    s = s + (1 - keep) * -1e9
+    pr = s.softmax(-1)
+    o_ref = (pr @ v).transpose(1, 2).reshape(B * T, D)
+    o, probs = ops.relpos_attn_fwd(qkv.detach(), e.detach(), klen, qlen, B, T, H, d)
+    check_close("o", o, o_ref, RT, AT)
+    check_close("probs", probs, pr, RT, 1e-6)
+    do = _r("do", (B * T, D))
+    (o_ref * do).sum().backward()
+    dqkv, de = ops.relpos_attn_bwd(do, qkv.detach(), e.detach(), probs, B, T, H, d)
+    check_close("dqkv", dqkv, qkv.grad, RT, AT)
+    check_close("de", de, e.grad, RT, 1e-3)
+
+
+def test_stft_mel_log_matches_reference_fixture_and_restatement():
+    fix = load_golden("audio_logmel.pt")
+    wave = seeded.randn("wave", (3, 4000), 1, 0.1)
+    wave[1, 3000:] = 0.0
+    wave[2, 1700:] = 0.0
+    fb = restate.mel_filterbank().to(DEV)
+    mel = ops.stft_mel_log(wave.to(DEV), fb, layout=1)
+    check_close("logmel vs reference", mel, fix["mel"], RT, 1e-3)
+    mel0 = ops.stft_mel_log(wave.to(DEV), fb, layout=0)
+    check_close("layout", mel0.transpose(1, 2), mel, 0, 0)
+    big = seeded.randn("wave2", (2, 64000), 2, 0.1)
+    check_close("logmel 4s", ops.stft_mel_log(big.to(DEV), fb, layout=1), restate.logmel(big), RT, 1e-3)
+
+
+def test_bn_relu_maxpool_and_avgpool():
+    N, H, W, C = 3, 12, 12, 64
+    u = _r("u", (N, H, W, C)).requires_grad_(True)
+    sc, sh = 1 + 0.1 * _r("sc", (C,)), 0.1 * _r("sh", (C,))
+    z = F.relu(u * sc + sh).permute(0, 3, 1, 2)
+    yr = F.max_pool2d(F.pad(z, (1, 1, 1, 1)), 3, 2).permute(0, 2, 3, 1)
+    y, idx = ops.bn_relu_maxpool_fwd(u.detach().view(-1, C), sc, sh, N, H, W, C)
+    check_close("maxpool", y, yr, 1e-5, 1e-6)
+    dy = _r("dy", tuple(yr.shape))
+    (yr * dy).sum().backward()
+    dz = ops.bn_relu_maxpool_bwd(dy, idx, N, H, W, C)           # gradient w.r.t. z = scale*u+shift
+    check_close("maxpool bwd", dz.view(N, H, W, C) * sc, u.grad, 1e-4, 1e-5)
+    x = _r("x", (5, 3, 3, 512))
+    check_close("avgpool", ops.avgpool_fwd(x, 5, 9, 512), x.mean((1, 2)), 1e-5, 1e-6)
+    check_close("avgpool bwd", ops.avgpool_bwd(x[:, 0, 0].contiguous(), 5, 9, 512).view(5, 3, 3, 512),
+                (x[:, 0, 0] / 9)[:, None, None, :].expand(5, 3, 3, 512), 1e-5, 1e-6)

@@ -1,0 +1,60 @@
+"""CPU tests of the host-side mirror: state_dict keys / shapes / parameter counts equal the reference's (known answers
+from demo.ipynb cell 12), length bookkeeping, mel filterbank and positional table restatements."""
+import json
+import os
+
+import pytest
+import torch
+
+from avec_b200 import nnet
+from avec_b200.nnet.modules import rel_pos_table
+from conftest import GOLDEN
+from oracle import restate
+
+
+@pytest.mark.parametrize("name", ["AudioEfficientConformerInterCTC", "VisualEfficientConformerInterCTC", "AudioVisualEfficientConformerInterCTC"])
+def test_state_dict_contract(name):
+    ref = json.load(open(os.path.join(GOLDEN, "state_dict_keys.json")))[name]
+    m = getattr(nnet, name)()
+    sd = {k: list(v.shape) for k, v in m.state_dict().items()}
+    assert list(sd.keys()) == list(ref["keys"].keys())
+    assert sd == ref["keys"]
+    assert m.num_params() == ref["params"]
+
+
+def test_known_parameter_counts():
+    assert nnet.VisualEfficientConformerInterCTC().num_params() == 40903112
+    assert nnet.AudioVisualEfficientConformerInterCTC().num_params() == 61738836
+    assert nnet.AudioEfficientConformerInterCTC(interctc_blocks=[]).num_params() == 31562460
+
+
+def test_mel_filterbank_matches_torchaudio():
+    torchaudio = pytest.importorskip("torchaudio")
+    fb = torchaudio.functional.melscale_fbanks(257, 0.0, 8000.0, 80, 16000, None, "htk")
+    assert torch.equal(fb, nnet.mel_filterbank())
+    assert torch.equal(fb, restate.mel_filterbank())
+
+
+def test_rel_pos_table():
+    T, D = 7, 12
+    pe = rel_pos_table(T, D, "cpu", torch.float32)
+    assert torch.equal(pe, restate.rel_pos_table(T, D))
+    # row r is the sinusoid of relative position T-1-r
+    r, k = 2, 3
+    pos = T - 1 - r
+    assert abs(pe[r, 2 * k].item() - torch.sin(torch.tensor(pos / 10000 ** (2 * k / D))).item()) < 1e-6
+
+
+def test_length_bookkeeping():
+    L0 = torch.tensor([64000, 63999, 640, 1])
+    f = torch.div(L0, 160, rounding_mode="floor") + 1
+    assert f.tolist() == [401, 400, 5, 1]
+    s = torch.div(f - 1, 2, rounding_mode="floor") + 1
+    assert s.tolist() == [201, 200, 3, 1]
+
+
+def test_dropout_guard():
+    m = nnet.AudioEfficientConformerInterCTC()
+    m.train()
+    with pytest.raises(RuntimeError, match="dropout"):
+        m((torch.zeros(1, 3200), torch.tensor([3200])))
