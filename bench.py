@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""bench.py - utterances/s of the Audio-Visual Efficient Conformer (AVEC) encoder forward+backward on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path (one rank per GPU under torchrun)
+    python bench.py --impl reference --gpus N ...              # CPU baseline: the pinned restatement of the reference
+
+Workload (BASELINE.json metric / configs[3]): AV EffConfInterCTC, per-GPU batch 64, 4 s of 16 kHz audio (64000
+samples) + 101 frames of 88x88 video (Tv = Ta // 640 + 1), synthetic data, random-init weights,
+train-mode forward (batch-stat BatchNorm, dropout 0 = the parity configuration) + CTC losses on the 6 heads + backward.
+One step = one batch.  `value` times steps with inputs resident in HBM; `e2e` times the public API call
+model((video, vlen, audio, alen)) fed from pinned host memory, H2D copies and the D2H read of the loss inside the timed
+region.  Under torchrun (N > 1) gradients are all-reduced over NCCL every step (pure data parallel, local BN).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+AV_GFLOP_PER_UTT = 216.38   # dense-contraction FLOPs fwd+bwd per utterance (torch flop counter on the reference)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="avec_b200", choices=["avec_b200", "reference"])
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--model", default="AV", choices=["AV", "AO", "VO"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-baseline", type=int, default=1, help="time the CPU restatement on a bounded sample (rank 0, N=1)")
+    ap.add_argument("--cpu-sample", type=int, default=4, help="utterances in the CPU baseline sample")
+    ap.add_argument("--loss", default="ctc", choices=["ctc", "sum"])
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------------- helpers
+def synth_inputs(model, B, device, seed=1234, pinned=False):
+    g = torch.Generator().manual_seed(seed)
+    Ls, Tv = 64000, (101 if model == "AV" else 100)
+    kw = dict(pin_memory=pinned)
+    audio = (0.1 * torch.randn(B, Ls, generator=g)).contiguous()
+    video = torch.randn(B, Tv, 88, 88, 1, generator=g).clamp_(-1, 1).contiguous()
+    alen = torch.full((B,), Ls, dtype=torch.long)
+    vlen = torch.full((B,), Tv, dtype=torch.long)
+    labels = torch.randint(1, 256, (B, 20), generator=g)
+    llen = torch.full((B,), 20, dtype=torch.long)
+    if pinned:
+        audio, video = audio.pin_memory(), video.pin_memory()
+    host = dict(audio=audio, video=video, alen=alen, vlen=vlen, labels=labels, llen=llen)
+    if device is None:
+        return host
+    return {k: v.to(device) for k, v in host.items()}
+
+
+def model_inputs(model, d):
+    if model == "AV":
+        return (d["video"], d["vlen"], d["audio"], d["alen"])
+    if model == "AO":
+        return (d["audio"], d["alen"])
+    return (d["video"], d["vlen"])
+
+
+class ClockSampler:
+    """samples nvidia-smi SM clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)"""
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("bf16_tflops_sustained", 1415.1), d.get("hbm_gbs", 6449.1), "measured"
+    return 1400.0, 6650.0, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------- CPU baseline (port)
+def cpu_baseline(args, steps=1, sample=None):
+    """reference arm: the pinned plain-torch restatement of the reference (oracle/restate.py, checked against fixtures
+    generated by the unmodified reference) forward+backward on the host cores, on a bounded sample of the workload."""
+    from oracle import restate
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import seeded
+    from avec_b200 import nnet
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B = sample or args.cpu_sample
+    m = {"AV": nnet.AudioVisualEfficientConformerInterCTC, "AO": nnet.AudioEfficientConformerInterCTC, "VO": nnet.VisualEfficientConformerInterCTC}[args.model]()
+    sd = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k and "Spectrogram" not in k and "MelScale" not in k)
+          for k, v in seeded.seeded_state_dict(m, 7).items()}
+    d = synth_inputs(args.model, B, None)
+    fn = {"AV": lambda: restate.av_model(sd, d["video"], d["vlen"], d["audio"], d["alen"]),
+          "AO": lambda: restate.ao_model(sd, d["audio"], d["alen"]),
+          "VO": lambda: restate.vo_model(sd, d["video"], d["vlen"])}[args.model]
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        out = fn()
+        loss = sum(v[0].float().mean() for v in out.values())
+        loss.backward()
+        times.append(time.perf_counter() - t0)
+        for v in sd.values():
+            v.grad = None
+    best = min(times)
+    return {"value": B / best, "unit": "utterances/s", "cores": cores, "kind": "port",
+            "sample": f"{B} utterances x {steps} fwd+bwd passes of the {args.model} encoder (fp32, torch CPU restatement oracle/restate.py), best pass",
+            "seconds": best}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = cpu_baseline(args, steps=max(1, min(args.steps, 2)), sample=args.cpu_sample)
+    line = {"impl": "reference", "metric": "utterances/sec fwd+bwd (4s audio+video)", "value": cb["value"], "unit": "utterances/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * cb["seconds"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.model} EffConfInterCTC fwd+bwd, bounded sample of {args.cpu_sample} utterances (4 s audio + video) on host cores"},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": "utterances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------------ GPU arm
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch.distributed as dist
+    import avec_b200
+    from avec_b200 import nnet, ops
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    avec_b200.set_compute_dtype(dtype)
+
+    torch.manual_seed(1234 + rank)
+    cls = {"AV": nnet.AudioVisualEfficientConformerInterCTC, "AO": nnet.AudioEfficientConformerInterCTC, "VO": nnet.VisualEfficientConformerInterCTC}[args.model]
+    model = nnet.zero_dropout(cls()).to(dev).train()
+    if world > 1:  # identical replicas
+        for p in model.parameters():
+            dist.broadcast(p.data, 0)
+    ctc = nnet.CTCLoss(zero_infinity=True, assert_shorter=False)
+    B = args.batch
+    host = synth_inputs(args.model, B, None, seed=1234 + rank, pinned=True)
+    resident = {k: v.to(dev) for k, v in host.items()}
+    params = [p for p in model.parameters()]
+
+    def step(d):
+        outputs = model(model_inputs(args.model, d))
+        if args.loss == "ctc":
+            targets = (d["labels"], d["llen"])
+            loss = sum(ctc(targets, v) for v in outputs.values()) / len(outputs)
+        else:
+            loss = sum(v[0].float().mean() for v in outputs.values())
+        loss.backward()
+        if world > 1:
+            flat = torch.cat([p.grad.reshape(-1) for p in params if p.grad is not None])
+            dist.all_reduce(flat)
+            flat /= world
+        for p in params:
+            p.grad = None
+        return loss
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        sync()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- warm-up, then the device-resident timing
+    for _ in range(max(3, args.warmup)):
+        step(resident)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ops.reset_launch_count()
+    ms_total = timed(lambda: step(resident), args.steps)
+    launches = ops.launch_count()
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- end to end: pinned host -> device copies + loss read back inside the timed region
+    def e2e_step():
+        d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        return float(step(d).item())
+    e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+
+    # ---- roofline of the dominant kernel (tcgen05 GEMM / implicit-GEMM conv): CUDA events around every avec_gemm launch
+    gemm_ms, gemm_flops, gemm_n = profile_gemm(lambda: step(resident), ops)
+    peak_tf, peak_hbm, which = measured_peaks()
+
+    if rank == 0:
+        ms_step = ms_total / args.steps
+        value = world * B / (ms_step / 1000.0)
+        ach = gemm_flops / (gemm_ms / 1000.0) / 1e12 if gemm_ms > 0 else 0.0
+        line = {
+            "metric": "utterances/sec fwd+bwd (4s audio+video)", "value": value, "unit": "utterances/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": f"{args.model} EffConfInterCTC fwd+bwd (train mode, dropout 0, 6 CTC heads), per-GPU batch {B}, "
+                                   f"64000 audio samples + {101 if args.model == 'AV' else 100}x88x88 video",
+                       "global_batch": world * B, "parallelism": f"dp{world}", "bn": "local batch statistics", "loss": args.loss,
+                       "l2": "inputs+activations per step (>1 GB) exceed the 126 MB L2; no flush needed",
+                       "achieved_tflops_whole_step": value / world * AV_GFLOP_PER_UTT / 1000.0 if args.model == "AV" else None,
+                       "frac_of_tensor_peak_whole_step": (value / world * AV_GFLOP_PER_UTT / 1000.0) / peak_tf if args.model == "AV" else None},
+            "e2e": {"value": world * B / (ms_e2e / args.steps / 1000.0), "unit": "utterances/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+                         "kernel": "gemm_tc_kernel (tcgen05 GEMM / implicit-GEMM conv), all launches of one step",
+                         "launches_per_step": gemm_n, "ms_per_step_in_kernel": gemm_ms, "peak_source": which + " bf16_tflops_sustained"},
+        }
+        if world == 1 and args.cpu_baseline:
+            cb = cpu_baseline(args)
+            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def profile_gemm(step_fn, ops):
+    """one extra step with a CUDA-event pair around every avec_gemm launch: sum of durations and of 2*M*N*K."""
+    recs = []
+    orig = ops._gemm
+
+    def hooked(a):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        orig(a)
+        e1.record()
+        recs.append((e0, e1, 2.0 * a.M * a.N * a.K))
+    ops._gemm = hooked
+    try:
+        step_fn()
+        torch.cuda.synchronize()
+    finally:
+        ops._gemm = orig
+    ms = sum(e0.elapsed_time(e1) for e0, e1, _ in recs)
+    return ms, sum(f for _, _, f in recs), len(recs)
+
+
+if __name__ == "__main__":
+    main()

@@ -27,6 +27,11 @@ def save(name, obj):
     print(f"{name}: {os.path.getsize(path) / 1024:.0f} KiB")
 
 
+def rel(a, b):
+    a, b = a.detach().float(), b.detach().float()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
 def grads_of(module, max_n=4096):
     return {k: seeded.subsample(p.grad, max_n) for k, p in module.named_parameters() if p.grad is not None}
 
@@ -61,6 +66,14 @@ def block_case(tag, D, De, stride, att, T, B, seed):
     blk.eval()
     with torch.no_grad():
         fix["y_eval"] = blk(x.detach(), mask=mask)
+    # the reference's own bf16 envelope: same block under CPU autocast(bfloat16) vs its fp32 result
+    blk.load_state_dict(seeded.seeded_state_dict(blk, seed))
+    blk.train()
+    xb = x.detach().clone().requires_grad_(True)
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        yb = blk(xb, mask=mask)
+    (yb.float() * gy).sum().backward()
+    fix["env"] = {"y": rel(yb, y), "dx": rel(xb.grad, x.grad)}
     save(f"block_{tag}.pt", fix)
 
 
@@ -83,8 +96,14 @@ def resnet_block_case(tag, cin, cout, stride, hw, n, seed):
     y = blk(x)
     gy = seeded.randn(tag + ".gy", tuple(y.shape), seed)
     (y * gy).sum().backward()
-    save(f"resblock_{tag}.pt", {"cfg": dict(cin=cin, cout=cout, stride=stride, hw=hw, n=n, seed=seed), "y": y.detach(),
-                                "dx": x.grad.clone(), "grads": grads_of(blk)})
+    fix = {"cfg": dict(cin=cin, cout=cout, stride=stride, hw=hw, n=n, seed=seed), "y": y.detach(), "dx": x.grad.clone(), "grads": grads_of(blk)}
+    blk.load_state_dict(seeded.seeded_state_dict(blk, seed))
+    xb = x.detach().clone().requires_grad_(True)
+    with torch.autocast("cpu", dtype=torch.bfloat16):
+        yb = blk(xb)
+    (yb.float() * gy).sum().backward()
+    fix["env"] = {"y": rel(yb, y), "dx": rel(xb.grad, x.grad)}
+    save(f"resblock_{tag}.pt", fix)
 
 
 # --------------------------------------------------------------------------------------------------------- full models
@@ -136,6 +155,14 @@ def model_case(kind, seed=3):
     with torch.no_grad():
         out_eval = m(inputs)
     fix["logits_eval"] = {k: out_eval[k][0] for k in keys}
+    # the reference's own bf16 envelope (CPU autocast) at the logits and the loss
+    m.load_state_dict(seeded.seeded_state_dict(m, seed))
+    m.train()
+    with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+        ob = m(inputs)
+    lb = sum(float(ctc((labels, llen), [ob[k][0].float(), ob[k][1]])) for k in keys) / len(keys)
+    fix["env"] = {"logits": {k: rel(ob[k][0], outputs[k][0]) for k in keys}, "total": abs(lb - float(total.detach())) / abs(float(total.detach()))}
+    print(kind, "bf16 envelope", fix["env"])
     save(f"model_{kind}.pt", fix)
 
 

@@ -178,3 +178,86 @@ def audio_stem(mel, sd, training=True, prefix=""):
     B, C, Fq, T = h.shape
     h = h.reshape(B, C * Fq, T).transpose(1, 2)
     return F.linear(h, sd[p + "linear.weight"], sd[p + "linear.bias"])
+
+
+# ------------------------------------------------------------------------------------------------------ full encoders
+def conformer_stack(x, lengths, sd, p, dims, num_blocks, interctc_blocks, patch, loss_prefix, training=True, H=4):
+    """ConformerInterCTC.forward (networks.py:262-307).  dims/num_blocks per stage, patch = patch size per stage."""
+    outs = {}
+    klen = lengths
+    i, j = 0, 0
+    for stage, nb in enumerate(num_blocks):
+        for b in range(nb):
+            down = (b == nb - 1) and (stage < len(num_blocks) - 1)
+            stride = 2 if down else 1
+            x, _, _ = conformer_block(x, sd, klen, H, patch[stage], stride, training, prefix=f"{p}conformer_blocks.{i}.")
+            logits = None
+            if i + 1 in interctc_blocks:
+                x, logits = interctc(x, sd, f"{p}interctc_modules.{j}.")
+                j += 1
+            if stride > 1:
+                lengths = torch.div(lengths - 1, stride, rounding_mode="floor") + 1
+                klen = lengths
+            if logits is not None:
+                outs[f"{loss_prefix}_{i}"] = [logits, lengths]
+            i += 1
+    return x, lengths, outs
+
+
+def visual_encoder(video, vlen, sd, p, num_blocks, interctc_blocks, loss_prefix, training=True, head=True):
+    """VisualEfficientConformerEncoder.forward (networks.py:497-512); video (B,T,H,W,1)."""
+    B, T = video.shape[0], video.shape[1]
+    h = video_stem(video.permute(0, 4, 1, 2, 3), sd, training, p + "front_end.")
+    strides = [1, 1, 2, 1, 2, 1, 2, 1]
+    for k in range(8):
+        h = resnet_block(h, sd, strides[k], training, f"{p}front_end.3.blocks.{k}.")
+    h = F.linear(h.mean((2, 3)), sd[p + "front_end.3.head.1.weight"], sd[p + "front_end.3.head.1.bias"]).view(B, T, -1)
+    x, lengths, outs = conformer_stack(h, vlen, sd, p + "back_end.", [256, 360], num_blocks, interctc_blocks, [1, 1], loss_prefix, training)
+    if head:
+        x = F.linear(x, sd[p + "head.weight"], sd[p + "head.bias"])
+    return x, lengths, outs
+
+
+def audio_encoder(audio, alen, sd, p, num_blocks, interctc_blocks, loss_prefix, training=True, head=True, att_patch=3):
+    """AudioEfficientConformerEncoder.forward (networks.py:411-440), SpecAugment bypassed."""
+    mel = logmel(audio)
+    lengths = torch.div(alen, 160, rounding_mode="floor") + 1
+    x = audio_stem(mel, sd, training, p)
+    lengths = torch.div(lengths - 1, 2, rounding_mode="floor") + 1
+    x, lengths, outs = conformer_stack(x, lengths, sd, p + "back_end.", [180, 256, 360], num_blocks, interctc_blocks,
+                                       [att_patch, 1, 1], loss_prefix, training)
+    if head:
+        x = F.linear(x, sd[p + "head.weight"], sd[p + "head.bias"])
+    return x, lengths, outs
+
+
+def av_model(sd, video, vlen, audio, alen, training=True):
+    """AudioVisualEfficientConformerInterCTC.forward (models_zoo.py:156-161, networks.py:559-579), default InterCTC blocks."""
+    p = "encoder."
+    v, vl, vo = visual_encoder(video, vlen, sd, p + "video_encoder.", [6, 1], [3, 6], "v_ctc", training, head=False)
+    a, al, ao = audio_encoder(audio, alen, sd, p + "audio_encoder.", [5, 6, 1], [8, 11], "a_ctc", training, head=False)
+    x = torch.cat([a, v], dim=-1)
+    x = F.linear(x, sd[p + "fusion_module.layers.0.weight"], sd[p + "fusion_module.layers.0.bias"])
+    x = x * torch.sigmoid(x)
+    x = F.linear(x, sd[p + "fusion_module.layers.2.weight"], sd[p + "fusion_module.layers.2.bias"])
+    x, lengths, fo = conformer_stack(x, al, sd, p + "audio_visual_encoder.", [360], [5], [2], [1], "f_ctc", training)
+    x = F.linear(x, sd[p + "head.weight"], sd[p + "head.bias"])
+    outs = {"outputs": [x, lengths]}
+    outs.update(fo)
+    outs.update(vo)
+    outs.update(ao)
+    return outs
+
+
+def ao_model(sd, audio, alen, training=True, interctc_blocks=(3, 6, 10, 13)):
+    x, lengths, outs = audio_encoder(audio, alen, sd, "encoder.", [5, 6, 5], list(interctc_blocks), "ctc", training)
+    o = {"outputs": [x, lengths]}
+    o.update(outs)
+    return o
+
+
+def vo_model(sd, video, vlen, training=True, interctc_blocks=(3, 6, 9)):
+    x, lengths, outs = visual_encoder(video, vlen, sd, "encoder.", [6, 6], list(interctc_blocks), "ctc", training)
+    o = {"outputs": [x, lengths]}
+    o.update(outs)
+    return o
