@@ -27,7 +27,9 @@ enum OperandKind {
     OP_PLAIN_MN = 1,   // element (row, k) at base[k*ld + row]               -> MN-major tile
     OP_CONV_FWD = 2,   // A: row = output site, k = (tap, ci)                 -> K-major
     OP_CONV_DGRAD = 3, // A: row = input site, k = (tap, co), gather from dY  -> K-major
-    OP_CONV_WGRAD_X = 4 // B: row = (tap, ci), k = output site, gather from X  -> MN-major
+    OP_CONV_WGRAD_X = 4, // B: row = (tap, ci), k = output site, gather from X  -> MN-major
+    OP_CONV_TAPS = 5,    // A, C == 1 (stems): row = output site, k = tap; element-wise im2col gather -> K-major
+    OP_CONV_TAPS_MN = 6  // B, C == 1 (stem wgrad): row = tap, k = output site              -> MN-major
 };
 
 struct TcParams {
@@ -145,10 +147,64 @@ __device__ __forceinline__ uint4 load_chunk(const bf16* p, int nv, int align) {
 
 struct RowInfo { int n, t, h, w; };
 
+// 8 consecutive filter taps of a single-channel input window whose origin is (n, t0, h0, w0); tapofs = kt | kh<<8 | kw<<16
+__device__ __forceinline__ uint4 gather_taps8(const bf16* __restrict__ x, const ConvGeom& g, int n, int t0, int h0, int w0, int tap0,
+                                              int ntaps, const int* __restrict__ tapofs) {
+    const unsigned short* xs = reinterpret_cast<const unsigned short*>(x);
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int tap = tap0 + j;
+        if (tap < ntaps) {
+            const int o = tapofs[tap];
+            const int ti = t0 + (o & 255), hi = h0 + ((o >> 8) & 255), wi = w0 + (o >> 16);
+            if ((unsigned)ti < (unsigned)g.Ti && (unsigned)hi < (unsigned)g.Hi && (unsigned)wi < (unsigned)g.Wi)
+                w[j >> 1] |= (uint32_t)__ldg(xs + (((long long)n * g.Ti + ti) * g.Hi + hi) * g.Wi + wi) << ((j & 1) * 16);
+        }
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// ---- asynchronous global -> shared copies (LDGSTS): no register staging, several k-blocks in flight per thread
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// copy one 16-byte chunk (8 bf16, `nv` of them valid, the rest zero-filled) to shared memory
+__device__ __forceinline__ void copy_chunk(uint8_t* dst, const bf16* src, int nv, int align, const bf16* safe) {
+    const uint32_t d = smem_u32(dst);
+    int bytes = nv <= 0 ? 0 : (nv >= 8 ? 16 : nv * 2);
+    if (bytes == 0) src = safe;
+    if (align >= 16) {
+        cp_async16(d, src, bytes);
+    } else if (align >= 8) {
+        cp_async8(d, src, min(bytes, 8));
+        cp_async8(d + 8, bytes > 8 ? src + 4 : safe, max(bytes - 8, 0));
+    } else if (align >= 4) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int bq = min(max(bytes - 4 * q, 0), 4);
+            cp_async4(d + 4 * q, bq > 0 ? src + 2 * q : safe, bq);
+        }
+    } else {
+        *reinterpret_cast<uint4*>(dst) = load_chunk(src, nv, align);
+    }
+}
+
 // Fill `rows` smem rows (128 B each, 128B-swizzled, tile base 1024-aligned) of one operand tile for k-block kb.
 // `tile0` = first matrix row (K-major kinds) or first MN index (MN-major kinds) of this CTA's tile.
 __device__ __forceinline__ void fill_operand(uint8_t* tile, int rows, int kind, const bf16* __restrict__ base, long long ld, int align,
-                                             int R, int K, int tile0, int kb, const TcParams& p, const RowInfo* __restrict__ rinfo, int pt) {
+                                             int R, int K, int tile0, int kb, const TcParams& p, const RowInfo* __restrict__ rinfo,
+                                             const int* __restrict__ tapofs, int pt) {
     const int chunk = pt & 7;
     const int r_first = pt >> 3;  // 0..15
     // filter tap of this k-block (conv kinds)
@@ -157,68 +213,147 @@ __device__ __forceinline__ void fill_operand(uint8_t* tile, int rows, int kind, 
         int tap = kb / p.cpb; cb = kb % p.cpb;
         kw = tap % p.g.KW; tap /= p.g.KW; kh = tap % p.g.KH; kt = tap / p.g.KH;
     }
-    for (int r0 = 0; r0 < rows; r0 += 128) {
-        uint4 v[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int r = r0 + r_first + 16 * i;
-            v[i] = make_uint4(0u, 0u, 0u, 0u);
-            if (r >= rows) continue;
-            const bf16* src = nullptr;
-            int nv = 0;
-            if (kind == OP_PLAIN_K) {
-                const int row = tile0 + r, k = kb * BKE + chunk * 8;
-                if (row < R) { src = base + (long long)row * ld + k; nv = K - k; }
-            } else if (kind == OP_PLAIN_MN) {
-                // smem row = (group g = r / 64, reduction index kk = r % 64); 128 bytes = MN indices tile0 + 64 g + [0, 64)
-                const int g = r >> 6, kk = kb * BKE + (r & 63), mn = tile0 + g * 64 + chunk * 8;
-                if (kk < K) { src = base + (long long)kk * ld + mn; nv = R - mn; }
-            } else if (kind == OP_CONV_FWD) {
-                const RowInfo ri = rinfo[r];
-                const int ti = ri.t + kt, hi = ri.h + kh, wi = ri.w + kw;
-                if (ri.n >= 0 && (unsigned)ti < (unsigned)p.g.Ti && (unsigned)hi < (unsigned)p.g.Hi && (unsigned)wi < (unsigned)p.g.Wi) {
-                    src = base + ((((long long)ri.n * p.g.Ti + ti) * p.g.Hi + hi) * p.g.Wi + wi) * p.g.C + cb * BKE + chunk * 8;
+    for (int r = r_first; r < rows; r += 16) {
+        uint8_t* dst = tile + (size_t)r * 128 + ((chunk ^ (r & 7)) << 4);
+        const bf16* src = nullptr;
+        int nv = 0;
+        if (kind == OP_CONV_TAPS) {
+            const RowInfo ri = rinfo[r];
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (ri.n >= 0) v = gather_taps8(base, p.g, ri.n, ri.t, ri.h, ri.w, kb * BKE + chunk * 8, K, tapofs);
+            *reinterpret_cast<uint4*>(dst) = v;
+            continue;
+        }
+        if (kind == OP_CONV_TAPS_MN) {
+            const long long site = (long long)kb * BKE + (r & 63);
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (site < K) {
+                long long s = site;
+                const int wo = (int)(s % p.g.Wo); s /= p.g.Wo;
+                const int ho = (int)(s % p.g.Ho); s /= p.g.Ho;
+                const int to = (int)(s % p.g.To); const int n = (int)(s / p.g.To);
+                v = gather_taps8(base, p.g, n, to * p.g.st - p.g.pt, ho * p.g.sh - p.g.ph, wo * p.g.sw - p.g.pw,
+                                 tile0 + (r >> 6) * 64 + chunk * 8, R, tapofs);
+            }
+            *reinterpret_cast<uint4*>(dst) = v;
+            continue;
+        }
+        if (kind == OP_PLAIN_K) {
+            const int row = tile0 + r, k = kb * BKE + chunk * 8;
+            if (row < R) { src = base + (long long)row * ld + k; nv = K - k; }
+        } else if (kind == OP_PLAIN_MN) {
+            // smem row = (group g = r / 64, reduction index kk = r % 64); 128 bytes = MN indices tile0 + 64 g + [0, 64)
+            const int g = r >> 6, kk = kb * BKE + (r & 63), mn = tile0 + g * 64 + chunk * 8;
+            if (kk < K) { src = base + (long long)kk * ld + mn; nv = R - mn; }
+        } else if (kind == OP_CONV_FWD) {
+            const RowInfo ri = rinfo[r];
+            const int ti = ri.t + kt, hi = ri.h + kh, wi = ri.w + kw;
+            if (ri.n >= 0 && (unsigned)ti < (unsigned)p.g.Ti && (unsigned)hi < (unsigned)p.g.Hi && (unsigned)wi < (unsigned)p.g.Wi) {
+                src = base + ((((long long)ri.n * p.g.Ti + ti) * p.g.Hi + hi) * p.g.Wi + wi) * p.g.C + cb * BKE + chunk * 8;
+                nv = 8;
+            }
+        } else if (kind == OP_CONV_DGRAD) {
+            const RowInfo ri = rinfo[r];
+            const int a = ri.t - kt, b = ri.h - kh, c = ri.w - kw;
+            if (ri.n >= 0 && a >= 0 && b >= 0 && c >= 0 && a % p.g.st == 0 && b % p.g.sh == 0 && c % p.g.sw == 0) {
+                const int to = a / p.g.st, ho = b / p.g.sh, wo = c / p.g.sw;
+                if (to < p.g.To && ho < p.g.Ho && wo < p.g.Wo) {
+                    src = base + ((((long long)ri.n * p.g.To + to) * p.g.Ho + ho) * p.g.Wo + wo) * p.g.Co + cb * BKE + chunk * 8;
                     nv = 8;
                 }
-            } else if (kind == OP_CONV_DGRAD) {
-                const RowInfo ri = rinfo[r];
-                const int a = ri.t - kt, b = ri.h - kh, c = ri.w - kw;
-                if (ri.n >= 0 && a >= 0 && b >= 0 && c >= 0 && a % p.g.st == 0 && b % p.g.sh == 0 && c % p.g.sw == 0) {
-                    const int to = a / p.g.st, ho = b / p.g.sh, wo = c / p.g.sw;
-                    if (to < p.g.To && ho < p.g.Ho && wo < p.g.Wo) {
-                        src = base + ((((long long)ri.n * p.g.To + to) * p.g.Ho + ho) * p.g.Wo + wo) * p.g.Co + cb * BKE + chunk * 8;
-                        nv = 8;
-                    }
-                }
-            } else {  // OP_CONV_WGRAD_X: group g -> (tap, ci block); smem row kk -> output site
-                const int g = r >> 6;
-                const int G = tile0 / 64 + g;
-                const long long site = (long long)kb * BKE + (r & 63);
-                if (site < K && G * 64 < R) {
-                    int tap = G / p.cpb; const int cbl = G % p.cpb;
-                    const int fw = tap % p.g.KW; tap /= p.g.KW; const int fh = tap % p.g.KH; const int ft = tap / p.g.KH;
-                    long long s = site;
-                    const int wo = (int)(s % p.g.Wo); s /= p.g.Wo;
-                    const int ho = (int)(s % p.g.Ho); s /= p.g.Ho;
-                    const int to = (int)(s % p.g.To); const int n = (int)(s / p.g.To);
-                    const int ti = to * p.g.st + ft - p.g.pt, hi = ho * p.g.sh + fh - p.g.ph, wi = wo * p.g.sw + fw - p.g.pw;
-                    if ((unsigned)ti < (unsigned)p.g.Ti && (unsigned)hi < (unsigned)p.g.Hi && (unsigned)wi < (unsigned)p.g.Wi) {
-                        src = base + ((((long long)n * p.g.Ti + ti) * p.g.Hi + hi) * p.g.Wi + wi) * p.g.C + cbl * BKE + chunk * 8;
-                        nv = 8;
-                    }
+            }
+        } else {  // OP_CONV_WGRAD_X: group g -> (tap, ci block); smem row kk -> output site
+            const int g = r >> 6;
+            const int G = tile0 / 64 + g;
+            const long long site = (long long)kb * BKE + (r & 63);
+            if (site < K && G * 64 < R) {
+                int tap = G / p.cpb; const int cbl = G % p.cpb;
+                const int fw = tap % p.g.KW; tap /= p.g.KW; const int fh = tap % p.g.KH; const int ft = tap / p.g.KH;
+                long long s = site;
+                const int wo = (int)(s % p.g.Wo); s /= p.g.Wo;
+                const int ho = (int)(s % p.g.Ho); s /= p.g.Ho;
+                const int to = (int)(s % p.g.To); const int n = (int)(s / p.g.To);
+                const int ti = to * p.g.st + ft - p.g.pt, hi = ho * p.g.sh + fh - p.g.ph, wi = wo * p.g.sw + fw - p.g.pw;
+                if ((unsigned)ti < (unsigned)p.g.Ti && (unsigned)hi < (unsigned)p.g.Hi && (unsigned)wi < (unsigned)p.g.Wi) {
+                    src = base + ((((long long)n * p.g.Ti + ti) * p.g.Hi + hi) * p.g.Wi + wi) * p.g.C + cbl * BKE + chunk * 8;
+                    nv = 8;
                 }
             }
-            if (src) v[i] = load_chunk(src, nv, align);
+        }
+        copy_chunk(dst, src, src ? nv : 0, align, base);
+    }
+}
+
+// ---- vectorised epilogue helpers: 16 consecutive columns of one output row
+__device__ __forceinline__ void load16(const void* p, int dtype, size_t idx, float (&v)[16]) {
+    if (dtype == AVEC_F32) {
+        const float* q = reinterpret_cast<const float*>(p) + idx;
+        if ((reinterpret_cast<uintptr_t>(q) & 15) == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { float4 t = __ldg(reinterpret_cast<const float4*>(q) + i); v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w; }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __ldg(q + i);
+        }
+    } else {
+        const bf16* q = reinterpret_cast<const bf16*>(p) + idx;
+        const uintptr_t a = reinterpret_cast<uintptr_t>(q);
+        uint32_t w[8];
+        if ((a & 15) == 0) {
+            uint4 t0 = __ldg(reinterpret_cast<const uint4*>(q)), t1 = __ldg(reinterpret_cast<const uint4*>(q) + 1);
+            w[0] = t0.x; w[1] = t0.y; w[2] = t0.z; w[3] = t0.w; w[4] = t1.x; w[5] = t1.y; w[6] = t1.z; w[7] = t1.w;
+        } else if ((a & 7) == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { uint2 t = __ldg(reinterpret_cast<const uint2*>(q) + i); w[2 * i] = t.x; w[2 * i + 1] = t.y; }
+        } else if ((a & 3) == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w[i] = __ldg(reinterpret_cast<const uint32_t*>(q) + i);
+        } else {
+            const unsigned short* h = reinterpret_cast<const unsigned short*>(q);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w[i] = (uint32_t)__ldg(h + 2 * i) | ((uint32_t)__ldg(h + 2 * i + 1) << 16);
         }
 #pragma unroll
+        for (int i = 0; i < 8; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u); }
+    }
+}
+__device__ __forceinline__ void store16(void* p, int dtype, size_t idx, const float (&v)[16]) {
+    if (dtype == AVEC_F32) {
+        float* q = reinterpret_cast<float*>(p) + idx;
+        if ((reinterpret_cast<uintptr_t>(q) & 15) == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) reinterpret_cast<float4*>(q)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) q[i] = v[i];
+        }
+    } else {
+        bf16* q = reinterpret_cast<bf16*>(p) + idx;
+        const uintptr_t a = reinterpret_cast<uintptr_t>(q);
+        uint32_t w[8];
+#pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const int r = r0 + r_first + 16 * i;
-            if (r < rows) *reinterpret_cast<uint4*>(tile + (size_t)r * 128 + ((chunk ^ (r & 7)) << 4)) = v[i];
+            __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            w[i] = *reinterpret_cast<uint32_t*>(&t);
+        }
+        if ((a & 15) == 0) {
+            reinterpret_cast<uint4*>(q)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+            reinterpret_cast<uint4*>(q)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+        } else if ((a & 7) == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) reinterpret_cast<uint2*>(q)[i] = make_uint2(w[2 * i], w[2 * i + 1]);
+        } else if ((a & 3) == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) reinterpret_cast<uint32_t*>(q)[i] = w[i];
+        } else {
+            unsigned short* h = reinterpret_cast<unsigned short*>(q);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { h[2 * i] = (unsigned short)(w[i] & 0xFFFF); h[2 * i + 1] = (unsigned short)(w[i] >> 16); }
         }
     }
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_constant__ TcParams p) {
+__global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_constant__ TcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int BN = p.BN;
@@ -232,6 +367,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     uint64_t* accum_bar = empty_bar + 8;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
     RowInfo* rinfo = reinterpret_cast<RowInfo*>(ctrl + 256);
+    int* tapofs = reinterpret_cast<int*>(ctrl + 256 + BM * sizeof(RowInfo));
+    float* cstat = reinterpret_cast<float*>(ctrl + 256 + BM * sizeof(RowInfo) + 256 * sizeof(int));  // [2][256]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
@@ -250,11 +387,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
     }
     if (warp == 4) tmem_alloc(tmem_slot, ncols);
     // per-row site decode for the conv gathers (A operand rows are fixed for the whole tile)
-    if (tid < BM && (p.a_kind == OP_CONV_FWD || p.a_kind == OP_CONV_DGRAD)) {
+    if (p.a_kind == OP_CONV_TAPS || p.b_kind == OP_CONV_TAPS_MN) {
+        for (int tap = tid; tap < 256; tap += TC_THREADS) {
+            int t = tap;
+            const int kw = t % p.g.KW; t /= p.g.KW; const int kh = t % p.g.KH; const int kt = t / p.g.KH;
+            tapofs[tap] = kt | (kh << 8) | (kw << 16);
+        }
+    }
+    if (tid < BM && (p.a_kind == OP_CONV_FWD || p.a_kind == OP_CONV_DGRAD || p.a_kind == OP_CONV_TAPS)) {
         RowInfo ri; ri.n = -1; ri.t = ri.h = ri.w = 0;
         long long m = (long long)m0 + tid;
         if (m < p.M) {
-            if (p.a_kind == OP_CONV_FWD) {
+            if (p.a_kind != OP_CONV_DGRAD) {
                 int wo = (int)(m % p.g.Wo); m /= p.g.Wo; int ho = (int)(m % p.g.Ho); m /= p.g.Ho; int to = (int)(m % p.g.To);
                 ri.n = (int)(m / p.g.To);
                 ri.t = to * p.g.st - p.g.pt; ri.h = ho * p.g.sh - p.g.ph; ri.w = wo * p.g.sw - p.g.pw;
@@ -273,18 +417,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
 
     if (warp < 4) {
         // ===================== producers =====================
-        const bool a_mn = p.a_kind == OP_PLAIN_MN;
-        for (int i = 0; i < nkb; ++i) {
-            const int s = i % p.stages;
-            const uint32_t ph = (uint32_t)((i / p.stages) & 1);
-            mbar_wait(&empty_bar[s], ph ^ 1u);
-            uint8_t* a_tile = smem + (size_t)s * stage_bytes;
-            uint8_t* b_tile = a_tile + a_bytes;
-            const int kb = kb_begin + i;
-            fill_operand(a_tile, BM, p.a_kind, p.A, p.a_ld, p.a_align, p.M, p.K, a_mn ? m0 : m0, kb, p, rinfo, tid);
-            fill_operand(b_tile, b_rows, p.b_kind, p.B, p.b_ld, p.b_align, p.N, p.K, n0, kb, p, rinfo, tid);
-            fence_proxy_async();
-            mbar_arrive(&full_bar[s]);
+        // cp.async groups: k-block i is published (proxy fence + mbarrier arrive) LAG iterations after it was issued, so
+        // each thread keeps up to LAG+1 k-blocks of loads in flight (stages >= LAG + 1)
+        constexpr int LAG = 2;
+        for (int i = 0; i < nkb + LAG; ++i) {
+            if (i < nkb) {
+                const int s = i % p.stages;
+                const uint32_t ph = (uint32_t)((i / p.stages) & 1);
+                mbar_wait(&empty_bar[s], ph ^ 1u);
+                uint8_t* a_tile = smem + (size_t)s * stage_bytes;
+                uint8_t* b_tile = a_tile + a_bytes;
+                const int kb = kb_begin + i;
+                fill_operand(a_tile, BM, p.a_kind, p.A, p.a_ld, p.a_align, p.M, p.K, m0, kb, p, rinfo, tapofs, tid);
+                fill_operand(b_tile, b_rows, p.b_kind, p.B, p.b_ld, p.b_align, p.N, p.K, n0, kb, p, rinfo, tapofs, tid);
+            }
+            cp_async_commit();
+            if (i >= LAG) {
+                cp_async_wait<LAG>();
+                fence_proxy_async();
+                mbar_arrive(&full_bar[(i - LAG) % p.stages]);
+            }
         }
         // ===================== epilogue =====================
         mbar_wait(accum_bar, 0u);
@@ -293,46 +445,87 @@ __global__ void __launch_bounds__(TC_THREADS, 1) gemm_tc_kernel(const __grid_con
         const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
         EpiParams ep = p.ep;
         if (blockIdx.z > 0) ep.bias = nullptr;
+        if (ep.colstats) {
+            for (int c = tid; c < 512; c += PRODUCER_THREADS) cstat[c] = 0.0f;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        const bool fast_kind = !p.out_transposed && ep.kind != AVEC_EPI_ACCUM;
         for (int c0 = 0; c0 < BN; c0 += 16) {
             float v[16];
             tmem_ld16(lane_addr + (uint32_t)c0, v);
-            float s1[16], s2[16];
+            const int c = n0 + c0;
+            const bool full = fast_kind && row < p.M && c + 16 <= p.N;
+            if (full) {
+                if (ep.bias) {
+                    float b[16];
+                    load16(ep.bias, AVEC_F32, (size_t)c, b);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int c = n0 + c0 + j;
-                float val = 0.0f;
-                if (row < p.M && c < p.N) {
-                    if (p.out_transposed) {
-                        // only LINEAR / ACCUM make sense transposed (weight gradients): out[c][row]
-                        float vv = v[j] + (ep.bias ? ep.bias[c] : 0.0f);
-                        size_t o = (size_t)c * ep.ldo + row;
-                        if (ep.kind == AVEC_EPI_ACCUM) atomicAdd(reinterpret_cast<float*>(ep.out) + o, ep.alpha * vv);
-                        else st_any(ep.out, ep.out_dtype, o, ep.alpha * vv);
-                        val = vv;
-                    } else {
-                        val = epilogue_elem(ep, row, c, v[j]);
+                    for (int j = 0; j < 16; ++j) v[j] += b[j];
+                }
+                float o[16];
+                const size_t oi = (size_t)row * ep.ldo + c;
+                if (ep.kind == AVEC_EPI_LINEAR) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) o[j] = ep.alpha * v[j];
+                } else if (ep.kind == AVEC_EPI_SWISH) {
+                    if (ep.out2) store16(ep.out2, ep.out2_dtype, (size_t)row * ep.ldo2 + c, v);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) o[j] = swishf_(v[j]);
+                } else {
+                    float x[16];
+                    if (ep.aux) load16(ep.aux, ep.aux_dtype, (size_t)row * ep.ldaux + c, x);
+                    if (ep.kind == AVEC_EPI_RESIDUAL) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) o[j] = x[j] + ep.alpha * v[j];
+                    } else if (ep.kind == AVEC_EPI_DSWISH) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) o[j] = ep.alpha * v[j] * dswishf_(x[j]);
+                    } else {  // RELU
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) o[j] = fmaxf(ep.alpha * v[j] + (ep.aux ? x[j] : 0.0f), 0.0f);
                     }
                 }
-                s1[j] = val; s2[j] = val * val;
-            }
-            if (ep.colstats) {
-                // column sums over this warp's 32 rows: butterfly reduce, then one atomic per column per warp
+                store16(ep.out, ep.out_dtype, oi, o);
+            } else {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) { s1[j] = warp_sum(s1[j]); s2[j] = warp_sum(s2[j]); }
-                if (lane < 16) {
-                    const int c = n0 + c0 + lane;
-                    float a = 0.0f, b = 0.0f;
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) if (j == lane) { a = s1[j]; b = s2[j]; }
-                    if (c < p.N) { atomicAdd(ep.colstats + c, a); atomicAdd(ep.colstats + p.N + c, b); }
+                for (int j = 0; j < 16; ++j) {
+                    const int cc = c + j;
+                    float val = 0.0f;
+                    if (row < p.M && cc < p.N) {
+                        if (p.out_transposed) {
+                            float vv = v[j] + (ep.bias ? ep.bias[cc] : 0.0f);
+                            size_t o = (size_t)cc * ep.ldo + row;
+                            if (ep.kind == AVEC_EPI_ACCUM) atomicAdd(reinterpret_cast<float*>(ep.out) + o, ep.alpha * vv);
+                            else st_any(ep.out, ep.out_dtype, o, ep.alpha * vv);
+                            val = vv;
+                        } else {
+                            val = epilogue_elem(ep, row, cc, v[j]);
+                        }
+                    }
+                    v[j] = val;
                 }
             }
+            if (ep.colstats) {
+                // v[] holds acc + bias for valid elements (0 elsewhere): column sums over this warp's 32 rows
+                const bool rv = row < p.M;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float x = (rv && c + j < p.N) ? v[j] : 0.0f;
+                    const float a = warp_sum(x), b = warp_sum(x * x);
+                    if (lane == j) { atomicAdd(&cstat[c0 + j], a); atomicAdd(&cstat[256 + c0 + j], b); }
+                }
+            }
+        }
+        if (ep.colstats) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            for (int cc = tid; cc < BN; cc += PRODUCER_THREADS)
+                if (n0 + cc < p.N) { atomicAdd(ep.colstats + n0 + cc, cstat[cc]); atomicAdd(ep.colstats + p.N + n0 + cc, cstat[256 + cc]); }
         }
         tc_fence_before();
     } else {
         // ===================== MMA issuer =====================
         const int a_mn = p.a_kind == OP_PLAIN_MN ? 1 : 0;
-        const int b_mn = (p.b_kind == OP_PLAIN_MN || p.b_kind == OP_CONV_WGRAD_X) ? 1 : 0;
+        const int b_mn = (p.b_kind == OP_PLAIN_MN || p.b_kind == OP_CONV_WGRAD_X || p.b_kind == OP_CONV_TAPS_MN) ? 1 : 0;
         const uint32_t idesc = make_idesc(BN, a_mn, b_mn);
         for (int i = 0; i < nkb; ++i) {
             const int s = i % p.stages;
@@ -388,9 +581,9 @@ bool avec_gemm_tc_supported(const avec_gemm_args* a) {
         if ((long long)a->M * a->N * a->K < (1LL << 18)) return false;
         return true;
     }
-    case AVEC_GEMM_CONV_FWD: return g.C % 64 == 0;
+    case AVEC_GEMM_CONV_FWD: return g.C % 64 == 0 || (g.C == 1 && g.KT * g.KH * g.KW <= 256 && g.KT < 256 && g.KH < 256);
     case AVEC_GEMM_CONV_DGRAD: return g.Co % 64 == 0;
-    case AVEC_GEMM_CONV_WGRAD: return g.C % 64 == 0;
+    case AVEC_GEMM_CONV_WGRAD: return g.C % 64 == 0 || (g.C == 1 && g.KT * g.KH * g.KW <= 256 && g.KT < 256 && g.KH < 256);
     default: return false;
     }
 }
@@ -413,9 +606,9 @@ int avec_gemm_tc(const avec_gemm_args* a, cudaStream_t st) {
         break;
     case AVEC_GEMM_CONV_FWD:
         AVEC_CHECK_ARG(a->K == taps * p.g.C && a->N == p.g.Co);
-        p.a_kind = OP_CONV_FWD; p.a_ld = p.g.C;
         p.b_kind = OP_PLAIN_K; p.b_ld = a->K;
-        p.cpb = p.g.C / 64; p.num_kb = taps * p.cpb;
+        if (p.g.C == 1) { p.a_kind = OP_CONV_TAPS; p.a_ld = 1; p.cpb = 1; p.num_kb = cdiv(taps, BKE); }
+        else { p.a_kind = OP_CONV_FWD; p.a_ld = p.g.C; p.cpb = p.g.C / 64; p.num_kb = taps * p.cpb; }
         break;
     case AVEC_GEMM_CONV_DGRAD:
         AVEC_CHECK_ARG(a->K == taps * p.g.Co && a->N == p.g.C);
@@ -426,24 +619,23 @@ int avec_gemm_tc(const avec_gemm_args* a, cudaStream_t st) {
     case AVEC_GEMM_CONV_WGRAD:
         AVEC_CHECK_ARG(a->M == p.g.Co && a->N == taps * p.g.C);
         p.a_kind = OP_PLAIN_MN; p.a_ld = p.g.Co;
-        p.b_kind = OP_CONV_WGRAD_X; p.b_ld = p.g.C;
-        p.cpb = p.g.C / 64; p.num_kb = cdiv(a->K, BKE);
+        p.b_kind = p.g.C == 1 ? OP_CONV_TAPS_MN : OP_CONV_WGRAD_X; p.b_ld = p.g.C;
+        p.cpb = p.g.C == 1 ? 1 : p.g.C / 64; p.num_kb = cdiv(a->K, BKE);
         break;
     default: return AVEC_ERR_INVALID;
     }
     p.a_align = ptr_align(p.A, p.a_ld);
     p.b_align = ptr_align(p.B, p.b_ld);
     p.BN = pick_bn(a->N);
-    if (p.b_kind == OP_CONV_WGRAD_X) p.BN = a->N >= 256 ? 256 : (a->N >= 192 ? 192 : (a->N >= 128 ? 128 : 64));
+    if (p.b_kind == OP_CONV_WGRAD_X || p.b_kind == OP_CONV_TAPS_MN) p.BN = a->N >= 256 ? 256 : (a->N >= 192 ? 192 : (a->N >= 128 ? 128 : 64));
     int split = (a->epi == AVEC_EPI_ACCUM && a->split_k > 1) ? a->split_k : 1;
     if (split > p.num_kb) split = p.num_kb;
     p.kb_per_split = cdiv(p.num_kb, split);
     split = cdiv(p.num_kb, p.kb_per_split);
     const int b_rows = (p.b_kind == OP_PLAIN_K) ? p.BN : cdiv(p.BN, 64) * 64;
     const int stage_bytes = BM * 128 + cdiv(b_rows * 128, 1024) * 1024;
-    p.stages = stage_bytes <= 32 * 1024 ? 3 : (stage_bytes <= 40 * 1024 ? 4 : 4);
-    if (p.stages > p.kb_per_split) p.stages = p.kb_per_split < 2 ? 2 : p.kb_per_split;
-    size_t smem = (size_t)p.stages * stage_bytes + 256 + BM * sizeof(RowInfo) + 1024;
+    p.stages = stage_bytes <= 32 * 1024 ? 3 : 4;   // >= LAG + 1 = 3 (producer cp.async run-ahead); <= 32 KB stages allow 2 CTAs / SM
+    size_t smem = (size_t)p.stages * stage_bytes + 256 + BM * sizeof(RowInfo) + 256 * sizeof(int) + 512 * sizeof(float) + 1024;
     if (smem > 227 * 1024) return AVEC_ERR_UNSUPPORTED;
     static bool attr_set = false;
     if (!attr_set) {

@@ -90,17 +90,27 @@ def test_conv2d_fwd_dgrad_wgrad(impl, dtype, tol, N, H, W, Ci, Co, k, s):
         ops.set_gemm_impl("auto")
 
 
-def test_conv3d_stem_simt_fp32():
-    ops.set_gemm_impl("simt")
+@pytest.mark.parametrize("impl,dtype,tol", [("simt", torch.float32, 1e-5), ("tcgen05", torch.bfloat16, 1e-2)])
+@pytest.mark.parametrize("B,T,H,W,Co,k,s", [(1, 4, 16, 16, 64, (5, 7, 7), (1, 2, 2)), (2, 1, 21, 80, 180, (1, 3, 3), (1, 2, 2)),
+                                             (2, 5, 88, 88, 64, (5, 7, 7), (1, 2, 2))])
+def test_single_channel_stem_conv_fwd_wgrad(impl, dtype, tol, B, T, H, W, Co, k, s):
+    """C = 1 stems (video Conv3d 5x7x7, audio Conv2d 3x3): element-wise im2col gather inside the GEMM producer"""
+    ops.set_gemm_impl(impl)
     try:
-        B, T, H, W, Co = 1, 4, 16, 16, 64
-        x = _rand(B, T, H, W, 1, seed=1)
-        w = _rand(Co, 1, 5, 7, 7, seed=2) / 245 ** 0.5
+        taps = k[0] * k[1] * k[2]
+        x = _rand(B, T, H, W, 1, dtype=dtype, seed=1)
+        w = (_rand(Co, 1, *k, seed=2) / taps ** 0.5).to(dtype)
         b = _rand(Co, seed=3)
-        g = ops.make_geom(B, T, H, W, 1, Co, (5, 7, 7), (1, 2, 2), (2, 3, 3))
+        pad = tuple((kk - 1) // 2 for kk in k)
+        g = ops.make_geom(B, T, H, W, 1, Co, k, s, pad)
         y = ops.conv_fwd(x, w.reshape(Co, -1).contiguous(), g, bias=b)
-        xr = x.view(B, 1, T, H, W)
-        yr = F.conv3d(F.pad(xr, (3, 3, 3, 3, 2, 2)), w, b, stride=(1, 2, 2))
-        _close(y, yr.permute(0, 2, 3, 4, 1).reshape(-1, Co), 1e-5)
+        xr = x.float().view(B, 1, T, H, W)
+        wr = w.float().requires_grad_(True)
+        yr = F.conv3d(F.pad(xr, (pad[2], k[2] // 2, pad[1], k[1] // 2, pad[0], k[0] // 2)), wr, b, stride=s)
+        _close(y, yr.permute(0, 2, 3, 4, 1).reshape(-1, Co), tol)
+        dy = _rand(*y.shape, dtype=dtype, seed=4)
+        yr.backward(dy.float().view(B, g.To, g.Ho, g.Wo, Co).permute(0, 4, 1, 2, 3))
+        dw = ops.conv_wgrad(dy, x, g)
+        _close(dw, wr.grad.reshape(Co, -1), tol if dtype == torch.bfloat16 else 1e-4)
     finally:
         ops.set_gemm_impl("auto")
