@@ -48,7 +48,42 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
+// ---- V consecutive elements <-> fp32 registers (V = 4 or 8; pointers must be V*sizeof(T)-aligned) -----------------
+template <int V> __device__ __forceinline__ void load_vec(const float* p, float (&v)[V]) {
+#pragma unroll
+    for (int i = 0; i < V / 4; ++i) { float4 t = reinterpret_cast<const float4*>(p)[i]; v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w; }
+}
+template <int V> __device__ __forceinline__ void load_vec(const bf16* p, float (&v)[V]) {
+    uint32_t w[V / 2];
+    if (V == 8) { uint4 t = *reinterpret_cast<const uint4*>(p); w[0] = t.x; w[1] = t.y; w[V / 2 - 2] = t.z; w[V / 2 - 1] = t.w; }
+    else { uint2 t = *reinterpret_cast<const uint2*>(p); w[0] = t.x; w[1] = t.y; }
+#pragma unroll
+    for (int i = 0; i < V / 2; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u); }
+}
+template <int V> __device__ __forceinline__ void store_vec(float* p, const float (&v)[V]) {
+#pragma unroll
+    for (int i = 0; i < V / 4; ++i) reinterpret_cast<float4*>(p)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+template <int V> __device__ __forceinline__ void store_vec(bf16* p, const float (&v)[V]) {
+    uint32_t w[V / 2];
+#pragma unroll
+    for (int i = 0; i < V / 2; ++i) { __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]); w[i] = *reinterpret_cast<uint32_t*>(&t); }
+    if (V == 8) *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[V / 2 - 2], w[V / 2 - 1]);
+    else *reinterpret_cast<uint2*>(p) = make_uint2(w[0], w[1]);
+}
+
 // dispatch a runtime dtype code onto a template parameter
+// dispatch dtype and vector width (V = 8 when C % 8 == 0, else 4; C % 4 == 0 is required by the vectorised kernels)
+#define AVEC_DISPATCH_DTYPE_VEC(code, C_, T, V, ...)                                       \
+    do {                                                                                    \
+        if ((C_) % 4 != 0) return AVEC_ERR_INVALID;                                         \
+        if ((code) == AVEC_F32) { using T = float;                                          \
+            if ((C_) % 8 == 0) { constexpr int V = 8; __VA_ARGS__; } else { constexpr int V = 4; __VA_ARGS__; } } \
+        else if ((code) == AVEC_BF16) { using T = bf16;                                     \
+            if ((C_) % 8 == 0) { constexpr int V = 8; __VA_ARGS__; } else { constexpr int V = 4; __VA_ARGS__; } } \
+        else return AVEC_ERR_INVALID;                                                       \
+    } while (0)
+
 #define AVEC_DISPATCH_DTYPE(code, T, ...)                                   \
     do {                                                                    \
         if ((code) == AVEC_F32) { using T = float; __VA_ARGS__; }           \

@@ -12,6 +12,7 @@
 // 16-byte aligned, which rules out a TMA descriptor), transposed operands of dgrad / wgrad (MN-major descriptors, no
 // transposed copies in HBM), and the ResNet / strided convolutions as implicit GEMMs (im2col never materialised).
 #include "common.cuh"
+#include <cuda.h>
 #include <cstring>
 #include <cstdint>
 
@@ -20,7 +21,7 @@ namespace {
 constexpr int BM = 128;
 constexpr int BKE = 64;                  // reduction elements per k-block (one 128-byte swizzle row)
 constexpr int PRODUCER_THREADS = 128;
-constexpr int TC_THREADS = 160;
+constexpr int TC_THREADS = 192;   // warps 0-3 gather producers + epilogue, warp 4 MMA issuer, warp 5 TMA producer
 
 enum OperandKind {
     OP_PLAIN_K = 0,    // element (row, k) at base[row*ld + k]               -> K-major tile
@@ -29,8 +30,17 @@ enum OperandKind {
     OP_CONV_DGRAD = 3, // A: row = input site, k = (tap, co), gather from dY  -> K-major
     OP_CONV_WGRAD_X = 4, // B: row = (tap, ci), k = output site, gather from X  -> MN-major
     OP_CONV_TAPS = 5,    // A, C == 1 (stems): row = output site, k = tap; element-wise im2col gather -> K-major
-    OP_CONV_TAPS_MN = 6  // B, C == 1 (stem wgrad): row = tap, k = output site              -> MN-major
+    OP_CONV_TAPS_MN = 6, // B, C == 1 (stem wgrad): row = tap, k = output site              -> MN-major
+    // ---- TMA-fed kinds (cp.async.bulk.tensor issued by one thread; 16-byte aligned strides required)
+    OP_TMA_K = 8,        // 2-d tensor map, box (64 k, rows)                                -> K-major
+    OP_TMA_MN = 9,       // 2-d tensor map, box (64 mn, 64 k) per 64-wide MN group          -> MN-major
+    OP_TMA_CONV_K = 10,  // A of a stride-1 conv fwd / dgrad: 4-d map (C,W,H,N), box (64,W,BH,BI) at the tap's shift -> K-major
+    OP_TMA_CONV_MN = 11  // wgrad operands: A = dY (no shift), B = X shifted by the group's tap  -> MN-major, k = site
 };
+__host__ __device__ inline bool is_tma(int kind) { return kind >= OP_TMA_K; }
+__host__ __device__ inline bool is_mn(int kind) {
+    return kind == OP_PLAIN_MN || kind == OP_CONV_WGRAD_X || kind == OP_CONV_TAPS_MN || kind == OP_TMA_MN || kind == OP_TMA_CONV_MN;
+}
 
 struct TcParams {
     int M, N, K;
@@ -44,6 +54,14 @@ struct TcParams {
     int cpb;  // 64-channel blocks per filter tap
     EpiParams ep;
     int out_transposed;
+    // TMA / tile geometry
+    int ksteps;                 // UMMA K=16 steps per k-block (4 for 64-element k-blocks)
+    int a_rows, b_rows;         // smem rows (128 B each) per stage of each operand
+    int a_group_stride, b_group_stride;  // bytes between 64-wide MN groups (MN-major LBO)
+    int a_tx, b_tx;             // bytes the TMA loads of one k-block deliver per operand
+    int conv_tiles;             // 1: the M (or reduction) tiles are row-aligned image tiles of BH rows x BI images
+    int ct_BH, ct_BI, ct_tph;   // tile rows, images per tile, tiles per image
+    int ct_dgrad;               // tap shift sign (dgrad reads dy[p + pad - tap])
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -96,6 +114,21 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
 // shared-memory matrix descriptor, SWIZZLE_128B, Blackwell version bits (cute::UMMA::SmemDescriptor layout)
@@ -353,13 +386,51 @@ __device__ __forceinline__ void store16(void* p, int dtype, size_t idx, const fl
     }
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_constant__ TcParams p) {
+// m-tile (or, for the TMA wgrad, reduction-tile) index -> first image / first image row of a row-aligned conv tile
+__device__ __forceinline__ void conv_tile_origin(const TcParams& p, int t, int& n0, int& h0) {
+    if (p.ct_BI == 1) { n0 = t / p.ct_tph; h0 = (t % p.ct_tph) * p.ct_BH; }
+    else { n0 = t * p.ct_BI; h0 = 0; }
+}
+
+// One thread issues the TMA loads of one operand for k-block kb into `tile`.
+__device__ __forceinline__ void tma_fill(const TcParams& p, int kind, const CUtensorMap* map, uint8_t* tile, uint64_t* bar, int rows,
+                                         int group_stride, int tile0, int kb, int mtile, bool is_a) {
+    const uint32_t dst = smem_u32(tile);
+    if (kind == OP_TMA_K) {
+        tma_load_2d(dst, map, bar, kb * BKE, tile0);
+    } else if (kind == OP_TMA_MN) {
+        for (int g = 0; g * 64 < rows; ++g) tma_load_2d(dst + g * group_stride, map, bar, tile0 + g * 64, kb * BKE);
+    } else if (kind == OP_TMA_CONV_K) {
+        int tap = kb / p.cpb; const int cb = kb % p.cpb;
+        const int kw = tap % p.g.KW, kh = tap / p.g.KW;
+        int n0, h0;
+        conv_tile_origin(p, mtile, n0, h0);
+        const int dh = p.ct_dgrad ? p.g.ph - kh : kh - p.g.ph, dw = p.ct_dgrad ? p.g.pw - kw : kw - p.g.pw;
+        tma_load_4d(dst, map, bar, cb * BKE, dw, h0 + dh, n0);
+    } else {  // OP_TMA_CONV_MN: the k-block is the conv tile kb
+        int n0, h0;
+        conv_tile_origin(p, kb, n0, h0);
+        const int ngroups = rows / (p.ksteps * 16);
+        for (int g = 0; g < ngroups; ++g) {
+            if (is_a) {
+                tma_load_4d(dst + g * group_stride, map, bar, tile0 + g * 64, 0, h0, n0);
+            } else {
+                const int G = tile0 / 64 + g;
+                int tap = G / p.cpb; const int cb = G % p.cpb;
+                const int kw = tap % p.g.KW, kh = tap / p.g.KW;
+                tma_load_4d(dst + g * group_stride, map, bar, cb * BKE, kw - p.g.pw, h0 + kh - p.g.ph, n0);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUtensorMap mapA,
+                                                               const __grid_constant__ CUtensorMap mapB) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int BN = p.BN;
-    const int a_bytes = BM * 128;
-    const int b_rows = (p.b_kind == OP_PLAIN_K) ? BN : ((BN + 63) / 64) * 64;
-    const int b_bytes = ((b_rows * 128 + 1023) / 1024) * 1024;
+    const int a_bytes = p.a_rows * 128;
+    const int b_bytes = ((p.b_rows * 128 + 1023) / 1024) * 1024;
     const int stage_bytes = a_bytes + b_bytes;
     uint8_t* ctrl = smem + (size_t)p.stages * stage_bytes;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);
@@ -371,22 +442,41 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
     float* cstat = reinterpret_cast<float*>(ctrl + 256 + BM * sizeof(RowInfo) + 256 * sizeof(int));  // [2][256]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int mtile = blockIdx.x;
+    const int n0 = blockIdx.y * BN;
     const int kb_begin = blockIdx.z * p.kb_per_split;
     const int kb_end = min(p.num_kb, kb_begin + p.kb_per_split);
     const int nkb = kb_end - kb_begin;
+    const bool a_tma = is_tma(p.a_kind), b_tma = is_tma(p.b_kind);
+    const bool any_gather = !a_tma || !b_tma, any_tma = a_tma || b_tma;
+
+    // output rows of this tile: row_base + r, r < rows_valid
+    long long row_base;
+    int rows_valid;
+    int m0 = mtile * BM;   // first A row (plain / gather kinds)
+    if (p.conv_tiles && p.a_kind == OP_TMA_CONV_K) {
+        int tn0, th0;
+        conv_tile_origin(p, mtile, tn0, th0);
+        row_base = ((long long)tn0 * p.g.Hi + th0) * p.g.Wi;
+        rows_valid = p.ct_BI == 1 ? min(p.ct_BH, p.g.Hi - th0) * p.g.Wi : min(p.ct_BI, p.g.N - tn0) * p.g.Hi * p.g.Wi;
+    } else {
+        row_base = m0;
+        rows_valid = min(BM, p.M - m0);
+    }
 
     // TMEM columns: power of two >= 32 covering BN
     uint32_t ncols = 32;
     while ((int)ncols < BN) ncols <<= 1;
 
     if (tid == 0) {
-        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], PRODUCER_THREADS); mbar_init(&empty_bar[s], 1); }
+        const uint32_t full_count = (any_gather ? PRODUCER_THREADS : 0) + (any_tma ? 1 : 0);
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], full_count); mbar_init(&empty_bar[s], 1); }
         mbar_init(accum_bar, 1);
         fence_barrier_init();
+        if (a_tma) tma_prefetch_desc(&mapA);
+        if (b_tma) tma_prefetch_desc(&mapB);
     }
     if (warp == 4) tmem_alloc(tmem_slot, ncols);
-    // per-row site decode for the conv gathers (A operand rows are fixed for the whole tile)
     if (p.a_kind == OP_CONV_TAPS || p.b_kind == OP_CONV_TAPS_MN) {
         for (int tap = tid; tap < 256; tap += TC_THREADS) {
             int t = tap;
@@ -394,6 +484,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
             tapofs[tap] = kt | (kh << 8) | (kw << 16);
         }
     }
+    // per-row site decode for the conv gathers (A operand rows are fixed for the whole tile)
     if (tid < BM && (p.a_kind == OP_CONV_FWD || p.a_kind == OP_CONV_DGRAD || p.a_kind == OP_CONV_TAPS)) {
         RowInfo ri; ri.n = -1; ri.t = ri.h = ri.w = 0;
         long long m = (long long)m0 + tid;
@@ -410,38 +501,50 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
         }
         rinfo[tid] = ri;
     }
+    // MN-major TMA tiles whose k extent (conv tile rows) is not a multiple of 16: the tail rows are never written by TMA
+    // and must read as zeros -> clear all stages once (generic proxy), then hand the buffers to the async proxy
+    if (p.a_kind == OP_TMA_CONV_MN || p.b_kind == OP_TMA_CONV_MN) {
+        uint4* z = reinterpret_cast<uint4*>(smem);
+        const int n16 = p.stages * stage_bytes / 16;
+        for (int i = tid; i < n16; i += TC_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        fence_proxy_async();
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp < 4) {
-        // ===================== producers =====================
-        // cp.async groups: k-block i is published (proxy fence + mbarrier arrive) LAG iterations after it was issued, so
-        // each thread keeps up to LAG+1 k-blocks of loads in flight (stages >= LAG + 1)
-        constexpr int LAG = 2;
-        for (int i = 0; i < nkb + LAG; ++i) {
-            if (i < nkb) {
-                const int s = i % p.stages;
-                const uint32_t ph = (uint32_t)((i / p.stages) & 1);
-                mbar_wait(&empty_bar[s], ph ^ 1u);
-                uint8_t* a_tile = smem + (size_t)s * stage_bytes;
-                uint8_t* b_tile = a_tile + a_bytes;
-                const int kb = kb_begin + i;
-                fill_operand(a_tile, BM, p.a_kind, p.A, p.a_ld, p.a_align, p.M, p.K, m0, kb, p, rinfo, tapofs, tid);
-                fill_operand(b_tile, b_rows, p.b_kind, p.B, p.b_ld, p.b_align, p.N, p.K, n0, kb, p, rinfo, tapofs, tid);
-            }
-            cp_async_commit();
-            if (i >= LAG) {
-                cp_async_wait<LAG>();
-                fence_proxy_async();
-                mbar_arrive(&full_bar[(i - LAG) % p.stages]);
+        // ===================== gather producers =====================
+        if (any_gather) {
+            // cp.async groups: k-block i is published (proxy fence + mbarrier arrive) LAG iterations after it was issued, so
+            // each thread keeps up to LAG+1 k-blocks of loads in flight (stages >= LAG + 1)
+            constexpr int LAG = 2;
+            for (int i = 0; i < nkb + LAG; ++i) {
+                if (i < nkb) {
+                    const int s = i % p.stages;
+                    const uint32_t ph = (uint32_t)((i / p.stages) & 1);
+                    mbar_wait(&empty_bar[s], ph ^ 1u);
+                    uint8_t* a_tile = smem + (size_t)s * stage_bytes;
+                    uint8_t* b_tile = a_tile + a_bytes;
+                    const int kb = kb_begin + i;
+                    if (!a_tma) fill_operand(a_tile, p.a_rows, p.a_kind, p.A, p.a_ld, p.a_align, p.M, p.K, m0, kb, p, rinfo, tapofs, tid);
+                    if (!b_tma) fill_operand(b_tile, p.b_rows, p.b_kind, p.B, p.b_ld, p.b_align, p.N, p.K, n0, kb, p, rinfo, tapofs, tid);
+                }
+                cp_async_commit();
+                if (i >= LAG) {
+                    cp_async_wait<LAG>();
+                    fence_proxy_async();
+                    mbar_arrive(&full_bar[(i - LAG) % p.stages]);
+                }
             }
         }
         // ===================== epilogue =====================
         mbar_wait(accum_bar, 0u);
         tc_fence_after();
-        const int row = m0 + warp * 32 + lane;
+        const int r = warp * 32 + lane;
+        const bool rv = r < rows_valid;
+        const long long row = row_base + r;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
         EpiParams ep = p.ep;
         if (blockIdx.z > 0) ep.bias = nullptr;
@@ -454,7 +557,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
             float v[16];
             tmem_ld16(lane_addr + (uint32_t)c0, v);
             const int c = n0 + c0;
-            const bool full = fast_kind && row < p.M && c + 16 <= p.N;
+            const bool full = fast_kind && rv && c + 16 <= p.N;
             if (full) {
                 if (ep.bias) {
                     float b[16];
@@ -491,7 +594,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
                 for (int j = 0; j < 16; ++j) {
                     const int cc = c + j;
                     float val = 0.0f;
-                    if (row < p.M && cc < p.N) {
+                    if (rv && cc < p.N) {
                         if (p.out_transposed) {
                             float vv = v[j] + (ep.bias ? ep.bias[cc] : 0.0f);
                             size_t o = (size_t)cc * ep.ldo + row;
@@ -499,15 +602,14 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
                             else st_any(ep.out, ep.out_dtype, o, ep.alpha * vv);
                             val = vv;
                         } else {
-                            val = epilogue_elem(ep, row, cc, v[j]);
+                            val = epilogue_elem(ep, (int)row, cc, v[j]);
                         }
                     }
                     v[j] = val;
                 }
             }
             if (ep.colstats) {
-                // v[] holds acc + bias for valid elements (0 elsewhere): column sums over this warp's 32 rows
-                const bool rv = row < p.M;
+                // v[] holds acc + bias for valid elements: column sums over this warp's 32 rows
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const float x = (rv && c + j < p.N) ? v[j] : 0.0f;
@@ -522,10 +624,25 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
                 if (n0 + cc < p.N) { atomicAdd(ep.colstats + n0 + cc, cstat[cc]); atomicAdd(ep.colstats + p.N + n0 + cc, cstat[256 + cc]); }
         }
         tc_fence_before();
+    } else if (warp == 5) {
+        // ===================== TMA producer (one thread) =====================
+        if (any_tma && lane == 0) {
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % p.stages;
+                const uint32_t ph = (uint32_t)((i / p.stages) & 1);
+                mbar_wait(&empty_bar[s], ph ^ 1u);
+                uint8_t* a_tile = smem + (size_t)s * stage_bytes;
+                uint8_t* b_tile = a_tile + a_bytes;
+                const int kb = kb_begin + i;
+                mbar_expect_tx(&full_bar[s], (uint32_t)((a_tma ? p.a_tx : 0) + (b_tma ? p.b_tx : 0)));
+                if (a_tma) tma_fill(p, p.a_kind, &mapA, a_tile, &full_bar[s], p.a_rows, p.a_group_stride, m0, kb, mtile, true);
+                if (b_tma) tma_fill(p, p.b_kind, &mapB, b_tile, &full_bar[s], p.b_rows, p.b_group_stride, n0, kb, mtile, false);
+            }
+        }
     } else {
         // ===================== MMA issuer =====================
-        const int a_mn = p.a_kind == OP_PLAIN_MN ? 1 : 0;
-        const int b_mn = (p.b_kind == OP_PLAIN_MN || p.b_kind == OP_CONV_WGRAD_X || p.b_kind == OP_CONV_TAPS_MN) ? 1 : 0;
+        const int a_mn = is_mn(p.a_kind) ? 1 : 0;
+        const int b_mn = is_mn(p.b_kind) ? 1 : 0;
         const uint32_t idesc = make_idesc(BN, a_mn, b_mn);
         for (int i = 0; i < nkb; ++i) {
             const int s = i % p.stages;
@@ -535,12 +652,11 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
             if (lane == 0) {
                 const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
                 const uint32_t b_addr = a_addr + a_bytes;
-#pragma unroll
-                for (int k = 0; k < BKE / 16; ++k) {
+                for (int k = 0; k < p.ksteps; ++k) {
                     // K-major: advance 32 bytes inside the 128-byte swizzle row; SBO = 1024 (8 rows).
-                    // MN-major: advance 16 reduction rows = 2048 bytes; LBO = 8192 (next 64-wide MN group), SBO = 1024.
-                    const uint64_t adesc = a_mn ? make_smem_desc(a_addr + k * 2048, 8192, 1024) : make_smem_desc(a_addr + k * 32, 16, 1024);
-                    const uint64_t bdesc = b_mn ? make_smem_desc(b_addr + k * 2048, 8192, 1024) : make_smem_desc(b_addr + k * 32, 16, 1024);
+                    // MN-major: advance 16 reduction rows = 2048 bytes; LBO = next 64-wide MN group, SBO = 1024.
+                    const uint64_t adesc = a_mn ? make_smem_desc(a_addr + k * 2048, p.a_group_stride, 1024) : make_smem_desc(a_addr + k * 32, 16, 1024);
+                    const uint64_t bdesc = b_mn ? make_smem_desc(b_addr + k * 2048, p.b_group_stride, 1024) : make_smem_desc(b_addr + k * 32, 16, 1024);
                     umma_f16(tmem_base, adesc, bdesc, idesc, (i > 0 || k > 0) ? 1u : 0u);
                 }
                 umma_commit(&empty_bar[s]);
@@ -567,7 +683,51 @@ int ptr_align(const void* p, long long ld_elems) {
     return al;
 }
 
+// ---- tensor maps (driver entry point resolved through the runtime: no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(f);
+    }
+    return fn;
+}
+// rank-d bf16 tensor map, 128B swizzle, zero OOB fill.  dims/box innermost first; strides (bytes) for dims 1..d-1.
+bool encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+    EncodeTiledFn fn = get_encode();
+    if (!fn) return false;
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+bool tma_ok_2d(const void* base, long long ld) { return (reinterpret_cast<uintptr_t>(base) % 16) == 0 && (ld * 2) % 16 == 0 && get_encode() != nullptr; }
+
+// row-aligned conv tiles: whole images (BI per tile) when an image has <= 128 sites, else BH image rows of one image
+bool conv_tiling(const ConvGeom& g, int& BH, int& BI, int& tph) {
+    const int hw = g.Hi * g.Wi;
+    if (g.Wi > 128) return false;
+    if (hw <= 128) { BI = 128 / hw; BH = g.Hi; tph = 1; }
+    else { BI = 1; BH = 128 / g.Wi; tph = cdiv(g.Hi, BH); }
+    return BH >= 1 && BH <= 256 && BI <= 256 && g.Wi <= 256;
+}
+bool conv_is_s1_same(const ConvGeom& g) {
+    return g.KT == 1 && g.Ti == 1 && g.st == 1 && g.sh == 1 && g.sw == 1 && g.Ho == g.Hi && g.Wo == g.Wi && g.KH == g.KW &&
+           g.ph == (g.KH - 1) / 2 && g.pw == (g.KW - 1) / 2 && (g.KH % 2) == 1;
+}
+
 }  // namespace
+
+static int g_tma_enabled = 1;
+extern "C" void avec_set_tma(int enabled) { g_tma_enabled = enabled; }
 
 bool avec_gemm_tc_supported(const avec_gemm_args* a) {
     if (a->ab_dtype != AVEC_BF16) return false;
@@ -591,13 +751,24 @@ bool avec_gemm_tc_supported(const avec_gemm_args* a) {
 int avec_gemm_tc(const avec_gemm_args* a, cudaStream_t st) {
     TcParams p;
     memset(&p, 0, sizeof(p));
+    CUtensorMap mapA, mapB;
+    memset(&mapA, 0, sizeof(mapA));
+    memset(&mapB, 0, sizeof(mapB));
     p.M = a->M; p.N = a->N; p.K = a->K;
     p.A = reinterpret_cast<const bf16*>(a->A);
     p.B = reinterpret_cast<const bf16*>(a->B);
     p.g = make_geom(a->g);
     p.ep = make_epi(a);
     p.out_transposed = 0;
+    p.ksteps = 4;
+    p.a_group_stride = p.b_group_stride = 8192;
     const int taps = p.g.KT * p.g.KH * p.g.KW;
+    int grid_m = cdiv(a->M, BM);
+    bool wgrad_bn_fixed = false;
+    int BH = 0, BI = 0, tph = 0;
+    const bool conv_tma = g_tma_enabled && get_encode() != nullptr && (a->mode == AVEC_GEMM_CONV_FWD || a->mode == AVEC_GEMM_CONV_DGRAD ||
+                          a->mode == AVEC_GEMM_CONV_WGRAD) && conv_is_s1_same(p.g) && p.g.C % 64 == 0 && p.g.Co % 64 == 0 &&
+                          conv_tiling(p.g, BH, BI, tph) && (reinterpret_cast<uintptr_t>(a->A) % 16) == 0 && (reinterpret_cast<uintptr_t>(a->B) % 16) == 0;
     switch (a->mode) {
     case AVEC_GEMM_PLAIN:
         if (a->sak == 1) { p.a_kind = OP_PLAIN_K; p.a_ld = a->sam; } else { p.a_kind = OP_PLAIN_MN; p.a_ld = a->sak; }
@@ -608,43 +779,97 @@ int avec_gemm_tc(const avec_gemm_args* a, cudaStream_t st) {
         AVEC_CHECK_ARG(a->K == taps * p.g.C && a->N == p.g.Co);
         p.b_kind = OP_PLAIN_K; p.b_ld = a->K;
         if (p.g.C == 1) { p.a_kind = OP_CONV_TAPS; p.a_ld = 1; p.cpb = 1; p.num_kb = cdiv(taps, BKE); }
-        else { p.a_kind = OP_CONV_FWD; p.a_ld = p.g.C; p.cpb = p.g.C / 64; p.num_kb = taps * p.cpb; }
+        else { p.a_kind = conv_tma ? OP_TMA_CONV_K : OP_CONV_FWD; p.a_ld = p.g.C; p.cpb = p.g.C / 64; p.num_kb = taps * p.cpb; }
         break;
     case AVEC_GEMM_CONV_DGRAD:
         AVEC_CHECK_ARG(a->K == taps * p.g.Co && a->N == p.g.C);
-        p.a_kind = OP_CONV_DGRAD; p.a_ld = p.g.Co;
+        p.a_kind = conv_tma ? OP_TMA_CONV_K : OP_CONV_DGRAD; p.a_ld = p.g.Co;
         p.b_kind = OP_PLAIN_K; p.b_ld = a->K;
         p.cpb = p.g.Co / 64; p.num_kb = taps * p.cpb;
+        p.ct_dgrad = 1;
         break;
     case AVEC_GEMM_CONV_WGRAD:
         AVEC_CHECK_ARG(a->M == p.g.Co && a->N == taps * p.g.C);
-        p.a_kind = OP_PLAIN_MN; p.a_ld = p.g.Co;
-        p.b_kind = p.g.C == 1 ? OP_CONV_TAPS_MN : OP_CONV_WGRAD_X; p.b_ld = p.g.C;
+        p.a_kind = conv_tma ? OP_TMA_CONV_MN : OP_PLAIN_MN; p.a_ld = p.g.Co;
+        p.b_kind = p.g.C == 1 ? OP_CONV_TAPS_MN : (conv_tma ? OP_TMA_CONV_MN : OP_CONV_WGRAD_X); p.b_ld = p.g.C;
         p.cpb = p.g.C == 1 ? 1 : p.g.C / 64; p.num_kb = cdiv(a->K, BKE);
+        wgrad_bn_fixed = true;
         break;
     default: return AVEC_ERR_INVALID;
     }
     p.a_align = ptr_align(p.A, p.a_ld);
     p.b_align = ptr_align(p.B, p.b_ld);
     p.BN = pick_bn(a->N);
-    if (p.b_kind == OP_CONV_WGRAD_X || p.b_kind == OP_CONV_TAPS_MN) p.BN = a->N >= 256 ? 256 : (a->N >= 192 ? 192 : (a->N >= 128 ? 128 : 64));
+    if (wgrad_bn_fixed) p.BN = a->N >= 256 ? 256 : (a->N >= 192 ? 192 : (a->N >= 128 ? 128 : 64));
+
+    // ---- conv TMA geometry
+    if (conv_tma) {
+        p.conv_tiles = 1; p.ct_BH = BH; p.ct_BI = BI; p.ct_tph = tph;
+        const int ntiles = BI == 1 ? p.g.N * tph : cdiv(p.g.N, BI);
+        const int tile_rows = BI == 1 ? BH * p.g.Wi : BI * p.g.Hi * p.g.Wi;   // <= 128
+        // 4-d maps over the NHWC tensors
+        const ConvGeom& g = p.g;
+        if (a->mode == AVEC_GEMM_CONV_WGRAD) {
+            if (p.BN > 128) p.BN = 128;   // 2 groups of B per stage keeps 3 stages in shared memory
+            p.ksteps = cdiv(tile_rows, 16);
+            const int krows = p.ksteps * 16;
+            p.a_rows = 2 * krows; p.b_rows = (p.BN / 64) * krows;
+            p.a_group_stride = p.b_group_stride = krows * 128;
+            p.num_kb = ntiles;
+            p.a_tx = 2 * tile_rows * 128; p.b_tx = (p.BN / 64) * tile_rows * 128;
+            cuuint64_t dA[4] = {(cuuint64_t)g.Co, (cuuint64_t)g.Wi, (cuuint64_t)g.Hi, (cuuint64_t)g.N};
+            cuuint64_t sA[3] = {(cuuint64_t)g.Co * 2, (cuuint64_t)g.Co * g.Wi * 2, (cuuint64_t)g.Co * g.Wi * g.Hi * 2};
+            cuuint64_t dB[4] = {(cuuint64_t)g.C, (cuuint64_t)g.Wi, (cuuint64_t)g.Hi, (cuuint64_t)g.N};
+            cuuint64_t sB[3] = {(cuuint64_t)g.C * 2, (cuuint64_t)g.C * g.Wi * 2, (cuuint64_t)g.C * g.Wi * g.Hi * 2};
+            cuuint32_t box[4] = {64, (cuuint32_t)g.Wi, (cuuint32_t)BH, (cuuint32_t)BI};
+            if (!encode_map(&mapA, a->A, 4, dA, sA, box) || !encode_map(&mapB, a->B, 4, dB, sB, box)) return AVEC_ERR_DRIVER;
+        } else {
+            const int Cin = a->mode == AVEC_GEMM_CONV_FWD ? g.C : g.Co;   // channels of the gathered tensor
+            grid_m = ntiles;
+            p.a_tx = tile_rows * 128;
+            cuuint64_t dA[4] = {(cuuint64_t)Cin, (cuuint64_t)g.Wi, (cuuint64_t)g.Hi, (cuuint64_t)g.N};
+            cuuint64_t sA[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cin * g.Wi * 2, (cuuint64_t)Cin * g.Wi * g.Hi * 2};
+            cuuint32_t box[4] = {64, (cuuint32_t)g.Wi, (cuuint32_t)BH, (cuuint32_t)BI};
+            if (!encode_map(&mapA, a->A, 4, dA, sA, box)) return AVEC_ERR_DRIVER;
+        }
+    }
+    // ---- plain 2-d TMA operands where strides allow it
+    if (g_tma_enabled && p.a_kind == OP_PLAIN_K && tma_ok_2d(p.A, p.a_ld)) {
+        cuuint64_t d[2] = {(cuuint64_t)a->K, (cuuint64_t)a->M}; cuuint64_t s1[1] = {(cuuint64_t)p.a_ld * 2}; cuuint32_t box[2] = {64, 128};
+        if (encode_map(&mapA, p.A, 2, d, s1, box)) { p.a_kind = OP_TMA_K; p.a_tx = 128 * 128; }
+    } else if (g_tma_enabled && p.a_kind == OP_PLAIN_MN && tma_ok_2d(p.A, p.a_ld)) {
+        cuuint64_t d[2] = {(cuuint64_t)a->M, (cuuint64_t)a->K}; cuuint64_t s1[1] = {(cuuint64_t)p.a_ld * 2}; cuuint32_t box[2] = {64, 64};
+        if (encode_map(&mapA, p.A, 2, d, s1, box)) { p.a_kind = OP_TMA_MN; p.a_tx = 2 * 64 * 128; }
+    }
+    if (g_tma_enabled && p.b_kind == OP_PLAIN_K && tma_ok_2d(p.B, p.b_ld)) {
+        cuuint64_t d[2] = {(cuuint64_t)a->K, (cuuint64_t)a->N}; cuuint64_t s1[1] = {(cuuint64_t)p.b_ld * 2}; cuuint32_t box[2] = {64, (cuuint32_t)p.BN};
+        if (encode_map(&mapB, p.B, 2, d, s1, box)) { p.b_kind = OP_TMA_K; p.b_tx = p.BN * 128; }
+    } else if (g_tma_enabled && p.b_kind == OP_PLAIN_MN && tma_ok_2d(p.B, p.b_ld)) {
+        cuuint64_t d[2] = {(cuuint64_t)a->N, (cuuint64_t)a->K}; cuuint64_t s1[1] = {(cuuint64_t)p.b_ld * 2}; cuuint32_t box[2] = {64, 64};
+        if (encode_map(&mapB, p.B, 2, d, s1, box)) { p.b_kind = OP_TMA_MN; p.b_tx = cdiv(p.BN, 64) * 64 * 128; }
+    }
+    if (p.a_rows == 0) p.a_rows = BM;
+    if (p.b_rows == 0) p.b_rows = is_mn(p.b_kind) ? cdiv(p.BN, 64) * 64 : p.BN;
+
     int split = (a->epi == AVEC_EPI_ACCUM && a->split_k > 1) ? a->split_k : 1;
     if (split > p.num_kb) split = p.num_kb;
     p.kb_per_split = cdiv(p.num_kb, split);
     split = cdiv(p.num_kb, p.kb_per_split);
-    const int b_rows = (p.b_kind == OP_PLAIN_K) ? p.BN : cdiv(p.BN, 64) * 64;
-    const int stage_bytes = BM * 128 + cdiv(b_rows * 128, 1024) * 1024;
-    p.stages = stage_bytes <= 32 * 1024 ? 3 : 4;   // >= LAG + 1 = 3 (producer cp.async run-ahead); <= 32 KB stages allow 2 CTAs / SM
-    size_t smem = (size_t)p.stages * stage_bytes + 256 + BM * sizeof(RowInfo) + 256 * sizeof(int) + 512 * sizeof(float) + 1024;
-    if (smem > 227 * 1024) return AVEC_ERR_UNSUPPORTED;
+    const int stage_bytes = p.a_rows * 128 + cdiv(p.b_rows * 128, 1024) * 1024;
+    p.stages = stage_bytes <= 32 * 1024 ? 3 : 4;   // >= LAG + 1 = 3 (gather run-ahead); <= 32 KB stages allow 2 CTAs / SM
+    const size_t ctrl_bytes = 256 + BM * sizeof(RowInfo) + 256 * sizeof(int) + 512 * sizeof(float) + 1024;
+    while (p.stages > 2 && (size_t)p.stages * stage_bytes + ctrl_bytes > 227 * 1024) --p.stages;
+    const bool any_gather = !is_tma(p.a_kind) || !is_tma(p.b_kind);
+    size_t smem = (size_t)p.stages * stage_bytes + ctrl_bytes;
+    if (smem > 227 * 1024 || (any_gather && p.stages < 3)) return AVEC_ERR_UNSUPPORTED;
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return AVEC_ERR_LAUNCH;
         attr_set = true;
     }
-    dim3 grid(cdiv(a->M, BM), cdiv(a->N, p.BN), split);
+    dim3 grid(grid_m, cdiv(a->N, p.BN), split);
     if (grid.y > 65535u || grid.z > 65535u) return AVEC_ERR_INVALID;
-    gemm_tc_kernel<<<grid, TC_THREADS, smem, st>>>(p);
+    gemm_tc_kernel<<<grid, TC_THREADS, smem, st>>>(p, mapA, mapB);
     AVEC_LAUNCH_CHECK();
     return AVEC_OK;
 }

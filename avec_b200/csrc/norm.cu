@@ -2,13 +2,14 @@
 // the ConformerBlock / ResNet paths.  All of these are HBM-bound: coalesced channel-contiguous accesses, fp32 math,
 // one pass over the data per kernel, per-channel reductions pre-reduced in shared memory before the global atomics.
 #include "common.cuh"
+#include <algorithm>
 
 namespace {
 
 // ------------------------------------------------------------------------------------------------------------------
 // LayerNorm forward: one warp per output token; the row lives in registers (C <= 32*LN_VPT).
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int LN_VPT = 16;
+constexpr int LN_G = 4;   // 4-channel groups per lane: C <= 32 * 4 * LN_G = 512, C % 4 == 0
 
 template <typename T>
 __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
@@ -18,35 +19,61 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const T* __restrict_
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= B * Tp) return;
     const int b = warp / Tp, tp = warp % Tp;
-    float out[LN_VPT];
+    float out[LN_G][4];
 #pragma unroll
-    for (int u = 0; u < LN_VPT; ++u) out[u] = 0.0f;
+    for (int u = 0; u < LN_G; ++u)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) out[u][j] = 0.0f;
     for (int p = 0; p < P; ++p) {
         int t = tp * P + p;
         if (t >= Tn) break;
         const T* xr = x + ((size_t)b * Tn + t) * C;
-        float v[LN_VPT];
+        float v[LN_G][4];
         float s = 0.0f;
 #pragma unroll
-        for (int u = 0; u < LN_VPT; ++u) { int c = lane + u * 32; v[u] = c < C ? ldf(xr + c) : 0.0f; s += v[u]; }
+        for (int u = 0; u < LN_G; ++u) {
+            int c = (lane + u * 32) * 4;
+            if (c < C) load_vec<4>(xr + c, v[u]);
+            else { v[u][0] = v[u][1] = v[u][2] = v[u][3] = 0.0f; }
+            s += v[u][0] + v[u][1] + v[u][2] + v[u][3];
+        }
         s = warp_sum(s);
         const float mu = s / C;
         float q = 0.0f;
 #pragma unroll
-        for (int u = 0; u < LN_VPT; ++u) { int c = lane + u * 32; float dv = c < C ? v[u] - mu : 0.0f; q += dv * dv; }
+        for (int u = 0; u < LN_G; ++u) {
+            int c = (lane + u * 32) * 4;
+            if (c < C) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { float dv = v[u][j] - mu; q += dv * dv; }
+            }
+        }
         q = warp_sum(q);
         const float rs = rsqrtf(q / C + eps);
         if (lane == 0) { mean[(size_t)b * Tn + t] = mu; rstd[(size_t)b * Tn + t] = rs; }
 #pragma unroll
-        for (int u = 0; u < LN_VPT; ++u) {
-            int c = lane + u * 32;
-            if (c < C) out[u] += (v[u] - mu) * rs * gamma[c] + beta[c];
+        for (int u = 0; u < LN_G; ++u) {
+            int c = (lane + u * 32) * 4;
+            if (c < C) {
+                float g[4], bb[4];
+                load_vec<4>(gamma + c, g);
+                load_vec<4>(beta + c, bb);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) out[u][j] += (v[u][j] - mu) * rs * g[j] + bb[j];
+            }
         }
     }
     const float invP = 1.0f / P;
     T* yr = y + ((size_t)b * Tp + tp) * C;
 #pragma unroll
-    for (int u = 0; u < LN_VPT; ++u) { int c = lane + u * 32; if (c < C) stf(yr + c, out[u] * invP); }
+    for (int u = 0; u < LN_G; ++u) {
+        int c = (lane + u * 32) * 4;
+        if (c < C) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) out[u][j] *= invP;
+            store_vec<4>(yr + c, out[u]);
+        }
+    }
 }
 
 // LayerNorm backward: warps stride over input rows; dgamma/dbeta partials live in registers, are reduced across the
@@ -61,29 +88,42 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict_
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const long long rows = (long long)B * Tn;
     const int Tr = res_stride > 0 ? (Tn - 1) / res_stride + 1 : 0;
-    float dg[LN_VPT], db[LN_VPT];
+    float dg[LN_G][4], db[LN_G][4], gm[LN_G][4];
 #pragma unroll
-    for (int u = 0; u < LN_VPT; ++u) { dg[u] = 0.0f; db[u] = 0.0f; }
+    for (int u = 0; u < LN_G; ++u) {
+        int c = (lane + u * 32) * 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { dg[u][j] = 0.0f; db[u][j] = 0.0f; gm[u][j] = 0.0f; }
+        if (c < C) load_vec<4>(gamma + c, gm[u]);
+    }
     const float invP = 1.0f / P;
     for (long long row = (long long)blockIdx.x * wpb + wib; row < rows; row += (long long)gridDim.x * wpb) {
         const int b = (int)(row / Tn), t = (int)(row % Tn);
         const T* xr = x + row * C;
         const T* dyr = dy + ((size_t)b * Tp + t / P) * C;
         const float mu = mean[row], rs = rstd[row];
-        float g[LN_VPT], xh[LN_VPT];
+        float g[LN_G][4], xh[LN_G][4];
         float s1 = 0.0f, s2 = 0.0f;
 #pragma unroll
-        for (int u = 0; u < LN_VPT; ++u) {
-            int c = lane + u * 32;
-            g[u] = 0.0f; xh[u] = 0.0f;
+        for (int u = 0; u < LN_G; ++u) {
+            int c = (lane + u * 32) * 4;
             if (c < C) {
-                float d = ldf(dyr + c) * invP;
-                xh[u] = (ldf(xr + c) - mu) * rs;
-                dg[u] += d * xh[u];
-                db[u] += d;
-                g[u] = d * gamma[c];
-                s1 += g[u];
-                s2 += g[u] * xh[u];
+                float d[4], xv[4];
+                load_vec<4>(dyr + c, d);
+                load_vec<4>(xr + c, xv);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float dd = d[j] * invP;
+                    xh[u][j] = (xv[j] - mu) * rs;
+                    dg[u][j] += dd * xh[u][j];
+                    db[u][j] += dd;
+                    g[u][j] = dd * gm[u][j];
+                    s1 += g[u][j];
+                    s2 += g[u][j] * xh[u][j];
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { g[u][j] = 0.0f; xh[u][j] = 0.0f; }
             }
         }
         s1 = warp_sum(s1) / C;
@@ -92,21 +132,31 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict_
         const T* rr = has_res ? dres + ((size_t)b * Tr + t / res_stride) * C : nullptr;
         T* dxr = dx + row * C;
 #pragma unroll
-        for (int u = 0; u < LN_VPT; ++u) {
-            int c = lane + u * 32;
+        for (int u = 0; u < LN_G; ++u) {
+            int c = (lane + u * 32) * 4;
             if (c < C) {
-                float v = rs * (g[u] - s1 - xh[u] * s2);
-                if (has_res) v += ldf(rr + c);
-                stf(dxr + c, v);
+                float o[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o[j] = rs * (g[u][j] - s1 - xh[u][j] * s2);
+                if (has_res) {
+                    float r4[4];
+                    load_vec<4>(rr + c, r4);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) o[j] += r4[j];
+                }
+                store_vec<4>(dxr + c, o);
             }
         }
     }
     for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) red[c] = 0.0f;
     __syncthreads();
 #pragma unroll
-    for (int u = 0; u < LN_VPT; ++u) {
-        int c = lane + u * 32;
-        if (c < C) { atomicAdd(&red[c], dg[u]); atomicAdd(&red[C + c], db[u]); }
+    for (int u = 0; u < LN_G; ++u) {
+        int c = (lane + u * 32) * 4;
+        if (c < C) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { atomicAdd(&red[c + j], dg[u][j]); atomicAdd(&red[C + c + j], db[u][j]); }
+        }
     }
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -115,31 +165,45 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict_
     }
 }
 
-template <typename T>
+template <typename T, int V>
 __global__ void upsample_add_kernel(const T* __restrict__ x, const T* __restrict__ o, T* __restrict__ y, int Tn, int Tp, int C,
                                     int P, long long total) {
+    const int Cv = C / V;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        int c = (int)(i % C);
-        long long row = i / C;
+        int c = (int)(i % Cv) * V;
+        long long row = i / Cv;
         int t = (int)(row % Tn);
         long long b = row / Tn;
-        stf(y + i, ldf(x + i) + ldf(o + (b * Tp + t / P) * C + c));
+        float a[V], w[V];
+        load_vec<V>(x + row * C + c, a);
+        load_vec<V>(o + (b * Tp + t / P) * C + c, w);
+#pragma unroll
+        for (int j = 0; j < V; ++j) a[j] += w[j];
+        store_vec<V>(y + row * C + c, a);
     }
 }
 
-template <typename T>
+template <typename T, int V>
 __global__ void pool_sum_kernel(const T* __restrict__ dy, T* __restrict__ dout, int Tn, int Tp, int C, int P, long long total) {
+    const int Cv = C / V;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        int c = (int)(i % C);
-        long long row = i / C;
+        int c = (int)(i % Cv) * V;
+        long long row = i / Cv;
         int tp = (int)(row % Tp);
         long long b = row / Tp;
-        float s = 0.0f;
+        float s[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) s[j] = 0.0f;
         for (int p = 0; p < P; ++p) {
             int t = tp * P + p;
-            if (t < Tn) s += ldf(dy + (b * Tn + t) * C + c);
+            if (t < Tn) {
+                float a[V];
+                load_vec<V>(dy + (b * Tn + t) * C + c, a);
+#pragma unroll
+                for (int j = 0; j < V; ++j) s[j] += a[j];
+            }
         }
-        stf(dout + i, s);
+        store_vec<V>(dout + row * C + c, s);
     }
 }
 
@@ -194,38 +258,48 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const T* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Column reductions over [rows, C] (C contiguous): thread x owns one channel, thread y strides rows.
-// F(row, c) returns up to two values to be summed per channel.
+// Column reductions over [rows, C] (C contiguous): thread x owns V consecutive channels, thread y strides rows.
+// F(row, c0, v0[V], v1[V]) produces up to two values per channel to be summed.
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int CR_X = 32, CR_Y = 16;
 
-template <typename F>
+template <typename F, int V>
 __global__ void __launch_bounds__(CR_X* CR_Y) colreduce_kernel(F f, long long rows, int C, long long rows_per_block,
                                                                float* __restrict__ out0, float* __restrict__ out1, float alpha) {
-    __shared__ float s0[CR_Y][CR_X + 1];
-    __shared__ float s1[CR_Y][CR_X + 1];
-    const int c = blockIdx.x * CR_X + threadIdx.x;
+    __shared__ float s0[CR_Y][CR_X * V + 1];
+    __shared__ float s1[CR_Y][CR_X * V + 1];
+    const int c = (blockIdx.x * CR_X + threadIdx.x) * V;
     const long long r0 = (long long)blockIdx.y * rows_per_block;
     const long long r1 = min(rows, r0 + rows_per_block);
-    float a0 = 0.0f, a1 = 0.0f;
-    if (c < C) {
-        for (long long r = r0 + threadIdx.y; r < r1; r += CR_Y) { float v0, v1; f(r, c, v0, v1); a0 += v0; a1 += v1; }
-    }
-    s0[threadIdx.y][threadIdx.x] = a0;
-    s1[threadIdx.y][threadIdx.x] = a1;
-    __syncthreads();
-    if (threadIdx.y == 0 && c < C) {
-        float t0 = 0.0f, t1 = 0.0f;
+    float a0[V], a1[V];
 #pragma unroll
-        for (int y = 0; y < CR_Y; ++y) { t0 += s0[y][threadIdx.x]; t1 += s1[y][threadIdx.x]; }
-        atomicAdd(out0 + c, alpha * t0);
-        if (out1) atomicAdd(out1 + c, alpha * t1);
+    for (int j = 0; j < V; ++j) { a0[j] = 0.0f; a1[j] = 0.0f; }
+    if (c < C) {
+        for (long long r = r0 + threadIdx.y; r < r1; r += CR_Y) {
+            float v0[V], v1[V];
+            f(r, c, v0, v1);
+#pragma unroll
+            for (int j = 0; j < V; ++j) { a0[j] += v0[j]; a1[j] += v1[j]; }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < V; ++j) { s0[threadIdx.y][threadIdx.x * V + j] = a0[j]; s1[threadIdx.y][threadIdx.x * V + j] = a1[j]; }
+    __syncthreads();
+    for (int cc = threadIdx.y * CR_X + threadIdx.x; cc < CR_X * V; cc += CR_X * CR_Y) {
+        const int cg = blockIdx.x * CR_X * V + cc;
+        if (cg < C) {
+            float t0 = 0.0f, t1 = 0.0f;
+#pragma unroll
+            for (int y = 0; y < CR_Y; ++y) { t0 += s0[y][cc]; t1 += s1[y][cc]; }
+            atomicAdd(out0 + cg, alpha * t0);
+            if (out1) atomicAdd(out1 + cg, alpha * t1);
+        }
     }
 }
 
-template <typename F>
+template <int V, typename F>
 int launch_colreduce(const F& f, long long rows, int C, float* out0, float* out1, float alpha, cudaStream_t st) {
-    int gx = cdiv(C, CR_X);
+    int gx = cdiv(C, CR_X * V);
     long long want = cdivll(148 * 8, gx);
     long long nchunk = min(want, cdivll(rows, CR_Y * 4));
     if (nchunk < 1) nchunk = 1;
@@ -233,35 +307,53 @@ int launch_colreduce(const F& f, long long rows, int C, float* out0, float* out1
     long long rpb = cdivll(rows, nchunk);
     nchunk = cdivll(rows, rpb);
     dim3 grid(gx, (unsigned)nchunk), block(CR_X, CR_Y);
-    colreduce_kernel<F><<<grid, block, 0, st>>>(f, rows, C, rpb, out0, out1, alpha);
+    colreduce_kernel<F, V><<<grid, block, 0, st>>>(f, rows, C, rpb, out0, out1, alpha);
     return 0;
 }
 
-template <typename T>
+template <typename T, int V>
 struct ColsumF {
     const T* x; long long ldx;
-    __device__ __forceinline__ void operator()(long long r, int c, float& v0, float& v1) const { v0 = ldf(x + r * ldx + c); v1 = 0.0f; }
+    __device__ __forceinline__ void operator()(long long r, int c, float (&v0)[V], float (&v1)[V]) const {
+        load_vec<V>(x + r * ldx + c, v0);
+#pragma unroll
+        for (int j = 0; j < V; ++j) v1[j] = 0.0f;
+    }
 };
-template <typename T>
+template <typename T, int V>
 struct StatsF {
     const T* x; int C;
-    __device__ __forceinline__ void operator()(long long r, int c, float& v0, float& v1) const { float v = ldf(x + r * C + c); v0 = v; v1 = v * v; }
+    __device__ __forceinline__ void operator()(long long r, int c, float (&v0)[V], float (&v1)[V]) const {
+        load_vec<V>(x + r * C + c, v0);
+#pragma unroll
+        for (int j = 0; j < V; ++j) v1[j] = v0[j] * v0[j];
+    }
 };
 
 __device__ __forceinline__ float act_fwd(float z, int act) { return act == AVEC_ACT_RELU ? fmaxf(z, 0.0f) : (act == AVEC_ACT_SWISH ? swishf_(z) : z); }
 __device__ __forceinline__ float act_bwd(float z, int act) { return act == AVEC_ACT_RELU ? (z > 0.0f ? 1.0f : 0.0f) : (act == AVEC_ACT_SWISH ? dswishf_(z) : 1.0f); }
 
-template <typename T>
+template <typename T, int V>
 struct BnBwdF {
     const T* dy; const T* u; const T* res; const float* scale; const float* shift; const float* mean; const float* rstd; int C; int act;
-    __device__ __forceinline__ void operator()(long long r, int c, float& v0, float& v1) const {
+    __device__ __forceinline__ void operator()(long long r, int c, float (&v0)[V], float (&v1)[V]) const {
         size_t i = (size_t)r * C + c;
-        float uu = ldf(u + i);
-        float z = scale[c] * uu + shift[c];
-        if (res) z += ldf(res + i);
-        float dz = ldf(dy + i) * act_bwd(z, act);
-        v0 = dz;
-        v1 = dz * (uu - mean[c]) * rstd[c];
+        float uu[V], d[V], rr[V], sc[V], sh[V], mu[V], rs[V];
+        load_vec<V>(u + i, uu);
+        load_vec<V>(dy + i, d);
+        load_vec<V>(scale + c, sc);
+        load_vec<V>(shift + c, sh);
+        load_vec<V>(mean + c, mu);
+        load_vec<V>(rstd + c, rs);
+        if (res) load_vec<V>(res + i, rr);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            float z = sc[j] * uu[j] + sh[j];
+            if (res) z += rr[j];
+            float dz = d[j] * act_bwd(z, act);
+            v0[j] = dz;
+            v1[j] = dz * (uu[j] - mu[j]) * rs[j];
+        }
     }
 };
 
@@ -295,48 +387,79 @@ __global__ void bn_eval_affine_kernel(const float* __restrict__ gamma, const flo
     shift[c] = b - rmean[c] * g * rs;
 }
 
-template <typename T>
+template <typename T, int V>
 __global__ void bn_apply_kernel(const T* __restrict__ u, const float* __restrict__ scale, const float* __restrict__ shift,
-                                const T* __restrict__ res, T* __restrict__ y, long long total, int C, int act) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        int c = (int)(i % C);
-        float z = scale[c] * ldf(u + i) + shift[c];
-        if (res) z += ldf(res + i);
-        stf(y + i, act_fwd(z, act));
+                                const T* __restrict__ res, T* __restrict__ y, long long totalv, int C, int act) {
+    const int Cv = C / V;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < totalv; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % Cv) * V;
+        const size_t e = (size_t)i * V;
+        float uu[V], sc[V], sh[V], rr[V];
+        load_vec<V>(u + e, uu);
+        load_vec<V>(scale + c, sc);
+        load_vec<V>(shift + c, sh);
+        if (res) load_vec<V>(res + e, rr);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            float z = sc[j] * uu[j] + sh[j];
+            if (res) z += rr[j];
+            uu[j] = act_fwd(z, act);
+        }
+        store_vec<V>(y + e, uu);
     }
 }
 
-template <typename T>
+template <typename T, int V>
 __global__ void bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ u, const float* __restrict__ scale,
                                     const float* __restrict__ shift, const T* __restrict__ res, const float* __restrict__ mean,
                                     const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ sums,
-                                    T* __restrict__ du, T* __restrict__ dres, long long total, int C, int act, float inv_count) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        int c = (int)(i % C);
-        float uu = ldf(u + i);
-        float z = scale[c] * uu + shift[c];
-        if (res) z += ldf(res + i);
-        float dz = ldf(dy + i) * act_bwd(z, act);
-        float xh = (uu - mean[c]) * rstd[c];
-        float g = gamma ? gamma[c] : 1.0f;
-        stf(du + i, g * rstd[c] * (dz - sums[c] * inv_count - xh * sums[C + c] * inv_count));
-        if (dres) stf(dres + i, dz);
+                                    T* __restrict__ du, T* __restrict__ dres, long long totalv, int C, int act, float inv_count) {
+    const int Cv = C / V;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < totalv; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % Cv) * V;
+        const size_t e = (size_t)i * V;
+        float uu[V], d[V], rr[V], sc[V], sh[V], mu[V], rs[V], g[V], s0[V], s1[V], o[V], dzv[V];
+        load_vec<V>(u + e, uu);
+        load_vec<V>(dy + e, d);
+        load_vec<V>(scale + c, sc);
+        load_vec<V>(shift + c, sh);
+        load_vec<V>(mean + c, mu);
+        load_vec<V>(rstd + c, rs);
+        load_vec<V>(sums + c, s0);
+        load_vec<V>(sums + C + c, s1);
+        if (gamma) load_vec<V>(gamma + c, g);
+        if (res) load_vec<V>(res + e, rr);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            float z = sc[j] * uu[j] + sh[j];
+            if (res) z += rr[j];
+            float dz = d[j] * act_bwd(z, act);
+            float xh = (uu[j] - mu[j]) * rs[j];
+            o[j] = (gamma ? g[j] : 1.0f) * rs[j] * (dz - s0[j] * inv_count - xh * s1[j] * inv_count);
+            dzv[j] = dz;
+        }
+        store_vec<V>(du + e, o);
+        if (dres) store_vec<V>(dres + e, dzv);
     }
 }
 
 // BN + ReLU + MaxPool 3x3 / stride 2 / zero pad 1 (post-ReLU values are >= 0, so the zero padding never wins a strict max)
-template <typename T>
+template <typename T, int V>
 __global__ void bn_relu_maxpool_fwd_kernel(const T* __restrict__ u, const float* __restrict__ scale, const float* __restrict__ shift,
-                                           T* __restrict__ y, uint8_t* __restrict__ idx, int Hi, int Wi, int C, int Ho, int Wo, long long total) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        int c = (int)(i % C);
-        long long t = i / C;
+                                           T* __restrict__ y, uint8_t* __restrict__ idx, int Hi, int Wi, int C, int Ho, int Wo, long long totalv) {
+    const int Cv = C / V;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < totalv; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % Cv) * V;
+        long long t = i / Cv;
         int wo = (int)(t % Wo); t /= Wo;
         int ho = (int)(t % Ho);
         long long n = t / Ho;
-        float best = 0.0f;  // the zero padding / ReLU floor
-        int bi = 255;
-        const float sc = scale[c], sh = shift[c];
+        float best[V], sc[V], sh[V];
+        int bi[V];
+        load_vec<V>(scale + c, sc);
+        load_vec<V>(shift + c, sh);
+#pragma unroll
+        for (int j = 0; j < V; ++j) { best[j] = 0.0f; bi[j] = 255; }   // the zero padding / ReLU floor
 #pragma unroll
         for (int kh = 0; kh < 3; ++kh) {
             int hi = ho * 2 + kh - 1;
@@ -345,26 +468,35 @@ __global__ void bn_relu_maxpool_fwd_kernel(const T* __restrict__ u, const float*
             for (int kw = 0; kw < 3; ++kw) {
                 int wi = wo * 2 + kw - 1;
                 if ((unsigned)wi >= (unsigned)Wi) continue;
-                float z = sc * ldf(u + ((n * Hi + hi) * Wi + wi) * C + c) + sh;
-                if (z > best) { best = z; bi = kh * 3 + kw; }
+                float uu[V];
+                load_vec<V>(u + ((n * Hi + hi) * Wi + wi) * C + c, uu);
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    float z = sc[j] * uu[j] + sh[j];
+                    if (z > best[j]) { best[j] = z; bi[j] = kh * 3 + kw; }
+                }
             }
         }
-        stf(y + i, best);
-        idx[i] = (uint8_t)bi;
+        store_vec<V>(y + (size_t)i * V, best);
+#pragma unroll
+        for (int j = 0; j < V; ++j) idx[(size_t)i * V + j] = (uint8_t)bi[j];
     }
 }
 
 // gather-form backward: input site (hi,wi) receives dy of every window whose saved argmax is this site (z > 0 there)
-template <typename T>
+template <typename T, int V>
 __global__ void bn_relu_maxpool_bwd_kernel(const T* __restrict__ dy, const uint8_t* __restrict__ idx, T* __restrict__ dz, int Hi,
-                                           int Wi, int C, int Ho, int Wo, long long total) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        int c = (int)(i % C);
-        long long t = i / C;
+                                           int Wi, int C, int Ho, int Wo, long long totalv) {
+    const int Cv = C / V;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < totalv; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % Cv) * V;
+        long long t = i / Cv;
         int wi = (int)(t % Wi); t /= Wi;
         int hi = (int)(t % Hi);
         long long n = t / Hi;
-        float acc = 0.0f;
+        float acc[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc[j] = 0.0f;
         // windows ho with ho*2+kh-1 == hi  ->  kh = hi+1-2*ho in [0,3)
         for (int kh = 0; kh < 3; ++kh) {
             int a = hi + 1 - kh;
@@ -377,10 +509,21 @@ __global__ void bn_relu_maxpool_bwd_kernel(const T* __restrict__ dy, const uint8
                 int wo = b >> 1;
                 if (wo >= Wo) continue;
                 size_t o = ((size_t)(n * Ho + ho) * Wo + wo) * C + c;
-                if (idx[o] == kh * 3 + kw) acc += ldf(dy + o);
+                float d[V];
+                load_vec<V>(dy + o, d);
+                const int code = kh * 3 + kw;
+                if (V == 8) {
+                    uint2 w = *reinterpret_cast<const uint2*>(idx + o);
+#pragma unroll
+                    for (int j = 0; j < V; ++j) { uint32_t word = j < 4 ? w.x : w.y; if ((int)((word >> ((j & 3) * 8)) & 255u) == code) acc[j] += d[j]; }
+                } else {
+                    uint32_t w = *reinterpret_cast<const uint32_t*>(idx + o);
+#pragma unroll
+                    for (int j = 0; j < V; ++j) if ((int)((w >> ((j & 3) * 8)) & 255u) == code) acc[j] += d[j];
+                }
             }
         }
-        stf(dz + i, acc);
+        store_vec<V>(dz + (size_t)i * V, acc);
     }
 }
 
@@ -411,6 +554,14 @@ __global__ void convert_kernel(const TI* __restrict__ src, long long lds, TO* __
         stf(dst + r * ldd + c, ldf(src + r * lds + c));
     }
 }
+// contiguous fp32 -> bf16, 8 elements per thread
+__global__ void convert_f32_bf16_vec_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long totalv) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < totalv; i += (long long)gridDim.x * blockDim.x) {
+        float v[8];
+        load_vec<8>(src + i * 8, v);
+        store_vec<8>(dst + i * 8, v);
+    }
+}
 
 inline int ew_blocks(long long total, int threads = 256) {
     long long b = cdivll(total, threads);
@@ -422,7 +573,7 @@ inline int ew_blocks(long long total, int threads = 256) {
 
 extern "C" int avec_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int B,
                                   int T, int C, int P, float eps, int dtype, avec_stream_t stream) {
-    AVEC_CHECK_ARG(x && gamma && beta && y && mean && rstd && B > 0 && T > 0 && P >= 1 && C > 0 && C <= 32 * LN_VPT);
+    AVEC_CHECK_ARG(x && gamma && beta && y && mean && rstd && B > 0 && T > 0 && P >= 1 && C > 0 && C <= 128 * LN_G && C % 4 == 0);
     const int Tp = cdiv(T, P);
     const long long warps = (long long)B * Tp;
     const int blocks = (int)cdivll(warps * 32, 256);
@@ -435,7 +586,7 @@ extern "C" int avec_layernorm_fwd(const void* x, const float* gamma, const float
 extern "C" int avec_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
                                   const void* dres, int res_stride, void* dx, float* dgamma, float* dbeta, int B, int T, int C,
                                   int P, int dtype, avec_stream_t stream) {
-    AVEC_CHECK_ARG(dy && x && gamma && mean && rstd && dx && B > 0 && T > 0 && P >= 1 && C > 0 && C <= 32 * LN_VPT);
+    AVEC_CHECK_ARG(dy && x && gamma && mean && rstd && dx && B > 0 && T > 0 && P >= 1 && C > 0 && C <= 128 * LN_G && C % 4 == 0);
     AVEC_CHECK_ARG(!dres || res_stride >= 1);
     const int Tp = cdiv(T, P);
     const long long rows = (long long)B * T;
@@ -451,8 +602,8 @@ extern "C" int avec_upsample_add(const void* x, const void* o, void* y, int B, i
                                  avec_stream_t stream) {
     AVEC_CHECK_ARG(x && o && y && B > 0 && T > 0 && P >= 1 && Tp == cdiv(T, P));
     long long total = (long long)B * T * C;
-    AVEC_DISPATCH_DTYPE(dtype, Tt, (upsample_add_kernel<Tt><<<ew_blocks(total), 256, 0, as_stream(stream)>>>(
-        (const Tt*)x, (const Tt*)o, (Tt*)y, T, Tp, C, P, total)));
+    AVEC_DISPATCH_DTYPE_VEC(dtype, C, Tt, V, (upsample_add_kernel<Tt, V><<<ew_blocks(total / V), 256, 0, as_stream(stream)>>>(
+        (const Tt*)x, (const Tt*)o, (Tt*)y, T, Tp, C, P, total / V)));
     AVEC_LAUNCH_CHECK();
     return AVEC_OK;
 }
@@ -460,8 +611,8 @@ extern "C" int avec_upsample_add(const void* x, const void* o, void* y, int B, i
 extern "C" int avec_pool_sum(const void* dy, void* dout, int B, int T, int Tp, int C, int P, int dtype, avec_stream_t stream) {
     AVEC_CHECK_ARG(dy && dout && B > 0 && T > 0 && P >= 1 && Tp == cdiv(T, P));
     long long total = (long long)B * Tp * C;
-    AVEC_DISPATCH_DTYPE(dtype, Tt, (pool_sum_kernel<Tt><<<ew_blocks(total), 256, 0, as_stream(stream)>>>(
-        (const Tt*)dy, (Tt*)dout, T, Tp, C, P, total)));
+    AVEC_DISPATCH_DTYPE_VEC(dtype, C, Tt, V, (pool_sum_kernel<Tt, V><<<ew_blocks(total / V), 256, 0, as_stream(stream)>>>(
+        (const Tt*)dy, (Tt*)dout, T, Tp, C, P, total / V)));
     AVEC_LAUNCH_CHECK();
     return AVEC_OK;
 }
@@ -498,7 +649,9 @@ extern "C" int avec_colsum(const void* x, int dtype, long long rows, int C, long
     AVEC_CHECK_ARG(x && out && rows > 0 && C > 0 && ldx >= C);
     cudaStream_t st = as_stream(stream);
     if (!accumulate) { zero_kernel<<<cdiv(C, 256), 256, 0, st>>>(out, C); avec_count_launch(); }
-    AVEC_DISPATCH_DTYPE(dtype, Tt, { ColsumF<Tt> f{(const Tt*)x, ldx}; launch_colreduce(f, rows, C, out, nullptr, alpha, st); });
+    if (C % 4 != 0 || ldx % 4 != 0) return AVEC_ERR_INVALID;
+    if (C % 8 == 0 && ldx % 8 == 0) { AVEC_DISPATCH_DTYPE(dtype, Tt, { ColsumF<Tt, 8> f{(const Tt*)x, ldx}; launch_colreduce<8>(f, rows, C, out, nullptr, alpha, st); }); }
+    else { AVEC_DISPATCH_DTYPE(dtype, Tt, { ColsumF<Tt, 4> f{(const Tt*)x, ldx}; launch_colreduce<4>(f, rows, C, out, nullptr, alpha, st); }); }
     AVEC_LAUNCH_CHECK();
     return AVEC_OK;
 }
@@ -506,7 +659,7 @@ extern "C" int avec_colsum(const void* x, int dtype, long long rows, int C, long
 extern "C" int avec_bn_stats(const void* u, int dtype, long long rows, int C, float* stats, avec_stream_t stream) {
     AVEC_CHECK_ARG(u && stats && rows > 0 && C > 0);
     cudaStream_t st = as_stream(stream);
-    AVEC_DISPATCH_DTYPE(dtype, Tt, { StatsF<Tt> f{(const Tt*)u, C}; launch_colreduce(f, rows, C, stats, stats + C, 1.0f, st); });
+    AVEC_DISPATCH_DTYPE_VEC(dtype, C, Tt, V, { StatsF<Tt, V> f{(const Tt*)u, C}; launch_colreduce<V>(f, rows, C, stats, stats + C, 1.0f, st); });
     AVEC_LAUNCH_CHECK();
     return AVEC_OK;
 }
@@ -534,8 +687,8 @@ extern "C" int avec_bn_apply(const void* u, const float* scale, const float* shi
                              int act, int dtype, avec_stream_t stream) {
     AVEC_CHECK_ARG(u && scale && shift && y && rows > 0 && C > 0);
     long long total = rows * C;
-    AVEC_DISPATCH_DTYPE(dtype, Tt, (bn_apply_kernel<Tt><<<ew_blocks(total), 256, 0, as_stream(stream)>>>(
-        (const Tt*)u, scale, shift, (const Tt*)res, (Tt*)y, total, C, act)));
+    AVEC_DISPATCH_DTYPE_VEC(dtype, C, Tt, V, (bn_apply_kernel<Tt, V><<<ew_blocks(total / V), 256, 0, as_stream(stream)>>>(
+        (const Tt*)u, scale, shift, (const Tt*)res, (Tt*)y, total / V, C, act)));
     AVEC_LAUNCH_CHECK();
     return AVEC_OK;
 }
@@ -545,9 +698,9 @@ extern "C" int avec_bn_bwd_reduce(const void* dy, const void* u, const float* sc
                                   avec_stream_t stream) {
     AVEC_CHECK_ARG(dy && u && scale && shift && mean && rstd && sums && rows > 0 && C > 0);
     cudaStream_t st = as_stream(stream);
-    AVEC_DISPATCH_DTYPE(dtype, Tt, {
-        BnBwdF<Tt> f{(const Tt*)dy, (const Tt*)u, (const Tt*)res, scale, shift, mean, rstd, C, act};
-        launch_colreduce(f, rows, C, sums, sums + C, 1.0f, st);
+    AVEC_DISPATCH_DTYPE_VEC(dtype, C, Tt, V, {
+        BnBwdF<Tt, V> f{(const Tt*)dy, (const Tt*)u, (const Tt*)res, scale, shift, mean, rstd, C, act};
+        launch_colreduce<V>(f, rows, C, sums, sums + C, 1.0f, st);
     });
     AVEC_LAUNCH_CHECK();
     return AVEC_OK;
@@ -558,8 +711,8 @@ extern "C" int avec_bn_bwd_apply(const void* dy, const void* u, const float* sca
                                  long long rows, int C, int act, int dtype, avec_stream_t stream) {
     AVEC_CHECK_ARG(dy && u && scale && shift && mean && rstd && sums && du && rows > 0 && C > 0);
     long long total = rows * C;
-    AVEC_DISPATCH_DTYPE(dtype, Tt, (bn_bwd_apply_kernel<Tt><<<ew_blocks(total), 256, 0, as_stream(stream)>>>(
-        (const Tt*)dy, (const Tt*)u, scale, shift, (const Tt*)res, mean, rstd, gamma, sums, (Tt*)du, (Tt*)dres, total, C, act,
+    AVEC_DISPATCH_DTYPE_VEC(dtype, C, Tt, V, (bn_bwd_apply_kernel<Tt, V><<<ew_blocks(total / V), 256, 0, as_stream(stream)>>>(
+        (const Tt*)dy, (const Tt*)u, scale, shift, (const Tt*)res, mean, rstd, gamma, sums, (Tt*)du, (Tt*)dres, total / V, C, act,
         (float)(1.0 / (double)rows))));
     AVEC_LAUNCH_CHECK();
     return AVEC_OK;
@@ -569,8 +722,8 @@ extern "C" int avec_bn_relu_maxpool_fwd(const void* u, const float* scale, const
                                         int Wi, int C, int Ho, int Wo, int dtype, avec_stream_t stream) {
     AVEC_CHECK_ARG(u && scale && shift && y && idx && N > 0 && Ho == (Hi - 1) / 2 + 1 && Wo == (Wi - 1) / 2 + 1);
     long long total = (long long)N * Ho * Wo * C;
-    AVEC_DISPATCH_DTYPE(dtype, Tt, (bn_relu_maxpool_fwd_kernel<Tt><<<ew_blocks(total), 256, 0, as_stream(stream)>>>(
-        (const Tt*)u, scale, shift, (Tt*)y, idx, Hi, Wi, C, Ho, Wo, total)));
+    AVEC_DISPATCH_DTYPE_VEC(dtype, C, Tt, V, (bn_relu_maxpool_fwd_kernel<Tt, V><<<ew_blocks(total / V), 256, 0, as_stream(stream)>>>(
+        (const Tt*)u, scale, shift, (Tt*)y, idx, Hi, Wi, C, Ho, Wo, total / V)));
     AVEC_LAUNCH_CHECK();
     return AVEC_OK;
 }
@@ -579,8 +732,8 @@ extern "C" int avec_bn_relu_maxpool_bwd(const void* dy, const uint8_t* idx, void
                                         int dtype, avec_stream_t stream) {
     AVEC_CHECK_ARG(dy && idx && dz && N > 0);
     long long total = (long long)N * Hi * Wi * C;
-    AVEC_DISPATCH_DTYPE(dtype, Tt, (bn_relu_maxpool_bwd_kernel<Tt><<<ew_blocks(total), 256, 0, as_stream(stream)>>>(
-        (const Tt*)dy, idx, (Tt*)dz, Hi, Wi, C, Ho, Wo, total)));
+    AVEC_DISPATCH_DTYPE_VEC(dtype, C, Tt, V, (bn_relu_maxpool_bwd_kernel<Tt, V><<<ew_blocks(total / V), 256, 0, as_stream(stream)>>>(
+        (const Tt*)dy, idx, (Tt*)dz, Hi, Wi, C, Ho, Wo, total / V)));
     AVEC_LAUNCH_CHECK();
     return AVEC_OK;
 }
@@ -606,7 +759,10 @@ extern "C" int avec_convert(const void* src, int src_dtype, long long lds, void*
     long long total = rows * C;
     cudaStream_t st = as_stream(stream);
     int blocks = ew_blocks(total);
-    if (src_dtype == AVEC_F32 && dst_dtype == AVEC_BF16) convert_kernel<float, bf16><<<blocks, 256, 0, st>>>((const float*)src, lds, (bf16*)dst, ldd, C, total);
+    if (src_dtype == AVEC_F32 && dst_dtype == AVEC_BF16 && lds == C && ldd == C && total % 8 == 0 &&
+        ((uintptr_t)src & 31) == 0 && ((uintptr_t)dst & 15) == 0)
+        convert_f32_bf16_vec_kernel<<<ew_blocks(total / 8), 256, 0, st>>>((const float*)src, (bf16*)dst, total / 8);
+    else if (src_dtype == AVEC_F32 && dst_dtype == AVEC_BF16) convert_kernel<float, bf16><<<blocks, 256, 0, st>>>((const float*)src, lds, (bf16*)dst, ldd, C, total);
     else if (src_dtype == AVEC_BF16 && dst_dtype == AVEC_F32) convert_kernel<bf16, float><<<blocks, 256, 0, st>>>((const bf16*)src, lds, (float*)dst, ldd, C, total);
     else if (src_dtype == AVEC_F32 && dst_dtype == AVEC_F32) convert_kernel<float, float><<<blocks, 256, 0, st>>>((const float*)src, lds, (float*)dst, ldd, C, total);
     else if (src_dtype == AVEC_BF16 && dst_dtype == AVEC_BF16) convert_kernel<bf16, bf16><<<blocks, 256, 0, st>>>((const bf16*)src, lds, (bf16*)dst, ldd, C, total);

@@ -39,8 +39,12 @@ def compute_dtype():
 _wcache = {}
 
 
-def new_step():
+def new_step(arena_numel=0, device=None):
+    """start of a forward pass: drop the compute-dtype weight copies of the previous step and (optionally) allocate the
+    zero-initialised fp32 arena that gradient accumulators and BatchNorm statistics of this step are carved from"""
     _wcache.clear()
+    if arena_numel and device is not None:
+        ops.ARENA.begin(arena_numel, device)
 
 
 def wc(param, tag="plain", fn=None):
@@ -342,7 +346,7 @@ class AudioStemFn(Function):
         g = ops.make_geom(B, 1, F, 80, 1, Co, (1, 3, 3), (1, 2, 2), (0, 1, 1))
         wp = wc(cw, "stem2d", lambda w: w[:, 0].transpose(1, 2).reshape(w.shape[0], 9))
         sites = ops.geom_sites(g)
-        stats = torch.zeros((2 * Co,), device=wave.device, dtype=torch.float32) if training else None
+        stats = ops.zeros_f32((2 * Co,), wave.device) if training else None
         u = ops.conv_fwd(melc, wp, g, bias=cb, colstats=stats)
         bnbuf = _bn_buf(stats, bn_w, bn_b, rm, rv, sites, training, momentum)
         v = ops.bn_apply(u, bnbuf[0], bnbuf[1], L.ACT_SWISH)
@@ -377,7 +381,7 @@ class VideoStemFn(Function):
         g = ops.make_geom(B, T, H, W, 1, Co, (kt, kh, kw), (1, 2, 2), ((kt - 1) // 2, (kh - 1) // 2, (kw - 1) // 2))
         wp = wc(cw, "stem3d", lambda w: w.reshape(w.shape[0], -1))
         sites = ops.geom_sites(g)
-        stats = torch.zeros((2 * Co,), device=video.device, dtype=torch.float32) if training else None
+        stats = ops.zeros_f32((2 * Co,), video.device) if training else None
         u = ops.conv_fwd(xc, wp, g, bias=cb, colstats=stats)
         bnbuf = _bn_buf(stats, bn_w, bn_b, rm, rv, sites, training, momentum)
         y, idx = ops.bn_relu_maxpool_fwd(u, bnbuf[0], bnbuf[1], B * T, g.Ho, g.Wo, Co)
@@ -423,7 +427,7 @@ class ResBlockFn(Function):
         dev = x.device
 
         def st():
-            return torch.zeros((2 * Co,), device=dev, dtype=torch.float32) if training else None
+            return ops.zeros_f32((2 * Co,), dev) if training else None
 
         ga = ops.make_geom(N, 1, H, W, Ci, Co, (1, 3, 3), (1, stride, stride), (0, 1, 1))
         s1 = st()

@@ -18,6 +18,7 @@ class CTCLoss(nn.Module):
         if self.assert_shorter:
             assert bool((y_len <= logits_len.to(y_len.device)).all()), "ctc: label longer than logits"
         logp = F.log_softmax(logits.float(), dim=-1).transpose(0, 1)
+        # CPU length tensors are passed through untouched (no device sync: required under CUDA-graph capture)
         loss = F.ctc_loss(logp, y, logits_len.to(torch.long), y_len.to(torch.long), blank=self.blank, reduction="none",
                           zero_infinity=self.zero_infinity)
         return loss.mean() if self.reduction == "mean" else loss.sum()

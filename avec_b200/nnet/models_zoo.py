@@ -28,9 +28,12 @@ class Model(nn.Module):
     def num_params(self):
         return sum(p.numel() for p in self.parameters())
 
-    def _prepare(self):
+    def _prepare(self, device=None):
         check_dropout(self)
-        AF.new_step()
+        if getattr(self, "_arena_numel", None) is None:
+            # parameter gradients + BatchNorm statistics / reduction scratch + positional-embedding gradients
+            self._arena_numel = int(1.3 * self.num_params()) + (8 << 20)
+        AF.new_step(self._arena_numel if (device is not None and device.type == "cuda") else 0, device)
 
     def compute_loss(self, outputs, targets):
         """sum_k w_k * CTC(outputs[k]) with weights mapped to the outputs by position for lists (model.py:217) or by
@@ -54,7 +57,7 @@ class AudioEfficientConformerInterCTC(Model):
         self.encoder = networks.AudioEfficientConformerEncoder(vocab_size=vocab_size, att_type=att_type, interctc_blocks=interctc_blocks)
 
     def forward(self, inputs):
-        self._prepare()
+        self._prepare(inputs[0].device)
         x, lengths = inputs
         x, lengths, interctc_outputs = self.encoder(x, lengths)
         outputs = {"outputs": [x, lengths]}
@@ -69,7 +72,7 @@ class VisualEfficientConformerInterCTC(Model):
         assert test_augments is None, "flip TTA is an evaluation-time feature outside the hot path"
 
     def forward(self, inputs):
-        self._prepare()
+        self._prepare(inputs[0].device)
         video, video_lengths = inputs
         x, lengths, interctc_outputs = self.encoder(video, video_lengths)
         outputs = {"outputs": [x, lengths]}
@@ -85,7 +88,7 @@ class AudioVisualEfficientConformerInterCTC(Model):
             f_interctc_blocks=f_interctc_blocks)
 
     def forward(self, inputs):
-        self._prepare()
+        self._prepare(inputs[0].device)
         video, video_len, audio, audio_len = inputs
         x, lengths, interctc_outputs = self.encoder(video, video_len, audio, audio_len)
         outputs = {"outputs": [x, lengths]}

@@ -15,6 +15,11 @@ def set_gemm_impl(name):
     GEMM_IMPL = {"auto": L.IMPL_AUTO, "simt": L.IMPL_SIMT, "tcgen05": L.IMPL_TCGEN05}[name]
 
 
+def set_tma(enabled):
+    """diagnostics: False forces the gather producers of the tcgen05 GEMM even where TMA descriptors are possible"""
+    L.load().avec_set_tma(1 if enabled else 0)
+
+
 def _stream():
     return torch.cuda.current_stream().cuda_stream
 
@@ -31,6 +36,33 @@ def _cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
             raise RuntimeError("avec_b200 ops need CUDA tensors: the hot path has no CPU fallback")
+
+
+# ---- zero-initialised fp32 scratch (gradient accumulators, BatchNorm statistics): one memset per step instead of ~900
+class _Arena:
+    def __init__(self):
+        self.buf, self.off = None, 0
+
+    def begin(self, numel, device):
+        self.buf = torch.zeros(int(numel), device=device, dtype=torch.float32) if numel else None
+        self.off = 0
+
+    def take(self, shape, device):
+        n = 1
+        for d in shape:
+            n *= int(d)
+        if self.buf is not None and self.buf.device == torch.device(device) and self.off + n <= self.buf.numel():
+            out = self.buf[self.off:self.off + n].view(*shape)
+            self.off += (n + 3) // 4 * 4
+            return out
+        return torch.zeros(shape, device=device, dtype=torch.float32)
+
+
+ARENA = _Arena()
+
+
+def zeros_f32(shape, device):
+    return ARENA.take(tuple(shape) if isinstance(shape, (tuple, list)) else (shape,), device)
 
 
 def launch_count():
@@ -104,7 +136,7 @@ def linear_wgrad(dy, x, alpha=1.0):
     _cuda(dy, x)
     M, N = dy.shape
     K = x.shape[1]
-    dw = torch.zeros((N, K), device=dy.device, dtype=torch.float32)
+    dw = zeros_f32((N, K), dy.device)
     a = L.GemmArgs()
     a.mode, a.impl, a.M, a.N, a.K = L.GEMM_PLAIN, GEMM_IMPL, N, K, M
     a.A, a.sam, a.sak = dy.data_ptr(), 1, dy.stride(0)
@@ -119,7 +151,7 @@ def linear_wgrad(dy, x, alpha=1.0):
 def colsum(x, alpha=1.0):
     _cuda(x)
     rows, Cn = x.shape
-    out = torch.zeros((Cn,), device=x.device, dtype=torch.float32)
+    out = zeros_f32((Cn,), x.device)
     L.check(L.load().avec_colsum(x.data_ptr(), _dt(x), rows, Cn, x.stride(0), alpha, out.data_ptr(), 1, _stream()), "avec_colsum")
     return out
 
@@ -171,7 +203,7 @@ def conv_wgrad(dy, x, g):
     _cuda(dy, x)
     taps = g.KT * g.KH * g.KW
     sites = geom_sites(g, True)
-    dw = torch.zeros((g.Co, taps * g.C), device=dy.device, dtype=torch.float32)
+    dw = zeros_f32((g.Co, taps * g.C), dy.device)
     a = L.GemmArgs()
     a.mode, a.impl, a.M, a.N, a.K = L.GEMM_CONV_WGRAD, GEMM_IMPL, g.Co, taps * g.C, sites
     a.A, a.B, a.ab_dtype, a.g = dy.data_ptr(), x.data_ptr(), _dt(dy), g
@@ -199,8 +231,8 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, P=1, dres=None, res_stride=1):
     """returns dx [B,T,C], dgamma, dbeta (fp32).  dx += dres[b, t/res_stride] on frames t % res_stride == 0."""
     B, T, Cn = x.shape
     dx = torch.empty_like(x)
-    dg = torch.zeros((Cn,), device=x.device, dtype=torch.float32)
-    db = torch.zeros_like(dg)
+    dg = zeros_f32((Cn,), x.device)
+    db = zeros_f32((Cn,), x.device)
     L.check(L.load().avec_layernorm_bwd(dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
                                         _p(dres), res_stride, dx.data_ptr(), dg.data_ptr(), db.data_ptr(), B, T, Cn, P,
                                         _dt(x), _stream()), "avec_layernorm_bwd")
@@ -240,7 +272,7 @@ def softmax_bwd(dy, y, dadd=None, out_dtype=None):
 
 def bn_stats(u2d):
     rows, Cn = u2d.shape
-    stats = torch.zeros((2 * Cn,), device=u2d.device, dtype=torch.float32)
+    stats = zeros_f32((2 * Cn,), u2d.device)
     L.check(L.load().avec_bn_stats(u2d.data_ptr(), _dt(u2d), rows, Cn, stats.data_ptr(), _stream()), "avec_bn_stats")
     return stats
 
@@ -274,7 +306,7 @@ def bn_bwd(dy2d, u2d, bnbuf, gamma, act, res=None, want_dres=False):
     """BatchNorm (+activation, + residual add before it) backward with batch statistics.
     returns du, dres (or None), dgamma, dbeta."""
     rows, Cn = u2d.shape
-    sums = torch.zeros((2 * Cn,), device=u2d.device, dtype=torch.float32)
+    sums = zeros_f32((2 * Cn,), u2d.device)
     lib = L.load()
     L.check(lib.avec_bn_bwd_reduce(dy2d.data_ptr(), u2d.data_ptr(), bnbuf[0].data_ptr(), bnbuf[1].data_ptr(), _p(res),
                                    bnbuf[2].data_ptr(), bnbuf[3].data_ptr(), sums.data_ptr(), rows, Cn, act, _dt(u2d),
@@ -300,7 +332,7 @@ def relpos_attn_fwd(qkv, e, klen, qlen, B, T, H, d):
 def relpos_attn_bwd(do, qkv, e, probs, B, T, H, d):
     D = H * d
     dqkv = torch.empty_like(qkv)
-    de = torch.zeros((2 * T - 1, D), device=qkv.device, dtype=torch.float32)
+    de = zeros_f32((2 * T - 1, D), qkv.device)
     ws = torch.empty_like(probs)
     L.check(L.load().avec_relpos_attn_bwd(do.data_ptr(), qkv.data_ptr(), e.data_ptr(), probs.data_ptr(), ws.data_ptr(),
                                           dqkv.data_ptr(), de.data_ptr(), B, T, H, d, _dt(qkv), _stream()),
@@ -315,7 +347,7 @@ def glu_dwconv_fwd(pre, w, bias, stride, ksize=15, want_stats=True):
     pad = (ksize - 1) // 2
     To = (T + 2 * pad - ksize) // stride + 1
     u = torch.empty((B, To, Cn), device=pre.device, dtype=pre.dtype)
-    stats = torch.zeros((2 * Cn,), device=pre.device, dtype=torch.float32) if want_stats else None
+    stats = zeros_f32((2 * Cn,), pre.device) if want_stats else None
     L.check(L.load().avec_glu_dwconv_fwd(pre.data_ptr(), w.data_ptr(), _p(bias), u.data_ptr(), _p(stats), B, T, To, Cn, ksize,
                                          stride, pad, _dt(pre), _stream()), "avec_glu_dwconv_fwd")
     return u, stats
@@ -327,8 +359,8 @@ def glu_dwconv_bwd(du, pre, w, stride, ksize=15):
     pad = (ksize - 1) // 2
     To = du.shape[1]
     dpre = torch.empty_like(pre)
-    dw = torch.zeros((Cn, ksize), device=pre.device, dtype=torch.float32)
-    db = torch.zeros((Cn,), device=pre.device, dtype=torch.float32)
+    dw = zeros_f32((Cn, ksize), pre.device)
+    db = zeros_f32((Cn,), pre.device)
     L.check(L.load().avec_glu_dwconv_bwd(du.data_ptr(), pre.data_ptr(), w.data_ptr(), dpre.data_ptr(), dw.data_ptr(),
                                          db.data_ptr(), B, T, To, Cn, ksize, stride, pad, _dt(pre), _stream()),
             "avec_glu_dwconv_bwd")

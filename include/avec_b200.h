@@ -101,6 +101,8 @@ typedef struct avec_gemm_args {
 } avec_gemm_args;
 
 int avec_gemm(const avec_gemm_args* args, avec_stream_t stream);
+/* diagnostics: 0 forces the cp.async gather producers even where a TMA descriptor is possible (default 1) */
+void avec_set_tma(int enabled);
 
 /* out[n] (+)= alpha * sum_m x[m][n]      — bias gradients (autograd of the bias add in addmm / conv) */
 int avec_colsum(const void* x, int dtype, long long rows, int C, long long ldx, float alpha, float* out, int accumulate,

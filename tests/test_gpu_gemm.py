@@ -24,10 +24,12 @@ def _rand(*shape, dtype=torch.float32, seed=0):
 SHAPES = [(300, 180, 720), (257, 720, 180), (128, 256, 1024), (1000, 360, 1440), (70, 540, 180), (513, 256, 7200), (64, 256, 512)]
 
 
-@pytest.mark.parametrize("impl,dtype,tol", [("simt", torch.float32, 1e-5), ("simt", torch.bfloat16, 1e-2), ("tcgen05", torch.bfloat16, 1e-2)])
+@pytest.mark.parametrize("impl,dtype,tol", [("simt", torch.float32, 1e-5), ("simt", torch.bfloat16, 1e-2), ("tcgen05", torch.bfloat16, 1e-2),
+                                            ("tcgen05-gather", torch.bfloat16, 1e-2)])
 @pytest.mark.parametrize("M,K,N", SHAPES)
 def test_linear_fwd_dgrad_wgrad(impl, dtype, tol, M, K, N):
-    ops.set_gemm_impl(impl)
+    ops.set_tma(impl != "tcgen05-gather")
+    ops.set_gemm_impl(impl.split("-")[0])
     try:
         x, w, b = _rand(M, K, dtype=dtype, seed=1), _rand(N, K, dtype=dtype, seed=2) / K ** 0.5, _rand(N, seed=3)
         dy = _rand(M, N, dtype=dtype, seed=4)
@@ -52,18 +54,20 @@ def test_linear_fwd_dgrad_wgrad(impl, dtype, tol, M, K, N):
         _close(cs, 0.5 * dyf.sum(0), 1e-4 if dtype == torch.float32 else 1e-3)
     finally:
         ops.set_gemm_impl("auto")
+        ops.set_tma(True)
 
 
 CONVS = [  # N, H, W, Cin, Cout, k, stride
-    (3, 8, 8, 64, 64, 3, 1), (2, 11, 11, 64, 128, 3, 2), (3, 6, 6, 128, 256, 3, 2), (5, 3, 3, 512, 512, 3, 1),
+    (3, 8, 8, 64, 64, 3, 1), (37, 3, 3, 512, 512, 3, 1), (7, 6, 6, 256, 256, 3, 1), (3, 11, 11, 128, 128, 3, 1), (2, 22, 22, 64, 64, 3, 1), (2, 11, 11, 64, 128, 3, 2), (3, 6, 6, 128, 256, 3, 2), (5, 3, 3, 512, 512, 3, 1),
     (2, 11, 11, 64, 128, 1, 2), (4, 22, 22, 64, 64, 3, 1),
 ]
 
 
-@pytest.mark.parametrize("impl,dtype,tol", [("simt", torch.float32, 1e-5), ("tcgen05", torch.bfloat16, 1e-2)])
+@pytest.mark.parametrize("impl,dtype,tol", [("simt", torch.float32, 1e-5), ("tcgen05", torch.bfloat16, 1e-2), ("tcgen05-gather", torch.bfloat16, 1e-2)])
 @pytest.mark.parametrize("N,H,W,Ci,Co,k,s", CONVS)
 def test_conv2d_fwd_dgrad_wgrad(impl, dtype, tol, N, H, W, Ci, Co, k, s):
-    ops.set_gemm_impl(impl)
+    ops.set_tma(impl != "tcgen05-gather")
+    ops.set_gemm_impl(impl.split("-")[0])
     try:
         x = _rand(N, H, W, Ci, dtype=dtype, seed=1)
         w = (_rand(Co, Ci, k, k, seed=2) / (Ci * k * k) ** 0.5).to(dtype)
@@ -88,6 +92,7 @@ def test_conv2d_fwd_dgrad_wgrad(impl, dtype, tol, N, H, W, Ci, Co, k, s):
         _close(dw, wr.grad.permute(0, 2, 3, 1).reshape(Co, -1), tol if dtype == torch.bfloat16 else 1e-4)
     finally:
         ops.set_gemm_impl("auto")
+        ops.set_tma(True)
 
 
 @pytest.mark.parametrize("impl,dtype,tol", [("simt", torch.float32, 1e-5), ("tcgen05", torch.bfloat16, 1e-2)])
