@@ -4,6 +4,7 @@
 // log(x + 1e-9), as called by AudioPreprocessing.forward (reference nnet/preprocessing.py:57-85).
 // cuFFT-free: one warp = one frame, radix-2 DIT in shared memory; HBM traffic = 4 B/sample in, 320 B/frame out.
 #include "common.cuh"
+#include <algorithm>
 
 namespace {
 
@@ -70,7 +71,58 @@ __global__ void __launch_bounds__(FR_PER_CTA * 32) stft_mel_log_kernel(const flo
     }
 }
 
+// single-channel im2col: col[site][tap] = x[n, to*st+kt-pt, ho*sh+kh-ph, wo*sw+kw-pw] (0 outside), taps padded with zeros to
+// Kpad.  One warp per output site, lane = 8 consecutive taps (one 16-byte store); the input (100 MB at B = 64) lives in L2.
+template <typename T>
+__global__ void __launch_bounds__(256) im2col_c1_kernel(const T* __restrict__ x, T* __restrict__ col, ConvGeom g, int taps, int Kpad,
+                                                        long long sites) {
+    __shared__ int tapofs[256];
+    for (int tap = threadIdx.x; tap < 256; tap += blockDim.x) {
+        int t = tap;
+        const int kw = t % g.KW; t /= g.KW; const int kh = t % g.KH; const int kt = t / g.KH;
+        tapofs[tap] = kt | (kh << 8) | (kw << 16);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long site = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; site < sites; site += warps) {
+        long long s = site;
+        const int wo = (int)(s % g.Wo); s /= g.Wo;
+        const int ho = (int)(s % g.Ho); s /= g.Ho;
+        const int to = (int)(s % g.To); const int n = (int)(s / g.To);
+        const int t0 = to * g.st - g.pt, h0 = ho * g.sh - g.ph, w0 = wo * g.sw - g.pw;
+        for (int c0 = lane * 8; c0 < Kpad; c0 += 256) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int tap = c0 + j;
+                float val = 0.0f;
+                if (tap < taps) {
+                    const int o = tapofs[tap];
+                    const int ti = t0 + (o & 255), hi = h0 + ((o >> 8) & 255), wi = w0 + (o >> 16);
+                    if ((unsigned)ti < (unsigned)g.Ti && (unsigned)hi < (unsigned)g.Hi && (unsigned)wi < (unsigned)g.Wi)
+                        val = ldf(x + (((long long)n * g.Ti + ti) * g.Hi + hi) * g.Wi + wi);
+                }
+                v[j] = val;
+            }
+            store_vec<8>(col + site * Kpad + c0, v);
+        }
+    }
+}
+
 }  // namespace
+
+extern "C" int avec_im2col_c1(const void* x, void* col, const avec_conv_geom* geom, int Kpad, int dtype, avec_stream_t stream) {
+    AVEC_CHECK_ARG(x && col && geom && geom->C == 1 && Kpad % 8 == 0);
+    ConvGeom g = make_geom(*geom);
+    const int taps = g.KT * g.KH * g.KW;
+    AVEC_CHECK_ARG(taps <= 256 && taps <= Kpad && g.KT < 256 && g.KH < 256);
+    const long long sites = (long long)g.N * g.To * g.Ho * g.Wo;
+    const int blocks = (int)std::min<long long>(cdivll(sites, 8), 148LL * 32);
+    AVEC_DISPATCH_DTYPE(dtype, Tt, (im2col_c1_kernel<Tt><<<blocks, 256, 0, as_stream(stream)>>>((const Tt*)x, (Tt*)col, g, taps, Kpad, sites)));
+    AVEC_LAUNCH_CHECK();
+    return AVEC_OK;
+}
 
 extern "C" int avec_stft_mel_log(const float* wave, const float* fb, float* out, int B, int L, int F, int layout,
                                  avec_stream_t stream) {

@@ -558,7 +558,15 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
             tmem_ld16(lane_addr + (uint32_t)c0, v);
             const int c = n0 + c0;
             const bool full = fast_kind && rv && c + 16 <= p.N;
-            if (full) {
+            if (ep.kind == AVEC_EPI_ACCUM && !p.out_transposed && rv && c + 16 <= p.N &&
+                ((reinterpret_cast<uintptr_t>(ep.out) + ((size_t)row * ep.ldo + c) * 4) & 15) == 0) {
+                // split-K partial sums: 4-wide vector reductions into the fp32 gradient (red.global.add.v4.f32)
+                float* o = reinterpret_cast<float*>(ep.out) + (size_t)row * ep.ldo + c;
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + j), "f"(ep.alpha * v[j]), "f"(ep.alpha * v[j + 1]),
+                                 "f"(ep.alpha * v[j + 2]), "f"(ep.alpha * v[j + 3]) : "memory");
+            } else if (full) {
                 if (ep.bias) {
                     float b[16];
                     load16(ep.bias, AVEC_F32, (size_t)c, b);
@@ -609,12 +617,33 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
                 }
             }
             if (ep.colstats) {
-                // v[] holds acc + bias for valid elements: column sums over this warp's 32 rows
+                // v[] holds acc + bias for valid elements.  Column sums over this warp's 32 rows by a shuffle
+                // reduce-scatter (16 + 16 shuffles instead of 16 x 2 x 5): after the four halving steps lane l owns column
+                // col(l) = 8*bit4 + 4*bit3 + 2*bit2 + bit1, one more exchange folds bit 0.
+                float sa[16], sq[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float x = (rv && c + j < p.N) ? v[j] : 0.0f;
-                    const float a = warp_sum(x), b = warp_sum(x * x);
-                    if (lane == j) { atomicAdd(&cstat[c0 + j], a); atomicAdd(&cstat[256 + c0 + j], b); }
+                for (int j = 0; j < 16; ++j) { const float x = (rv && c + j < p.N) ? v[j] : 0.0f; sa[j] = x; sq[j] = x * x; }
+#define AVEC_RS_STEP(W, MASK)                                                                   \
+                {                                                                               \
+                    const bool hi = (lane & MASK) != 0;                                         \
+                    _Pragma("unroll") for (int j = 0; j < W; ++j) {                             \
+                        const float s_send = hi ? sa[j] : sa[j + W], s_keep = hi ? sa[j + W] : sa[j]; \
+                        const float q_send = hi ? sq[j] : sq[j + W], q_keep = hi ? sq[j + W] : sq[j]; \
+                        sa[j] = s_keep + __shfl_xor_sync(0xffffffffu, s_send, MASK);            \
+                        sq[j] = q_keep + __shfl_xor_sync(0xffffffffu, q_send, MASK);            \
+                    }                                                                           \
+                }
+                AVEC_RS_STEP(8, 16)
+                AVEC_RS_STEP(4, 8)
+                AVEC_RS_STEP(2, 4)
+                AVEC_RS_STEP(1, 2)
+#undef AVEC_RS_STEP
+                sa[0] += __shfl_xor_sync(0xffffffffu, sa[0], 1);
+                sq[0] += __shfl_xor_sync(0xffffffffu, sq[0], 1);
+                if ((lane & 1) == 0) {
+                    const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+                    atomicAdd(&cstat[c0 + col], sa[0]);
+                    atomicAdd(&cstat[256 + c0 + col], sq[0]);
                 }
             }
         }

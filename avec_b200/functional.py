@@ -379,26 +379,31 @@ class VideoStemFn(Function):
         Co = cw.shape[0]
         kt, kh, kw = cw.shape[2], cw.shape[3], cw.shape[4]
         g = ops.make_geom(B, T, H, W, 1, Co, (kt, kh, kw), (1, 2, 2), ((kt - 1) // 2, (kh - 1) // 2, (kw - 1) // 2))
-        wp = wc(cw, "stem3d", lambda w: w.reshape(w.shape[0], -1))
+        taps = kt * kh * kw
+        Kpad = (taps + 63) // 64 * 64
+        # the C = 1 stem as im2col + plain TMA-fed GEMMs (fwd and wgrad share the [sites, Kpad] matrix)
+        wp = wc(cw, "stem3d", lambda w: torch.nn.functional.pad(w.reshape(w.shape[0], -1), (0, Kpad - taps)))
         sites = ops.geom_sites(g)
         stats = ops.zeros_f32((2 * Co,), video.device) if training else None
-        u = ops.conv_fwd(xc, wp, g, bias=cb, colstats=stats)
+        col = ops.im2col_c1(xc, g, Kpad)
+        u = ops.linear_fwd(col, wp, cb, colstats=stats)
         bnbuf = _bn_buf(stats, bn_w, bn_b, rm, rv, sites, training, momentum)
         y, idx = ops.bn_relu_maxpool_fwd(u, bnbuf[0], bnbuf[1], B * T, g.Ho, g.Wo, Co)
-        ctx.save_for_backward(xc, u, bnbuf, bn_w, cw, idx)
+        ctx.save_for_backward(col, u, bnbuf, bn_w, cw, idx)
         ctx.g, ctx.training = g, training
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        xc, u, bnbuf, bn_w, cw, idx = ctx.saved_tensors
+        col, u, bnbuf, bn_w, cw, idx = ctx.saved_tensors
         if not ctx.training:
             raise RuntimeError("avec_b200: stem backward needs training-mode BatchNorm statistics")
         g = ctx.g
         Co = cw.shape[0]
         dz = ops.bn_relu_maxpool_bwd(_c(dy), idx, g.N * g.To, g.Ho, g.Wo, Co)
         du, _, dgamma, dbeta = ops.bn_bwd(dz, u, bnbuf, bn_w, L.ACT_NONE)
-        dcw = ops.conv_wgrad(du, xc, g).view(cw.shape)
+        taps = cw.shape[2] * cw.shape[3] * cw.shape[4]
+        dcw = ops.linear_wgrad(du, col)[:, :taps].reshape(cw.shape)
         dcb = ops.colsum(du)
         return None, dcw, dcb, dgamma, dbeta, None, None, None, None
 

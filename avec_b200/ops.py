@@ -93,9 +93,10 @@ def _epi(args, epi, alpha, bias, out, out2=None, aux=None, colstats=None):
 
 
 def _split_for(M, N, K):
+    """split-K factor of a weight-gradient GEMM: about one wave of CTAs, at least 8 k-blocks (512 reduction rows) each"""
     tiles = -(-M // 128) * -(-N // 192)
     kb = -(-K // 64)
-    return max(1, min(kb, 296 // max(1, tiles), 512))
+    return max(1, min(kb // 8 if kb >= 16 else 1, max(1, 160 // max(1, tiles)), 512))
 
 
 def linear_fwd(x, w, bias=None, epi=L.EPI_LINEAR, alpha=1.0, aux=None, out_dtype=None, want_pre=False, colstats=None):
@@ -376,6 +377,13 @@ def stft_mel_log(wave, fb, layout=0):
     L.check(L.load().avec_stft_mel_log(wave.data_ptr(), fb.data_ptr(), out.data_ptr(), B, Ln, F, layout, _stream()),
             "avec_stft_mel_log")
     return out
+
+
+def im2col_c1(x, g, Kpad):
+    """x [N,Ti,Hi,Wi,1] -> col [sites_out, Kpad] (filter taps, zero padded)"""
+    col = torch.empty((geom_sites(g), Kpad), device=x.device, dtype=x.dtype)
+    L.check(L.load().avec_im2col_c1(x.data_ptr(), col.data_ptr(), g, Kpad, _dt(x), _stream()), "avec_im2col_c1")
+    return col
 
 
 def bn_relu_maxpool_fwd(u, scale, shift, N, Hi, Wi, Cn):

@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--cpu-baseline", type=int, default=1, help="time the CPU restatement on a bounded sample (rank 0, N=1)")
     ap.add_argument("--cpu-sample", type=int, default=4, help="utterances in the CPU baseline sample")
     ap.add_argument("--loss", default="ctc", choices=["ctc", "sum"])
+    ap.add_argument("--graph", type=int, default=1, help="capture forward+backward in one CUDA graph (falls back to eager if capture fails)")
     return ap.parse_args()
 
 
@@ -186,20 +187,40 @@ def main():
     resident = {k: v.to(dev) for k, v in host.items()}
     params = [p for p in model.parameters()]
 
-    def step(d):
+    llen_cpu = host["llen"].clone()
+
+    def fwd_bwd(d):
+        """forward + 6 CTC losses + backward; leaves the gradients in p.grad"""
+        for p in params:
+            p.grad = None
         outputs = model(model_inputs(args.model, d))
         if args.loss == "ctc":
-            targets = (d["labels"], d["llen"])
-            loss = sum(ctc(targets, v) for v in outputs.values()) / len(outputs)
+            # full-length synthetic utterances: output lengths are the logits' time extent (CPU tensors: no device sync)
+            loss = sum(ctc((d["labels"], llen_cpu), [v[0], torch.full((B,), v[0].shape[1], dtype=torch.long)])
+                       for v in outputs.values()) / len(outputs)
         else:
             loss = sum(v[0].float().mean() for v in outputs.values())
         loss.backward()
+        return loss.detach()
+
+    def allreduce_grads():
         if world > 1:
-            flat = torch.cat([p.grad.reshape(-1) for p in params if p.grad is not None])
+            grads = [p.grad for p in params if p.grad is not None]
+            flat = torch._utils._flatten_dense_tensors(grads)
             dist.all_reduce(flat)
             flat /= world
-        for p in params:
-            p.grad = None
+            for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
+                g.copy_(f)
+
+    graph, static_loss = None, None
+
+    def step(d):
+        if graph is not None and d is resident:
+            graph.replay()
+            loss = static_loss
+        else:
+            loss = fwd_bwd(d)
+        allreduce_grads()
         return loss
 
     def sync():
@@ -220,19 +241,41 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    # ---- warm-up, then the device-resident timing
+    # ---- warm-up (eager), optional CUDA-graph capture of forward+backward, warm-up again
+    for _ in range(2):
+        step(resident)
+    use_graph = False
+    if args.graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                fwd_bwd(resident)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            gobj = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gobj):
+                static_loss = fwd_bwd(resident)
+            graph, use_graph = gobj, True
+        except Exception as e:  # noqa: BLE001
+            if rank == 0:
+                print(f"[bench] CUDA-graph capture failed, running eager: {type(e).__name__}: {str(e)[:200]}", file=sys.stderr)
+            graph = None
+            torch.cuda.synchronize()
     for _ in range(max(3, args.warmup)):
         step(resident)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ops.reset_launch_count()
     ms_total = timed(lambda: step(resident), args.steps)
-    launches = ops.launch_count()
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- end to end: pinned host -> device copies + loss read back inside the timed region
     def e2e_step():
+        if graph is not None:   # H2D into the graph's static input buffers
+            for k in ("audio", "video", "labels"):
+                resident[k].copy_(host[k], non_blocking=True)
+            return float(step(resident).item())
         d = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
         return float(step(d).item())
     e2e_step()
@@ -240,7 +283,10 @@ def main():
     h2d = sum(v.numel() * v.element_size() for v in host.values())
 
     # ---- roofline of the dominant kernel (tcgen05 GEMM / implicit-GEMM conv): CUDA events around every avec_gemm launch
-    gemm_ms, gemm_flops, gemm_n = profile_gemm(lambda: step(resident), ops)
+    gemm_ms, gemm_flops, gemm_n = profile_gemm(lambda: fwd_bwd(resident), ops)
+    ops.reset_launch_count()
+    fwd_bwd(resident)
+    launches = ops.launch_count()   # kernels of this library in one eager step (a graph replay launches the same set)
     peak_tf, peak_hbm, which = measured_peaks()
 
     if rank == 0:
@@ -253,12 +299,12 @@ def main():
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": f"{args.model} EffConfInterCTC fwd+bwd (train mode, dropout 0, 6 CTC heads), per-GPU batch {B}, "
                                    f"64000 audio samples + {101 if args.model == 'AV' else 100}x88x88 video",
-                       "global_batch": world * B, "parallelism": f"dp{world}", "bn": "local batch statistics", "loss": args.loss,
+                       "global_batch": world * B, "parallelism": f"dp{world}", "bn": "local batch statistics", "loss": args.loss, "cuda_graph": bool(use_graph),
                        "l2": "inputs+activations per step (>1 GB) exceed the 126 MB L2; no flush needed",
                        "achieved_tflops_whole_step": value / world * AV_GFLOP_PER_UTT / 1000.0 if args.model == "AV" else None,
                        "frac_of_tensor_peak_whole_step": (value / world * AV_GFLOP_PER_UTT / 1000.0) / peak_tf if args.model == "AV" else None},
             "e2e": {"value": world * B / (ms_e2e / args.steps / 1000.0), "unit": "utterances/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches) * args.steps,
             "clocks": clocks,
             "roofline": {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
                          "kernel": "gemm_tc_kernel (tcgen05 GEMM / implicit-GEMM conv), all launches of one step",

@@ -189,6 +189,10 @@ int avec_bn_bwd_apply(const void* dy, const void* u, const float* scale, const f
 int avec_stft_mel_log(const float* wave, const float* fb, float* out, int B, int L, int F, int layout,
                       avec_stream_t stream);
 
+/* single-channel im2col for the C = 1 stems (Conv3d (5,7,7) of nnet/networks.py:460-468): x [N,Ti,Hi,Wi,1] ->
+ * col [sites, Kpad] (taps then zero padding), so that the stem convolution and its weight gradient run as plain GEMMs */
+int avec_im2col_c1(const void* x, void* col, const avec_conv_geom* geom, int Kpad, int dtype, avec_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Visual front-end helpers (nnet/networks.py:459-472): BN3d + ReLU + MaxPool3d((1,3,3), s (1,2,2), zero "same" pad)
  * fused: u [N,Hi,Wi,C] -> y [N,Ho,Wo,C], argmax index (0..8, uint8) saved for the backward.

@@ -119,3 +119,16 @@ def test_single_channel_stem_conv_fwd_wgrad(impl, dtype, tol, B, T, H, W, Co, k,
         _close(dw, wr.grad.reshape(Co, -1), tol if dtype == torch.bfloat16 else 1e-4)
     finally:
         ops.set_gemm_impl("auto")
+
+
+def test_im2col_single_channel():
+    B, T, H, W = 2, 5, 20, 24
+    for dtype in (torch.float32, torch.bfloat16):
+        x = _rand(B, T, H, W, 1, dtype=dtype, seed=3)
+        g = ops.make_geom(B, T, H, W, 1, 64, (5, 7, 7), (1, 2, 2), (2, 3, 3))
+        col = ops.im2col_c1(x, g, 256)
+        xr = F.pad(x.float().view(B, 1, T, H, W), (3, 3, 3, 3, 2, 2))
+        ref = xr.unfold(2, 5, 1).unfold(3, 7, 2).unfold(4, 7, 2)          # (B,1,To,Ho,Wo,5,7,7)
+        ref = ref.reshape(B * g.To * g.Ho * g.Wo, 245)
+        assert torch.equal(col[:, :245].float(), ref)
+        assert float(col[:, 245:].abs().max()) == 0.0
