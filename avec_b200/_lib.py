@@ -69,6 +69,8 @@ PROTOTYPES = {
     "avec_bn_relu_maxpool_bwd": ([_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P], _I),
     "avec_avgpool_fwd": ([_P, _P, _I, _I, _I, _I, _P], _I),
     "avec_avgpool_bwd": ([_P, _P, _I, _I, _I, _I, _P], _I),
+    "avec_zero_upsample": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P], _I),
+    "avec_ctc_loss": ([_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P], _I),
     "avec_convert": ([_P, _I, _L, _P, _I, _L, _L, _I, _P], _I),
 }
 

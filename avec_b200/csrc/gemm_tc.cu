@@ -60,7 +60,8 @@ struct TcParams {
     int a_group_stride, b_group_stride;  // bytes between 64-wide MN groups (MN-major LBO)
     int a_tx, b_tx;             // bytes the TMA loads of one k-block deliver per operand
     int conv_tiles;             // 1: the M (or reduction) tiles are row-aligned image tiles of BH rows x BI images
-    int ct_BH, ct_BI, ct_tph;   // tile rows, images per tile, tiles per image
+    int ct_BH, ct_BI, ct_tph;   // tile rows, images per tile, tiles per image (on the conv's OUTPUT grid ct_H x ct_W)
+    int ct_H, ct_W, ct_s;       // output grid and spatial stride (1 or 2; strided taps use the tensor map's element strides)
     int ct_dgrad;               // tap shift sign (dgrad reads dy[p + pad - tap])
 };
 
@@ -406,7 +407,7 @@ __device__ __forceinline__ void tma_fill(const TcParams& p, int kind, const CUte
         int n0, h0;
         conv_tile_origin(p, mtile, n0, h0);
         const int dh = p.ct_dgrad ? p.g.ph - kh : kh - p.g.ph, dw = p.ct_dgrad ? p.g.pw - kw : kw - p.g.pw;
-        tma_load_4d(dst, map, bar, cb * BKE, dw, h0 + dh, n0);
+        tma_load_4d(dst, map, bar, cb * BKE, dw, h0 * p.ct_s + dh, n0);
     } else {  // OP_TMA_CONV_MN: the k-block is the conv tile kb
         int n0, h0;
         conv_tile_origin(p, kb, n0, h0);
@@ -418,7 +419,7 @@ __device__ __forceinline__ void tma_fill(const TcParams& p, int kind, const CUte
                 const int G = tile0 / 64 + g;
                 int tap = G / p.cpb; const int cb = G % p.cpb;
                 const int kw = tap % p.g.KW, kh = tap / p.g.KW;
-                tma_load_4d(dst + g * group_stride, map, bar, cb * BKE, kw - p.g.pw, h0 + kh - p.g.ph, n0);
+                tma_load_4d(dst + g * group_stride, map, bar, cb * BKE, kw - p.g.pw, h0 * p.ct_s + kh - p.g.ph, n0);
             }
         }
     }
@@ -457,8 +458,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
     if (p.conv_tiles && p.a_kind == OP_TMA_CONV_K) {
         int tn0, th0;
         conv_tile_origin(p, mtile, tn0, th0);
-        row_base = ((long long)tn0 * p.g.Hi + th0) * p.g.Wi;
-        rows_valid = p.ct_BI == 1 ? min(p.ct_BH, p.g.Hi - th0) * p.g.Wi : min(p.ct_BI, p.g.N - tn0) * p.g.Hi * p.g.Wi;
+        row_base = ((long long)tn0 * p.ct_H + th0) * p.ct_W;
+        rows_valid = p.ct_BI == 1 ? min(p.ct_BH, p.ct_H - th0) * p.ct_W : min(p.ct_BI, p.g.N - tn0) * p.ct_H * p.ct_W;
     } else {
         row_base = m0;
         rows_valid = min(BM, p.M - m0);
@@ -729,10 +730,12 @@ EncodeTiledFn get_encode() {
     return fn;
 }
 // rank-d bf16 tensor map, 128B swizzle, zero OOB fill.  dims/box innermost first; strides (bytes) for dims 1..d-1.
-bool encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+bool encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box,
+                const cuuint32_t* elem_strides = nullptr) {
     EncodeTiledFn fn = get_encode();
     if (!fn) return false;
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    if (elem_strides) for (int i = 0; i < rank; ++i) es[i] = elem_strides[i];
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, es,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -740,17 +743,19 @@ bool encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* di
 }
 bool tma_ok_2d(const void* base, long long ld) { return (reinterpret_cast<uintptr_t>(base) % 16) == 0 && (ld * 2) % 16 == 0 && get_encode() != nullptr; }
 
-// row-aligned conv tiles: whole images (BI per tile) when an image has <= 128 sites, else BH image rows of one image
+// row-aligned conv tiles on the OUTPUT grid: whole images (BI per tile) when an image has <= 128 sites, else BH rows of one image
 bool conv_tiling(const ConvGeom& g, int& BH, int& BI, int& tph) {
-    const int hw = g.Hi * g.Wi;
-    if (g.Wi > 128) return false;
-    if (hw <= 128) { BI = 128 / hw; BH = g.Hi; tph = 1; }
-    else { BI = 1; BH = 128 / g.Wi; tph = cdiv(g.Hi, BH); }
-    return BH >= 1 && BH <= 256 && BI <= 256 && g.Wi <= 256;
+    const int hw = g.Ho * g.Wo;
+    if (g.Wo > 128) return false;
+    if (hw <= 128) { BI = 128 / hw; BH = g.Ho; tph = 1; }
+    else { BI = 1; BH = 128 / g.Wo; tph = cdiv(g.Ho, BH); }
+    return BH >= 1 && (BH - 1) * g.sh + 1 <= 256 && BI <= 256 && (g.Wo - 1) * g.sw + 1 <= 256;
 }
-bool conv_is_s1_same(const ConvGeom& g) {
-    return g.KT == 1 && g.Ti == 1 && g.st == 1 && g.sh == 1 && g.sw == 1 && g.Ho == g.Hi && g.Wo == g.Wi && g.KH == g.KW &&
-           g.ph == (g.KH - 1) / 2 && g.pw == (g.KW - 1) / 2 && (g.KH % 2) == 1;
+// 2-d "same" convolutions with odd square filters and stride 1 or 2 (strided ones via tensor-map element strides)
+bool conv_tma_geom_ok(const ConvGeom& g, bool dgrad) {
+    const bool base = g.KT == 1 && g.Ti == 1 && g.st == 1 && g.sh == g.sw && (g.sh == 1 || g.sh == 2) && g.KH == g.KW && (g.KH % 2) == 1 &&
+                      g.ph == (g.KH - 1) / 2 && g.pw == (g.KW - 1) / 2 && g.Ho == (g.Hi - 1) / g.sh + 1 && g.Wo == (g.Wi - 1) / g.sw + 1;
+    return base && (!dgrad || g.sh == 1);
 }
 
 }  // namespace
@@ -796,7 +801,7 @@ int avec_gemm_tc(const avec_gemm_args* a, cudaStream_t st) {
     bool wgrad_bn_fixed = false;
     int BH = 0, BI = 0, tph = 0;
     const bool conv_tma = g_tma_enabled && get_encode() != nullptr && (a->mode == AVEC_GEMM_CONV_FWD || a->mode == AVEC_GEMM_CONV_DGRAD ||
-                          a->mode == AVEC_GEMM_CONV_WGRAD) && conv_is_s1_same(p.g) && p.g.C % 64 == 0 && p.g.Co % 64 == 0 &&
+                          a->mode == AVEC_GEMM_CONV_WGRAD) && conv_tma_geom_ok(p.g, a->mode == AVEC_GEMM_CONV_DGRAD) && p.g.C % 64 == 0 && p.g.Co % 64 == 0 &&
                           conv_tiling(p.g, BH, BI, tph) && (reinterpret_cast<uintptr_t>(a->A) % 16) == 0 && (reinterpret_cast<uintptr_t>(a->B) % 16) == 0;
     switch (a->mode) {
     case AVEC_GEMM_PLAIN:
@@ -834,8 +839,11 @@ int avec_gemm_tc(const avec_gemm_args* a, cudaStream_t st) {
     // ---- conv TMA geometry
     if (conv_tma) {
         p.conv_tiles = 1; p.ct_BH = BH; p.ct_BI = BI; p.ct_tph = tph;
+        p.ct_H = p.g.Ho; p.ct_W = p.g.Wo; p.ct_s = p.g.sh;
         const int ntiles = BI == 1 ? p.g.N * tph : cdiv(p.g.N, BI);
-        const int tile_rows = BI == 1 ? BH * p.g.Wi : BI * p.g.Hi * p.g.Wi;   // <= 128
+        const int tile_rows = BI == 1 ? BH * p.g.Wo : BI * p.g.Ho * p.g.Wo;   // <= 128
+        const cuuint32_t sbox[4] = {64, (cuuint32_t)((p.g.Wo - 1) * p.g.sw + 1), (cuuint32_t)((BH - 1) * p.g.sh + 1), (cuuint32_t)BI};
+        const cuuint32_t sstr[4] = {1, (cuuint32_t)p.g.sw, (cuuint32_t)p.g.sh, 1};
         // 4-d maps over the NHWC tensors
         const ConvGeom& g = p.g;
         if (a->mode == AVEC_GEMM_CONV_WGRAD) {
@@ -846,20 +854,19 @@ int avec_gemm_tc(const avec_gemm_args* a, cudaStream_t st) {
             p.a_group_stride = p.b_group_stride = krows * 128;
             p.num_kb = ntiles;
             p.a_tx = 2 * tile_rows * 128; p.b_tx = (p.BN / 64) * tile_rows * 128;
-            cuuint64_t dA[4] = {(cuuint64_t)g.Co, (cuuint64_t)g.Wi, (cuuint64_t)g.Hi, (cuuint64_t)g.N};
-            cuuint64_t sA[3] = {(cuuint64_t)g.Co * 2, (cuuint64_t)g.Co * g.Wi * 2, (cuuint64_t)g.Co * g.Wi * g.Hi * 2};
+            cuuint64_t dA[4] = {(cuuint64_t)g.Co, (cuuint64_t)g.Wo, (cuuint64_t)g.Ho, (cuuint64_t)g.N};
+            cuuint64_t sA[3] = {(cuuint64_t)g.Co * 2, (cuuint64_t)g.Co * g.Wo * 2, (cuuint64_t)g.Co * g.Wo * g.Ho * 2};
             cuuint64_t dB[4] = {(cuuint64_t)g.C, (cuuint64_t)g.Wi, (cuuint64_t)g.Hi, (cuuint64_t)g.N};
             cuuint64_t sB[3] = {(cuuint64_t)g.C * 2, (cuuint64_t)g.C * g.Wi * 2, (cuuint64_t)g.C * g.Wi * g.Hi * 2};
-            cuuint32_t box[4] = {64, (cuuint32_t)g.Wi, (cuuint32_t)BH, (cuuint32_t)BI};
-            if (!encode_map(&mapA, a->A, 4, dA, sA, box) || !encode_map(&mapB, a->B, 4, dB, sB, box)) return AVEC_ERR_DRIVER;
+            cuuint32_t box[4] = {64, (cuuint32_t)g.Wo, (cuuint32_t)BH, (cuuint32_t)BI};
+            if (!encode_map(&mapA, a->A, 4, dA, sA, box) || !encode_map(&mapB, a->B, 4, dB, sB, sbox, sstr)) return AVEC_ERR_DRIVER;
         } else {
             const int Cin = a->mode == AVEC_GEMM_CONV_FWD ? g.C : g.Co;   // channels of the gathered tensor
             grid_m = ntiles;
             p.a_tx = tile_rows * 128;
             cuuint64_t dA[4] = {(cuuint64_t)Cin, (cuuint64_t)g.Wi, (cuuint64_t)g.Hi, (cuuint64_t)g.N};
             cuuint64_t sA[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cin * g.Wi * 2, (cuuint64_t)Cin * g.Wi * g.Hi * 2};
-            cuuint32_t box[4] = {64, (cuuint32_t)g.Wi, (cuuint32_t)BH, (cuuint32_t)BI};
-            if (!encode_map(&mapA, a->A, 4, dA, sA, box)) return AVEC_ERR_DRIVER;
+            if (!encode_map(&mapA, a->A, 4, dA, sA, sbox, sstr)) return AVEC_ERR_DRIVER;
         }
     }
     // ---- plain 2-d TMA operands where strides allow it

@@ -546,6 +546,24 @@ __global__ void avgpool_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx,
     }
 }
 
+// zero insertion: out[n, i*s, j*s, :] = in[n, i, j, :], zeros elsewhere (turns the dgrad of a strided conv into a stride-1 conv)
+template <typename T, int V>
+__global__ void zero_upsample_kernel(const T* __restrict__ in, T* __restrict__ out, int Ho, int Wo, int Hi, int Wi, int C, int s, long long totalv) {
+    const int Cv = C / V;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < totalv; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % Cv) * V;
+        long long t = i / Cv;
+        const int w = (int)(t % Wi); t /= Wi;
+        const int h = (int)(t % Hi);
+        const long long n = t / Hi;
+        float v[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) v[j] = 0.0f;
+        if (h % s == 0 && w % s == 0 && h / s < Ho && w / s < Wo) load_vec<V>(in + ((n * Ho + h / s) * Wo + w / s) * C + c, v);
+        store_vec<V>(out + (size_t)i * V, v);
+    }
+}
+
 template <typename TI, typename TO>
 __global__ void convert_kernel(const TI* __restrict__ src, long long lds, TO* __restrict__ dst, long long ldd, int C, long long total) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -749,6 +767,16 @@ extern "C" int avec_avgpool_bwd(const void* dy, void* dx, int N, int HW, int C, 
     AVEC_CHECK_ARG(dy && dx && N > 0 && HW > 0 && C > 0);
     long long total = (long long)N * HW * C;
     AVEC_DISPATCH_DTYPE(dtype, Tt, (avgpool_bwd_kernel<Tt><<<ew_blocks(total), 256, 0, as_stream(stream)>>>((const Tt*)dy, (Tt*)dx, HW, C, total)));
+    AVEC_LAUNCH_CHECK();
+    return AVEC_OK;
+}
+
+extern "C" int avec_zero_upsample(const void* in, void* out, int N, int Ho, int Wo, int Hi, int Wi, int C, int s, int dtype,
+                                  avec_stream_t stream) {
+    AVEC_CHECK_ARG(in && out && N > 0 && s >= 1 && (Ho - 1) * s < Hi && (Wo - 1) * s < Wi);
+    long long total = (long long)N * Hi * Wi * C;
+    AVEC_DISPATCH_DTYPE_VEC(dtype, C, Tt, V, (zero_upsample_kernel<Tt, V><<<ew_blocks(total / V), 256, 0, as_stream(stream)>>>(
+        (const Tt*)in, (Tt*)out, Ho, Wo, Hi, Wi, C, s, total / V)));
     AVEC_LAUNCH_CHECK();
     return AVEC_OK;
 }

@@ -495,3 +495,23 @@ class AvgPoolFn(Function):
     def backward(ctx, dy):
         N, H, W, Cn = ctx.shp
         return ops.avgpool_bwd(_c(dy), N, H * W, Cn).view(ctx.shp)
+
+
+class CTCFn(Function):
+    """per-utterance CTC negative log-likelihood of fp32 logits [B,T,V] (log-softmax fused)"""
+
+    @staticmethod
+    def forward(ctx, logits, labels, in_len, lab_len, blank, zero_infinity):
+        lg = _c(logits.float())
+        dev = lg.device
+        lab = _c(labels.to(device=dev, dtype=torch.long))
+        il = _c(in_len.to(device=dev, dtype=torch.long)) if in_len is not None else None
+        ll = _c(lab_len.to(device=dev, dtype=torch.long))
+        nll, grad = ops.ctc_loss(lg, lab, il, ll, blank, zero_infinity)
+        ctx.save_for_backward(grad)
+        return nll
+
+    @staticmethod
+    def backward(ctx, gout):
+        (grad,) = ctx.saved_tensors
+        return grad * gout.view(-1, 1, 1), None, None, None, None, None

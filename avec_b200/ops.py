@@ -189,6 +189,15 @@ def conv_fwd(x, wp, g, bias=None, epi=L.EPI_LINEAR, colstats=None, aux=None):
 def conv_dgrad(dy, wd, g, epi=L.EPI_LINEAR, aux=None):
     """dy [sites_out, Co], wd [C, taps*Co] -> dx [sites_in, C] (optionally + aux: merging two gradient branches)."""
     _cuda(dy, wd)
+    if (g.sh > 1 or g.sw > 1) and g.sh == g.sw and g.KT == 1 and g.Ti == 1 and dy.dtype == torch.bfloat16 and GEMM_IMPL != L.IMPL_SIMT \
+            and g.C % 64 == 0 and g.Co % 64 == 0:
+        # strided conv: insert zeros into dY and run the stride-1 TMA dgrad (4x redundant MMAs but tensor-core fed by
+        # TMA; the exact alternative - one launch per output parity class - is future work)
+        up = torch.empty((g.N * g.Hi * g.Wi, g.Co), device=dy.device, dtype=dy.dtype)
+        L.check(L.load().avec_zero_upsample(dy.data_ptr(), up.data_ptr(), g.N, g.Ho, g.Wo, g.Hi, g.Wi, g.Co, g.sh, _dt(dy), _stream()),
+                "avec_zero_upsample")
+        g1 = make_geom(g.N, 1, g.Hi, g.Wi, g.C, g.Co, (1, g.KH, g.KW), (1, 1, 1), (0, g.ph, g.pw))
+        return conv_dgrad(up, wd, g1, epi, aux)
     M = geom_sites(g, False)
     out = torch.empty((M, g.C), device=dy.device, dtype=dy.dtype)
     a = L.GemmArgs()
@@ -413,6 +422,19 @@ def avgpool_bwd(dy, N, HW, Cn):
     dx = torch.empty((N * HW, Cn), device=dy.device, dtype=dy.dtype)
     L.check(L.load().avec_avgpool_bwd(dy.data_ptr(), dx.data_ptr(), N, HW, Cn, _dt(dy), _stream()), "avec_avgpool_bwd")
     return dx
+
+
+def ctc_loss(logits, labels, in_len, lab_len, blank=0, zero_infinity=False):
+    """logits [B,T,V] fp32 -> (nll [B], grad [B,T,V]); lengths are int64 device tensors (no host sync)."""
+    _cuda(logits, labels, lab_len)
+    B, T, V = logits.shape
+    Lmax = labels.shape[1]
+    nll = torch.empty((B,), device=logits.device, dtype=torch.float32)
+    grad = torch.empty_like(logits)
+    ws = torch.empty((B * T * (2 * Lmax + 1),), device=logits.device, dtype=torch.float32)
+    L.check(L.load().avec_ctc_loss(logits.data_ptr(), labels.data_ptr(), _p(in_len), lab_len.data_ptr(), nll.data_ptr(), grad.data_ptr(),
+                                   ws.data_ptr(), B, T, V, Lmax, blank, 1 if zero_infinity else 0, _stream()), "avec_ctc_loss")
+    return nll, grad
 
 
 def convert(src, dtype):

@@ -206,6 +206,20 @@ int avec_bn_relu_maxpool_bwd(const void* dy, const uint8_t* idx, void* dz, int N
 int avec_avgpool_fwd(const void* x, void* y, int N, int HW, int C, int dtype, avec_stream_t stream);
 int avec_avgpool_bwd(const void* dy, void* dx, int N, int HW, int C, int dtype, avec_stream_t stream);
 
+/* zero insertion out[n, i*s, j*s, :] = in[n, i, j, :] ([N,Ho,Wo,C] -> [N,Hi,Wi,C]): the input gradient of a stride-s
+ * convolution is then a stride-1 convolution over the zero-inserted dY (TMA-fed implicit GEMM) */
+int avec_zero_upsample(const void* in, void* out, int N, int Ho, int Wo, int Hi, int Wi, int C, int s, int dtype,
+                       avec_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * CTC loss fused with log-softmax (nnet/losses.py:292-334: log_softmax -> transpose -> nn.CTCLoss(reduction="none")).
+ * logits [B,T,V] fp32, labels [B,Lmax] int64, in_len / lab_len [B] int64 on the DEVICE (in_len may be NULL = T).
+ * nll [B] = per-utterance negative log-likelihood; grad [B,T,V] = d nll_b / d logits (0 beyond in_len);
+ * ws: workspace of B*T*(2*Lmax+1) floats.  zero_infinity: infeasible alignments give nll = 0, grad = 0.
+ * ------------------------------------------------------------------------------------------------------------------ */
+int avec_ctc_loss(const float* logits, const long long* labels, const long long* in_len, const long long* lab_len, float* nll,
+                  float* grad, float* ws, int B, int T, int V, int Lmax, int blank, int zero_infinity, avec_stream_t stream);
+
 /* dtype conversion / strided copy helper: dst[r][c] = (T)src[r][c] */
 int avec_convert(const void* src, int src_dtype, long long lds, void* dst, int dst_dtype, long long ldd, long long rows,
                  int C, avec_stream_t stream);

@@ -170,3 +170,26 @@ def test_bn_relu_maxpool_and_avgpool():
     check_close("avgpool", ops.avgpool_fwd(x, 5, 9, 512), x.mean((1, 2)), 1e-5, 1e-6)
     check_close("avgpool bwd", ops.avgpool_bwd(x[:, 0, 0].contiguous(), 5, 9, 512).view(5, 3, 3, 512),
                 (x[:, 0, 0] / 9)[:, None, None, :].expand(5, 3, 3, 512), 1e-5, 1e-6)
+
+
+@pytest.mark.parametrize("B,T,V,Lmax", [(5, 51, 256, 20), (3, 9, 256, 4), (4, 101, 256, 20)])
+def test_ctc_loss_and_gradient(B, T, V, Lmax):
+    """fused log-softmax + CTC kernel against torch (the reference's nn.CTCLoss(reduction='none') path, losses.py:324-329)"""
+    g = torch.Generator().manual_seed(B * 100 + T)
+    logits = (2.0 * torch.randn(B, T, V, generator=g)).to(DEV).requires_grad_(True)
+    labels = torch.randint(1, V, (B, Lmax), generator=g)
+    labels[0, 1] = labels[0, 0]                           # repeated label: forces a blank between them
+    lab_len = torch.tensor([Lmax] + [max(1, Lmax - 1 - i) for i in range(B - 1)])
+    in_len = torch.tensor([T] + [max(T // 2 + 1, T - 2 * i) for i in range(1, B)])
+    lab_len = torch.minimum(lab_len, in_len // 2)
+    logp = logits.log_softmax(-1).transpose(0, 1)
+    ref = F.ctc_loss(logp, labels.to(DEV), in_len, lab_len, blank=0, reduction="none", zero_infinity=False)
+    w = torch.rand(B, generator=g).to(DEV)
+    (ref * w).sum().backward()
+    nll, grad = ops.ctc_loss(logits.detach(), labels.to(DEV), in_len.to(DEV), lab_len.to(DEV))
+    check_close("nll", nll, ref, 1e-4, 1e-4)
+    check_close("grad", grad * w.view(-1, 1, 1), logits.grad, 1e-3, 1e-5)
+    # infeasible alignment (label longer than the input): zero_infinity zeroes loss and gradient
+    bad_len = torch.full((B,), 2)
+    nll2, grad2 = ops.ctc_loss(logits.detach(), labels.to(DEV), bad_len.to(DEV), torch.full((B,), Lmax).to(DEV), zero_infinity=True)
+    assert float(nll2.abs().max()) == 0.0 and float(grad2.abs().max()) == 0.0

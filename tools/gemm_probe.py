@@ -61,7 +61,11 @@ g = ops.make_geom(B, T, 88, 88, 1, 64, (5, 7, 7), (1, 2, 2), (2, 3, 3))
 wp = torch.randn(64, 245, device=dev, dtype=bf)
 dy = torch.randn(ops.geom_sites(g), 64, device=dev, dtype=bf)
 fl = 2.0 * ops.geom_sites(g) * 64 * 245
-for name, fn in [("fwd", lambda: ops.conv_fwd(x, wp, g)), ("wgrad", lambda: ops.conv_wgrad(dy, x, g))]:
+col = ops.im2col_c1(x, g, 256)
+wp256 = torch.randn(64, 256, device=dev, dtype=bf)
+st = torch.zeros(128, device=dev)
+for name, fn in [("im2col", lambda: ops.im2col_c1(x, g, 256)), ("fwd", lambda: ops.linear_fwd(col, wp256, None, colstats=st)),
+                 ("wgrad", lambda: ops.linear_wgrad(dy, col))]:
     ms = timeit(fn, 3)
     res.append({"op": f"stem3d_{name}", "ms": ms, "tflops": fl / ms / 1e9})
     print(res[-1], flush=True)
