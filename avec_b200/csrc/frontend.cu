@@ -72,38 +72,47 @@ __global__ void __launch_bounds__(FR_PER_CTA * 32) stft_mel_log_kernel(const flo
 }
 
 // single-channel im2col: col[site][tap] = x[n, to*st+kt-pt, ho*sh+kh-ph, wo*sw+kw-pw] (0 outside), taps padded with zeros to
-// Kpad.  One warp per output site, lane = 8 consecutive taps (one 16-byte store); the input (100 MB at B = 64) lives in L2.
+// Kpad.  One CTA = one (n, to) slice x IM_BH output rows x all Wo columns: the input window (KT x IH x IW elements, zero
+// padding applied once) is staged in shared memory with coalesced loads, then every warp emits whole 2*Kpad-byte rows
+// (lane = 8 consecutive taps = one 16-byte store).  HBM-bound on the col write (6.4 GB at B = 64).
+constexpr int IM_BH = 4;
+
 template <typename T>
 __global__ void __launch_bounds__(256) im2col_c1_kernel(const T* __restrict__ x, T* __restrict__ col, ConvGeom g, int taps, int Kpad,
-                                                        long long sites) {
-    __shared__ int tapofs[256];
+                                                        int IH, int IW) {
+    extern __shared__ float tile[];    // [KT][IH][IW]
+    __shared__ int tapofs[256];        // tap -> offset inside the tile
+    const int hob = blockIdx.y * IM_BH;
+    const int to = blockIdx.x % g.To, n = blockIdx.x / g.To;
     for (int tap = threadIdx.x; tap < 256; tap += blockDim.x) {
         int t = tap;
         const int kw = t % g.KW; t /= g.KW; const int kh = t % g.KH; const int kt = t / g.KH;
-        tapofs[tap] = kt | (kh << 8) | (kw << 16);
+        tapofs[tap] = tap < taps ? (kt * IH + kh) * IW + kw : -1;
+    }
+    const int t0 = to * g.st - g.pt, h0 = hob * g.sh - g.ph, w0 = -g.pw;
+    const int n_el = g.KT * IH * IW;
+    for (int i = threadIdx.x; i < n_el; i += blockDim.x) {
+        const int iw = i % IW; int r = i / IW; const int ih = r % IH; const int kt = r / IH;
+        const int ti = t0 + kt, hi = h0 + ih, wi = w0 + iw;
+        float v = 0.0f;
+        if ((unsigned)ti < (unsigned)g.Ti && (unsigned)hi < (unsigned)g.Hi && (unsigned)wi < (unsigned)g.Wi)
+            v = ldf(x + (((long long)n * g.Ti + ti) * g.Hi + hi) * g.Wi + wi);
+        tile[i] = v;
     }
     __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
-    for (long long site = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; site < sites; site += warps) {
-        long long s = site;
-        const int wo = (int)(s % g.Wo); s /= g.Wo;
-        const int ho = (int)(s % g.Ho); s /= g.Ho;
-        const int to = (int)(s % g.To); const int n = (int)(s / g.To);
-        const int t0 = to * g.st - g.pt, h0 = ho * g.sh - g.ph, w0 = wo * g.sw - g.pw;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int rows = min(IM_BH, g.Ho - hob);
+    for (int sidx = warp; sidx < rows * g.Wo; sidx += nw) {
+        const int hl = sidx / g.Wo, wo = sidx % g.Wo;
+        const long long site = (((long long)n * g.To + to) * g.Ho + hob + hl) * g.Wo + wo;
+        const int base = hl * g.sh * IW + wo * g.sw;
         for (int c0 = lane * 8; c0 < Kpad; c0 += 256) {
             float v[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int tap = c0 + j;
-                float val = 0.0f;
-                if (tap < taps) {
-                    const int o = tapofs[tap];
-                    const int ti = t0 + (o & 255), hi = h0 + ((o >> 8) & 255), wi = w0 + (o >> 16);
-                    if ((unsigned)ti < (unsigned)g.Ti && (unsigned)hi < (unsigned)g.Hi && (unsigned)wi < (unsigned)g.Wi)
-                        val = ldf(x + (((long long)n * g.Ti + ti) * g.Hi + hi) * g.Wi + wi);
-                }
-                v[j] = val;
+                const int o = tap < 256 ? tapofs[tap] : -1;
+                v[j] = o >= 0 ? tile[base + o] : 0.0f;
             }
             store_vec<8>(col + site * Kpad + c0, v);
         }
@@ -116,10 +125,16 @@ extern "C" int avec_im2col_c1(const void* x, void* col, const avec_conv_geom* ge
     AVEC_CHECK_ARG(x && col && geom && geom->C == 1 && Kpad % 8 == 0);
     ConvGeom g = make_geom(*geom);
     const int taps = g.KT * g.KH * g.KW;
-    AVEC_CHECK_ARG(taps <= 256 && taps <= Kpad && g.KT < 256 && g.KH < 256);
-    const long long sites = (long long)g.N * g.To * g.Ho * g.Wo;
-    const int blocks = (int)std::min<long long>(cdivll(sites, 8), 148LL * 32);
-    AVEC_DISPATCH_DTYPE(dtype, Tt, (im2col_c1_kernel<Tt><<<blocks, 256, 0, as_stream(stream)>>>((const Tt*)x, (Tt*)col, g, taps, Kpad, sites)));
+    AVEC_CHECK_ARG(taps <= 256 && taps <= Kpad);
+    const int IH = (IM_BH - 1) * g.sh + g.KH, IW = (g.Wo - 1) * g.sw + g.KW;
+    const size_t smem = (size_t)g.KT * IH * IW * sizeof(float);
+    if (smem > 200 * 1024 || cdiv(g.Ho, IM_BH) > 65535) return AVEC_ERR_UNSUPPORTED;
+    dim3 grid(g.N * g.To, cdiv(g.Ho, IM_BH));
+    AVEC_DISPATCH_DTYPE(dtype, Tt, {
+        auto kfn = im2col_c1_kernel<Tt>;
+        if (smem > 48 * 1024 && cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return AVEC_ERR_LAUNCH;
+        kfn<<<grid, 256, smem, as_stream(stream)>>>((const Tt*)x, (Tt*)col, g, taps, Kpad, IH, IW);
+    });
     AVEC_LAUNCH_CHECK();
     return AVEC_OK;
 }

@@ -541,11 +541,18 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
             }
         }
         // ===================== epilogue =====================
-        mbar_wait(accum_bar, 0u);
-        tc_fence_after();
         const int r = warp * 32 + lane;
         const bool rv = r < rows_valid;
         const long long row = row_base + r;
+        // pull this thread's residual / auxiliary row segment towards L1 while the MMAs are still running
+        if (rv && p.ep.aux && !p.out_transposed) {
+            const int esz = p.ep.aux_dtype == AVEC_F32 ? 4 : 2;
+            const char* a0 = reinterpret_cast<const char*>(p.ep.aux) + ((size_t)row * p.ep.ldaux + n0) * esz;
+            const int nbytes = min(BN, p.N - n0) * esz;
+            for (int o = 0; o < nbytes; o += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(a0 + o));
+        }
+        mbar_wait(accum_bar, 0u);
+        tc_fence_after();
         const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
         EpiParams ep = p.ep;
         if (blockIdx.z > 0) ep.bias = nullptr;
@@ -700,8 +707,11 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
     if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_base, ncols); }
 }
 
-int pick_bn(int N) {
+// tile width: as wide as possible (<= 256, multiple of 16, awkward N such as 180 / 720 / 1080 split evenly), but narrow
+// enough that small problems still put >= ~100 CTAs on the 148 SMs (never below 64 columns)
+int pick_bn(int N, int mtiles) {
     int ntiles = cdiv(N, 256);
+    while (mtiles * ntiles < 100 && cdiv(cdiv(N, ntiles + 1), 16) * 16 >= 64) ++ntiles;
     int bn = cdiv(cdiv(N, ntiles), 16) * 16;
     return bn < 16 ? 16 : bn;
 }
@@ -833,7 +843,7 @@ int avec_gemm_tc(const avec_gemm_args* a, cudaStream_t st) {
     }
     p.a_align = ptr_align(p.A, p.a_ld);
     p.b_align = ptr_align(p.B, p.b_ld);
-    p.BN = pick_bn(a->N);
+    p.BN = pick_bn(a->N, a->mode == AVEC_GEMM_PLAIN ? cdiv(a->M, BM) : 1000);
     if (wgrad_bn_fixed) p.BN = a->N >= 256 ? 256 : (a->N >= 192 ? 192 : (a->N >= 128 ? 128 : 64));
 
     // ---- conv TMA geometry

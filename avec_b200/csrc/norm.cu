@@ -261,52 +261,64 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const T* __restrict__ 
 // Column reductions over [rows, C] (C contiguous): thread x owns V consecutive channels, thread y strides rows.
 // F(row, c0, v0[V], v1[V]) produces up to two values per channel to be summed.
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int CR_X = 32, CR_Y = 16;
+constexpr int CR_THREADS = 512;
 
+// blockDim = (X, 512 / X) with X = min(32, pow2ceil(C / V)): for narrow tensors (C = 64: X = 8) a warp then reads 4 whole
+// consecutive rows (512 contiguous bytes) instead of leaving 3/4 of its lanes idle.
 template <typename F, int V>
-__global__ void __launch_bounds__(CR_X* CR_Y) colreduce_kernel(F f, long long rows, int C, long long rows_per_block,
+__global__ void __launch_bounds__(CR_THREADS) colreduce_kernel(F f_in, long long rows, int C, long long rows_per_block,
                                                                float* __restrict__ out0, float* __restrict__ out1, float alpha) {
-    __shared__ float s0[CR_Y][CR_X * V + 1];
-    __shared__ float s1[CR_Y][CR_X * V + 1];
-    const int c = (blockIdx.x * CR_X + threadIdx.x) * V;
+    __shared__ float s0[CR_THREADS * V];
+    __shared__ float s1[CR_THREADS * V];
+    F f = f_in;
+    const int X = blockDim.x, Y = blockDim.y;
+    const int c = (blockIdx.x * X + threadIdx.x) * V;
     const long long r0 = (long long)blockIdx.y * rows_per_block;
     const long long r1 = min(rows, r0 + rows_per_block);
     float a0[V], a1[V];
 #pragma unroll
     for (int j = 0; j < V; ++j) { a0[j] = 0.0f; a1[j] = 0.0f; }
     if (c < C) {
-        for (long long r = r0 + threadIdx.y; r < r1; r += CR_Y) {
+        f.prep(c);   // per-channel constants (this thread's channel group is fixed)
+        for (long long r = r0 + threadIdx.y; r < r1; r += Y) {
             float v0[V], v1[V];
             f(r, c, v0, v1);
 #pragma unroll
             for (int j = 0; j < V; ++j) { a0[j] += v0[j]; a1[j] += v1[j]; }
         }
     }
+    const int W = X * V;   // channels covered by this block
 #pragma unroll
-    for (int j = 0; j < V; ++j) { s0[threadIdx.y][threadIdx.x * V + j] = a0[j]; s1[threadIdx.y][threadIdx.x * V + j] = a1[j]; }
+    for (int j = 0; j < V; ++j) { s0[threadIdx.y * W + threadIdx.x * V + j] = a0[j]; s1[threadIdx.y * W + threadIdx.x * V + j] = a1[j]; }
     __syncthreads();
-    for (int cc = threadIdx.y * CR_X + threadIdx.x; cc < CR_X * V; cc += CR_X * CR_Y) {
-        const int cg = blockIdx.x * CR_X * V + cc;
+    // tree over y in shared memory, then one atomic per channel per block
+    for (int h = Y >> 1; h >= 1; h >>= 1) {
+        for (int i = threadIdx.y * X + threadIdx.x; i < h * W; i += CR_THREADS) { s0[i] += s0[i + h * W]; s1[i] += s1[i + h * W]; }
+        __syncthreads();
+    }
+    for (int cc = threadIdx.y * X + threadIdx.x; cc < W; cc += CR_THREADS) {
+        const int cg = blockIdx.x * W + cc;
         if (cg < C) {
-            float t0 = 0.0f, t1 = 0.0f;
-#pragma unroll
-            for (int y = 0; y < CR_Y; ++y) { t0 += s0[y][cc]; t1 += s1[y][cc]; }
-            atomicAdd(out0 + cg, alpha * t0);
-            if (out1) atomicAdd(out1 + cg, alpha * t1);
+            atomicAdd(out0 + cg, alpha * s0[cc]);
+            if (out1) atomicAdd(out1 + cg, alpha * s1[cc]);
         }
     }
 }
 
 template <int V, typename F>
 int launch_colreduce(const F& f, long long rows, int C, float* out0, float* out1, float alpha, cudaStream_t st) {
-    int gx = cdiv(C, CR_X * V);
+    const int Cv = cdiv(C, V);
+    int X = 1;
+    while (X < 32 && X < Cv) X <<= 1;
+    const int Y = CR_THREADS / X;
+    int gx = cdiv(Cv, X);
     long long want = cdivll(148 * 8, gx);
-    long long nchunk = min(want, cdivll(rows, CR_Y * 4));
+    long long nchunk = min(want, cdivll(rows, (long long)Y * 4));
     if (nchunk < 1) nchunk = 1;
     if (nchunk > 65535) nchunk = 65535;
     long long rpb = cdivll(rows, nchunk);
     nchunk = cdivll(rows, rpb);
-    dim3 grid(gx, (unsigned)nchunk), block(CR_X, CR_Y);
+    dim3 grid(gx, (unsigned)nchunk), block(X, Y);
     colreduce_kernel<F, V><<<grid, block, 0, st>>>(f, rows, C, rpb, out0, out1, alpha);
     return 0;
 }
@@ -314,6 +326,7 @@ int launch_colreduce(const F& f, long long rows, int C, float* out0, float* out1
 template <typename T, int V>
 struct ColsumF {
     const T* x; long long ldx;
+    __device__ __forceinline__ void prep(int) {}
     __device__ __forceinline__ void operator()(long long r, int c, float (&v0)[V], float (&v1)[V]) const {
         load_vec<V>(x + r * ldx + c, v0);
 #pragma unroll
@@ -323,6 +336,7 @@ struct ColsumF {
 template <typename T, int V>
 struct StatsF {
     const T* x; int C;
+    __device__ __forceinline__ void prep(int) {}
     __device__ __forceinline__ void operator()(long long r, int c, float (&v0)[V], float (&v1)[V]) const {
         load_vec<V>(x + r * C + c, v0);
 #pragma unroll
@@ -336,15 +350,18 @@ __device__ __forceinline__ float act_bwd(float z, int act) { return act == AVEC_
 template <typename T, int V>
 struct BnBwdF {
     const T* dy; const T* u; const T* res; const float* scale; const float* shift; const float* mean; const float* rstd; int C; int act;
-    __device__ __forceinline__ void operator()(long long r, int c, float (&v0)[V], float (&v1)[V]) const {
-        size_t i = (size_t)r * C + c;
-        float uu[V], d[V], rr[V], sc[V], sh[V], mu[V], rs[V];
-        load_vec<V>(u + i, uu);
-        load_vec<V>(dy + i, d);
+    float sc[V], sh[V], mu[V], rs[V];
+    __device__ __forceinline__ void prep(int c) {
         load_vec<V>(scale + c, sc);
         load_vec<V>(shift + c, sh);
         load_vec<V>(mean + c, mu);
         load_vec<V>(rstd + c, rs);
+    }
+    __device__ __forceinline__ void operator()(long long r, int c, float (&v0)[V], float (&v1)[V]) const {
+        size_t i = (size_t)r * C + c;
+        float uu[V], d[V], rr[V];
+        load_vec<V>(u + i, uu);
+        load_vec<V>(dy + i, d);
         if (res) load_vec<V>(res + i, rr);
 #pragma unroll
         for (int j = 0; j < V; ++j) {
@@ -391,13 +408,17 @@ template <typename T, int V>
 __global__ void bn_apply_kernel(const T* __restrict__ u, const float* __restrict__ scale, const float* __restrict__ shift,
                                 const T* __restrict__ res, T* __restrict__ y, long long totalv, int C, int act) {
     const int Cv = C / V;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < totalv; i += (long long)gridDim.x * blockDim.x) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const bool fixed_c = (stride % Cv) == 0;   // every iteration of this thread hits the same channel group
+    float sc[V], sh[V];
+    const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (fixed_c) { const int c = (int)(i0 % Cv) * V; load_vec<V>(scale + c, sc); load_vec<V>(shift + c, sh); }
+    for (long long i = i0; i < totalv; i += stride) {
         const int c = (int)(i % Cv) * V;
         const size_t e = (size_t)i * V;
-        float uu[V], sc[V], sh[V], rr[V];
+        float uu[V], rr[V];
         load_vec<V>(u + e, uu);
-        load_vec<V>(scale + c, sc);
-        load_vec<V>(shift + c, sh);
+        if (!fixed_c) { load_vec<V>(scale + c, sc); load_vec<V>(shift + c, sh); }
         if (res) load_vec<V>(res + e, rr);
 #pragma unroll
         for (int j = 0; j < V; ++j) {
@@ -415,12 +436,12 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restric
                                     const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ sums,
                                     T* __restrict__ du, T* __restrict__ dres, long long totalv, int C, int act, float inv_count) {
     const int Cv = C / V;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < totalv; i += (long long)gridDim.x * blockDim.x) {
-        const int c = (int)(i % Cv) * V;
-        const size_t e = (size_t)i * V;
-        float uu[V], d[V], rr[V], sc[V], sh[V], mu[V], rs[V], g[V], s0[V], s1[V], o[V], dzv[V];
-        load_vec<V>(u + e, uu);
-        load_vec<V>(dy + e, d);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const bool fixed_c = (stride % Cv) == 0;
+    // du = k1*dz + k2*u + k3 with per-channel k1 = g*rs, k2 = -g*rs^2*s1/n, k3 = -g*rs*s0/n + g*rs^2*mu*s1/n
+    float sc[V], sh[V], k1[V], k2[V], k3[V];
+    auto load_coef = [&](int c) {
+        float mu[V], rs[V], g[V], s0[V], s1[V];
         load_vec<V>(scale + c, sc);
         load_vec<V>(shift + c, sh);
         load_vec<V>(mean + c, mu);
@@ -428,14 +449,30 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restric
         load_vec<V>(sums + c, s0);
         load_vec<V>(sums + C + c, s1);
         if (gamma) load_vec<V>(gamma + c, g);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const float gg = (gamma ? g[j] : 1.0f) * rs[j];
+            k1[j] = gg;
+            k2[j] = -gg * rs[j] * s1[j] * inv_count;
+            k3[j] = -gg * s0[j] * inv_count + gg * rs[j] * mu[j] * s1[j] * inv_count;
+        }
+    };
+    const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (fixed_c) load_coef((int)(i0 % Cv) * V);
+    for (long long i = i0; i < totalv; i += stride) {
+        const int c = (int)(i % Cv) * V;
+        const size_t e = (size_t)i * V;
+        float uu[V], d[V], rr[V], o[V], dzv[V];
+        load_vec<V>(u + e, uu);
+        load_vec<V>(dy + e, d);
+        if (!fixed_c) load_coef(c);
         if (res) load_vec<V>(res + e, rr);
 #pragma unroll
         for (int j = 0; j < V; ++j) {
             float z = sc[j] * uu[j] + sh[j];
             if (res) z += rr[j];
             float dz = d[j] * act_bwd(z, act);
-            float xh = (uu[j] - mu[j]) * rs[j];
-            o[j] = (gamma ? g[j] : 1.0f) * rs[j] * (dz - s0[j] * inv_count - xh * s1[j] * inv_count);
+            o[j] = k1[j] * dz + k2[j] * uu[j] + k3[j];
             dzv[j] = dz;
         }
         store_vec<V>(du + e, o);
@@ -717,7 +754,7 @@ extern "C" int avec_bn_bwd_reduce(const void* dy, const void* u, const float* sc
     AVEC_CHECK_ARG(dy && u && scale && shift && mean && rstd && sums && rows > 0 && C > 0);
     cudaStream_t st = as_stream(stream);
     AVEC_DISPATCH_DTYPE_VEC(dtype, C, Tt, V, {
-        BnBwdF<Tt, V> f{(const Tt*)dy, (const Tt*)u, (const Tt*)res, scale, shift, mean, rstd, C, act};
+        BnBwdF<Tt, V> f{(const Tt*)dy, (const Tt*)u, (const Tt*)res, scale, shift, mean, rstd, C, act, {}, {}, {}, {}};
         launch_colreduce<V>(f, rows, C, sums, sums + C, 1.0f, st);
     });
     AVEC_LAUNCH_CHECK();

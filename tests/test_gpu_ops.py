@@ -188,7 +188,7 @@ def test_ctc_loss_and_gradient(B, T, V, Lmax):
     (ref * w).sum().backward()
     nll, grad = ops.ctc_loss(logits.detach(), labels.to(DEV), in_len.to(DEV), lab_len.to(DEV))
     check_close("nll", nll, ref, 1e-4, 1e-4)
-    check_close("grad", grad * w.view(-1, 1, 1), logits.grad, 1e-3, 1e-5)
+    check_close("grad", grad * w.view(-1, 1, 1), logits.grad, 1e-3, 5e-5)
     # infeasible alignment (label longer than the input): zero_infinity zeroes loss and gradient
     bad_len = torch.full((B,), 2)
     nll2, grad2 = ops.ctc_loss(logits.detach(), labels.to(DEV), bad_len.to(DEV), torch.full((B,), Lmax).to(DEV), zero_infinity=True)
