@@ -15,6 +15,7 @@
 #include <cuda.h>
 #include <cstring>
 #include <cstdint>
+#include <cstdlib>
 
 namespace {
 
@@ -63,6 +64,7 @@ struct TcParams {
     int ct_BH, ct_BI, ct_tph;   // tile rows, images per tile, tiles per image (on the conv's OUTPUT grid ct_H x ct_W)
     int ct_H, ct_W, ct_s;       // output grid and spatial stride (1 or 2; strided taps use the tensor map's element strides)
     int ct_dgrad;               // tap shift sign (dgrad reads dy[p + pad - tap])
+    int dbg_rowofs;             // diagnostics (AVEC_DEBUG_ROWOFS): A tile loaded `ofs` rows early, descriptor started `ofs` rows in
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -398,7 +400,7 @@ __device__ __forceinline__ void tma_fill(const TcParams& p, int kind, const CUte
                                          int group_stride, int tile0, int kb, int mtile, bool is_a) {
     const uint32_t dst = smem_u32(tile);
     if (kind == OP_TMA_K) {
-        tma_load_2d(dst, map, bar, kb * BKE, tile0);
+        tma_load_2d(dst, map, bar, kb * BKE, tile0 - (is_a ? p.dbg_rowofs : 0));
     } else if (kind == OP_TMA_MN) {
         for (int g = 0; g * 64 < rows; ++g) tma_load_2d(dst + g * group_stride, map, bar, tile0 + g * 64, kb * BKE);
     } else if (kind == OP_TMA_CONV_K) {
@@ -687,8 +689,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
             mbar_wait(&full_bar[s], ph);
             tc_fence_after();
             if (lane == 0) {
-                const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
-                const uint32_t b_addr = a_addr + a_bytes;
+                const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes) + (uint32_t)p.dbg_rowofs * 128u;
+                const uint32_t b_addr = smem_u32(smem + (size_t)s * stage_bytes) + a_bytes;
                 for (int k = 0; k < p.ksteps; ++k) {
                     // K-major: advance 32 bytes inside the 128-byte swizzle row; SBO = 1024 (8 rows).
                     // MN-major: advance 16 reduction rows = 2048 bytes; LBO = next 64-wide MN group, SBO = 1024.
@@ -843,7 +845,7 @@ int avec_gemm_tc(const avec_gemm_args* a, cudaStream_t st) {
     }
     p.a_align = ptr_align(p.A, p.a_ld);
     p.b_align = ptr_align(p.B, p.b_ld);
-    p.BN = pick_bn(a->N, a->mode == AVEC_GEMM_PLAIN ? cdiv(a->M, BM) : 1000);
+    p.BN = pick_bn(a->N, (a->mode == AVEC_GEMM_PLAIN && a->epi != AVEC_EPI_ACCUM) ? cdiv(a->M, BM) : 1000);
     if (wgrad_bn_fixed) p.BN = a->N >= 256 ? 256 : (a->N >= 192 ? 192 : (a->N >= 128 ? 128 : 64));
 
     // ---- conv TMA geometry
@@ -893,6 +895,11 @@ int avec_gemm_tc(const avec_gemm_args* a, cudaStream_t st) {
     } else if (g_tma_enabled && p.b_kind == OP_PLAIN_MN && tma_ok_2d(p.B, p.b_ld)) {
         cuuint64_t d[2] = {(cuuint64_t)a->N, (cuuint64_t)a->K}; cuuint64_t s1[1] = {(cuuint64_t)p.b_ld * 2}; cuuint32_t box[2] = {64, 64};
         if (encode_map(&mapB, p.B, 2, d, s1, box)) { p.b_kind = OP_TMA_MN; p.b_tx = cdiv(p.BN, 64) * 64 * 128; }
+    }
+    {
+        static int dbg = -1;
+        if (dbg < 0) { const char* e = getenv("AVEC_DEBUG_ROWOFS"); dbg = e ? atoi(e) : 0; }
+        if (dbg > 0 && p.a_kind == OP_TMA_K && a->mode == AVEC_GEMM_PLAIN) p.dbg_rowofs = dbg;
     }
     if (p.a_rows == 0) p.a_rows = BM;
     if (p.b_rows == 0) p.b_rows = is_mn(p.b_kind) ? cdiv(p.BN, 64) * 64 : p.BN;
