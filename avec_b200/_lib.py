@@ -46,6 +46,7 @@ PROTOTYPES = {
     "avec_reset_launch_count": ([], None),
     "avec_gemm": ([C.POINTER(GemmArgs), _P], _I),
     "avec_set_tma": ([_I], None),
+    "avec_set_debug_timestamps": ([_P], None),
     "avec_colsum": ([_P, _I, _L, _I, _L, _F, _P, _I, _P], _I),
     "avec_layernorm_fwd": ([_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _P], _I),
     "avec_layernorm_bwd": ([_P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P], _I),

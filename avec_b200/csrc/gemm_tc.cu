@@ -64,6 +64,7 @@ struct TcParams {
     int ct_BH, ct_BI, ct_tph;   // tile rows, images per tile, tiles per image (on the conv's OUTPUT grid ct_H x ct_W)
     int ct_H, ct_W, ct_s;       // output grid and spatial stride (1 or 2; strided taps use the tensor map's element strides)
     int ct_dgrad;               // tap shift sign (dgrad reads dy[p + pad - tap])
+    unsigned long long* dbg_ts; // diagnostics (avec_set_debug_timestamps): CTA (0,0,0) records globaltimer at phase boundaries
     int dbg_rowofs;             // diagnostics (AVEC_DEBUG_ROWOFS): A tile loaded `ofs` rows early, descriptor started `ofs` rows in
 };
 
@@ -130,6 +131,13 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                  ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define AVEC_TS(slot) do { if (p.dbg_ts && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) p.dbg_ts[slot] = gtime(); } while (0)
+
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -445,6 +453,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
     float* cstat = reinterpret_cast<float*>(ctrl + 256 + BM * sizeof(RowInfo) + 256 * sizeof(int));  // [2][256]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) AVEC_TS(0);   // kernel start
     const int mtile = blockIdx.x;
     const int n0 = blockIdx.y * BN;
     const int kb_begin = blockIdx.z * p.kb_per_split;
@@ -516,6 +525,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (tid == 0) AVEC_TS(1);   // setup done (barriers, TMEM alloc)
 
     if (warp < 4) {
         // ===================== gather producers =====================
@@ -555,6 +565,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
         }
         mbar_wait(accum_bar, 0u);
         tc_fence_after();
+        if (tid == 0) AVEC_TS(4);   // accumulator complete, epilogue starts
         const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
         EpiParams ep = p.ep;
         if (blockIdx.z > 0) ep.bias = nullptr;
@@ -662,6 +673,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
             for (int cc = tid; cc < BN; cc += PRODUCER_THREADS)
                 if (n0 + cc < p.N) { atomicAdd(ep.colstats + n0 + cc, cstat[cc]); atomicAdd(ep.colstats + p.N + n0 + cc, cstat[256 + cc]); }
         }
+        if (tid == 0) AVEC_TS(5);   // epilogue done
         tc_fence_before();
     } else if (warp == 5) {
         // ===================== TMA producer (one thread) =====================
@@ -689,6 +701,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
             mbar_wait(&full_bar[s], ph);
             tc_fence_after();
             if (lane == 0) {
+                if (i == 0) AVEC_TS(2);   // first k-block landed in shared memory
                 const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes) + (uint32_t)p.dbg_rowofs * 128u;
                 const uint32_t b_addr = smem_u32(smem + (size_t)s * stage_bytes) + a_bytes;
                 for (int k = 0; k < p.ksteps; ++k) {
@@ -699,14 +712,14 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
                     umma_f16(tmem_base, adesc, bdesc, idesc, (i > 0 || k > 0) ? 1u : 0u);
                 }
                 umma_commit(&empty_bar[s]);
-                if (i == nkb - 1) umma_commit(accum_bar);
+                if (i == nkb - 1) { umma_commit(accum_bar); AVEC_TS(3); }   // last MMA issued
             }
             __syncwarp();
         }
         tc_fence_before();
     }
     __syncthreads();
-    if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_base, ncols); }
+    if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_base, ncols); if (lane == 0) AVEC_TS(6); }
 }
 
 // tile width: as wide as possible (<= 256, multiple of 16, awkward N such as 180 / 720 / 1080 split evenly), but narrow
@@ -773,7 +786,9 @@ bool conv_tma_geom_ok(const ConvGeom& g, bool dgrad) {
 }  // namespace
 
 static int g_tma_enabled = 1;
+static unsigned long long* g_dbg_ts = nullptr;
 extern "C" void avec_set_tma(int enabled) { g_tma_enabled = enabled; }
+extern "C" void avec_set_debug_timestamps(void* dev_buf_8_u64) { g_dbg_ts = reinterpret_cast<unsigned long long*>(dev_buf_8_u64); }
 
 bool avec_gemm_tc_supported(const avec_gemm_args* a) {
     if (a->ab_dtype != AVEC_BF16) return false;
@@ -807,6 +822,7 @@ int avec_gemm_tc(const avec_gemm_args* a, cudaStream_t st) {
     p.ep = make_epi(a);
     p.out_transposed = 0;
     p.ksteps = 4;
+    p.dbg_ts = g_dbg_ts;
     p.a_group_stride = p.b_group_stride = 8192;
     const int taps = p.g.KT * p.g.KH * p.g.KW;
     int grid_m = cdiv(a->M, BM);

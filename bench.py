@@ -164,7 +164,7 @@ def main():
 
     import torch.distributed as dist
     import avec_b200
-    from avec_b200 import nnet, ops
+    from avec_b200 import nnet, ops, parallel
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -179,8 +179,7 @@ def main():
     cls = {"AV": nnet.AudioVisualEfficientConformerInterCTC, "AO": nnet.AudioEfficientConformerInterCTC, "VO": nnet.VisualEfficientConformerInterCTC}[args.model]
     model = nnet.zero_dropout(cls()).to(dev).train()
     if world > 1:  # identical replicas
-        for p in model.parameters():
-            dist.broadcast(p.data, 0)
+        parallel.broadcast_parameters(model)
     ctc = nnet.CTCLoss(zero_infinity=True, assert_shorter=False)
     B = args.batch
     host = synth_inputs(args.model, B, None, seed=1234 + rank, pinned=True)
@@ -202,12 +201,7 @@ def main():
 
     def allreduce_grads():
         if world > 1:
-            grads = [p.grad for p in params if p.grad is not None]
-            flat = torch._utils._flatten_dense_tensors(grads)
-            dist.all_reduce(flat)
-            flat /= world
-            for g, f in zip(grads, torch._utils._unflatten_dense_tensors(flat, grads)):
-                g.copy_(f)
+            parallel.allreduce_gradients(params, world)
 
     graph, static_loss = None, None
 

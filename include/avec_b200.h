@@ -103,6 +103,10 @@ typedef struct avec_gemm_args {
 int avec_gemm(const avec_gemm_args* args, avec_stream_t stream);
 /* diagnostics: 0 forces the cp.async gather producers even where a TMA descriptor is possible (default 1) */
 void avec_set_tma(int enabled);
+/* diagnostics: device buffer of 8 uint64; CTA (0,0,0) of every tcgen05 GEMM launch records %globaltimer (ns) at
+ * [0] start, [1] setup done, [2] first k-block in smem, [3] last MMA issued, [4] accumulator complete, [5] epilogue
+ * done, [6] TMEM released.  NULL disables. */
+void avec_set_debug_timestamps(void* dev_buf_8_u64);
 
 /* out[n] (+)= alpha * sum_m x[m][n]      — bias gradients (autograd of the bias add in addmm / conv) */
 int avec_colsum(const void* x, int dtype, long long rows, int C, long long ldx, float alpha, float* out, int accumulate,
