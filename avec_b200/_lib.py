@@ -14,6 +14,7 @@ GEMM_PLAIN, GEMM_CONV_FWD, GEMM_CONV_DGRAD, GEMM_CONV_WGRAD = 0, 1, 2, 3
 EPI_LINEAR, EPI_SWISH, EPI_RESIDUAL, EPI_DSWISH, EPI_ACCUM, EPI_RELU = 0, 1, 2, 3, 4, 5
 IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_SWISH = 0, 1, 2
+STATS_REPLICAS = 32   # copies of the GEMM-epilogue BatchNorm statistics accumulator (AVEC_STATS_REPLICAS in common.cuh)
 
 
 class ConvGeom(C.Structure):
@@ -58,7 +59,7 @@ PROTOTYPES = {
     "avec_softmax_bwd": ([_P, _P, _I, _P, _P, _I, _L, _I, _P], _I),
     "avec_glu_dwconv_fwd": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P], _I),
     "avec_glu_dwconv_bwd": ([_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P], _I),
-    "avec_bn_finalize": ([_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _F, _F, _P], _I),
+    "avec_bn_finalize": ([_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _F, _F, _I, _P], _I),
     "avec_bn_eval_affine": ([_P, _P, _P, _P, _P, _P, _I, _F, _P], _I),
     "avec_bn_stats": ([_P, _I, _L, _I, _P, _P], _I),
     "avec_bn_apply": ([_P, _P, _P, _P, _P, _L, _I, _I, _I, _P], _I),

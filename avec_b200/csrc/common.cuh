@@ -17,6 +17,10 @@ static inline long long cdivll(long long a, long long b) { return (a + b - 1) / 
 
 typedef __nv_bfloat16 bf16;
 
+// BatchNorm column statistics are accumulated into one of AVEC_STATS_REPLICAS copies (selected by CTA index) to spread the
+// same-address L2 atomics; avec_bn_finalize sums the copies.
+#define AVEC_STATS_REPLICAS 32
+
 __device__ __forceinline__ float ldf(const float* p) { return *p; }
 __device__ __forceinline__ float ldf(const bf16* p) { return __bfloat162float(*p); }
 __device__ __forceinline__ void stf(float* p, float v) { *p = v; }

@@ -134,8 +134,9 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(LA la, LB lb, int K, int 
         for (int j = 0; j < 4; ++j) { atomicAdd(&cs[0][tx * 4 + j], s1[j]); atomicAdd(&cs[1][tx * 4 + j], s2[j]); }
         __syncthreads();
         if (tid < BN && n0 + tid < ep.N) {
-            atomicAdd(ep.colstats + n0 + tid, cs[0][tid]);
-            atomicAdd(ep.colstats + ep.N + n0 + tid, cs[1][tid]);
+            float* dst = ep.colstats + (size_t)(blockIdx.x % AVEC_STATS_REPLICAS) * 2 * ep.N;
+            atomicAdd(dst + n0 + tid, cs[0][tid]);
+            atomicAdd(dst + ep.N + n0 + tid, cs[1][tid]);
         }
     }
 }

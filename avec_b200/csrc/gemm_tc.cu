@@ -142,6 +142,22 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // shared-memory matrix descriptor, SWIZZLE_128B, Blackwell version bits (cute::UMMA::SmemDescriptor layout)
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
     uint64_t d = 0;
@@ -451,6 +467,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
     RowInfo* rinfo = reinterpret_cast<RowInfo*>(ctrl + 256);
     int* tapofs = reinterpret_cast<int*>(ctrl + 256 + BM * sizeof(RowInfo));
     float* cstat = reinterpret_cast<float*>(ctrl + 256 + BM * sizeof(RowInfo) + 256 * sizeof(int));  // [2][256]
+    float* bias_s = cstat + 512;                                                                     // [256]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) AVEC_TS(0);   // kernel start
@@ -513,6 +530,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
         }
         rinfo[tid] = ri;
     }
+    // bias slice of this tile (0 where absent / beyond N / for split-K slices other than the first) and zeroed statistics
+    for (int c = tid; c < 256; c += TC_THREADS)
+        bias_s[c] = (p.ep.bias && blockIdx.z == 0 && c < BN && n0 + c < p.N) ? p.ep.bias[n0 + c] : 0.0f;
+    if (p.ep.colstats) for (int c = tid; c < 512; c += TC_THREADS) cstat[c] = 0.0f;
     // MN-major TMA tiles whose k extent (conv tile rows) is not a multiple of 16: the tail rows are never written by TMA
     // and must read as zeros -> clear all stages once (generic proxy), then hand the buffers to the async proxy
     if (p.a_kind == OP_TMA_CONV_MN || p.b_kind == OP_TMA_CONV_MN) {
@@ -568,110 +589,112 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
         if (tid == 0) AVEC_TS(4);   // accumulator complete, epilogue starts
         const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
         EpiParams ep = p.ep;
-        if (blockIdx.z > 0) ep.bias = nullptr;
-        if (ep.colstats) {
-            for (int c = tid; c < 512; c += PRODUCER_THREADS) cstat[c] = 0.0f;
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-        }
+        ep.bias = nullptr;   // the bias slice lives in shared memory (bias_s)
         const bool fast_kind = !p.out_transposed && ep.kind != AVEC_EPI_ACCUM;
-        for (int c0 = 0; c0 < BN; c0 += 16) {
-            float v[16];
-            tmem_ld16(lane_addr + (uint32_t)c0, v);
+        const bool need_aux = ep.aux != nullptr && (ep.kind == AVEC_EPI_RESIDUAL || ep.kind == AVEC_EPI_DSWISH || ep.kind == AVEC_EPI_RELU);
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            const int nch = (BN - c0 >= 32) ? 2 : 1;   // BN is a multiple of 16
             const int c = n0 + c0;
-            const bool full = fast_kind && rv && c + 16 <= p.N;
-            if (ep.kind == AVEC_EPI_ACCUM && !p.out_transposed && rv && c + 16 <= p.N &&
-                ((reinterpret_cast<uintptr_t>(ep.out) + ((size_t)row * ep.ldo + c) * 4) & 15) == 0) {
-                // split-K partial sums: 4-wide vector reductions into the fp32 gradient (red.global.add.v4.f32)
-                float* o = reinterpret_cast<float*>(ep.out) + (size_t)row * ep.ldo + c;
+            // auxiliary operand of this 32-column group: issued before the TMEM load so that both latencies overlap
+            float x[32];
+            const bool full0 = fast_kind && rv && c + 16 <= p.N, full1 = nch == 2 && fast_kind && rv && c + 32 <= p.N;
+            if (need_aux) {
+                if (full0) load16(ep.aux, ep.aux_dtype, (size_t)row * ep.ldaux + c, *reinterpret_cast<float(*)[16]>(&x[0]));
+                if (full1) load16(ep.aux, ep.aux_dtype, (size_t)row * ep.ldaux + c + 16, *reinterpret_cast<float(*)[16]>(&x[16]));
+            }
+            float v[32];
+            if (nch == 2) tmem_ld32(lane_addr + (uint32_t)c0, v);
+            else tmem_ld16(lane_addr + (uint32_t)c0, *reinterpret_cast<float(*)[16]>(&v[0]));
 #pragma unroll
-                for (int j = 0; j < 16; j += 4)
-                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + j), "f"(ep.alpha * v[j]), "f"(ep.alpha * v[j + 1]),
-                                 "f"(ep.alpha * v[j + 2]), "f"(ep.alpha * v[j + 3]) : "memory");
-            } else if (full) {
-                if (ep.bias) {
-                    float b[16];
-                    load16(ep.bias, AVEC_F32, (size_t)c, b);
+            for (int h = 0; h < 2; ++h) {
+                if (h >= nch) break;
+                float (&vv)[16] = *reinterpret_cast<float(*)[16]>(&v[16 * h]);
+                float (&xx)[16] = *reinterpret_cast<float(*)[16]>(&x[16 * h]);
+                const int ch = c + 16 * h;
+                const bool full = h == 0 ? full0 : full1;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] += b[j];
-                }
-                float o[16];
-                const size_t oi = (size_t)row * ep.ldo + c;
-                if (ep.kind == AVEC_EPI_LINEAR) {
+                for (int j = 0; j < 16; ++j) vv[j] += bias_s[c0 + 16 * h + j];
+                if (ep.kind == AVEC_EPI_ACCUM && !p.out_transposed && rv && ch + 16 <= p.N &&
+                    ((reinterpret_cast<uintptr_t>(ep.out) + ((size_t)row * ep.ldo + ch) * 4) & 15) == 0) {
+                    // split-K partial sums: 4-wide vector reductions into the fp32 gradient (red.global.add.v4.f32)
+                    float* o = reinterpret_cast<float*>(ep.out) + (size_t)row * ep.ldo + ch;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) o[j] = ep.alpha * v[j];
-                } else if (ep.kind == AVEC_EPI_SWISH) {
-                    if (ep.out2) store16(ep.out2, ep.out2_dtype, (size_t)row * ep.ldo2 + c, v);
+                    for (int j = 0; j < 16; j += 4)
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + j), "f"(ep.alpha * vv[j]), "f"(ep.alpha * vv[j + 1]),
+                                     "f"(ep.alpha * vv[j + 2]), "f"(ep.alpha * vv[j + 3]) : "memory");
+                } else if (full) {
+                    float o[16];
+                    const size_t oi = (size_t)row * ep.ldo + ch;
+                    if (ep.kind == AVEC_EPI_LINEAR) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) o[j] = swishf_(v[j]);
-                } else {
-                    float x[16];
-                    if (ep.aux) load16(ep.aux, ep.aux_dtype, (size_t)row * ep.ldaux + c, x);
-                    if (ep.kind == AVEC_EPI_RESIDUAL) {
+                        for (int j = 0; j < 16; ++j) o[j] = ep.alpha * vv[j];
+                    } else if (ep.kind == AVEC_EPI_SWISH) {
+                        if (ep.out2) store16(ep.out2, ep.out2_dtype, (size_t)row * ep.ldo2 + ch, vv);
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) o[j] = x[j] + ep.alpha * v[j];
+                        for (int j = 0; j < 16; ++j) o[j] = swishf_(vv[j]);
+                    } else if (ep.kind == AVEC_EPI_RESIDUAL) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) o[j] = xx[j] + ep.alpha * vv[j];
                     } else if (ep.kind == AVEC_EPI_DSWISH) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) o[j] = ep.alpha * v[j] * dswishf_(x[j]);
+                        for (int j = 0; j < 16; ++j) o[j] = ep.alpha * vv[j] * dswishf_(xx[j]);
                     } else {  // RELU
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) o[j] = fmaxf(ep.alpha * v[j] + (ep.aux ? x[j] : 0.0f), 0.0f);
+                        for (int j = 0; j < 16; ++j) o[j] = fmaxf(ep.alpha * vv[j] + (need_aux ? xx[j] : 0.0f), 0.0f);
                     }
-                }
-                store16(ep.out, ep.out_dtype, oi, o);
-            } else {
+                    store16(ep.out, ep.out_dtype, oi, o);
+                } else {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int cc = c + j;
-                    float val = 0.0f;
-                    if (rv && cc < p.N) {
-                        if (p.out_transposed) {
-                            float vv = v[j] + (ep.bias ? ep.bias[cc] : 0.0f);
-                            size_t o = (size_t)cc * ep.ldo + row;
-                            if (ep.kind == AVEC_EPI_ACCUM) atomicAdd(reinterpret_cast<float*>(ep.out) + o, ep.alpha * vv);
-                            else st_any(ep.out, ep.out_dtype, o, ep.alpha * vv);
-                            val = vv;
-                        } else {
-                            val = epilogue_elem(ep, (int)row, cc, v[j]);
+                    for (int j = 0; j < 16; ++j) {
+                        const int cc = ch + j;
+                        if (rv && cc < p.N) {
+                            if (p.out_transposed) {
+                                size_t o = (size_t)cc * ep.ldo + row;
+                                if (ep.kind == AVEC_EPI_ACCUM) atomicAdd(reinterpret_cast<float*>(ep.out) + o, ep.alpha * vv[j]);
+                                else st_any(ep.out, ep.out_dtype, o, ep.alpha * vv[j]);
+                            } else {
+                                epilogue_elem(ep, (int)row, cc, vv[j]);   // bias already added (ep.bias == nullptr)
+                            }
                         }
                     }
-                    v[j] = val;
                 }
-            }
-            if (ep.colstats) {
-                // v[] holds acc + bias for valid elements.  Column sums over this warp's 32 rows by a shuffle
-                // reduce-scatter (16 + 16 shuffles instead of 16 x 2 x 5): after the four halving steps lane l owns column
-                // col(l) = 8*bit4 + 4*bit3 + 2*bit2 + bit1, one more exchange folds bit 0.
-                float sa[16], sq[16];
+                if (ep.colstats) {
+                    // vv[] holds acc + bias.  Column sums over this warp's 32 rows by a shuffle reduce-scatter (16 + 16
+                    // shuffles): after the four halving steps lane l owns column 8*bit4 + 4*bit3 + 2*bit2 + bit1.
+                    float sa[16], sq[16];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) { const float x = (rv && c + j < p.N) ? v[j] : 0.0f; sa[j] = x; sq[j] = x * x; }
-#define AVEC_RS_STEP(W, MASK)                                                                   \
-                {                                                                               \
-                    const bool hi = (lane & MASK) != 0;                                         \
-                    _Pragma("unroll") for (int j = 0; j < W; ++j) {                             \
-                        const float s_send = hi ? sa[j] : sa[j + W], s_keep = hi ? sa[j + W] : sa[j]; \
-                        const float q_send = hi ? sq[j] : sq[j + W], q_keep = hi ? sq[j + W] : sq[j]; \
-                        sa[j] = s_keep + __shfl_xor_sync(0xffffffffu, s_send, MASK);            \
-                        sq[j] = q_keep + __shfl_xor_sync(0xffffffffu, q_send, MASK);            \
-                    }                                                                           \
-                }
-                AVEC_RS_STEP(8, 16)
-                AVEC_RS_STEP(4, 8)
-                AVEC_RS_STEP(2, 4)
-                AVEC_RS_STEP(1, 2)
+                    for (int j = 0; j < 16; ++j) { const float xv = (rv && ch + j < p.N) ? vv[j] : 0.0f; sa[j] = xv; sq[j] = xv * xv; }
+#define AVEC_RS_STEP(W, MASK)                                                                       \
+                    {                                                                               \
+                        const bool hi = (lane & MASK) != 0;                                         \
+                        _Pragma("unroll") for (int j = 0; j < W; ++j) {                             \
+                            const float s_send = hi ? sa[j] : sa[j + W], s_keep = hi ? sa[j + W] : sa[j]; \
+                            const float q_send = hi ? sq[j] : sq[j + W], q_keep = hi ? sq[j + W] : sq[j]; \
+                            sa[j] = s_keep + __shfl_xor_sync(0xffffffffu, s_send, MASK);            \
+                            sq[j] = q_keep + __shfl_xor_sync(0xffffffffu, q_send, MASK);            \
+                        }                                                                           \
+                    }
+                    AVEC_RS_STEP(8, 16)
+                    AVEC_RS_STEP(4, 8)
+                    AVEC_RS_STEP(2, 4)
+                    AVEC_RS_STEP(1, 2)
 #undef AVEC_RS_STEP
-                sa[0] += __shfl_xor_sync(0xffffffffu, sa[0], 1);
-                sq[0] += __shfl_xor_sync(0xffffffffu, sq[0], 1);
-                if ((lane & 1) == 0) {
-                    const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-                    atomicAdd(&cstat[c0 + col], sa[0]);
-                    atomicAdd(&cstat[256 + c0 + col], sq[0]);
+                    sa[0] += __shfl_xor_sync(0xffffffffu, sa[0], 1);
+                    sq[0] += __shfl_xor_sync(0xffffffffu, sq[0], 1);
+                    if ((lane & 1) == 0) {
+                        const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+                        atomicAdd(&cstat[c0 + 16 * h + col], sa[0]);
+                        atomicAdd(&cstat[256 + c0 + 16 * h + col], sq[0]);
+                    }
                 }
             }
         }
         if (ep.colstats) {
+            // one of AVEC_STATS_REPLICAS copies of the accumulator (by CTA index): 32x fewer same-address L2 atomics
             asm volatile("bar.sync 1, 128;" ::: "memory");
+            float* dst = ep.colstats + (size_t)(blockIdx.x % AVEC_STATS_REPLICAS) * 2 * p.N;
             for (int cc = tid; cc < BN; cc += PRODUCER_THREADS)
-                if (n0 + cc < p.N) { atomicAdd(ep.colstats + n0 + cc, cstat[cc]); atomicAdd(ep.colstats + p.N + n0 + cc, cstat[256 + cc]); }
+                if (n0 + cc < p.N) { atomicAdd(dst + n0 + cc, cstat[cc]); atomicAdd(dst + p.N + n0 + cc, cstat[256 + cc]); }
         }
         if (tid == 0) AVEC_TS(5);   // epilogue done
         tc_fence_before();
@@ -862,6 +885,11 @@ int avec_gemm_tc(const avec_gemm_args* a, cudaStream_t st) {
     p.a_align = ptr_align(p.A, p.a_ld);
     p.b_align = ptr_align(p.B, p.b_ld);
     p.BN = pick_bn(a->N, (a->mode == AVEC_GEMM_PLAIN && a->epi != AVEC_EPI_ACCUM) ? cdiv(a->M, BM) : 1000);
+    {
+        static int max_bn = -1;
+        if (max_bn < 0) { const char* e = getenv("AVEC_MAX_BN"); max_bn = e ? atoi(e) : 256; }
+        if (p.BN > max_bn) p.BN = cdiv(cdiv(a->N, cdiv(a->N, max_bn)), 16) * 16;
+    }
     if (wgrad_bn_fixed) p.BN = a->N >= 256 ? 256 : (a->N >= 192 ? 192 : (a->N >= 128 ? 128 : 64));
 
     // ---- conv TMA geometry
@@ -926,7 +954,7 @@ int avec_gemm_tc(const avec_gemm_args* a, cudaStream_t st) {
     split = cdiv(p.num_kb, p.kb_per_split);
     const int stage_bytes = p.a_rows * 128 + cdiv(p.b_rows * 128, 1024) * 1024;
     p.stages = stage_bytes <= 32 * 1024 ? 3 : 4;   // >= LAG + 1 = 3 (gather run-ahead); <= 32 KB stages allow 2 CTAs / SM
-    const size_t ctrl_bytes = 256 + BM * sizeof(RowInfo) + 256 * sizeof(int) + 512 * sizeof(float) + 1024;
+    const size_t ctrl_bytes = 256 + BM * sizeof(RowInfo) + 256 * sizeof(int) + 768 * sizeof(float) + 1024;
     while (p.stages > 2 && (size_t)p.stages * stage_bytes + ctrl_bytes > 227 * 1024) --p.stages;
     const bool any_gather = !is_tma(p.a_kind) || !is_tma(p.b_kind);
     size_t smem = (size_t)p.stages * stage_bytes + ctrl_bytes;

@@ -379,11 +379,13 @@ __global__ void zero_kernel(float* p, int n) { int i = blockIdx.x * blockDim.x +
 __global__ void bn_finalize_kernel(const float* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean,
                                    float* __restrict__ rstd, float* __restrict__ rmean, float* __restrict__ rvar,
-                                   float inv_count, float unbias, int C, float eps, float momentum) {
+                                   float inv_count, float unbias, int C, float eps, float momentum, int replicas) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
-    float mu = stats[c] * inv_count;
-    float var = fmaxf(stats[C + c] * inv_count - mu * mu, 0.0f);
+    float s1 = 0.0f, s2 = 0.0f;
+    for (int r = 0; r < replicas; ++r) { s1 += stats[(size_t)r * 2 * C + c]; s2 += stats[(size_t)r * 2 * C + C + c]; }
+    float mu = s1 * inv_count;
+    float var = fmaxf(s2 * inv_count - mu * mu, 0.0f);
     float rs = rsqrtf(var + eps);
     float g = gamma ? gamma[c] : 1.0f, b = beta ? beta[c] : 0.0f;
     scale[c] = g * rs;
@@ -721,11 +723,11 @@ extern "C" int avec_bn_stats(const void* u, int dtype, long long rows, int C, fl
 
 extern "C" int avec_bn_finalize(const float* stats, const float* gamma, const float* beta, float* scale, float* shift, float* mean,
                                 float* rstd, float* running_mean, float* running_var, long long count, int C, float eps,
-                                float momentum, avec_stream_t stream) {
-    AVEC_CHECK_ARG(stats && scale && shift && count > 0 && C > 0);
+                                float momentum, int replicas, avec_stream_t stream) {
+    AVEC_CHECK_ARG(stats && scale && shift && count > 0 && C > 0 && replicas >= 1);
     float unbias = count > 1 ? (float)((double)count / (double)(count - 1)) : 1.0f;
     bn_finalize_kernel<<<cdiv(C, 128), 128, 0, as_stream(stream)>>>(stats, gamma, beta, scale, shift, mean, rstd, running_mean,
-                                                                   running_var, (float)(1.0 / (double)count), unbias, C, eps, momentum);
+                                                                   running_var, (float)(1.0 / (double)count), unbias, C, eps, momentum, replicas);
     AVEC_LAUNCH_CHECK();
     return AVEC_OK;
 }

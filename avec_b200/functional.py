@@ -346,7 +346,7 @@ class AudioStemFn(Function):
         g = ops.make_geom(B, 1, F, 80, 1, Co, (1, 3, 3), (1, 2, 2), (0, 1, 1))
         wp = wc(cw, "stem2d", lambda w: w[:, 0].transpose(1, 2).reshape(w.shape[0], 9))
         sites = ops.geom_sites(g)
-        stats = ops.zeros_f32((2 * Co,), wave.device) if training else None
+        stats = ops.gemm_stats_buffer(Co, wave.device) if training else None
         u = ops.conv_fwd(melc, wp, g, bias=cb, colstats=stats)
         bnbuf = _bn_buf(stats, bn_w, bn_b, rm, rv, sites, training, momentum)
         v = ops.bn_apply(u, bnbuf[0], bnbuf[1], L.ACT_SWISH)
@@ -384,7 +384,7 @@ class VideoStemFn(Function):
         # the C = 1 stem as im2col + plain TMA-fed GEMMs (fwd and wgrad share the [sites, Kpad] matrix)
         wp = wc(cw, "stem3d", lambda w: torch.nn.functional.pad(w.reshape(w.shape[0], -1), (0, Kpad - taps)))
         sites = ops.geom_sites(g)
-        stats = ops.zeros_f32((2 * Co,), video.device) if training else None
+        stats = ops.gemm_stats_buffer(Co, video.device) if training else None
         col = ops.im2col_c1(xc, g, Kpad)
         u = ops.linear_fwd(col, wp, cb, colstats=stats)
         bnbuf = _bn_buf(stats, bn_w, bn_b, rm, rv, sites, training, momentum)
@@ -432,7 +432,7 @@ class ResBlockFn(Function):
         dev = x.device
 
         def st():
-            return ops.zeros_f32((2 * Co,), dev) if training else None
+            return ops.gemm_stats_buffer(Co, dev) if training else None
 
         ga = ops.make_geom(N, 1, H, W, Ci, Co, (1, 3, 3), (1, stride, stride), (0, 1, 1))
         s1 = st()

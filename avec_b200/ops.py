@@ -287,12 +287,18 @@ def bn_stats(u2d):
     return stats
 
 
+def gemm_stats_buffer(Cn, device):
+    """zeroed accumulator for the GEMM-epilogue BatchNorm statistics: [STATS_REPLICAS][2*C]"""
+    return zeros_f32((L.STATS_REPLICAS * 2 * Cn,), device)
+
+
 def bn_finalize(stats, gamma, beta, count, running_mean=None, running_var=None, eps=1e-5, momentum=0.1):
-    Cn = stats.numel() // 2
+    Cn = gamma.numel() if gamma is not None else stats.numel() // 2
+    replicas = stats.numel() // (2 * Cn)
     buf = torch.empty((4, Cn), device=stats.device, dtype=torch.float32)  # scale, shift, mean, rstd
     L.check(L.load().avec_bn_finalize(stats.data_ptr(), _p(gamma), _p(beta), buf[0].data_ptr(), buf[1].data_ptr(),
                                       buf[2].data_ptr(), buf[3].data_ptr(), _p(running_mean), _p(running_var), count, Cn,
-                                      eps, momentum, _stream()), "avec_bn_finalize")
+                                      eps, momentum, replicas, _stream()), "avec_bn_finalize")
     return buf
 
 

@@ -96,7 +96,8 @@ typedef struct avec_gemm_args {
     const void* aux;
     int aux_dtype;
     long long ldaux;
-    float* colstats; /* optional [2*N]: += sum_m v, += sum_m v^2 of v = acc + bias (BatchNorm batch statistics) */
+    float* colstats; /* optional [32][2*N] (32 replicas selected by CTA index, summed by avec_bn_finalize):
+                        += sum_m v, += sum_m v^2 of v = acc + bias (BatchNorm batch statistics) */
     int split_k;     /* ACCUM epilogue: number of K slices (0/1 = none) */
 } avec_gemm_args;
 
@@ -162,7 +163,7 @@ int avec_glu_dwconv_bwd(const void* du, const void* pre, const float* w, void* d
 
 /* ------------------------------------------------------------------------------------------------------------------
  * BatchNorm over channels-last rows (BatchNorm1d/2d/3d of nnet/normalizations.py:42-170; eps 1e-5, momentum 0.1).
- * finalize: from stats (sum, sumsq over `count` rows) -> scale/shift (gamma*rstd, beta-mean*gamma*rstd), saved mean /
+ * finalize: from stats ([replicas][2C]: sum, sumsq over `count` rows; GEMM colstats use 32 replicas, others 1) -> scale/shift (gamma*rstd, beta-mean*gamma*rstd), saved mean /
  *   rstd, and the running-stat update (unbiased variance) when running_mean != NULL.  In eval mode call
  *   avec_bn_eval_affine instead.
  * apply: y = act(scale*u + shift (+ res))                act: 0 none, 1 ReLU, 2 Swish
@@ -172,7 +173,7 @@ int avec_glu_dwconv_bwd(const void* du, const void* pre, const float* w, void* d
 enum avec_act { AVEC_ACT_NONE = 0, AVEC_ACT_RELU = 1, AVEC_ACT_SWISH = 2 };
 int avec_bn_finalize(const float* stats, const float* gamma, const float* beta, float* scale, float* shift, float* mean,
                      float* rstd, float* running_mean, float* running_var, long long count, int C, float eps,
-                     float momentum, avec_stream_t stream);
+                     float momentum, int replicas, avec_stream_t stream);
 int avec_bn_eval_affine(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
                         float* scale, float* shift, int C, float eps, avec_stream_t stream);
 int avec_bn_stats(const void* u, int dtype, long long rows, int C, float* stats, avec_stream_t stream);

@@ -78,8 +78,9 @@ def test_conv2d_fwd_dgrad_wgrad(impl, dtype, tol, N, H, W, Ci, Co, k, s):
         xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
         wr = w.float().requires_grad_(True)
         yr = F.conv2d(F.pad(xr, (p, k // 2, p, k // 2)), wr, None, stride=s)
-        stats = torch.zeros(2 * Co, device=DEV)
-        y = ops.conv_fwd(x, wp, g, colstats=stats)
+        stats_r = torch.zeros(L.STATS_REPLICAS * 2 * Co, device=DEV)
+        y = ops.conv_fwd(x, wp, g, colstats=stats_r)
+        stats = stats_r.view(L.STATS_REPLICAS, 2 * Co).sum(0)
         yr_cl = yr.permute(0, 2, 3, 1).reshape(-1, Co)
         _close(y, yr_cl, tol)
         _close(stats[:Co], yr_cl.sum(0), 1e-2 if dtype == torch.bfloat16 else 1e-4)

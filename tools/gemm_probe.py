@@ -47,7 +47,7 @@ for N, H, W, Ci, Co, k, s in [(6464, 22, 22, 64, 64, 3, 1), (6464, 22, 22, 64, 1
     wp = torch.randn(Co, k * k * Ci, device=dev, dtype=bf)
     wd = torch.randn(Ci, k * k * Co, device=dev, dtype=bf)
     dy = torch.randn(ops.geom_sites(g), Co, device=dev, dtype=bf)
-    st = torch.zeros(2 * Co, device=dev)
+    st = torch.zeros(32 * 2 * Co, device=dev)
     fl = 2.0 * ops.geom_sites(g) * Co * k * k * Ci
     for name, fn in [("fwd", lambda: ops.conv_fwd(x, wp, g, colstats=st)), ("dgrad", lambda: ops.conv_dgrad(dy, wd, g)),
                      ("wgrad", lambda: ops.conv_wgrad(dy, x, g))]:
@@ -63,7 +63,7 @@ dy = torch.randn(ops.geom_sites(g), 64, device=dev, dtype=bf)
 fl = 2.0 * ops.geom_sites(g) * 64 * 245
 col = ops.im2col_c1(x, g, 256)
 wp256 = torch.randn(64, 256, device=dev, dtype=bf)
-st = torch.zeros(128, device=dev)
+st = torch.zeros(32 * 128, device=dev)
 for name, fn in [("im2col", lambda: ops.im2col_c1(x, g, 256)), ("fwd", lambda: ops.linear_fwd(col, wp256, None, colstats=st)),
                  ("wgrad", lambda: ops.linear_wgrad(dy, col))]:
     ms = timeit(fn, 3)

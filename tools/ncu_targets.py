@@ -24,7 +24,7 @@ if which in ("all", "conv1"):     # ResNet stage-1 conv forward with BatchNorm s
     x = torch.randn(N, H, W, C, device=dev, dtype=bf)
     g = ops.make_geom(N, 1, H, W, C, C, (1, 3, 3), (1, 1, 1), (0, 1, 1))
     wp = torch.randn(C, 9 * C, device=dev, dtype=bf)
-    st = torch.zeros(2 * C, device=dev)
+    st = torch.zeros(32 * 2 * C, device=dev)
     rep(lambda: ops.conv_fwd(x, wp, g, colstats=st))
     dy = torch.randn(N * H * W, C, device=dev, dtype=bf)
     rep(lambda: ops.conv_wgrad(dy, x, g))

@@ -33,7 +33,7 @@ N, H, W, C = 6464, 22, 22, 64
 xi = torch.randn(N, H, W, C, device=dev, dtype=bf)
 g = ops.make_geom(N, 1, H, W, C, C, (1, 3, 3), (1, 1, 1), (0, 1, 1))
 wp = torch.randn(C, 9 * C, device=dev, dtype=bf)
-st = torch.zeros(2 * C, device=dev)
+st = torch.zeros(32 * 2 * C, device=dev)
 run("conv stage-1 fwd + stats", lambda: ops.conv_fwd(xi, wp, g, colstats=st))
 run("conv stage-1 fwd no stats", lambda: ops.conv_fwd(xi, wp, g))
 N, H, W, C = 6464, 6, 6, 256
