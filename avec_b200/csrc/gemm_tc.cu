@@ -16,6 +16,7 @@
 #include <cstring>
 #include <cstdint>
 #include <cstdlib>
+#include <algorithm>
 
 namespace {
 
@@ -64,6 +65,7 @@ struct TcParams {
     int ct_BH, ct_BI, ct_tph;   // tile rows, images per tile, tiles per image (on the conv's OUTPUT grid ct_H x ct_W)
     int ct_H, ct_W, ct_s;       // output grid and spatial stride (1 or 2; strided taps use the tensor map's element strides)
     int ct_dgrad;               // tap shift sign (dgrad reads dy[p + pad - tap])
+    int grid_m, grid_n, splits; // tile grid (the launch grid is min(#tiles, resident CTAs): persistent tile loop)
     unsigned long long* dbg_ts; // diagnostics (avec_set_debug_timestamps): CTA (0,0,0) records globaltimer at phase boundaries
     int dbg_rowofs;             // diagnostics (AVEC_DEBUG_ROWOFS): A tile loaded `ofs` rows early, descriptor started `ofs` rows in
 };
@@ -451,6 +453,34 @@ __device__ __forceinline__ void tma_fill(const TcParams& p, int kind, const CUte
     }
 }
 
+struct TileInfo {
+    int mtile, n0, z, kb_begin, nkb, m0, rows_valid;
+    long long row_base;
+};
+
+__device__ __forceinline__ TileInfo decode_tile(const TcParams& p, int t) {
+    TileInfo ti;
+    ti.mtile = t % p.grid_m; t /= p.grid_m;
+    ti.n0 = (t % p.grid_n) * p.BN;
+    ti.z = t / p.grid_n;
+    ti.kb_begin = ti.z * p.kb_per_split;
+    ti.nkb = min(p.num_kb, ti.kb_begin + p.kb_per_split) - ti.kb_begin;
+    ti.m0 = ti.mtile * BM;
+    if (p.conv_tiles && p.a_kind == OP_TMA_CONV_K) {
+        int tn0, th0;
+        conv_tile_origin(p, ti.mtile, tn0, th0);
+        ti.row_base = ((long long)tn0 * p.ct_H + th0) * p.ct_W;
+        ti.rows_valid = p.ct_BI == 1 ? min(p.ct_BH, p.ct_H - th0) * p.ct_W : min(p.ct_BI, p.g.N - tn0) * p.ct_H * p.ct_W;
+    } else {
+        ti.row_base = ti.m0;
+        ti.rows_valid = min(BM, p.M - ti.m0);
+    }
+    return ti;
+}
+
+// Persistent, warp-specialised: every CTA walks the tile list t = blockIdx.x, blockIdx.x + gridDim.x, ... ; the smem ring
+// and its phases run on across tiles, and the accumulator is double-buffered in TMEM (2 x BN columns) so that the epilogue
+// of tile j overlaps the TMA + MMA main loop of tile j + 1.
 __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUtensorMap mapA,
                                                                const __grid_constant__ CUtensorMap mapB) {
     extern __shared__ uint8_t smem_raw[];
@@ -462,8 +492,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
     uint8_t* ctrl = smem + (size_t)p.stages * stage_bytes;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);
     uint64_t* empty_bar = full_bar + 8;
-    uint64_t* accum_bar = empty_bar + 8;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+    uint64_t* accum_full = empty_bar + 8;    // [2]
+    uint64_t* accum_empty = accum_full + 2;  // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_empty + 2);
     RowInfo* rinfo = reinterpret_cast<RowInfo*>(ctrl + 256);
     int* tapofs = reinterpret_cast<int*>(ctrl + 256 + BM * sizeof(RowInfo));
     float* cstat = reinterpret_cast<float*>(ctrl + 256 + BM * sizeof(RowInfo) + 256 * sizeof(int));  // [2][256]
@@ -471,36 +502,18 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) AVEC_TS(0);   // kernel start
-    const int mtile = blockIdx.x;
-    const int n0 = blockIdx.y * BN;
-    const int kb_begin = blockIdx.z * p.kb_per_split;
-    const int kb_end = min(p.num_kb, kb_begin + p.kb_per_split);
-    const int nkb = kb_end - kb_begin;
     const bool a_tma = is_tma(p.a_kind), b_tma = is_tma(p.b_kind);
     const bool any_gather = !a_tma || !b_tma, any_tma = a_tma || b_tma;
+    const int tiles_total = p.grid_m * p.grid_n * p.splits;
 
-    // output rows of this tile: row_base + r, r < rows_valid
-    long long row_base;
-    int rows_valid;
-    int m0 = mtile * BM;   // first A row (plain / gather kinds)
-    if (p.conv_tiles && p.a_kind == OP_TMA_CONV_K) {
-        int tn0, th0;
-        conv_tile_origin(p, mtile, tn0, th0);
-        row_base = ((long long)tn0 * p.ct_H + th0) * p.ct_W;
-        rows_valid = p.ct_BI == 1 ? min(p.ct_BH, p.ct_H - th0) * p.ct_W : min(p.ct_BI, p.g.N - tn0) * p.ct_H * p.ct_W;
-    } else {
-        row_base = m0;
-        rows_valid = min(BM, p.M - m0);
-    }
-
-    // TMEM columns: power of two >= 32 covering BN
+    // TMEM columns: two accumulator buffers of BN columns, power of two >= 32
     uint32_t ncols = 32;
-    while ((int)ncols < BN) ncols <<= 1;
+    while ((int)ncols < 2 * BN) ncols <<= 1;
 
     if (tid == 0) {
         const uint32_t full_count = (any_gather ? PRODUCER_THREADS : 0) + (any_tma ? 1 : 0);
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], full_count); mbar_init(&empty_bar[s], 1); }
-        mbar_init(accum_bar, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&accum_full[i], 1); mbar_init(&accum_empty[i], PRODUCER_THREADS); }
         fence_barrier_init();
         if (a_tma) tma_prefetch_desc(&mapA);
         if (b_tma) tma_prefetch_desc(&mapB);
@@ -513,27 +526,6 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
             tapofs[tap] = kt | (kh << 8) | (kw << 16);
         }
     }
-    // per-row site decode for the conv gathers (A operand rows are fixed for the whole tile)
-    if (tid < BM && (p.a_kind == OP_CONV_FWD || p.a_kind == OP_CONV_DGRAD || p.a_kind == OP_CONV_TAPS)) {
-        RowInfo ri; ri.n = -1; ri.t = ri.h = ri.w = 0;
-        long long m = (long long)m0 + tid;
-        if (m < p.M) {
-            if (p.a_kind != OP_CONV_DGRAD) {
-                int wo = (int)(m % p.g.Wo); m /= p.g.Wo; int ho = (int)(m % p.g.Ho); m /= p.g.Ho; int to = (int)(m % p.g.To);
-                ri.n = (int)(m / p.g.To);
-                ri.t = to * p.g.st - p.g.pt; ri.h = ho * p.g.sh - p.g.ph; ri.w = wo * p.g.sw - p.g.pw;
-            } else {
-                int wi = (int)(m % p.g.Wi); m /= p.g.Wi; int hi = (int)(m % p.g.Hi); m /= p.g.Hi; int ti = (int)(m % p.g.Ti);
-                ri.n = (int)(m / p.g.Ti);
-                ri.t = ti + p.g.pt; ri.h = hi + p.g.ph; ri.w = wi + p.g.pw;
-            }
-        }
-        rinfo[tid] = ri;
-    }
-    // bias slice of this tile (0 where absent / beyond N / for split-K slices other than the first) and zeroed statistics
-    for (int c = tid; c < 256; c += TC_THREADS)
-        bias_s[c] = (p.ep.bias && blockIdx.z == 0 && c < BN && n0 + c < p.N) ? p.ep.bias[n0 + c] : 0.0f;
-    if (p.ep.colstats) for (int c = tid; c < 512; c += TC_THREADS) cstat[c] = 0.0f;
     // MN-major TMA tiles whose k extent (conv tile rows) is not a multiple of 16: the tail rows are never written by TMA
     // and must read as zeros -> clear all stages once (generic proxy), then hand the buffers to the async proxy
     if (p.a_kind == OP_TMA_CONV_MN || p.b_kind == OP_TMA_CONV_MN) {
@@ -549,45 +541,75 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
     if (tid == 0) AVEC_TS(1);   // setup done (barriers, TMEM alloc)
 
     if (warp < 4) {
-        // ===================== gather producers =====================
-        if (any_gather) {
-            // cp.async groups: k-block i is published (proxy fence + mbarrier arrive) LAG iterations after it was issued, so
-            // each thread keeps up to LAG+1 k-blocks of loads in flight (stages >= LAG + 1)
-            constexpr int LAG = 2;
-            for (int i = 0; i < nkb + LAG; ++i) {
-                if (i < nkb) {
-                    const int s = i % p.stages;
-                    const uint32_t ph = (uint32_t)((i / p.stages) & 1);
-                    mbar_wait(&empty_bar[s], ph ^ 1u);
-                    uint8_t* a_tile = smem + (size_t)s * stage_bytes;
-                    uint8_t* b_tile = a_tile + a_bytes;
-                    const int kb = kb_begin + i;
-                    if (!a_tma) fill_operand(a_tile, p.a_rows, p.a_kind, p.A, p.a_ld, p.a_align, p.M, p.K, m0, kb, p, rinfo, tapofs, tid);
-                    if (!b_tma) fill_operand(b_tile, p.b_rows, p.b_kind, p.B, p.b_ld, p.b_align, p.N, p.K, n0, kb, p, rinfo, tapofs, tid);
+        // ===================== gather producers (when an operand is not TMA-fed), then epilogue =====================
+        int it = 0;   // k-blocks pushed through the ring so far
+        int j = 0;    // local tile counter
+        for (int t = blockIdx.x; t < tiles_total; t += gridDim.x, ++j) {
+            const TileInfo ti = decode_tile(p, t);
+            const int n0 = ti.n0, nkb = ti.nkb;
+            asm volatile("bar.sync 1, 128;" ::: "memory");   // previous tile's epilogue has released bias_s / cstat / rinfo
+            for (int c = tid; c < 256; c += PRODUCER_THREADS)
+                bias_s[c] = (p.ep.bias && ti.z == 0 && c < BN && n0 + c < p.N) ? p.ep.bias[n0 + c] : 0.0f;
+            if (p.ep.colstats) for (int c = tid; c < 512; c += PRODUCER_THREADS) cstat[c] = 0.0f;
+            if (p.a_kind == OP_CONV_FWD || p.a_kind == OP_CONV_DGRAD || p.a_kind == OP_CONV_TAPS) {
+                // per-row site decode for the conv gathers (A operand rows are fixed for the whole tile)
+                RowInfo ri; ri.n = -1; ri.t = ri.h = ri.w = 0;
+                long long m = (long long)ti.m0 + tid;
+                if (m < p.M) {
+                    if (p.a_kind != OP_CONV_DGRAD) {
+                        int wo = (int)(m % p.g.Wo); m /= p.g.Wo; int ho = (int)(m % p.g.Ho); m /= p.g.Ho; int to = (int)(m % p.g.To);
+                        ri.n = (int)(m / p.g.To);
+                        ri.t = to * p.g.st - p.g.pt; ri.h = ho * p.g.sh - p.g.ph; ri.w = wo * p.g.sw - p.g.pw;
+                    } else {
+                        int wi = (int)(m % p.g.Wi); m /= p.g.Wi; int hi = (int)(m % p.g.Hi); m /= p.g.Hi; int ti_ = (int)(m % p.g.Ti);
+                        ri.n = (int)(m / p.g.Ti);
+                        ri.t = ti_ + p.g.pt; ri.h = hi + p.g.ph; ri.w = wi + p.g.pw;
+                    }
                 }
-                cp_async_commit();
-                if (i >= LAG) {
-                    cp_async_wait<LAG>();
-                    fence_proxy_async();
-                    mbar_arrive(&full_bar[(i - LAG) % p.stages]);
+                rinfo[tid] = ri;
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (any_gather) {
+                // cp.async groups: k-block i is published (proxy fence + mbarrier arrive) LAG iterations after it was issued,
+                // so each thread keeps up to LAG+1 k-blocks of loads in flight (stages >= LAG + 1)
+                constexpr int LAG = 2;
+                for (int i = 0; i < nkb + LAG; ++i) {
+                    if (i < nkb) {
+                        const int g = it + i;
+                        const int s = g % p.stages;
+                        const uint32_t ph = (uint32_t)((g / p.stages) & 1);
+                        mbar_wait(&empty_bar[s], ph ^ 1u);
+                        uint8_t* a_tile = smem + (size_t)s * stage_bytes;
+                        uint8_t* b_tile = a_tile + a_bytes;
+                        const int kb = ti.kb_begin + i;
+                        if (!a_tma) fill_operand(a_tile, p.a_rows, p.a_kind, p.A, p.a_ld, p.a_align, p.M, p.K, ti.m0, kb, p, rinfo, tapofs, tid);
+                        if (!b_tma) fill_operand(b_tile, p.b_rows, p.b_kind, p.B, p.b_ld, p.b_align, p.N, p.K, n0, kb, p, rinfo, tapofs, tid);
+                    }
+                    cp_async_commit();
+                    if (i >= LAG) {
+                        cp_async_wait<LAG>();
+                        fence_proxy_async();
+                        mbar_arrive(&full_bar[(it + i - LAG) % p.stages]);
+                    }
                 }
             }
-        }
-        // ===================== epilogue =====================
-        const int r = warp * 32 + lane;
-        const bool rv = r < rows_valid;
-        const long long row = row_base + r;
-        // pull this thread's residual / auxiliary row segment towards L1 while the MMAs are still running
-        if (rv && p.ep.aux && !p.out_transposed) {
-            const int esz = p.ep.aux_dtype == AVEC_F32 ? 4 : 2;
-            const char* a0 = reinterpret_cast<const char*>(p.ep.aux) + ((size_t)row * p.ep.ldaux + n0) * esz;
-            const int nbytes = min(BN, p.N - n0) * esz;
-            for (int o = 0; o < nbytes; o += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(a0 + o));
-        }
-        mbar_wait(accum_bar, 0u);
-        tc_fence_after();
-        if (tid == 0) AVEC_TS(4);   // accumulator complete, epilogue starts
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+            it += nkb;
+            // ---------------- epilogue of tile j (accumulator buffer j & 1) ----------------
+            const int buf = j & 1;
+            const int r = warp * 32 + lane;
+            const bool rv = r < ti.rows_valid;
+            const long long row = ti.row_base + r;
+            // pull this thread's residual / auxiliary row segment towards L1 while the MMAs are still running
+            if (rv && p.ep.aux && !p.out_transposed) {
+                const int esz = p.ep.aux_dtype == AVEC_F32 ? 4 : 2;
+                const char* a0 = reinterpret_cast<const char*>(p.ep.aux) + ((size_t)row * p.ep.ldaux + n0) * esz;
+                const int nbytes = min(BN, p.N - n0) * esz;
+                for (int o = 0; o < nbytes; o += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(a0 + o));
+            }
+            mbar_wait(&accum_full[buf], (uint32_t)((j >> 1) & 1));
+            tc_fence_after();
+            if (tid == 0 && j == 0) AVEC_TS(4);   // accumulator complete, epilogue starts
+            const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * BN);
         EpiParams ep = p.ep;
         ep.bias = nullptr;   // the bias slice lives in shared memory (bias_s)
         const bool fast_kind = !p.out_transposed && ep.kind != AVEC_EPI_ACCUM;
@@ -689,28 +711,38 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
                 }
             }
         }
-        if (ep.colstats) {
-            // one of AVEC_STATS_REPLICAS copies of the accumulator (by CTA index): 32x fewer same-address L2 atomics
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            float* dst = ep.colstats + (size_t)(blockIdx.x % AVEC_STATS_REPLICAS) * 2 * p.N;
-            for (int cc = tid; cc < BN; cc += PRODUCER_THREADS)
-                if (n0 + cc < p.N) { atomicAdd(dst + n0 + cc, cstat[cc]); atomicAdd(dst + p.N + n0 + cc, cstat[256 + cc]); }
+            // all TMEM reads of this buffer are complete: hand it back to the MMA warp
+            tc_fence_before();
+            mbar_arrive(&accum_empty[buf]);
+            if (ep.colstats) {
+                // one of AVEC_STATS_REPLICAS copies of the accumulator (by tile index): 32x fewer same-address L2 atomics
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                float* dst = ep.colstats + (size_t)(ti.mtile % AVEC_STATS_REPLICAS) * 2 * p.N;
+                for (int cc = tid; cc < BN; cc += PRODUCER_THREADS)
+                    if (n0 + cc < p.N) { atomicAdd(dst + n0 + cc, cstat[cc]); atomicAdd(dst + p.N + n0 + cc, cstat[256 + cc]); }
+            }
+            if (tid == 0 && j == 0) AVEC_TS(5);   // epilogue done
         }
-        if (tid == 0) AVEC_TS(5);   // epilogue done
         tc_fence_before();
     } else if (warp == 5) {
         // ===================== TMA producer (one thread) =====================
         if (any_tma && lane == 0) {
-            for (int i = 0; i < nkb; ++i) {
-                const int s = i % p.stages;
-                const uint32_t ph = (uint32_t)((i / p.stages) & 1);
-                mbar_wait(&empty_bar[s], ph ^ 1u);
-                uint8_t* a_tile = smem + (size_t)s * stage_bytes;
-                uint8_t* b_tile = a_tile + a_bytes;
-                const int kb = kb_begin + i;
-                mbar_expect_tx(&full_bar[s], (uint32_t)((a_tma ? p.a_tx : 0) + (b_tma ? p.b_tx : 0)));
-                if (a_tma) tma_fill(p, p.a_kind, &mapA, a_tile, &full_bar[s], p.a_rows, p.a_group_stride, m0, kb, mtile, true);
-                if (b_tma) tma_fill(p, p.b_kind, &mapB, b_tile, &full_bar[s], p.b_rows, p.b_group_stride, n0, kb, mtile, false);
+            int it = 0;
+            for (int t = blockIdx.x; t < tiles_total; t += gridDim.x) {
+                const TileInfo ti = decode_tile(p, t);
+                for (int i = 0; i < ti.nkb; ++i) {
+                    const int g = it + i;
+                    const int s = g % p.stages;
+                    const uint32_t ph = (uint32_t)((g / p.stages) & 1);
+                    mbar_wait(&empty_bar[s], ph ^ 1u);
+                    uint8_t* a_tile = smem + (size_t)s * stage_bytes;
+                    uint8_t* b_tile = a_tile + a_bytes;
+                    const int kb = ti.kb_begin + i;
+                    mbar_expect_tx(&full_bar[s], (uint32_t)((a_tma ? p.a_tx : 0) + (b_tma ? p.b_tx : 0)));
+                    if (a_tma) tma_fill(p, p.a_kind, &mapA, a_tile, &full_bar[s], p.a_rows, p.a_group_stride, ti.m0, kb, ti.mtile, true);
+                    if (b_tma) tma_fill(p, p.b_kind, &mapB, b_tile, &full_bar[s], p.b_rows, p.b_group_stride, ti.n0, kb, ti.mtile, false);
+                }
+                it += ti.nkb;
             }
         }
     } else {
@@ -718,26 +750,36 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
         const int a_mn = is_mn(p.a_kind) ? 1 : 0;
         const int b_mn = is_mn(p.b_kind) ? 1 : 0;
         const uint32_t idesc = make_idesc(BN, a_mn, b_mn);
-        for (int i = 0; i < nkb; ++i) {
-            const int s = i % p.stages;
-            const uint32_t ph = (uint32_t)((i / p.stages) & 1);
-            mbar_wait(&full_bar[s], ph);
+        int it = 0, j = 0;
+        for (int t = blockIdx.x; t < tiles_total; t += gridDim.x, ++j) {
+            const TileInfo ti = decode_tile(p, t);
+            const int buf = j & 1;
+            mbar_wait(&accum_empty[buf], (uint32_t)(((j >> 1) & 1) ^ 1));   // epilogue has drained this accumulator buffer
             tc_fence_after();
-            if (lane == 0) {
-                if (i == 0) AVEC_TS(2);   // first k-block landed in shared memory
-                const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes) + (uint32_t)p.dbg_rowofs * 128u;
-                const uint32_t b_addr = smem_u32(smem + (size_t)s * stage_bytes) + a_bytes;
-                for (int k = 0; k < p.ksteps; ++k) {
-                    // K-major: advance 32 bytes inside the 128-byte swizzle row; SBO = 1024 (8 rows).
-                    // MN-major: advance 16 reduction rows = 2048 bytes; LBO = next 64-wide MN group, SBO = 1024.
-                    const uint64_t adesc = a_mn ? make_smem_desc(a_addr + k * 2048, p.a_group_stride, 1024) : make_smem_desc(a_addr + k * 32, 16, 1024);
-                    const uint64_t bdesc = b_mn ? make_smem_desc(b_addr + k * 2048, p.b_group_stride, 1024) : make_smem_desc(b_addr + k * 32, 16, 1024);
-                    umma_f16(tmem_base, adesc, bdesc, idesc, (i > 0 || k > 0) ? 1u : 0u);
+            const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+            for (int i = 0; i < ti.nkb; ++i) {
+                const int g = it + i;
+                const int s = g % p.stages;
+                const uint32_t ph = (uint32_t)((g / p.stages) & 1);
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                if (lane == 0) {
+                    if (i == 0 && j == 0) AVEC_TS(2);   // first k-block landed in shared memory
+                    const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes) + (uint32_t)p.dbg_rowofs * 128u;
+                    const uint32_t b_addr = smem_u32(smem + (size_t)s * stage_bytes) + a_bytes;
+                    for (int k = 0; k < p.ksteps; ++k) {
+                        // K-major: advance 32 bytes inside the 128-byte swizzle row; SBO = 1024 (8 rows).
+                        // MN-major: advance 16 reduction rows = 2048 bytes; LBO = next 64-wide MN group, SBO = 1024.
+                        const uint64_t adesc = a_mn ? make_smem_desc(a_addr + k * 2048, p.a_group_stride, 1024) : make_smem_desc(a_addr + k * 32, 16, 1024);
+                        const uint64_t bdesc = b_mn ? make_smem_desc(b_addr + k * 2048, p.b_group_stride, 1024) : make_smem_desc(b_addr + k * 32, 16, 1024);
+                        umma_f16(d_tmem, adesc, bdesc, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[s]);
+                    if (i == ti.nkb - 1) { umma_commit(&accum_full[buf]); if (j == 0) AVEC_TS(3); }   // last MMA of the tile issued
                 }
-                umma_commit(&empty_bar[s]);
-                if (i == nkb - 1) { umma_commit(accum_bar); AVEC_TS(3); }   // last MMA issued
+                __syncwarp();
             }
-            __syncwarp();
+            it += ti.nkb;
         }
         tc_fence_before();
     }
@@ -964,9 +1006,20 @@ int avec_gemm_tc(const avec_gemm_args* a, cudaStream_t st) {
         if (cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return AVEC_ERR_LAUNCH;
         attr_set = true;
     }
-    dim3 grid(grid_m, cdiv(a->N, p.BN), split);
-    if (grid.y > 65535u || grid.z > 65535u) return AVEC_ERR_INVALID;
-    gemm_tc_kernel<<<grid, TC_THREADS, smem, st>>>(p, mapA, mapB);
+    p.grid_m = grid_m; p.grid_n = cdiv(a->N, p.BN); p.splits = split;
+    const long long tiles = (long long)p.grid_m * p.grid_n * p.splits;
+    if (tiles > 0x7fffffffLL) return AVEC_ERR_INVALID;
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
+    }
+    // persistent launch when both operands are TMA-fed (the gather producers double as epilogue warps, so gather kinds keep
+    // one tile per CTA); two CTAs per SM when shared memory and TMEM (2 x BN columns each) allow it
+    const int occ = (smem <= 113 * 1024 && p.BN <= 128) ? 2 : 1;
+    long long ctas = any_gather ? tiles : std::min<long long>(tiles, (long long)num_sms * occ);
+    gemm_tc_kernel<<<(unsigned)ctas, TC_THREADS, smem, st>>>(p, mapA, mapB);
     AVEC_LAUNCH_CHECK();
     return AVEC_OK;
 }
