@@ -65,6 +65,7 @@ struct TcParams {
     int ct_BH, ct_BI, ct_tph;   // tile rows, images per tile, tiles per image (on the conv's OUTPUT grid ct_H x ct_W)
     int ct_H, ct_W, ct_s;       // output grid and spatial stride (1 or 2; strided taps use the tensor map's element strides)
     int ct_dgrad;               // tap shift sign (dgrad reads dy[p + pad - tap])
+    int stg_dedicated;          // 1: epilogue staging has its own shared memory (persistent launches); 0: it aliases the drained ring
     int grid_m, grid_n, splits; // tile grid (the launch grid is min(#tiles, resident CTAs): persistent tile loop)
     unsigned long long* dbg_ts; // diagnostics (avec_set_debug_timestamps): CTA (0,0,0) records globaltimer at phase boundaries
     int dbg_rowofs;             // diagnostics (AVEC_DEBUG_ROWOFS): A tile loaded `ofs` rows early, descriptor started `ofs` rows in
@@ -478,6 +479,184 @@ __device__ __forceinline__ TileInfo decode_tile(const TcParams& p, int t) {
     return ti;
 }
 
+
+// ---- 8 consecutive columns of one output row (transposed-domain epilogue: 8 lanes cover one 64-column row segment)
+__device__ __forceinline__ void load8(const void* p, int dtype, size_t idx, float (&v)[8]) {
+    if (dtype == AVEC_F32) {
+        const float* q = reinterpret_cast<const float*>(p) + idx;
+        if ((reinterpret_cast<uintptr_t>(q) & 15) == 0) {
+            float4 a = __ldg(reinterpret_cast<const float4*>(q)), b = __ldg(reinterpret_cast<const float4*>(q) + 1);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __ldg(q + i);
+        }
+    } else {
+        const bf16* q = reinterpret_cast<const bf16*>(p) + idx;
+        const uintptr_t a = reinterpret_cast<uintptr_t>(q);
+        uint32_t w[4];
+        if ((a & 15) == 0) { uint4 t = __ldg(reinterpret_cast<const uint4*>(q)); w[0] = t.x; w[1] = t.y; w[2] = t.z; w[3] = t.w; }
+        else if ((a & 7) == 0) { uint2 t0 = __ldg(reinterpret_cast<const uint2*>(q)), t1 = __ldg(reinterpret_cast<const uint2*>(q) + 1); w[0] = t0.x; w[1] = t0.y; w[2] = t1.x; w[3] = t1.y; }
+        else if ((a & 3) == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) w[i] = __ldg(reinterpret_cast<const uint32_t*>(q) + i);
+        } else {
+            const unsigned short* h = reinterpret_cast<const unsigned short*>(q);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) w[i] = (uint32_t)__ldg(h + 2 * i) | ((uint32_t)__ldg(h + 2 * i + 1) << 16);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u); }
+    }
+}
+__device__ __forceinline__ void store8(void* p, int dtype, size_t idx, const float (&v)[8]) {
+    if (dtype == AVEC_F32) {
+        float* q = reinterpret_cast<float*>(p) + idx;
+        if ((reinterpret_cast<uintptr_t>(q) & 15) == 0) {
+            reinterpret_cast<float4*>(q)[0] = make_float4(v[0], v[1], v[2], v[3]);
+            reinterpret_cast<float4*>(q)[1] = make_float4(v[4], v[5], v[6], v[7]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) q[i] = v[i];
+        }
+    } else {
+        bf16* q = reinterpret_cast<bf16*>(p) + idx;
+        const uintptr_t a = reinterpret_cast<uintptr_t>(q);
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]); w[i] = *reinterpret_cast<uint32_t*>(&t); }
+        if ((a & 15) == 0) *reinterpret_cast<uint4*>(q) = make_uint4(w[0], w[1], w[2], w[3]);
+        else if ((a & 7) == 0) { reinterpret_cast<uint2*>(q)[0] = make_uint2(w[0], w[1]); reinterpret_cast<uint2*>(q)[1] = make_uint2(w[2], w[3]); }
+        else if ((a & 3) == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) reinterpret_cast<uint32_t*>(q)[i] = w[i];
+        } else {
+            unsigned short* h = reinterpret_cast<unsigned short*>(q);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { h[2 * i] = (unsigned short)(w[i] & 0xFFFF); h[2 * i + 1] = (unsigned short)(w[i] >> 16); }
+        }
+    }
+}
+
+constexpr int STG_LD = 68;                       // floats per staged row (64 columns + pad: conflict-free 128-bit accesses)
+constexpr int STG_WARP = 32 * STG_LD;            // floats per warp
+constexpr int STG_BYTES = 4 * STG_WARP * 4;      // 34816 bytes per CTA
+
+// Epilogue of one 128 x BN tile for one warp (32 accumulator rows).  The accumulator comes out of TMEM one ROW per lane
+// (tcgen05.ld 32x32b); writing global memory in that shape would touch 32 different cache lines per instruction, so the
+// 64-column slab is staged in shared memory and re-read TRANSPOSED: 8 lanes cover one row's 64 columns (one full 128-byte
+// line of bf16), 4 rows per instruction.  Bias, activation, residual / Swish' operands, fp32 split-K reductions and the
+// BatchNorm column statistics are all applied in that coalesced domain.
+__device__ __forceinline__ void epilogue_warp(const TcParams& p, const EpiParams& ep, const TileInfo& ti, uint32_t lane_addr, float* stg,
+                                              const float* bias_s, float* cstat, int warp, int lane) {
+    const int BN = p.BN;
+    const int q = lane & 7, rs = lane >> 3;
+    for (int c0 = 0; c0 < BN; c0 += 64) {
+        const int ncol = min(64, BN - c0);   // multiple of 16
+        // ---- row domain: TMEM -> registers (+ bias) -> staging
+        for (int cc = 0; cc < ncol; cc += 32) {
+            float v[32];
+            const bool two = ncol - cc >= 32;
+            if (two) tmem_ld32(lane_addr + (uint32_t)(c0 + cc), v);
+            else tmem_ld16(lane_addr + (uint32_t)(c0 + cc), *reinterpret_cast<float(*)[16]>(&v[0]));
+            const int nv = two ? 32 : 16;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                if (j < nv) {
+                    const float4 b = *reinterpret_cast<const float4*>(bias_s + c0 + cc + j);
+                    *reinterpret_cast<float4*>(stg + lane * STG_LD + cc + j) = make_float4(v[j] + b.x, v[j + 1] + b.y, v[j + 2] + b.z, v[j + 3] + b.w);
+                }
+            }
+        }
+        __syncwarp();
+        // ---- transposed domain
+        float s1[8], s2[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s1[j] = 0.0f; s2[j] = 0.0f; }
+        const int lc = q * 8;                 // column inside the slab
+        const int gc = ti.n0 + c0 + lc;       // global column
+        if (lc < ncol) {
+#pragma unroll 2
+            for (int pass = 0; pass < 8; ++pass) {
+                const int rr = pass * 4 + rs;
+                const int r = warp * 32 + rr;
+                if (r >= ti.rows_valid) continue;
+                const long long row = ti.row_base + r;
+                float a[8];
+                {
+                    const float4 t0 = *reinterpret_cast<const float4*>(stg + rr * STG_LD + lc);
+                    const float4 t1 = *reinterpret_cast<const float4*>(stg + rr * STG_LD + lc + 4);
+                    a[0] = t0.x; a[1] = t0.y; a[2] = t0.z; a[3] = t0.w; a[4] = t1.x; a[5] = t1.y; a[6] = t1.z; a[7] = t1.w;
+                }
+                if (gc + 8 <= p.N) {
+                    const size_t oi = (size_t)row * ep.ldo + gc;
+                    float o[8];
+                    if (ep.kind == AVEC_EPI_ACCUM) {
+                        float* dst = reinterpret_cast<float*>(ep.out) + oi;
+                        if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(ep.alpha * a[0]), "f"(ep.alpha * a[1]),
+                                         "f"(ep.alpha * a[2]), "f"(ep.alpha * a[3]) : "memory");
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(ep.alpha * a[4]), "f"(ep.alpha * a[5]),
+                                         "f"(ep.alpha * a[6]), "f"(ep.alpha * a[7]) : "memory");
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) atomicAdd(dst + j, ep.alpha * a[j]);
+                        }
+                    } else {
+                        if (ep.kind == AVEC_EPI_LINEAR) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) o[j] = ep.alpha * a[j];
+                        } else if (ep.kind == AVEC_EPI_SWISH) {
+                            if (ep.out2) store8(ep.out2, ep.out2_dtype, (size_t)row * ep.ldo2 + gc, a);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) o[j] = swishf_(a[j]);
+                        } else {
+                            float x[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) x[j] = 0.0f;
+                            if (ep.aux) load8(ep.aux, ep.aux_dtype, (size_t)row * ep.ldaux + gc, x);
+                            if (ep.kind == AVEC_EPI_RESIDUAL) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) o[j] = x[j] + ep.alpha * a[j];
+                            } else if (ep.kind == AVEC_EPI_DSWISH) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) o[j] = ep.alpha * a[j] * dswishf_(x[j]);
+                            } else {  // RELU
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) o[j] = fmaxf(ep.alpha * a[j] + x[j], 0.0f);
+                            }
+                        }
+                        store8(ep.out, ep.out_dtype, oi, o);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { s1[j] += a[j]; s2[j] += a[j] * a[j]; }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (gc + j < p.N) {
+                            epilogue_elem(ep, (int)row, gc + j, a[j]);   // bias already added (ep.bias == nullptr)
+                            s1[j] += a[j]; s2[j] += a[j] * a[j];
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (ep.colstats) {
+            // lanes with equal q hold partial sums of the same 8 columns: fold the 4 row groups, then one shared atomic each
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 8);  s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 8);
+                s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 16); s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 16);
+            }
+            if (rs == 0 && lc < ncol) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { atomicAdd(&cstat[c0 + lc + j], s1[j]); atomicAdd(&cstat[256 + c0 + lc + j], s2[j]); }
+            }
+        }
+    }
+}
+
 // Persistent, warp-specialised: every CTA walks the tile list t = blockIdx.x, blockIdx.x + gridDim.x, ... ; the smem ring
 // and its phases run on across tiles, and the accumulator is double-buffered in TMEM (2 x BN columns) so that the epilogue
 // of tile j overlaps the TMA + MMA main loop of tile j + 1.
@@ -489,7 +668,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
     const int a_bytes = p.a_rows * 128;
     const int b_bytes = ((p.b_rows * 128 + 1023) / 1024) * 1024;
     const int stage_bytes = a_bytes + b_bytes;
-    uint8_t* ctrl = smem + (size_t)p.stages * stage_bytes;
+    uint8_t* ctrl = smem + (size_t)p.stages * stage_bytes + (p.stg_dedicated ? STG_BYTES : 0);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);
     uint64_t* empty_bar = full_bar + 8;
     uint64_t* accum_full = empty_bar + 8;    // [2]
@@ -610,107 +789,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
             tc_fence_after();
             if (tid == 0 && j == 0) AVEC_TS(4);   // accumulator complete, epilogue starts
             const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * BN);
-        EpiParams ep = p.ep;
-        ep.bias = nullptr;   // the bias slice lives in shared memory (bias_s)
-        const bool fast_kind = !p.out_transposed && ep.kind != AVEC_EPI_ACCUM;
-        const bool need_aux = ep.aux != nullptr && (ep.kind == AVEC_EPI_RESIDUAL || ep.kind == AVEC_EPI_DSWISH || ep.kind == AVEC_EPI_RELU);
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            const int nch = (BN - c0 >= 32) ? 2 : 1;   // BN is a multiple of 16
-            const int c = n0 + c0;
-            // auxiliary operand of this 32-column group: issued before the TMEM load so that both latencies overlap
-            float x[32];
-            const bool full0 = fast_kind && rv && c + 16 <= p.N, full1 = nch == 2 && fast_kind && rv && c + 32 <= p.N;
-            if (need_aux) {
-                if (full0) load16(ep.aux, ep.aux_dtype, (size_t)row * ep.ldaux + c, *reinterpret_cast<float(*)[16]>(&x[0]));
-                if (full1) load16(ep.aux, ep.aux_dtype, (size_t)row * ep.ldaux + c + 16, *reinterpret_cast<float(*)[16]>(&x[16]));
-            }
-            float v[32];
-            if (nch == 2) tmem_ld32(lane_addr + (uint32_t)c0, v);
-            else tmem_ld16(lane_addr + (uint32_t)c0, *reinterpret_cast<float(*)[16]>(&v[0]));
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                if (h >= nch) break;
-                float (&vv)[16] = *reinterpret_cast<float(*)[16]>(&v[16 * h]);
-                float (&xx)[16] = *reinterpret_cast<float(*)[16]>(&x[16 * h]);
-                const int ch = c + 16 * h;
-                const bool full = h == 0 ? full0 : full1;
-#pragma unroll
-                for (int j = 0; j < 16; ++j) vv[j] += bias_s[c0 + 16 * h + j];
-                if (ep.kind == AVEC_EPI_ACCUM && !p.out_transposed && rv && ch + 16 <= p.N &&
-                    ((reinterpret_cast<uintptr_t>(ep.out) + ((size_t)row * ep.ldo + ch) * 4) & 15) == 0) {
-                    // split-K partial sums: 4-wide vector reductions into the fp32 gradient (red.global.add.v4.f32)
-                    float* o = reinterpret_cast<float*>(ep.out) + (size_t)row * ep.ldo + ch;
-#pragma unroll
-                    for (int j = 0; j < 16; j += 4)
-                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + j), "f"(ep.alpha * vv[j]), "f"(ep.alpha * vv[j + 1]),
-                                     "f"(ep.alpha * vv[j + 2]), "f"(ep.alpha * vv[j + 3]) : "memory");
-                } else if (full) {
-                    float o[16];
-                    const size_t oi = (size_t)row * ep.ldo + ch;
-                    if (ep.kind == AVEC_EPI_LINEAR) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) o[j] = ep.alpha * vv[j];
-                    } else if (ep.kind == AVEC_EPI_SWISH) {
-                        if (ep.out2) store16(ep.out2, ep.out2_dtype, (size_t)row * ep.ldo2 + ch, vv);
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) o[j] = swishf_(vv[j]);
-                    } else if (ep.kind == AVEC_EPI_RESIDUAL) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) o[j] = xx[j] + ep.alpha * vv[j];
-                    } else if (ep.kind == AVEC_EPI_DSWISH) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) o[j] = ep.alpha * vv[j] * dswishf_(xx[j]);
-                    } else {  // RELU
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) o[j] = fmaxf(ep.alpha * vv[j] + (need_aux ? xx[j] : 0.0f), 0.0f);
-                    }
-                    store16(ep.out, ep.out_dtype, oi, o);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int cc = ch + j;
-                        if (rv && cc < p.N) {
-                            if (p.out_transposed) {
-                                size_t o = (size_t)cc * ep.ldo + row;
-                                if (ep.kind == AVEC_EPI_ACCUM) atomicAdd(reinterpret_cast<float*>(ep.out) + o, ep.alpha * vv[j]);
-                                else st_any(ep.out, ep.out_dtype, o, ep.alpha * vv[j]);
-                            } else {
-                                epilogue_elem(ep, (int)row, cc, vv[j]);   // bias already added (ep.bias == nullptr)
-                            }
-                        }
-                    }
-                }
-                if (ep.colstats) {
-                    // vv[] holds acc + bias.  Column sums over this warp's 32 rows by a shuffle reduce-scatter (16 + 16
-                    // shuffles): after the four halving steps lane l owns column 8*bit4 + 4*bit3 + 2*bit2 + bit1.
-                    float sa[16], sq[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) { const float xv = (rv && ch + j < p.N) ? vv[j] : 0.0f; sa[j] = xv; sq[j] = xv * xv; }
-#define AVEC_RS_STEP(W, MASK)                                                                       \
-                    {                                                                               \
-                        const bool hi = (lane & MASK) != 0;                                         \
-                        _Pragma("unroll") for (int j = 0; j < W; ++j) {                             \
-                            const float s_send = hi ? sa[j] : sa[j + W], s_keep = hi ? sa[j + W] : sa[j]; \
-                            const float q_send = hi ? sq[j] : sq[j + W], q_keep = hi ? sq[j + W] : sq[j]; \
-                            sa[j] = s_keep + __shfl_xor_sync(0xffffffffu, s_send, MASK);            \
-                            sq[j] = q_keep + __shfl_xor_sync(0xffffffffu, q_send, MASK);            \
-                        }                                                                           \
-                    }
-                    AVEC_RS_STEP(8, 16)
-                    AVEC_RS_STEP(4, 8)
-                    AVEC_RS_STEP(2, 4)
-                    AVEC_RS_STEP(1, 2)
-#undef AVEC_RS_STEP
-                    sa[0] += __shfl_xor_sync(0xffffffffu, sa[0], 1);
-                    sq[0] += __shfl_xor_sync(0xffffffffu, sq[0], 1);
-                    if ((lane & 1) == 0) {
-                        const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-                        atomicAdd(&cstat[c0 + 16 * h + col], sa[0]);
-                        atomicAdd(&cstat[256 + c0 + 16 * h + col], sq[0]);
-                    }
-                }
-            }
-        }
+            EpiParams ep = p.ep;
+            ep.bias = nullptr;   // the bias slice lives in shared memory (bias_s)
+            float* stg = (p.stg_dedicated ? reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes) : reinterpret_cast<float*>(smem)) + warp * STG_WARP;
+            epilogue_warp(p, ep, ti, lane_addr, stg, bias_s, cstat, warp, lane);
             // all TMEM reads of this buffer are complete: hand it back to the MMA warp
             tc_fence_before();
             mbar_arrive(&accum_empty[buf]);
@@ -995,12 +1077,24 @@ int avec_gemm_tc(const avec_gemm_args* a, cudaStream_t st) {
     p.kb_per_split = cdiv(p.num_kb, split);
     split = cdiv(p.num_kb, p.kb_per_split);
     const int stage_bytes = p.a_rows * 128 + cdiv(p.b_rows * 128, 1024) * 1024;
-    p.stages = stage_bytes <= 32 * 1024 ? 3 : 4;   // >= LAG + 1 = 3 (gather run-ahead); <= 32 KB stages allow 2 CTAs / SM
-    const size_t ctrl_bytes = 256 + BM * sizeof(RowInfo) + 256 * sizeof(int) + 768 * sizeof(float) + 1024;
-    while (p.stages > 2 && (size_t)p.stages * stage_bytes + ctrl_bytes > 227 * 1024) --p.stages;
     const bool any_gather = !is_tma(p.a_kind) || !is_tma(p.b_kind);
-    size_t smem = (size_t)p.stages * stage_bytes + ctrl_bytes;
-    if (smem > 227 * 1024 || (any_gather && p.stages < 3)) return AVEC_ERR_UNSUPPORTED;
+    const size_t ctrl_bytes = 256 + BM * sizeof(RowInfo) + 256 * sizeof(int) + 768 * sizeof(float) + 1024;
+    size_t smem;
+    if (any_gather) {
+        // one tile per CTA; the epilogue staging aliases the drained ring; <= 32 KB stages allow 2 CTAs / SM
+        p.stages = stage_bytes <= 32 * 1024 ? 3 : 4;   // >= LAG + 1 = 3 (cp.async run-ahead)
+        while (p.stages > 3 && (size_t)p.stages * stage_bytes + ctrl_bytes > 227 * 1024) --p.stages;
+        p.stg_dedicated = 0;
+        smem = (size_t)p.stages * stage_bytes + ctrl_bytes;
+        if (smem > 227 * 1024 || (size_t)p.stages * stage_bytes < STG_BYTES) return AVEC_ERR_UNSUPPORTED;
+    } else {
+        // persistent: one CTA per SM, as many ring stages as fit beside the dedicated epilogue staging
+        p.stg_dedicated = 1;
+        p.stages = 8;
+        while (p.stages > 2 && (size_t)p.stages * stage_bytes + STG_BYTES + ctrl_bytes > 227 * 1024) --p.stages;
+        smem = (size_t)p.stages * stage_bytes + STG_BYTES + ctrl_bytes;
+        if (smem > 227 * 1024) return AVEC_ERR_UNSUPPORTED;
+    }
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return AVEC_ERR_LAUNCH;
@@ -1017,8 +1111,7 @@ int avec_gemm_tc(const avec_gemm_args* a, cudaStream_t st) {
     }
     // persistent launch when both operands are TMA-fed (the gather producers double as epilogue warps, so gather kinds keep
     // one tile per CTA); two CTAs per SM when shared memory and TMEM (2 x BN columns each) allow it
-    const int occ = (smem <= 113 * 1024 && p.BN <= 128) ? 2 : 1;
-    long long ctas = any_gather ? tiles : std::min<long long>(tiles, (long long)num_sms * occ);
+    long long ctas = any_gather ? tiles : std::min<long long>(tiles, (long long)num_sms);
     gemm_tc_kernel<<<(unsigned)ctas, TC_THREADS, smem, st>>>(p, mapA, mapB);
     AVEC_LAUNCH_CHECK();
     return AVEC_OK;
