@@ -7,6 +7,16 @@
 
 namespace {
 
+// Grouped attention (GroupedRelPosMultiHeadSelfAttention.forwardQKV, reference nnet/attentions.py:579-650): a token is G
+// consecutive frames concatenated (G * D1 wide, split into H heads of d = G * D1 / H channels); frames past the real
+// length Tf are zero rows.  Element e = h * d + c of token `tok` therefore lives in frame tok * G + e / D1, column e % D1.
+// G = 1 is the plain layout.  `which` selects q (0), k (1) or v (2) inside the [frames, 3 * D1] matrix.
+template <typename T>
+__device__ __forceinline__ float fetch_qkv(const T* __restrict__ qkv_b, int tok, int e, int which, int G, int D1, int Tf) {
+    const int i = e / D1, col = e - i * D1, frame = tok * G + i;
+    return frame < Tf ? ldf(qkv_b + (size_t)frame * 3 * D1 + which * D1 + col) : 0.0f;
+}
+
 constexpr int ATT_THREADS = 256;
 constexpr int ATT_WARPS = ATT_THREADS / 32;
 constexpr int MAX_KPL = 10;  // keys per lane  -> T <= 320
@@ -15,22 +25,22 @@ constexpr int MAX_CPL = 5;   // head channels per lane -> d <= 160
 template <typename T>
 __global__ void __launch_bounds__(ATT_THREADS) relpos_attn_fwd_kernel(
     const T* __restrict__ qkv, const T* __restrict__ e, const int* __restrict__ klen, int qlen, T* __restrict__ o,
-    float* __restrict__ probs, int Tn, int H, int d) {
+    float* __restrict__ probs, int Tn, int H, int d, int G, int D1, int Tf, const float* __restrict__ ub, const float* __restrict__ vb) {
     extern __shared__ float sm[];
     const int ds = d + 1;
     float* Ks = sm;                       // [Tn][ds]
     float* Vs = Ks + (size_t)Tn * ds;     // [Tn][ds]
     float* Es = Vs + (size_t)Tn * ds;     // [2Tn-1][ds]
-    float* qs = Es + (size_t)(2 * Tn - 1) * ds;  // [ATT_WARPS][ds]
-    float* ps = qs + ATT_WARPS * ds;      // [ATT_WARPS][Tn]
+    float* qs = Es + (size_t)(2 * Tn - 1) * ds;  // [ATT_WARPS][2][ds]  (q + u | q + v)
+    float* ps = qs + ATT_WARPS * 2 * ds;  // [ATT_WARPS][Tn]
     const int b = blockIdx.x / H, h = blockIdx.x % H;
     const int D = H * d;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const T* base = qkv + (size_t)b * Tn * 3 * D + h * d;
+    const T* qkv_b = qkv + (size_t)b * Tf * 3 * D1;
     for (int idx = tid; idx < Tn * d; idx += ATT_THREADS) {
         int j = idx / d, c = idx % d;
-        Ks[j * ds + c] = ldf(base + (size_t)j * 3 * D + D + c);
-        Vs[j * ds + c] = ldf(base + (size_t)j * 3 * D + 2 * D + c);
+        Ks[j * ds + c] = fetch_qkv(qkv_b, j, h * d + c, 1, G, D1, Tf);
+        Vs[j * ds + c] = fetch_qkv(qkv_b, j, h * d + c, 2, G, D1, Tf);
     }
     for (int idx = tid; idx < (2 * Tn - 1) * d; idx += ATT_THREADS) {
         int r = idx / d, c = idx % d;
@@ -39,10 +49,15 @@ __global__ void __launch_bounds__(ATT_THREADS) relpos_attn_fwd_kernel(
     __syncthreads();
     const int kl = klen ? klen[b] : Tn;
     const float scale = rsqrtf((float)d);
-    float* q = qs + warp * ds;
+    float* q = qs + warp * 2 * ds;   // q + u (content term)
+    float* qv = q + ds;              // q + v (position term)
     float* p = ps + warp * Tn;
     for (int i = warp; i < Tn; i += ATT_WARPS) {
-        for (int c = lane; c < d; c += 32) q[c] = ldf(base + (size_t)i * 3 * D + c);
+        for (int c = lane; c < d; c += 32) {
+            const float qq = fetch_qkv(qkv_b, i, h * d + c, 0, G, D1, Tf);
+            q[c] = qq + (ub ? ub[(h * d + c) % D1] : 0.0f);
+            qv[c] = qq + (vb ? vb[(h * d + c) % D1] : 0.0f);
+        }
         __syncwarp();
         float s[MAX_KPL];
         float mx = -INFINITY;
@@ -54,7 +69,7 @@ __global__ void __launch_bounds__(ATT_THREADS) relpos_attn_fwd_kernel(
                 const float* kr = Ks + j * ds;
                 const float* er = Es + (Tn - 1 + j - i) * ds;
                 float acc = 0.0f;
-                for (int c = 0; c < d; ++c) acc = fmaf(q[c], kr[c] + er[c], acc);
+                for (int c = 0; c < d; ++c) acc = fmaf(q[c], kr[c], fmaf(qv[c], er[c], acc));
                 acc *= scale;
                 if (j >= kl || i >= qlen) acc += -1e9f;
                 s[u] = acc;
@@ -87,7 +102,13 @@ __global__ void __launch_bounds__(ATT_THREADS) relpos_attn_fwd_kernel(
             for (int u = 0; u < MAX_CPL; ++u) { int c = lane + u * 32; if (c < d) acc[u] = fmaf(pj, vr[c], acc[u]); }
         }
 #pragma unroll
-        for (int u = 0; u < MAX_CPL; ++u) { int c = lane + u * 32; if (c < d) stf(o + ((size_t)b * Tn + i) * D + h * d + c, acc[u]); }
+        for (int u = 0; u < MAX_CPL; ++u) {
+            int c = lane + u * 32;
+            if (c < d) {
+                const int ee = h * d + c, fi = ee / D1, frame = i * G + fi;
+                if (frame < Tf) stf(o + ((size_t)b * Tf + frame) * D1 + (ee - fi * D1), acc[u]);
+            }
+        }
         __syncwarp();
     }
 }
@@ -96,7 +117,8 @@ __global__ void __launch_bounds__(ATT_THREADS) relpos_attn_fwd_kernel(
 template <typename T>
 __global__ void __launch_bounds__(ATT_THREADS) relpos_attn_bwd_kernel(
     const T* __restrict__ d_o, const T* __restrict__ qkv, const T* __restrict__ e, const float* __restrict__ probs,
-    float* __restrict__ ds_ws, T* __restrict__ dqkv, float* __restrict__ de, int Tn, int H, int d) {
+    float* __restrict__ ds_ws, T* __restrict__ dqkv, float* __restrict__ de, int Tn, int H, int d, int G, int D1, int Tf,
+    const float* __restrict__ ub, const float* __restrict__ vb, float* __restrict__ dub, float* __restrict__ dvb) {
     extern __shared__ float sm[];
     const int ds = d + 1;
     float* Qs = sm;
@@ -107,15 +129,21 @@ __global__ void __launch_bounds__(ATT_THREADS) relpos_attn_bwd_kernel(
     const int b = blockIdx.x / H, h = blockIdx.x % H;
     const int D = H * d;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const T* base = qkv + (size_t)b * Tn * 3 * D + h * d;
-    T* dbase = dqkv + (size_t)b * Tn * 3 * D + h * d;
+    const T* qkv_b = qkv + (size_t)b * Tf * 3 * D1;
+    T* dqkv_b = dqkv + (size_t)b * Tf * 3 * D1;
     for (int idx = tid; idx < Tn * d; idx += ATT_THREADS) {
         int j = idx / d, c = idx % d;
-        Qs[j * ds + c] = ldf(base + (size_t)j * 3 * D + c);
-        Ks[j * ds + c] = ldf(base + (size_t)j * 3 * D + D + c);
-        Vs[j * ds + c] = ldf(base + (size_t)j * 3 * D + 2 * D + c);
-        Os[j * ds + c] = ldf(d_o + ((size_t)b * Tn + j) * D + h * d + c);
+        const int ee = h * d + c, fi = ee / D1, frame = j * G + fi;
+        Qs[j * ds + c] = fetch_qkv(qkv_b, j, ee, 0, G, D1, Tf);
+        Ks[j * ds + c] = fetch_qkv(qkv_b, j, ee, 1, G, D1, Tf);
+        Vs[j * ds + c] = fetch_qkv(qkv_b, j, ee, 2, G, D1, Tf);
+        Os[j * ds + c] = frame < Tf ? ldf(d_o + ((size_t)b * Tf + frame) * D1 + (ee - fi * D1)) : 0.0f;
     }
+    // gradient element (token, channel c of this head) -> [frames, 3 * D1] matrix; padded frames are dropped
+    auto store_grad = [&](int tok, int c, int which, float val) {
+        const int ee = h * d + c, fi = ee / D1, frame = tok * G + fi;
+        if (frame < Tf) stf(dqkv_b + (size_t)frame * 3 * D1 + which * D1 + (ee - fi * D1), val);
+    };
     __syncthreads();
     const float scale = rsqrtf((float)d);
     const float* P = probs + ((size_t)b * H + h) * Tn * Tn;
@@ -139,7 +167,17 @@ __global__ void __launch_bounds__(ATT_THREADS) relpos_attn_bwd_kernel(
             }
         }
 #pragma unroll
-        for (int u = 0; u < MAX_CPL; ++u) { int c = lane + u * 32; if (c < d) stf(dbase + (size_t)j * 3 * D + 2 * D + c, acc[u]); }
+        for (int u = 0; u < MAX_CPL; ++u) { int c = lane + u * 32; if (c < d) store_grad(j, c, 2, acc[u]); }
+    }
+
+    // per-lane u / v bias values of this head's channels, and their gradient accumulators (summed over this warp's rows)
+    float ubv[MAX_CPL], vbv[MAX_CPL], du_acc[MAX_CPL], dv_acc[MAX_CPL];
+#pragma unroll
+    for (int u = 0; u < MAX_CPL; ++u) {
+        int c = lane + u * 32;
+        ubv[u] = (ub && c < d) ? ub[(h * d + c) % D1] : 0.0f;
+        vbv[u] = (vb && c < d) ? vb[(h * d + c) % D1] : 0.0f;
+        du_acc[u] = 0.0f; dv_acc[u] = 0.0f;
     }
 
     // ---- phase A: per query row i: dP_ij = dO_i.V_j, delta, dS_ij, dQ_i
@@ -167,23 +205,42 @@ __global__ void __launch_bounds__(ATT_THREADS) relpos_attn_bwd_kernel(
             if (j < Tn) { float v = pr[u] * (dp[u] - delta) * scale; p[j] = v; dS[(size_t)i * Tn + j] = v; }
         }
         __syncwarp();
-        float acc[MAX_CPL];
+        float acc[MAX_CPL], acce[MAX_CPL];
 #pragma unroll
-        for (int u = 0; u < MAX_CPL; ++u) acc[u] = 0.0f;
+        for (int u = 0; u < MAX_CPL; ++u) { acc[u] = 0.0f; acce[u] = 0.0f; }
         for (int j = 0; j < Tn; ++j) {
             float sv = p[j];
             const float* kr = Ks + j * ds;
             const T* er = e + (size_t)(Tn - 1 + j - i) * D + h * d;
 #pragma unroll
-            for (int u = 0; u < MAX_CPL; ++u) { int c = lane + u * 32; if (c < d) acc[u] = fmaf(sv, kr[c] + ldf(er + c), acc[u]); }
+            for (int u = 0; u < MAX_CPL; ++u) {
+                int c = lane + u * 32;
+                if (c < d) { acc[u] = fmaf(sv, kr[c], acc[u]); acce[u] = fmaf(sv, ldf(er + c), acce[u]); }
+            }
         }
 #pragma unroll
-        for (int u = 0; u < MAX_CPL; ++u) { int c = lane + u * 32; if (c < d) stf(dbase + (size_t)i * 3 * D + c, acc[u]); }
+        for (int u = 0; u < MAX_CPL; ++u) {
+            int c = lane + u * 32;
+            if (c < d) {
+                store_grad(i, c, 0, acc[u] + acce[u]);
+                // u / v biases are added to every (also zero-padded) query row: their gradients take the two parts separately
+                du_acc[u] += acc[u];
+                dv_acc[u] += acce[u];
+            }
+        }
         __syncwarp();
+    }
+#pragma unroll
+    for (int u = 0; u < MAX_CPL; ++u) {
+        int c = lane + u * 32;
+        if (c < d) {
+            if (dub) atomicAdd(dub + (h * d + c) % D1, du_acc[u]);
+            if (dvb) atomicAdd(dvb + (h * d + c) % D1, dv_acc[u]);
+        }
     }
     __syncthreads();
 
-    // ---- phase C1: dK_j = sum_i dS[i][j] * Q_i
+    // ---- phase C1: dK_j = sum_i dS[i][j] * (Q_i + u)
     for (int j = warp; j < Tn; j += ATT_WARPS) {
         float acc[MAX_CPL];
 #pragma unroll
@@ -196,11 +253,11 @@ __global__ void __launch_bounds__(ATT_THREADS) relpos_attn_bwd_kernel(
                 float sv = __shfl_sync(0xffffffffu, sij, ii);
                 const float* qrow = Qs + (i0 + ii) * ds;
 #pragma unroll
-                for (int u = 0; u < MAX_CPL; ++u) { int c = lane + u * 32; if (c < d) acc[u] = fmaf(sv, qrow[c], acc[u]); }
+                for (int u = 0; u < MAX_CPL; ++u) { int c = lane + u * 32; if (c < d) acc[u] = fmaf(sv, qrow[c] + ubv[u], acc[u]); }
             }
         }
 #pragma unroll
-        for (int u = 0; u < MAX_CPL; ++u) { int c = lane + u * 32; if (c < d) stf(dbase + (size_t)j * 3 * D + D + c, acc[u]); }
+        for (int u = 0; u < MAX_CPL; ++u) { int c = lane + u * 32; if (c < d) store_grad(j, c, 1, acc[u]); }
     }
     // ---- phase C2: dE_r = sum_{i, j = r-(Tn-1)+i in [0,Tn)} dS[i][j] * Q_i   (summed over the batch: atomics)
     for (int r = warp; r < 2 * Tn - 1; r += ATT_WARPS) {
@@ -216,7 +273,7 @@ __global__ void __launch_bounds__(ATT_THREADS) relpos_attn_bwd_kernel(
                 float sv = __shfl_sync(0xffffffffu, sij, ii);
                 const float* qrow = Qs + (i0 + ii) * ds;
 #pragma unroll
-                for (int u = 0; u < MAX_CPL; ++u) { int c = lane + u * 32; if (c < d) acc[u] = fmaf(sv, qrow[c], acc[u]); }
+                for (int u = 0; u < MAX_CPL; ++u) { int c = lane + u * 32; if (c < d) acc[u] = fmaf(sv, qrow[c] + vbv[u], acc[u]); }
             }
         }
 #pragma unroll
@@ -224,36 +281,40 @@ __global__ void __launch_bounds__(ATT_THREADS) relpos_attn_bwd_kernel(
     }
 }
 
-size_t fwd_smem(int T, int d) { return ((size_t)(4 * T - 1) * (d + 1) + ATT_WARPS * (d + 1) + ATT_WARPS * T) * sizeof(float); }
+size_t fwd_smem(int T, int d) { return ((size_t)(4 * T - 1) * (d + 1) + ATT_WARPS * 2 * (d + 1) + ATT_WARPS * T) * sizeof(float); }
 size_t bwd_smem(int T, int d) { return ((size_t)4 * T * (d + 1) + ATT_WARPS * T) * sizeof(float); }
 
 }  // namespace
 
 extern "C" int avec_relpos_attn_fwd(const void* qkv, const void* e, const int* klen, int qlen, void* o, float* probs, int B,
-                                    int T, int H, int d, int dtype, avec_stream_t stream) {
-    AVEC_CHECK_ARG(qkv && e && o && probs && B > 0 && T > 0 && H > 0 && d > 0);
-    AVEC_CHECK_ARG(T <= 32 * MAX_KPL && d <= 32 * MAX_CPL);
+                                    int T, int H, int d, int G, int Tf, const float* u, const float* v, int dtype, avec_stream_t stream) {
+    AVEC_CHECK_ARG(qkv && e && o && probs && B > 0 && T > 0 && H > 0 && d > 0 && G >= 1 && (H * d) % G == 0);
+    AVEC_CHECK_ARG(T <= 32 * MAX_KPL && d <= 32 * MAX_CPL && Tf > (T - 1) * G && Tf <= T * G);
+    const int D1 = H * d / G;
     size_t smem = fwd_smem(T, d);
     if (smem > 227 * 1024) return AVEC_ERR_UNSUPPORTED;
     AVEC_DISPATCH_DTYPE(dtype, Tt, {
         auto kfn = relpos_attn_fwd_kernel<Tt>;
         if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return AVEC_ERR_LAUNCH;
-        kfn<<<B * H, ATT_THREADS, smem, as_stream(stream)>>>((const Tt*)qkv, (const Tt*)e, klen, qlen, (Tt*)o, probs, T, H, d);
+        kfn<<<B * H, ATT_THREADS, smem, as_stream(stream)>>>((const Tt*)qkv, (const Tt*)e, klen, qlen, (Tt*)o, probs, T, H, d, G, D1, Tf, u, v);
     });
     AVEC_LAUNCH_CHECK();
     return AVEC_OK;
 }
 
 extern "C" int avec_relpos_attn_bwd(const void* d_o, const void* qkv, const void* e, const float* probs, float* ds_ws,
-                                    void* dqkv, float* de, int B, int T, int H, int d, int dtype, avec_stream_t stream) {
-    AVEC_CHECK_ARG(d_o && qkv && e && probs && ds_ws && dqkv && de && B > 0 && T > 0);
-    AVEC_CHECK_ARG(T <= 32 * MAX_KPL && d <= 32 * MAX_CPL);
+                                    void* dqkv, float* de, int B, int T, int H, int d, int G, int Tf, const float* u, const float* v,
+                                    float* du, float* dv, int dtype, avec_stream_t stream) {
+    AVEC_CHECK_ARG(d_o && qkv && e && probs && ds_ws && dqkv && de && B > 0 && T > 0 && G >= 1 && (H * d) % G == 0);
+    AVEC_CHECK_ARG(T <= 32 * MAX_KPL && d <= 32 * MAX_CPL && Tf > (T - 1) * G && Tf <= T * G);
+    const int D1 = H * d / G;
     size_t smem = bwd_smem(T, d);
     if (smem > 227 * 1024) return AVEC_ERR_UNSUPPORTED;
     AVEC_DISPATCH_DTYPE(dtype, Tt, {
         auto kfn = relpos_attn_bwd_kernel<Tt>;
         if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return AVEC_ERR_LAUNCH;
-        kfn<<<B * H, ATT_THREADS, smem, as_stream(stream)>>>((const Tt*)d_o, (const Tt*)qkv, (const Tt*)e, probs, ds_ws, (Tt*)dqkv, de, T, H, d);
+        kfn<<<B * H, ATT_THREADS, smem, as_stream(stream)>>>((const Tt*)d_o, (const Tt*)qkv, (const Tt*)e, probs, ds_ws, (Tt*)dqkv, de, T, H, d,
+                                                             G, D1, Tf, u, v, du, dv);
     });
     AVEC_LAUNCH_CHECK();
     return AVEC_OK;

@@ -576,7 +576,19 @@ __device__ __forceinline__ void epilogue_warp(const TcParams& p, const EpiParams
         const int lc = q * 8;                 // column inside the slab
         const int gc = ti.n0 + c0 + lc;       // global column
         if (lc < ncol) {
-#pragma unroll 2
+            const bool vec = gc + 8 <= p.N;
+            const bool need_aux = vec && ep.aux != nullptr &&
+                                  (ep.kind == AVEC_EPI_RESIDUAL || ep.kind == AVEC_EPI_DSWISH || ep.kind == AVEC_EPI_RELU);
+            // all eight residual / Swish' row segments of this lane are requested up front: one exposed latency, not eight
+            float x[8][8];
+            if (need_aux) {
+#pragma unroll
+                for (int pass = 0; pass < 8; ++pass) {
+                    const int r = warp * 32 + pass * 4 + rs;
+                    if (r < ti.rows_valid) load8(ep.aux, ep.aux_dtype, (size_t)(ti.row_base + r) * ep.ldaux + gc, x[pass]);
+                }
+            }
+#pragma unroll
             for (int pass = 0; pass < 8; ++pass) {
                 const int rr = pass * 4 + rs;
                 const int r = warp * 32 + rr;
@@ -588,7 +600,7 @@ __device__ __forceinline__ void epilogue_warp(const TcParams& p, const EpiParams
                     const float4 t1 = *reinterpret_cast<const float4*>(stg + rr * STG_LD + lc + 4);
                     a[0] = t0.x; a[1] = t0.y; a[2] = t0.z; a[3] = t0.w; a[4] = t1.x; a[5] = t1.y; a[6] = t1.z; a[7] = t1.w;
                 }
-                if (gc + 8 <= p.N) {
+                if (vec) {
                     const size_t oi = (size_t)row * ep.ldo + gc;
                     float o[8];
                     if (ep.kind == AVEC_EPI_ACCUM) {
@@ -610,21 +622,15 @@ __device__ __forceinline__ void epilogue_warp(const TcParams& p, const EpiParams
                             if (ep.out2) store8(ep.out2, ep.out2_dtype, (size_t)row * ep.ldo2 + gc, a);
 #pragma unroll
                             for (int j = 0; j < 8; ++j) o[j] = swishf_(a[j]);
-                        } else {
-                            float x[8];
+                        } else if (ep.kind == AVEC_EPI_RESIDUAL) {
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) x[j] = 0.0f;
-                            if (ep.aux) load8(ep.aux, ep.aux_dtype, (size_t)row * ep.ldaux + gc, x);
-                            if (ep.kind == AVEC_EPI_RESIDUAL) {
+                            for (int j = 0; j < 8; ++j) o[j] = x[pass][j] + ep.alpha * a[j];
+                        } else if (ep.kind == AVEC_EPI_DSWISH) {
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) o[j] = x[j] + ep.alpha * a[j];
-                            } else if (ep.kind == AVEC_EPI_DSWISH) {
+                            for (int j = 0; j < 8; ++j) o[j] = ep.alpha * a[j] * dswishf_(x[pass][j]);
+                        } else {  // RELU
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) o[j] = ep.alpha * a[j] * dswishf_(x[j]);
-                            } else {  // RELU
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) o[j] = fmaxf(ep.alpha * a[j] + x[j], 0.0f);
-                            }
+                            for (int j = 0; j < 8; ++j) o[j] = fmaxf(ep.alpha * a[j] + (need_aux ? x[pass][j] : 0.0f), 0.0f);
                         }
                         store8(ep.out, ep.out_dtype, oi, o);
                     }

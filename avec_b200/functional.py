@@ -148,7 +148,7 @@ class AttentionFn(Function):
         do = ops.linear_dgrad(dproj, wc(wo))
         dwo = ops.linear_wgrad(dproj, o)
         dbo = ops.colsum(dproj)
-        dqkv, de = ops.relpos_attn_bwd(do, qkv, e, probs, B, Tp, H, d)
+        dqkv, de, _, _ = ops.relpos_attn_bwd(do, qkv, e, probs, B, Tp, H, d)
         dwp = ops.linear_wgrad(ops.convert(de, x.dtype), pe)
         dbp = ops.colsum(de)
         wqkv = wc_cat((wq, wk, wv), "qkv")
@@ -158,6 +158,54 @@ class AttentionFn(Function):
         dx, dg, db = ops.layernorm_bwd(dxp.view(B, Tp, D), x, ln_w, mean, rstd, P=P, dres=dy, res_stride=1)
         return (dx, dg, db, dwqkv[:D], dbqkv[:D], dwqkv[D:2 * D], dbqkv[D:2 * D], dwqkv[2 * D:], dbqkv[2 * D:], dwo, dbo,
                 dwp, dbp, None, None, None, None)
+
+
+class GroupedAttentionFn(Function):
+    """y = x + Wo attn_G(LN(x)) + bo: Transformer-XL style relative attention with content / position biases u, v over
+    tokens made of G consecutive frames (GroupedRelPosMultiHeadSelfAttention, reference nnet/attentions.py:579-650;
+    G = 1 is RelPosMultiHeadSelfAttention).  Projections run at full frame rate, grouping is pure addressing."""
+
+    @staticmethod
+    def forward(ctx, x, ln_w, ln_b, wq, bq, wk, bk, wv, bv, wo, bo, wp, bp, u, v, pe, klen, H, G):
+        B, T, D = x.shape
+        Tn = -(-T // G)
+        d = G * D // H
+        x = _c(x)
+        xn, mean, rstd = ops.layernorm_fwd(x, ln_w, ln_b)
+        wqkv = wc_cat((wq, wk, wv), "qkv")
+        bqkv = wc_cat((bq, bk, bv), "bqkv").reshape(-1)
+        qkv = ops.linear_fwd(xn.view(B * T, D), wqkv, bqkv)
+        e = ops.linear_fwd(pe, wc(wp), bp)                      # [2*Tp-G, D] == [2*Tn-1, G*D]
+        klen_g = torch.div(klen + (G - 1), G, rounding_mode="floor").to(torch.int32) if klen is not None else None
+        o, probs = ops.relpos_attn_fwd(qkv, e, klen_g, Tn, B, Tn, H, d, G=G, Tf=T, u=u, v=v)
+        y = ops.linear_fwd(o, wc(wo), bo, L.EPI_RESIDUAL, aux=x.view(B * T, D)).view(B, T, D)
+        ctx.save_for_backward(x, ln_w, mean, rstd, xn, qkv, e, probs, o, pe, wq, wk, wv, wo, wp, u, v)
+        ctx.H, ctx.G = H, G
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, ln_w, mean, rstd, xn, qkv, e, probs, o, pe, wq, wk, wv, wo, wp, u, v = ctx.saved_tensors
+        H, G = ctx.H, ctx.G
+        B, T, D = x.shape
+        Tn = -(-T // G)
+        d = G * D // H
+        dy = _c(dy)
+        dy2 = dy.view(B * T, D)
+        do = ops.linear_dgrad(dy2, wc(wo))
+        dwo = ops.linear_wgrad(dy2, o)
+        dbo = ops.colsum(dy2)
+        dqkv, de, du, dv = ops.relpos_attn_bwd(do, qkv, e, probs, B, Tn, H, d, G=G, Tf=T, u=u, v=v)
+        de2 = de.view(-1, D)
+        dwp = ops.linear_wgrad(ops.convert(de2, x.dtype), pe)
+        dbp = ops.colsum(de2)
+        wqkv = wc_cat((wq, wk, wv), "qkv")
+        dxn = ops.linear_dgrad(dqkv, wqkv)
+        dwqkv = ops.linear_wgrad(dqkv, xn.view(B * T, D))
+        dbqkv = ops.colsum(dqkv)
+        dx, dg, db = ops.layernorm_bwd(dxn.view(B, T, D), x, ln_w, mean, rstd, dres=dy, res_stride=1)
+        return (dx, dg, db, dwqkv[:D], dbqkv[:D], dwqkv[D:2 * D], dbqkv[D:2 * D], dwqkv[2 * D:], dbqkv[2 * D:], dwo, dbo,
+                dwp, dbp, du, dv, None, None, None, None)
 
 
 # ------------------------------------------------------------------------------------------------------- conv module

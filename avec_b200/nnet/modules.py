@@ -26,6 +26,24 @@ def rel_pos_table(T, D, device, dtype):
     return t
 
 
+def grouped_rel_pos_table(Tp, D, G, device, dtype):
+    """GroupedRelativeSinusoidalPositionalEncoding slice for a (padded) length Tp = multiple of G, odd G
+    (embeddings.py:160-216): 2*Tp - G rows, relative positions Tp-1-G//2 ... -(Tp-1-G//2)."""
+    assert G % 2 == 1, "even group sizes use a different table layout in the reference and are not used by AVEC"
+    key = ("g", Tp, D, G, str(device), dtype)
+    t = _pe_cache.get(key)
+    if t is None:
+        half = Tp - 1 - G // 2
+        pos = torch.arange(half, -half - 1, -1, dtype=torch.float).unsqueeze(1)
+        angles = pos / 10000 ** (2 * torch.arange(0, D // 2, dtype=torch.float).unsqueeze(0) / D)
+        pe = torch.zeros(2 * Tp - G, D)
+        pe[:, 0::2] = angles.sin()
+        pe[:, 1::2] = angles.cos()
+        t = pe.to(device=device, dtype=dtype).contiguous()
+        _pe_cache[key] = t
+    return t
+
+
 class FeedForwardModule(nn.Module):
     def __init__(self, dim_model, dim_ffn, drop_rate, act_fun="Swish", inner_dropout=True):
         super().__init__()
@@ -72,9 +90,29 @@ class RelPosPatch1dMultiHeadAttention(RelPos1dMultiHeadAttention):
         self.patch_size = patch_size
 
 
+class GroupedRelPosMultiHeadSelfAttention(nn.Module):
+    """Parameter holder of the grouped / Transformer-XL relative attention (attentions.py:384-413, 556-577):
+    u, v content / position biases registered before the projections, as in the reference's state_dict order."""
+
+    def __init__(self, dim_model, num_heads, attn_drop_rate, max_pos_encoding, group_size, causal=False,
+                 weight_init="scaled_uniform", bias_init="zeros", output_proj=True):
+        super().__init__()
+        assert not causal and output_proj and attn_drop_rate == 0.0 and (group_size * dim_model) % num_heads == 0
+        self.num_heads, self.dim_model, self.group_size = num_heads, dim_model, group_size
+        self.dim_head = (group_size * dim_model) // num_heads
+        self.u = nn.Parameter(torch.zeros(dim_model))
+        self.v = nn.Parameter(torch.zeros(dim_model))
+        self.query_layer = Linear(dim_model, dim_model, bias_init=bias_init)
+        self.key_layer = Linear(dim_model, dim_model, bias_init=bias_init)
+        self.value_layer = Linear(dim_model, dim_model, bias_init=bias_init)
+        self.output_layer = Linear(dim_model, dim_model, bias_init=bias_init)
+        self.pos_layer = Linear(dim_model, dim_model)
+
+
 att_dict = {
     "RelPos1dMultiHeadAttention": RelPos1dMultiHeadAttention,
     "RelPosPatch1dMultiHeadAttention": RelPosPatch1dMultiHeadAttention,
+    "GroupedRelPosMultiHeadSelfAttention": GroupedRelPosMultiHeadSelfAttention,
 }
 
 
@@ -92,6 +130,15 @@ class AttentionModule(nn.Module):
         """x + MHSA(LN(x)) with key-padding lengths klen (int32 [B] on device, or None)."""
         a = self.attention
         B, T, D = x.shape
+        if isinstance(a, GroupedRelPosMultiHeadSelfAttention):
+            G = a.group_size
+            Tp = -(-T // G) * G
+            pe = grouped_rel_pos_table(Tp, D, G, x.device, x.dtype)
+            return AF.GroupedAttentionFn.apply(
+                x, self.norm.weight, self.norm.bias,
+                a.query_layer.weight, a.query_layer.bias, a.key_layer.weight, a.key_layer.bias,
+                a.value_layer.weight, a.value_layer.bias, a.output_layer.weight, a.output_layer.bias,
+                a.pos_layer.weight, a.pos_layer.bias, a.u, a.v, pe, klen, a.num_heads, G)
         P = a.patch_size
         Tp = -(-T // P)
         pe = rel_pos_table(Tp, D, x.device, x.dtype)

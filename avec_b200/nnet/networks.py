@@ -94,8 +94,6 @@ class AudioEfficientConformerEncoder(nn.Module):
                  loss_prefix="ctc"):
         super().__init__()
         assert att_type in ["regular", "grouped", "patch"]
-        if att_type == "grouped":
-            raise NotImplementedError("avec_b200: grouped attention (config-5 ablation) is not implemented yet")
         filters, n_mels, dim_model, heads = 180, 80, [180, 256, 360], 4
         self.audio_preprocessing = _AudioPreprocessingParams()
         self.spec_augment = Placeholder("SpecAugment(mF=2, F=27, mT=5, pS=0.05): training-only augmentation, bypassed")
@@ -105,10 +103,17 @@ class AudioEfficientConformerEncoder(nn.Module):
         self.transpose = Placeholder("Transpose")
         self.linear = Linear(filters * n_mels // 2, dim_model[0])
         reg = _att("RelPos1dMultiHeadAttention", heads)
-        first = reg if att_type == "regular" else _att("RelPosPatch1dMultiHeadAttention", heads, patch_size=3)
+        if att_type == "grouped":   # Efficient-Conformer grouped attention (group 3 in stage 1), networks.py:389-393
+            def grp(g):
+                return {"class": "GroupedRelPosMultiHeadSelfAttention",
+                        "params": {"num_heads": heads, "group_size": g, "attn_drop_rate": 0.0, "max_pos_encoding": 10000, "causal": False}}
+            att_list = [grp(3), grp(1), grp(1)]
+        else:
+            first = reg if att_type == "regular" else _att("RelPosPatch1dMultiHeadAttention", heads, patch_size=3)
+            att_list = [first, reg, reg]
         self.back_end = ConformerInterCTC(
             dim_model=dim_model, num_blocks=num_blocks, interctc_blocks=interctc_blocks, vocab_size=vocab_size,
-            att_params=[first, reg, reg], conv_params={"class": "Conv1d", "params": {"padding": "same", "kernel_size": 15}},
+            att_params=att_list, conv_params={"class": "Conv1d", "params": {"padding": "same", "kernel_size": 15}},
             ff_ratio=4, drop_rate=0.1, conv_stride=2, batch_norm=True, loss_prefix=loss_prefix)
         self.head = Linear(dim_model[-1], vocab_size) if include_head else nn.Identity()
         self._filters, self._nf = filters, n_mels // 2

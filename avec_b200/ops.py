@@ -336,24 +336,29 @@ def bn_bwd(dy2d, u2d, bnbuf, gamma, act, res=None, want_dres=False):
 
 
 # ----------------------------------------------------------------------------------------------------------- attention
-def relpos_attn_fwd(qkv, e, klen, qlen, B, T, H, d):
-    D = H * d
-    o = torch.empty((B * T, D), device=qkv.device, dtype=qkv.dtype)
+def relpos_attn_fwd(qkv, e, klen, qlen, B, T, H, d, G=1, Tf=None, u=None, v=None):
+    """qkv [B*Tf, 3*D1] (frames), e [2T-1, G*D1] -> o [B*Tf, D1], probs [B,H,T,T]; T = ceil(Tf/G) tokens of G frames"""
+    Tf = T if Tf is None else Tf
+    D1 = H * d // G
+    o = torch.empty((B * Tf, D1), device=qkv.device, dtype=qkv.dtype)
     probs = torch.empty((B, H, T, T), device=qkv.device, dtype=torch.float32)
     L.check(L.load().avec_relpos_attn_fwd(qkv.data_ptr(), e.data_ptr(), _p(klen), qlen, o.data_ptr(), probs.data_ptr(), B, T,
-                                          H, d, _dt(qkv), _stream()), "avec_relpos_attn_fwd")
+                                          H, d, G, Tf, _p(u), _p(v), _dt(qkv), _stream()), "avec_relpos_attn_fwd")
     return o, probs
 
 
-def relpos_attn_bwd(do, qkv, e, probs, B, T, H, d):
-    D = H * d
+def relpos_attn_bwd(do, qkv, e, probs, B, T, H, d, G=1, Tf=None, u=None, v=None):
+    Tf = T if Tf is None else Tf
+    D1 = H * d // G
     dqkv = torch.empty_like(qkv)
-    de = zeros_f32((2 * T - 1, D), qkv.device)
+    de = zeros_f32((2 * T - 1, G * D1), qkv.device)
+    du = zeros_f32((D1,), qkv.device) if u is not None else None
+    dv = zeros_f32((D1,), qkv.device) if v is not None else None
     ws = torch.empty_like(probs)
     L.check(L.load().avec_relpos_attn_bwd(do.data_ptr(), qkv.data_ptr(), e.data_ptr(), probs.data_ptr(), ws.data_ptr(),
-                                          dqkv.data_ptr(), de.data_ptr(), B, T, H, d, _dt(qkv), _stream()),
-            "avec_relpos_attn_bwd")
-    return dqkv, de
+                                          dqkv.data_ptr(), de.data_ptr(), B, T, H, d, G, Tf, _p(u), _p(v), _p(du), _p(dv),
+                                          _dt(qkv), _stream()), "avec_relpos_attn_bwd")
+    return dqkv, de, du, dv
 
 
 # --------------------------------------------------------------------------------------------------------- conv module

@@ -133,18 +133,22 @@ int avec_upsample_add(const void* x, const void* o, void* y, int B, int T, int T
 int avec_pool_sum(const void* dy, void* dout, int B, int T, int Tp, int C, int P, int dtype, avec_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
- * Relative-position multi-head self-attention core (nnet/attentions.py:280-323 incl. rel_to_abs 258-276):
- *   S[i,j] = (q_i . k_j + q_i . e_{T-1+j-i}) / sqrt(d);  S += -1e9 where masked;  P = softmax_j(S);  o_i = sum_j P k v_j
- * qkv is [B*T, 3*D] (q | k | v, each D = H*d wide), e is [2T-1, D] (pos_layer(R), computed once, not B times),
- * klen[b] = number of unmasked keys of item b, qlen = number of query rows that are not fully masked (rows >= qlen see
- * every key masked, as happens for the zero-padded last patch, nnet/attentions.py:140-171,355-363).
- * probs [B,H,T,T] fp32 is saved for the backward.  bwd: dqkv [B*T,3D]; de [2T-1, D] fp32, accumulated atomically;
- * ds_ws is a caller-provided [B,H,T,T] fp32 scratch (dS).
+ * Relative-position multi-head self-attention core (nnet/attentions.py:280-323 incl. rel_to_abs 258-276; grouped /
+ * Transformer-XL variant 579-650):
+ *   S[i,j] = ((q_i+u) . k_j + (q_i+v) . e_{T-1+j-i}) / sqrt(d);  S += -1e9 where masked;  P = softmax_j(S);  o_i = sum_j P v_j
+ * qkv is [B*Tf, 3*D1] per FRAME (q | k | v, D1 = H*d/G wide each); a token is G consecutive frames concatenated
+ * (G = 1: token = frame), T = ceil(Tf / G) tokens, frames >= Tf are zero rows.  e is [2T-1, G*D1] (pos_layer(R) regrouped,
+ * computed once, not B times); u, v: optional fp32 [D1] content / position biases (grouped attention), tiled over the group.
+ * klen[b] = number of unmasked key tokens of item b, qlen = number of query rows that are not fully masked (rows >= qlen
+ * see every key masked, as happens for the zero-padded last patch, nnet/attentions.py:140-171,355-363).
+ * o is [B*Tf, D1]; probs [B,H,T,T] fp32 is saved for the backward.
+ * bwd: dqkv [B*Tf, 3*D1]; de [2T-1, G*D1], du, dv [D1] fp32, accumulated atomically; ds_ws: [B,H,T,T] fp32 scratch (dS).
  * ------------------------------------------------------------------------------------------------------------------ */
 int avec_relpos_attn_fwd(const void* qkv, const void* e, const int* klen, int qlen, void* o, float* probs, int B, int T,
-                         int H, int d, int dtype, avec_stream_t stream);
+                         int H, int d, int G, int Tf, const float* u, const float* v, int dtype, avec_stream_t stream);
 int avec_relpos_attn_bwd(const void* d_o, const void* qkv, const void* e, const float* probs, float* ds_ws, void* dqkv,
-                         float* de, int B, int T, int H, int d, int dtype, avec_stream_t stream);
+                         float* de, int B, int T, int H, int d, int G, int Tf, const float* u, const float* v, float* du,
+                         float* dv, int dtype, avec_stream_t stream);
 
 /* row softmax / its backward (InterCTCResModule, nnet/modules.py:397-398).  dadd (optional, fp32) is added to dx. */
 int avec_softmax_fwd(const void* x, int x_dtype, void* y, int y_dtype, long long rows, int C, avec_stream_t stream);

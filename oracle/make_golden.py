@@ -43,7 +43,10 @@ def mask_from_lengths(T, lengths):
 
 # ---------------------------------------------------------------------------------------------------- ConformerBlock
 def block_case(tag, D, De, stride, att, T, B, seed):
-    if att == "patch":
+    if att.startswith("grouped"):
+        att_params = {"class": "GroupedRelPosMultiHeadSelfAttention", "params": {"num_heads": 4, "group_size": int(att[7:]), "attn_drop_rate": 0.0,
+                      "max_pos_encoding": 10000, "causal": False}}
+    elif att == "patch":
         att_params = {"class": "RelPosPatch1dMultiHeadAttention", "params": {"num_heads": 4, "patch_size": 3, "attn_drop_rate": 0.0,
                       "num_pos_embeddings": 10000, "weight_init": "default", "bias_init": "default"}}
     else:
@@ -191,6 +194,8 @@ if __name__ == "__main__":
     block_case("s2_regular_T17", 256, 256, 1, "regular", 17, 2, 13)
     block_case("s3_regular_T9", 360, 360, 1, "regular", 9, 2, 14)
     block_case("s2_down_T12", 256, 360, 2, "regular", 12, 2, 15)
+    block_case("s1_grouped3_T20", 180, 180, 1, "grouped3", 20, 3, 16)   # config-5 ablation: T % 3 == 2, d = 135
+    block_case("s2_grouped1_T13", 256, 256, 1, "grouped1", 13, 2, 17)
     audio_frontend_case()
     resnet_block_case("64_64_s1", 64, 64, 1, 8, 2, 21)
     resnet_block_case("64_128_s2", 64, 128, 2, 11, 2, 22)

@@ -95,6 +95,40 @@ def relpos_attention(x, sd, p, klen, H, P):
     return o
 
 
+def grouped_attention(x, sd, p, klen, H, G):
+    """AttentionModule + GroupedRelPosMultiHeadSelfAttention.forwardQKV (attentions.py:579-650): projections at full
+    length, zero-pad to a multiple of G AFTER the projections, G consecutive frames concatenated per token, Transformer-XL
+    content / position biases u, v, grouped sinusoid table of 2*Tp-G rows (embeddings.py:160-216), mask[::G, ::G]."""
+    B, T, D = x.shape
+    h = F.layer_norm(x, (D,), sd[p + "norm.weight"], sd[p + "norm.bias"], 1e-6)
+    a = p + "attention."
+    q = F.linear(h, sd[a + "query_layer.weight"], sd[a + "query_layer.bias"])
+    k = F.linear(h, sd[a + "key_layer.weight"], sd[a + "key_layer.bias"])
+    v = F.linear(h, sd[a + "value_layer.weight"], sd[a + "value_layer.bias"])
+    pad = (G - T % G) % G
+    if pad:
+        q, k, v = [F.pad(t, (0, 0, 0, pad)) for t in (q, k, v)]
+    Tp = T + pad
+    Tn, d = Tp // G, G * D // H
+    qu, qv = q + sd[a + "u"], q + sd[a + "v"]
+    half = Tp - 1 - G // 2
+    pos = torch.arange(half, -half - 1, -1, dtype=torch.float).unsqueeze(1)
+    ang = pos / 10000 ** (2 * torch.arange(0, D // 2, dtype=torch.float).unsqueeze(0) / D)
+    pe = torch.zeros(2 * Tp - G, D)
+    pe[:, 0::2], pe[:, 1::2] = ang.sin(), ang.cos()
+    e = F.linear(pe.to(x), sd[a + "pos_layer.weight"], sd[a + "pos_layer.bias"])
+    qu, qv, k, v = [t.reshape(B, Tn, H, d).transpose(1, 2) for t in (qu, qv, k, v)]
+    e = e.reshape(2 * Tn - 1, H, d).transpose(0, 1)
+    idx = (Tn - 1) + torch.arange(Tn).unsqueeze(0) - torch.arange(Tn).unsqueeze(1)
+    s = (qu @ k.transpose(2, 3) + (qv @ e.transpose(1, 2).unsqueeze(0)).gather(3, idx.to(x.device).expand(B, H, Tn, Tn))) / d ** 0.5
+    if klen is not None:
+        kl = torch.div(klen + G - 1, G, rounding_mode="floor")
+        keep = (torch.arange(Tn, device=x.device)[None, None, None, :] < kl[:, None, None, None]).float()
+        s = s + (1.0 - keep) * -1e9
+    o = (s.softmax(dim=-1) @ v).transpose(1, 2).reshape(B, Tp, D)[:, :T]
+    return F.linear(o, sd[a + "output_layer.weight"], sd[a + "output_layer.bias"])
+
+
 def conv_module(x, sd, p, stride, training, bn_momentum=0.1):
     """ConvolutionModule (modules.py:372-381): LN -> PW conv -> GLU -> depthwise k15 (same pad 7/7) -> BN1d -> Swish -> PW."""
     D = x.shape[-1]
@@ -111,11 +145,14 @@ def conv_module(x, sd, p, stride, training, bn_momentum=0.1):
     return h.transpose(1, 2), rm, rv
 
 
-def conformer_block(x, sd, klen, H, P, stride, training=True, prefix=""):
-    """ConformerBlock.forward (blocks.py:289-306)."""
+def conformer_block(x, sd, klen, H, P, stride, training=True, prefix="", G=None):
+    """ConformerBlock.forward (blocks.py:289-306).  G: group size when the block uses grouped attention."""
     p = prefix
     x = x + 0.5 * ffn(x, sd, p + "ff_module1.")
-    x = x + relpos_attention(x, sd, p + "self_att_module.", klen, H, P)
+    if G is not None:
+        x = x + grouped_attention(x, sd, p + "self_att_module.", klen, H, G)
+    else:
+        x = x + relpos_attention(x, sd, p + "self_att_module.", klen, H, P)
     c, rm, rv = conv_module(x, sd, p + "conv_module.", stride, training)
     if p + "conv_res.weight" in sd:
         r = F.conv1d(x.transpose(1, 2), sd[p + "conv_res.weight"], sd[p + "conv_res.bias"], stride=stride).transpose(1, 2)

@@ -6,6 +6,9 @@ import seeded
 
 def att_params(att):
     base = {"num_heads": 4, "attn_drop_rate": 0.0, "num_pos_embeddings": 10000, "weight_init": "default", "bias_init": "default"}
+    if att.startswith("grouped"):
+        return {"class": "GroupedRelPosMultiHeadSelfAttention", "params": {"num_heads": 4, "group_size": int(att[7:]), "attn_drop_rate": 0.0,
+                                                                            "max_pos_encoding": 10000, "causal": False}}
     if att == "patch":
         return {"class": "RelPosPatch1dMultiHeadAttention", "params": dict(base, patch_size=3)}
     return {"class": "RelPos1dMultiHeadAttention", "params": base}
@@ -18,6 +21,10 @@ def make_block(cfg):
     sd = seeded.seeded_state_dict(blk, cfg["seed"])
     blk.load_state_dict(sd)
     return blk, sd
+
+
+def block_G(cfg):
+    return int(cfg["att"][7:]) if cfg["att"].startswith("grouped") else None
 
 
 def block_lengths(cfg):

@@ -135,7 +135,7 @@ def test_relpos_attention_core(B, T, H, d, ragged, qlen_short):
     check_close("probs", probs, pr, RT, 1e-6)
     do = _r("do", (B * T, D))
     (o_ref * do).sum().backward()
-    dqkv, de = ops.relpos_attn_bwd(do, qkv.detach(), e.detach(), probs, B, T, H, d)
+    dqkv, de, _, _ = ops.relpos_attn_bwd(do, qkv.detach(), e.detach(), probs, B, T, H, d)
     check_close("dqkv", dqkv, qkv.grad, RT, AT)
     check_close("de", de, e.grad, RT, 1e-3)
 
