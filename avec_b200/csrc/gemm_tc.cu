@@ -37,7 +37,10 @@ enum OperandKind {
     OP_TMA_K = 8,        // 2-d tensor map, box (64 k, rows)                                -> K-major
     OP_TMA_MN = 9,       // 2-d tensor map, box (64 mn, 64 k) per 64-wide MN group          -> MN-major
     OP_TMA_CONV_K = 10,  // A of a stride-1 conv fwd / dgrad: 4-d map (C,W,H,N), box (64,W,BH,BI) at the tap's shift -> K-major
-    OP_TMA_CONV_MN = 11  // wgrad operands: A = dY (no shift), B = X shifted by the group's tap  -> MN-major, k = site
+    OP_TMA_CONV_MN = 11, // wgrad operands: A = dY (no shift), B = X shifted by the group's tap  -> MN-major, k = site
+    OP_TMA_CONV_HALO = 12 // A of a stride-1 3x3 conv on images wider than a tile: ONE halo tile ((BH+2) x (W+2) sites x 64 ch)
+                          // per 64-channel block is loaded per output tile and all 9 taps read it through row-offset
+                          // descriptors (the accumulator rows then live on the (W+2)-wide halo grid)  -> K-major
 };
 __host__ __device__ inline bool is_tma(int kind) { return kind >= OP_TMA_K; }
 __host__ __device__ inline bool is_mn(int kind) {
@@ -65,6 +68,8 @@ struct TcParams {
     int ct_BH, ct_BI, ct_tph;   // tile rows, images per tile, tiles per image (on the conv's OUTPUT grid ct_H x ct_W)
     int ct_H, ct_W, ct_s;       // output grid and spatial stride (1 or 2; strided taps use the tensor map's element strides)
     int ct_dgrad;               // tap shift sign (dgrad reads dy[p + pad - tap])
+    int halo_bytes;             // bytes of one halo tile (multiple of 1024); 0 = no halo mode
+    int halo_W2;                // W + 2
     int stg_dedicated;          // 1: epilogue staging has its own shared memory (persistent launches); 0: it aliases the drained ring
     int grid_m, grid_n, splits; // tile grid (the launch grid is min(#tiles, resident CTAs): persistent tile loop)
     unsigned long long* dbg_ts; // diagnostics (avec_set_debug_timestamps): CTA (0,0,0) records globaltimer at phase boundaries
@@ -467,7 +472,12 @@ __device__ __forceinline__ TileInfo decode_tile(const TcParams& p, int t) {
     ti.kb_begin = ti.z * p.kb_per_split;
     ti.nkb = min(p.num_kb, ti.kb_begin + p.kb_per_split) - ti.kb_begin;
     ti.m0 = ti.mtile * BM;
-    if (p.conv_tiles && p.a_kind == OP_TMA_CONV_K) {
+    if (p.conv_tiles && p.a_kind == OP_TMA_CONV_HALO) {
+        int tn0, th0;
+        conv_tile_origin(p, ti.mtile, tn0, th0);
+        ti.row_base = ((long long)tn0 * p.ct_H + th0) * p.ct_W;
+        ti.rows_valid = min(p.ct_BH, p.ct_H - th0);   // image rows (see tile_row)
+    } else if (p.conv_tiles && p.a_kind == OP_TMA_CONV_K) {
         int tn0, th0;
         conv_tile_origin(p, ti.mtile, tn0, th0);
         ti.row_base = ((long long)tn0 * p.ct_H + th0) * p.ct_W;
@@ -479,6 +489,17 @@ __device__ __forceinline__ TileInfo decode_tile(const TcParams& p, int t) {
     return ti;
 }
 
+
+// accumulator row r (0..127) of a tile -> output row (false: the row holds no output)
+__device__ __forceinline__ bool tile_row(const TcParams& p, const TileInfo& ti, int r, long long& row) {
+    if (p.halo_bytes) {   // rows live on the (W+2)-wide halo grid
+        const int hh = r / p.halo_W2, ww = r - hh * p.halo_W2;
+        row = ti.row_base + (long long)hh * p.ct_W + ww;
+        return ww < p.ct_W && hh < ti.rows_valid;   // rows_valid = image rows of this tile
+    }
+    row = ti.row_base + r;
+    return r < ti.rows_valid;
+}
 
 // ---- 8 consecutive columns of one output row (transposed-domain epilogue: 8 lanes cover one 64-column row segment)
 __device__ __forceinline__ void load8(const void* p, int dtype, size_t idx, float (&v)[8]) {
@@ -576,31 +597,18 @@ __device__ __forceinline__ void epilogue_warp(const TcParams& p, const EpiParams
         const int lc = q * 8;                 // column inside the slab
         const int gc = ti.n0 + c0 + lc;       // global column
         if (lc < ncol) {
-            const bool vec = gc + 8 <= p.N;
-            const bool need_aux = vec && ep.aux != nullptr &&
-                                  (ep.kind == AVEC_EPI_RESIDUAL || ep.kind == AVEC_EPI_DSWISH || ep.kind == AVEC_EPI_RELU);
-            // all eight residual / Swish' row segments of this lane are requested up front: one exposed latency, not eight
-            float x[8][8];
-            if (need_aux) {
-#pragma unroll
-                for (int pass = 0; pass < 8; ++pass) {
-                    const int r = warp * 32 + pass * 4 + rs;
-                    if (r < ti.rows_valid) load8(ep.aux, ep.aux_dtype, (size_t)(ti.row_base + r) * ep.ldaux + gc, x[pass]);
-                }
-            }
-#pragma unroll
+#pragma unroll 2
             for (int pass = 0; pass < 8; ++pass) {
                 const int rr = pass * 4 + rs;
-                const int r = warp * 32 + rr;
-                if (r >= ti.rows_valid) continue;
-                const long long row = ti.row_base + r;
+                long long row;
+                if (!tile_row(p, ti, warp * 32 + rr, row)) continue;
                 float a[8];
                 {
                     const float4 t0 = *reinterpret_cast<const float4*>(stg + rr * STG_LD + lc);
                     const float4 t1 = *reinterpret_cast<const float4*>(stg + rr * STG_LD + lc + 4);
                     a[0] = t0.x; a[1] = t0.y; a[2] = t0.z; a[3] = t0.w; a[4] = t1.x; a[5] = t1.y; a[6] = t1.z; a[7] = t1.w;
                 }
-                if (vec) {
+                if (gc + 8 <= p.N) {
                     const size_t oi = (size_t)row * ep.ldo + gc;
                     float o[8];
                     if (ep.kind == AVEC_EPI_ACCUM) {
@@ -622,15 +630,21 @@ __device__ __forceinline__ void epilogue_warp(const TcParams& p, const EpiParams
                             if (ep.out2) store8(ep.out2, ep.out2_dtype, (size_t)row * ep.ldo2 + gc, a);
 #pragma unroll
                             for (int j = 0; j < 8; ++j) o[j] = swishf_(a[j]);
-                        } else if (ep.kind == AVEC_EPI_RESIDUAL) {
+                        } else {
+                            float x[8];
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) o[j] = x[pass][j] + ep.alpha * a[j];
-                        } else if (ep.kind == AVEC_EPI_DSWISH) {
+                            for (int j = 0; j < 8; ++j) x[j] = 0.0f;
+                            if (ep.aux) load8(ep.aux, ep.aux_dtype, (size_t)row * ep.ldaux + gc, x);
+                            if (ep.kind == AVEC_EPI_RESIDUAL) {
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) o[j] = ep.alpha * a[j] * dswishf_(x[pass][j]);
-                        } else {  // RELU
+                                for (int j = 0; j < 8; ++j) o[j] = x[j] + ep.alpha * a[j];
+                            } else if (ep.kind == AVEC_EPI_DSWISH) {
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) o[j] = fmaxf(ep.alpha * a[j] + (need_aux ? x[pass][j] : 0.0f), 0.0f);
+                                for (int j = 0; j < 8; ++j) o[j] = ep.alpha * a[j] * dswishf_(x[j]);
+                            } else {  // RELU
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) o[j] = fmaxf(ep.alpha * a[j] + x[j], 0.0f);
+                            }
                         }
                         store8(ep.out, ep.out_dtype, oi, o);
                     }
@@ -669,7 +683,9 @@ __device__ __forceinline__ void epilogue_warp(const TcParams& p, const EpiParams
 __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUtensorMap mapA,
                                                                const __grid_constant__ CUtensorMap mapB) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_al = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* halo = smem_al;                                   // [2 slots][cpb][halo_bytes] (halo mode only)
+    uint8_t* smem = smem_al + 2 * p.cpb * p.halo_bytes;        // ring
     const int BN = p.BN;
     const int a_bytes = p.a_rows * 128;
     const int b_bytes = ((p.b_rows * 128 + 1023) / 1024) * 1024;
@@ -679,7 +695,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
     uint64_t* empty_bar = full_bar + 8;
     uint64_t* accum_full = empty_bar + 8;    // [2]
     uint64_t* accum_empty = accum_full + 2;  // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_empty + 2);
+    uint64_t* halo_full = accum_empty + 2;   // [2]
+    uint64_t* halo_empty = halo_full + 2;    // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(halo_empty + 2);
     RowInfo* rinfo = reinterpret_cast<RowInfo*>(ctrl + 256);
     int* tapofs = reinterpret_cast<int*>(ctrl + 256 + BM * sizeof(RowInfo));
     float* cstat = reinterpret_cast<float*>(ctrl + 256 + BM * sizeof(RowInfo) + 256 * sizeof(int));  // [2][256]
@@ -698,7 +716,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
     if (tid == 0) {
         const uint32_t full_count = (any_gather ? PRODUCER_THREADS : 0) + (any_tma ? 1 : 0);
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], full_count); mbar_init(&empty_bar[s], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&accum_full[i], 1); mbar_init(&accum_empty[i], PRODUCER_THREADS); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&accum_full[i], 1); mbar_init(&accum_empty[i], PRODUCER_THREADS);
+            mbar_init(&halo_full[i], 1); mbar_init(&halo_empty[i], 1);
+        }
         fence_barrier_init();
         if (a_tma) tma_prefetch_desc(&mapA);
         if (b_tma) tma_prefetch_desc(&mapB);
@@ -815,9 +836,21 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
     } else if (warp == 5) {
         // ===================== TMA producer (one thread) =====================
         if (any_tma && lane == 0) {
-            int it = 0;
-            for (int t = blockIdx.x; t < tiles_total; t += gridDim.x) {
+            int it = 0, j = 0;
+            const bool halo_mode = p.a_kind == OP_TMA_CONV_HALO;
+            for (int t = blockIdx.x; t < tiles_total; t += gridDim.x, ++j) {
                 const TileInfo ti = decode_tile(p, t);
+                if (halo_mode) {
+                    // one halo tile per 64-channel block for this output tile (double-buffered across tiles)
+                    const int slot = j & 1;
+                    mbar_wait(&halo_empty[slot], (uint32_t)(((j >> 1) & 1) ^ 1));
+                    int tn0, th0;
+                    conv_tile_origin(p, ti.mtile, tn0, th0);
+                    mbar_expect_tx(&halo_full[slot], (uint32_t)(p.cpb * p.a_tx));
+                    for (int cb = 0; cb < p.cpb; ++cb)
+                        tma_load_4d(smem_u32(halo + (size_t)(slot * p.cpb + cb) * p.halo_bytes), &mapA, &halo_full[slot], cb * BKE, -p.g.pw,
+                                    th0 - p.g.ph, tn0);
+                }
                 for (int i = 0; i < ti.nkb; ++i) {
                     const int g = it + i;
                     const int s = g % p.stages;
@@ -826,8 +859,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
                     uint8_t* a_tile = smem + (size_t)s * stage_bytes;
                     uint8_t* b_tile = a_tile + a_bytes;
                     const int kb = ti.kb_begin + i;
-                    mbar_expect_tx(&full_bar[s], (uint32_t)((a_tma ? p.a_tx : 0) + (b_tma ? p.b_tx : 0)));
-                    if (a_tma) tma_fill(p, p.a_kind, &mapA, a_tile, &full_bar[s], p.a_rows, p.a_group_stride, ti.m0, kb, ti.mtile, true);
+                    mbar_expect_tx(&full_bar[s], (uint32_t)(((a_tma && !halo_mode) ? p.a_tx : 0) + (b_tma ? p.b_tx : 0)));
+                    if (a_tma && !halo_mode) tma_fill(p, p.a_kind, &mapA, a_tile, &full_bar[s], p.a_rows, p.a_group_stride, ti.m0, kb, ti.mtile, true);
                     if (b_tma) tma_fill(p, p.b_kind, &mapB, b_tile, &full_bar[s], p.b_rows, p.b_group_stride, ti.n0, kb, ti.mtile, false);
                 }
                 it += ti.nkb;
@@ -845,6 +878,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
             mbar_wait(&accum_empty[buf], (uint32_t)(((j >> 1) & 1) ^ 1));   // epilogue has drained this accumulator buffer
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
+            const bool halo_mode = p.a_kind == OP_TMA_CONV_HALO;
+            if (halo_mode) { mbar_wait(&halo_full[buf], (uint32_t)((j >> 1) & 1)); tc_fence_after(); }
             for (int i = 0; i < ti.nkb; ++i) {
                 const int g = it + i;
                 const int s = g % p.stages;
@@ -853,8 +888,17 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
                 tc_fence_after();
                 if (lane == 0) {
                     if (i == 0 && j == 0) AVEC_TS(2);   // first k-block landed in shared memory
-                    const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes) + (uint32_t)p.dbg_rowofs * 128u;
+                    uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes) + (uint32_t)p.dbg_rowofs * 128u;
                     const uint32_t b_addr = smem_u32(smem + (size_t)s * stage_bytes) + a_bytes;
+                    if (halo_mode) {
+                        // tap (kh, kw) of 64-channel block cb reads the resident halo tile from row kh*(W+2)+kw on
+                        // (dgrad: the mirrored tap); a 128-byte row offset keeps the 128B-swizzle phase consistent
+                        const int kb = ti.kb_begin + i;
+                        const int tap = kb / p.cpb, cb = kb - tap * p.cpb;
+                        int kh = tap / p.g.KW, kw = tap - kh * p.g.KW;
+                        if (p.ct_dgrad) { kh = p.g.KH - 1 - kh; kw = p.g.KW - 1 - kw; }
+                        a_addr = smem_u32(halo + (size_t)(buf * p.cpb + cb) * p.halo_bytes) + (uint32_t)(kh * p.halo_W2 + kw) * 128u;
+                    }
                     for (int k = 0; k < p.ksteps; ++k) {
                         // K-major: advance 32 bytes inside the 128-byte swizzle row; SBO = 1024 (8 rows).
                         // MN-major: advance 16 reduction rows = 2048 bytes; LBO = next 64-wide MN group, SBO = 1024.
@@ -863,7 +907,11 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
                         umma_f16(d_tmem, adesc, bdesc, idesc, (i > 0 || k > 0) ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[s]);
-                    if (i == ti.nkb - 1) { umma_commit(&accum_full[buf]); if (j == 0) AVEC_TS(3); }   // last MMA of the tile issued
+                    if (i == ti.nkb - 1) {   // last MMA of the tile issued
+                        umma_commit(&accum_full[buf]);
+                        if (halo_mode) umma_commit(&halo_empty[buf]);
+                        if (j == 0) AVEC_TS(3);
+                    }
                 }
                 __syncwarp();
             }
@@ -1022,13 +1070,32 @@ int avec_gemm_tc(const avec_gemm_args* a, cudaStream_t st) {
     }
     if (wgrad_bn_fixed) p.BN = a->N >= 256 ? 256 : (a->N >= 192 ? 192 : (a->N >= 128 ? 128 : 64));
 
+    // ---- halo mode: stride-1 3x3 fwd / dgrad on images larger than one tile (ResNet stage 1)
+    bool halo = false;
+    {
+        static int halo_on = -1;
+        if (halo_on < 0) { const char* e = getenv("AVEC_HALO"); halo_on = e ? atoi(e) : 1; }
+        const ConvGeom& g = p.g;
+        if (conv_tma && halo_on && (a->mode == AVEC_GEMM_CONV_FWD || a->mode == AVEC_GEMM_CONV_DGRAD) && g.sh == 1 && g.KH == 3 && g.KW == 3 &&
+            g.Ho * g.Wo > 128 && g.Wo + 2 <= 128) {
+            const int W2 = g.Wo + 2, bh = 128 / W2;
+            const int cin_blocks = (a->mode == AVEC_GEMM_CONV_FWD ? g.C : g.Co) / 64;
+            const int hb = cdiv((bh + 2) * W2 * 128, 1024) * 1024;
+            if (bh >= 1 && bh * g.Wo * 10 >= BH * g.Wo * 9 && 2 * cin_blocks * hb <= 96 * 1024) {
+                halo = true;
+                BH = bh; BI = 1; tph = cdiv(g.Ho, bh);
+                p.halo_bytes = hb; p.halo_W2 = W2;
+            }
+        }
+    }
     // ---- conv TMA geometry
     if (conv_tma) {
         p.conv_tiles = 1; p.ct_BH = BH; p.ct_BI = BI; p.ct_tph = tph;
         p.ct_H = p.g.Ho; p.ct_W = p.g.Wo; p.ct_s = p.g.sh;
         const int ntiles = BI == 1 ? p.g.N * tph : cdiv(p.g.N, BI);
         const int tile_rows = BI == 1 ? BH * p.g.Wo : BI * p.g.Ho * p.g.Wo;   // <= 128
-        const cuuint32_t sbox[4] = {64, (cuuint32_t)((p.g.Wo - 1) * p.g.sw + 1), (cuuint32_t)((BH - 1) * p.g.sh + 1), (cuuint32_t)BI};
+        const cuuint32_t sbox[4] = {64, (cuuint32_t)(halo ? p.halo_W2 : (p.g.Wo - 1) * p.g.sw + 1),
+                                    (cuuint32_t)(halo ? BH + 2 : (BH - 1) * p.g.sh + 1), (cuuint32_t)BI};
         const cuuint32_t sstr[4] = {1, (cuuint32_t)p.g.sw, (cuuint32_t)p.g.sh, 1};
         // 4-d maps over the NHWC tensors
         const ConvGeom& g = p.g;
@@ -1049,7 +1116,8 @@ int avec_gemm_tc(const avec_gemm_args* a, cudaStream_t st) {
         } else {
             const int Cin = a->mode == AVEC_GEMM_CONV_FWD ? g.C : g.Co;   // channels of the gathered tensor
             grid_m = ntiles;
-            p.a_tx = tile_rows * 128;
+            p.a_tx = halo ? (BH + 2) * p.halo_W2 * 128 : tile_rows * 128;
+            if (halo) p.a_kind = OP_TMA_CONV_HALO;
             cuuint64_t dA[4] = {(cuuint64_t)Cin, (cuuint64_t)g.Wi, (cuuint64_t)g.Hi, (cuuint64_t)g.N};
             cuuint64_t sA[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cin * g.Wi * 2, (cuuint64_t)Cin * g.Wi * g.Hi * 2};
             if (!encode_map(&mapA, a->A, 4, dA, sA, sbox, sstr)) return AVEC_ERR_DRIVER;
@@ -1075,7 +1143,7 @@ int avec_gemm_tc(const avec_gemm_args* a, cudaStream_t st) {
         if (dbg < 0) { const char* e = getenv("AVEC_DEBUG_ROWOFS"); dbg = e ? atoi(e) : 0; }
         if (dbg > 0 && p.a_kind == OP_TMA_K && a->mode == AVEC_GEMM_PLAIN) p.dbg_rowofs = dbg;
     }
-    if (p.a_rows == 0) p.a_rows = BM;
+    if (p.a_rows == 0) p.a_rows = halo ? 0 : BM;
     if (p.b_rows == 0) p.b_rows = is_mn(p.b_kind) ? cdiv(p.BN, 64) * 64 : p.BN;
 
     int split = (a->epi == AVEC_EPI_ACCUM && a->split_k > 1) ? a->split_k : 1;
@@ -1098,7 +1166,9 @@ int avec_gemm_tc(const avec_gemm_args* a, cudaStream_t st) {
         p.stg_dedicated = 1;
         p.stages = 8;
         while (p.stages > 2 && (size_t)p.stages * stage_bytes + STG_BYTES + ctrl_bytes > 227 * 1024) --p.stages;
-        smem = (size_t)p.stages * stage_bytes + STG_BYTES + ctrl_bytes;
+        const size_t halo_total = 2 * (size_t)p.cpb * p.halo_bytes;
+        while (p.stages > 2 && halo_total + (size_t)p.stages * stage_bytes + STG_BYTES + ctrl_bytes > 227 * 1024) --p.stages;
+        smem = halo_total + (size_t)p.stages * stage_bytes + STG_BYTES + ctrl_bytes;
         if (smem > 227 * 1024) return AVEC_ERR_UNSUPPORTED;
     }
     static bool attr_set = false;
