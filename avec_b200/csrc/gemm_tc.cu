@@ -783,7 +783,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
                     if (i < nkb) {
                         const int g = it + i;
                         const int s = g % p.stages;
-                        const uint32_t ph = (uint32_t)((g / p.stages) & 1);
+                        const uint32_t ph = (uint32_t)((g / p.stages) & 1);   // (one tile per CTA in gather mode: cheap enough)
                         mbar_wait(&empty_bar[s], ph ^ 1u);
                         uint8_t* a_tile = smem + (size_t)s * stage_bytes;
                         uint8_t* b_tile = a_tile + a_bytes;
@@ -836,34 +836,51 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
     } else if (warp == 5) {
         // ===================== TMA producer (one thread) =====================
         if (any_tma && lane == 0) {
-            int it = 0, j = 0;
+            // One thread feeds the whole ring: everything per k-block is kept to a handful of scalar instructions (running
+            // stage / phase / tap counters, no integer divisions) - with 64-column tiles a k-block is only 128 MMA cycles.
+            int j = 0, st = 0;
+            uint32_t ph = 0;
             const bool halo_mode = p.a_kind == OP_TMA_CONV_HALO;
+            const uint32_t tx = (uint32_t)(((a_tma && !halo_mode) ? p.a_tx : 0) + (b_tma ? p.b_tx : 0));
+            const uint32_t ring0 = smem_u32(smem);
             for (int t = blockIdx.x; t < tiles_total; t += gridDim.x, ++j) {
                 const TileInfo ti = decode_tile(p, t);
+                int tn0 = 0, th0 = 0;
+                if (p.conv_tiles && p.a_kind != OP_TMA_CONV_MN) conv_tile_origin(p, ti.mtile, tn0, th0);
                 if (halo_mode) {
                     // one halo tile per 64-channel block for this output tile (double-buffered across tiles)
                     const int slot = j & 1;
                     mbar_wait(&halo_empty[slot], (uint32_t)(((j >> 1) & 1) ^ 1));
-                    int tn0, th0;
-                    conv_tile_origin(p, ti.mtile, tn0, th0);
                     mbar_expect_tx(&halo_full[slot], (uint32_t)(p.cpb * p.a_tx));
                     for (int cb = 0; cb < p.cpb; ++cb)
                         tma_load_4d(smem_u32(halo + (size_t)(slot * p.cpb + cb) * p.halo_bytes), &mapA, &halo_full[slot], cb * BKE, -p.g.pw,
                                     th0 - p.g.ph, tn0);
                 }
+                int kh = 0, kw = 0, cb = 0;   // filter tap / channel block of the current k-block (conv K-major A)
                 for (int i = 0; i < ti.nkb; ++i) {
-                    const int g = it + i;
-                    const int s = g % p.stages;
-                    const uint32_t ph = (uint32_t)((g / p.stages) & 1);
-                    mbar_wait(&empty_bar[s], ph ^ 1u);
-                    uint8_t* a_tile = smem + (size_t)s * stage_bytes;
-                    uint8_t* b_tile = a_tile + a_bytes;
+                    mbar_wait(&empty_bar[st], ph ^ 1u);
+                    const uint32_t a_dst = ring0 + (uint32_t)st * (uint32_t)stage_bytes;
+                    const uint32_t b_dst = a_dst + (uint32_t)a_bytes;
+                    uint64_t* bar = &full_bar[st];
                     const int kb = ti.kb_begin + i;
-                    mbar_expect_tx(&full_bar[s], (uint32_t)(((a_tma && !halo_mode) ? p.a_tx : 0) + (b_tma ? p.b_tx : 0)));
-                    if (a_tma && !halo_mode) tma_fill(p, p.a_kind, &mapA, a_tile, &full_bar[s], p.a_rows, p.a_group_stride, ti.m0, kb, ti.mtile, true);
-                    if (b_tma) tma_fill(p, p.b_kind, &mapB, b_tile, &full_bar[s], p.b_rows, p.b_group_stride, ti.n0, kb, ti.mtile, false);
+                    mbar_expect_tx(bar, tx);
+                    if (a_tma && !halo_mode) {
+                        if (p.a_kind == OP_TMA_K) {
+                            tma_load_2d(a_dst, &mapA, bar, kb * BKE, ti.m0 - p.dbg_rowofs);
+                        } else if (p.a_kind == OP_TMA_CONV_K) {
+                            const int dh = p.ct_dgrad ? p.g.ph - kh : kh - p.g.ph, dw = p.ct_dgrad ? p.g.pw - kw : kw - p.g.pw;
+                            tma_load_4d(a_dst, &mapA, bar, cb * BKE, dw, th0 * p.ct_s + dh, tn0);
+                        } else {
+                            tma_fill(p, p.a_kind, &mapA, smem + (size_t)st * stage_bytes, bar, p.a_rows, p.a_group_stride, ti.m0, kb, ti.mtile, true);
+                        }
+                    }
+                    if (b_tma) {
+                        if (p.b_kind == OP_TMA_K) tma_load_2d(b_dst, &mapB, bar, kb * BKE, ti.n0);
+                        else tma_fill(p, p.b_kind, &mapB, smem + (size_t)st * stage_bytes + a_bytes, bar, p.b_rows, p.b_group_stride, ti.n0, kb, ti.mtile, false);
+                    }
+                    if (++cb == p.cpb) { cb = 0; if (++kw == p.g.KW) { kw = 0; ++kh; } }
+                    if (++st == p.stages) { st = 0; ph ^= 1u; }
                 }
-                it += ti.nkb;
             }
         }
     } else {
@@ -871,42 +888,42 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
         const int a_mn = is_mn(p.a_kind) ? 1 : 0;
         const int b_mn = is_mn(p.b_kind) ? 1 : 0;
         const uint32_t idesc = make_idesc(BN, a_mn, b_mn);
-        int it = 0, j = 0;
+        const bool halo_mode = p.a_kind == OP_TMA_CONV_HALO;
+        // descriptors: constant high part + (address >> 4); per K-step the address advances 32 B (K-major) / 2048 B (MN-major)
+        const uint64_t a_desc0 = a_mn ? make_smem_desc(0, p.a_group_stride, 1024) : make_smem_desc(0, 16, 1024);
+        const uint64_t b_desc0 = b_mn ? make_smem_desc(0, p.b_group_stride, 1024) : make_smem_desc(0, 16, 1024);
+        const uint32_t a_kstep = a_mn ? (2048u >> 4) : (32u >> 4), b_kstep = b_mn ? (2048u >> 4) : (32u >> 4);
+        const uint32_t ring0 = smem_u32(smem) >> 4, stage_step = (uint32_t)stage_bytes >> 4, a_bytes16 = (uint32_t)a_bytes >> 4;
+        const uint32_t rowofs16 = ((uint32_t)p.dbg_rowofs * 128u) >> 4;
+        int j = 0, st = 0;
+        uint32_t ph = 0;
         for (int t = blockIdx.x; t < tiles_total; t += gridDim.x, ++j) {
             const TileInfo ti = decode_tile(p, t);
             const int buf = j & 1;
             mbar_wait(&accum_empty[buf], (uint32_t)(((j >> 1) & 1) ^ 1));   // epilogue has drained this accumulator buffer
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
-            const bool halo_mode = p.a_kind == OP_TMA_CONV_HALO;
             if (halo_mode) { mbar_wait(&halo_full[buf], (uint32_t)((j >> 1) & 1)); tc_fence_after(); }
+            int kh = 0, kw = 0, cb = 0;
             for (int i = 0; i < ti.nkb; ++i) {
-                const int g = it + i;
-                const int s = g % p.stages;
-                const uint32_t ph = (uint32_t)((g / p.stages) & 1);
-                mbar_wait(&full_bar[s], ph);
+                mbar_wait(&full_bar[st], ph);
                 tc_fence_after();
                 if (lane == 0) {
                     if (i == 0 && j == 0) AVEC_TS(2);   // first k-block landed in shared memory
-                    uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes) + (uint32_t)p.dbg_rowofs * 128u;
-                    const uint32_t b_addr = smem_u32(smem + (size_t)s * stage_bytes) + a_bytes;
+                    const uint32_t stage16 = ring0 + (uint32_t)st * stage_step;
+                    uint32_t a16 = stage16 + rowofs16;
                     if (halo_mode) {
                         // tap (kh, kw) of 64-channel block cb reads the resident halo tile from row kh*(W+2)+kw on
                         // (dgrad: the mirrored tap); a 128-byte row offset keeps the 128B-swizzle phase consistent
-                        const int kb = ti.kb_begin + i;
-                        const int tap = kb / p.cpb, cb = kb - tap * p.cpb;
-                        int kh = tap / p.g.KW, kw = tap - kh * p.g.KW;
-                        if (p.ct_dgrad) { kh = p.g.KH - 1 - kh; kw = p.g.KW - 1 - kw; }
-                        a_addr = smem_u32(halo + (size_t)(buf * p.cpb + cb) * p.halo_bytes) + (uint32_t)(kh * p.halo_W2 + kw) * 128u;
+                        const int th = p.ct_dgrad ? p.g.KH - 1 - kh : kh, tw = p.ct_dgrad ? p.g.KW - 1 - kw : kw;
+                        a16 = (smem_u32(halo + (size_t)(buf * p.cpb + cb) * p.halo_bytes) + (uint32_t)(th * p.halo_W2 + tw) * 128u) >> 4;
                     }
+                    uint64_t adesc = a_desc0 + a16, bdesc = b_desc0 + stage16 + a_bytes16;
                     for (int k = 0; k < p.ksteps; ++k) {
-                        // K-major: advance 32 bytes inside the 128-byte swizzle row; SBO = 1024 (8 rows).
-                        // MN-major: advance 16 reduction rows = 2048 bytes; LBO = next 64-wide MN group, SBO = 1024.
-                        const uint64_t adesc = a_mn ? make_smem_desc(a_addr + k * 2048, p.a_group_stride, 1024) : make_smem_desc(a_addr + k * 32, 16, 1024);
-                        const uint64_t bdesc = b_mn ? make_smem_desc(b_addr + k * 2048, p.b_group_stride, 1024) : make_smem_desc(b_addr + k * 32, 16, 1024);
                         umma_f16(d_tmem, adesc, bdesc, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                        adesc += a_kstep; bdesc += b_kstep;
                     }
-                    umma_commit(&empty_bar[s]);
+                    umma_commit(&empty_bar[st]);
                     if (i == ti.nkb - 1) {   // last MMA of the tile issued
                         umma_commit(&accum_full[buf]);
                         if (halo_mode) umma_commit(&halo_empty[buf]);
@@ -914,8 +931,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
                     }
                 }
                 __syncwarp();
+                if (++cb == p.cpb) { cb = 0; if (++kw == p.g.KW) { kw = 0; ++kh; } }
+                if (++st == p.stages) { st = 0; ph ^= 1u; }
             }
-            it += ti.nkb;
         }
         tc_fence_before();
     }
