@@ -7,7 +7,7 @@
 
 namespace {
 
-constexpr int DW_TO = 32;    // output frames per CTA
+constexpr int DW_TO = 8;     // output frames per CTA (short tiles: these launches are latency-, not bandwidth-bound)
 constexpr int DW_CH = 128;   // channels per CTA (= threads)
 constexpr int DW_MAXK = 15;
 

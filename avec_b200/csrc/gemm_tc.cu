@@ -73,6 +73,7 @@ struct TcParams {
     int stg_dedicated;          // 1: epilogue staging has its own shared memory (persistent launches); 0: it aliases the drained ring
     int grid_m, grid_n, splits; // tile grid (the launch grid is min(#tiles, resident CTAs): persistent tile loop)
     unsigned long long* dbg_ts; // diagnostics (avec_set_debug_timestamps): CTA (0,0,0) records globaltimer at phase boundaries
+    int dbg_mode;               // diagnostics (AVEC_DEBUG_MODE bits): 1 no TMA loads, 2 no MMAs, 4 sleeping epilogue wait, 8 one-lane MMA poll
     int dbg_rowofs;             // diagnostics (AVEC_DEBUG_ROWOFS): A tile loaded `ofs` rows early, descriptor started `ofs` rows in
 };
 
@@ -93,6 +94,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "@p bra WAIT_DONE;\n\t"
         "bra WAIT_LOOP;\n\t"
         "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// one elected lane of a converged warp (elect.sync): code under it may feed warp-uniform operands straight to the uniform
+// datapath (UTCHMMA / UTMALDG) - a plain `lane == 0` branch makes ptxas wrap every such instruction in an
+// ELECT / R2UR.BROADCAST waterfall loop (~160 cycles per MMA)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try(bar, parity)) __nanosleep(100);
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -145,6 +163,12 @@ __device__ __forceinline__ unsigned long long gtime() {
     return t;
 }
 #define AVEC_TS(slot) do { if (p.dbg_ts && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) p.dbg_ts[slot] = gtime(); } while (0)
+// per-tile timeline of CTA 0 (tiles j < 32): slots 8 + 5 j + {0 epilogue starts waiting, 1 accumulator ready, 2 epilogue done,
+// 3 first k-block in shared memory, 4 last MMA issued}; the debug buffer holds 8 + 5 * 32 = 168 values
+// k-block level trace of tile 6 of CTA 0 in SM clocks: [168 + 2 i + {0 full-wait done, 1 MMAs + commit issued}] (MMA thread),
+// [200 + 2 i + {0 empty-wait done, 1 TMA issued}] (producer thread), i < 16; buffer holds 232 values
+#define AVEC_TSK(j, i, base, k) do { if (p.dbg_ts && blockIdx.x == 0 && (j) == 6 && (i) < 16) p.dbg_ts[(base) + 2 * (i) + (k)] = (unsigned long long)clock64(); } while (0)
+#define AVEC_TSJ(j, k) do { if (p.dbg_ts && blockIdx.x == 0 && (j) < 32) p.dbg_ts[8 + 5 * (j) + (k)] = gtime(); } while (0)
 
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -703,7 +727,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
     float* cstat = reinterpret_cast<float*>(ctrl + 256 + BM * sizeof(RowInfo) + 256 * sizeof(int));  // [2][256]
     float* bias_s = cstat + 512;                                                                     // [256]
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform by construction (and known to be so by ptxas)
     if (tid == 0) AVEC_TS(0);   // kernel start
     const bool a_tma = is_tma(p.a_kind), b_tma = is_tma(p.b_kind);
     const bool any_gather = !a_tma || !b_tma, any_tma = a_tma || b_tma;
@@ -812,9 +837,12 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
                 const int nbytes = min(BN, p.N - n0) * esz;
                 for (int o = 0; o < nbytes; o += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(a0 + o));
             }
-            mbar_wait(&accum_full[buf], (uint32_t)((j >> 1) & 1));
+            if (tid == 0) AVEC_TSJ(j, 0);
+            if (p.dbg_mode & 4) mbar_wait_sleep(&accum_full[buf], (uint32_t)((j >> 1) & 1));
+            else mbar_wait(&accum_full[buf], (uint32_t)((j >> 1) & 1));
             tc_fence_after();
             if (tid == 0 && j == 0) AVEC_TS(4);   // accumulator complete, epilogue starts
+            if (tid == 0) AVEC_TSJ(j, 1);
             const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * BN);
             EpiParams ep = p.ep;
             ep.bias = nullptr;   // the bias slice lives in shared memory (bias_s)
@@ -831,11 +859,12 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
                     if (n0 + cc < p.N) { atomicAdd(dst + n0 + cc, cstat[cc]); atomicAdd(dst + p.N + n0 + cc, cstat[256 + cc]); }
             }
             if (tid == 0 && j == 0) AVEC_TS(5);   // epilogue done
+            if (tid == 0) AVEC_TSJ(j, 2);
         }
         tc_fence_before();
     } else if (warp == 5) {
-        // ===================== TMA producer (one thread) =====================
-        if (any_tma && lane == 0) {
+        // ===================== TMA producer (whole warp walks the ring, one elected lane issues) =====================
+        if (any_tma) {
             // One thread feeds the whole ring: everything per k-block is kept to a handful of scalar instructions (running
             // stage / phase / tap counters, no integer divisions) - with 64-column tiles a k-block is only 128 MMA cycles.
             int j = 0, st = 0;
@@ -851,33 +880,45 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
                     // one halo tile per 64-channel block for this output tile (double-buffered across tiles)
                     const int slot = j & 1;
                     mbar_wait(&halo_empty[slot], (uint32_t)(((j >> 1) & 1) ^ 1));
-                    mbar_expect_tx(&halo_full[slot], (uint32_t)(p.cpb * p.a_tx));
-                    for (int cb = 0; cb < p.cpb; ++cb)
-                        tma_load_4d(smem_u32(halo + (size_t)(slot * p.cpb + cb) * p.halo_bytes), &mapA, &halo_full[slot], cb * BKE, -p.g.pw,
-                                    th0 - p.g.ph, tn0);
+                    if (elect_one()) {
+                        mbar_expect_tx(&halo_full[slot], (uint32_t)(p.cpb * p.a_tx));
+                        for (int cb = 0; cb < p.cpb; ++cb)
+                            tma_load_4d(smem_u32(halo + (size_t)(slot * p.cpb + cb) * p.halo_bytes), &mapA, &halo_full[slot], cb * BKE, -p.g.pw,
+                                        th0 - p.g.ph, tn0);
+                    }
+                    __syncwarp();
                 }
                 int kh = 0, kw = 0, cb = 0;   // filter tap / channel block of the current k-block (conv K-major A)
                 for (int i = 0; i < ti.nkb; ++i) {
                     mbar_wait(&empty_bar[st], ph ^ 1u);
-                    const uint32_t a_dst = ring0 + (uint32_t)st * (uint32_t)stage_bytes;
-                    const uint32_t b_dst = a_dst + (uint32_t)a_bytes;
-                    uint64_t* bar = &full_bar[st];
-                    const int kb = ti.kb_begin + i;
-                    mbar_expect_tx(bar, tx);
-                    if (a_tma && !halo_mode) {
-                        if (p.a_kind == OP_TMA_K) {
-                            tma_load_2d(a_dst, &mapA, bar, kb * BKE, ti.m0 - p.dbg_rowofs);
-                        } else if (p.a_kind == OP_TMA_CONV_K) {
-                            const int dh = p.ct_dgrad ? p.g.ph - kh : kh - p.g.ph, dw = p.ct_dgrad ? p.g.pw - kw : kw - p.g.pw;
-                            tma_load_4d(a_dst, &mapA, bar, cb * BKE, dw, th0 * p.ct_s + dh, tn0);
+                    if (elect_one()) {
+                        const uint32_t a_dst = ring0 + (uint32_t)st * (uint32_t)stage_bytes;
+                        const uint32_t b_dst = a_dst + (uint32_t)a_bytes;
+                        uint64_t* bar = &full_bar[st];
+                        const int kb = ti.kb_begin + i;
+                        AVEC_TSK(j, i, 200, 0);
+                        if (p.dbg_mode & 1) {
+                            mbar_arrive(bar);
                         } else {
-                            tma_fill(p, p.a_kind, &mapA, smem + (size_t)st * stage_bytes, bar, p.a_rows, p.a_group_stride, ti.m0, kb, ti.mtile, true);
+                            mbar_expect_tx(bar, tx);
+                            if (a_tma && !halo_mode) {
+                                if (p.a_kind == OP_TMA_K) {
+                                    tma_load_2d(a_dst, &mapA, bar, kb * BKE, ti.m0 - p.dbg_rowofs);
+                                } else if (p.a_kind == OP_TMA_CONV_K) {
+                                    const int dh = p.ct_dgrad ? p.g.ph - kh : kh - p.g.ph, dw = p.ct_dgrad ? p.g.pw - kw : kw - p.g.pw;
+                                    tma_load_4d(a_dst, &mapA, bar, cb * BKE, dw, th0 * p.ct_s + dh, tn0);
+                                } else {
+                                    tma_fill(p, p.a_kind, &mapA, smem + (size_t)st * stage_bytes, bar, p.a_rows, p.a_group_stride, ti.m0, kb, ti.mtile, true);
+                                }
+                            }
+                            if (b_tma) {
+                                if (p.b_kind == OP_TMA_K) tma_load_2d(b_dst, &mapB, bar, kb * BKE, ti.n0);
+                                else tma_fill(p, p.b_kind, &mapB, smem + (size_t)st * stage_bytes + a_bytes, bar, p.b_rows, p.b_group_stride, ti.n0, kb, ti.mtile, false);
+                            }
                         }
+                        AVEC_TSK(j, i, 200, 1);
                     }
-                    if (b_tma) {
-                        if (p.b_kind == OP_TMA_K) tma_load_2d(b_dst, &mapB, bar, kb * BKE, ti.n0);
-                        else tma_fill(p, p.b_kind, &mapB, smem + (size_t)st * stage_bytes + a_bytes, bar, p.b_rows, p.b_group_stride, ti.n0, kb, ti.mtile, false);
-                    }
+                    __syncwarp();
                     if (++cb == p.cpb) { cb = 0; if (++kw == p.g.KW) { kw = 0; ++kh; } }
                     if (++st == p.stages) { st = 0; ph ^= 1u; }
                 }
@@ -908,8 +949,15 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
             for (int i = 0; i < ti.nkb; ++i) {
                 mbar_wait(&full_bar[st], ph);
                 tc_fence_after();
-                if (lane == 0) {
+                const bool leader = elect_one();
+                if (leader && (p.dbg_mode & 2)) {
+                    if (i == 0) AVEC_TSJ(j, 3);
+                    mbar_arrive(&empty_bar[st]);
+                    if (i == ti.nkb - 1) { mbar_arrive(&accum_full[buf]); AVEC_TSJ(j, 4); }
+                } else if (leader) {
+                    AVEC_TSK(j, i, 168, 0);
                     if (i == 0 && j == 0) AVEC_TS(2);   // first k-block landed in shared memory
+                    if (i == 0) AVEC_TSJ(j, 3);
                     const uint32_t stage16 = ring0 + (uint32_t)st * stage_step;
                     uint32_t a16 = stage16 + rowofs16;
                     if (halo_mode) {
@@ -928,7 +976,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
                         umma_commit(&accum_full[buf]);
                         if (halo_mode) umma_commit(&halo_empty[buf]);
                         if (j == 0) AVEC_TS(3);
+                        AVEC_TSJ(j, 4);
                     }
+                    AVEC_TSK(j, i, 168, 1);
                 }
                 __syncwarp();
                 if (++cb == p.cpb) { cb = 0; if (++kw == p.g.KW) { kw = 0; ++kh; } }
@@ -1092,7 +1142,7 @@ int avec_gemm_tc(const avec_gemm_args* a, cudaStream_t st) {
     bool halo = false;
     {
         static int halo_on = -1;
-        if (halo_on < 0) { const char* e = getenv("AVEC_HALO"); halo_on = e ? atoi(e) : 1; }
+        if (halo_on < 0) { const char* e = getenv("AVEC_HALO"); halo_on = e ? atoi(e) : 0; }
         const ConvGeom& g = p.g;
         if (conv_tma && halo_on && (a->mode == AVEC_GEMM_CONV_FWD || a->mode == AVEC_GEMM_CONV_DGRAD) && g.sh == 1 && g.KH == 3 && g.KW == 3 &&
             g.Ho * g.Wo > 128 && g.Wo + 2 <= 128) {
@@ -1160,6 +1210,9 @@ int avec_gemm_tc(const avec_gemm_args* a, cudaStream_t st) {
         static int dbg = -1;
         if (dbg < 0) { const char* e = getenv("AVEC_DEBUG_ROWOFS"); dbg = e ? atoi(e) : 0; }
         if (dbg > 0 && p.a_kind == OP_TMA_K && a->mode == AVEC_GEMM_PLAIN) p.dbg_rowofs = dbg;
+        static int dbg_mode = -1;
+        if (dbg_mode < 0) { const char* e = getenv("AVEC_DEBUG_MODE"); dbg_mode = e ? atoi(e) : 0; }
+        p.dbg_mode = dbg_mode;
     }
     if (p.a_rows == 0) p.a_rows = halo ? 0 : BM;
     if (p.b_rows == 0) p.b_rows = is_mn(p.b_kind) ? cdiv(p.BN, 64) * 64 : p.BN;

@@ -280,7 +280,18 @@ __global__ void __launch_bounds__(CR_THREADS) colreduce_kernel(F f_in, long long
     for (int j = 0; j < V; ++j) { a0[j] = 0.0f; a1[j] = 0.0f; }
     if (c < C) {
         f.prep(c);   // per-channel constants (this thread's channel group is fixed)
-        for (long long r = r0 + threadIdx.y; r < r1; r += Y) {
+        long long r = r0 + threadIdx.y;
+        // four rows per iteration: 4x the loads in flight per thread (these kernels are pure HBM streams)
+        for (; r + 3LL * Y < r1; r += 4LL * Y) {
+            float v0[4][V], v1[4][V];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) f(r + (long long)q * Y, c, v0[q], v1[q]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int j = 0; j < V; ++j) { a0[j] += v0[q][j]; a1[j] += v1[q][j]; }
+        }
+        for (; r < r1; r += Y) {
             float v0[V], v1[V];
             f(r, c, v0, v1);
 #pragma unroll

@@ -104,10 +104,11 @@ typedef struct avec_gemm_args {
 int avec_gemm(const avec_gemm_args* args, avec_stream_t stream);
 /* diagnostics: 0 forces the cp.async gather producers even where a TMA descriptor is possible (default 1) */
 void avec_set_tma(int enabled);
-/* diagnostics: device buffer of 8 uint64; CTA (0,0,0) of every tcgen05 GEMM launch records %globaltimer (ns) at
+/* diagnostics: device buffer of 232 uint64; CTA (0,0,0) of every tcgen05 GEMM launch records %globaltimer (ns) at
  * [0] start, [1] setup done, [2] first k-block in smem, [3] last MMA issued, [4] accumulator complete, [5] epilogue
- * done, [6] TMEM released.  NULL disables. */
-void avec_set_debug_timestamps(void* dev_buf_8_u64);
+ * done, [6] TMEM released; [8 + 5 j + k], j < 32: per-tile timeline of that CTA (k = 0 epilogue starts waiting,
+ * 1 accumulator ready, 2 epilogue done, 3 first k-block in smem, 4 last MMA issued).  NULL disables. */
+void avec_set_debug_timestamps(void* dev_buf_232_u64);
 
 /* out[n] (+)= alpha * sum_m x[m][n]      — bias gradients (autograd of the bias add in addmm / conv) */
 int avec_colsum(const void* x, int dtype, long long rows, int C, long long ldx, float alpha, float* out, int accumulate,

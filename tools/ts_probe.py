@@ -6,13 +6,15 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from avec_b200 import ops, _lib as L
 
 dev, bf = "cuda", torch.bfloat16
-ts = torch.zeros(8, dtype=torch.int64, device=dev)
+ts = torch.zeros(232, dtype=torch.int64, device=dev)
 lib = L.load()
 names = ["setup", "first k-block", "mainloop issue", "drain->accum", "epilogue", "dealloc"]
 
 
 def run(label, fn):
     fn(); fn()
+    torch.cuda.synchronize()
+    ts.zero_()
     torch.cuda.synchronize()
     lib.avec_set_debug_timestamps(ts.data_ptr())
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -21,6 +23,18 @@ def run(label, fn):
     lib.avec_set_debug_timestamps(0)
     t = ts.cpu().tolist()
     d = [t[i + 1] - t[i] for i in range(6)]
+    if t[8 + 5 * 6]:
+        for j in range(4, 9):
+            b = 8 + 5 * j
+            if not t[b + 2]:
+                break
+            print(f"   tile {j}: kb0 ready +{t[b + 3] - t[b - 5 + 2]} (rel. prev epilogue end), last MMA issued +{t[b + 4] - t[b + 3]}, "
+                  f"epilogue waited {t[b + 1] - t[b]}, epilogue ran {t[b + 2] - t[b + 1]}, period {t[b + 2] - t[b - 5 + 2]}")
+    if t[168]:
+        m = [t[168 + i] - t[168] for i in range(32) if t[168 + i]]
+        q = [t[200 + i] - t[168] for i in range(32) if t[200 + i]]
+        print("   tile 6 MMA thread (cycles rel. first full-wait done; pairs = wait done, issued):", m)
+        print("   tile 6 producer   (same origin; pairs = empty-wait done, TMA issued):", q)
     print(f"{label}: kernel {e0.elapsed_time(e1) * 1000:.1f} us; CTA0 phases (ns): " + ", ".join(f"{n} {v}" for n, v in zip(names, d)) + f"; total {t[6] - t[0]}")
 
 
