@@ -593,7 +593,7 @@ constexpr int STG_BYTES = 4 * STG_WARP * 4;      // 34816 bytes per CTA
 // line of bf16), 4 rows per instruction.  Bias, activation, residual / Swish' operands, fp32 split-K reductions and the
 // BatchNorm column statistics are all applied in that coalesced domain.
 __device__ __forceinline__ void epilogue_warp(const TcParams& p, const EpiParams& ep, const TileInfo& ti, uint32_t lane_addr, float* stg,
-                                              const float* bias_s, float* cstat, int warp, int lane) {
+                                              const float* bias_s, float* stats_dst, int warp, int lane) {
     const int BN = p.BN;
     const int q = lane & 7, rs = lane >> 3;
     for (int c0 = 0; c0 < BN; c0 += 64) {
@@ -687,15 +687,29 @@ __device__ __forceinline__ void epilogue_warp(const TcParams& p, const EpiParams
         }
         __syncwarp();
         if (ep.colstats) {
-            // lanes with equal q hold partial sums of the same 8 columns: fold the 4 row groups, then one shared atomic each
+            // lanes with equal q hold partial sums of the same 8 columns: fold the 4 row groups (every lane ends up with the
+            // totals), then each row group flushes one quarter with a single 128-bit reduction: {sum 0-3, sum 4-7, sq 0-3, sq 4-7}
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 8);  s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 8);
                 s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 16); s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 16);
             }
-            if (rs == 0 && lc < ncol) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) { atomicAdd(&cstat[c0 + lc + j], s1[j]); atomicAdd(&cstat[256 + c0 + lc + j], s2[j]); }
+            if (lc < ncol) {
+                const bool hi = (rs & 1) != 0, sq = rs >= 2;
+                const float r0 = sq ? (hi ? s2[4] : s2[0]) : (hi ? s1[4] : s1[0]);
+                const float r1 = sq ? (hi ? s2[5] : s2[1]) : (hi ? s1[5] : s1[1]);
+                const float r2 = sq ? (hi ? s2[6] : s2[2]) : (hi ? s1[6] : s1[2]);
+                const float r3 = sq ? (hi ? s2[7] : s2[3]) : (hi ? s1[7] : s1[3]);
+                const int col = gc + (hi ? 4 : 0);
+                float* dst = stats_dst + (sq ? p.N : 0) + col;
+                if (col + 4 <= p.N && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(r0), "f"(r1), "f"(r2), "f"(r3) : "memory");
+                } else {
+                    if (col < p.N) atomicAdd(dst, r0);
+                    if (col + 1 < p.N) atomicAdd(dst + 1, r1);
+                    if (col + 2 < p.N) atomicAdd(dst + 2, r2);
+                    if (col + 3 < p.N) atomicAdd(dst + 3, r3);
+                }
             }
         }
     }
@@ -724,8 +738,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(halo_empty + 2);
     RowInfo* rinfo = reinterpret_cast<RowInfo*>(ctrl + 256);
     int* tapofs = reinterpret_cast<int*>(ctrl + 256 + BM * sizeof(RowInfo));
-    float* cstat = reinterpret_cast<float*>(ctrl + 256 + BM * sizeof(RowInfo) + 256 * sizeof(int));  // [2][256]
-    float* bias_s = cstat + 512;                                                                     // [256]
+    float* bias_s = reinterpret_cast<float*>(ctrl + 256 + BM * sizeof(RowInfo) + 256 * sizeof(int));   // [256]
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform by construction (and known to be so by ptxas)
@@ -775,13 +788,19 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
         // ===================== gather producers (when an operand is not TMA-fed), then epilogue =====================
         int it = 0;   // k-blocks pushed through the ring so far
         int j = 0;    // local tile counter
+        int cur_n0 = -1;
+        bool cur_bias_on = false;
         for (int t = blockIdx.x; t < tiles_total; t += gridDim.x, ++j) {
             const TileInfo ti = decode_tile(p, t);
             const int n0 = ti.n0, nkb = ti.nkb;
-            asm volatile("bar.sync 1, 128;" ::: "memory");   // previous tile's epilogue has released bias_s / cstat / rinfo
+            // per-tile shared state (bias slice, conv row decode) is rebuilt only when it changes: persistent CTAs walk the
+            // m tiles of one column block back to back, so most tiles skip both barriers
+            const bool refresh = j == 0 || n0 != cur_n0 || (ti.z == 0) != cur_bias_on;
+            cur_n0 = n0; cur_bias_on = ti.z == 0;
+            if (refresh) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");   // previous tile's epilogue has released bias_s / rinfo
             for (int c = tid; c < 256; c += PRODUCER_THREADS)
                 bias_s[c] = (p.ep.bias && ti.z == 0 && c < BN && n0 + c < p.N) ? p.ep.bias[n0 + c] : 0.0f;
-            if (p.ep.colstats) for (int c = tid; c < 512; c += PRODUCER_THREADS) cstat[c] = 0.0f;
             if (p.a_kind == OP_CONV_FWD || p.a_kind == OP_CONV_DGRAD || p.a_kind == OP_CONV_TAPS) {
                 // per-row site decode for the conv gathers (A operand rows are fixed for the whole tile)
                 RowInfo ri; ri.n = -1; ri.t = ri.h = ri.w = 0;
@@ -800,6 +819,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
                 rinfo[tid] = ri;
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
             if (any_gather) {
                 // cp.async groups: k-block i is published (proxy fence + mbarrier arrive) LAG iterations after it was issued,
                 // so each thread keeps up to LAG+1 k-blocks of loads in flight (stages >= LAG + 1)
@@ -847,17 +867,13 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
             EpiParams ep = p.ep;
             ep.bias = nullptr;   // the bias slice lives in shared memory (bias_s)
             float* stg = (p.stg_dedicated ? reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes) : reinterpret_cast<float*>(smem)) + warp * STG_WARP;
-            epilogue_warp(p, ep, ti, lane_addr, stg, bias_s, cstat, warp, lane);
+            // BatchNorm statistics go to one of AVEC_STATS_REPLICAS copies of the accumulator (by tile index): 32x fewer
+            // same-address L2 reductions
+            float* stats_dst = ep.colstats ? ep.colstats + (size_t)(ti.mtile % AVEC_STATS_REPLICAS) * 2 * p.N : nullptr;
+            epilogue_warp(p, ep, ti, lane_addr, stg, bias_s, stats_dst, warp, lane);
             // all TMEM reads of this buffer are complete: hand it back to the MMA warp
             tc_fence_before();
             mbar_arrive(&accum_empty[buf]);
-            if (ep.colstats) {
-                // one of AVEC_STATS_REPLICAS copies of the accumulator (by tile index): 32x fewer same-address L2 atomics
-                asm volatile("bar.sync 1, 128;" ::: "memory");
-                float* dst = ep.colstats + (size_t)(ti.mtile % AVEC_STATS_REPLICAS) * 2 * p.N;
-                for (int cc = tid; cc < BN; cc += PRODUCER_THREADS)
-                    if (n0 + cc < p.N) { atomicAdd(dst + n0 + cc, cstat[cc]); atomicAdd(dst + p.N + n0 + cc, cstat[256 + cc]); }
-            }
             if (tid == 0 && j == 0) AVEC_TS(5);   // epilogue done
             if (tid == 0) AVEC_TSJ(j, 2);
         }
@@ -1223,7 +1239,7 @@ int avec_gemm_tc(const avec_gemm_args* a, cudaStream_t st) {
     split = cdiv(p.num_kb, p.kb_per_split);
     const int stage_bytes = p.a_rows * 128 + cdiv(p.b_rows * 128, 1024) * 1024;
     const bool any_gather = !is_tma(p.a_kind) || !is_tma(p.b_kind);
-    const size_t ctrl_bytes = 256 + BM * sizeof(RowInfo) + 256 * sizeof(int) + 768 * sizeof(float) + 1024;
+    const size_t ctrl_bytes = 256 + BM * sizeof(RowInfo) + 256 * sizeof(int) + 256 * sizeof(float) + 1024;
     size_t smem;
     if (any_gather) {
         // one tile per CTA; the epilogue staging aliases the drained ring; <= 32 KB stages allow 2 CTAs / SM
