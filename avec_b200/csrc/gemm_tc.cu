@@ -71,6 +71,7 @@ struct TcParams {
     int halo_bytes;             // bytes of one halo tile (multiple of 1024); 0 = no halo mode
     int halo_W2;                // W + 2
     int stg_dedicated;          // 1: epilogue staging has its own shared memory (persistent launches); 0: it aliases the drained ring
+    int epi_fast;               // 0: generic epilogue, 1: fast epilogue with 8-byte aligned rows, 2: 16-byte aligned rows
     int grid_m, grid_n, splits; // tile grid (the launch grid is min(#tiles, resident CTAs): persistent tile loop)
     unsigned long long* dbg_ts; // diagnostics (avec_set_debug_timestamps): CTA (0,0,0) records globaltimer at phase boundaries
     int dbg_mode;               // diagnostics (AVEC_DEBUG_MODE bits): 1 no TMA loads, 2 no MMAs, 4 sleeping epilogue wait, 8 one-lane MMA poll
@@ -587,6 +588,181 @@ constexpr int STG_LD = 68;                       // floats per staged row (64 co
 constexpr int STG_WARP = 32 * STG_LD;            // floats per warp
 constexpr int STG_BYTES = 4 * STG_WARP * 4;      // 34816 bytes per CTA
 
+// ---- explicit shared-space accesses for the epilogue staging (the staging pointer is derived from a runtime select of two
+// bases, so plain C++ accesses compile to generic LD.E / ST.E with their longer latency)
+__device__ __forceinline__ void sts128(uint32_t a, float x, float y, float z, float w) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+    float4 r;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(a) : "memory");
+    return r;
+}
+// 64 accumulator columns of this lane's row with ONE wait (two x32 loads in flight)
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
+    uint32_t r[64];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%64];\n\t"
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%65];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]),
+          "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]),
+          "=r"(r[46]), "=r"(r[47]), "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]),
+          "=r"(r[55]), "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+        : "r"(taddr), "r"(taddr + 32u)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
+}
+// 8 consecutive bf16 (aligned to 16 bytes when AL16, else to 8 bytes) <-> packed words
+template <bool AL16>
+__device__ __forceinline__ uint4 ldg_bf16x8(const bf16* q) {
+    if (AL16) return __ldg(reinterpret_cast<const uint4*>(q));
+    const uint2 a = __ldg(reinterpret_cast<const uint2*>(q)), b = __ldg(reinterpret_cast<const uint2*>(q) + 1);
+    return make_uint4(a.x, a.y, b.x, b.y);
+}
+template <bool AL16>
+__device__ __forceinline__ void stg_bf16x8(bf16* q, const float (&v)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]); w[i] = *reinterpret_cast<uint32_t*>(&t); }
+    if (AL16) *reinterpret_cast<uint4*>(q) = make_uint4(w[0], w[1], w[2], w[3]);
+    else { reinterpret_cast<uint2*>(q)[0] = make_uint2(w[0], w[1]); reinterpret_cast<uint2*>(q)[1] = make_uint2(w[2], w[3]); }
+}
+__device__ __forceinline__ void unpack_bf16x8(const uint4& t, float (&v)[8]) {
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u); }
+}
+
+// Fast epilogue of one 128 x BN tile for one warp: the common launch-constant cases (bf16 output / auxiliary operands with
+// rows aligned to 8 or 16 bytes, N % 8 == 0, fp32 reductions for ACCUM) compiled per epilogue kind, so the transposed-domain
+// loop is branch-free: four row passes at a time with all their shared-memory and auxiliary loads issued before the first
+// use, bias kept in registers (a lane owns the same 8 columns in every pass).
+template <int KIND, bool STATS, bool AL16>
+__device__ __forceinline__ void epilogue_fast(const TcParams& p, const EpiParams& ep, const TileInfo& ti, uint32_t lane_addr, uint32_t stg_s,
+                                              uint32_t bias_sa, float* stats_dst, int warp, int lane) {
+    const int BN = p.BN;
+    const int q = lane & 7, rs = lane >> 3;
+    const int lc = q * 8;
+    const float alpha = ep.alpha;
+    const int rows_left = ti.rows_valid - warp * 32;   // valid rows of this warp's quarter (may be <= 0 or >= 32)
+    for (int c0 = 0; c0 < BN; c0 += 64) {
+        const int ncol = min(64, BN - c0);   // multiple of 16
+        const int gc = ti.n0 + c0 + lc;
+        const bool col_ok = lc < ncol && gc < p.N;
+        // ---- auxiliary operand of the first four passes: does not depend on the accumulator, so it is requested first
+        uint4 xa[4];
+        constexpr bool HAS_AUX = KIND == AVEC_EPI_RESIDUAL || KIND == AVEC_EPI_DSWISH || KIND == AVEC_EPI_RELU;
+        const bool aux_on = HAS_AUX && ep.aux != nullptr;
+        const bf16* auxp = reinterpret_cast<const bf16*>(ep.aux);
+        if (HAS_AUX) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int rr = u * 4 + rs;
+                xa[u] = make_uint4(0u, 0u, 0u, 0u);
+                if (aux_on && col_ok && rr < rows_left) xa[u] = ldg_bf16x8<AL16>(auxp + (size_t)(ti.row_base + warp * 32 + rr) * ep.ldaux + gc);
+            }
+        }
+        // ---- row domain: TMEM -> registers -> staging
+        if (ncol == 64) {
+            float v[64];
+            tmem_ld64(lane_addr + (uint32_t)c0, v);
+#pragma unroll
+            for (int j = 0; j < 64; j += 4) sts128(stg_s + (uint32_t)(lane * STG_LD + j) * 4u, v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+            for (int cc = 0; cc < ncol; cc += 16) {
+                float v[16];
+                tmem_ld16(lane_addr + (uint32_t)(c0 + cc), v);
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) sts128(stg_s + (uint32_t)(lane * STG_LD + cc + j) * 4u, v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+        }
+        uint4 xb[4];
+        if (HAS_AUX) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int rr = (4 + u) * 4 + rs;
+                xb[u] = make_uint4(0u, 0u, 0u, 0u);
+                if (aux_on && col_ok && rr < rows_left) xb[u] = ldg_bf16x8<AL16>(auxp + (size_t)(ti.row_base + warp * 32 + rr) * ep.ldaux + gc);
+            }
+        }
+        __syncwarp();
+        // ---- transposed domain
+        float b[8];
+        {
+            const float4 b0 = lds128(bias_sa + (uint32_t)(c0 + (col_ok ? lc : 0)) * 4u), b1 = lds128(bias_sa + (uint32_t)(c0 + (col_ok ? lc : 0) + 4) * 4u);
+            b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+        }
+        float s1[8], s2[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s1[j] = 0.0f; s2[j] = 0.0f; }
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            float4 t[8];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int rr = (g * 4 + u) * 4 + rs;
+                const uint32_t sa = stg_s + (uint32_t)(rr * STG_LD + (col_ok ? lc : 0)) * 4u;
+                t[2 * u] = lds128(sa); t[2 * u + 1] = lds128(sa + 16u);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int rr = (g * 4 + u) * 4 + rs;
+                if (!(col_ok && rr < rows_left)) continue;
+                const size_t row = (size_t)(ti.row_base + warp * 32 + rr);
+                float a[8] = {t[2 * u].x + b[0], t[2 * u].y + b[1], t[2 * u].z + b[2], t[2 * u].w + b[3],
+                              t[2 * u + 1].x + b[4], t[2 * u + 1].y + b[5], t[2 * u + 1].z + b[6], t[2 * u + 1].w + b[7]};
+                const size_t oi = row * ep.ldo + gc;
+                if (KIND == AVEC_EPI_ACCUM) {
+                    float* dst = reinterpret_cast<float*>(ep.out) + oi;
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(alpha * a[0]), "f"(alpha * a[1]), "f"(alpha * a[2]), "f"(alpha * a[3]) : "memory");
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(alpha * a[4]), "f"(alpha * a[5]), "f"(alpha * a[6]), "f"(alpha * a[7]) : "memory");
+                } else {
+                    float o[8], x[8];
+                    if (HAS_AUX) unpack_bf16x8(g == 0 ? xa[u] : xb[u], x);
+                    if (KIND == AVEC_EPI_SWISH && ep.out2) stg_bf16x8<AL16>(reinterpret_cast<bf16*>(ep.out2) + row * ep.ldo2 + gc, a);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (KIND == AVEC_EPI_LINEAR) o[j] = alpha * a[j];
+                        else if (KIND == AVEC_EPI_SWISH) o[j] = swishf_(a[j]);
+                        else if (KIND == AVEC_EPI_RESIDUAL) o[j] = x[j] + alpha * a[j];
+                        else if (KIND == AVEC_EPI_DSWISH) o[j] = alpha * a[j] * dswishf_(x[j]);
+                        else o[j] = fmaxf(alpha * a[j] + x[j], 0.0f);
+                    }
+                    stg_bf16x8<AL16>(reinterpret_cast<bf16*>(ep.out) + oi, o);
+                }
+                if (STATS) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { s1[j] += a[j]; s2[j] += a[j] * a[j]; }
+                }
+            }
+        }
+        __syncwarp();
+        if (STATS) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 8);  s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 8);
+                s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], 16); s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], 16);
+            }
+            if (col_ok) {
+                const bool hi = (rs & 1) != 0, sq = rs >= 2;
+                const float r0 = sq ? (hi ? s2[4] : s2[0]) : (hi ? s1[4] : s1[0]);
+                const float r1 = sq ? (hi ? s2[5] : s2[1]) : (hi ? s1[5] : s1[1]);
+                const float r2 = sq ? (hi ? s2[6] : s2[2]) : (hi ? s1[6] : s1[2]);
+                const float r3 = sq ? (hi ? s2[7] : s2[3]) : (hi ? s1[7] : s1[3]);
+                float* dst = stats_dst + (sq ? p.N : 0) + gc + (hi ? 4 : 0);   // 16-byte aligned: N % 8 == 0, gc % 8 == 0
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(r0), "f"(r1), "f"(r2), "f"(r3) : "memory");
+            }
+        }
+    }
+}
+
 // Epilogue of one 128 x BN tile for one warp (32 accumulator rows).  The accumulator comes out of TMEM one ROW per lane
 // (tcgen05.ld 32x32b); writing global memory in that shape would touch 32 different cache lines per instruction, so the
 // 64-column slab is staged in shared memory and re-read TRANSPOSED: 8 lanes cover one row's 64 columns (one full 128-byte
@@ -712,6 +888,22 @@ __device__ __forceinline__ void epilogue_warp(const TcParams& p, const EpiParams
                 }
             }
         }
+    }
+}
+
+template <bool AL16>
+__device__ __forceinline__ void epilogue_fast_dispatch(const TcParams& p, const EpiParams& ep, const TileInfo& ti, uint32_t lane_addr, uint32_t stg_s,
+                                                       uint32_t bias_sa, float* stats_dst, int warp, int lane) {
+    switch (ep.kind) {
+    case AVEC_EPI_LINEAR:
+        if (ep.colstats) epilogue_fast<AVEC_EPI_LINEAR, true, AL16>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane);
+        else epilogue_fast<AVEC_EPI_LINEAR, false, AL16>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane);
+        break;
+    case AVEC_EPI_SWISH: epilogue_fast<AVEC_EPI_SWISH, false, AL16>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane); break;
+    case AVEC_EPI_RESIDUAL: epilogue_fast<AVEC_EPI_RESIDUAL, false, AL16>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane); break;
+    case AVEC_EPI_DSWISH: epilogue_fast<AVEC_EPI_DSWISH, false, AL16>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane); break;
+    case AVEC_EPI_ACCUM: epilogue_fast<AVEC_EPI_ACCUM, false, AL16>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane); break;
+    default: epilogue_fast<AVEC_EPI_RELU, false, AL16>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane); break;
     }
 }
 
@@ -870,7 +1062,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
             // BatchNorm statistics go to one of AVEC_STATS_REPLICAS copies of the accumulator (by tile index): 32x fewer
             // same-address L2 reductions
             float* stats_dst = ep.colstats ? ep.colstats + (size_t)(ti.mtile % AVEC_STATS_REPLICAS) * 2 * p.N : nullptr;
-            epilogue_warp(p, ep, ti, lane_addr, stg, bias_s, stats_dst, warp, lane);
+            if (p.epi_fast == 2) epilogue_fast_dispatch<true>(p, ep, ti, lane_addr, smem_u32(stg), smem_u32(bias_s), stats_dst, warp, lane);
+            else if (p.epi_fast == 1) epilogue_fast_dispatch<false>(p, ep, ti, lane_addr, smem_u32(stg), smem_u32(bias_s), stats_dst, warp, lane);
+            else epilogue_warp(p, ep, ti, lane_addr, stg, bias_s, stats_dst, warp, lane);
             // all TMEM reads of this buffer are complete: hand it back to the MMA warp
             tc_fence_before();
             mbar_arrive(&accum_empty[buf]);
@@ -1068,6 +1262,16 @@ bool conv_tma_geom_ok(const ConvGeom& g, bool dgrad) {
     return base && (!dgrad || g.sh == 1);
 }
 
+int num_sms_cached() {
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
+    }
+    return num_sms;
+}
+
 }  // namespace
 
 static int g_tma_enabled = 1;
@@ -1241,6 +1445,8 @@ int avec_gemm_tc(const avec_gemm_args* a, cudaStream_t st) {
     const bool any_gather = !is_tma(p.a_kind) || !is_tma(p.b_kind);
     const size_t ctrl_bytes = 256 + BM * sizeof(RowInfo) + 256 * sizeof(int) + 256 * sizeof(float) + 1024;
     size_t smem;
+    int ctas_per_sm = 1;
+    const long long tiles_for_cta2 = (long long)grid_m * cdiv(a->N, p.BN) * split;
     if (any_gather) {
         // one tile per CTA; the epilogue staging aliases the drained ring; <= 32 KB stages allow 2 CTAs / SM
         p.stages = stage_bytes <= 32 * 1024 ? 3 : 4;   // >= LAG + 1 = 3 (cp.async run-ahead)
@@ -1257,24 +1463,50 @@ int avec_gemm_tc(const avec_gemm_args* a, cudaStream_t st) {
         while (p.stages > 2 && halo_total + (size_t)p.stages * stage_bytes + STG_BYTES + ctrl_bytes > 227 * 1024) --p.stages;
         smem = halo_total + (size_t)p.stages * stage_bytes + STG_BYTES + ctrl_bytes;
         if (smem > 227 * 1024) return AVEC_ERR_UNSUPPORTED;
+        // narrow tiles (BN <= 64: a k-block is only 128 tensor-pipe cycles, the epilogue and the per-k-block handshakes are
+        // latency bound): two co-resident CTAs per SM interleave their MMA streams and run two epilogues at a time
+        static int cta2 = -1;
+        if (cta2 < 0) { const char* e = getenv("AVEC_CTA2"); cta2 = e ? atoi(e) : 1; }
+        if (cta2 && !halo && p.BN <= 64) {
+            int st2 = 6;
+            while (st2 > 3 && (size_t)st2 * stage_bytes + STG_BYTES + ctrl_bytes > 112 * 1024) --st2;
+            if ((size_t)st2 * stage_bytes + STG_BYTES + ctrl_bytes <= 112 * 1024 && tiles_for_cta2 > num_sms_cached()) {
+                p.stages = st2; ctas_per_sm = 2;
+                smem = (size_t)p.stages * stage_bytes + STG_BYTES + ctrl_bytes;
+            }
+        }
     }
     static bool attr_set = false;
     if (!attr_set) {
         if (cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return AVEC_ERR_LAUNCH;
         attr_set = true;
     }
+    // ---- fast epilogue: launch-constant eligibility (see epilogue_fast)
+    {
+        static int fast_on = -1;
+        if (fast_on < 0) { const char* e = getenv("AVEC_EPI_FAST"); fast_on = e ? atoi(e) : 1; }
+        const EpiParams& ep = p.ep;
+        int al = 16;
+        bool ok = fast_on && !halo && a->N % 8 == 0 && !p.out_transposed;
+        if (ep.kind == AVEC_EPI_ACCUM) {
+            ok = ok && ep.out_dtype == AVEC_F32 && (reinterpret_cast<uintptr_t>(ep.out) % 16) == 0 && ep.ldo % 4 == 0 && !ep.colstats;
+        } else {
+            ok = ok && ep.out_dtype == AVEC_BF16 && ep.kind >= AVEC_EPI_LINEAR && ep.kind <= AVEC_EPI_RELU;
+            al = std::min(al, ptr_align(ep.out, ep.ldo));
+            if (ep.aux) { ok = ok && ep.aux_dtype == AVEC_BF16; al = std::min(al, ptr_align(ep.aux, ep.ldaux)); }
+            if (ep.out2) { ok = ok && ep.out2_dtype == AVEC_BF16 && ep.kind == AVEC_EPI_SWISH; al = std::min(al, ptr_align(ep.out2, ep.ldo2)); }
+            if (ep.colstats) ok = ok && ep.kind == AVEC_EPI_LINEAR && (reinterpret_cast<uintptr_t>(ep.colstats) % 16) == 0;
+            if ((ep.kind == AVEC_EPI_RESIDUAL || ep.kind == AVEC_EPI_DSWISH) && !ep.aux) ok = false;
+        }
+        p.epi_fast = ok && al >= 8 ? (al >= 16 ? 2 : 1) : 0;
+    }
     p.grid_m = grid_m; p.grid_n = cdiv(a->N, p.BN); p.splits = split;
     const long long tiles = (long long)p.grid_m * p.grid_n * p.splits;
     if (tiles > 0x7fffffffLL) return AVEC_ERR_INVALID;
-    static int num_sms = 0;
-    if (num_sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
-    }
+    const int num_sms = num_sms_cached();
     // persistent launch when both operands are TMA-fed (the gather producers double as epilogue warps, so gather kinds keep
     // one tile per CTA); two CTAs per SM when shared memory and TMEM (2 x BN columns each) allow it
-    long long ctas = any_gather ? tiles : std::min<long long>(tiles, (long long)num_sms);
+    long long ctas = any_gather ? tiles : std::min<long long>(tiles, (long long)num_sms * ctas_per_sm);
     gemm_tc_kernel<<<(unsigned)ctas, TC_THREADS, smem, st>>>(p, mapA, mapB);
     AVEC_LAUNCH_CHECK();
     return AVEC_OK;
