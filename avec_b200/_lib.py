@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libavec_b200.so")
+# AVEC_LIB selects another build of the same sources (e.g. the -DAVEC_TIMELINE diagnostics build used by tools/ts_probe.py)
+LIB_PATH = os.environ.get("AVEC_LIB") or os.path.join(_HERE, "libavec_b200.so")
 
 F32, BF16 = 0, 1
 GEMM_PLAIN, GEMM_CONV_FWD, GEMM_CONV_DGRAD, GEMM_CONV_WGRAD = 0, 1, 2, 3

@@ -113,6 +113,15 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
     while (!mbar_try(bar, parity)) __nanosleep(100);
 }
+__device__ __forceinline__ void mbar_wait_addr(uint32_t bar_saddr, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP_A:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE_A;\n\t"
+        "bra WAIT_LOOP_A;\n\t"
+        "WAIT_DONE_A:\n\t}" ::"r"(bar_saddr), "r"(parity) : "memory");
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -127,6 +136,9 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_commit_addr(uint32_t bar_saddr) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_saddr) : "memory");
 }
 __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -163,6 +175,10 @@ __device__ __forceinline__ unsigned long long gtime() {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
 }
+// Timeline / ablation diagnostics are compiled only with -DAVEC_TIMELINE (tools/ts_probe.py needs such a build): in the
+// production build the per-k-block loops of the single-thread MMA issuer and TMA producer carry no trace of them (those
+// loops are instruction-latency bound: every scalar instruction per k-block costs ~4-5 cycles of issue time).
+#ifdef AVEC_TIMELINE
 #define AVEC_TS(slot) do { if (p.dbg_ts && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) p.dbg_ts[slot] = gtime(); } while (0)
 // per-tile timeline of CTA 0 (tiles j < 32): slots 8 + 5 j + {0 epilogue starts waiting, 1 accumulator ready, 2 epilogue done,
 // 3 first k-block in shared memory, 4 last MMA issued}; the debug buffer holds 8 + 5 * 32 = 168 values
@@ -170,6 +186,13 @@ __device__ __forceinline__ unsigned long long gtime() {
 // [200 + 2 i + {0 empty-wait done, 1 TMA issued}] (producer thread), i < 16; buffer holds 232 values
 #define AVEC_TSK(j, i, base, k) do { if (p.dbg_ts && blockIdx.x == 0 && (j) == 6 && (i) < 16) p.dbg_ts[(base) + 2 * (i) + (k)] = (unsigned long long)clock64(); } while (0)
 #define AVEC_TSJ(j, k) do { if (p.dbg_ts && blockIdx.x == 0 && (j) < 32) p.dbg_ts[8 + 5 * (j) + (k)] = gtime(); } while (0)
+#define AVEC_DBG_MODE(bit) ((p.dbg_mode & (bit)) != 0)
+#else
+#define AVEC_TS(slot) do { } while (0)
+#define AVEC_TSK(j, i, base, k) do { } while (0)
+#define AVEC_TSJ(j, k) do { } while (0)
+#define AVEC_DBG_MODE(bit) false
+#endif
 
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -1050,7 +1073,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
                 for (int o = 0; o < nbytes; o += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(a0 + o));
             }
             if (tid == 0) AVEC_TSJ(j, 0);
-            if (p.dbg_mode & 4) mbar_wait_sleep(&accum_full[buf], (uint32_t)((j >> 1) & 1));
+            if (AVEC_DBG_MODE(4)) mbar_wait_sleep(&accum_full[buf], (uint32_t)((j >> 1) & 1));
             else mbar_wait(&accum_full[buf], (uint32_t)((j >> 1) & 1));
             tc_fence_after();
             if (tid == 0 && j == 0) AVEC_TS(4);   // accumulator complete, epilogue starts
@@ -1099,36 +1122,32 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
                     __syncwarp();
                 }
                 int kh = 0, kw = 0, cb = 0;   // filter tap / channel block of the current k-block (conv K-major A)
+                const int a_simple = (a_tma && !halo_mode) ? (p.a_kind == OP_TMA_K ? 1 : (p.a_kind == OP_TMA_CONV_K ? 2 : 3)) : 0;
+                const int b_simple = b_tma ? (p.b_kind == OP_TMA_K ? 1 : 3) : 0;
+                const int sgn = p.ct_dgrad ? -1 : 1;
+                const int th0s = th0 * p.ct_s;
+                int kcoord = ti.kb_begin * BKE;
                 for (int i = 0; i < ti.nkb; ++i) {
                     mbar_wait(&empty_bar[st], ph ^ 1u);
                     if (elect_one()) {
                         const uint32_t a_dst = ring0 + (uint32_t)st * (uint32_t)stage_bytes;
                         const uint32_t b_dst = a_dst + (uint32_t)a_bytes;
                         uint64_t* bar = &full_bar[st];
-                        const int kb = ti.kb_begin + i;
                         AVEC_TSK(j, i, 200, 0);
-                        if (p.dbg_mode & 1) {
+                        if (AVEC_DBG_MODE(1)) {
                             mbar_arrive(bar);
                         } else {
                             mbar_expect_tx(bar, tx);
-                            if (a_tma && !halo_mode) {
-                                if (p.a_kind == OP_TMA_K) {
-                                    tma_load_2d(a_dst, &mapA, bar, kb * BKE, ti.m0 - p.dbg_rowofs);
-                                } else if (p.a_kind == OP_TMA_CONV_K) {
-                                    const int dh = p.ct_dgrad ? p.g.ph - kh : kh - p.g.ph, dw = p.ct_dgrad ? p.g.pw - kw : kw - p.g.pw;
-                                    tma_load_4d(a_dst, &mapA, bar, cb * BKE, dw, th0 * p.ct_s + dh, tn0);
-                                } else {
-                                    tma_fill(p, p.a_kind, &mapA, smem + (size_t)st * stage_bytes, bar, p.a_rows, p.a_group_stride, ti.m0, kb, ti.mtile, true);
-                                }
-                            }
-                            if (b_tma) {
-                                if (p.b_kind == OP_TMA_K) tma_load_2d(b_dst, &mapB, bar, kb * BKE, ti.n0);
-                                else tma_fill(p, p.b_kind, &mapB, smem + (size_t)st * stage_bytes + a_bytes, bar, p.b_rows, p.b_group_stride, ti.n0, kb, ti.mtile, false);
-                            }
+                            if (a_simple == 1) tma_load_2d(a_dst, &mapA, bar, kcoord, ti.m0 - p.dbg_rowofs);
+                            else if (a_simple == 2) tma_load_4d(a_dst, &mapA, bar, cb * BKE, sgn * (kw - p.g.pw), th0s + sgn * (kh - p.g.ph), tn0);
+                            else if (a_simple == 3) tma_fill(p, p.a_kind, &mapA, smem + (size_t)st * stage_bytes, bar, p.a_rows, p.a_group_stride, ti.m0, ti.kb_begin + i, ti.mtile, true);
+                            if (b_simple == 1) tma_load_2d(b_dst, &mapB, bar, kcoord, ti.n0);
+                            else if (b_simple == 3) tma_fill(p, p.b_kind, &mapB, smem + (size_t)st * stage_bytes + a_bytes, bar, p.b_rows, p.b_group_stride, ti.n0, ti.kb_begin + i, ti.mtile, false);
                         }
                         AVEC_TSK(j, i, 200, 1);
                     }
                     __syncwarp();
+                    kcoord += BKE;
                     if (++cb == p.cpb) { cb = 0; if (++kw == p.g.KW) { kw = 0; ++kh; } }
                     if (++st == p.stages) { st = 0; ph ^= 1u; }
                 }
@@ -1136,18 +1155,25 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
         }
     } else {
         // ===================== MMA issuer =====================
+        // One elected thread issues everything; per k-block it executes a few dozen scalar instructions (running stage
+        // address / barrier / phase, 32-bit descriptor arithmetic: the 14-bit address field never carries out of the low
+        // word), because at 64-column tiles a k-block is only 128 tensor-pipe cycles.
         const int a_mn = is_mn(p.a_kind) ? 1 : 0;
         const int b_mn = is_mn(p.b_kind) ? 1 : 0;
         const uint32_t idesc = make_idesc(BN, a_mn, b_mn);
         const bool halo_mode = p.a_kind == OP_TMA_CONV_HALO;
-        // descriptors: constant high part + (address >> 4); per K-step the address advances 32 B (K-major) / 2048 B (MN-major)
         const uint64_t a_desc0 = a_mn ? make_smem_desc(0, p.a_group_stride, 1024) : make_smem_desc(0, 16, 1024);
         const uint64_t b_desc0 = b_mn ? make_smem_desc(0, p.b_group_stride, 1024) : make_smem_desc(0, 16, 1024);
+        const uint32_t a_hi = (uint32_t)(a_desc0 >> 32), b_hi = (uint32_t)(b_desc0 >> 32);
+        const uint32_t a_lo0 = (uint32_t)a_desc0, b_lo0 = (uint32_t)b_desc0;
         const uint32_t a_kstep = a_mn ? (2048u >> 4) : (32u >> 4), b_kstep = b_mn ? (2048u >> 4) : (32u >> 4);
         const uint32_t ring0 = smem_u32(smem) >> 4, stage_step = (uint32_t)stage_bytes >> 4, a_bytes16 = (uint32_t)a_bytes >> 4;
         const uint32_t rowofs16 = ((uint32_t)p.dbg_rowofs * 128u) >> 4;
+        const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+        const int ksteps = p.ksteps;
         int j = 0, st = 0;
         uint32_t ph = 0;
+        uint32_t stage16 = ring0;
         for (int t = blockIdx.x; t < tiles_total; t += gridDim.x, ++j) {
             const TileInfo ti = decode_tile(p, t);
             const int buf = j & 1;
@@ -1156,33 +1182,41 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
             const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BN);
             if (halo_mode) { mbar_wait(&halo_full[buf], (uint32_t)((j >> 1) & 1)); tc_fence_after(); }
             int kh = 0, kw = 0, cb = 0;
-            for (int i = 0; i < ti.nkb; ++i) {
-                mbar_wait(&full_bar[st], ph);
+            const int nkb = ti.nkb;
+            for (int i = 0; i < nkb; ++i) {
+                mbar_wait_addr(full0 + 8u * (uint32_t)st, ph);
                 tc_fence_after();
                 const bool leader = elect_one();
-                if (leader && (p.dbg_mode & 2)) {
+                if (leader && AVEC_DBG_MODE(2)) {
                     if (i == 0) AVEC_TSJ(j, 3);
                     mbar_arrive(&empty_bar[st]);
-                    if (i == ti.nkb - 1) { mbar_arrive(&accum_full[buf]); AVEC_TSJ(j, 4); }
+                    if (i == nkb - 1) { mbar_arrive(&accum_full[buf]); AVEC_TSJ(j, 4); }
                 } else if (leader) {
                     AVEC_TSK(j, i, 168, 0);
                     if (i == 0 && j == 0) AVEC_TS(2);   // first k-block landed in shared memory
                     if (i == 0) AVEC_TSJ(j, 3);
-                    const uint32_t stage16 = ring0 + (uint32_t)st * stage_step;
-                    uint32_t a16 = stage16 + rowofs16;
+                    uint32_t alo = a_lo0 + stage16 + rowofs16;
                     if (halo_mode) {
                         // tap (kh, kw) of 64-channel block cb reads the resident halo tile from row kh*(W+2)+kw on
                         // (dgrad: the mirrored tap); a 128-byte row offset keeps the 128B-swizzle phase consistent
                         const int th = p.ct_dgrad ? p.g.KH - 1 - kh : kh, tw = p.ct_dgrad ? p.g.KW - 1 - kw : kw;
-                        a16 = (smem_u32(halo + (size_t)(buf * p.cpb + cb) * p.halo_bytes) + (uint32_t)(th * p.halo_W2 + tw) * 128u) >> 4;
+                        alo = a_lo0 + ((smem_u32(halo + (size_t)(buf * p.cpb + cb) * p.halo_bytes) + (uint32_t)(th * p.halo_W2 + tw) * 128u) >> 4);
                     }
-                    uint64_t adesc = a_desc0 + a16, bdesc = b_desc0 + stage16 + a_bytes16;
-                    for (int k = 0; k < p.ksteps; ++k) {
-                        umma_f16(d_tmem, adesc, bdesc, idesc, (i > 0 || k > 0) ? 1u : 0u);
-                        adesc += a_kstep; bdesc += b_kstep;
+                    uint32_t blo = b_lo0 + stage16 + a_bytes16;
+                    if (ksteps == 4) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            umma_f16(d_tmem, ((uint64_t)a_hi << 32) | alo, ((uint64_t)b_hi << 32) | blo, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                            alo += a_kstep; blo += b_kstep;
+                        }
+                    } else {
+                        for (int k = 0; k < ksteps; ++k) {
+                            umma_f16(d_tmem, ((uint64_t)a_hi << 32) | alo, ((uint64_t)b_hi << 32) | blo, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                            alo += a_kstep; blo += b_kstep;
+                        }
                     }
-                    umma_commit(&empty_bar[st]);
-                    if (i == ti.nkb - 1) {   // last MMA of the tile issued
+                    umma_commit_addr(empty0 + 8u * (uint32_t)st);
+                    if (i == nkb - 1) {   // last MMA of the tile issued
                         umma_commit(&accum_full[buf]);
                         if (halo_mode) umma_commit(&halo_empty[buf]);
                         if (j == 0) AVEC_TS(3);
@@ -1191,8 +1225,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
                     AVEC_TSK(j, i, 168, 1);
                 }
                 __syncwarp();
-                if (++cb == p.cpb) { cb = 0; if (++kw == p.g.KW) { kw = 0; ++kh; } }
-                if (++st == p.stages) { st = 0; ph ^= 1u; }
+                if (halo_mode) { if (++cb == p.cpb) { cb = 0; if (++kw == p.g.KW) { kw = 0; ++kh; } } }
+                stage16 += stage_step;
+                if (++st == p.stages) { st = 0; ph ^= 1u; stage16 = ring0; }
             }
         }
         tc_fence_before();
