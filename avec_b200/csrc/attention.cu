@@ -286,10 +286,19 @@ size_t bwd_smem(int T, int d) { return ((size_t)4 * T * (d + 1) + ATT_WARPS * T)
 
 }  // namespace
 
+// tensor-core kernels (attention_mma.cu); AVEC_ERR_UNSUPPORTED = shape outside their envelope
+int avec_attn_mma_fwd(const void* qkv, const void* e, const int* klen, int qlen, void* o, float* probs, int B, int T, int H, int d, cudaStream_t st);
+int avec_attn_mma_bwd(const void* d_o, const void* qkv, const void* e, const float* probs, void* dqkv, float* de, int B, int T, int H, int d,
+                      cudaStream_t st);
+
 extern "C" int avec_relpos_attn_fwd(const void* qkv, const void* e, const int* klen, int qlen, void* o, float* probs, int B,
                                     int T, int H, int d, int G, int Tf, const float* u, const float* v, int dtype, avec_stream_t stream) {
     AVEC_CHECK_ARG(qkv && e && o && probs && B > 0 && T > 0 && H > 0 && d > 0 && G >= 1 && (H * d) % G == 0);
     AVEC_CHECK_ARG(T <= 32 * MAX_KPL && d <= 32 * MAX_CPL && Tf > (T - 1) * G && Tf <= T * G);
+    if (dtype == AVEC_BF16 && G == 1 && !u && !v && Tf == T) {
+        const int rc = avec_attn_mma_fwd(qkv, e, klen, qlen, o, probs, B, T, H, d, as_stream(stream));
+        if (rc != AVEC_ERR_UNSUPPORTED) return rc;
+    }
     const int D1 = H * d / G;
     size_t smem = fwd_smem(T, d);
     if (smem > 227 * 1024) return AVEC_ERR_UNSUPPORTED;
@@ -307,6 +316,10 @@ extern "C" int avec_relpos_attn_bwd(const void* d_o, const void* qkv, const void
                                     float* du, float* dv, int dtype, avec_stream_t stream) {
     AVEC_CHECK_ARG(d_o && qkv && e && probs && ds_ws && dqkv && de && B > 0 && T > 0 && G >= 1 && (H * d) % G == 0);
     AVEC_CHECK_ARG(T <= 32 * MAX_KPL && d <= 32 * MAX_CPL && Tf > (T - 1) * G && Tf <= T * G);
+    if (dtype == AVEC_BF16 && G == 1 && !u && !v && !du && !dv && Tf == T) {
+        const int rc = avec_attn_mma_bwd(d_o, qkv, e, probs, dqkv, de, B, T, H, d, as_stream(stream));
+        if (rc != AVEC_ERR_UNSUPPORTED) return rc;
+    }
     const int D1 = H * d / G;
     size_t smem = bwd_smem(T, d);
     if (smem > 227 * 1024) return AVEC_ERR_UNSUPPORTED;

@@ -140,6 +140,45 @@ def test_relpos_attention_core(B, T, H, d, ragged, qlen_short):
     check_close("de", de, e.grad, RT, 1e-3)
 
 
+@pytest.mark.parametrize("B,T,H,d,ragged,qlen_short", [(3, 7, 4, 45, True, True), (2, 17, 4, 64, True, False), (2, 51, 4, 90, False, False),
+                                                      (2, 101, 4, 64, True, False), (1, 67, 4, 45, True, True), (2, 100, 4, 64, False, False),
+                                                      (2, 128, 4, 64, True, False), (2, 112, 4, 48, False, True)])
+def test_relpos_attention_core_bf16_tensor_core(B, T, H, d, ragged, qlen_short):
+    """bf16 production path (mma.sync kernels of csrc/attention_mma.cu; T = 128 backward falls back to the SIMT kernel) against
+    torch fp32 on the same bf16-rounded inputs.  Probabilities only see fp32 arithmetic on exact products (atol 2e-5); outputs
+    and gradients carry the bf16 rounding of P / dS / results (norm-wise 1e-2, element-wise 3e-2 of the tensor's absmax)."""
+    from common import rel_err
+    D = H * d
+    bf = torch.bfloat16
+    qkv16 = _r("qkv", (B * T, 3 * D), 0.5).to(bf)
+    e16 = _r("e", (2 * T - 1, D), 0.5).to(bf)
+    qkv, e = qkv16.float().requires_grad_(True), e16.float().requires_grad_(True)
+    klen = torch.tensor([T] + [max(1, T - 2 - i) for i in range(B - 1)], device=DEV, dtype=torch.int32) if ragged else None
+    qlen = T - 1 if qlen_short else T
+    q, k, v = [t.view(B, T, H, d).transpose(1, 2) for t in qkv.view(B, T, 3, D).unbind(2)]
+    eh = e.view(2 * T - 1, H, d).transpose(0, 1)
+    idx = (T - 1) + torch.arange(T, device=DEV)[None, :] - torch.arange(T, device=DEV)[:, None]
+    s = (q @ k.transpose(2, 3) + (q @ eh.transpose(1, 2)).gather(3, idx.expand(B, H, T, T))) / d ** 0.5
+    keep = torch.ones(B, 1, T, T, device=DEV)
+    if klen is not None:
+        keep = keep * (torch.arange(T, device=DEV)[None, None, None, :] < klen[:, None, None, None]).float()
+    keep = keep * (torch.arange(T, device=DEV)[None, None, :, None] < qlen).float()
+    s = s + (1 - keep) * -1e9
+    pr = s.softmax(-1)
+    o_ref = (pr @ v).transpose(1, 2).reshape(B * T, D)
+    o, probs = ops.relpos_attn_fwd(qkv16, e16, klen, qlen, B, T, H, d)
+    check_close("probs", probs, pr, 1e-3, 2e-5)
+    assert rel_err(o, o_ref) < 1e-2
+    check_close("o", o, o_ref, 0.0, 3e-2 * float(o_ref.abs().max()))
+    do16 = _r("do", (B * T, D)).to(bf)
+    (o_ref * do16.float()).sum().backward()
+    dqkv, de, _, _ = ops.relpos_attn_bwd(do16, qkv16, e16, probs, B, T, H, d)
+    assert rel_err(dqkv, qkv.grad) < 1e-2, rel_err(dqkv, qkv.grad)
+    assert rel_err(de, e.grad) < 1e-2, rel_err(de, e.grad)
+    check_close("dqkv", dqkv, qkv.grad, 0.0, 3e-2 * float(qkv.grad.abs().max()))
+    check_close("de", de, e.grad, 0.0, 3e-2 * float(e.grad.abs().max()))
+
+
 def test_stft_mel_log_matches_reference_fixture_and_restatement():
     fix = load_golden("audio_logmel.pt")
     wave = seeded.randn("wave", (3, 4000), 1, 0.1)
