@@ -10,6 +10,9 @@ namespace {
 constexpr int DW_TO = 8;     // output frames per CTA (short tiles: these launches are latency-, not bandwidth-bound)
 constexpr int DW_CH = 128;   // channels per CTA (= threads)
 constexpr int DW_MAXK = 15;
+// the backward accumulates 16 same-address atomics per thread (dW, db): longer tiles = 4x fewer of them (they, not the
+// streams, bounded the kernel at 8-frame tiles)
+constexpr int DW_TO_BWD = 32;
 
 template <typename T>
 __global__ void __launch_bounds__(DW_CH) glu_dwconv_fwd_kernel(const T* __restrict__ pre, const float* __restrict__ w,
@@ -58,15 +61,15 @@ __global__ void __launch_bounds__(DW_CH) glu_dwconv_bwd_kernel(const T* __restri
                                                                int C, int ksize, int stride, int pad) {
     extern __shared__ float sm[];
     const int b = blockIdx.z, c = blockIdx.y * DW_CH + threadIdx.x;
-    const int to0 = blockIdx.x * DW_TO;
+    const int to0 = blockIdx.x * DW_TO_BWD;
     const bool cv = c < C;
     // g tile: input frames [to0*s - pad, to0*s - pad + grows)
     const int g_lo = to0 * stride - pad;
-    const int grows = (DW_TO - 1) * stride + ksize;
-    // du tile: output frames needed by dg of input frames [t0, t0 + DW_TO*s): to in [floor((t0+pad-(k-1))/s), (t0+DW_TO*s-1+pad)/s]
+    const int grows = (DW_TO_BWD - 1) * stride + ksize;
+    // du tile: output frames needed by dg of input frames [t0, t0 + DW_TO_BWD*s): to in [floor((t0+pad-(k-1))/s), (t0+DW_TO_BWD*s-1+pad)/s]
     const int t0 = to0 * stride;
     const int d_lo = (t0 + pad - (ksize - 1) - (stride - 1)) / stride - 1;  // conservative lower bound (may be negative)
-    const int d_hi = (t0 + DW_TO * stride - 1 + pad) / stride;
+    const int d_hi = (t0 + DW_TO_BWD * stride - 1 + pad) / stride;
     const int drows = d_hi - d_lo + 1;
     float* gs = sm;                    // [grows][DW_CH]
     float* dsm = sm + grows * DW_CH;   // [drows][DW_CH]
@@ -91,7 +94,7 @@ __global__ void __launch_bounds__(DW_CH) glu_dwconv_bwd_kernel(const T* __restri
     for (int k = 0; k < DW_MAXK; ++k) { wk[k] = k < ksize ? w[c * ksize + k] : 0.0f; dwk[k] = 0.0f; }
     // weight / bias gradients from this CTA's output frames
     float dbs = 0.0f;
-    for (int j = 0; j < DW_TO; ++j) {
+    for (int j = 0; j < DW_TO_BWD; ++j) {
         int to = to0 + j;
         if (to >= To) break;
         float d = dsm[(to - d_lo) * DW_CH + threadIdx.x];
@@ -105,7 +108,7 @@ __global__ void __launch_bounds__(DW_CH) glu_dwconv_bwd_kernel(const T* __restri
         if (k < ksize) atomicAdd(dw + c * ksize + k, dwk[k]);
     if (db) atomicAdd(db + c, dbs);
     // input gradients for this CTA's input frames, then back through the GLU
-    for (int j = 0; j < DW_TO * stride; ++j) {
+    for (int j = 0; j < DW_TO_BWD * stride; ++j) {
         int t = t0 + j;
         if (t >= Tn) break;
         float dg = 0.0f;
@@ -149,9 +152,9 @@ extern "C" int avec_glu_dwconv_bwd(const void* du, const void* pre, const float*
                                    int To, int C, int ksize, int stride, int pad, int dtype, avec_stream_t stream) {
     AVEC_CHECK_ARG(du && pre && w && dpre && dw && B > 0 && T > 0 && C > 0 && ksize >= 1 && ksize <= DW_MAXK && stride >= 1);
     AVEC_CHECK_ARG(To == (T + 2 * pad - ksize) / stride + 1 && B <= 65535);
-    dim3 grid(cdiv(To, DW_TO), cdiv(C, DW_CH), B);
-    const int grows = (DW_TO - 1) * stride + ksize;
-    const int drows = DW_TO + (ksize + stride) / stride + 4;  // upper bound of d_hi - d_lo + 1 for any tile
+    dim3 grid(cdiv(To, DW_TO_BWD), cdiv(C, DW_CH), B);
+    const int grows = (DW_TO_BWD - 1) * stride + ksize;
+    const int drows = DW_TO_BWD + (ksize + stride) / stride + 4;  // upper bound of d_hi - d_lo + 1 for any tile
     size_t smem = (size_t)(grows + drows) * DW_CH * sizeof(float);
     AVEC_DISPATCH_DTYPE(dtype, Tt, {
         auto kfn = glu_dwconv_bwd_kernel<Tt>;

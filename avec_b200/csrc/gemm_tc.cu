@@ -1236,6 +1236,350 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
     if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_base, ncols); if (lane == 0) AVEC_TS(6); }
 }
 
+// =====================================================================================================================
+// Visual stem: Conv3d(1 -> 64, k (5,7,7), s (1,2,2), "same") on single-channel video as a direct tcgen05 implicit GEMM.
+// (reference nnet/networks.py:459-471, layers.Conv3d).  With C = 1 an im2col row is 245 scattered bf16 values, which a TMA
+// box cannot fetch and which costs 6.4 GB of HBM when materialised.  Here the im2col tile is built IN SHARED MEMORY:
+//   * builder warps stage the raw input window of a tile (5 frames x 13 rows x 88 pixels, 13.5 KB, cp.async, double
+//     buffered, zero padding applied once) and expand it into the canonical no-swizzle UMMA layout: one 16-byte chunk per
+//     (site, kt, kh) = the 7 kw taps + 1 pad tap, read as five aligned words and funnel-shifted (window origin 2wo-3 is
+//     odd); chunk block c = kt*7+kh holds [128 sites][16 B], so K-adjacent core matrices are 2048 B apart (LBO) and
+//     8-site groups 128 B apart (SBO).  K = 36 chunks x 8 = 288 (245 real taps; the weights of pad taps are zero);
+//   * the same tile is the K-major A operand of the forward (M = sites) and the MN-major B operand of the weight gradient
+//     (N = taps, K = sites) - no transposed copy;
+//   * weights (forward) stay resident in shared memory for the whole persistent CTA; the forward epilogue is the GEMM
+//     kernel's fast epilogue (bias, bf16 store, BatchNorm column statistics).
+constexpr int ST_CHUNKS = 36, ST_HALF = 18;
+constexpr int ST_WROW = 104;                       // window row: 8 zero | <= 88 pixels | zeros
+constexpr int ST_WROWS = 13;                       // input rows a 128-site tile can touch: 2*3 + 7
+constexpr int ST_WIN_BYTES = 13568;                // 5 * 13 * 104 * 2 = 13520, rounded up to 128
+constexpr int ST_SLOT_BYTES = ST_HALF * 2048;      // 36864: half an im2col tile (18 chunk blocks of [128][16 B])
+constexpr int ST_SLOTS = 3;
+constexpr int ST_KPAD = 320;                       // forward weight rows: 5 k-blocks of 64 (k = (kt*7+kh)*8 + kw)
+constexpr int ST_B_BYTES = 5 * 64 * 128;           // 40960
+constexpr int ST_BUILDERS = 128;
+
+struct StemParams {
+    const bf16* x;            // [Nb][T][H][W] bf16
+    int Nb, T, H, W, Ho, Wo;
+    int tpf;                  // tiles per frame = cdiv(Ho*Wo, 128)
+    int total_tiles;
+    TcParams tc;              // forward: BN = N = 64 + epilogue parameters
+    float* dw;                // weight gradient [64][245] fp32 (atomic accumulation)
+};
+
+__device__ __forceinline__ uint64_t make_smem_desc_ns(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;  // descriptor version (sm_100); layout type 0 = no swizzle
+    return d;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+    uint32_t r;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(r) : "r"(a) : "memory");
+    return r;
+}
+__device__ __forceinline__ void sts128u(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+struct StemTile { int n, t, s0, ho0; long long frame; };
+__device__ __forceinline__ StemTile stem_tile(const StemParams& p, int tile) {
+    StemTile st;
+    st.frame = tile / p.tpf;
+    const int k = tile - (int)st.frame * p.tpf;
+    st.n = (int)(st.frame / p.T); st.t = (int)(st.frame - (long long)st.n * p.T);
+    st.s0 = k * 128; st.ho0 = st.s0 / p.Wo;
+    return st;
+}
+// cp.async the input window of `tile` into `win` (rows / frames outside the video are zero-filled); one commit group
+__device__ __forceinline__ void stem_issue_window(const StemParams& p, int tile, uint32_t win, int btid) {
+    const StemTile st = stem_tile(p, tile);
+    const int segs = p.W / 8;   // 16-byte segments per input row
+    const int hi_base = 2 * st.ho0 - 3;
+    const int n_el = 5 * ST_WROWS * segs;
+    for (int idx = btid; idx < n_el; idx += ST_BUILDERS) {
+        const int seg = idx % segs; const int rr = idx / segs; const int r = rr % ST_WROWS; const int kt = rr / ST_WROWS;
+        const int ti = st.t - 2 + kt, hi = hi_base + r;
+        const bool ok = (unsigned)ti < (unsigned)p.T && (unsigned)hi < (unsigned)p.H;
+        const bf16* src = ok ? p.x + ((((long long)st.n * p.T + ti) * p.H + hi) * p.W + seg * 8) : p.x;
+        cp_async16(win + (uint32_t)(((kt * ST_WROWS + r) * ST_WROW + 8 + seg * 8) * 2), src, ok ? 16 : 0);
+    }
+    cp_async_commit();
+}
+// expand one half (18 chunk blocks) of the im2col tile of this thread's site from the staged window
+template <int HALF>
+__device__ __forceinline__ void stem_build_half(uint32_t slot, uint32_t wsite, int btid) {
+#pragma unroll
+    for (int cc = 0; cc < ST_HALF; ++cc) {
+        constexpr int dummy = 0; (void)dummy;
+        const int chunk = HALF * ST_HALF + cc;
+        const uint32_t dst = slot + (uint32_t)cc * 2048u + (uint32_t)btid * 16u;
+        if (chunk >= 35) { sts128u(dst, 0u, 0u, 0u, 0u); continue; }
+        const int kt = chunk / 7, kh = chunk % 7;
+        const uint32_t a = wsite + (uint32_t)((kt * ST_WROWS + kh) * (ST_WROW / 2)) * 4u;
+        const uint32_t w0 = lds32(a), w1 = lds32(a + 4), w2 = lds32(a + 8), w3 = lds32(a + 12), w4 = lds32(a + 16);
+        sts128u(dst, __funnelshift_r(w0, w1, 16), __funnelshift_r(w1, w2, 16), __funnelshift_r(w2, w3, 16), __funnelshift_r(w3, w4, 16));
+    }
+}
+// builder warps: window prefetch + im2col expansion for every tile of this CTA
+__device__ __forceinline__ void stem_builder_loop(const StemParams& p, uint8_t* a_ring, uint8_t* wins, uint64_t* a_full, uint64_t* a_empty, int btid) {
+    // zero both windows once (the pad columns are never written again)
+    for (int i = btid; i < 2 * ST_WIN_BYTES / 16; i += ST_BUILDERS) reinterpret_cast<uint4*>(wins)[i] = make_uint4(0u, 0u, 0u, 0u);
+    asm volatile("bar.sync 2, 128;" ::: "memory");
+    const uint32_t win0 = smem_u32(wins), ring0 = smem_u32(a_ring);
+    int j = 0, slot = 0;
+    uint32_t round = 0;
+    if ((int)blockIdx.x < p.total_tiles) stem_issue_window(p, blockIdx.x, win0, btid);
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++j) {
+        const int tn = t + gridDim.x;
+        if (tn < p.total_tiles) stem_issue_window(p, tn, win0 + (uint32_t)(((j + 1) & 1) * ST_WIN_BYTES), btid);
+        else cp_async_commit();
+        cp_async_wait<1>();
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        const StemTile st = stem_tile(p, t);
+        const int s = st.s0 + btid;
+        const int ho = s / p.Wo, wo = s - ho * p.Wo;
+        // word address of element (row 2*(ho-ho0), column 2*wo + 4) of frame slice 0
+        const uint32_t wsite = win0 + (uint32_t)((j & 1) * ST_WIN_BYTES) + (uint32_t)((2 * (ho - st.ho0)) * (ST_WROW / 2) + wo + 2) * 4u;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            mbar_wait(&a_empty[slot], round ^ 1u);
+            const uint32_t sl = ring0 + (uint32_t)slot * ST_SLOT_BYTES;
+            if (half == 0) stem_build_half<0>(sl, wsite, btid); else stem_build_half<1>(sl, wsite, btid);
+            fence_proxy_async();
+            mbar_arrive(&a_full[slot]);
+            if (++slot == ST_SLOTS) { slot = 0; round ^= 1u; }
+        }
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+    }
+}
+
+// ---- forward: warps 0-3 epilogue, warp 4 MMA issuer (+ TMEM, weight TMA), warps 5-8 builders
+constexpr int ST_FWD_THREADS = 288;
+constexpr size_t ST_FWD_SMEM = 1024 + ST_B_BYTES + ST_SLOTS * ST_SLOT_BYTES + 2 * ST_WIN_BYTES + STG_BYTES + 1024;
+
+__global__ void __launch_bounds__(ST_FWD_THREADS, 1) stem3d_fwd_kernel(const __grid_constant__ StemParams p, const __grid_constant__ CUtensorMap mapW) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* b_s = smem;
+    uint8_t* a_ring = b_s + ST_B_BYTES;
+    uint8_t* wins = a_ring + ST_SLOTS * ST_SLOT_BYTES;
+    float* stg_all = reinterpret_cast<float*>(wins + 2 * ST_WIN_BYTES);
+    uint8_t* ctrl = reinterpret_cast<uint8_t*>(stg_all) + STG_BYTES;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(ctrl);        // [3]
+    uint64_t* a_empty = a_full + 4;                               // [3]
+    uint64_t* accum_full = a_empty + 4;                           // [2]
+    uint64_t* accum_empty = accum_full + 2;                       // [2]
+    uint64_t* b_full = accum_empty + 2;                           // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 2);
+    float* bias_s = reinterpret_cast<float*>(ctrl + 256);         // [64]
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    if (tid == 0) {
+        for (int i = 0; i < ST_SLOTS; ++i) { mbar_init(&a_full[i], ST_BUILDERS); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&accum_full[i], 1); mbar_init(&accum_empty[i], PRODUCER_THREADS); }
+        mbar_init(b_full, 1);
+        fence_barrier_init();
+        tma_prefetch_desc(&mapW);
+    }
+    if (warp == 4) tmem_alloc(tmem_slot, 128);
+    for (int c = tid; c < 64; c += ST_FWD_THREADS) bias_s[c] = p.tc.ep.bias ? p.tc.ep.bias[c] : 0.0f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        // ===================== epilogue =====================
+        int j = 0;
+        EpiParams ep = p.tc.ep;
+        ep.bias = nullptr;
+        const uint32_t stg_s = smem_u32(stg_all + warp * STG_WARP), bias_sa = smem_u32(bias_s);
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++j) {
+            const StemTile st = stem_tile(p, t);
+            TileInfo ti;
+            ti.mtile = t; ti.n0 = 0; ti.z = 0; ti.kb_begin = 0; ti.nkb = 0; ti.m0 = 0;
+            ti.row_base = st.frame * (long long)(p.Ho * p.Wo) + st.s0;
+            ti.rows_valid = min(128, p.Ho * p.Wo - st.s0);
+            const int buf = j & 1;
+            mbar_wait(&accum_full[buf], (uint32_t)((j >> 1) & 1));
+            tc_fence_after();
+            const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * 64);
+            float* stats_dst = ep.colstats ? ep.colstats + (size_t)(t % AVEC_STATS_REPLICAS) * 2 * 64 : nullptr;
+            if (ep.colstats) epilogue_fast<AVEC_EPI_LINEAR, true, true>(p.tc, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane);
+            else epilogue_fast<AVEC_EPI_LINEAR, false, true>(p.tc, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane);
+            tc_fence_before();
+            mbar_arrive(&accum_empty[buf]);
+        }
+        tc_fence_before();
+    } else if (warp == 4) {
+        // ===================== weight load + MMA issuer =====================
+        if (elect_one()) {
+            mbar_expect_tx(b_full, ST_B_BYTES);
+            for (int kb = 0; kb < 5; ++kb) tma_load_2d(smem_u32(b_s) + (uint32_t)kb * 8192u, &mapW, b_full, kb * 64, 0);
+        }
+        __syncwarp();
+        mbar_wait(b_full, 0);
+        tc_fence_after();
+        const uint32_t idesc = make_idesc(64, 0, 0);
+        const uint64_t a_desc0 = make_smem_desc_ns(0, 2048, 128);
+        const uint64_t b_desc0 = make_smem_desc(0, 16, 1024);
+        const uint32_t a_hi = (uint32_t)(a_desc0 >> 32), b_hi = (uint32_t)(b_desc0 >> 32);
+        const uint32_t ring16 = smem_u32(a_ring) >> 4, b16 = smem_u32(b_s) >> 4;
+        int j = 0, slot = 0;
+        uint32_t round = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++j) {
+            const int buf = j & 1;
+            mbar_wait(&accum_empty[buf], (uint32_t)(((j >> 1) & 1) ^ 1));
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 64);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                mbar_wait(&a_full[slot], round);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t alo0 = (uint32_t)a_desc0 + ring16 + (uint32_t)slot * (ST_SLOT_BYTES >> 4);
+#pragma unroll
+                    for (int sI = 0; sI < 9; ++sI) {
+                        const int sg = half * 9 + sI;
+                        const uint32_t alo = alo0 + (uint32_t)sI * (4096u >> 4);
+                        const uint32_t blo = (uint32_t)b_desc0 + b16 + (uint32_t)(sg >> 2) * (8192u >> 4) + (uint32_t)(sg & 3) * (32u >> 4);
+                        umma_f16(d_tmem, ((uint64_t)a_hi << 32) | alo, ((uint64_t)b_hi << 32) | blo, idesc, sg > 0 ? 1u : 0u);
+                    }
+                    umma_commit(&a_empty[slot]);
+                    if (half == 1) umma_commit(&accum_full[buf]);
+                }
+                __syncwarp();
+                if (++slot == ST_SLOTS) { slot = 0; round ^= 1u; }
+            }
+        }
+        tc_fence_before();
+    } else {
+        stem_builder_loop(p, a_ring, wins, a_full, a_empty, tid - 160);
+    }
+    __syncthreads();
+    if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_base, 128); }
+}
+
+// ---- weight gradient: dW[co][tap] = sum_sites dY[site][co] * col[site][tap].  A = dY tile (MN-major, 128B swizzle, TMA; the
+// second 64-wide M group is a zero block so a full M = 128 instruction can be used), B = the im2col tile (MN-major, no
+// swizzle: N = taps, 144 per half tile), two accumulators of 144 columns that live in TMEM for the CTA's whole tile range.
+// warps 0-3 final epilogue, warp 4 MMA issuer (+ TMEM), warp 5 dY TMA, warps 6-9 builders
+constexpr int ST_WG_THREADS = 320;
+constexpr int ST_Y_BYTES = 2 * 128 * 128;   // dY stage: group 0 (TMA) + group 1 (zeros)
+constexpr size_t ST_WG_SMEM = 1024 + 2 * ST_Y_BYTES + ST_SLOTS * ST_SLOT_BYTES + 2 * ST_WIN_BYTES + 1024;
+
+__global__ void __launch_bounds__(ST_WG_THREADS, 1) stem3d_wgrad_kernel(const __grid_constant__ StemParams p, const __grid_constant__ CUtensorMap mapY) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* y_s = smem;                                   // [2 stages][2 groups][128 sites][128 B]
+    uint8_t* a_ring = y_s + 2 * ST_Y_BYTES;
+    uint8_t* wins = a_ring + ST_SLOTS * ST_SLOT_BYTES;
+    uint8_t* ctrl = wins + 2 * ST_WIN_BYTES;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(ctrl);
+    uint64_t* a_empty = a_full + 4;
+    uint64_t* y_full = a_empty + 4;      // [2]
+    uint64_t* y_empty = y_full + 2;      // [2]
+    uint64_t* done = y_empty + 2;        // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 2);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    if (tid == 0) {
+        for (int i = 0; i < ST_SLOTS; ++i) { mbar_init(&a_full[i], ST_BUILDERS); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&y_full[i], 1); mbar_init(&y_empty[i], 1); }
+        mbar_init(done, 1);
+        fence_barrier_init();
+        tma_prefetch_desc(&mapY);
+    }
+    if (warp == 4) tmem_alloc(tmem_slot, 512);
+    // zero M groups (generic proxy writes, then handed to the async proxy)
+    for (int i = tid; i < 2 * ST_Y_BYTES / 16; i += ST_WG_THREADS) reinterpret_cast<uint4*>(y_s)[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const bool any_tile = (int)blockIdx.x < p.total_tiles;
+
+    if (warp < 4) {
+        // ===================== final epilogue: rows = co (lanes 0-63), columns = (chunk, kw) =====================
+        if (any_tile && warp < 2) {
+            mbar_wait(done, 0);
+            tc_fence_after();
+            const int co = warp * 32 + lane;
+            for (int c0 = 0; c0 < 288; c0 += 16) {
+                float v[16];
+                tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int n = c0 + i, chunk = n >> 3, kw = n & 7;
+                    if (kw < 7 && chunk < 35) atomicAdd(p.dw + (size_t)co * 245 + chunk * 7 + kw, v[i]);
+                }
+            }
+        }
+        tc_fence_before();
+    } else if (warp == 4) {
+        // ===================== MMA issuer =====================
+        const uint32_t idesc = make_idesc(144, 1, 1);
+        const uint64_t a_desc0 = make_smem_desc(0, 128 * 128, 1024);       // MN-major, 128B swizzle: LBO = 64-wide group stride
+        const uint64_t b_desc0 = make_smem_desc_ns(0, 128, 2048);          // MN-major, no swizzle: LBO = next 8 sites, SBO = next 8 taps
+        const uint32_t a_hi = (uint32_t)(a_desc0 >> 32), b_hi = (uint32_t)(b_desc0 >> 32);
+        const uint32_t ring16 = smem_u32(a_ring) >> 4, y16 = smem_u32(y_s) >> 4;
+        int j = 0, slot = 0;
+        uint32_t round = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++j) {
+            const int ys = j & 1;
+            mbar_wait(&y_full[ys], (uint32_t)((j >> 1) & 1));
+            tc_fence_after();
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                mbar_wait(&a_full[slot], round);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(half * 144);
+                    const uint32_t alo0 = (uint32_t)a_desc0 + y16 + (uint32_t)ys * (ST_Y_BYTES >> 4);
+                    const uint32_t blo0 = (uint32_t)b_desc0 + ring16 + (uint32_t)slot * (ST_SLOT_BYTES >> 4);
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks)
+                        umma_f16(d_tmem, ((uint64_t)a_hi << 32) | (alo0 + (uint32_t)ks * (2048u >> 4)), ((uint64_t)b_hi << 32) | (blo0 + (uint32_t)ks * (256u >> 4)),
+                                 idesc, (j > 0 || ks > 0) ? 1u : 0u);
+                    umma_commit(&a_empty[slot]);
+                    if (half == 1) umma_commit(&y_empty[ys]);
+                }
+                __syncwarp();
+                if (++slot == ST_SLOTS) { slot = 0; round ^= 1u; }
+            }
+        }
+        if (any_tile && elect_one()) umma_commit(done);
+        __syncwarp();
+        tc_fence_before();
+    } else if (warp == 5) {
+        // ===================== dY TMA producer =====================
+        int j = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++j) {
+            const int ys = j & 1;
+            mbar_wait(&y_empty[ys], (uint32_t)(((j >> 1) & 1) ^ 1));
+            if (elect_one()) {
+                const StemTile st = stem_tile(p, t);
+                mbar_expect_tx(&y_full[ys], 128 * 128);
+                tma_load_3d(smem_u32(y_s) + (uint32_t)ys * ST_Y_BYTES, &mapY, &y_full[ys], 0, st.s0, (int)st.frame);
+            }
+            __syncwarp();
+        }
+    } else {
+        stem_builder_loop(p, a_ring, wins, a_full, a_empty, tid - 192);
+    }
+    __syncthreads();
+    if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
 // tile width: as wide as possible (<= 256, multiple of 16, awkward N such as 180 / 720 / 1080 split evenly), but narrow
 // enough that small problems still put >= ~100 CTAs on the 148 SMs (never below 64 columns)
 int pick_bn(int N, int mtiles) {
@@ -1543,6 +1887,64 @@ int avec_gemm_tc(const avec_gemm_args* a, cudaStream_t st) {
     // one tile per CTA); two CTAs per SM when shared memory and TMEM (2 x BN columns each) allow it
     long long ctas = any_gather ? tiles : std::min<long long>(tiles, (long long)num_sms * ctas_per_sm);
     gemm_tc_kernel<<<(unsigned)ctas, TC_THREADS, smem, st>>>(p, mapA, mapB);
+    AVEC_LAUNCH_CHECK();
+    return AVEC_OK;
+}
+
+// ---- visual stem entry points -----------------------------------------------------------------------------------------
+static bool stem_geom_ok(int Nb, int T, int H, int W) {
+    return Nb > 0 && T > 0 && H >= 8 && W == 88 && H % 2 == 0 && (long long)Nb * T * cdiv((H / 2) * (W / 2), 128) < 0x7fffffffLL;
+}
+static void stem_fill(StemParams& p, const void* x, int Nb, int T, int H, int W) {
+    memset(&p, 0, sizeof(p));
+    p.x = reinterpret_cast<const bf16*>(x);
+    p.Nb = Nb; p.T = T; p.H = H; p.W = W; p.Ho = (H - 1) / 2 + 1; p.Wo = (W - 1) / 2 + 1;
+    p.tpf = cdiv(p.Ho * p.Wo, 128);
+    p.total_tiles = Nb * T * p.tpf;
+}
+
+extern "C" int avec_stem3d_fwd(const void* x, const void* wp, const float* bias, void* out, float* colstats, int Nb, int T, int H, int W,
+                               avec_stream_t stream) {
+    AVEC_CHECK_ARG(x && wp && out && stem_geom_ok(Nb, T, H, W));
+    AVEC_CHECK_ARG((reinterpret_cast<uintptr_t>(x) % 16) == 0 && (reinterpret_cast<uintptr_t>(wp) % 16) == 0 && (reinterpret_cast<uintptr_t>(out) % 16) == 0);
+    AVEC_CHECK_ARG(!colstats || (reinterpret_cast<uintptr_t>(colstats) % 16) == 0);
+    StemParams p;
+    stem_fill(p, x, Nb, T, H, W);
+    p.tc.BN = 64; p.tc.N = 64; p.tc.M = (int)std::min<long long>((long long)Nb * T * p.Ho * p.Wo, 0x7fffffffLL); p.tc.epi_fast = 2;
+    EpiParams& ep = p.tc.ep;
+    ep.M = p.tc.M; ep.N = 64; ep.kind = AVEC_EPI_LINEAR; ep.alpha = 1.0f; ep.bias = bias;
+    ep.out = out; ep.out_dtype = AVEC_BF16; ep.ldo = 64; ep.colstats = colstats;
+    CUtensorMap mapW;
+    cuuint64_t d[2] = {(cuuint64_t)ST_KPAD, 64}; cuuint64_t s1[1] = {(cuuint64_t)ST_KPAD * 2}; cuuint32_t box[2] = {64, 64};
+    if (!encode_map(&mapW, wp, 2, d, s1, box)) return AVEC_ERR_DRIVER;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(stem3d_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_FWD_SMEM) != cudaSuccess) return AVEC_ERR_LAUNCH;
+        attr_set = true;
+    }
+    const int ctas = std::min(p.total_tiles, num_sms_cached());
+    stem3d_fwd_kernel<<<ctas, ST_FWD_THREADS, ST_FWD_SMEM, as_stream(stream)>>>(p, mapW);
+    AVEC_LAUNCH_CHECK();
+    return AVEC_OK;
+}
+
+extern "C" int avec_stem3d_wgrad(const void* x, const void* dy, float* dw, int Nb, int T, int H, int W, avec_stream_t stream) {
+    AVEC_CHECK_ARG(x && dy && dw && stem_geom_ok(Nb, T, H, W));
+    AVEC_CHECK_ARG((reinterpret_cast<uintptr_t>(x) % 16) == 0 && (reinterpret_cast<uintptr_t>(dy) % 16) == 0);
+    StemParams p;
+    stem_fill(p, x, Nb, T, H, W);
+    p.dw = dw;
+    CUtensorMap mapY;
+    const cuuint64_t sites = (cuuint64_t)p.Ho * p.Wo;
+    cuuint64_t d[3] = {64, sites, (cuuint64_t)Nb * T}; cuuint64_t st[2] = {128, sites * 128}; cuuint32_t box[3] = {64, 128, 1};
+    if (!encode_map(&mapY, dy, 3, d, st, box)) return AVEC_ERR_DRIVER;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(stem3d_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_WG_SMEM) != cudaSuccess) return AVEC_ERR_LAUNCH;
+        attr_set = true;
+    }
+    const int ctas = std::min(p.total_tiles, num_sms_cached());
+    stem3d_wgrad_kernel<<<ctas, ST_WG_THREADS, ST_WG_SMEM, as_stream(stream)>>>(p, mapY);
     AVEC_LAUNCH_CHECK();
     return AVEC_OK;
 }

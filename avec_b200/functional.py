@@ -428,17 +428,23 @@ class VideoStemFn(Function):
         kt, kh, kw = cw.shape[2], cw.shape[3], cw.shape[4]
         g = ops.make_geom(B, T, H, W, 1, Co, (kt, kh, kw), (1, 2, 2), ((kt - 1) // 2, (kh - 1) // 2, (kw - 1) // 2))
         taps = kt * kh * kw
-        Kpad = (taps + 63) // 64 * 64
-        # the C = 1 stem as im2col + plain TMA-fed GEMMs (fwd and wgrad share the [sites, Kpad] matrix)
-        wp = wc(cw, "stem3d", lambda w: torch.nn.functional.pad(w.reshape(w.shape[0], -1), (0, Kpad - taps)))
         sites = ops.geom_sites(g)
         stats = ops.gemm_stats_buffer(Co, video.device) if training else None
-        col = ops.im2col_c1(xc, g, Kpad)
-        u = ops.linear_fwd(col, wp, cb, colstats=stats)
+        direct = ops.stem3d_supported(xc, Co, kt, kh, kw)
+        if direct:
+            # direct tcgen05 implicit GEMM: the im2col tile only ever exists in shared memory
+            u = ops.stem3d_fwd(xc, wc(cw, "stem3d_direct", ops.stem3d_pack_weight), cb, colstats=stats)
+            col = xc
+        else:
+            # fallback (fp32 parity mode / other geometries): im2col + plain GEMMs (fwd and wgrad share the [sites, Kpad] matrix)
+            Kpad = (taps + 63) // 64 * 64
+            wp = wc(cw, "stem3d", lambda w: torch.nn.functional.pad(w.reshape(w.shape[0], -1), (0, Kpad - taps)))
+            col = ops.im2col_c1(xc, g, Kpad)
+            u = ops.linear_fwd(col, wp, cb, colstats=stats)
         bnbuf = _bn_buf(stats, bn_w, bn_b, rm, rv, sites, training, momentum)
         y, idx = ops.bn_relu_maxpool_fwd(u, bnbuf[0], bnbuf[1], B * T, g.Ho, g.Wo, Co)
         ctx.save_for_backward(col, u, bnbuf, bn_w, cw, idx)
-        ctx.g, ctx.training = g, training
+        ctx.g, ctx.training, ctx.direct = g, training, direct
         return y
 
     @staticmethod
@@ -451,7 +457,10 @@ class VideoStemFn(Function):
         dz = ops.bn_relu_maxpool_bwd(_c(dy), idx, g.N * g.To, g.Ho, g.Wo, Co)
         du, _, dgamma, dbeta = ops.bn_bwd(dz, u, bnbuf, bn_w, L.ACT_NONE)
         taps = cw.shape[2] * cw.shape[3] * cw.shape[4]
-        dcw = ops.linear_wgrad(du, col)[:, :taps].reshape(cw.shape)
+        if ctx.direct:
+            dcw = ops.stem3d_wgrad(col, du).reshape(cw.shape)
+        else:
+            dcw = ops.linear_wgrad(du, col)[:, :taps].reshape(cw.shape)
         dcb = ops.colsum(du)
         return None, dcw, dcb, dgamma, dbeta, None, None, None, None
 

@@ -406,6 +406,43 @@ def im2col_c1(x, g, Kpad):
     return col
 
 
+STEM_KPAD = 320   # forward weight row of the direct stem kernel: k = (kt*7+kh)*8 + kw, zero padded (ST_KPAD in gemm_tc.cu)
+
+
+def stem3d_supported(x, Co, kt, kh, kw):
+    """the direct tcgen05 stem kernel covers the reference's visual stem: bf16, 1 -> 64 channels, k (5,7,7), s (1,2,2), 88-pixel rows
+    (a 128-site tile must span at most 4 output rows: its staged input window holds 13 rows)"""
+    B, T, H, W = x.shape[0], x.shape[1], x.shape[2], x.shape[3]
+    return (x.dtype == torch.bfloat16 and Co == 64 and (kt, kh, kw) == (5, 7, 7) and W == 88 and H % 2 == 0 and H >= 8
+            and GEMM_IMPL != L.IMPL_SIMT)
+
+
+def stem3d_pack_weight(w):
+    """(64, 1, 5, 7, 7) -> [64, 320] with k = (kt*7+kh)*8 + kw"""
+    Co = w.shape[0]
+    wp = torch.zeros((Co, 35, 8), device=w.device, dtype=w.dtype)
+    wp[:, :, :7] = w.reshape(Co, 35, 7)
+    return torch.nn.functional.pad(wp.reshape(Co, 280), (0, STEM_KPAD - 280))
+
+
+def stem3d_fwd(x, wp, bias, colstats=None):
+    """x [B,T,H,W,1] bf16, wp [64,320] -> u [B*T*(H/2)*(W/2), 64] (+ BatchNorm column sums)"""
+    _cuda(x, wp)
+    B, T, H, W = x.shape[0], x.shape[1], x.shape[2], x.shape[3]
+    out = torch.empty((B * T * (H // 2) * (W // 2), 64), device=x.device, dtype=x.dtype)
+    L.check(L.load().avec_stem3d_fwd(x.data_ptr(), wp.data_ptr(), _p(bias), out.data_ptr(), _p(colstats), B, T, H, W, _stream()), "avec_stem3d_fwd")
+    return out
+
+
+def stem3d_wgrad(x, dy):
+    """dw [64, 245] fp32 of the same convolution (x [B,T,H,W,1] bf16, dy [sites, 64] bf16)"""
+    _cuda(x, dy)
+    B, T, H, W = x.shape[0], x.shape[1], x.shape[2], x.shape[3]
+    dw = zeros_f32((64, 245), x.device)
+    L.check(L.load().avec_stem3d_wgrad(x.data_ptr(), dy.data_ptr(), dw.data_ptr(), B, T, H, W, _stream()), "avec_stem3d_wgrad")
+    return dw
+
+
 def bn_relu_maxpool_fwd(u, scale, shift, N, Hi, Wi, Cn):
     Ho, Wo = (Hi - 1) // 2 + 1, (Wi - 1) // 2 + 1
     y = torch.empty((N, Ho, Wo, Cn), device=u.device, dtype=u.dtype)

@@ -199,6 +199,16 @@ int avec_bn_bwd_apply(const void* dy, const void* u, const float* scale, const f
 int avec_stft_mel_log(const float* wave, const float* fb, float* out, int B, int L, int F, int layout,
                       avec_stream_t stream);
 
+/* Visual stem Conv3d(1->64, k(5,7,7), s(1,2,2), "same") as a direct tcgen05 implicit GEMM (im2col tile built in shared memory;
+ * replaces layers.Conv3d.forward of nnet/networks.py:459-471 / nnet/layers.py:326-503 for the single-channel video input).
+ * x [Nb][T][H][W] bf16 (W = 88: a 128-site tile spans <= 4 output rows; H even); wp [64][320] bf16 with k = (kt*7+kh)*8 + kw (kw = 7 and k >= 280 zero);
+ * out [Nb*T*(H/2)*(W/2)][64] bf16 = conv + bias; colstats (optional) [AVEC_STATS_REPLICAS][2][64] fp32 BatchNorm sums. */
+int avec_stem3d_fwd(const void* x, const void* wp, const float* bias, void* out, float* colstats, int Nb, int T, int H, int W,
+                    avec_stream_t stream);
+/* weight gradient of the same convolution: dw [64][245] fp32 += sum_sites dy[site][co] * x[window(site)][tap] (dy bf16 [sites][64]) */
+int avec_stem3d_wgrad(const void* x, const void* dy, float* dw, int Nb, int T, int H, int W, avec_stream_t stream);
+
+
 /* single-channel im2col for the C = 1 stems (Conv3d (5,7,7) of nnet/networks.py:460-468): x [N,Ti,Hi,Wi,1] ->
  * col [sites, Kpad] (taps then zero padding), so that the stem convolution and its weight gradient run as plain GEMMs */
 int avec_im2col_c1(const void* x, void* col, const avec_conv_geom* geom, int Kpad, int dtype, avec_stream_t stream);

@@ -122,6 +122,31 @@ def test_single_channel_stem_conv_fwd_wgrad(impl, dtype, tol, B, T, H, W, Co, k,
         ops.set_gemm_impl("auto")
 
 
+@pytest.mark.parametrize("B,T,H,W", [(2, 5, 88, 88), (1, 3, 24, 88), (3, 1, 8, 88), (1, 7, 16, 88)])
+def test_direct_stem3d_fwd_wgrad(B, T, H, W):
+    """direct tcgen05 visual stem (im2col tile built in shared memory, no-swizzle UMMA operands) against conv3d in fp32 on the
+    same bf16-rounded operands: output (+ bias), BatchNorm column sums from the epilogue, weight gradient"""
+    bf = torch.bfloat16
+    x = _rand(B, T, H, W, 1, dtype=bf, seed=1)
+    w = (_rand(64, 1, 5, 7, 7, seed=2) / 245 ** 0.5).to(bf)
+    b = _rand(64, seed=3)
+    assert ops.stem3d_supported(x, 64, 5, 7, 7)
+    stats = ops.gemm_stats_buffer(64, x.device)
+    y = ops.stem3d_fwd(x, ops.stem3d_pack_weight(w.view(64, 1, 5, 7, 7)).contiguous(), b, colstats=stats)
+    wr = w.float().requires_grad_(True)
+    yr = F.conv3d(F.pad(x.float().view(B, 1, T, H, W), (3, 3, 3, 3, 2, 2)), wr, b, stride=(1, 2, 2))
+    Ho, Wo = H // 2, W // 2
+    yr2 = yr.permute(0, 2, 3, 4, 1).reshape(-1, 64)
+    _close(y, yr2, 1e-2)
+    st = stats.view(L.STATS_REPLICAS, 2, 64).sum(0)
+    _close(st[0], yr2.sum(0), 2e-3)
+    _close(st[1], (yr2 ** 2).sum(0), 2e-3)
+    dy = _rand(*y.shape, dtype=bf, seed=4)
+    yr.backward(dy.float().view(B, T, Ho, Wo, 64).permute(0, 4, 1, 2, 3))
+    dw = ops.stem3d_wgrad(x, dy)
+    _close(dw, wr.grad.reshape(64, 245), 1e-2)
+
+
 def test_im2col_single_channel():
     B, T, H, W = 2, 5, 20, 24
     for dtype in (torch.float32, torch.bfloat16):
