@@ -1257,7 +1257,7 @@ constexpr int ST_SLOT_BYTES = ST_HALF * 2048;      // 36864: half an im2col tile
 constexpr int ST_SLOTS = 3;
 constexpr int ST_KPAD = 320;                       // forward weight rows: 5 k-blocks of 64 (k = (kt*7+kh)*8 + kw)
 constexpr int ST_B_BYTES = 5 * 64 * 128;           // 40960
-constexpr int ST_BUILDERS = 128;
+constexpr int ST_BUILDERS = 256;             // two groups of 128 (thread = site), one per half tile
 
 struct StemParams {
     const bf16* x;            // [Nb][T][H][W] bf16
@@ -1266,6 +1266,7 @@ struct StemParams {
     int total_tiles;
     TcParams tc;              // forward: BN = N = 64 + epilogue parameters
     float* dw;                // weight gradient [64][245] fp32 (atomic accumulation)
+    int dbg;                  // ablation bits (AVEC_STEM_DBG): 1 no im2col expansion, 2 no MMAs, 4 no epilogue body, 8 no window copies
 };
 
 __device__ __forceinline__ uint64_t make_smem_desc_ns(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -1298,29 +1299,13 @@ __device__ __forceinline__ StemTile stem_tile(const StemParams& p, int tile) {
     st.s0 = k * 128; st.ho0 = st.s0 / p.Wo;
     return st;
 }
-// cp.async the input window of `tile` into `win` (rows / frames outside the video are zero-filled); one commit group
-__device__ __forceinline__ void stem_issue_window(const StemParams& p, int tile, uint32_t win, int btid) {
-    const StemTile st = stem_tile(p, tile);
-    const int segs = p.W / 8;   // 16-byte segments per input row
-    const int hi_base = 2 * st.ho0 - 3;
-    const int n_el = 5 * ST_WROWS * segs;
-    for (int idx = btid; idx < n_el; idx += ST_BUILDERS) {
-        const int seg = idx % segs; const int rr = idx / segs; const int r = rr % ST_WROWS; const int kt = rr / ST_WROWS;
-        const int ti = st.t - 2 + kt, hi = hi_base + r;
-        const bool ok = (unsigned)ti < (unsigned)p.T && (unsigned)hi < (unsigned)p.H;
-        const bf16* src = ok ? p.x + ((((long long)st.n * p.T + ti) * p.H + hi) * p.W + seg * 8) : p.x;
-        cp_async16(win + (uint32_t)(((kt * ST_WROWS + r) * ST_WROW + 8 + seg * 8) * 2), src, ok ? 16 : 0);
-    }
-    cp_async_commit();
-}
 // expand one half (18 chunk blocks) of the im2col tile of this thread's site from the staged window
 template <int HALF>
-__device__ __forceinline__ void stem_build_half(uint32_t slot, uint32_t wsite, int btid) {
+__device__ __forceinline__ void stem_build_half(uint32_t slot, uint32_t wsite, int site) {
 #pragma unroll
     for (int cc = 0; cc < ST_HALF; ++cc) {
-        constexpr int dummy = 0; (void)dummy;
         const int chunk = HALF * ST_HALF + cc;
-        const uint32_t dst = slot + (uint32_t)cc * 2048u + (uint32_t)btid * 16u;
+        const uint32_t dst = slot + (uint32_t)cc * 2048u + (uint32_t)site * 16u;
         if (chunk >= 35) { sts128u(dst, 0u, 0u, 0u, 0u); continue; }
         const int kt = chunk / 7, kh = chunk % 7;
         const uint32_t a = wsite + (uint32_t)((kt * ST_WROWS + kh) * (ST_WROW / 2)) * 4u;
@@ -1328,41 +1313,67 @@ __device__ __forceinline__ void stem_build_half(uint32_t slot, uint32_t wsite, i
         sts128u(dst, __funnelshift_r(w0, w1, 16), __funnelshift_r(w1, w2, 16), __funnelshift_r(w2, w3, 16), __funnelshift_r(w3, w4, 16));
     }
 }
-// builder warps: window prefetch + im2col expansion for every tile of this CTA
+// Builder warps (256 threads): window prefetch + im2col expansion for every tile of this CTA.  The two groups of 128 threads
+// expand the two halves of a tile concurrently (thread = site), each into its own ring slot; a single warp per scheduler
+// issues one dependent instruction every ~4 cycles, so the per-tile instruction count per thread is what bounds this loop:
+// window copies use per-thread offsets that are tile-invariant (computed once), 3 x 16 bytes per thread and tile.
 __device__ __forceinline__ void stem_builder_loop(const StemParams& p, uint8_t* a_ring, uint8_t* wins, uint64_t* a_full, uint64_t* a_empty, int btid) {
-    // zero both windows once (the pad columns are never written again)
+    constexpr int SEGS = 11, N_COPY = 5 * ST_WROWS * SEGS, CPT = (N_COPY + ST_BUILDERS - 1) / ST_BUILDERS;   // 715 copies, 3 per thread
     for (int i = btid; i < 2 * ST_WIN_BYTES / 16; i += ST_BUILDERS) reinterpret_cast<uint4*>(wins)[i] = make_uint4(0u, 0u, 0u, 0u);
-    asm volatile("bar.sync 2, 128;" ::: "memory");
+    asm volatile("bar.sync 2, 256;" ::: "memory");
     const uint32_t win0 = smem_u32(wins), ring0 = smem_u32(a_ring);
-    int j = 0, slot = 0;
-    uint32_t round = 0;
-    if ((int)blockIdx.x < p.total_tiles) stem_issue_window(p, blockIdx.x, win0, btid);
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++j) {
+    const int grp = btid >> 7, site = btid & 127;
+    int c_kt[CPT], c_r[CPT], c_src[CPT];
+    uint32_t c_dst[CPT];
+#pragma unroll
+    for (int k = 0; k < CPT; ++k) {
+        const int idx = btid + k * ST_BUILDERS;
+        const int seg = idx % SEGS, rr = idx / SEGS;
+        c_r[k] = rr % ST_WROWS; c_kt[k] = idx < N_COPY ? rr / ST_WROWS : -100;   // -100: no copy (frame test fails)
+        c_src[k] = (c_kt[k] * p.H + c_r[k]) * p.W + seg * 8;
+        c_dst[k] = (uint32_t)(((rr / ST_WROWS * ST_WROWS + c_r[k]) * ST_WROW + 8 + seg * 8) * 2);
+    }
+    auto issue_window = [&](int tile, uint32_t win) {
+        const StemTile st = stem_tile(p, tile);
+        const int hi_base = 2 * st.ho0 - 3;
+        const long long base = (((long long)st.n * p.T + st.t - 2) * p.H + hi_base) * p.W;
+        if (!(p.dbg & 8)) {
+#pragma unroll
+            for (int k = 0; k < CPT; ++k) {
+                const int ti = st.t - 2 + c_kt[k], hi = hi_base + c_r[k];
+                const bool inside = c_kt[k] >= 0;
+                const bool ok = inside && (unsigned)ti < (unsigned)p.T && (unsigned)hi < (unsigned)p.H;
+                if (inside) cp_async16(win + c_dst[k], ok ? p.x + base + c_src[k] : p.x, ok ? 16 : 0);
+            }
+        }
+        cp_async_commit();
+    };
+    int j = 0;
+    int it = grp;   // half-tile counter of this group: slot = it % 3, use parity = (it / 3) & 1
+    if ((int)blockIdx.x < p.total_tiles) issue_window(blockIdx.x, win0);
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++j, it += 2) {
         const int tn = t + gridDim.x;
-        if (tn < p.total_tiles) stem_issue_window(p, tn, win0 + (uint32_t)(((j + 1) & 1) * ST_WIN_BYTES), btid);
+        if (tn < p.total_tiles) issue_window(tn, win0 + (uint32_t)(((j + 1) & 1) * ST_WIN_BYTES));
         else cp_async_commit();
         cp_async_wait<1>();
-        asm volatile("bar.sync 2, 128;" ::: "memory");
+        asm volatile("bar.sync 2, 256;" ::: "memory");
         const StemTile st = stem_tile(p, t);
-        const int s = st.s0 + btid;
+        const int s = st.s0 + site;
         const int ho = s / p.Wo, wo = s - ho * p.Wo;
         // word address of element (row 2*(ho-ho0), column 2*wo + 4) of frame slice 0
         const uint32_t wsite = win0 + (uint32_t)((j & 1) * ST_WIN_BYTES) + (uint32_t)((2 * (ho - st.ho0)) * (ST_WROW / 2) + wo + 2) * 4u;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            mbar_wait(&a_empty[slot], round ^ 1u);
-            const uint32_t sl = ring0 + (uint32_t)slot * ST_SLOT_BYTES;
-            if (half == 0) stem_build_half<0>(sl, wsite, btid); else stem_build_half<1>(sl, wsite, btid);
-            fence_proxy_async();
-            mbar_arrive(&a_full[slot]);
-            if (++slot == ST_SLOTS) { slot = 0; round ^= 1u; }
-        }
-        asm volatile("bar.sync 2, 128;" ::: "memory");
+        const int slot = it % ST_SLOTS;
+        mbar_wait(&a_empty[slot], (uint32_t)(((it / ST_SLOTS) & 1) ^ 1));
+        const uint32_t sl = ring0 + (uint32_t)slot * ST_SLOT_BYTES;
+        if (!(p.dbg & 1)) { if (grp == 0) stem_build_half<0>(sl, wsite, site); else stem_build_half<1>(sl, wsite, site); }
+        fence_proxy_async();
+        mbar_arrive(&a_full[slot]);
+        asm volatile("bar.sync 2, 256;" ::: "memory");
     }
 }
 
-// ---- forward: warps 0-3 epilogue, warp 4 MMA issuer (+ TMEM, weight TMA), warps 5-8 builders
-constexpr int ST_FWD_THREADS = 288;
+// ---- forward: warps 0-3 epilogue, warp 4 MMA issuer (+ TMEM, weight TMA), warps 5-12 builders
+constexpr int ST_FWD_THREADS = 416;
 constexpr size_t ST_FWD_SMEM = 1024 + ST_B_BYTES + ST_SLOTS * ST_SLOT_BYTES + 2 * ST_WIN_BYTES + STG_BYTES + 1024;
 
 __global__ void __launch_bounds__(ST_FWD_THREADS, 1) stem3d_fwd_kernel(const __grid_constant__ StemParams p, const __grid_constant__ CUtensorMap mapW) {
@@ -1383,7 +1394,7 @@ __global__ void __launch_bounds__(ST_FWD_THREADS, 1) stem3d_fwd_kernel(const __g
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     if (tid == 0) {
-        for (int i = 0; i < ST_SLOTS; ++i) { mbar_init(&a_full[i], ST_BUILDERS); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < ST_SLOTS; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&accum_full[i], 1); mbar_init(&accum_empty[i], PRODUCER_THREADS); }
         mbar_init(b_full, 1);
         fence_barrier_init();
@@ -1413,7 +1424,8 @@ __global__ void __launch_bounds__(ST_FWD_THREADS, 1) stem3d_fwd_kernel(const __g
             tc_fence_after();
             const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * 64);
             float* stats_dst = ep.colstats ? ep.colstats + (size_t)(t % AVEC_STATS_REPLICAS) * 2 * 64 : nullptr;
-            if (ep.colstats) epilogue_fast<AVEC_EPI_LINEAR, true, true>(p.tc, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane);
+            if (p.dbg & 4) { }
+            else if (ep.colstats) epilogue_fast<AVEC_EPI_LINEAR, true, true>(p.tc, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane);
             else epilogue_fast<AVEC_EPI_LINEAR, false, true>(p.tc, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane);
             tc_fence_before();
             mbar_arrive(&accum_empty[buf]);
@@ -1451,7 +1463,7 @@ __global__ void __launch_bounds__(ST_FWD_THREADS, 1) stem3d_fwd_kernel(const __g
                         const int sg = half * 9 + sI;
                         const uint32_t alo = alo0 + (uint32_t)sI * (4096u >> 4);
                         const uint32_t blo = (uint32_t)b_desc0 + b16 + (uint32_t)(sg >> 2) * (8192u >> 4) + (uint32_t)(sg & 3) * (32u >> 4);
-                        umma_f16(d_tmem, ((uint64_t)a_hi << 32) | alo, ((uint64_t)b_hi << 32) | blo, idesc, sg > 0 ? 1u : 0u);
+                        if (!(p.dbg & 2)) umma_f16(d_tmem, ((uint64_t)a_hi << 32) | alo, ((uint64_t)b_hi << 32) | blo, idesc, sg > 0 ? 1u : 0u);
                     }
                     umma_commit(&a_empty[slot]);
                     if (half == 1) umma_commit(&accum_full[buf]);
@@ -1471,8 +1483,8 @@ __global__ void __launch_bounds__(ST_FWD_THREADS, 1) stem3d_fwd_kernel(const __g
 // ---- weight gradient: dW[co][tap] = sum_sites dY[site][co] * col[site][tap].  A = dY tile (MN-major, 128B swizzle, TMA; the
 // second 64-wide M group is a zero block so a full M = 128 instruction can be used), B = the im2col tile (MN-major, no
 // swizzle: N = taps, 144 per half tile), two accumulators of 144 columns that live in TMEM for the CTA's whole tile range.
-// warps 0-3 final epilogue, warp 4 MMA issuer (+ TMEM), warp 5 dY TMA, warps 6-9 builders
-constexpr int ST_WG_THREADS = 320;
+// warps 0-3 final epilogue, warp 4 MMA issuer (+ TMEM), warp 5 dY TMA, warps 6-13 builders
+constexpr int ST_WG_THREADS = 448;
 constexpr int ST_Y_BYTES = 2 * 128 * 128;   // dY stage: group 0 (TMA) + group 1 (zeros)
 constexpr size_t ST_WG_SMEM = 1024 + 2 * ST_Y_BYTES + ST_SLOTS * ST_SLOT_BYTES + 2 * ST_WIN_BYTES + 1024;
 
@@ -1492,7 +1504,7 @@ __global__ void __launch_bounds__(ST_WG_THREADS, 1) stem3d_wgrad_kernel(const __
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     if (tid == 0) {
-        for (int i = 0; i < ST_SLOTS; ++i) { mbar_init(&a_full[i], ST_BUILDERS); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < ST_SLOTS; ++i) { mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&y_full[i], 1); mbar_init(&y_empty[i], 1); }
         mbar_init(done, 1);
         fence_barrier_init();
@@ -1548,7 +1560,7 @@ __global__ void __launch_bounds__(ST_WG_THREADS, 1) stem3d_wgrad_kernel(const __
                     const uint32_t blo0 = (uint32_t)b_desc0 + ring16 + (uint32_t)slot * (ST_SLOT_BYTES >> 4);
 #pragma unroll
                     for (int ks = 0; ks < 8; ++ks)
-                        umma_f16(d_tmem, ((uint64_t)a_hi << 32) | (alo0 + (uint32_t)ks * (2048u >> 4)), ((uint64_t)b_hi << 32) | (blo0 + (uint32_t)ks * (256u >> 4)),
+                        if (!(p.dbg & 2)) umma_f16(d_tmem, ((uint64_t)a_hi << 32) | (alo0 + (uint32_t)ks * (2048u >> 4)), ((uint64_t)b_hi << 32) | (blo0 + (uint32_t)ks * (256u >> 4)),
                                  idesc, (j > 0 || ks > 0) ? 1u : 0u);
                     umma_commit(&a_empty[slot]);
                     if (half == 1) umma_commit(&y_empty[ys]);
@@ -1901,6 +1913,9 @@ static void stem_fill(StemParams& p, const void* x, int Nb, int T, int H, int W)
     p.Nb = Nb; p.T = T; p.H = H; p.W = W; p.Ho = (H - 1) / 2 + 1; p.Wo = (W - 1) / 2 + 1;
     p.tpf = cdiv(p.Ho * p.Wo, 128);
     p.total_tiles = Nb * T * p.tpf;
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("AVEC_STEM_DBG"); dbg = e ? atoi(e) : 0; }
+    p.dbg = dbg;
 }
 
 extern "C" int avec_stem3d_fwd(const void* x, const void* wp, const float* bias, void* out, float* colstats, int Nb, int T, int H, int W,
