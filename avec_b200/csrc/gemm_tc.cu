@@ -71,6 +71,12 @@ struct TcParams {
     int halo_bytes;             // bytes of one halo tile (multiple of 1024); 0 = no halo mode
     int halo_W2;                // W + 2
     int stg_dedicated;          // 1: epilogue staging has its own shared memory (persistent launches); 0: it aliases the drained ring
+    // parity-class mode of strided dgrads: filter taps come from a table (tile shift + weight k offset per tap) and output rows
+    // are scattered: row = tile base + rowrel[r] (table in shared memory), tile base = ((n0 * rm_Hi + rm_sy * h0 + rm_a) * rm_Wi + rm_b)
+    int gen_taps;               // number of table taps (0 = regular 3x3 / 1x1 addressing)
+    signed char tap_dh[9], tap_dw[9];
+    int tap_koff[9];            // element offset of the tap's 64-channel blocks inside a B row
+    int rm_on, rm_Hi, rm_Wi, rm_sy, rm_sx, rm_a, rm_b;
     int epi_fast;               // 0: generic epilogue, 1: fast epilogue with 8-byte aligned rows, 2: 16-byte aligned rows
     int grid_m, grid_n, splits; // tile grid (the launch grid is min(#tiles, resident CTAs): persistent tile loop)
     unsigned long long* dbg_ts; // diagnostics (avec_set_debug_timestamps): CTA (0,0,0) records globaltimer at phase boundaries
@@ -528,7 +534,7 @@ __device__ __forceinline__ TileInfo decode_tile(const TcParams& p, int t) {
     } else if (p.conv_tiles && p.a_kind == OP_TMA_CONV_K) {
         int tn0, th0;
         conv_tile_origin(p, ti.mtile, tn0, th0);
-        ti.row_base = ((long long)tn0 * p.ct_H + th0) * p.ct_W;
+        ti.row_base = p.rm_on ? ((long long)tn0 * p.rm_Hi + p.rm_sy * th0 + p.rm_a) * p.rm_Wi + p.rm_b : ((long long)tn0 * p.ct_H + th0) * p.ct_W;
         ti.rows_valid = p.ct_BI == 1 ? min(p.ct_BH, p.ct_H - th0) * p.ct_W : min(p.ct_BI, p.g.N - tn0) * p.ct_H * p.ct_W;
     } else {
         ti.row_base = ti.m0;
@@ -669,12 +675,22 @@ __device__ __forceinline__ void unpack_bf16x8(const uint4& t, float (&v)[8]) {
 // use, bias kept in registers (a lane owns the same 8 columns in every pass).
 template <int KIND, bool STATS, bool AL16>
 __device__ __forceinline__ void epilogue_fast(const TcParams& p, const EpiParams& ep, const TileInfo& ti, uint32_t lane_addr, uint32_t stg_s,
-                                              uint32_t bias_sa, float* stats_dst, int warp, int lane) {
+                                              uint32_t bias_sa, float* stats_dst, int warp, int lane, uint32_t rowrel_sa = 0u) {
     const int BN = p.BN;
     const int q = lane & 7, rs = lane >> 3;
     const int lc = q * 8;
     const float alpha = ep.alpha;
     const int rows_left = ti.rows_valid - warp * 32;   // valid rows of this warp's quarter (may be <= 0 or >= 32)
+    // output row of tile row r: contiguous, or scattered through the row table (parity classes of strided dgrads)
+    auto out_row = [&](int rr) -> size_t {
+        const int r = warp * 32 + rr;
+        if (p.rm_on) {
+            int rel;
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(rel) : "r"(rowrel_sa + (uint32_t)r * 4u) : "memory");
+            return (size_t)(ti.row_base + rel);
+        }
+        return (size_t)(ti.row_base + r);
+    };
     for (int c0 = 0; c0 < BN; c0 += 64) {
         const int ncol = min(64, BN - c0);   // multiple of 16
         const int gc = ti.n0 + c0 + lc;
@@ -689,7 +705,7 @@ __device__ __forceinline__ void epilogue_fast(const TcParams& p, const EpiParams
             for (int u = 0; u < 4; ++u) {
                 const int rr = u * 4 + rs;
                 xa[u] = make_uint4(0u, 0u, 0u, 0u);
-                if (aux_on && col_ok && rr < rows_left) xa[u] = ldg_bf16x8<AL16>(auxp + (size_t)(ti.row_base + warp * 32 + rr) * ep.ldaux + gc);
+                if (aux_on && col_ok && rr < rows_left) xa[u] = ldg_bf16x8<AL16>(auxp + out_row(rr) * ep.ldaux + gc);
             }
         }
         // ---- row domain: TMEM -> registers -> staging
@@ -712,7 +728,7 @@ __device__ __forceinline__ void epilogue_fast(const TcParams& p, const EpiParams
             for (int u = 0; u < 4; ++u) {
                 const int rr = (4 + u) * 4 + rs;
                 xb[u] = make_uint4(0u, 0u, 0u, 0u);
-                if (aux_on && col_ok && rr < rows_left) xb[u] = ldg_bf16x8<AL16>(auxp + (size_t)(ti.row_base + warp * 32 + rr) * ep.ldaux + gc);
+                if (aux_on && col_ok && rr < rows_left) xb[u] = ldg_bf16x8<AL16>(auxp + out_row(rr) * ep.ldaux + gc);
             }
         }
         __syncwarp();
@@ -738,7 +754,7 @@ __device__ __forceinline__ void epilogue_fast(const TcParams& p, const EpiParams
             for (int u = 0; u < 4; ++u) {
                 const int rr = (g * 4 + u) * 4 + rs;
                 if (!(col_ok && rr < rows_left)) continue;
-                const size_t row = (size_t)(ti.row_base + warp * 32 + rr);
+                const size_t row = out_row(rr);
                 float a[8] = {t[2 * u].x + b[0], t[2 * u].y + b[1], t[2 * u].z + b[2], t[2 * u].w + b[3],
                               t[2 * u + 1].x + b[4], t[2 * u + 1].y + b[5], t[2 * u + 1].z + b[6], t[2 * u + 1].w + b[7]};
                 const size_t oi = row * ep.ldo + gc;
@@ -916,17 +932,17 @@ __device__ __forceinline__ void epilogue_warp(const TcParams& p, const EpiParams
 
 template <bool AL16>
 __device__ __forceinline__ void epilogue_fast_dispatch(const TcParams& p, const EpiParams& ep, const TileInfo& ti, uint32_t lane_addr, uint32_t stg_s,
-                                                       uint32_t bias_sa, float* stats_dst, int warp, int lane) {
+                                                       uint32_t bias_sa, float* stats_dst, int warp, int lane, uint32_t rowrel_sa) {
     switch (ep.kind) {
     case AVEC_EPI_LINEAR:
-        if (ep.colstats) epilogue_fast<AVEC_EPI_LINEAR, true, AL16>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane);
-        else epilogue_fast<AVEC_EPI_LINEAR, false, AL16>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane);
+        if (ep.colstats) epilogue_fast<AVEC_EPI_LINEAR, true, AL16>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane, rowrel_sa);
+        else epilogue_fast<AVEC_EPI_LINEAR, false, AL16>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane, rowrel_sa);
         break;
-    case AVEC_EPI_SWISH: epilogue_fast<AVEC_EPI_SWISH, false, AL16>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane); break;
-    case AVEC_EPI_RESIDUAL: epilogue_fast<AVEC_EPI_RESIDUAL, false, AL16>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane); break;
-    case AVEC_EPI_DSWISH: epilogue_fast<AVEC_EPI_DSWISH, false, AL16>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane); break;
-    case AVEC_EPI_ACCUM: epilogue_fast<AVEC_EPI_ACCUM, false, AL16>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane); break;
-    default: epilogue_fast<AVEC_EPI_RELU, false, AL16>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane); break;
+    case AVEC_EPI_SWISH: epilogue_fast<AVEC_EPI_SWISH, false, AL16>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane, rowrel_sa); break;
+    case AVEC_EPI_RESIDUAL: epilogue_fast<AVEC_EPI_RESIDUAL, false, AL16>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane, rowrel_sa); break;
+    case AVEC_EPI_DSWISH: epilogue_fast<AVEC_EPI_DSWISH, false, AL16>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane, rowrel_sa); break;
+    case AVEC_EPI_ACCUM: epilogue_fast<AVEC_EPI_ACCUM, false, AL16>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane, rowrel_sa); break;
+    default: epilogue_fast<AVEC_EPI_RELU, false, AL16>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane, rowrel_sa); break;
     }
 }
 
@@ -1001,6 +1017,14 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
 
     if (warp < 4) {
         // ===================== gather producers (when an operand is not TMA-fed), then epilogue =====================
+        if (p.rm_on) {
+            // tile row r = ((image il) * ct_H' + row i) * ct_W + column j  ->  relative output row on the strided grid
+            const int per_img = p.ct_BI == 1 ? 0x7fffffff : p.ct_H * p.ct_W;
+            const int il = tid / per_img, rem = tid - il * per_img;
+            const int i = rem / p.ct_W, j = rem - i * p.ct_W;
+            reinterpret_cast<int*>(rinfo)[tid] = (il * p.rm_Hi + p.rm_sy * i) * p.rm_Wi + p.rm_sx * j;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
         int it = 0;   // k-blocks pushed through the ring so far
         int j = 0;    // local tile counter
         int cur_n0 = -1;
@@ -1085,8 +1109,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
             // BatchNorm statistics go to one of AVEC_STATS_REPLICAS copies of the accumulator (by tile index): 32x fewer
             // same-address L2 reductions
             float* stats_dst = ep.colstats ? ep.colstats + (size_t)(ti.mtile % AVEC_STATS_REPLICAS) * 2 * p.N : nullptr;
-            if (p.epi_fast == 2) epilogue_fast_dispatch<true>(p, ep, ti, lane_addr, smem_u32(stg), smem_u32(bias_s), stats_dst, warp, lane);
-            else if (p.epi_fast == 1) epilogue_fast_dispatch<false>(p, ep, ti, lane_addr, smem_u32(stg), smem_u32(bias_s), stats_dst, warp, lane);
+            if (p.epi_fast == 2) epilogue_fast_dispatch<true>(p, ep, ti, lane_addr, smem_u32(stg), smem_u32(bias_s), stats_dst, warp, lane, smem_u32(rinfo));
+            else if (p.epi_fast == 1) epilogue_fast_dispatch<false>(p, ep, ti, lane_addr, smem_u32(stg), smem_u32(bias_s), stats_dst, warp, lane, smem_u32(rinfo));
             else epilogue_warp(p, ep, ti, lane_addr, stg, bias_s, stats_dst, warp, lane);
             // all TMEM reads of this buffer are complete: hand it back to the MMA warp
             tc_fence_before();
@@ -1126,6 +1150,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
                 const int b_simple = b_tma ? (p.b_kind == OP_TMA_K ? 1 : 3) : 0;
                 const int sgn = p.ct_dgrad ? -1 : 1;
                 const int th0s = th0 * p.ct_s;
+                const int kw_wrap = p.gen_taps ? 0x7fffffff : p.g.KW;
                 int kcoord = ti.kb_begin * BKE;
                 for (int i = 0; i < ti.nkb; ++i) {
                     mbar_wait(&empty_bar[st], ph ^ 1u);
@@ -1139,16 +1164,18 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
                         } else {
                             mbar_expect_tx(bar, tx);
                             if (a_simple == 1) tma_load_2d(a_dst, &mapA, bar, kcoord, ti.m0 - p.dbg_rowofs);
+                            else if (a_simple == 2 && p.gen_taps) tma_load_4d(a_dst, &mapA, bar, cb * BKE, (int)p.tap_dw[kw], th0s + (int)p.tap_dh[kw], tn0);
                             else if (a_simple == 2) tma_load_4d(a_dst, &mapA, bar, cb * BKE, sgn * (kw - p.g.pw), th0s + sgn * (kh - p.g.ph), tn0);
                             else if (a_simple == 3) tma_fill(p, p.a_kind, &mapA, smem + (size_t)st * stage_bytes, bar, p.a_rows, p.a_group_stride, ti.m0, ti.kb_begin + i, ti.mtile, true);
-                            if (b_simple == 1) tma_load_2d(b_dst, &mapB, bar, kcoord, ti.n0);
+                            if (b_simple == 1 && p.gen_taps) tma_load_2d(b_dst, &mapB, bar, p.tap_koff[kw] + cb * BKE, ti.n0);
+                            else if (b_simple == 1) tma_load_2d(b_dst, &mapB, bar, kcoord, ti.n0);
                             else if (b_simple == 3) tma_fill(p, p.b_kind, &mapB, smem + (size_t)st * stage_bytes + a_bytes, bar, p.b_rows, p.b_group_stride, ti.n0, ti.kb_begin + i, ti.mtile, false);
                         }
                         AVEC_TSK(j, i, 200, 1);
                     }
                     __syncwarp();
                     kcoord += BKE;
-                    if (++cb == p.cpb) { cb = 0; if (++kw == p.g.KW) { kw = 0; ++kh; } }
+                    if (++cb == p.cpb) { cb = 0; if (++kw == kw_wrap) { kw = 0; ++kh; } }   // table mode: kw = running tap index
                     if (++st == p.stages) { st = 0; ph ^= 1u; }
                 }
             }
@@ -1666,6 +1693,7 @@ int num_sms_cached() {
 }  // namespace
 
 static int g_tma_enabled = 1;
+static bool g_tma_enabled_flag() { return g_tma_enabled != 0; }
 static unsigned long long* g_dbg_ts = nullptr;
 extern "C" void avec_set_tma(int enabled) { g_tma_enabled = enabled; }
 extern "C" void avec_set_debug_timestamps(void* dev_buf_8_u64) { g_dbg_ts = reinterpret_cast<unsigned long long*>(dev_buf_8_u64); }
@@ -1689,7 +1717,42 @@ bool avec_gemm_tc_supported(const avec_gemm_args* a) {
     }
 }
 
+namespace {
+struct DgradClass { int a, b; };   // output parity class (rows 2i + a, columns 2j + b) of a stride-2 3x3 dgrad
+}
+static int gemm_tc_launch(const avec_gemm_args* a, cudaStream_t st, const DgradClass* dc);
+
+// Stride-2 3x3 dgrad, exact: dx[2i+a, 2j+b] only receives the filter taps of matching parity (1, 2, 2 or 4 of the 9), so each
+// of the 4 parity classes is a stride-1 convolution over the dY grid with a sub-filter, written to a strided sub-grid of dx
+// (together the classes cover dx exactly once).  9 tap-GEMMs instead of the 36 of the zero-insertion formulation.
+static bool dgrad_classes_ok(const avec_gemm_args* a) {
+    const avec_conv_geom& g = a->g;
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("AVEC_DGRAD_CLASSES"); on = e ? atoi(e) : 1; }
+    if (!on || a->mode != AVEC_GEMM_CONV_DGRAD || !g_tma_enabled_flag() || get_encode() == nullptr) return false;
+    if (!(g.KT == 1 && g.Ti == 1 && g.st == 1 && g.sh == 2 && g.sw == 2 && g.KH == 3 && g.KW == 3 && g.ph == 1 && g.pw == 1)) return false;
+    if (g.C % 64 != 0 || g.Co % 64 != 0 || g.Ho != (g.Hi - 1) / 2 + 1 || g.Wo != (g.Wi - 1) / 2 + 1 || (g.Wi + 1) / 2 > 128) return false;
+    if (a->ab_dtype != AVEC_BF16 || a->out_dtype != AVEC_BF16 || (a->epi != AVEC_EPI_LINEAR && a->epi != AVEC_EPI_RESIDUAL)) return false;
+    if (a->bias || a->colstats || a->out2 || (a->epi == AVEC_EPI_RESIDUAL && (!a->aux || a->aux_dtype != AVEC_BF16))) return false;
+    if (ptr_align(a->out, a->ldo) < 8 || (a->aux && ptr_align(a->aux, a->ldaux) < 8)) return false;
+    return (reinterpret_cast<uintptr_t>(a->A) % 16) == 0 && (reinterpret_cast<uintptr_t>(a->B) % 16) == 0;
+}
+
 int avec_gemm_tc(const avec_gemm_args* a, cudaStream_t st) {
+    if (dgrad_classes_ok(a)) {
+        for (int ca = 0; ca < 2; ++ca)
+            for (int cb = 0; cb < 2; ++cb) {
+                if ((a->g.Hi - ca + 1) / 2 <= 0 || (a->g.Wi - cb + 1) / 2 <= 0) continue;
+                DgradClass dc{ca, cb};
+                const int rc = gemm_tc_launch(a, st, &dc);
+                if (rc != AVEC_OK) return rc;
+            }
+        return AVEC_OK;
+    }
+    return gemm_tc_launch(a, st, nullptr);
+}
+
+static int gemm_tc_launch(const avec_gemm_args* a, cudaStream_t st, const DgradClass* dc) {
     TcParams p;
     memset(&p, 0, sizeof(p));
     CUtensorMap mapA, mapB;
@@ -1708,7 +1771,7 @@ int avec_gemm_tc(const avec_gemm_args* a, cudaStream_t st) {
     int grid_m = cdiv(a->M, BM);
     bool wgrad_bn_fixed = false;
     int BH = 0, BI = 0, tph = 0;
-    const bool conv_tma = g_tma_enabled && get_encode() != nullptr && (a->mode == AVEC_GEMM_CONV_FWD || a->mode == AVEC_GEMM_CONV_DGRAD ||
+    const bool conv_tma = !dc && g_tma_enabled && get_encode() != nullptr && (a->mode == AVEC_GEMM_CONV_FWD || a->mode == AVEC_GEMM_CONV_DGRAD ||
                           a->mode == AVEC_GEMM_CONV_WGRAD) && conv_tma_geom_ok(p.g, a->mode == AVEC_GEMM_CONV_DGRAD) && p.g.C % 64 == 0 && p.g.Co % 64 == 0 &&
                           conv_tiling(p.g, BH, BI, tph) && (reinterpret_cast<uintptr_t>(a->A) % 16) == 0 && (reinterpret_cast<uintptr_t>(a->B) % 16) == 0;
     switch (a->mode) {
@@ -1738,6 +1801,34 @@ int avec_gemm_tc(const avec_gemm_args* a, cudaStream_t st) {
         wgrad_bn_fixed = true;
         break;
     default: return AVEC_ERR_INVALID;
+    }
+    int class_tile_rows = 0;
+    if (dc) {
+        const ConvGeom& g = p.g;
+        const int Hs = (g.Hi - dc->a + 1) / 2, Ws = (g.Wi - dc->b + 1) / 2;
+        ConvGeom gs = g;
+        gs.Ho = Hs; gs.Wo = Ws; gs.sh = gs.sw = 1;
+        if (!conv_tiling(gs, BH, BI, tph)) return AVEC_ERR_UNSUPPORTED;
+        // taps of matching parity: (kh, dh) in {(1, 0)} for even rows, {(0, +1), (2, 0)} for odd rows; same for columns
+        const int kh_a[2][2] = {{1, -1}, {0, 2}}, dh_a[2][2] = {{0, 0}, {1, 0}}, n_a[2] = {1, 2};
+        int nt = 0;
+        for (int i = 0; i < n_a[dc->a]; ++i)
+            for (int j = 0; j < n_a[dc->b]; ++j) {
+                p.tap_dh[nt] = (signed char)dh_a[dc->a][i]; p.tap_dw[nt] = (signed char)dh_a[dc->b][j];
+                p.tap_koff[nt] = (kh_a[dc->a][i] * 3 + kh_a[dc->b][j]) * g.Co;
+                ++nt;
+            }
+        p.gen_taps = nt;
+        p.a_kind = OP_TMA_CONV_K; p.cpb = g.Co / 64; p.num_kb = nt * p.cpb; p.ct_dgrad = 0;
+        p.conv_tiles = 1; p.ct_BH = BH; p.ct_BI = BI; p.ct_tph = tph; p.ct_H = Hs; p.ct_W = Ws; p.ct_s = 1;
+        grid_m = BI == 1 ? g.N * tph : cdiv(g.N, BI);
+        class_tile_rows = BI == 1 ? BH * Ws : BI * Hs * Ws;
+        p.a_tx = class_tile_rows * 128;
+        p.rm_on = 1; p.rm_Hi = g.Hi; p.rm_Wi = g.Wi; p.rm_sy = 2; p.rm_sx = 2; p.rm_a = dc->a; p.rm_b = dc->b;
+        cuuint64_t dA[4] = {(cuuint64_t)g.Co, (cuuint64_t)g.Wo, (cuuint64_t)g.Ho, (cuuint64_t)g.N};
+        cuuint64_t sA[3] = {(cuuint64_t)g.Co * 2, (cuuint64_t)g.Co * g.Wo * 2, (cuuint64_t)g.Co * g.Wo * g.Ho * 2};
+        cuuint32_t box[4] = {64, (cuuint32_t)Ws, (cuuint32_t)BH, (cuuint32_t)BI};
+        if (!encode_map(&mapA, a->A, 4, dA, sA, box)) return AVEC_ERR_DRIVER;
     }
     p.a_align = ptr_align(p.A, p.a_ld);
     p.b_align = ptr_align(p.B, p.b_ld);
@@ -1891,6 +1982,7 @@ int avec_gemm_tc(const avec_gemm_args* a, cudaStream_t st) {
         }
         p.epi_fast = ok && al >= 8 ? (al >= 16 ? 2 : 1) : 0;
     }
+    if (dc && (!p.epi_fast || p.b_kind != OP_TMA_K)) return AVEC_ERR_UNSUPPORTED;
     p.grid_m = grid_m; p.grid_n = cdiv(a->N, p.BN); p.splits = split;
     const long long tiles = (long long)p.grid_m * p.grid_n * p.splits;
     if (tiles > 0x7fffffffLL) return AVEC_ERR_INVALID;

@@ -1,5 +1,7 @@
 """Tensor-level wrappers over the C ABI: they take torch CUDA tensors, allocate outputs with torch (device memory and
 streams are the only things PyTorch provides here) and launch the sm_100a kernels on the current stream."""
+import os
+
 import torch
 
 from . import _lib as L
@@ -186,13 +188,16 @@ def conv_fwd(x, wp, g, bias=None, epi=L.EPI_LINEAR, colstats=None, aux=None):
     return out
 
 
+DGRAD_CLASSES = os.environ.get("AVEC_DGRAD_CLASSES", "1") != "0"
+
+
 def conv_dgrad(dy, wd, g, epi=L.EPI_LINEAR, aux=None):
     """dy [sites_out, Co], wd [C, taps*Co] -> dx [sites_in, C] (optionally + aux: merging two gradient branches)."""
     _cuda(dy, wd)
     if (g.sh > 1 or g.sw > 1) and g.sh == g.sw and g.KT == 1 and g.Ti == 1 and dy.dtype == torch.bfloat16 and GEMM_IMPL != L.IMPL_SIMT \
-            and g.C % 64 == 0 and g.Co % 64 == 0:
-        # strided conv: insert zeros into dY and run the stride-1 TMA dgrad (4x redundant MMAs but tensor-core fed by
-        # TMA; the exact alternative - one launch per output parity class - is future work)
+            and g.C % 64 == 0 and g.Co % 64 == 0 and not (g.KH == 3 and g.KW == 3 and g.sh == 2 and DGRAD_CLASSES):
+        # strided 1x1 conv (ResNet shortcuts): insert zeros into dY and run the stride-1 TMA dgrad.  Stride-2 3x3 convs go
+        # straight to avec_gemm, which runs one exact launch per output parity class (9 tap-GEMMs instead of 36)
         up = torch.empty((g.N * g.Hi * g.Wi, g.Co), device=dy.device, dtype=dy.dtype)
         L.check(L.load().avec_zero_upsample(dy.data_ptr(), up.data_ptr(), g.N, g.Ho, g.Wo, g.Hi, g.Wi, g.Co, g.sh, _dt(dy), _stream()),
                 "avec_zero_upsample")

@@ -59,7 +59,7 @@ def test_linear_fwd_dgrad_wgrad(impl, dtype, tol, M, K, N):
 
 CONVS = [  # N, H, W, Cin, Cout, k, stride
     (3, 8, 8, 64, 64, 3, 1), (37, 3, 3, 512, 512, 3, 1), (7, 6, 6, 256, 256, 3, 1), (3, 11, 11, 128, 128, 3, 1), (2, 22, 22, 64, 64, 3, 1), (2, 11, 11, 64, 128, 3, 2), (3, 6, 6, 128, 256, 3, 2), (5, 3, 3, 512, 512, 3, 1),
-    (2, 11, 11, 64, 128, 1, 2), (4, 22, 22, 64, 64, 3, 1),
+    (2, 11, 11, 64, 128, 1, 2), (4, 22, 22, 64, 64, 3, 1), (2, 22, 22, 64, 128, 3, 2), (5, 6, 6, 256, 512, 3, 2), (17, 6, 6, 256, 512, 3, 2),
 ]
 
 
@@ -94,6 +94,23 @@ def test_conv2d_fwd_dgrad_wgrad(impl, dtype, tol, N, H, W, Ci, Co, k, s):
     finally:
         ops.set_gemm_impl("auto")
         ops.set_tma(True)
+
+
+@pytest.mark.parametrize("N,H,W,Ci,Co", [(3, 22, 22, 64, 128), (4, 11, 11, 128, 256), (20, 6, 6, 256, 512), (2, 12, 10, 64, 64)])
+def test_strided_dgrad_parity_classes_with_residual(N, H, W, Ci, Co):
+    """stride-2 3x3 dgrad as four exact parity-class launches (tap table + scattered output rows), residual epilogue"""
+    bf = torch.bfloat16
+    g = ops.make_geom(N, 1, H, W, Ci, Co, (1, 3, 3), (1, 2, 2), (0, 1, 1))
+    w = (_rand(Co, Ci, 3, 3, seed=2) / (Ci * 9) ** 0.5).to(bf)
+    wd = w.permute(1, 2, 3, 0).reshape(Ci, -1).contiguous()
+    dy = _rand(N * g.Ho * g.Wo, Co, dtype=bf, seed=3)
+    aux = _rand(N * H * W, Ci, dtype=bf, seed=4)
+    xr = torch.zeros(N, Ci, H, W, device=DEV, requires_grad=True)
+    yr = F.conv2d(F.pad(xr, (1, 1, 1, 1)), w.float(), None, stride=2)
+    yr.backward(dy.float().view(N, g.Ho, g.Wo, Co).permute(0, 3, 1, 2))
+    want = xr.grad.permute(0, 2, 3, 1).reshape(-1, Ci)
+    _close(ops.conv_dgrad(dy, wd, g), want, 1e-2)
+    _close(ops.conv_dgrad(dy, wd, g, epi=L.EPI_RESIDUAL, aux=aux), want + aux.float(), 1e-2)
 
 
 @pytest.mark.parametrize("impl,dtype,tol", [("simt", torch.float32, 1e-5), ("tcgen05", torch.bfloat16, 1e-2)])
