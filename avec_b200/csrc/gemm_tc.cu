@@ -1619,6 +1619,133 @@ __global__ void __launch_bounds__(ST_WG_THREADS, 1) stem3d_wgrad_kernel(const __
     if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
+// =====================================================================================================================
+// Weight gradient of the 64 -> 64 channel 3x3 stride-1 convolutions (ResNet stage 1: 3.1 M sites at B = 64, the largest
+// reduction of the model).  As a generic 128 x 128-tile GEMM this launch re-reads X once per filter tap and dY once per column
+// block from L2 (1.3 ms, L2 -> SMEM bound).  Here one persistent CTA keeps the COMPLETE dW (64 x 576 fp32) in tensor memory and
+// streams every site exactly once: per tile of BH image rows a TMA box of dY on the (W+2)-wide halo grid (columns W, W+1 and
+// rows past the image are zero-filled by the TMA unit) and ONE halo tile of X ((BH+2) x (W+2) sites x 64 channels).  Filter
+// tap (kh, kw) is the halo tile read from row kh*(W+2)+kw on (128-byte row offsets keep the 128B-swizzle phase), so the 9
+// taps cost no extra traffic.  MMA shape: A = X halo, MN-major, M = 128 = two taps (kh, kh+1) x 64 input channels (the second
+// 64-wide group starts (W+2) rows further: LBO = (W+2)*128 bytes, a multiple of the 1024-byte swizzle atom because
+// (W+2) % 8 == 0), B = dY, MN-major, N = 64 output channels, K = 128 halo sites per tile; six accumulators of 64 columns:
+// (kh 0|1, kw 0..2) and (kh 1|2, kw 0..2) - the kh = 1 taps are computed twice so that no operand ever reads past the tile.
+// warps 0-3: final flush (fp32 atomics into dW[co][tap*64+ci]); warp 4: MMA issuer + TMEM; warp 5: TMA producer.
+constexpr int WH_THREADS = 192;
+constexpr int WH_Y_BYTES = 128 * 128;      // dY stage: 128 K rows (rows >= BH*(W+2) stay zero)
+constexpr int WH_X_BYTES = 184 * 128;      // X halo stage: <= 168 rows from TMA + zero tail read by the last taps' K padding
+constexpr int WH_STAGE_BYTES = 40960;
+constexpr int WH_STAGES = 4;
+constexpr size_t WH_SMEM = 1024 + (size_t)WH_STAGES * WH_STAGE_BYTES + 1024;
+
+struct WgHaloParams {
+    int N, H, W, W2, BH, tph, total_tiles;
+    int y_tx, x_tx;
+    float alpha;
+    float* dw;    // [64][576] fp32
+};
+
+__global__ void __launch_bounds__(WH_THREADS, 1) wgrad_halo64_kernel(const __grid_constant__ WgHaloParams p, const __grid_constant__ CUtensorMap mapY,
+                                                                    const __grid_constant__ CUtensorMap mapX) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* ctrl = smem + (size_t)WH_STAGES * WH_STAGE_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(ctrl);   // [4]
+    uint64_t* empty = full + WH_STAGES;                     // [4]
+    uint64_t* done = empty + WH_STAGES;                     // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 2);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    if (tid == 0) {
+        for (int i = 0; i < WH_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(done, 1);
+        fence_barrier_init();
+        tma_prefetch_desc(&mapY);
+        tma_prefetch_desc(&mapX);
+    }
+    if (warp == 4) tmem_alloc(tmem_slot, 512);
+    // rows the TMA boxes never write must read as zeros (K padding of dY, tail of the halo tile)
+    for (int i = tid; i < WH_STAGES * WH_STAGE_BYTES / 16; i += WH_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const bool any_tile = (int)blockIdx.x < p.total_tiles;
+
+    if (warp < 4) {
+        // ===================== final flush: lane = (tap row g, input channel c), columns = output channels =====================
+        if (any_tile) {
+            mbar_wait(done, 0);
+            tc_fence_after();
+            const int row = warp * 32 + lane, g = row >> 6, c = row & 63;
+            for (int q = 0; q < 6; ++q) {
+                const int set = q / 3, kw = q - set * 3, kh = set + g;
+                if (set == 1 && g == 0) continue;   // kh = 1 duplicate (warp-uniform: g is fixed per warp)
+                float* dst = p.dw + (size_t)(kh * 3 + kw) * 64 + c;
+                for (int c0 = 0; c0 < 64; c0 += 16) {
+                    float v[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(q * 64 + c0), v);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) atomicAdd(dst + (size_t)(c0 + i) * 576, p.alpha * v[i]);
+                }
+            }
+        }
+        tc_fence_before();
+    } else if (warp == 4) {
+        // ===================== MMA issuer =====================
+        const uint32_t idesc = make_idesc(64, 1, 1);
+        const uint64_t a_desc0 = make_smem_desc(0, (uint32_t)p.W2 * 128u, 1024);   // X halo: second 64-row M group = next filter row
+        const uint64_t b_desc0 = make_smem_desc(0, WH_Y_BYTES, 1024);              // dY: single 64-wide N group
+        const uint32_t a_hi = (uint32_t)(a_desc0 >> 32), b_hi = (uint32_t)(b_desc0 >> 32);
+        const uint32_t base16 = smem_u32(smem) >> 4;
+        int j = 0, st = 0;
+        uint32_t ph = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++j) {
+            mbar_wait(&full[st], ph);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t y16 = base16 + (uint32_t)st * (WH_STAGE_BYTES >> 4);
+                const uint32_t x16 = y16 + (WH_Y_BYTES >> 4);
+#pragma unroll
+                for (int q = 0; q < 6; ++q) {
+                    const int set = q / 3, kw = q - set * 3;
+                    const uint32_t a0 = (uint32_t)a_desc0 + x16 + (uint32_t)((set * p.W2 + kw) * 128 >> 4);
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(q * 64);
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks)
+                        umma_f16(d_tmem, ((uint64_t)a_hi << 32) | (a0 + (uint32_t)ks * (2048u >> 4)),
+                                 ((uint64_t)b_hi << 32) | ((uint32_t)b_desc0 + y16 + (uint32_t)ks * (2048u >> 4)), idesc, (j > 0 || ks > 0) ? 1u : 0u);
+                }
+                umma_commit(&empty[st]);
+            }
+            __syncwarp();
+            if (++st == WH_STAGES) { st = 0; ph ^= 1u; }
+        }
+        if (any_tile && elect_one()) umma_commit(done);
+        __syncwarp();
+        tc_fence_before();
+    } else {
+        // ===================== TMA producer =====================
+        int st = 0;
+        uint32_t ph = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            mbar_wait(&empty[st], ph ^ 1u);
+            if (elect_one()) {
+                const int n = t / p.tph, h0 = (t - n * p.tph) * p.BH;
+                const uint32_t ydst = smem_u32(smem) + (uint32_t)st * WH_STAGE_BYTES;
+                mbar_expect_tx(&full[st], (uint32_t)(p.y_tx + p.x_tx));
+                tma_load_4d(ydst, &mapY, &full[st], 0, 0, h0, n);
+                tma_load_4d(ydst + WH_Y_BYTES, &mapX, &full[st], 0, -1, h0 - 1, n);
+            }
+            __syncwarp();
+            if (++st == WH_STAGES) { st = 0; ph ^= 1u; }
+        }
+    }
+    __syncthreads();
+    if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
 // tile width: as wide as possible (<= 256, multiple of 16, awkward N such as 180 / 720 / 1080 split evenly), but narrow
 // enough that small problems still put >= ~100 CTAs on the 148 SMs (never below 64 columns)
 int pick_bn(int N, int mtiles) {
@@ -1738,7 +1865,50 @@ static bool dgrad_classes_ok(const avec_gemm_args* a) {
     return (reinterpret_cast<uintptr_t>(a->A) % 16) == 0 && (reinterpret_cast<uintptr_t>(a->B) % 16) == 0;
 }
 
+// ---- 64-channel 3x3 stride-1 wgrad on halo tiles (see wgrad_halo64_kernel)
+static bool wgrad_halo_ok(const avec_gemm_args* a) {
+    const avec_conv_geom& g = a->g;
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("AVEC_WGRAD_HALO"); on = e ? atoi(e) : 1; }
+    if (!on || a->mode != AVEC_GEMM_CONV_WGRAD || !g_tma_enabled || get_encode() == nullptr || a->ab_dtype != AVEC_BF16) return false;
+    if (!(g.KT == 1 && g.Ti == 1 && g.st == 1 && g.sh == 1 && g.sw == 1 && g.KH == 3 && g.KW == 3 && g.ph == 1 && g.pw == 1)) return false;
+    if (g.C != 64 || g.Co != 64 || g.Ho != g.Hi || g.Wo != g.Wi) return false;
+    const int W2 = g.Wi + 2;
+    if (W2 % 8 != 0 || W2 > 64 || g.Hi < 1) return false;
+    const int BH = 128 / W2;
+    if (BH < 1 || (BH + 2) * W2 > 168) return false;
+    if (a->epi != AVEC_EPI_ACCUM || a->out_dtype != AVEC_F32 || a->ldo != 576 || a->bias || a->colstats) return false;
+    return (reinterpret_cast<uintptr_t>(a->A) % 16) == 0 && (reinterpret_cast<uintptr_t>(a->B) % 16) == 0;
+}
+
+static int wgrad_halo_launch(const avec_gemm_args* a, cudaStream_t st) {
+    const avec_conv_geom& g = a->g;
+    WgHaloParams p;
+    memset(&p, 0, sizeof(p));
+    p.N = g.N; p.H = g.Hi; p.W = g.Wi; p.W2 = g.Wi + 2; p.BH = 128 / p.W2; p.tph = cdiv(p.H, p.BH);
+    const long long tiles = (long long)p.N * p.tph;
+    if (tiles > 0x7fffffffLL) return AVEC_ERR_INVALID;
+    p.total_tiles = (int)tiles;
+    p.y_tx = p.BH * p.W2 * 128; p.x_tx = (p.BH + 2) * p.W2 * 128;
+    p.alpha = a->alpha; p.dw = reinterpret_cast<float*>(a->out);
+    CUtensorMap mapY, mapX;
+    cuuint64_t d[4] = {64, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.N};
+    cuuint64_t sb[3] = {128, (cuuint64_t)p.W * 128, (cuuint64_t)p.W * p.H * 128};
+    cuuint32_t boxY[4] = {64, (cuuint32_t)p.W2, (cuuint32_t)p.BH, 1}, boxX[4] = {64, (cuuint32_t)p.W2, (cuuint32_t)(p.BH + 2), 1};
+    if (!encode_map(&mapY, a->A, 4, d, sb, boxY) || !encode_map(&mapX, a->B, 4, d, sb, boxX)) return AVEC_ERR_DRIVER;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(wgrad_halo64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WH_SMEM) != cudaSuccess) return AVEC_ERR_LAUNCH;
+        attr_set = true;
+    }
+    const int ctas = std::min(p.total_tiles, num_sms_cached());
+    wgrad_halo64_kernel<<<ctas, WH_THREADS, WH_SMEM, st>>>(p, mapY, mapX);
+    AVEC_LAUNCH_CHECK();
+    return AVEC_OK;
+}
+
 int avec_gemm_tc(const avec_gemm_args* a, cudaStream_t st) {
+    if (wgrad_halo_ok(a)) return wgrad_halo_launch(a, st);
     if (dgrad_classes_ok(a)) {
         for (int ca = 0; ca < 2; ++ca)
             for (int cb = 0; cb < 2; ++cb) {

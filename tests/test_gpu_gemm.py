@@ -60,6 +60,7 @@ def test_linear_fwd_dgrad_wgrad(impl, dtype, tol, M, K, N):
 CONVS = [  # N, H, W, Cin, Cout, k, stride
     (3, 8, 8, 64, 64, 3, 1), (37, 3, 3, 512, 512, 3, 1), (7, 6, 6, 256, 256, 3, 1), (3, 11, 11, 128, 128, 3, 1), (2, 22, 22, 64, 64, 3, 1), (2, 11, 11, 64, 128, 3, 2), (3, 6, 6, 128, 256, 3, 2), (5, 3, 3, 512, 512, 3, 1),
     (2, 11, 11, 64, 128, 1, 2), (4, 22, 22, 64, 64, 3, 1), (2, 22, 22, 64, 128, 3, 2), (5, 6, 6, 256, 512, 3, 2), (17, 6, 6, 256, 512, 3, 2),
+    (3, 14, 14, 64, 64, 3, 1), (2, 9, 6, 64, 64, 3, 1), (150, 22, 22, 64, 64, 3, 1),   # halo-tile wgrad geometries ((W+2) % 8 == 0)
 ]
 
 
