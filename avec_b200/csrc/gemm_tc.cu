@@ -682,14 +682,14 @@ __device__ __forceinline__ void epilogue_fast(const TcParams& p, const EpiParams
     const float alpha = ep.alpha;
     const int rows_left = ti.rows_valid - warp * 32;   // valid rows of this warp's quarter (may be <= 0 or >= 32)
     // output row of tile row r: contiguous, or scattered through the row table (parity classes of strided dgrads)
-    auto out_row = [&](int rr) -> size_t {
+    auto out_row = [&](int rr) -> long long {   // < 0: the tile row holds no output (halo-grid columns past the image)
         const int r = warp * 32 + rr;
         if (p.rm_on) {
             int rel;
             asm volatile("ld.shared.b32 %0, [%1];" : "=r"(rel) : "r"(rowrel_sa + (uint32_t)r * 4u) : "memory");
-            return (size_t)(ti.row_base + rel);
+            return rel == (int)0x80000000 ? -1LL : ti.row_base + rel;
         }
-        return (size_t)(ti.row_base + r);
+        return ti.row_base + r;
     };
     for (int c0 = 0; c0 < BN; c0 += 64) {
         const int ncol = min(64, BN - c0);   // multiple of 16
@@ -705,7 +705,7 @@ __device__ __forceinline__ void epilogue_fast(const TcParams& p, const EpiParams
             for (int u = 0; u < 4; ++u) {
                 const int rr = u * 4 + rs;
                 xa[u] = make_uint4(0u, 0u, 0u, 0u);
-                if (aux_on && col_ok && rr < rows_left) xa[u] = ldg_bf16x8<AL16>(auxp + out_row(rr) * ep.ldaux + gc);
+                if (aux_on && col_ok && rr < rows_left) { const long long ro = out_row(rr); if (ro >= 0) xa[u] = ldg_bf16x8<AL16>(auxp + (size_t)ro * ep.ldaux + gc); }
             }
         }
         // ---- row domain: TMEM -> registers -> staging
@@ -728,7 +728,7 @@ __device__ __forceinline__ void epilogue_fast(const TcParams& p, const EpiParams
             for (int u = 0; u < 4; ++u) {
                 const int rr = (4 + u) * 4 + rs;
                 xb[u] = make_uint4(0u, 0u, 0u, 0u);
-                if (aux_on && col_ok && rr < rows_left) xb[u] = ldg_bf16x8<AL16>(auxp + out_row(rr) * ep.ldaux + gc);
+                if (aux_on && col_ok && rr < rows_left) { const long long ro = out_row(rr); if (ro >= 0) xb[u] = ldg_bf16x8<AL16>(auxp + (size_t)ro * ep.ldaux + gc); }
             }
         }
         __syncwarp();
@@ -754,7 +754,9 @@ __device__ __forceinline__ void epilogue_fast(const TcParams& p, const EpiParams
             for (int u = 0; u < 4; ++u) {
                 const int rr = (g * 4 + u) * 4 + rs;
                 if (!(col_ok && rr < rows_left)) continue;
-                const size_t row = out_row(rr);
+                const long long row_ = out_row(rr);
+                if (row_ < 0) continue;
+                const size_t row = (size_t)row_;
                 float a[8] = {t[2 * u].x + b[0], t[2 * u].y + b[1], t[2 * u].z + b[2], t[2 * u].w + b[3],
                               t[2 * u + 1].x + b[4], t[2 * u + 1].y + b[5], t[2 * u + 1].z + b[6], t[2 * u + 1].w + b[7]};
                 const size_t oi = row * ep.ldo + gc;
@@ -1746,6 +1748,148 @@ __global__ void __launch_bounds__(WH_THREADS, 1) wgrad_halo64_kernel(const __gri
     if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
+// =====================================================================================================================
+// Forward / data gradient of the 64 -> 64 channel 3x3 stride-1 convolutions (ResNet stage 1) on halo tiles.  The generic
+// kernel loads one shifted copy of the input tile per filter tap plus the tap's weights per k-block (198 KB from L2 per
+// 110 output sites - L2 -> SMEM bound) and pays one producer/consumer handshake per 128 tensor-pipe cycles.  Here the 72 KB
+// of weights stay resident in shared memory for the whole persistent CTA, ONE halo tile ((BH+2) x (W+2) sites x 64 ch,
+// 21 KB) is loaded per output tile and all 36 MMAs of the tile (9 taps x 4 K-steps; tap = 128-byte row offset into the halo
+// tile) are issued behind a single barrier wait.  Accumulator rows live on the (W+2)-wide halo grid; the fast epilogue maps
+// them to output rows through a small table and skips the two pad columns.  Two epilogue warpgroups alternate tiles (one
+// TMEM accumulator each), because at 64 columns a tile is only ~1150 tensor-pipe cycles - about one epilogue.
+// warps 0-3 / 4-7: epilogue groups, warp 8: MMA issuer + TMEM + weight TMA, warp 9: halo TMA producer
+constexpr int CH_THREADS = 320;
+constexpr int CH_W_BYTES = 9 * 64 * 128;      // 73728
+constexpr int CH_X_BYTES = 184 * 128;         // halo stage (168 rows from TMA; rows up to 177 are read by discarded accumulator rows)
+constexpr int CH_STAGES = 3;
+constexpr size_t CH_SMEM = 1024 + CH_W_BYTES + (size_t)CH_STAGES * CH_X_BYTES + 2 * STG_BYTES + 1024;
+
+struct ConvHaloParams {
+    int N, H, W, W2, BH, tph, total_tiles, x_tx, dgrad;
+    TcParams tc;   // BN = N = 64, epilogue parameters, rm_on = 1
+};
+
+__global__ void __launch_bounds__(CH_THREADS, 1) conv3x3_halo64_kernel(const __grid_constant__ ConvHaloParams p, const __grid_constant__ CUtensorMap mapX,
+                                                                      const __grid_constant__ CUtensorMap mapW) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* w_s = smem;
+    uint8_t* x_s = w_s + CH_W_BYTES;
+    float* stg_all = reinterpret_cast<float*>(x_s + CH_STAGES * CH_X_BYTES);
+    uint8_t* ctrl = reinterpret_cast<uint8_t*>(stg_all) + 2 * STG_BYTES;
+    uint64_t* x_full = reinterpret_cast<uint64_t*>(ctrl);     // [3]
+    uint64_t* x_empty = x_full + 4;                             // [3]
+    uint64_t* accum_full = x_empty + 4;                         // [2]
+    uint64_t* accum_empty = accum_full + 2;                     // [2]
+    uint64_t* w_full = accum_empty + 2;                         // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 2);
+    float* bias_s = reinterpret_cast<float*>(ctrl + 128);       // [64]
+    int* rowrel = reinterpret_cast<int*>(ctrl + 128 + 256);     // [128]
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    if (tid == 0) {
+        for (int i = 0; i < CH_STAGES; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&accum_full[i], 1); mbar_init(&accum_empty[i], 128); }
+        mbar_init(w_full, 1);
+        fence_barrier_init();
+        tma_prefetch_desc(&mapX);
+        tma_prefetch_desc(&mapW);
+    }
+    if (warp == 8) tmem_alloc(tmem_slot, 128);
+    if (tid < 64) bias_s[tid] = p.tc.ep.bias ? p.tc.ep.bias[tid] : 0.0f;
+    if (tid < 128) {
+        const int hh = tid / p.W2, ww = tid - hh * p.W2;
+        rowrel[tid] = (ww < p.W && hh < p.BH) ? hh * p.W + ww : (int)0x80000000;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 8) {
+        // ===================== epilogue group grp handles tiles j with (j & 1) == grp =====================
+        const int grp = warp >> 2, w4 = warp & 3;
+        EpiParams ep = p.tc.ep;
+        ep.bias = nullptr;
+        const uint32_t stg_s = smem_u32(stg_all + (size_t)grp * (STG_BYTES / 4) + w4 * STG_WARP), bias_sa = smem_u32(bias_s), rowrel_sa = smem_u32(rowrel);
+        int j = grp;
+        for (int t = blockIdx.x + grp * gridDim.x; t < p.total_tiles; t += 2 * gridDim.x, j += 2) {
+            const int n = t / p.tph, h0 = (t - n * p.tph) * p.BH;
+            TileInfo ti;
+            ti.mtile = t; ti.n0 = 0; ti.z = 0; ti.kb_begin = 0; ti.nkb = 0; ti.m0 = 0;
+            ti.row_base = ((long long)n * p.H + h0) * p.W;
+            ti.rows_valid = min(p.BH, p.H - h0) * p.W2;
+            mbar_wait(&accum_full[grp], (uint32_t)((j >> 1) & 1));
+            tc_fence_after();
+            const uint32_t lane_addr = tmem_base + ((uint32_t)(w4 * 32) << 16) + (uint32_t)(grp * 64);
+            float* stats_dst = ep.colstats ? ep.colstats + (size_t)(t % AVEC_STATS_REPLICAS) * 2 * 64 : nullptr;
+            if (ep.kind == AVEC_EPI_RESIDUAL) epilogue_fast<AVEC_EPI_RESIDUAL, false, true>(p.tc, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, w4, lane, rowrel_sa);
+            else if (ep.colstats) epilogue_fast<AVEC_EPI_LINEAR, true, true>(p.tc, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, w4, lane, rowrel_sa);
+            else epilogue_fast<AVEC_EPI_LINEAR, false, true>(p.tc, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, w4, lane, rowrel_sa);
+            tc_fence_before();
+            mbar_arrive(&accum_empty[grp]);
+        }
+        tc_fence_before();
+    } else if (warp == 8) {
+        // ===================== weight load + MMA issuer =====================
+        if (elect_one()) {
+            mbar_expect_tx(w_full, CH_W_BYTES);
+            for (int tap = 0; tap < 9; ++tap) tma_load_2d(smem_u32(w_s) + (uint32_t)tap * 8192u, &mapW, w_full, tap * 64, 0);
+        }
+        __syncwarp();
+        mbar_wait(w_full, 0);
+        tc_fence_after();
+        const uint32_t idesc = make_idesc(64, 0, 0);
+        const uint64_t desc0 = make_smem_desc(0, 16, 1024);
+        const uint32_t d_hi = (uint32_t)(desc0 >> 32), d_lo = (uint32_t)desc0;
+        const uint32_t w16 = smem_u32(w_s) >> 4, x16_0 = smem_u32(x_s) >> 4;
+        int j = 0, st = 0;
+        uint32_t ph = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++j) {
+            const int buf = j & 1;
+            mbar_wait(&accum_empty[buf], (uint32_t)(((j >> 1) & 1) ^ 1));
+            mbar_wait(&x_full[st], ph);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 64);
+                const uint32_t x16 = x16_0 + (uint32_t)st * (CH_X_BYTES >> 4);
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+                    const int kh = tap / 3, kw = tap - kh * 3;
+                    const int th = p.dgrad ? 2 - kh : kh, tw = p.dgrad ? 2 - kw : kw;
+                    const uint32_t a0 = d_lo + x16 + (uint32_t)((th * p.W2 + tw) * 128 >> 4);
+                    const uint32_t b0 = d_lo + w16 + (uint32_t)tap * (8192u >> 4);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                        umma_f16(d_tmem, ((uint64_t)d_hi << 32) | (a0 + (uint32_t)ks * 2u), ((uint64_t)d_hi << 32) | (b0 + (uint32_t)ks * 2u), idesc,
+                                 (tap > 0 || ks > 0) ? 1u : 0u);
+                }
+                umma_commit(&x_empty[st]);
+                umma_commit(&accum_full[buf]);
+            }
+            __syncwarp();
+            if (++st == CH_STAGES) { st = 0; ph ^= 1u; }
+        }
+        tc_fence_before();
+    } else {
+        // ===================== halo TMA producer =====================
+        int st = 0;
+        uint32_t ph = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            mbar_wait(&x_empty[st], ph ^ 1u);
+            if (elect_one()) {
+                const int n = t / p.tph, h0 = (t - n * p.tph) * p.BH;
+                mbar_expect_tx(&x_full[st], (uint32_t)p.x_tx);
+                tma_load_4d(smem_u32(x_s) + (uint32_t)st * CH_X_BYTES, &mapX, &x_full[st], 0, -1, h0 - 1, n);
+            }
+            __syncwarp();
+            if (++st == CH_STAGES) { st = 0; ph ^= 1u; }
+        }
+    }
+    __syncthreads();
+    if (warp == 8) { tc_fence_after(); tmem_dealloc(tmem_base, 128); }
+}
+
 // tile width: as wide as possible (<= 256, multiple of 16, awkward N such as 180 / 720 / 1080 split evenly), but narrow
 // enough that small problems still put >= ~100 CTAs on the 148 SMs (never below 64 columns)
 int pick_bn(int N, int mtiles) {
@@ -1907,8 +2051,56 @@ static int wgrad_halo_launch(const avec_gemm_args* a, cudaStream_t st) {
     return AVEC_OK;
 }
 
+// ---- 64-channel 3x3 stride-1 forward / dgrad on halo tiles (see conv3x3_halo64_kernel)
+static bool conv_halo_ok(const avec_gemm_args* a) {
+    const avec_conv_geom& g = a->g;
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("AVEC_CONV_HALO64"); on = e ? atoi(e) : 1; }
+    if (!on || (a->mode != AVEC_GEMM_CONV_FWD && a->mode != AVEC_GEMM_CONV_DGRAD) || !g_tma_enabled || get_encode() == nullptr) return false;
+    if (!(g.KT == 1 && g.Ti == 1 && g.st == 1 && g.sh == 1 && g.sw == 1 && g.KH == 3 && g.KW == 3 && g.ph == 1 && g.pw == 1)) return false;
+    if (g.C != 64 || g.Co != 64 || g.Ho != g.Hi || g.Wo != g.Wi || a->ab_dtype != AVEC_BF16 || a->out_dtype != AVEC_BF16) return false;
+    const int W2 = g.Wi + 2;
+    if (W2 > 64 || g.Hi * g.Wi <= 128) return false;   // small images: whole-image tiles of the generic kernel are better
+    const int BH = 128 / W2;
+    if (BH < 1 || (BH + 2) * W2 > 168) return false;
+    if (a->epi != AVEC_EPI_LINEAR && a->epi != AVEC_EPI_RESIDUAL) return false;
+    if (a->out2 || a->alpha != 1.0f || (a->epi == AVEC_EPI_RESIDUAL && (!a->aux || a->aux_dtype != AVEC_BF16 || a->colstats))) return false;
+    if (ptr_align(a->out, a->ldo) < 16 || (a->aux && ptr_align(a->aux, a->ldaux) < 16) || (a->colstats && (reinterpret_cast<uintptr_t>(a->colstats) % 16) != 0)) return false;
+    return (reinterpret_cast<uintptr_t>(a->A) % 16) == 0 && (reinterpret_cast<uintptr_t>(a->B) % 16) == 0 && a->K == 576;
+}
+
+static int conv_halo_launch(const avec_gemm_args* a, cudaStream_t st) {
+    const avec_conv_geom& g = a->g;
+    ConvHaloParams p;
+    memset(&p, 0, sizeof(p));
+    p.N = g.N; p.H = g.Hi; p.W = g.Wi; p.W2 = g.Wi + 2; p.BH = 128 / p.W2; p.tph = cdiv(p.H, p.BH);
+    const long long tiles = (long long)p.N * p.tph;
+    if (tiles > 0x7fffffffLL) return AVEC_ERR_INVALID;
+    p.total_tiles = (int)tiles;
+    p.x_tx = (p.BH + 2) * p.W2 * 128;
+    p.dgrad = a->mode == AVEC_GEMM_CONV_DGRAD ? 1 : 0;
+    p.tc.BN = 64; p.tc.N = 64; p.tc.M = a->M; p.tc.epi_fast = 2; p.tc.rm_on = 1;
+    p.tc.ep = make_epi(a);
+    CUtensorMap mapX, mapW;
+    cuuint64_t d[4] = {64, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.N};
+    cuuint64_t sb[3] = {128, (cuuint64_t)p.W * 128, (cuuint64_t)p.W * p.H * 128};
+    cuuint32_t boxX[4] = {64, (cuuint32_t)p.W2, (cuuint32_t)(p.BH + 2), 1};
+    cuuint64_t dw_[2] = {576, 64}; cuuint64_t sw_[1] = {576 * 2}; cuuint32_t boxW[2] = {64, 64};
+    if (!encode_map(&mapX, a->A, 4, d, sb, boxX) || !encode_map(&mapW, a->B, 2, dw_, sw_, boxW)) return AVEC_ERR_DRIVER;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(conv3x3_halo64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CH_SMEM) != cudaSuccess) return AVEC_ERR_LAUNCH;
+        attr_set = true;
+    }
+    const int ctas = std::min(p.total_tiles, num_sms_cached());
+    conv3x3_halo64_kernel<<<ctas, CH_THREADS, CH_SMEM, st>>>(p, mapX, mapW);
+    AVEC_LAUNCH_CHECK();
+    return AVEC_OK;
+}
+
 int avec_gemm_tc(const avec_gemm_args* a, cudaStream_t st) {
     if (wgrad_halo_ok(a)) return wgrad_halo_launch(a, st);
+    if (conv_halo_ok(a)) return conv_halo_launch(a, st);
     if (dgrad_classes_ok(a)) {
         for (int ca = 0; ca < 2; ++ca)
             for (int cb = 0; cb < 2; ++cb) {
