@@ -10,9 +10,9 @@ namespace {
 constexpr int DW_TO = 8;     // output frames per CTA (short tiles: these launches are latency-, not bandwidth-bound)
 constexpr int DW_CH = 128;   // channels per CTA (= threads)
 constexpr int DW_MAXK = 15;
-// the backward accumulates 16 same-address atomics per thread (dW, db): longer tiles = 4x fewer of them (they, not the
-// streams, bounded the kernel at 8-frame tiles)
-constexpr int DW_TO_BWD = 32;
+// backward tile: 16 output frames (the kernel is instruction bound: the 14-frame halo is amortised over twice as many outputs as
+// in the forward, while the grid still fills the 148 SMs)
+constexpr int DW_TO_BWD = 16;
 
 template <typename T>
 __global__ void __launch_bounds__(DW_CH) glu_dwconv_fwd_kernel(const T* __restrict__ pre, const float* __restrict__ w,
@@ -54,11 +54,12 @@ __global__ void __launch_bounds__(DW_CH) glu_dwconv_fwd_kernel(const T* __restri
     if (stats) { atomicAdd(stats + c, s1); atomicAdd(stats + C + c, s2); }
 }
 
-template <typename T>
+template <typename T, int STRIDE>
 __global__ void __launch_bounds__(DW_CH) glu_dwconv_bwd_kernel(const T* __restrict__ du, const T* __restrict__ pre,
                                                                const float* __restrict__ w, T* __restrict__ dpre,
                                                                float* __restrict__ dw, float* __restrict__ db, int Tn, int To,
-                                                               int C, int ksize, int stride, int pad) {
+                                                               int C, int ksize, int stride_rt, int pad) {
+    const int stride = STRIDE > 0 ? STRIDE : stride_rt;   // compile-time stride (1 / 2): no division in the tap loops
     extern __shared__ float sm[];
     const int b = blockIdx.z, c = blockIdx.y * DW_CH + threadIdx.x;
     const int to0 = blockIdx.x * DW_TO_BWD;
@@ -112,13 +113,22 @@ __global__ void __launch_bounds__(DW_CH) glu_dwconv_bwd_kernel(const T* __restri
         int t = t0 + j;
         if (t >= Tn) break;
         float dg = 0.0f;
+        if (STRIDE == 1) {
+            // dg[t] = sum_k w[k] du[t + pad - k]; rows outside [0, To) of the staged tile are zero
 #pragma unroll
-        for (int k = 0; k < DW_MAXK; ++k) {
-            if (k < ksize) {
-                int a = t + pad - k;
-                if (a >= 0 && a % stride == 0) {
-                    int to = a / stride;
-                    if (to < To) dg = fmaf(wk[k], dsm[(to - d_lo) * DW_CH + threadIdx.x], dg);
+            for (int k = 0; k < DW_MAXK; ++k) {
+                const int to = t + pad - k;
+                if (k < ksize) dg = fmaf(wk[k], dsm[(to - d_lo) * DW_CH + threadIdx.x], dg);   // d_lo <= to <= d_hi by construction
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < DW_MAXK; ++k) {
+                if (k < ksize) {
+                    int a = t + pad - k;
+                    if (a >= 0 && a % stride == 0) {
+                        int to = a / stride;
+                        if (to < To) dg = fmaf(wk[k], dsm[(to - d_lo) * DW_CH + threadIdx.x], dg);
+                    }
                 }
             }
         }
@@ -157,7 +167,7 @@ extern "C" int avec_glu_dwconv_bwd(const void* du, const void* pre, const float*
     const int drows = DW_TO_BWD + (ksize + stride) / stride + 4;  // upper bound of d_hi - d_lo + 1 for any tile
     size_t smem = (size_t)(grows + drows) * DW_CH * sizeof(float);
     AVEC_DISPATCH_DTYPE(dtype, Tt, {
-        auto kfn = glu_dwconv_bwd_kernel<Tt>;
+        auto kfn = stride == 1 ? glu_dwconv_bwd_kernel<Tt, 1> : (stride == 2 ? glu_dwconv_bwd_kernel<Tt, 2> : glu_dwconv_bwd_kernel<Tt, 0>);
         if (smem > 48 * 1024 && cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return AVEC_ERR_LAUNCH;
         kfn<<<grid, DW_CH, smem, as_stream(stream)>>>((const Tt*)du, (const Tt*)pre, w, (Tt*)dpre, dw, db, T, To, C, ksize, stride, pad);
     });

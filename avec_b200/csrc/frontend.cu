@@ -119,6 +119,115 @@ __global__ void __launch_bounds__(256) im2col_c1_kernel(const T* __restrict__ x,
     }
 }
 
+
+// ---- audio stem: Conv2d(1 -> Co, 3x3, stride 2, pad 1) on the log-mel image (reference nnet/networks.py:359-368).  K = 9 with a
+// single input channel is far below a tensor-core tile and the op is bound by the [sites, Co] output write (185 MB at B = 64),
+// so it is a SIMT kernel: a thread owns 4 output channels (its 36 weights live in registers) and walks output sites; the
+// 9 taps of a site are broadcast loads, the 45 threads of a site store one contiguous 360-byte row.  BatchNorm column sums
+// (forward) and the weight gradient (backward: same walk, dY instead of the weights) are reduced per CTA, then by atomics.
+constexpr int S2_ROWS = 4;      // sites processed concurrently per CTA
+constexpr int S2_GROUPS = 64;   // channel groups of 4 per site row (Co <= 256)
+
+template <typename T>
+__device__ __forceinline__ void stem2d_taps(const T* __restrict__ x, int n, int ho, int wo, int H, int W, float (&t)[9]) {
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+            const int hi = 2 * ho + kh - 1, wi = 2 * wo + kw - 1;
+            t[kh * 3 + kw] = ((unsigned)hi < (unsigned)H && (unsigned)wi < (unsigned)W) ? ldf(x + ((size_t)n * H + hi) * W + wi) : 0.0f;
+        }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(S2_ROWS * S2_GROUPS) stem2d_fwd_kernel(const T* __restrict__ x, const T* __restrict__ w, const float* __restrict__ bias,
+                                                                        T* __restrict__ out, float* __restrict__ stats, int N, int H, int W, int Ho,
+                                                                        int Wo, int Co, long long sites, long long sites_per_cta) {
+    __shared__ float red[2][S2_ROWS][S2_GROUPS * 4];
+    const int grp = threadIdx.x % S2_GROUPS, row = threadIdx.x / S2_GROUPS;
+    const int c0 = grp * 4;
+    const bool cv = c0 < Co;
+    float wr[4][9], b4[4], s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        b4[j] = (cv && bias) ? bias[c0 + j] : 0.0f;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) wr[j][k] = cv ? ldf(w + (size_t)(c0 + j) * 9 + k) : 0.0f;
+    }
+    const long long sbeg = (long long)blockIdx.x * sites_per_cta, send = min(sites, sbeg + sites_per_cta);
+    for (long long s = sbeg + row; s < send; s += S2_ROWS) {
+        const int wo = (int)(s % Wo); const long long r = s / Wo; const int ho = (int)(r % Ho), n = (int)(r / Ho);
+        float t[9];
+        stem2d_taps(x, n, ho, wo, H, W, t);
+        if (cv) {
+            float y[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float a = b4[j];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) a = fmaf(wr[j][k], t[k], a);
+                y[j] = a; s1[j] += a; s2[j] += a * a;
+            }
+            store_vec<4>(out + (size_t)s * Co + c0, y);
+        }
+    }
+    if (stats) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { red[0][row][grp * 4 + j] = s1[j]; red[1][row][grp * 4 + j] = s2[j]; }
+        __syncthreads();
+        float* dst = stats + (size_t)(blockIdx.x % AVEC_STATS_REPLICAS) * 2 * Co;
+        for (int i = threadIdx.x; i < 2 * S2_GROUPS * 4; i += blockDim.x) {
+            const int q = i / (S2_GROUPS * 4), c = i % (S2_GROUPS * 4);
+            if (c < Co) {
+                float v = 0.f;
+#pragma unroll
+                for (int rr = 0; rr < S2_ROWS; ++rr) v += red[q][rr][c];
+                atomicAdd(dst + q * Co + c, v);
+            }
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(S2_ROWS * S2_GROUPS) stem2d_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dw, int N, int H,
+                                                                          int W, int Ho, int Wo, int Co, long long sites, long long sites_per_cta) {
+    __shared__ float red[S2_ROWS][S2_GROUPS * 4][9];
+    const int grp = threadIdx.x % S2_GROUPS, row = threadIdx.x / S2_GROUPS;
+    const int c0 = grp * 4;
+    const bool cv = c0 < Co;
+    float acc[4][9];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < 9; ++k) acc[j][k] = 0.0f;
+    const long long sbeg = (long long)blockIdx.x * sites_per_cta, send = min(sites, sbeg + sites_per_cta);
+    for (long long s = sbeg + row; s < send; s += S2_ROWS) {
+        const int wo = (int)(s % Wo); const long long r = s / Wo; const int ho = (int)(r % Ho), n = (int)(r / Ho);
+        float t[9];
+        stem2d_taps(x, n, ho, wo, H, W, t);
+        if (cv) {
+            float d[4];
+            load_vec<4>(dy + (size_t)s * Co + c0, d);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int k = 0; k < 9; ++k) acc[j][k] = fmaf(d[j], t[k], acc[j][k]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int k = 0; k < 9; ++k) red[row][grp * 4 + j][k] = acc[j][k];
+    __syncthreads();
+    for (int i = threadIdx.x; i < Co * 9; i += blockDim.x) {
+        const int c = i / 9, k = i % 9;
+        float v = 0.f;
+#pragma unroll
+        for (int rr = 0; rr < S2_ROWS; ++rr) v += red[rr][c][k];
+        atomicAdd(dw + (size_t)c * 9 + k, v);
+    }
+}
+
 }  // namespace
 
 extern "C" int avec_im2col_c1(const void* x, void* col, const avec_conv_geom* geom, int Kpad, int dtype, avec_stream_t stream) {
@@ -134,6 +243,38 @@ extern "C" int avec_im2col_c1(const void* x, void* col, const avec_conv_geom* ge
         auto kfn = im2col_c1_kernel<Tt>;
         if (smem > 48 * 1024 && cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return AVEC_ERR_LAUNCH;
         kfn<<<grid, 256, smem, as_stream(stream)>>>((const Tt*)x, (Tt*)col, g, taps, Kpad, IH, IW);
+    });
+    AVEC_LAUNCH_CHECK();
+    return AVEC_OK;
+}
+
+static bool stem2d_args_ok(const void* x, const void* o, int N, int H, int W, int Co) {
+    return x && o && N > 0 && H > 0 && W > 0 && Co > 0 && Co % 4 == 0 && Co <= S2_GROUPS * 4;
+}
+
+extern "C" int avec_stem2d_fwd(const void* x, const void* w, const float* bias, void* out, float* colstats, int N, int H, int W, int Co, int dtype,
+                               avec_stream_t stream) {
+    AVEC_CHECK_ARG(stem2d_args_ok(x, out, N, H, W, Co) && w);
+    const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+    const long long sites = (long long)N * Ho * Wo;
+    const int ctas = (int)std::min<long long>(cdivll(sites, 64), 148 * 8);
+    const long long spc = cdivll(sites, ctas);
+    AVEC_DISPATCH_DTYPE(dtype, Tt, {
+        stem2d_fwd_kernel<Tt><<<(unsigned)cdivll(sites, spc), S2_ROWS * S2_GROUPS, 0, as_stream(stream)>>>((const Tt*)x, (const Tt*)w, bias, (Tt*)out, colstats, N, H, W, Ho,
+                                                                                                         Wo, Co, sites, spc);
+    });
+    AVEC_LAUNCH_CHECK();
+    return AVEC_OK;
+}
+
+extern "C" int avec_stem2d_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int Co, int dtype, avec_stream_t stream) {
+    AVEC_CHECK_ARG(stem2d_args_ok(x, dy, N, H, W, Co) && dw);
+    const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+    const long long sites = (long long)N * Ho * Wo;
+    const int ctas = (int)std::min<long long>(cdivll(sites, 64), 148 * 4);
+    const long long spc = cdivll(sites, ctas);
+    AVEC_DISPATCH_DTYPE(dtype, Tt, {
+        stem2d_wgrad_kernel<Tt><<<(unsigned)cdivll(sites, spc), S2_ROWS * S2_GROUPS, 0, as_stream(stream)>>>((const Tt*)x, (const Tt*)dy, dw, N, H, W, Ho, Wo, Co, sites, spc);
     });
     AVEC_LAUNCH_CHECK();
     return AVEC_OK;

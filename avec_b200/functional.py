@@ -395,11 +395,12 @@ class AudioStemFn(Function):
         wp = wc(cw, "stem2d", lambda w: w[:, 0].transpose(1, 2).reshape(w.shape[0], 9))
         sites = ops.geom_sites(g)
         stats = ops.gemm_stats_buffer(Co, wave.device) if training else None
-        u = ops.conv_fwd(melc, wp, g, bias=cb, colstats=stats)
+        direct = Co % 4 == 0 and Co <= 256   # SIMT stem kernel (K = 9 is far below a tensor-core tile; output-write bound)
+        u = ops.stem2d_fwd(melc, wp, cb, colstats=stats) if direct else ops.conv_fwd(melc, wp, g, bias=cb, colstats=stats)
         bnbuf = _bn_buf(stats, bn_w, bn_b, rm, rv, sites, training, momentum)
         v = ops.bn_apply(u, bnbuf[0], bnbuf[1], L.ACT_SWISH)
         ctx.save_for_backward(melc, u, bnbuf, bn_w, cw)
-        ctx.g, ctx.training = g, training
+        ctx.g, ctx.training, ctx.direct = g, training, direct
         return v.view(B, g.Ho, g.Wo * Co)
 
     @staticmethod
@@ -411,7 +412,7 @@ class AudioStemFn(Function):
         Co = cw.shape[0]
         dv2 = _c(dv).view(-1, Co)
         du, _, dgamma, dbeta = ops.bn_bwd(dv2, u, bnbuf, bn_w, L.ACT_SWISH)
-        dwp = ops.conv_wgrad(du, melc, g)
+        dwp = ops.stem2d_wgrad(melc, du) if ctx.direct else ops.conv_wgrad(du, melc, g)
         dcw = dwp.view(Co, 3, 3).transpose(1, 2).reshape(cw.shape)
         dcb = ops.colsum(du)
         return None, None, dcw, dcb, dgamma, dbeta, None, None, None, None

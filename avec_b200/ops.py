@@ -411,6 +411,25 @@ def im2col_c1(x, g, Kpad):
     return col
 
 
+def stem2d_fwd(x, w9, bias, colstats=None):
+    """audio stem conv: x [N,H,W] (C = 1), w9 [Co, 9] -> u [N*Ho*Wo, Co] (+ BatchNorm column sums)"""
+    _cuda(x, w9)
+    N, H, W = x.shape[0], x.shape[1], x.shape[2]
+    Co = w9.shape[0]
+    out = torch.empty((N * ((H - 1) // 2 + 1) * ((W - 1) // 2 + 1), Co), device=x.device, dtype=x.dtype)
+    L.check(L.load().avec_stem2d_fwd(x.data_ptr(), w9.data_ptr(), _p(bias), out.data_ptr(), _p(colstats), N, H, W, Co, _dt(x), _stream()), "avec_stem2d_fwd")
+    return out
+
+
+def stem2d_wgrad(x, dy):
+    _cuda(x, dy)
+    N, H, W = x.shape[0], x.shape[1], x.shape[2]
+    Co = dy.shape[1]
+    dw = zeros_f32((Co, 9), x.device)
+    L.check(L.load().avec_stem2d_wgrad(x.data_ptr(), dy.data_ptr(), dw.data_ptr(), N, H, W, Co, _dt(x), _stream()), "avec_stem2d_wgrad")
+    return dw
+
+
 STEM_KPAD = 320   # forward weight row of the direct stem kernel: k = (kt*7+kh)*8 + kw, zero padded (ST_KPAD in gemm_tc.cu)
 
 

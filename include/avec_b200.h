@@ -209,6 +209,14 @@ int avec_stem3d_fwd(const void* x, const void* wp, const float* bias, void* out,
 int avec_stem3d_wgrad(const void* x, const void* dy, float* dw, int Nb, int T, int H, int W, avec_stream_t stream);
 
 
+/* Audio stem Conv2d(1 -> Co, 3x3, stride 2, pad 1) on the log-mel image x [N][H][W] (layers.Conv2d of the subsampling module,
+ * nnet/networks.py:359-368, nnet/modules.py:70-130): out [N*Ho*Wo][Co] = conv + bias, w [Co][9] in the compute dtype,
+ * colstats (optional) [AVEC_STATS_REPLICAS][2][Co] fp32 BatchNorm sums; wgrad: dw [Co][9] fp32 += sum_sites dy * taps. */
+int avec_stem2d_fwd(const void* x, const void* w, const float* bias, void* out, float* colstats, int N, int H, int W, int Co, int dtype,
+                    avec_stream_t stream);
+int avec_stem2d_wgrad(const void* x, const void* dy, float* dw, int N, int H, int W, int Co, int dtype, avec_stream_t stream);
+
+
 /* single-channel im2col for the C = 1 stems (Conv3d (5,7,7) of nnet/networks.py:460-468): x [N,Ti,Hi,Wi,1] ->
  * col [sites, Kpad] (taps then zero padding), so that the stem convolution and its weight gradient run as plain GEMMs */
 int avec_im2col_c1(const void* x, void* col, const avec_conv_geom* geom, int Kpad, int dtype, avec_stream_t stream);

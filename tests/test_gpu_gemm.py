@@ -165,6 +165,27 @@ def test_direct_stem3d_fwd_wgrad(B, T, H, W):
     _close(dw, wr.grad.reshape(64, 245), 1e-2)
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 1e-2)])
+@pytest.mark.parametrize("N,H,W,Co", [(2, 21, 80, 180), (3, 401, 80, 180), (1, 7, 10, 64)])
+def test_audio_stem_conv2d_simt(dtype, tol, N, H, W, Co):
+    """SIMT audio stem (Conv2d 1 -> Co, 3x3, stride 2, pad 1): output + bias, BatchNorm column sums, weight gradient"""
+    x = _rand(N, H, W, dtype=dtype, seed=1)
+    w = (_rand(Co, 9, seed=2) / 3).to(dtype)
+    b = _rand(Co, seed=3)
+    stats = ops.gemm_stats_buffer(Co, x.device)
+    y = ops.stem2d_fwd(x, w, b, colstats=stats)
+    wr = w.float().view(Co, 1, 3, 3).requires_grad_(True)
+    yr = F.conv2d(F.pad(x.float().view(N, 1, H, W), (1, 1, 1, 1)), wr, b, stride=2)
+    yr2 = yr.permute(0, 2, 3, 1).reshape(-1, Co)
+    _close(y, yr2, tol)
+    st = stats.view(L.STATS_REPLICAS, 2, Co).sum(0)
+    _close(st[0], yr2.sum(0), 2e-3 if dtype == torch.bfloat16 else 1e-4)
+    _close(st[1], (yr2 ** 2).sum(0), 2e-3 if dtype == torch.bfloat16 else 1e-4)
+    dy = _rand(*y.shape, dtype=dtype, seed=4)
+    yr.backward(dy.float().view(N, yr.shape[2], yr.shape[3], Co).permute(0, 3, 1, 2))
+    _close(ops.stem2d_wgrad(x, dy), wr.grad.reshape(Co, 9), tol if dtype == torch.bfloat16 else 1e-4)
+
+
 def test_im2col_single_channel():
     B, T, H, W = 2, 5, 20, 24
     for dtype in (torch.float32, torch.bfloat16):
