@@ -68,6 +68,7 @@ PROTOTYPES = {
     "avec_bn_bwd_apply": ([_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _P], _I),
     "avec_stft_mel_log": ([_P, _P, _P, _I, _I, _I, _I, _P], _I),
     "avec_im2col_c1": ([_P, _P, C.POINTER(ConvGeom), _I, _I, _P], _I),
+    "avec_bn_bwd_pool": ([_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P], _I),
     "avec_stem2d_fwd": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P], _I),
     "avec_stem2d_wgrad": ([_P, _P, _P, _I, _I, _I, _I, _I, _P], _I),
     "avec_stem3d_fwd": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _P], _I),

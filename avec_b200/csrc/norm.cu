@@ -358,6 +358,85 @@ struct StatsF {
 __device__ __forceinline__ float act_fwd(float z, int act) { return act == AVEC_ACT_RELU ? fmaxf(z, 0.0f) : (act == AVEC_ACT_SWISH ? swishf_(z) : z); }
 __device__ __forceinline__ float act_bwd(float z, int act) { return act == AVEC_ACT_RELU ? (z > 0.0f ? 1.0f : 0.0f) : (act == AVEC_ACT_SWISH ? dswishf_(z) : 1.0f); }
 
+// gradient reaching input site (n, hi, wi) of a 3x3 / stride-2 / pad-1 max pool: dy of every window whose saved argmax code
+// points at this site (code 255 = the ReLU floor won: no gradient)
+template <typename T, int V>
+__device__ __forceinline__ void pool_gather(const T* __restrict__ dy, const uint8_t* __restrict__ idx, long long n, int hi, int wi, int c,
+                                            int C, int Ho, int Wo, float (&acc)[V]) {
+#pragma unroll
+    for (int j = 0; j < V; ++j) acc[j] = 0.0f;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+        const int a = hi + 1 - kh;
+        if (a < 0 || (a & 1)) continue;
+        const int ho = a >> 1;
+        if (ho >= Ho) continue;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+            const int b = wi + 1 - kw;
+            if (b < 0 || (b & 1)) continue;
+            const int wo = b >> 1;
+            if (wo >= Wo) continue;
+            const size_t o = ((size_t)(n * Ho + ho) * Wo + wo) * C + c;
+            float d[V];
+            load_vec<V>(dy + o, d);
+            const int code = kh * 3 + kw;
+            if (V == 8) {
+                const uint2 w = *reinterpret_cast<const uint2*>(idx + o);
+#pragma unroll
+                for (int j = 0; j < V; ++j) { const uint32_t word = j < 4 ? w.x : w.y; if ((int)((word >> ((j & 3) * 8)) & 255u) == code) acc[j] += d[j]; }
+            } else {
+                const uint32_t w = *reinterpret_cast<const uint32_t*>(idx + o);
+#pragma unroll
+                for (int j = 0; j < V; ++j) if ((int)((w >> ((j & 3) * 8)) & 255u) == code) acc[j] += d[j];
+            }
+        }
+    }
+}
+
+// BatchNorm backward reduction whose upstream gradient is the max-pool backward, computed on the fly (the [N,Hi,Wi,C]
+// gradient tensor - 1.6 GB for the visual stem at B = 64 - is never written or re-read)
+template <typename T, int V>
+struct BnBwdPoolF {
+    const T* dyp; const uint8_t* idx; const T* u; const float* mean; const float* rstd; int C, Hi, Wi, Ho, Wo;
+    float mu[V], rs[V];
+    __device__ __forceinline__ void prep(int c) { load_vec<V>(mean + c, mu); load_vec<V>(rstd + c, rs); }
+    __device__ __forceinline__ void operator()(long long r, int c, float (&v0)[V], float (&v1)[V]) const {
+        const int wi = (int)(r % Wi); const long long t = r / Wi; const int hi = (int)(t % Hi); const long long n = t / Hi;
+        float uu[V];
+        load_vec<V>(u + (size_t)r * C + c, uu);
+        pool_gather<T, V>(dyp, idx, n, hi, wi, c, C, Ho, Wo, v0);
+#pragma unroll
+        for (int j = 0; j < V; ++j) v1[j] = v0[j] * (uu[j] - mu[j]) * rs[j];
+    }
+};
+
+template <typename T, int V>
+__global__ void bn_bwd_apply_pool_kernel(const T* __restrict__ dyp, const uint8_t* __restrict__ idx, const T* __restrict__ u,
+                                         const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                         const float* __restrict__ sums, T* __restrict__ du, long long totalv, int C, int Hi, int Wi, int Ho,
+                                         int Wo, float inv_count) {
+    const int Cv = C / V;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < totalv; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % Cv) * V;
+        const long long r = i / Cv;
+        const int wi = (int)(r % Wi); const long long t = r / Wi; const int hi = (int)(t % Hi); const long long n = t / Hi;
+        float mu[V], rs[V], g[V], s0[V], s1[V], uu[V], dz[V], o[V];
+        load_vec<V>(u + (size_t)i * V, uu);
+        load_vec<V>(mean + c, mu); load_vec<V>(rstd + c, rs);
+        load_vec<V>(sums + c, s0); load_vec<V>(sums + C + c, s1);
+        if (gamma) load_vec<V>(gamma + c, g);
+        pool_gather<T, V>(dyp, idx, n, hi, wi, c, C, Ho, Wo, dz);
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const float gg = (gamma ? g[j] : 1.0f) * rs[j];
+            const float xh = (uu[j] - mu[j]) * rs[j];
+            o[j] = gg * (dz[j] - s0[j] * inv_count - xh * s1[j] * inv_count);
+        }
+        store_vec<V>(du + (size_t)i * V, o);
+    }
+}
+
 template <typename T, int V>
 struct BnBwdF {
     const T* dy; const T* u; const T* res; const float* scale; const float* shift; const float* mean; const float* rstd; int C; int act;
@@ -426,7 +505,24 @@ __global__ void bn_apply_kernel(const T* __restrict__ u, const float* __restrict
     float sc[V], sh[V];
     const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (fixed_c) { const int c = (int)(i0 % Cv) * V; load_vec<V>(scale + c, sc); load_vec<V>(shift + c, sh); }
-    for (long long i = i0; i < totalv; i += stride) {
+    long long i = i0;
+    if (fixed_c) {
+        for (; i + stride < totalv; i += 2 * stride) {
+            const size_t e0 = (size_t)i * V, e1 = (size_t)(i + stride) * V;
+            float u0[V], u1[V], r0[V], r1[V];
+            load_vec<V>(u + e0, u0); load_vec<V>(u + e1, u1);
+            if (res) { load_vec<V>(res + e0, r0); load_vec<V>(res + e1, r1); }
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                float z0 = sc[j] * u0[j] + sh[j], z1 = sc[j] * u1[j] + sh[j];
+                if (res) { z0 += r0[j]; z1 += r1[j]; }
+                u0[j] = act_fwd(z0, act); u1[j] = act_fwd(z1, act);
+            }
+            store_vec<V>(y + e0, u0);
+            store_vec<V>(y + e1, u1);
+        }
+    }
+    for (; i < totalv; i += stride) {
         const int c = (int)(i % Cv) * V;
         const size_t e = (size_t)i * V;
         float uu[V], rr[V];
@@ -472,14 +568,8 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restric
     };
     const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (fixed_c) load_coef((int)(i0 % Cv) * V);
-    for (long long i = i0; i < totalv; i += stride) {
-        const int c = (int)(i % Cv) * V;
-        const size_t e = (size_t)i * V;
-        float uu[V], d[V], rr[V], o[V], dzv[V];
-        load_vec<V>(u + e, uu);
-        load_vec<V>(dy + e, d);
-        if (!fixed_c) load_coef(c);
-        if (res) load_vec<V>(res + e, rr);
+    auto body = [&](const float (&uu)[V], const float (&d)[V], const float (&rr)[V], size_t e) {
+        float o[V], dzv[V];
 #pragma unroll
         for (int j = 0; j < V; ++j) {
             float z = sc[j] * uu[j] + sh[j];
@@ -490,6 +580,29 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restric
         }
         store_vec<V>(du + e, o);
         if (dres) store_vec<V>(dres + e, dzv);
+    };
+    long long i = i0;
+    if (fixed_c) {
+        // two elements per iteration with all six loads issued first: twice the bytes in flight per thread (pure HBM stream)
+        for (; i + stride < totalv; i += 2 * stride) {
+            const size_t e0 = (size_t)i * V, e1 = (size_t)(i + stride) * V;
+            float u0[V], d0[V], r0[V], u1[V], d1[V], r1[V];
+            load_vec<V>(u + e0, u0); load_vec<V>(u + e1, u1);
+            load_vec<V>(dy + e0, d0); load_vec<V>(dy + e1, d1);
+            if (res) { load_vec<V>(res + e0, r0); load_vec<V>(res + e1, r1); }
+            body(u0, d0, r0, e0);
+            body(u1, d1, r1, e1);
+        }
+    }
+    for (; i < totalv; i += stride) {
+        const int c = (int)(i % Cv) * V;
+        const size_t e = (size_t)i * V;
+        float uu[V], d[V], rr[V];
+        load_vec<V>(u + e, uu);
+        load_vec<V>(dy + e, d);
+        if (!fixed_c) load_coef(c);
+        if (res) load_vec<V>(res + e, rr);
+        body(uu, d, rr, e);
     }
 }
 
@@ -782,6 +895,22 @@ extern "C" int avec_bn_bwd_apply(const void* dy, const void* u, const float* sca
     AVEC_DISPATCH_DTYPE_VEC(dtype, C, Tt, V, (bn_bwd_apply_kernel<Tt, V><<<ew_blocks(total / V), 256, 0, as_stream(stream)>>>(
         (const Tt*)dy, (const Tt*)u, scale, shift, (const Tt*)res, mean, rstd, gamma, sums, (Tt*)du, (Tt*)dres, total / V, C, act,
         (float)(1.0 / (double)rows))));
+    AVEC_LAUNCH_CHECK();
+    return AVEC_OK;
+}
+
+extern "C" int avec_bn_bwd_pool(const void* dyp, const uint8_t* idx, const void* u, const float* mean, const float* rstd, const float* gamma,
+                                float* sums, void* du, int N, int Hi, int Wi, int C, int Ho, int Wo, int dtype, avec_stream_t stream) {
+    AVEC_CHECK_ARG(dyp && idx && u && mean && rstd && sums && du && N > 0 && C > 0 && Ho == (Hi - 1) / 2 + 1 && Wo == (Wi - 1) / 2 + 1);
+    cudaStream_t st = as_stream(stream);
+    const long long rows = (long long)N * Hi * Wi, total = rows * C;
+    AVEC_DISPATCH_DTYPE_VEC(dtype, C, Tt, V, {
+        BnBwdPoolF<Tt, V> f{(const Tt*)dyp, idx, (const Tt*)u, mean, rstd, C, Hi, Wi, Ho, Wo, {}, {}};
+        launch_colreduce<V>(f, rows, C, sums, sums + C, 1.0f, st);
+        bn_bwd_apply_pool_kernel<Tt, V><<<ew_blocks(total / V), 256, 0, st>>>((const Tt*)dyp, idx, (const Tt*)u, mean, rstd, gamma, sums, (Tt*)du,
+                                                                            total / V, C, Hi, Wi, Ho, Wo, (float)(1.0 / (double)rows));
+    });
+    avec_count_launch();
     AVEC_LAUNCH_CHECK();
     return AVEC_OK;
 }

@@ -340,6 +340,18 @@ def bn_bwd(dy2d, u2d, bnbuf, gamma, act, res=None, want_dres=False):
     return du, dres, sums[Cn:], sums[:Cn]
 
 
+def bn_bwd_pool(dyp, idx, u2d, bnbuf, gamma, N, Hi, Wi):
+    """BatchNorm backward fed by the max-pool backward (gathered on the fly): returns du, dgamma, dbeta"""
+    _cuda(dyp, u2d)
+    Cn = u2d.shape[1]
+    Ho, Wo = (Hi - 1) // 2 + 1, (Wi - 1) // 2 + 1
+    sums = zeros_f32((2 * Cn,), u2d.device)
+    du = torch.empty_like(u2d)
+    L.check(L.load().avec_bn_bwd_pool(dyp.data_ptr(), idx.data_ptr(), u2d.data_ptr(), bnbuf[2].data_ptr(), bnbuf[3].data_ptr(), _p(gamma),
+                                      sums.data_ptr(), du.data_ptr(), N, Hi, Wi, Cn, Ho, Wo, _dt(u2d), _stream()), "avec_bn_bwd_pool")
+    return du, sums[Cn:], sums[:Cn]
+
+
 # ----------------------------------------------------------------------------------------------------------- attention
 def relpos_attn_fwd(qkv, e, klen, qlen, B, T, H, d, G=1, Tf=None, u=None, v=None):
     """qkv [B*Tf, 3*D1] (frames), e [2T-1, G*D1] -> o [B*Tf, D1], probs [B,H,T,T]; T = ceil(Tf/G) tokens of G frames"""

@@ -11,21 +11,35 @@ def broadcast_parameters(module, src=0):
         dist.broadcast(t.data, src)
 
 
-def allreduce_gradients(params, world_size=None, bucket_bytes=256 << 20):
-    """mean of the gradients over ranks, in a few large flat buckets (61.7 M parameters = 247 MB fp32 for AV)."""
+def allreduce_gradients(params, world_size=None, bucket_bytes=256 << 20, grads=None):
+    """mean of the gradients over ranks in a few large flat buckets (61.7 M parameters = 247 MB fp32 for AV).
+
+    Per bucket: ONE flatten (torch.cat), one all-reduce (ReduceOp.AVG on NCCL; sum + scale on gloo), and the averaged values
+    are handed back as VIEWS of the flat buffer (`p.grad = view`) - no per-tensor copy kernels (1100 launches per step
+    otherwise).  `grads` (optional) are the tensors to reduce when they are not `p.grad` itself, e.g. the static gradient
+    tensors a captured CUDA graph writes on every replay."""
     world_size = world_size or dist.get_world_size()
-    grads = [p.grad for p in params if p.grad is not None]
+    pairs = [(p, p.grad if grads is None else g) for p, g in zip(params, grads if grads is not None else params)]
+    pairs = [(p, g) for p, g in pairs if g is not None]
+    avg = dist.get_backend() == "nccl"
     bucket, size = [], 0
-    for g in grads + [None]:
-        if g is not None and (size + g.numel() * g.element_size() <= bucket_bytes or not bucket):
-            bucket.append(g)
-            size += g.numel() * g.element_size()
+    for item in pairs + [None]:
+        nbytes = item[1].numel() * item[1].element_size() if item is not None else 0
+        if item is not None and (size + nbytes <= bucket_bytes or not bucket):
+            bucket.append(item)
+            size += nbytes
             continue
         if bucket:
-            flat = torch._utils._flatten_dense_tensors(bucket)
-            dist.all_reduce(flat)
-            flat.div_(world_size)
-            for dst, src in zip(bucket, torch._utils._unflatten_dense_tensors(flat, bucket)):
-                dst.copy_(src)
-        bucket, size = ([g], g.numel() * g.element_size()) if g is not None else ([], 0)
-    return len(grads)
+            flat = torch.cat([g.reshape(-1) for _, g in bucket])
+            if avg:
+                dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+            else:
+                dist.all_reduce(flat)
+                flat.div_(world_size)
+            off = 0
+            for p, g in bucket:
+                n = g.numel()
+                p.grad = flat[off:off + n].view_as(g)
+                off += n
+        bucket, size = ([item], nbytes) if item is not None else ([], 0)
+    return len(pairs)

@@ -199,9 +199,11 @@ def main():
         loss.backward()
         return loss.detach()
 
+    static_grads = None   # gradient tensors the captured graph writes on every replay
+
     def allreduce_grads():
         if world > 1:
-            parallel.allreduce_gradients(params, world)
+            parallel.allreduce_gradients(params, world, grads=static_grads if graph is not None else None)
 
     graph, static_loss = None, None
 
@@ -248,6 +250,7 @@ def main():
             with torch.cuda.graph(gobj):
                 static_loss = fwd_bwd(resident)
             graph, use_graph = gobj, True
+            static_grads = [p.grad for p in params]
         except Exception as e:  # noqa: BLE001
             if rank == 0:
                 print(f"[bench] CUDA-graph capture failed, running eager: {type(e).__name__}: {str(e)[:200]}", file=sys.stderr)

@@ -221,6 +221,14 @@ int avec_stem2d_wgrad(const void* x, const void* dy, float* dw, int N, int H, in
  * col [sites, Kpad] (taps then zero padding), so that the stem convolution and its weight gradient run as plain GEMMs */
 int avec_im2col_c1(const void* x, void* col, const avec_conv_geom* geom, int Kpad, int dtype, avec_stream_t stream);
 
+/* BatchNorm backward (batch statistics, no activation) whose upstream gradient is the 3x3 / stride-2 max-pool backward of
+ * avec_bn_relu_maxpool_fwd, gathered on the fly from the pooled gradient dyp [N,Ho,Wo,C] and the saved argmax codes: both
+ * passes (column sums -> sums [2C] = {sum dz, sum dz*xhat}, then du [N,Hi,Wi,C]) without materialising dz.  Replaces
+ * MaxPool3d.backward + BatchNorm3d.backward of the visual stem (nnet/networks.py:459-471, nnet/layers.py:839-915). */
+int avec_bn_bwd_pool(const void* dyp, const uint8_t* idx, const void* u, const float* mean, const float* rstd, const float* gamma,
+                     float* sums, void* du, int N, int Hi, int Wi, int C, int Ho, int Wo, int dtype, avec_stream_t stream);
+
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Visual front-end helpers (nnet/networks.py:459-472): BN3d + ReLU + MaxPool3d((1,3,3), s (1,2,2), zero "same" pad)
  * fused: u [N,Hi,Wi,C] -> y [N,Ho,Wo,C], argmax index (0..8, uint8) saved for the backward.

@@ -179,6 +179,27 @@ def test_relpos_attention_core_bf16_tensor_core(B, T, H, d, ragged, qlen_short):
     check_close("de", de, e.grad, 0.0, 3e-2 * float(e.grad.abs().max()))
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("N,Hi,Wi,C", [(3, 12, 12, 64), (2, 9, 7, 64), (5, 44, 44, 64)])
+def test_bn_backward_fused_with_maxpool_backward(dtype, N, Hi, Wi, C):
+    """avec_bn_bwd_pool (pool gradient gathered on the fly in both BatchNorm passes) == max-pool backward + BatchNorm backward"""
+    u = _r("u", (N * Hi * Wi, C)).to(dtype)
+    gam, bet = 1 + 0.1 * _r("g", (C,)), 0.1 * _r("b", (C,))
+    st = torch.stack([u.float().sum(0), (u.float() ** 2).sum(0)]).reshape(-1).contiguous()
+    buf = ops.bn_finalize(st, gam, bet, N * Hi * Wi)
+    y, idx = ops.bn_relu_maxpool_fwd(u, buf[0], buf[1], N, Hi, Wi, C)
+    dyp = _r("dy", tuple(y.shape)).to(dtype)
+    dz = ops.bn_relu_maxpool_bwd(dyp, idx, N, Hi, Wi, C)
+    du_ref, _, dg_ref, db_ref = ops.bn_bwd(dz, u, buf, gam, L.ACT_NONE)
+    du, dg, db = ops.bn_bwd_pool(dyp, idx, u, buf, gam, N, Hi, Wi)
+    tol = 1e-5 if dtype == torch.float32 else 2e-2
+    check_close("du", du, du_ref, tol, tol * float(du_ref.float().abs().max()))
+    # the two-kernel path rounds dz to the compute dtype before summing it; the fused path sums the unrounded values
+    st = 1e-3 if dtype == torch.float32 else 2e-2
+    check_close("dgamma", dg, dg_ref, st, st * float(dg_ref.abs().max()) + 1e-4)
+    check_close("dbeta", db, db_ref, st, st * float(db_ref.abs().max()) + 1e-4)
+
+
 def test_stft_mel_log_matches_reference_fixture_and_restatement():
     fix = load_golden("audio_logmel.pt")
     wave = seeded.randn("wave", (3, 4000), 1, 0.1)
