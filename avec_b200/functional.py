@@ -455,8 +455,10 @@ class VideoStemFn(Function):
             raise RuntimeError("avec_b200: stem backward needs training-mode BatchNorm statistics")
         g = ctx.g
         Co = cw.shape[0]
-        # max-pool backward fused into both BatchNorm-backward passes (the 1.6 GB pre-pool gradient is never materialised)
-        du, dgamma, dbeta = ops.bn_bwd_pool(_c(dy), idx, u, bnbuf, bn_w, g.N * g.To, g.Ho, g.Wo)
+        # (ops.bn_bwd_pool fuses the max-pool backward into both BatchNorm passes and never materialises the 1.6 GB pre-pool
+        # gradient, but its gathers make the two passes 4.25 ms against 3.2 ms for the three streaming kernels below)
+        dz = ops.bn_relu_maxpool_bwd(_c(dy), idx, g.N * g.To, g.Ho, g.Wo, Co)
+        du, _, dgamma, dbeta = ops.bn_bwd(dz, u, bnbuf, bn_w, L.ACT_NONE)
         taps = cw.shape[2] * cw.shape[3] * cw.shape[4]
         if ctx.direct:
             dcw = ops.stem3d_wgrad(col, du).reshape(cw.shape)

@@ -37,7 +37,7 @@ def parse():
     ap.add_argument("--model", default="AV", choices=["AV", "AO", "VO"])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-baseline", type=int, default=1, help="time the CPU restatement on a bounded sample (rank 0, N=1)")
-    ap.add_argument("--cpu-sample", type=int, default=4, help="utterances in the CPU baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=8, help="utterances in the CPU baseline sample")
     ap.add_argument("--loss", default="ctc", choices=["ctc", "sum"])
     ap.add_argument("--graph", type=int, default=1, help="capture forward+backward in one CUDA graph (falls back to eager if capture fails)")
     return ap.parse_args()
@@ -101,6 +101,15 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
 
 
+def gemm_traffic():
+    """DRAM bytes (read + write) of all tcgen05 GEMM / conv launches of one step, from the committed ncu pass
+    (profiles/r01_gemm_traffic.json: `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` over tools/one_step.py)"""
+    p = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("dram_bytes_per_step")
+    return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -110,7 +119,7 @@ def measured_peaks():
 
 
 # ------------------------------------------------------------------------------------------------- CPU baseline (port)
-def cpu_baseline(args, steps=1, sample=None):
+def cpu_baseline(args, steps=2, sample=None):
     """reference arm: the pinned plain-torch restatement of the reference (oracle/restate.py, checked against fixtures
     generated by the unmodified reference) forward+backward on the host cores, on a bounded sample of the workload."""
     from oracle import restate
@@ -300,8 +309,9 @@ def main():
             "e2e": {"value": world * B / (ms_e2e / args.steps / 1000.0), "unit": "utterances/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches) * args.steps,
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
-                         "kernel": "gemm_tc_kernel (tcgen05 GEMM / implicit-GEMM conv), all launches of one step",
+            "roofline": {"bound": "tensor", "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": gemm_traffic(),
+                         "kernel": "tcgen05 GEMM / implicit-GEMM conv kernels of csrc/gemm_tc.cu (gemm_tc_kernel, conv3x3_halo64, wgrad_halo64, stem3d_*), "
+                                   "all launches of one step; achieved = their 2*M*N*K FLOPs / their summed CUDA-event time; traffic = their summed DRAM bytes (ncu)",
                          "launches_per_step": gemm_n, "ms_per_step_in_kernel": gemm_ms, "peak_source": which + " bf16_tflops_sustained"},
         }
         if world == 1 and args.cpu_baseline:
@@ -324,11 +334,25 @@ def profile_gemm(step_fn, ops):
         e1.record()
         recs.append((e0, e1, 2.0 * a.M * a.N * a.K))
     ops._gemm = hooked
+    stem_orig = (ops.stem3d_fwd, ops.stem3d_wgrad)
+
+    def timed_stem(fn):
+        def wrapper(x, *a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn(x, *a, **k)
+            e1.record()
+            B_, T_, H_, W_ = x.shape[0], x.shape[1], x.shape[2], x.shape[3]
+            recs.append((e0, e1, 2.0 * B_ * T_ * (H_ // 2) * (W_ // 2) * 64 * 245))
+            return out
+        return wrapper
+    ops.stem3d_fwd, ops.stem3d_wgrad = timed_stem(stem_orig[0]), timed_stem(stem_orig[1])
     try:
         step_fn()
         torch.cuda.synchronize()
     finally:
         ops._gemm = orig
+        ops.stem3d_fwd, ops.stem3d_wgrad = stem_orig
     ms = sum(e0.elapsed_time(e1) for e0, e1, _ in recs)
     return ms, sum(f for _, _, f in recs), len(recs)
 
