@@ -675,11 +675,12 @@ __device__ __forceinline__ void unpack_bf16x8(const uint4& t, float (&v)[8]) {
 // use, bias kept in registers (a lane owns the same 8 columns in every pass).
 template <int KIND, bool STATS, bool AL16>
 __device__ __forceinline__ void epilogue_fast(const TcParams& p, const EpiParams& ep, const TileInfo& ti, uint32_t lane_addr, uint32_t stg_s,
-                                              uint32_t bias_sa, float* stats_dst, int warp, int lane, uint32_t rowrel_sa = 0u) {
+                                              uint32_t bias_sa, float* stats_dst, int warp, int lane, bool bias_on, uint32_t rowrel_sa = 0u) {
     const int BN = p.BN;
     const int q = lane & 7, rs = lane >> 3;
     const int lc = q * 8;
     const float alpha = ep.alpha;
+    const bool scale_on = alpha != 1.0f;   // kernel-uniform: the common alpha == 1 / no-bias launches skip 16 FP32 ops per row segment
     const int rows_left = ti.rows_valid - warp * 32;   // valid rows of this warp's quarter (may be <= 0 or >= 32)
     // output row of tile row r: contiguous, or scattered through the row table (parity classes of strided dgrads)
     auto out_row = [&](int rr) -> long long {   // < 0: the tile row holds no output (halo-grid columns past the image)
@@ -733,8 +734,8 @@ __device__ __forceinline__ void epilogue_fast(const TcParams& p, const EpiParams
         }
         __syncwarp();
         // ---- transposed domain
-        float b[8];
-        {
+        float b[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (bias_on) {
             const float4 b0 = lds128(bias_sa + (uint32_t)(c0 + (col_ok ? lc : 0)) * 4u), b1 = lds128(bias_sa + (uint32_t)(c0 + (col_ok ? lc : 0) + 4) * 4u);
             b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
         }
@@ -757,24 +758,34 @@ __device__ __forceinline__ void epilogue_fast(const TcParams& p, const EpiParams
                 const long long row_ = out_row(rr);
                 if (row_ < 0) continue;
                 const size_t row = (size_t)row_;
-                float a[8] = {t[2 * u].x + b[0], t[2 * u].y + b[1], t[2 * u].z + b[2], t[2 * u].w + b[3],
-                              t[2 * u + 1].x + b[4], t[2 * u + 1].y + b[5], t[2 * u + 1].z + b[6], t[2 * u + 1].w + b[7]};
+                float a[8] = {t[2 * u].x, t[2 * u].y, t[2 * u].z, t[2 * u].w, t[2 * u + 1].x, t[2 * u + 1].y, t[2 * u + 1].z, t[2 * u + 1].w};
+                if (bias_on) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) a[j] += b[j];
+                }
                 const size_t oi = row * ep.ldo + gc;
+                float sa_[8];   // alpha * a (a itself feeds the BatchNorm statistics and the Swish pre-activation copy)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) sa_[j] = a[j];
+                if (scale_on) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) sa_[j] *= alpha;
+                }
                 if (KIND == AVEC_EPI_ACCUM) {
                     float* dst = reinterpret_cast<float*>(ep.out) + oi;
-                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(alpha * a[0]), "f"(alpha * a[1]), "f"(alpha * a[2]), "f"(alpha * a[3]) : "memory");
-                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(alpha * a[4]), "f"(alpha * a[5]), "f"(alpha * a[6]), "f"(alpha * a[7]) : "memory");
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(sa_[0]), "f"(sa_[1]), "f"(sa_[2]), "f"(sa_[3]) : "memory");
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(sa_[4]), "f"(sa_[5]), "f"(sa_[6]), "f"(sa_[7]) : "memory");
                 } else {
                     float o[8], x[8];
                     if (HAS_AUX) unpack_bf16x8(g == 0 ? xa[u] : xb[u], x);
                     if (KIND == AVEC_EPI_SWISH && ep.out2) stg_bf16x8<AL16>(reinterpret_cast<bf16*>(ep.out2) + row * ep.ldo2 + gc, a);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        if (KIND == AVEC_EPI_LINEAR) o[j] = alpha * a[j];
+                        if (KIND == AVEC_EPI_LINEAR) o[j] = sa_[j];
                         else if (KIND == AVEC_EPI_SWISH) o[j] = swishf_(a[j]);
-                        else if (KIND == AVEC_EPI_RESIDUAL) o[j] = x[j] + alpha * a[j];
-                        else if (KIND == AVEC_EPI_DSWISH) o[j] = alpha * a[j] * dswishf_(x[j]);
-                        else o[j] = fmaxf(alpha * a[j] + x[j], 0.0f);
+                        else if (KIND == AVEC_EPI_RESIDUAL) o[j] = x[j] + sa_[j];
+                        else if (KIND == AVEC_EPI_DSWISH) o[j] = sa_[j] * dswishf_(x[j]);
+                        else o[j] = fmaxf(sa_[j] + x[j], 0.0f);
                     }
                     stg_bf16x8<AL16>(reinterpret_cast<bf16*>(ep.out) + oi, o);
                 }
@@ -934,17 +945,17 @@ __device__ __forceinline__ void epilogue_warp(const TcParams& p, const EpiParams
 
 template <bool AL16>
 __device__ __forceinline__ void epilogue_fast_dispatch(const TcParams& p, const EpiParams& ep, const TileInfo& ti, uint32_t lane_addr, uint32_t stg_s,
-                                                       uint32_t bias_sa, float* stats_dst, int warp, int lane, uint32_t rowrel_sa) {
+                                                       uint32_t bias_sa, float* stats_dst, int warp, int lane, bool bias_on, uint32_t rowrel_sa) {
     switch (ep.kind) {
     case AVEC_EPI_LINEAR:
-        if (ep.colstats) epilogue_fast<AVEC_EPI_LINEAR, true, AL16>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane, rowrel_sa);
-        else epilogue_fast<AVEC_EPI_LINEAR, false, AL16>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane, rowrel_sa);
+        if (ep.colstats) epilogue_fast<AVEC_EPI_LINEAR, true, AL16>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane, bias_on, rowrel_sa);
+        else epilogue_fast<AVEC_EPI_LINEAR, false, AL16>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane, bias_on, rowrel_sa);
         break;
-    case AVEC_EPI_SWISH: epilogue_fast<AVEC_EPI_SWISH, false, AL16>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane, rowrel_sa); break;
-    case AVEC_EPI_RESIDUAL: epilogue_fast<AVEC_EPI_RESIDUAL, false, AL16>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane, rowrel_sa); break;
-    case AVEC_EPI_DSWISH: epilogue_fast<AVEC_EPI_DSWISH, false, AL16>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane, rowrel_sa); break;
-    case AVEC_EPI_ACCUM: epilogue_fast<AVEC_EPI_ACCUM, false, AL16>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane, rowrel_sa); break;
-    default: epilogue_fast<AVEC_EPI_RELU, false, AL16>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane, rowrel_sa); break;
+    case AVEC_EPI_SWISH: epilogue_fast<AVEC_EPI_SWISH, false, AL16>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane, bias_on, rowrel_sa); break;
+    case AVEC_EPI_RESIDUAL: epilogue_fast<AVEC_EPI_RESIDUAL, false, AL16>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane, bias_on, rowrel_sa); break;
+    case AVEC_EPI_DSWISH: epilogue_fast<AVEC_EPI_DSWISH, false, AL16>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane, bias_on, rowrel_sa); break;
+    case AVEC_EPI_ACCUM: epilogue_fast<AVEC_EPI_ACCUM, false, AL16>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane, bias_on, rowrel_sa); break;
+    default: epilogue_fast<AVEC_EPI_RELU, false, AL16>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane, bias_on, rowrel_sa); break;
     }
 }
 
@@ -1111,8 +1122,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
             // BatchNorm statistics go to one of AVEC_STATS_REPLICAS copies of the accumulator (by tile index): 32x fewer
             // same-address L2 reductions
             float* stats_dst = ep.colstats ? ep.colstats + (size_t)(ti.mtile % AVEC_STATS_REPLICAS) * 2 * p.N : nullptr;
-            if (p.epi_fast == 2) epilogue_fast_dispatch<true>(p, ep, ti, lane_addr, smem_u32(stg), smem_u32(bias_s), stats_dst, warp, lane, smem_u32(rinfo));
-            else if (p.epi_fast == 1) epilogue_fast_dispatch<false>(p, ep, ti, lane_addr, smem_u32(stg), smem_u32(bias_s), stats_dst, warp, lane, smem_u32(rinfo));
+            const bool bias_on = p.ep.bias != nullptr && ti.z == 0;
+            if (p.epi_fast == 2) epilogue_fast_dispatch<true>(p, ep, ti, lane_addr, smem_u32(stg), smem_u32(bias_s), stats_dst, warp, lane, bias_on, smem_u32(rinfo));
+            else if (p.epi_fast == 1) epilogue_fast_dispatch<false>(p, ep, ti, lane_addr, smem_u32(stg), smem_u32(bias_s), stats_dst, warp, lane, bias_on, smem_u32(rinfo));
             else epilogue_warp(p, ep, ti, lane_addr, stg, bias_s, stats_dst, warp, lane);
             // all TMEM reads of this buffer are complete: hand it back to the MMA warp
             tc_fence_before();
@@ -1454,8 +1466,8 @@ __global__ void __launch_bounds__(ST_FWD_THREADS, 1) stem3d_fwd_kernel(const __g
             const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * 64);
             float* stats_dst = ep.colstats ? ep.colstats + (size_t)(t % AVEC_STATS_REPLICAS) * 2 * 64 : nullptr;
             if (p.dbg & 4) { }
-            else if (ep.colstats) epilogue_fast<AVEC_EPI_LINEAR, true, true>(p.tc, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane);
-            else epilogue_fast<AVEC_EPI_LINEAR, false, true>(p.tc, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane);
+            else if (ep.colstats) epilogue_fast<AVEC_EPI_LINEAR, true, true>(p.tc, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane, p.tc.ep.bias != nullptr);
+            else epilogue_fast<AVEC_EPI_LINEAR, false, true>(p.tc, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane, p.tc.ep.bias != nullptr);
             tc_fence_before();
             mbar_arrive(&accum_empty[buf]);
         }
@@ -1823,9 +1835,10 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv3x3_halo64_kernel(const __g
             tc_fence_after();
             const uint32_t lane_addr = tmem_base + ((uint32_t)(w4 * 32) << 16) + (uint32_t)(grp * 64);
             float* stats_dst = ep.colstats ? ep.colstats + (size_t)(t % AVEC_STATS_REPLICAS) * 2 * 64 : nullptr;
-            if (ep.kind == AVEC_EPI_RESIDUAL) epilogue_fast<AVEC_EPI_RESIDUAL, false, true>(p.tc, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, w4, lane, rowrel_sa);
-            else if (ep.colstats) epilogue_fast<AVEC_EPI_LINEAR, true, true>(p.tc, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, w4, lane, rowrel_sa);
-            else epilogue_fast<AVEC_EPI_LINEAR, false, true>(p.tc, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, w4, lane, rowrel_sa);
+            const bool bias_on = p.tc.ep.bias != nullptr;
+            if (ep.kind == AVEC_EPI_RESIDUAL) epilogue_fast<AVEC_EPI_RESIDUAL, false, true>(p.tc, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, w4, lane, bias_on, rowrel_sa);
+            else if (ep.colstats) epilogue_fast<AVEC_EPI_LINEAR, true, true>(p.tc, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, w4, lane, bias_on, rowrel_sa);
+            else epilogue_fast<AVEC_EPI_LINEAR, false, true>(p.tc, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, w4, lane, bias_on, rowrel_sa);
             tc_fence_before();
             mbar_arrive(&accum_empty[grp]);
         }
