@@ -1903,6 +1903,125 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv3x3_halo64_kernel(const __g
     if (warp == 8) { tc_fence_after(); tmem_dealloc(tmem_base, 128); }
 }
 
+// ---- the same resident-dW scheme for the wider 3x3 stride-1 stages whose images fit one tile (ResNet stage 2: 11 x 11 x 128,
+// stage 3: 6 x 6 x 256).  A tile is BI whole images, each laid out on a (H+2) x G grid (G = W+2 rounded up to a multiple of 8 so
+// that the second filter-row M group starts on a 1024-byte swizzle atom); dY and the X halo use the same per-image pitch, so
+// a filter tap is again a constant row offset kh*G+kw for the whole tile.  dW (Co x 9C fp32) exceeds tensor memory, so each
+// persistent CTA owns one (64 input channels) x (64 output channels) block of it (6 accumulators x 64 columns) and streams
+// its share of the images; CTA i works on block i % nblocks.
+constexpr int WI_THREADS = 192;
+constexpr size_t WI_SMEM_MAX = 225 * 1024;
+
+struct WgImgParams {
+    int N, H, W, G, BI, C, Co, ksteps, k_rows, x_rows, stage_bytes, stages, ncb, ncob, tiles;
+    int y_tx, x_tx;
+    float alpha;
+    float* dw;    // [Co][9 * C] fp32
+};
+
+__global__ void __launch_bounds__(WI_THREADS, 1) wgrad_img_kernel(const __grid_constant__ WgImgParams p, const __grid_constant__ CUtensorMap mapY,
+                                                                 const __grid_constant__ CUtensorMap mapX) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* ctrl = smem + (size_t)p.stages * p.stage_bytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(ctrl);   // [<= 8]
+    uint64_t* empty = full + 8;
+    uint64_t* done = empty + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 2);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    if (tid == 0) {
+        for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(done, 1);
+        fence_barrier_init();
+        tma_prefetch_desc(&mapY);
+        tma_prefetch_desc(&mapX);
+    }
+    if (warp == 4) tmem_alloc(tmem_slot, 512);
+    for (int i = tid; i < p.stages * p.stage_bytes / 16; i += WI_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int nblocks = p.ncb * p.ncob;
+    const int blk = blockIdx.x % nblocks, part = blockIdx.x / nblocks, nparts = gridDim.x / nblocks;   // gridDim.x is a multiple of nblocks
+    const int c0 = (blk % p.ncb) * 64, co0 = (blk / p.ncb) * 64;
+    const bool any_tile = part < p.tiles;
+    const int y_bytes = p.k_rows * 128;
+
+    if (warp < 4) {
+        if (any_tile) {
+            mbar_wait(done, 0);
+            tc_fence_after();
+            const int row = warp * 32 + lane, g = row >> 6, c = row & 63;
+            const size_t ldw = (size_t)9 * p.C;
+            for (int q = 0; q < 6; ++q) {
+                const int set = q / 3, kw = q - set * 3, kh = set + g;
+                if (set == 1 && g == 0) continue;   // kh = 1 duplicate (g is warp-uniform)
+                float* dst = p.dw + (size_t)co0 * ldw + (size_t)(kh * 3 + kw) * p.C + c0 + c;
+                for (int cc = 0; cc < 64; cc += 16) {
+                    float v[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(q * 64 + cc), v);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) atomicAdd(dst + (size_t)(cc + i) * ldw, p.alpha * v[i]);
+                }
+            }
+        }
+        tc_fence_before();
+    } else if (warp == 4) {
+        const uint32_t idesc = make_idesc(64, 1, 1);
+        const uint64_t a_desc0 = make_smem_desc(0, (uint32_t)p.G * 128u, 1024);
+        const uint64_t b_desc0 = make_smem_desc(0, 16384, 1024);
+        const uint32_t a_hi = (uint32_t)(a_desc0 >> 32), b_hi = (uint32_t)(b_desc0 >> 32);
+        const uint32_t base16 = smem_u32(smem) >> 4;
+        int j = 0, st = 0;
+        uint32_t ph = 0;
+        for (int t = part; t < p.tiles; t += nparts, ++j) {
+            mbar_wait(&full[st], ph);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t y16 = base16 + (uint32_t)st * ((uint32_t)p.stage_bytes >> 4);
+                const uint32_t x16 = y16 + ((uint32_t)y_bytes >> 4);
+#pragma unroll
+                for (int q = 0; q < 6; ++q) {
+                    const int set = q / 3, kw = q - set * 3;
+                    uint32_t a0 = (uint32_t)a_desc0 + x16 + (uint32_t)((set * p.G + kw) * 128 >> 4);
+                    uint32_t b0 = (uint32_t)b_desc0 + y16;
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(q * 64);
+                    for (int ks = 0; ks < p.ksteps; ++ks) {
+                        umma_f16(d_tmem, ((uint64_t)a_hi << 32) | a0, ((uint64_t)b_hi << 32) | b0, idesc, (j > 0 || ks > 0) ? 1u : 0u);
+                        a0 += 2048u >> 4; b0 += 2048u >> 4;
+                    }
+                }
+                umma_commit(&empty[st]);
+            }
+            __syncwarp();
+            if (++st == p.stages) { st = 0; ph ^= 1u; }
+        }
+        if (any_tile && elect_one()) umma_commit(done);
+        __syncwarp();
+        tc_fence_before();
+    } else {
+        int st = 0;
+        uint32_t ph = 0;
+        for (int t = part; t < p.tiles; t += nparts) {
+            mbar_wait(&empty[st], ph ^ 1u);
+            if (elect_one()) {
+                const int n0 = t * p.BI;
+                const uint32_t ydst = smem_u32(smem) + (uint32_t)st * (uint32_t)p.stage_bytes;
+                mbar_expect_tx(&full[st], (uint32_t)(p.y_tx + p.x_tx));
+                tma_load_4d(ydst, &mapY, &full[st], co0, 0, 0, n0);
+                tma_load_4d(ydst + (uint32_t)y_bytes, &mapX, &full[st], c0, -1, -1, n0);
+            }
+            __syncwarp();
+            if (++st == p.stages) { st = 0; ph ^= 1u; }
+        }
+    }
+    __syncthreads();
+    if (warp == 4) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
 // tile width: as wide as possible (<= 256, multiple of 16, awkward N such as 180 / 720 / 1080 split evenly), but narrow
 // enough that small problems still put >= ~100 CTAs on the 148 SMs (never below 64 columns)
 int pick_bn(int N, int mtiles) {
@@ -2111,8 +2230,65 @@ static int conv_halo_launch(const avec_gemm_args* a, cudaStream_t st) {
     return AVEC_OK;
 }
 
+// ---- whole-image resident-dW wgrad (see wgrad_img_kernel)
+static bool wgrad_img_plan(const avec_gemm_args* a, WgImgParams& p) {
+    const avec_conv_geom& g = a->g;
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("AVEC_WGRAD_IMG"); on = e ? atoi(e) : 1; }
+    if (!on || a->mode != AVEC_GEMM_CONV_WGRAD || !g_tma_enabled || get_encode() == nullptr || a->ab_dtype != AVEC_BF16) return false;
+    if (!(g.KT == 1 && g.Ti == 1 && g.st == 1 && g.sh == 1 && g.sw == 1 && g.KH == 3 && g.KW == 3 && g.ph == 1 && g.pw == 1)) return false;
+    if (g.C % 64 != 0 || g.Co % 64 != 0 || g.Ho != g.Hi || g.Wo != g.Wi) return false;
+    if (a->epi != AVEC_EPI_ACCUM || a->out_dtype != AVEC_F32 || a->ldo != 9LL * g.C || a->bias || a->colstats) return false;
+    if ((reinterpret_cast<uintptr_t>(a->A) % 16) != 0 || (reinterpret_cast<uintptr_t>(a->B) % 16) != 0) return false;
+    memset(&p, 0, sizeof(p));
+    p.N = g.N; p.H = g.Hi; p.W = g.Wi; p.C = g.C; p.Co = g.Co;
+    p.G = (g.Wi + 2 + 7) / 8 * 8;
+    const int P = (g.Hi + 2) * p.G;                     // rows per image (dY grid and X halo share the pitch)
+    if (p.G > 32 || P > 256 || g.Hi * g.Wi * 5 < P * 2) return false;   // at least 40 % of the grid must be real sites
+    p.BI = 1;
+    while ((p.BI + 1) * P <= 128) ++p.BI;
+    while ((p.BI * P) % 16 != 0) ++p.BI;                 // P is a multiple of 8
+    if (p.BI * P > 256 || p.BI > 256) return false;
+    p.k_rows = p.BI * P; p.ksteps = p.k_rows / 16;
+    p.x_rows = p.k_rows + 2 * p.G + 8;
+    p.stage_bytes = ((p.k_rows + p.x_rows) * 128 + 1023) / 1024 * 1024;
+    p.stages = (int)std::min<size_t>(6, (WI_SMEM_MAX - 2048) / p.stage_bytes);
+    if (p.stages < 2) return false;
+    p.ncb = g.C / 64; p.ncob = g.Co / 64;
+    if (p.ncb * p.ncob > num_sms_cached()) return false;
+    p.tiles = cdiv(g.N, p.BI);
+    p.y_tx = p.k_rows * 128; p.x_tx = p.k_rows * 128;
+    p.alpha = a->alpha; p.dw = reinterpret_cast<float*>(a->out);
+    return true;
+}
+
+static int wgrad_img_launch(const avec_gemm_args* a, const WgImgParams& p, cudaStream_t st) {
+    CUtensorMap mapY, mapX;
+    cuuint64_t dY[4] = {(cuuint64_t)p.Co, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.N};
+    cuuint64_t sY[3] = {(cuuint64_t)p.Co * 2, (cuuint64_t)p.W * p.Co * 2, (cuuint64_t)p.W * p.H * p.Co * 2};
+    cuuint64_t dX[4] = {(cuuint64_t)p.C, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.N};
+    cuuint64_t sX[3] = {(cuuint64_t)p.C * 2, (cuuint64_t)p.W * p.C * 2, (cuuint64_t)p.W * p.H * p.C * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)p.G, (cuuint32_t)(p.H + 2), (cuuint32_t)p.BI};
+    if (!encode_map(&mapY, a->A, 4, dY, sY, box) || !encode_map(&mapX, a->B, 4, dX, sX, box)) return AVEC_ERR_DRIVER;
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(wgrad_img_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WI_SMEM_MAX) != cudaSuccess) return AVEC_ERR_LAUNCH;
+        attr_set = true;
+    }
+    const int nblocks = p.ncb * p.ncob;
+    const int parts = std::max(1, std::min(num_sms_cached() / nblocks, p.tiles));
+    const size_t smem = 1024 + (size_t)p.stages * p.stage_bytes + 1024;
+    wgrad_img_kernel<<<nblocks * parts, WI_THREADS, smem, st>>>(p, mapY, mapX);
+    AVEC_LAUNCH_CHECK();
+    return AVEC_OK;
+}
+
 int avec_gemm_tc(const avec_gemm_args* a, cudaStream_t st) {
     if (wgrad_halo_ok(a)) return wgrad_halo_launch(a, st);
+    {
+        WgImgParams wp;
+        if (wgrad_img_plan(a, wp)) return wgrad_img_launch(a, wp, st);
+    }
     if (conv_halo_ok(a)) return conv_halo_launch(a, st);
     if (dgrad_classes_ok(a)) {
         for (int ca = 0; ca < 2; ++ca)

@@ -323,38 +323,52 @@ def main():
 
 
 def profile_gemm(step_fn, ops):
-    """one extra step with a CUDA-event pair around every avec_gemm launch: sum of durations and of 2*M*N*K."""
-    recs = []
+    """CUDA-event pair around every tcgen05 GEMM / conv launch of an eager step: summed durations and summed 2*M*N*K.
+    The step is run three times behind a device-side sleep (so the host runs ahead of the GPU and an event window holds the
+    kernel, not host launch latency) and every launch keeps the minimum of its three windows."""
     orig = ops._gemm
-
-    def hooked(a):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        orig(a)
-        e1.record()
-        recs.append((e0, e1, 2.0 * a.M * a.N * a.K))
-    ops._gemm = hooked
     stem_orig = (ops.stem3d_fwd, ops.stem3d_wgrad)
+    runs = []
+    for _ in range(3):
+        recs = []
 
-    def timed_stem(fn):
-        def wrapper(x, *a, **k):
+        def hooked(a, recs=recs):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            out = fn(x, *a, **k)
+            orig(a)
             e1.record()
-            B_, T_, H_, W_ = x.shape[0], x.shape[1], x.shape[2], x.shape[3]
-            recs.append((e0, e1, 2.0 * B_ * T_ * (H_ // 2) * (W_ // 2) * 64 * 245))
-            return out
-        return wrapper
-    ops.stem3d_fwd, ops.stem3d_wgrad = timed_stem(stem_orig[0]), timed_stem(stem_orig[1])
-    try:
-        step_fn()
-        torch.cuda.synchronize()
-    finally:
-        ops._gemm = orig
-        ops.stem3d_fwd, ops.stem3d_wgrad = stem_orig
-    ms = sum(e0.elapsed_time(e1) for e0, e1, _ in recs)
-    return ms, sum(f for _, _, f in recs), len(recs)
+            recs.append((e0, e1, 2.0 * a.M * a.N * a.K, (a.mode, a.M, a.N, a.K)))
+
+        def timed_stem(fn, recs=recs):
+            def wrapper(x, *a, **k):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                out = fn(x, *a, **k)
+                e1.record()
+                B_, T_, H_, W_ = x.shape[0], x.shape[1], x.shape[2], x.shape[3]
+                recs.append((e0, e1, 2.0 * B_ * T_ * (H_ // 2) * (W_ // 2) * 64 * 245, ("stem3d", B_ * T_, H_, W_)))
+                return out
+            return wrapper
+        ops._gemm = hooked
+        ops.stem3d_fwd, ops.stem3d_wgrad = timed_stem(stem_orig[0]), timed_stem(stem_orig[1])
+        try:
+            torch.cuda._sleep(int(0.05 * 1.9e9))
+            step_fn()
+            torch.cuda.synchronize()
+        finally:
+            ops._gemm = orig
+            ops.stem3d_fwd, ops.stem3d_wgrad = stem_orig
+        runs.append([(e0.elapsed_time(e1), f, key) for e0, e1, f, key in recs])
+    n = min(len(r) for r in runs)
+    best = [min(r[i][0] for r in runs) for i in range(n)]
+    if os.environ.get("AVEC_BENCH_VERBOSE"):
+        agg = {}
+        for i in range(n):
+            k = runs[0][i][2]
+            agg[k] = agg.get(k, 0.0) + best[i]
+        for k, v in sorted(agg.items(), key=lambda kv: -kv[1])[:12]:
+            print(f"[bench] gemm {k}: {v:.3f} ms", file=sys.stderr)
+    return sum(best), sum(runs[0][i][1] for i in range(n)), n
 
 
 if __name__ == "__main__":
