@@ -17,6 +17,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <algorithm>
+#include <type_traits>
 
 namespace {
 
@@ -1767,8 +1768,8 @@ __global__ void __launch_bounds__(WH_THREADS, 1) wgrad_halo64_kernel(const __gri
 // of weights stay resident in shared memory for the whole persistent CTA, ONE halo tile ((BH+2) x (W+2) sites x 64 ch,
 // 21 KB) is loaded per output tile and all 36 MMAs of the tile (9 taps x 4 K-steps; tap = 128-byte row offset into the halo
 // tile) are issued behind a single barrier wait.  Accumulator rows live on the (W+2)-wide halo grid; the fast epilogue maps
-// them to output rows through a small table and skips the two pad columns.  Two epilogue warpgroups alternate tiles (one
-// TMEM accumulator each), because at 64 columns a tile is only ~1150 tensor-pipe cycles - about one epilogue.
+// them to output rows through a small table and skips the two pad columns.  Two epilogue warpgroups alternate tiles (two
+// TMEM accumulators each, so the MMA warp can run two tiles ahead of either group), because at 64 columns a tile is only ~1150 tensor-pipe cycles - about one epilogue.
 // warps 0-3 / 4-7: epilogue groups, warp 8: MMA issuer + TMEM + weight TMA, warp 9: halo TMA producer
 constexpr int CH_THREADS = 320;
 constexpr int CH_W_BYTES = 9 * 64 * 128;      // 73728
@@ -1791,23 +1792,23 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv3x3_halo64_kernel(const __g
     uint8_t* ctrl = reinterpret_cast<uint8_t*>(stg_all) + 2 * STG_BYTES;
     uint64_t* x_full = reinterpret_cast<uint64_t*>(ctrl);     // [3]
     uint64_t* x_empty = x_full + 4;                             // [3]
-    uint64_t* accum_full = x_empty + 4;                         // [2]
-    uint64_t* accum_empty = accum_full + 2;                     // [2]
-    uint64_t* w_full = accum_empty + 2;                         // [1]
+    uint64_t* accum_full = x_empty + 4;                         // [4]: two TMEM accumulators per epilogue warpgroup
+    uint64_t* accum_empty = accum_full + 4;                     // [4]
+    uint64_t* w_full = accum_empty + 4;                         // [1]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_full + 2);
-    float* bias_s = reinterpret_cast<float*>(ctrl + 128);       // [64]
-    int* rowrel = reinterpret_cast<int*>(ctrl + 128 + 256);     // [128]
+    float* bias_s = reinterpret_cast<float*>(ctrl + 192);       // [64]
+    int* rowrel = reinterpret_cast<int*>(ctrl + 192 + 256);     // [128]
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     if (tid == 0) {
         for (int i = 0; i < CH_STAGES; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&accum_full[i], 1); mbar_init(&accum_empty[i], 128); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&accum_full[i], 1); mbar_init(&accum_empty[i], 128); }
         mbar_init(w_full, 1);
         fence_barrier_init();
         tma_prefetch_desc(&mapX);
         tma_prefetch_desc(&mapW);
     }
-    if (warp == 8) tmem_alloc(tmem_slot, 128);
+    if (warp == 8) tmem_alloc(tmem_slot, 256);
     if (tid < 64) bias_s[tid] = p.tc.ep.bias ? p.tc.ep.bias[tid] : 0.0f;
     if (tid < 128) {
         const int hh = tid / p.W2, ww = tid - hh * p.W2;
@@ -1831,16 +1832,17 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv3x3_halo64_kernel(const __g
             ti.mtile = t; ti.n0 = 0; ti.z = 0; ti.kb_begin = 0; ti.nkb = 0; ti.m0 = 0;
             ti.row_base = ((long long)n * p.H + h0) * p.W;
             ti.rows_valid = min(p.BH, p.H - h0) * p.W2;
-            mbar_wait(&accum_full[grp], (uint32_t)((j >> 1) & 1));
+            const int buf = grp * 2 + ((j >> 1) & 1);   // this group's k-th tile (k = j >> 1) uses its accumulator k & 1
+            mbar_wait(&accum_full[buf], (uint32_t)((j >> 2) & 1));
             tc_fence_after();
-            const uint32_t lane_addr = tmem_base + ((uint32_t)(w4 * 32) << 16) + (uint32_t)(grp * 64);
+            const uint32_t lane_addr = tmem_base + ((uint32_t)(w4 * 32) << 16) + (uint32_t)(buf * 64);
             float* stats_dst = ep.colstats ? ep.colstats + (size_t)(t % AVEC_STATS_REPLICAS) * 2 * 64 : nullptr;
             const bool bias_on = p.tc.ep.bias != nullptr;
             if (ep.kind == AVEC_EPI_RESIDUAL) epilogue_fast<AVEC_EPI_RESIDUAL, false, true>(p.tc, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, w4, lane, bias_on, rowrel_sa);
             else if (ep.colstats) epilogue_fast<AVEC_EPI_LINEAR, true, true>(p.tc, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, w4, lane, bias_on, rowrel_sa);
             else epilogue_fast<AVEC_EPI_LINEAR, false, true>(p.tc, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, w4, lane, bias_on, rowrel_sa);
             tc_fence_before();
-            mbar_arrive(&accum_empty[grp]);
+            mbar_arrive(&accum_empty[buf]);
         }
         tc_fence_before();
     } else if (warp == 8) {
@@ -1859,8 +1861,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv3x3_halo64_kernel(const __g
         int j = 0, st = 0;
         uint32_t ph = 0;
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++j) {
-            const int buf = j & 1;
-            mbar_wait(&accum_empty[buf], (uint32_t)(((j >> 1) & 1) ^ 1));
+            const int buf = (j & 1) * 2 + ((j >> 1) & 1);
+            mbar_wait(&accum_empty[buf], (uint32_t)(((j >> 2) & 1) ^ 1));
             mbar_wait(&x_full[st], ph);
             tc_fence_after();
             if (elect_one()) {
@@ -1900,7 +1902,7 @@ __global__ void __launch_bounds__(CH_THREADS, 1) conv3x3_halo64_kernel(const __g
         }
     }
     __syncthreads();
-    if (warp == 8) { tc_fence_after(); tmem_dealloc(tmem_base, 128); }
+    if (warp == 8) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
 }
 
 // ---- the same resident-dW scheme for the wider 3x3 stride-1 stages whose images fit one tile (ResNet stage 2: 11 x 11 x 128,
@@ -1983,17 +1985,32 @@ __global__ void __launch_bounds__(WI_THREADS, 1) wgrad_img_kernel(const __grid_c
             if (elect_one()) {
                 const uint32_t y16 = base16 + (uint32_t)st * ((uint32_t)p.stage_bytes >> 4);
                 const uint32_t x16 = y16 + ((uint32_t)y_bytes >> 4);
+                // the issue loop is instruction bound (one MMA = 32 tensor-pipe cycles): fully unrolled for the two tile depths
+                // the model uses (8 k-steps: two 6x6 images, 13: one 11x11 image) so that descriptor offsets are immediates
+                auto issue = [&](auto KS) {
+                    constexpr int NKS = decltype(KS)::value;
+                    const int nks = NKS > 0 ? NKS : p.ksteps;
 #pragma unroll
-                for (int q = 0; q < 6; ++q) {
-                    const int set = q / 3, kw = q - set * 3;
-                    uint32_t a0 = (uint32_t)a_desc0 + x16 + (uint32_t)((set * p.G + kw) * 128 >> 4);
-                    uint32_t b0 = (uint32_t)b_desc0 + y16;
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(q * 64);
-                    for (int ks = 0; ks < p.ksteps; ++ks) {
-                        umma_f16(d_tmem, ((uint64_t)a_hi << 32) | a0, ((uint64_t)b_hi << 32) | b0, idesc, (j > 0 || ks > 0) ? 1u : 0u);
-                        a0 += 2048u >> 4; b0 += 2048u >> 4;
+                    for (int q = 0; q < 6; ++q) {
+                        const int set = q / 3, kw = q - set * 3;
+                        const uint32_t a0 = (uint32_t)a_desc0 + x16 + (uint32_t)((set * p.G + kw) * 128 >> 4);
+                        const uint32_t b0 = (uint32_t)b_desc0 + y16;
+                        const uint32_t d_tmem = tmem_base + (uint32_t)(q * 64);
+                        if (NKS > 0) {
+#pragma unroll
+                            for (int ks = 0; ks < (NKS > 0 ? NKS : 1); ++ks)
+                                umma_f16(d_tmem, ((uint64_t)a_hi << 32) | (a0 + (uint32_t)ks * (2048u >> 4)), ((uint64_t)b_hi << 32) | (b0 + (uint32_t)ks * (2048u >> 4)),
+                                         idesc, (j > 0 || ks > 0) ? 1u : 0u);
+                        } else {
+                            for (int ks = 0; ks < nks; ++ks)
+                                umma_f16(d_tmem, ((uint64_t)a_hi << 32) | (a0 + (uint32_t)ks * (2048u >> 4)), ((uint64_t)b_hi << 32) | (b0 + (uint32_t)ks * (2048u >> 4)),
+                                         idesc, (j > 0 || ks > 0) ? 1u : 0u);
+                        }
                     }
-                }
+                };
+                if (p.ksteps == 8) issue(std::integral_constant<int, 8>{});
+                else if (p.ksteps == 13) issue(std::integral_constant<int, 13>{});
+                else issue(std::integral_constant<int, 0>{});
                 umma_commit(&empty[st]);
             }
             __syncwarp();
