@@ -25,6 +25,7 @@ constexpr int BM = 128;
 constexpr int BKE = 64;                  // reduction elements per k-block (one 128-byte swizzle row)
 constexpr int PRODUCER_THREADS = 128;
 constexpr int TC_THREADS = 192;   // warps 0-3 gather producers + epilogue, warp 4 MMA issuer, warp 5 TMA producer
+constexpr int TC_THREADS_WIDE = 320;   // + warps 6-9: second epilogue warpgroup (tiles wider than 64 columns: it takes the odd slabs)
 
 enum OperandKind {
     OP_PLAIN_K = 0,    // element (row, k) at base[row*ld + k]               -> K-major tile
@@ -676,7 +677,8 @@ __device__ __forceinline__ void unpack_bf16x8(const uint4& t, float (&v)[8]) {
 // use, bias kept in registers (a lane owns the same 8 columns in every pass).
 template <int KIND, bool STATS, bool AL16>
 __device__ __forceinline__ void epilogue_fast(const TcParams& p, const EpiParams& ep, const TileInfo& ti, uint32_t lane_addr, uint32_t stg_s,
-                                              uint32_t bias_sa, float* stats_dst, int warp, int lane, bool bias_on, uint32_t rowrel_sa = 0u) {
+                                              uint32_t bias_sa, float* stats_dst, int warp, int lane, bool bias_on, uint32_t rowrel_sa = 0u,
+                                              int slab0 = 0, int slab_step = 64) {
     const int BN = p.BN;
     const int q = lane & 7, rs = lane >> 3;
     const int lc = q * 8;
@@ -693,7 +695,7 @@ __device__ __forceinline__ void epilogue_fast(const TcParams& p, const EpiParams
         }
         return ti.row_base + r;
     };
-    for (int c0 = 0; c0 < BN; c0 += 64) {
+    for (int c0 = slab0; c0 < BN; c0 += slab_step) {   // with two epilogue warpgroups each takes every other 64-column slab
         const int ncol = min(64, BN - c0);   // multiple of 16
         const int gc = ti.n0 + c0 + lc;
         const bool col_ok = lc < ncol && gc < p.N;
@@ -822,10 +824,10 @@ __device__ __forceinline__ void epilogue_fast(const TcParams& p, const EpiParams
 // line of bf16), 4 rows per instruction.  Bias, activation, residual / Swish' operands, fp32 split-K reductions and the
 // BatchNorm column statistics are all applied in that coalesced domain.
 __device__ __forceinline__ void epilogue_warp(const TcParams& p, const EpiParams& ep, const TileInfo& ti, uint32_t lane_addr, float* stg,
-                                              const float* bias_s, float* stats_dst, int warp, int lane) {
+                                              const float* bias_s, float* stats_dst, int warp, int lane, int slab0 = 0, int slab_step = 64) {
     const int BN = p.BN;
     const int q = lane & 7, rs = lane >> 3;
-    for (int c0 = 0; c0 < BN; c0 += 64) {
+    for (int c0 = slab0; c0 < BN; c0 += slab_step) {
         const int ncol = min(64, BN - c0);   // multiple of 16
         // ---- row domain: TMEM -> registers (+ bias) -> staging
         for (int cc = 0; cc < ncol; cc += 32) {
@@ -946,24 +948,24 @@ __device__ __forceinline__ void epilogue_warp(const TcParams& p, const EpiParams
 
 template <bool AL16>
 __device__ __forceinline__ void epilogue_fast_dispatch(const TcParams& p, const EpiParams& ep, const TileInfo& ti, uint32_t lane_addr, uint32_t stg_s,
-                                                       uint32_t bias_sa, float* stats_dst, int warp, int lane, bool bias_on, uint32_t rowrel_sa) {
+                                                       uint32_t bias_sa, float* stats_dst, int warp, int lane, bool bias_on, uint32_t rowrel_sa, int slab0, int slab_step) {
     switch (ep.kind) {
     case AVEC_EPI_LINEAR:
-        if (ep.colstats) epilogue_fast<AVEC_EPI_LINEAR, true, AL16>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane, bias_on, rowrel_sa);
-        else epilogue_fast<AVEC_EPI_LINEAR, false, AL16>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane, bias_on, rowrel_sa);
+        if (ep.colstats) epilogue_fast<AVEC_EPI_LINEAR, true, AL16>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane, bias_on, rowrel_sa, slab0, slab_step);
+        else epilogue_fast<AVEC_EPI_LINEAR, false, AL16>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane, bias_on, rowrel_sa, slab0, slab_step);
         break;
-    case AVEC_EPI_SWISH: epilogue_fast<AVEC_EPI_SWISH, false, AL16>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane, bias_on, rowrel_sa); break;
-    case AVEC_EPI_RESIDUAL: epilogue_fast<AVEC_EPI_RESIDUAL, false, AL16>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane, bias_on, rowrel_sa); break;
-    case AVEC_EPI_DSWISH: epilogue_fast<AVEC_EPI_DSWISH, false, AL16>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane, bias_on, rowrel_sa); break;
-    case AVEC_EPI_ACCUM: epilogue_fast<AVEC_EPI_ACCUM, false, AL16>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane, bias_on, rowrel_sa); break;
-    default: epilogue_fast<AVEC_EPI_RELU, false, AL16>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane, bias_on, rowrel_sa); break;
+    case AVEC_EPI_SWISH: epilogue_fast<AVEC_EPI_SWISH, false, AL16>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane, bias_on, rowrel_sa, slab0, slab_step); break;
+    case AVEC_EPI_RESIDUAL: epilogue_fast<AVEC_EPI_RESIDUAL, false, AL16>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane, bias_on, rowrel_sa, slab0, slab_step); break;
+    case AVEC_EPI_DSWISH: epilogue_fast<AVEC_EPI_DSWISH, false, AL16>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane, bias_on, rowrel_sa, slab0, slab_step); break;
+    case AVEC_EPI_ACCUM: epilogue_fast<AVEC_EPI_ACCUM, false, AL16>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane, bias_on, rowrel_sa, slab0, slab_step); break;
+    default: epilogue_fast<AVEC_EPI_RELU, false, AL16>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane, bias_on, rowrel_sa, slab0, slab_step); break;
     }
 }
 
 // Persistent, warp-specialised: every CTA walks the tile list t = blockIdx.x, blockIdx.x + gridDim.x, ... ; the smem ring
 // and its phases run on across tiles, and the accumulator is double-buffered in TMEM (2 x BN columns) so that the epilogue
 // of tile j overlaps the TMA + MMA main loop of tile j + 1.
-__global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUtensorMap mapA,
+__global__ void __launch_bounds__(TC_THREADS_WIDE, 1) gemm_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUtensorMap mapA,
                                                                const __grid_constant__ CUtensorMap mapB) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem_al = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -973,7 +975,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
     const int a_bytes = p.a_rows * 128;
     const int b_bytes = ((p.b_rows * 128 + 1023) / 1024) * 1024;
     const int stage_bytes = a_bytes + b_bytes;
-    uint8_t* ctrl = smem + (size_t)p.stages * stage_bytes + (p.stg_dedicated ? STG_BYTES : 0);
+    const int epi_groups = blockDim.x > TC_THREADS ? 2 : 1;
+    uint8_t* ctrl = smem + (size_t)p.stages * stage_bytes + (p.stg_dedicated ? STG_BYTES * epi_groups : 0);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);
     uint64_t* empty_bar = full_bar + 8;
     uint64_t* accum_full = empty_bar + 8;    // [2]
@@ -1000,7 +1003,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
         const uint32_t full_count = (any_gather ? PRODUCER_THREADS : 0) + (any_tma ? 1 : 0);
         for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], full_count); mbar_init(&empty_bar[s], 1); }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&accum_full[i], 1); mbar_init(&accum_empty[i], PRODUCER_THREADS);
+            mbar_init(&accum_full[i], 1); mbar_init(&accum_empty[i], PRODUCER_THREADS * epi_groups);
             mbar_init(&halo_full[i], 1); mbar_init(&halo_empty[i], 1);
         }
         fence_barrier_init();
@@ -1009,7 +1012,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
     }
     if (warp == 4) tmem_alloc(tmem_slot, ncols);
     if (p.a_kind == OP_CONV_TAPS || p.b_kind == OP_CONV_TAPS_MN) {
-        for (int tap = tid; tap < 256; tap += TC_THREADS) {
+        for (int tap = tid; tap < 256; tap += blockDim.x) {
             int t = tap;
             const int kw = t % p.g.KW; t /= p.g.KW; const int kh = t % p.g.KH; const int kt = t / p.g.KH;
             tapofs[tap] = kt | (kh << 8) | (kw << 16);
@@ -1020,7 +1023,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
     if (p.a_kind == OP_TMA_CONV_MN || p.b_kind == OP_TMA_CONV_MN) {
         uint4* z = reinterpret_cast<uint4*>(smem);
         const int n16 = p.stages * stage_bytes / 16;
-        for (int i = tid; i < n16; i += TC_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = tid; i < n16; i += blockDim.x) z[i] = make_uint4(0u, 0u, 0u, 0u);
         fence_proxy_async();
     }
     tc_fence_before();
@@ -1029,15 +1032,18 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
     const uint32_t tmem_base = *tmem_slot;
     if (tid == 0) AVEC_TS(1);   // setup done (barriers, TMEM alloc)
 
-    if (warp < 4) {
+    if (warp < 4 || warp >= 6) {
         // ===================== gather producers (when an operand is not TMA-fed), then epilogue =====================
-        if (p.rm_on) {
+        // warps 0-3: producers + epilogue warpgroup 0; warps 6-9 (wide launches): epilogue warpgroup 1 (odd 64-column slabs)
+        const int grp = warp >= 6 ? 1 : 0, qw = warp & 3;   // qw = TMEM lane quarter this warp may access
+        const int nepi = PRODUCER_THREADS * epi_groups;
+        if (p.rm_on && grp == 0) {
             // tile row r = ((image il) * ct_H' + row i) * ct_W + column j  ->  relative output row on the strided grid
             const int per_img = p.ct_BI == 1 ? 0x7fffffff : p.ct_H * p.ct_W;
             const int il = tid / per_img, rem = tid - il * per_img;
             const int i = rem / p.ct_W, j = rem - i * p.ct_W;
             reinterpret_cast<int*>(rinfo)[tid] = (il * p.rm_Hi + p.rm_sy * i) * p.rm_Wi + p.rm_sx * j;
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 3, 128;" ::: "memory");   // (warpgroup 1 sees the table after the first refresh barrier)
         }
         int it = 0;   // k-blocks pushed through the ring so far
         int j = 0;    // local tile counter
@@ -1051,10 +1057,12 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
             const bool refresh = j == 0 || n0 != cur_n0 || (ti.z == 0) != cur_bias_on;
             cur_n0 = n0; cur_bias_on = ti.z == 0;
             if (refresh) {
-            asm volatile("bar.sync 1, 128;" ::: "memory");   // previous tile's epilogue has released bias_s / rinfo
+            asm volatile("bar.sync 1, %0;" ::"r"(nepi) : "memory");   // previous tile's epilogues have released bias_s / rinfo
+            if (grp == 0) {
             for (int c = tid; c < 256; c += PRODUCER_THREADS)
                 bias_s[c] = (p.ep.bias && ti.z == 0 && c < BN && n0 + c < p.N) ? p.ep.bias[n0 + c] : 0.0f;
-            if (p.a_kind == OP_CONV_FWD || p.a_kind == OP_CONV_DGRAD || p.a_kind == OP_CONV_TAPS) {
+            }
+            if (grp == 0 && (p.a_kind == OP_CONV_FWD || p.a_kind == OP_CONV_DGRAD || p.a_kind == OP_CONV_TAPS)) {
                 // per-row site decode for the conv gathers (A operand rows are fixed for the whole tile)
                 RowInfo ri; ri.n = -1; ri.t = ri.h = ri.w = 0;
                 long long m = (long long)ti.m0 + tid;
@@ -1071,9 +1079,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
                 }
                 rinfo[tid] = ri;
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"r"(nepi) : "memory");
             }
-            if (any_gather) {
+            if (any_gather && grp == 0) {
                 // cp.async groups: k-block i is published (proxy fence + mbarrier arrive) LAG iterations after it was issued,
                 // so each thread keeps up to LAG+1 k-blocks of loads in flight (stages >= LAG + 1)
                 constexpr int LAG = 2;
@@ -1100,7 +1108,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
             it += nkb;
             // ---------------- epilogue of tile j (accumulator buffer j & 1) ----------------
             const int buf = j & 1;
-            const int r = warp * 32 + lane;
+            const int r = qw * 32 + lane;
             const bool rv = r < ti.rows_valid;
             const long long row = ti.row_base + r;
             // pull this thread's residual / auxiliary row segment towards L1 while the MMAs are still running
@@ -1116,17 +1124,18 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
             tc_fence_after();
             if (tid == 0 && j == 0) AVEC_TS(4);   // accumulator complete, epilogue starts
             if (tid == 0) AVEC_TSJ(j, 1);
-            const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * BN);
+            const uint32_t lane_addr = tmem_base + ((uint32_t)(qw * 32) << 16) + (uint32_t)(buf * BN);
             EpiParams ep = p.ep;
             ep.bias = nullptr;   // the bias slice lives in shared memory (bias_s)
-            float* stg = (p.stg_dedicated ? reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes) : reinterpret_cast<float*>(smem)) + warp * STG_WARP;
+            float* stg = (p.stg_dedicated ? reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes) : reinterpret_cast<float*>(smem)) + grp * (STG_BYTES / 4) + qw * STG_WARP;
+            const int slab0 = grp * 64, slab_step = 64 * epi_groups;
             // BatchNorm statistics go to one of AVEC_STATS_REPLICAS copies of the accumulator (by tile index): 32x fewer
             // same-address L2 reductions
             float* stats_dst = ep.colstats ? ep.colstats + (size_t)(ti.mtile % AVEC_STATS_REPLICAS) * 2 * p.N : nullptr;
             const bool bias_on = p.ep.bias != nullptr && ti.z == 0;
-            if (p.epi_fast == 2) epilogue_fast_dispatch<true>(p, ep, ti, lane_addr, smem_u32(stg), smem_u32(bias_s), stats_dst, warp, lane, bias_on, smem_u32(rinfo));
-            else if (p.epi_fast == 1) epilogue_fast_dispatch<false>(p, ep, ti, lane_addr, smem_u32(stg), smem_u32(bias_s), stats_dst, warp, lane, bias_on, smem_u32(rinfo));
-            else epilogue_warp(p, ep, ti, lane_addr, stg, bias_s, stats_dst, warp, lane);
+            if (p.epi_fast == 2) epilogue_fast_dispatch<true>(p, ep, ti, lane_addr, smem_u32(stg), smem_u32(bias_s), stats_dst, qw, lane, bias_on, smem_u32(rinfo), slab0, slab_step);
+            else if (p.epi_fast == 1) epilogue_fast_dispatch<false>(p, ep, ti, lane_addr, smem_u32(stg), smem_u32(bias_s), stats_dst, qw, lane, bias_on, smem_u32(rinfo), slab0, slab_step);
+            else epilogue_warp(p, ep, ti, lane_addr, stg, bias_s, stats_dst, qw, lane, slab0, slab_step);
             // all TMEM reads of this buffer are complete: hand it back to the MMA warp
             tc_fence_before();
             mbar_arrive(&accum_empty[buf]);
@@ -2496,6 +2505,10 @@ static int gemm_tc_launch(const avec_gemm_args* a, cudaStream_t st, const DgradC
     const size_t ctrl_bytes = 256 + BM * sizeof(RowInfo) + 256 * sizeof(int) + 256 * sizeof(float) + 1024;
     size_t smem;
     int ctas_per_sm = 1;
+    // second epilogue warpgroup for tiles wider than one 64-column slab (the epilogue of a 128 x 256 tile is 4 slabs of ~1.3 us)
+    static int epi2 = -1;
+    if (epi2 < 0) { const char* e = getenv("AVEC_EPI2"); epi2 = e ? atoi(e) : 1; }
+    int epi_groups = (epi2 && p.BN > 64) ? 2 : 1;
     const long long tiles_for_cta2 = (long long)grid_m * cdiv(a->N, p.BN) * split;
     if (any_gather) {
         // one tile per CTA; the epilogue staging aliases the drained ring; <= 32 KB stages allow 2 CTAs / SM
@@ -2503,15 +2516,17 @@ static int gemm_tc_launch(const avec_gemm_args* a, cudaStream_t st, const DgradC
         while (p.stages > 3 && (size_t)p.stages * stage_bytes + ctrl_bytes > 227 * 1024) --p.stages;
         p.stg_dedicated = 0;
         smem = (size_t)p.stages * stage_bytes + ctrl_bytes;
+        if ((size_t)p.stages * stage_bytes < (size_t)STG_BYTES * epi_groups) epi_groups = 1;
         if (smem > 227 * 1024 || (size_t)p.stages * stage_bytes < STG_BYTES) return AVEC_ERR_UNSUPPORTED;
     } else {
         // persistent: one CTA per SM, as many ring stages as fit beside the dedicated epilogue staging
         p.stg_dedicated = 1;
         p.stages = 8;
-        while (p.stages > 2 && (size_t)p.stages * stage_bytes + STG_BYTES + ctrl_bytes > 227 * 1024) --p.stages;
+        const size_t stg_total = (size_t)STG_BYTES * epi_groups;
+        while (p.stages > 2 && (size_t)p.stages * stage_bytes + stg_total + ctrl_bytes > 227 * 1024) --p.stages;
         const size_t halo_total = 2 * (size_t)p.cpb * p.halo_bytes;
-        while (p.stages > 2 && halo_total + (size_t)p.stages * stage_bytes + STG_BYTES + ctrl_bytes > 227 * 1024) --p.stages;
-        smem = halo_total + (size_t)p.stages * stage_bytes + STG_BYTES + ctrl_bytes;
+        while (p.stages > 2 && halo_total + (size_t)p.stages * stage_bytes + stg_total + ctrl_bytes > 227 * 1024) --p.stages;
+        smem = halo_total + (size_t)p.stages * stage_bytes + stg_total + ctrl_bytes;
         if (smem > 227 * 1024) return AVEC_ERR_UNSUPPORTED;
         // narrow tiles (BN <= 64: a k-block is only 128 tensor-pipe cycles, the epilogue and the per-k-block handshakes are
         // latency bound): two co-resident CTAs per SM interleave their MMA streams and run two epilogues at a time
@@ -2558,7 +2573,7 @@ static int gemm_tc_launch(const avec_gemm_args* a, cudaStream_t st, const DgradC
     // persistent launch when both operands are TMA-fed (the gather producers double as epilogue warps, so gather kinds keep
     // one tile per CTA); two CTAs per SM when shared memory and TMEM (2 x BN columns each) allow it
     long long ctas = any_gather ? tiles : std::min<long long>(tiles, (long long)num_sms * ctas_per_sm);
-    gemm_tc_kernel<<<(unsigned)ctas, TC_THREADS, smem, st>>>(p, mapA, mapB);
+    gemm_tc_kernel<<<(unsigned)ctas, epi_groups == 2 ? TC_THREADS_WIDE : TC_THREADS, smem, st>>>(p, mapA, mapB);
     AVEC_LAUNCH_CHECK();
     return AVEC_OK;
 }
