@@ -464,6 +464,110 @@ struct BnBwdF {
     }
 };
 
+// BatchNorm-backward column reduction (sum dz, sum dz * xhat), the heaviest of the column reductions (39 launches per AV step
+// over up to 400 MB tensors).  Same block shape as colreduce_kernel, but the loop is memory-level-parallelism bound (3.7 TB/s with
+// 12 loads in flight per thread, 2.7 TB/s with 8), so the raw 16-byte vectors of ROWS rows are all requested before the first
+// one is consumed: 12 (no residual) / 15 (residual) 16-byte loads in flight per thread for bf16.
+template <typename T, int V> struct alignas(16) RawVec { T v[V]; };
+template <int V> struct alignas(16) RawVec<bf16, V> { uint32_t w[V / 2]; };   // packed pairs: unpacked with shifts, never addressed
+template <int V> __device__ __forceinline__ void raw_unpack(const RawVec<float, V>& r, float (&f)[V]) {
+#pragma unroll
+    for (int j = 0; j < V; ++j) f[j] = r.v[j];
+}
+template <int V> __device__ __forceinline__ void raw_unpack(const RawVec<bf16, V>& r, float (&f)[V]) {
+#pragma unroll
+    for (int j = 0; j < V / 2; ++j) { f[2 * j] = __uint_as_float(r.w[j] << 16); f[2 * j + 1] = __uint_as_float(r.w[j] & 0xFFFF0000u); }
+}
+
+template <typename T, int V, int ROWS, bool HAS_RES>
+__global__ void __launch_bounds__(CR_THREADS) bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ u, const T* __restrict__ res,
+                                                                   const float* __restrict__ scale, const float* __restrict__ shift,
+                                                                   const float* __restrict__ mean, const float* __restrict__ rstd, long long rows, int C,
+                                                                   long long rows_per_block, int act, float* __restrict__ out0, float* __restrict__ out1) {
+    __shared__ float s0[CR_THREADS * V];
+    __shared__ float s1[CR_THREADS * V];
+    const int X = blockDim.x, Y = blockDim.y;
+    const int c = (blockIdx.x * X + threadIdx.x) * V;
+    const long long r0 = (long long)blockIdx.y * rows_per_block;
+    const long long r1 = min(rows, r0 + rows_per_block);
+    float a0[V], a1[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) { a0[j] = 0.0f; a1[j] = 0.0f; }
+    if (c < C) {
+        // sum dz * xhat = rstd * (sum dz * u - mean * sum dz): the loop accumulates sum dz * u (mean / rstd applied once per
+        // block below), which keeps 16 registers free for loads in flight
+        float sc[V], sh[V];
+        load_vec<V>(scale + c, sc); load_vec<V>(shift + c, sh);
+        auto consume = [&](const RawVec<T, V>& ru, const RawVec<T, V>& rd, const RawVec<T, V>& rr) {
+            float fu[V], fd[V], fr[V];
+            raw_unpack(ru, fu); raw_unpack(rd, fd);
+            if (HAS_RES) raw_unpack(rr, fr);
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                const float uu = fu[j];
+                float z = sc[j] * uu + sh[j];
+                if (HAS_RES) z += fr[j];
+                const float dz = fd[j] * act_bwd(z, act);
+                a0[j] += dz;
+                a1[j] = fmaf(dz, uu, a1[j]);
+            }
+        };
+        long long r = r0 + threadIdx.y;
+        for (; r + (long long)(ROWS - 1) * Y < r1; r += (long long)ROWS * Y) {
+            RawVec<T, V> ru[ROWS], rd[ROWS], rr[HAS_RES ? ROWS : 1];
+#pragma unroll
+            for (int q = 0; q < ROWS; ++q) {
+                const size_t i = (size_t)(r + (long long)q * Y) * C + c;
+                ru[q] = *reinterpret_cast<const RawVec<T, V>*>(u + i);
+                rd[q] = *reinterpret_cast<const RawVec<T, V>*>(dy + i);
+                if (HAS_RES) rr[q] = *reinterpret_cast<const RawVec<T, V>*>(res + i);
+            }
+#pragma unroll
+            for (int q = 0; q < ROWS; ++q) consume(ru[q], rd[q], rr[HAS_RES ? q : 0]);
+        }
+        for (; r < r1; r += Y) {
+            const size_t i = (size_t)r * C + c;
+            RawVec<T, V> ru = *reinterpret_cast<const RawVec<T, V>*>(u + i), rd = *reinterpret_cast<const RawVec<T, V>*>(dy + i), rr = ru;
+            if (HAS_RES) rr = *reinterpret_cast<const RawVec<T, V>*>(res + i);
+            consume(ru, rd, rr);
+        }
+    }
+    const int W = X * V;
+#pragma unroll
+    for (int j = 0; j < V; ++j) { s0[threadIdx.y * W + threadIdx.x * V + j] = a0[j]; s1[threadIdx.y * W + threadIdx.x * V + j] = a1[j]; }
+    __syncthreads();
+    for (int h = Y >> 1; h >= 1; h >>= 1) {
+        for (int i = threadIdx.y * X + threadIdx.x; i < h * W; i += CR_THREADS) { s0[i] += s0[i + h * W]; s1[i] += s1[i + h * W]; }
+        __syncthreads();
+    }
+    for (int cc = threadIdx.y * X + threadIdx.x; cc < W; cc += CR_THREADS) {
+        const int cg = blockIdx.x * W + cc;
+        if (cg < C) { atomicAdd(out0 + cg, s0[cc]); atomicAdd(out1 + cg, rstd[cg] * (s1[cc] - mean[cg] * s0[cc])); }
+    }
+}
+
+template <typename T, int V>
+int launch_bn_bwd_reduce(const T* dy, const T* u, const T* res, const float* scale, const float* shift, const float* mean, const float* rstd,
+                         long long rows, int C, int act, float* sums, cudaStream_t st) {
+    const int Cv = cdiv(C, V);
+    int X = 1;
+    while (X < 32 && X < Cv) X <<= 1;
+    const int Y = CR_THREADS / X;
+    const int gx = cdiv(Cv, X);
+    constexpr bool HALF = sizeof(T) == 2;        // rows in flight are bounded by the 128-register budget of a 512-thread block
+    constexpr int RR = HALF ? 5 : 2, RN = HALF ? 6 : 3;
+    const int ROWS_ = res ? RR : RN;
+    long long nchunk = std::min<long long>(cdivll(148 * 8, gx), cdivll(rows, (long long)Y * ROWS_));
+    if (nchunk < 1) nchunk = 1;
+    if (nchunk > 65535) nchunk = 65535;
+    const long long rpb = cdivll(rows, nchunk);
+    nchunk = cdivll(rows, rpb);
+    dim3 grid(gx, (unsigned)nchunk), block(X, Y);
+    if (res) bn_bwd_reduce_kernel<T, V, RR, true><<<grid, block, 0, st>>>(dy, u, res, scale, shift, mean, rstd, rows, C, rpb, act, sums, sums + C);
+    else bn_bwd_reduce_kernel<T, V, RN, false><<<grid, block, 0, st>>>(dy, u, res, scale, shift, mean, rstd, rows, C, rpb, act, sums, sums + C);
+    return 0;
+}
+
 __global__ void zero_kernel(float* p, int n) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = 0.0f; }
 
 __global__ void bn_finalize_kernel(const float* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -880,8 +984,7 @@ extern "C" int avec_bn_bwd_reduce(const void* dy, const void* u, const float* sc
     AVEC_CHECK_ARG(dy && u && scale && shift && mean && rstd && sums && rows > 0 && C > 0);
     cudaStream_t st = as_stream(stream);
     AVEC_DISPATCH_DTYPE_VEC(dtype, C, Tt, V, {
-        BnBwdF<Tt, V> f{(const Tt*)dy, (const Tt*)u, (const Tt*)res, scale, shift, mean, rstd, C, act, {}, {}, {}, {}};
-        launch_colreduce<V>(f, rows, C, sums, sums + C, 1.0f, st);
+        launch_bn_bwd_reduce<Tt, V>((const Tt*)dy, (const Tt*)u, (const Tt*)res, scale, shift, mean, rstd, rows, C, act, sums, st);
     });
     AVEC_LAUNCH_CHECK();
     return AVEC_OK;
