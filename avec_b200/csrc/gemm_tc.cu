@@ -1681,8 +1681,8 @@ __global__ void __launch_bounds__(WH_THREADS, 1) wgrad_halo64_kernel(const __gri
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     if (tid == 0) {
-        for (int i = 0; i < WH_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        mbar_init(done, 1);
+        for (int i = 0; i < WH_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 2); }   // two MMA-issuing threads release a stage
+        mbar_init(done, 2);
         fence_barrier_init();
         tma_prefetch_desc(&mapY);
         tma_prefetch_desc(&mapX);
@@ -1696,9 +1696,47 @@ __global__ void __launch_bounds__(WH_THREADS, 1) wgrad_halo64_kernel(const __gri
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const bool any_tile = (int)blockIdx.x < p.total_tiles;
+    // ===================== MMA issue loop for accumulators [q_lo, q_lo + 3): two issuing threads (warp 4 and warp 0) share the
+    // six accumulators - one thread needs ~36 cycles of scalar work per 32-cycle 128x64x16 MMA =====================
+    auto issue_loop = [&](int q_lo) {
+        const uint32_t idesc = make_idesc(64, 1, 1);
+        const uint64_t a_desc0 = make_smem_desc(0, (uint32_t)p.W2 * 128u, 1024);   // X halo: second 64-row M group = next filter row
+        const uint64_t b_desc0 = make_smem_desc(0, WH_Y_BYTES, 1024);              // dY: single 64-wide N group
+        const uint32_t a_hi = (uint32_t)(a_desc0 >> 32), b_hi = (uint32_t)(b_desc0 >> 32);
+        const uint32_t base16 = smem_u32(smem) >> 4;
+        int j = 0, st = 0;
+        uint32_t ph = 0;
+        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++j) {
+            mbar_wait(&full[st], ph);
+            tc_fence_after();
+            if (elect_one()) {
+                const uint32_t y16 = base16 + (uint32_t)st * (WH_STAGE_BYTES >> 4);
+                const uint32_t x16 = y16 + (WH_Y_BYTES >> 4);
+#pragma unroll
+                for (int qq = 0; qq < 3; ++qq) {
+                    const int q = q_lo + qq;
+                    const int set = q / 3, kw = q - set * 3;
+                    const uint32_t a0 = (uint32_t)a_desc0 + x16 + (uint32_t)((set * p.W2 + kw) * 128 >> 4);
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(q * 64);
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks)
+                        umma_f16(d_tmem, ((uint64_t)a_hi << 32) | (a0 + (uint32_t)ks * (2048u >> 4)),
+                                 ((uint64_t)b_hi << 32) | ((uint32_t)b_desc0 + y16 + (uint32_t)ks * (2048u >> 4)), idesc, (j > 0 || ks > 0) ? 1u : 0u);
+                }
+                umma_commit(&empty[st]);
+            }
+            __syncwarp();
+            if (++st == WH_STAGES) { st = 0; ph ^= 1u; }
+        }
+        if (any_tile && elect_one()) umma_commit(done);
+        __syncwarp();
+        tc_fence_before();
+    };
+
 
     if (warp < 4) {
         // ===================== final flush: lane = (tap row g, input channel c), columns = output channels =====================
+        if (warp == 0) { issue_loop(3); tc_fence_after(); }
         if (any_tile) {
             mbar_wait(done, 0);
             tc_fence_after();
@@ -1717,38 +1755,7 @@ __global__ void __launch_bounds__(WH_THREADS, 1) wgrad_halo64_kernel(const __gri
         }
         tc_fence_before();
     } else if (warp == 4) {
-        // ===================== MMA issuer =====================
-        const uint32_t idesc = make_idesc(64, 1, 1);
-        const uint64_t a_desc0 = make_smem_desc(0, (uint32_t)p.W2 * 128u, 1024);   // X halo: second 64-row M group = next filter row
-        const uint64_t b_desc0 = make_smem_desc(0, WH_Y_BYTES, 1024);              // dY: single 64-wide N group
-        const uint32_t a_hi = (uint32_t)(a_desc0 >> 32), b_hi = (uint32_t)(b_desc0 >> 32);
-        const uint32_t base16 = smem_u32(smem) >> 4;
-        int j = 0, st = 0;
-        uint32_t ph = 0;
-        for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++j) {
-            mbar_wait(&full[st], ph);
-            tc_fence_after();
-            if (elect_one()) {
-                const uint32_t y16 = base16 + (uint32_t)st * (WH_STAGE_BYTES >> 4);
-                const uint32_t x16 = y16 + (WH_Y_BYTES >> 4);
-#pragma unroll
-                for (int q = 0; q < 6; ++q) {
-                    const int set = q / 3, kw = q - set * 3;
-                    const uint32_t a0 = (uint32_t)a_desc0 + x16 + (uint32_t)((set * p.W2 + kw) * 128 >> 4);
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(q * 64);
-#pragma unroll
-                    for (int ks = 0; ks < 8; ++ks)
-                        umma_f16(d_tmem, ((uint64_t)a_hi << 32) | (a0 + (uint32_t)ks * (2048u >> 4)),
-                                 ((uint64_t)b_hi << 32) | ((uint32_t)b_desc0 + y16 + (uint32_t)ks * (2048u >> 4)), idesc, (j > 0 || ks > 0) ? 1u : 0u);
-                }
-                umma_commit(&empty[st]);
-            }
-            __syncwarp();
-            if (++st == WH_STAGES) { st = 0; ph ^= 1u; }
-        }
-        if (any_tile && elect_one()) umma_commit(done);
-        __syncwarp();
-        tc_fence_before();
+        issue_loop(0);
     } else {
         // ===================== TMA producer =====================
         int st = 0;
@@ -1942,8 +1949,8 @@ __global__ void __launch_bounds__(WI_THREADS, 1) wgrad_img_kernel(const __grid_c
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     if (tid == 0) {
-        for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-        mbar_init(done, 1);
+        for (int i = 0; i < p.stages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 2); }   // two MMA-issuing threads release a stage
+        mbar_init(done, 2);
         fence_barrier_init();
         tma_prefetch_desc(&mapY);
         tma_prefetch_desc(&mapX);
@@ -1960,27 +1967,9 @@ __global__ void __launch_bounds__(WI_THREADS, 1) wgrad_img_kernel(const __grid_c
     const int c0 = (blk % p.ncb) * 64, co0 = (blk / p.ncb) * 64;
     const bool any_tile = part < p.tiles;
     const int y_bytes = p.k_rows * 128;
-
-    if (warp < 4) {
-        if (any_tile) {
-            mbar_wait(done, 0);
-            tc_fence_after();
-            const int row = warp * 32 + lane, g = row >> 6, c = row & 63;
-            const size_t ldw = (size_t)9 * p.C;
-            for (int q = 0; q < 6; ++q) {
-                const int set = q / 3, kw = q - set * 3, kh = set + g;
-                if (set == 1 && g == 0) continue;   // kh = 1 duplicate (g is warp-uniform)
-                float* dst = p.dw + (size_t)co0 * ldw + (size_t)(kh * 3 + kw) * p.C + c0 + c;
-                for (int cc = 0; cc < 64; cc += 16) {
-                    float v[16];
-                    tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(q * 64 + cc), v);
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) atomicAdd(dst + (size_t)(cc + i) * ldw, p.alpha * v[i]);
-                }
-            }
-        }
-        tc_fence_before();
-    } else if (warp == 4) {
+    // MMA issue loop for accumulators [q_lo, q_hi).  One thread needs ~36 cycles of scalar work per 32-cycle 128x64x16 MMA, so
+    // the six accumulators are split over TWO issuing threads (warp 4 and warp 0, which only has the final flush to do)
+    auto issue_loop = [&](int q_lo, int q_hi) {
         const uint32_t idesc = make_idesc(64, 1, 1);
         const uint64_t a_desc0 = make_smem_desc(0, (uint32_t)p.G * 128u, 1024);
         const uint64_t b_desc0 = make_smem_desc(0, 16384, 1024);
@@ -1994,13 +1983,12 @@ __global__ void __launch_bounds__(WI_THREADS, 1) wgrad_img_kernel(const __grid_c
             if (elect_one()) {
                 const uint32_t y16 = base16 + (uint32_t)st * ((uint32_t)p.stage_bytes >> 4);
                 const uint32_t x16 = y16 + ((uint32_t)y_bytes >> 4);
-                // the issue loop is instruction bound (one MMA = 32 tensor-pipe cycles): fully unrolled for the two tile depths
-                // the model uses (8 k-steps: two 6x6 images, 13: one 11x11 image) so that descriptor offsets are immediates
                 auto issue = [&](auto KS) {
                     constexpr int NKS = decltype(KS)::value;
                     const int nks = NKS > 0 ? NKS : p.ksteps;
 #pragma unroll
-                    for (int q = 0; q < 6; ++q) {
+                    for (int qq = 0; qq < 3; ++qq) {
+                        const int q = q_lo + qq;
                         const int set = q / 3, kw = q - set * 3;
                         const uint32_t a0 = (uint32_t)a_desc0 + x16 + (uint32_t)((set * p.G + kw) * 128 >> 4);
                         const uint32_t b0 = (uint32_t)b_desc0 + y16;
@@ -2025,10 +2013,36 @@ __global__ void __launch_bounds__(WI_THREADS, 1) wgrad_img_kernel(const __grid_c
             __syncwarp();
             if (++st == p.stages) { st = 0; ph ^= 1u; }
         }
+        (void)q_hi;
         if (any_tile && elect_one()) umma_commit(done);
         __syncwarp();
         tc_fence_before();
-    } else {
+    };
+
+
+    if (warp < 4) {
+        if (warp == 0) { issue_loop(3, 6); tc_fence_after(); }
+        if (any_tile) {
+            mbar_wait(done, 0);
+            tc_fence_after();
+            const int row = warp * 32 + lane, g = row >> 6, c = row & 63;
+            const size_t ldw = (size_t)9 * p.C;
+            for (int q = 0; q < 6; ++q) {
+                const int set = q / 3, kw = q - set * 3, kh = set + g;
+                if (set == 1 && g == 0) continue;   // kh = 1 duplicate (g is warp-uniform)
+                float* dst = p.dw + (size_t)co0 * ldw + (size_t)(kh * 3 + kw) * p.C + c0 + c;
+                for (int cc = 0; cc < 64; cc += 16) {
+                    float v[16];
+                    tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(q * 64 + cc), v);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) atomicAdd(dst + (size_t)(cc + i) * ldw, p.alpha * v[i]);
+                }
+            }
+        }
+        tc_fence_before();
+    } else if (warp == 4) {
+        issue_loop(0, 3);
+        } else {
         int st = 0;
         uint32_t ph = 0;
         for (int t = part; t < p.tiles; t += nparts) {
