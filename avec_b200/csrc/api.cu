@@ -1,11 +1,13 @@
 // Library-level entry points: status strings, diagnostics and the avec_gemm dispatcher.
 #include "common.cuh"
+#include <atomic>
 
 static thread_local int g_last_cuda_error = 0;
-static thread_local long long g_launches = 0;
+// process-wide: the autograd backward of the host mirror runs on PyTorch's backward thread, the forward on the caller's
+static std::atomic<long long> g_launches{0};
 
 void avec_set_last_cuda_error(int e) { g_last_cuda_error = e; }
-void avec_count_launch() { ++g_launches; }
+void avec_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int avec_gemm_simt(const avec_gemm_args* a, cudaStream_t st);
 int avec_gemm_tc(const avec_gemm_args* a, cudaStream_t st);       // gemm_tc.cu
@@ -23,8 +25,8 @@ extern "C" const char* avec_strerror(int status) {
 }
 extern "C" int avec_last_cuda_error(void) { return g_last_cuda_error; }
 extern "C" int avec_version(void) { return 100; }
-extern "C" long long avec_launch_count(void) { return g_launches; }
-extern "C" void avec_reset_launch_count(void) { g_launches = 0; }
+extern "C" long long avec_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+extern "C" void avec_reset_launch_count(void) { g_launches.store(0, std::memory_order_relaxed); }
 
 extern "C" int avec_gemm(const avec_gemm_args* a, avec_stream_t stream) {
     AVEC_CHECK_ARG(a && a->A && a->B && a->out && a->M > 0 && a->N > 0 && a->K > 0);
