@@ -39,12 +39,21 @@ def compute_dtype():
 _wcache = {}
 
 
-def new_step(arena_numel=0, device=None):
+def new_step(arena_numel=0, device=None, advance_rng=False):
     """start of a forward pass: drop the compute-dtype weight copies of the previous step and (optionally) allocate the
-    zero-initialised fp32 arena that gradient accumulators and BatchNorm statistics of this step are carved from"""
+    zero-initialised fp32 arena that gradient accumulators and BatchNorm statistics of this step are carved from;
+    advance_rng: bump the device-side RNG step (training passes: fresh dropout / SpecAugment draws, also per graph replay)"""
     _wcache.clear()
+    ops.RNG.site = 0
     if arena_numel and device is not None:
         ops.ARENA.begin(arena_numel, device)
+    if advance_rng and device is not None and torch.device(device).type == "cuda":
+        ops.RNG.advance(device)
+
+
+def manual_seed(seed):
+    """seed of the dropout / SpecAugment generator (Philox key); the step counter restarts at 0"""
+    ops.RNG.manual_seed(seed)
 
 
 def wc(param, tag="plain", fn=None):
@@ -78,32 +87,48 @@ def _c(t):
 
 # --------------------------------------------------------------------------------------------------------------- FFN
 class FFNFn(Function):
-    """y = x + 0.5 * (W2 swish(W1 LN(x) + b1) + b2)"""
+    """y = x + 0.5 * drop_o(W2 drop_i(swish(W1 LN(x) + b1)) + b2)   (p_in / p_out = 0: no dropout kernels are launched)"""
 
     @staticmethod
-    def forward(ctx, x, ln_w, ln_b, w1, b1, w2, b2):
+    def forward(ctx, x, ln_w, ln_b, w1, b1, w2, b2, p_in=0.0, p_out=0.0):
         B, T, D = x.shape
         x = _c(x)
         xn, mean, rstd = ops.layernorm_fwd(x, ln_w, ln_b)
         h, pre = ops.linear_fwd(xn.view(B * T, D), wc(w1), b1, L.EPI_SWISH, want_pre=True)
-        y = ops.linear_fwd(h, wc(w2), b2, L.EPI_RESIDUAL, alpha=0.5, aux=x.view(B * T, D))
+        s_in = s_out = 0
+        if p_in > 0:
+            s_in = ops.RNG.next_site()
+            ops.dropout(h, p_in, s_in, out=h)
+        if p_out > 0:
+            s_out = ops.RNG.next_site()
+            y = ops.dropout(ops.linear_fwd(h, wc(w2), b2), p_out, s_out, res=x.view(B * T, D), alpha=0.5)
+        else:
+            y = ops.linear_fwd(h, wc(w2), b2, L.EPI_RESIDUAL, alpha=0.5, aux=x.view(B * T, D))
         ctx.save_for_backward(x, ln_w, mean, rstd, xn, pre, h, w1, w2)
+        ctx.drop = (p_in, s_in, p_out, s_out)
         return y.view(B, T, D)
 
     @staticmethod
     def backward(ctx, dy):
         x, ln_w, mean, rstd, xn, pre, h, w1, w2 = ctx.saved_tensors
+        p_in, s_in, p_out, s_out = ctx.drop
         B, T, D = x.shape
         dy = _c(dy)
         dy2 = dy.view(B * T, D)
-        dpre = ops.linear_dgrad(dy2, wc(w2), L.EPI_DSWISH, alpha=0.5, aux=pre)
-        dw2 = ops.linear_wgrad(dy2, h, alpha=0.5)
-        db2 = ops.colsum(dy2, 0.5)
+        if p_out > 0:
+            dyd, a = ops.dropout(dy2, p_out, s_out, alpha=0.5), 1.0
+        else:
+            dyd, a = dy2, 0.5
+        dpre = ops.linear_dgrad(dyd, wc(w2), L.EPI_DSWISH, alpha=a, aux=pre)
+        if p_in > 0:
+            ops.dropout(dpre, p_in, s_in, out=dpre)
+        dw2 = ops.linear_wgrad(dyd, h, alpha=a)
+        db2 = ops.colsum(dyd, a)
         dxn = ops.linear_dgrad(dpre, wc(w1))
         dw1 = ops.linear_wgrad(dpre, xn.view(B * T, D))
         db1 = ops.colsum(dpre)
         dx, dg, db = ops.layernorm_bwd(dxn.view(B, T, D), x, ln_w, mean, rstd, dres=dy, res_stride=1)
-        return dx, dg, db, dw1, db1, dw2, db2
+        return dx, dg, db, dw1, db1, dw2, db2, None, None
 
 
 # --------------------------------------------------------------------------------------------------------- attention
@@ -111,7 +136,7 @@ class AttentionFn(Function):
     """y = x + upsample_P( Wo attn( pool_P(LN(x)) ) + bo )   with relative-position scores (P = 1: regular RelPos1d)."""
 
     @staticmethod
-    def forward(ctx, x, ln_w, ln_b, wq, bq, wk, bk, wv, bv, wo, bo, wp, bp, pe, klen, H, P):
+    def forward(ctx, x, ln_w, ln_b, wq, bq, wk, bk, wv, bv, wo, bo, wp, bp, pe, klen, H, P, p_drop=0.0):
         B, T, D = x.shape
         d = D // H
         x = _c(x)
@@ -127,13 +152,19 @@ class AttentionFn(Function):
         else:
             klen_p, qlen = klen, Tp
         o, probs = ops.relpos_attn_fwd(qkv, e, klen_p, qlen, B, Tp, H, d)
-        if P == 1:
+        site = 0
+        if p_drop > 0:
+            # AttentionModule.dropout acts on the upsampled (B, T, D) output: one mask element per frame (modules.py:333)
+            site = ops.RNG.next_site()
+            proj = ops.linear_fwd(o, wc(wo), bo)
+            y = ops.dropout(proj, p_drop, site, res=x.view(B * T, D), up=(T, Tp, P) if P > 1 else None).view(B, T, D)
+        elif P == 1:
             y = ops.linear_fwd(o, wc(wo), bo, L.EPI_RESIDUAL, aux=x.view(B * T, D)).view(B, T, D)
         else:
             proj = ops.linear_fwd(o, wc(wo), bo)
             y = ops.upsample_add(x, proj.view(B, Tp, D), P)
         ctx.save_for_backward(x, ln_w, mean, rstd, xp, qkv, e, probs, o, pe, wq, wk, wv, wo, wp)
-        ctx.H, ctx.P = H, P
+        ctx.H, ctx.P, ctx.drop = H, P, (p_drop, site)
         return y
 
     @staticmethod
@@ -144,7 +175,9 @@ class AttentionFn(Function):
         Tp = xp.shape[1]
         d = D // H
         dy = _c(dy)
-        dproj = dy.view(B * T, D) if P == 1 else ops.pool_sum(dy, P).view(B * Tp, D)
+        p_drop, site = ctx.drop
+        dyd = ops.dropout(dy.view(B * T, D), p_drop, site).view(B, T, D) if p_drop > 0 else dy
+        dproj = dyd.view(B * T, D) if P == 1 else ops.pool_sum(dyd, P).view(B * Tp, D)
         do = ops.linear_dgrad(dproj, wc(wo))
         dwo = ops.linear_wgrad(dproj, o)
         dbo = ops.colsum(dproj)
@@ -157,7 +190,7 @@ class AttentionFn(Function):
         dbqkv = ops.colsum(dqkv)
         dx, dg, db = ops.layernorm_bwd(dxp.view(B, Tp, D), x, ln_w, mean, rstd, P=P, dres=dy, res_stride=1)
         return (dx, dg, db, dwqkv[:D], dbqkv[:D], dwqkv[D:2 * D], dbqkv[D:2 * D], dwqkv[2 * D:], dbqkv[2 * D:], dwo, dbo,
-                dwp, dbp, None, None, None, None)
+                dwp, dbp, None, None, None, None, None)
 
 
 class GroupedAttentionFn(Function):
@@ -166,7 +199,7 @@ class GroupedAttentionFn(Function):
     G = 1 is RelPosMultiHeadSelfAttention).  Projections run at full frame rate, grouping is pure addressing."""
 
     @staticmethod
-    def forward(ctx, x, ln_w, ln_b, wq, bq, wk, bk, wv, bv, wo, bo, wp, bp, u, v, pe, klen, H, G):
+    def forward(ctx, x, ln_w, ln_b, wq, bq, wk, bk, wv, bv, wo, bo, wp, bp, u, v, pe, klen, H, G, p_drop=0.0):
         B, T, D = x.shape
         Tn = -(-T // G)
         d = G * D // H
@@ -178,9 +211,14 @@ class GroupedAttentionFn(Function):
         e = ops.linear_fwd(pe, wc(wp), bp)                      # [2*Tp-G, D] == [2*Tn-1, G*D]
         klen_g = torch.div(klen + (G - 1), G, rounding_mode="floor").to(torch.int32) if klen is not None else None
         o, probs = ops.relpos_attn_fwd(qkv, e, klen_g, Tn, B, Tn, H, d, G=G, Tf=T, u=u, v=v)
-        y = ops.linear_fwd(o, wc(wo), bo, L.EPI_RESIDUAL, aux=x.view(B * T, D)).view(B, T, D)
+        site = 0
+        if p_drop > 0:
+            site = ops.RNG.next_site()
+            y = ops.dropout(ops.linear_fwd(o, wc(wo), bo), p_drop, site, res=x.view(B * T, D)).view(B, T, D)
+        else:
+            y = ops.linear_fwd(o, wc(wo), bo, L.EPI_RESIDUAL, aux=x.view(B * T, D)).view(B, T, D)
         ctx.save_for_backward(x, ln_w, mean, rstd, xn, qkv, e, probs, o, pe, wq, wk, wv, wo, wp, u, v)
-        ctx.H, ctx.G = H, G
+        ctx.H, ctx.G, ctx.drop = H, G, (p_drop, site)
         return y
 
     @staticmethod
@@ -191,7 +229,8 @@ class GroupedAttentionFn(Function):
         Tn = -(-T // G)
         d = G * D // H
         dy = _c(dy)
-        dy2 = dy.view(B * T, D)
+        p_drop, site = ctx.drop
+        dy2 = ops.dropout(dy.view(B * T, D), p_drop, site) if p_drop > 0 else dy.view(B * T, D)
         do = ops.linear_dgrad(dy2, wc(wo))
         dwo = ops.linear_wgrad(dy2, o)
         dbo = ops.colsum(dy2)
@@ -205,7 +244,7 @@ class GroupedAttentionFn(Function):
         dbqkv = ops.colsum(dqkv)
         dx, dg, db = ops.layernorm_bwd(dxn.view(B, T, D), x, ln_w, mean, rstd, dres=dy, res_stride=1)
         return (dx, dg, db, dwqkv[:D], dbqkv[:D], dwqkv[D:2 * D], dbqkv[D:2 * D], dwqkv[2 * D:], dbqkv[2 * D:], dwo, dbo,
-                dwp, dbp, du, dv, None, None, None, None)
+                dwp, dbp, du, dv, None, None, None, None, None)
 
 
 # ------------------------------------------------------------------------------------------------------- conv module
@@ -213,7 +252,7 @@ class ConvModuleFn(Function):
     """y = res(x) + W3 swish(BN(dwconv_k15,s(GLU(W1 LN(x) + b1)))) + b3,  res = identity | Conv1d(k=1, stride s)"""
 
     @staticmethod
-    def forward(ctx, x, ln_w, ln_b, w1, b1, wd, bd, bn_w, bn_b, rm, rv, w3, b3, wr, br, stride, training, momentum):
+    def forward(ctx, x, ln_w, ln_b, w1, b1, wd, bd, bn_w, bn_b, rm, rv, w3, b3, wr, br, stride, training, momentum, p_drop=0.0):
         B, T, D = x.shape
         De = w3.shape[0]
         ks = wd.shape[-1]
@@ -235,9 +274,14 @@ class ConvModuleFn(Function):
         else:
             xs = _c(x[:, ::stride]).view(B * To, D) if stride > 1 else x.view(B * T, D)
             aux = ops.linear_fwd(xs, wc(wr), br)
-        y = ops.linear_fwd(v, wc(w3), b3, L.EPI_RESIDUAL, aux=aux).view(B, To, De)
+        site = 0
+        if p_drop > 0:
+            site = ops.RNG.next_site()
+            y = ops.dropout(ops.linear_fwd(v, wc(w3), b3), p_drop, site, res=aux).view(B, To, De)
+        else:
+            y = ops.linear_fwd(v, wc(w3), b3, L.EPI_RESIDUAL, aux=aux).view(B, To, De)
         ctx.save_for_backward(x, ln_w, mean, rstd, xn, pre, u, bnbuf, v, xs, w1, wd, bn_w, w3, wr)
-        ctx.stride, ctx.training = stride, training
+        ctx.stride, ctx.training, ctx.drop = stride, training, (p_drop, site)
         return y
 
     @staticmethod
@@ -251,9 +295,11 @@ class ConvModuleFn(Function):
         ks = wd.shape[-1]
         dy = _c(dy)
         dy2 = dy.view(B * To, De)
-        dv = ops.linear_dgrad(dy2, wc(w3))
-        dw3 = ops.linear_wgrad(dy2, v)
-        db3 = ops.colsum(dy2)
+        p_drop, site = ctx.drop
+        dyd = ops.dropout(dy2, p_drop, site) if p_drop > 0 else dy2
+        dv = ops.linear_dgrad(dyd, wc(w3))
+        dw3 = ops.linear_wgrad(dyd, v)
+        db3 = ops.colsum(dyd)
         du, _, dgamma, dbeta = ops.bn_bwd(dv, u.view(B * To, De), bnbuf, bn_w, L.ACT_SWISH)
         dpre, dwd, dbd = ops.glu_dwconv_bwd(du.view(B, To, De), pre, wd.detach().reshape(De, ks), stride, ks)
         dpre2 = dpre.view(B * T, 2 * De)
@@ -265,10 +311,25 @@ class ConvModuleFn(Function):
         else:
             dres = ops.linear_dgrad(dy2, wc(wr)).view(B, To, D)
             dwr = ops.linear_wgrad(dy2, xs).view(wr.shape)
-            dbr = db3.clone()
+            dbr = db3.clone() if p_drop == 0 else ops.colsum(dy2)
         dx, dg, db = ops.layernorm_bwd(dxn.view(B, T, D), x, ln_w, mean, rstd, dres=dres, res_stride=stride)
         return (dx, dg, db, dw1.view(w1.shape), db1, dwd.view(wd.shape), dbd, dgamma, dbeta, None, None, dw3.view(w3.shape), db3,
-                dwr, dbr, None, None, None)
+                dwr, dbr, None, None, None, None)
+
+
+class DropoutFn(Function):
+    """nn.Dropout on a (.., C) tensor (ConformerInterCTC input dropout, networks.py:269)"""
+
+    @staticmethod
+    def forward(ctx, x, p):
+        site = ops.RNG.next_site()
+        ctx.drop = (p, site)
+        return ops.dropout(_c(x), p, site)
+
+    @staticmethod
+    def backward(ctx, dy):
+        p, site = ctx.drop
+        return ops.dropout(_c(dy), p, site), None
 
 
 class LayerNormFn(Function):
@@ -385,9 +446,11 @@ class AudioStemFn(Function):
     """wave [B,L] -> log-mel [B,F,80] -> Conv2d(1->C, k3, s2, same) + BN2d + Swish -> [B, F', 40*C] (feature = f*C + c)"""
 
     @staticmethod
-    def forward(ctx, wave, fb, cw, cb, bn_w, bn_b, rm, rv, training, momentum):
+    def forward(ctx, wave, fb, cw, cb, bn_w, bn_b, rm, rv, training, momentum, spec=None, mel_len=None):
         B = wave.shape[0]
         mel = ops.stft_mel_log(_c(wave.float()), fb, layout=0)
+        if spec is not None:      # SpecAugment (mF, F, mT, pS) on the fp32 log-mel, in place (networks.py:423-424)
+            ops.spec_augment_(mel, mel_len, ops.RNG.next_site(), *spec)
         F = mel.shape[1]
         melc = ops.convert(mel, compute_dtype())
         Co = cw.shape[0]
@@ -415,7 +478,7 @@ class AudioStemFn(Function):
         dwp = ops.stem2d_wgrad(melc, du) if ctx.direct else ops.conv_wgrad(du, melc, g)
         dcw = dwp.view(Co, 3, 3).transpose(1, 2).reshape(cw.shape)
         dcb = ops.colsum(du)
-        return None, None, dcw, dcb, dgamma, dbeta, None, None, None, None
+        return None, None, dcw, dcb, dgamma, dbeta, None, None, None, None, None, None
 
 
 class VideoStemFn(Function):

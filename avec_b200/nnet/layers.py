@@ -59,15 +59,14 @@ class Placeholder(nn.Module):
 
 
 class Dropout(nn.Dropout):
-    """Placeholder with the reference's p.  The fused kernels implement p = 0 only (parity / throughput runs set every
-    dropout to 0 on both sides); a non-zero p in training mode raises."""
+    """Holder of the reference's p.  The owning module applies it inside its fused Function (counter-based Philox masks
+    regenerated in the backward, csrc/train.cu avec_dropout); calling this layer directly dispatches to the same kernel."""
 
-
-def check_dropout(module):
-    for m in module.modules():
-        if isinstance(m, nn.Dropout) and m.p > 0 and m.training:
-            raise RuntimeError("avec_b200: dropout p > 0 is not implemented by the fused kernels; call "
-                               "avec_b200.nnet.zero_dropout(model) (the parity/bench configuration)")
+    def forward(self, x):
+        if not self.training or self.p == 0:
+            return x
+        from .. import functional as AF
+        return AF.DropoutFn.apply(x, float(self.p))
 
 
 def mel_filterbank(n_freqs=257, f_min=0.0, f_max=8000.0, n_mels=80, sample_rate=16000):

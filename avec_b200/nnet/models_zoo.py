@@ -7,7 +7,6 @@ import torch.nn as nn
 
 from .. import functional as AF
 from . import networks
-from .layers import check_dropout
 from .losses import CTCLoss
 
 
@@ -29,11 +28,10 @@ class Model(nn.Module):
         return sum(p.numel() for p in self.parameters())
 
     def _prepare(self, device=None):
-        check_dropout(self)
         if getattr(self, "_arena_numel", None) is None:
             # parameter gradients + BatchNorm statistics / reduction scratch + positional-embedding gradients
             self._arena_numel = int(1.3 * self.num_params()) + (8 << 20)
-        AF.new_step(self._arena_numel if (device is not None and device.type == "cuda") else 0, device)
+        AF.new_step(self._arena_numel if (device is not None and device.type == "cuda") else 0, device, advance_rng=self.training)
 
     def compute_loss(self, outputs, targets):
         """sum_k w_k * CTC(outputs[k]) with weights mapped to the outputs by position for lists (model.py:217) or by

@@ -10,6 +10,11 @@ from .layers import Linear, Conv1d, Placeholder, Dropout, Swish
 _pe_cache = {}
 
 
+def _drop_p(m, training):
+    """effective dropout probability of a Dropout / Identity slot"""
+    return float(m.p) if (training and isinstance(m, nn.Dropout)) else 0.0
+
+
 def rel_pos_table(T, D, device, dtype):
     """rows r = 0..2T-2 hold the sinusoid of relative position T-1-r (even channels sin, odd cos); the slice
     pos_encoding[max_len-T : max_len-1+T] of RelativeSinusoidalPositionalEncoding (embeddings.py:117-152)."""
@@ -60,7 +65,8 @@ class FeedForwardModule(nn.Module):
     def forward_residual(self, x):
         """x + 1/2 * FFN(x): the half-step residual of ConformerBlock.forward (blocks.py:292,301) is fused in."""
         l = self.layers
-        return AF.FFNFn.apply(x, l[0].weight, l[0].bias, l[1].weight, l[1].bias, l[4].weight, l[4].bias)
+        return AF.FFNFn.apply(x, l[0].weight, l[0].bias, l[1].weight, l[1].bias, l[4].weight, l[4].bias,
+                              _drop_p(l[3], self.training), _drop_p(l[5], self.training))
 
 
 class RelPos1dMultiHeadAttention(nn.Module):
@@ -138,7 +144,7 @@ class AttentionModule(nn.Module):
                 x, self.norm.weight, self.norm.bias,
                 a.query_layer.weight, a.query_layer.bias, a.key_layer.weight, a.key_layer.bias,
                 a.value_layer.weight, a.value_layer.bias, a.output_layer.weight, a.output_layer.bias,
-                a.pos_layer.weight, a.pos_layer.bias, a.u, a.v, pe, klen, a.num_heads, G)
+                a.pos_layer.weight, a.pos_layer.bias, a.u, a.v, pe, klen, a.num_heads, G, _drop_p(self.dropout, self.training))
         P = a.patch_size
         Tp = -(-T // P)
         pe = rel_pos_table(Tp, D, x.device, x.dtype)
@@ -146,7 +152,7 @@ class AttentionModule(nn.Module):
             x, self.norm.weight, self.norm.bias,
             a.query_layer.weight, a.query_layer.bias, a.key_layer.weight, a.key_layer.bias,
             a.value_layer.weight, a.value_layer.bias, a.output_layer.weight, a.output_layer.bias,
-            a.pos_layer.weight, a.pos_layer.bias, pe, klen, a.num_heads, P)
+            a.pos_layer.weight, a.pos_layer.bias, pe, klen, a.num_heads, P, _drop_p(self.dropout, self.training))
 
 
 class ConvolutionModule(nn.Module):
@@ -180,7 +186,7 @@ class ConvolutionModule(nn.Module):
             x, l[0].weight, l[0].bias, l[1].weight, l[1].bias, l[3].weight, l[3].bias,
             bn.weight, bn.bias, bn.running_mean, bn.running_var, l[6].weight, l[6].bias,
             conv_res.weight if has_res else None, conv_res.bias if has_res else None,
-            self.stride, training, bn.momentum)
+            self.stride, training, bn.momentum, _drop_p(l[7], training))
 
 
 class InterCTCResModule(nn.Module):

@@ -6,8 +6,9 @@ import torch.nn as nn
 
 from .. import functional as AF
 from .blocks import ConformerBlock, ResNetBlock
-from .layers import Linear, Conv2d, Conv3d, Placeholder, Dropout, Swish, mel_filterbank, check_dropout
+from .layers import Linear, Conv2d, Conv3d, Placeholder, Dropout, Swish, mel_filterbank
 from .modules import InterCTCResModule, FusionModule
+from .preprocessing import SpecAugment
 
 
 class ConformerInterCTC(nn.Module):
@@ -44,6 +45,7 @@ class ConformerInterCTC(nn.Module):
     def forward(self, x, lengths):
         """x (B,T,D) compute dtype, lengths (B,) int -> (x, lengths, {prefix_i: [logits fp32, lengths]})."""
         klen = lengths.to(device=x.device, dtype=torch.int32) if lengths is not None else None
+        x = self.dropout(x)                                                  # networks.py:268-269
         interctc_outputs = {}
         j = 0
         for i, block in enumerate(self.conformer_blocks):
@@ -96,7 +98,7 @@ class AudioEfficientConformerEncoder(nn.Module):
         assert att_type in ["regular", "grouped", "patch"]
         filters, n_mels, dim_model, heads = 180, 80, [180, 256, 360], 4
         self.audio_preprocessing = _AudioPreprocessingParams()
-        self.spec_augment = Placeholder("SpecAugment(mF=2, F=27, mT=5, pS=0.05): training-only augmentation, bypassed")
+        self.spec_augment = SpecAugment(mF=2, F=27, mT=5, pS=0.05)          # networks.py:347-353
         self.unsqueeze = Placeholder("Unsqueeze")
         self.subsampling_module = _SubsamplingParams(filters)
         self.reshape = Placeholder("Reshape")
@@ -129,9 +131,11 @@ class AudioEfficientConformerEncoder(nn.Module):
         conv, bn = self.subsampling_module.layers[0][0], self.subsampling_module.layers[0][1]
         if self.training:
             bn.num_batches_tracked.add_(1)
-        x = AF.AudioStemFn.apply(x, self.audio_preprocessing.MelScale.fb, conv.weight, conv.bias, bn.weight, bn.bias,
-                                 bn.running_mean, bn.running_var, self.training, bn.momentum)
         lengths = torch.div(lengths, 160, rounding_mode="floor") + 1      # preprocessing.py:76-77
+        spec = self.spec_augment.params() if (self.training and self.spec_augment.enabled) else None
+        mel_len = lengths.to(device=x.device, dtype=torch.long) if spec is not None else None
+        x = AF.AudioStemFn.apply(x, self.audio_preprocessing.MelScale.fb, conv.weight, conv.bias, bn.weight, bn.bias,
+                                 bn.running_mean, bn.running_var, self.training, bn.momentum, spec, mel_len)
         lengths = torch.div(lengths - 1, 2, rounding_mode="floor") + 1    # modules.py:127
         x = AF.LinearFn.apply(x, self.linear.weight, self.linear.bias, False, self._proj_layout)
         x, lengths, interctc_outputs = self.back_end(x, lengths)

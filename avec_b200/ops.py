@@ -532,3 +532,98 @@ def convert(src, dtype):
     L.check(L.load().avec_convert(s2.data_ptr(), _dt(s2), s2.stride(0), dst.data_ptr(), _dt(dst), dst.stride(0), s2.shape[0],
                                   s2.shape[1], _stream()), "avec_convert")
     return dst.reshape(src.shape)
+
+
+# ------------------------------------------------------------------------------------- training-step kernels (train.cu)
+class _Rng:
+    """{seed, step} as two uint64 in device memory per GPU, plus the per-forward dropout site counter.  The step is advanced
+    by a kernel (capturable: every CUDA-graph replay draws fresh masks); sites are handed out in call order and are
+    therefore identical in the forward and its backward."""
+
+    def __init__(self):
+        self.state, self.seed, self.site = {}, 0x5EEDA7EC, 0
+
+    def manual_seed(self, seed):
+        self.seed = int(seed) & 0x7FFFFFFFFFFFFFFF
+        for st in self.state.values():
+            st.copy_(torch.tensor([self.seed, 0], dtype=torch.int64))
+
+    def get(self, device):
+        device = torch.device(device)
+        if device.type == "cuda" and device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        st = self.state.get(device)
+        if st is None:
+            st = torch.tensor([self.seed, 0], dtype=torch.int64).to(device)
+            self.state[device] = st
+        return st
+
+    def advance(self, device):
+        st = self.get(device)
+        L.check(L.load().avec_counter_advance(st.data_ptr() + 8, _stream()), "avec_counter_advance")
+
+    def next_site(self):
+        self.site += 1
+        return self.site
+
+
+RNG = _Rng()
+
+
+def dropout(x, p, site, res=None, alpha=1.0, out=None, up=None):
+    """out = (res or 0) + alpha * keep * x / (1 - p) with the Philox mask of (seed, step, site); the backward calls it again
+    on the gradient with the same site.  up = (T, Tp, P): x is [B*Tp, C] patch rows repeated over the T frames of out / res."""
+    _cuda(x, res)
+    C = x.shape[-1]
+    if up is None:
+        rows, T, Tp, P = x.numel() // C, 0, 0, 1
+        out = torch.empty_like(x) if out is None else out
+    else:
+        T, Tp, P = up
+        rows = (x.numel() // C // Tp) * T
+        out = torch.empty((rows, C), device=x.device, dtype=x.dtype) if out is None else out
+    assert x.is_contiguous() and out.is_contiguous() and (res is None or (res.is_contiguous() and res.dtype == x.dtype))
+    L.check(L.load().avec_dropout(x.data_ptr(), _p(res), out.data_ptr(), rows, C, _dt(x), float(p), float(alpha),
+                                  RNG.get(x.device).data_ptr(), int(site), T, Tp, P, _stream()), "avec_dropout")
+    return out
+
+
+def spec_augment_(mel, lengths, site, mF=2, Fmax=27, mT=5, pS=0.05, want_intervals=False):
+    """in-place SpecAugment of mel [B, F, M] fp32 (frame-major); lengths [B] int64 device tensor of valid frames or None"""
+    _cuda(mel, lengths)
+    assert mel.dtype == torch.float32 and mel.is_contiguous()
+    B, F, M = mel.shape
+    iv = torch.empty((B, mF + mT, 2), device=mel.device, dtype=torch.int32) if want_intervals else None
+    L.check(L.load().avec_spec_augment(mel.data_ptr(), _p(lengths), B, F, M, mF, Fmax, mT, float(pS),
+                                       RNG.get(mel.device).data_ptr(), int(site), _p(iv), _stream()), "avec_spec_augment")
+    return iv
+
+
+def ctc_greedy_decode(logits, in_len=None, blank=0, want_align=False):
+    """logits [B,T,V] fp32 -> (tokens [B,T] int32 padded with -1, ntok [B] int32[, align [B,T] int32])"""
+    _cuda(logits, in_len)
+    assert logits.dtype == torch.float32 and logits.is_contiguous()
+    B, T, V = logits.shape
+    tokens = torch.empty((B, T), device=logits.device, dtype=torch.int32)
+    ntok = torch.empty((B,), device=logits.device, dtype=torch.int32)
+    align = torch.empty((B, T), device=logits.device, dtype=torch.int32) if want_align else None
+    L.check(L.load().avec_ctc_greedy_decode(logits.data_ptr(), _p(in_len), _p(align), tokens.data_ptr(), ntok.data_ptr(), B, T, V,
+                                            blank, _stream()), "avec_ctc_greedy_decode")
+    return (tokens, ntok, align) if want_align else (tokens, ntok)
+
+
+def sumsq(g, out):
+    """out[0] += sum g^2 over a flat fp32 buffer (out: zero-initialised device float)"""
+    _cuda(g, out)
+    L.check(L.load().avec_sumsq(g.data_ptr(), g.numel(), out.data_ptr(), _stream()), "avec_sumsq")
+    return out
+
+
+def adam_step(p, g, m, v, step, lr_mode, lr_a, lr_b=1.0, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, sumsq_buf=None,
+              max_norm=0.0, ema=None, ema_tau=0.0, info=None):
+    """fused Adam over flat fp32 buffers (see include/avec_b200.h); step: device int64 holding the 1-based step count"""
+    _cuda(p, g, m, v, step)
+    assert p.dtype == g.dtype == m.dtype == v.dtype == torch.float32 and p.numel() == g.numel() == m.numel() == v.numel()
+    L.check(L.load().avec_adam_step(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _p(ema), p.numel(), betas[0], betas[1],
+                                    eps, weight_decay, lr_mode, lr_a, lr_b, max_norm, ema_tau, step.data_ptr(), _p(sumsq_buf),
+                                    _p(info), _stream()), "avec_adam_step")

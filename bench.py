@@ -6,7 +6,8 @@
 
 Workload (BASELINE.json metric / configs[3]): AV EffConfInterCTC, per-GPU batch 64, 4 s of 16 kHz audio (64000
 samples) + 101 frames of 88x88 video (Tv = Ta // 640 + 1, SURVEY section 0 item 4), synthetic data, random-init weights,
-train-mode forward (batch-stat BatchNorm, dropout 0 = the parity configuration) + CTC losses on the 6 heads + backward.
+train-mode forward (batch-stat BatchNorm; dropout 0.1 + SpecAugment as in the reference's training graph, --dropout 0 = the
+deterministic parity configuration) + CTC losses on the 6 heads + backward.
 One step = one batch.  `value` times steps with inputs resident in HBM; `e2e` times the public API call
 model((video, vlen, audio, alen)) fed from pinned host memory, H2D copies and the D2H read of the loss inside the timed
 region.  Under torchrun (N > 1) gradients are all-reduced over NCCL every step (pure data parallel, local BN).
@@ -39,6 +40,8 @@ def parse():
     ap.add_argument("--cpu-baseline", type=int, default=1, help="time the CPU restatement on a bounded sample (rank 0, N=1)")
     ap.add_argument("--cpu-sample", type=int, default=8, help="utterances in the CPU baseline sample")
     ap.add_argument("--loss", default="ctc", choices=["ctc", "sum"])
+    ap.add_argument("--dropout", type=float, default=0.1, help="0.1 = the reference's training graph (dropout at every site + "
+                    "SpecAugment, networks.py:327,347-353); 0 = the deterministic parity graph (dropout off, SpecAugment bypassed)")
     ap.add_argument("--graph", type=int, default=1, help="capture forward+backward in one CUDA graph (falls back to eager if capture fails)")
     return ap.parse_args()
 
@@ -186,7 +189,14 @@ def main():
 
     torch.manual_seed(1234 + rank)
     cls = {"AV": nnet.AudioVisualEfficientConformerInterCTC, "AO": nnet.AudioEfficientConformerInterCTC, "VO": nnet.VisualEfficientConformerInterCTC}[args.model]
-    model = nnet.zero_dropout(cls()).to(dev).train()
+    model = cls()
+    if args.dropout == 0:
+        nnet.zero_dropout(model)
+    else:
+        for mod in model.modules():
+            if isinstance(mod, torch.nn.Dropout):
+                mod.p = args.dropout
+    model = model.to(dev).train()
     if world > 1:  # identical replicas
         parallel.broadcast_parameters(model)
     ctc = nnet.CTCLoss(zero_infinity=True, assert_shorter=False)
@@ -313,12 +323,14 @@ def main():
     if rank == 0:
         ms_step = ms_total / args.steps
         value = world * B / (ms_step / 1000.0)
+        aug = (f"dropout {args.dropout:g} at every site + SpecAugment(2,27,5,0.05): the reference's training graph" if args.dropout > 0
+               else "dropout 0, SpecAugment bypassed: parity graph")
         ach = gemm_flops / (gemm_ms / 1000.0) / 1e12 if gemm_ms > 0 else 0.0
         line = {
             "metric": "utterances/sec fwd+bwd (4s audio+video)", "value": value, "unit": "utterances/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": f"{args.model} EffConfInterCTC fwd+bwd (train mode, dropout 0, 6 CTC heads), per-GPU batch {B}, "
+            "config": {"workload": f"{args.model} EffConfInterCTC fwd+bwd (train mode, {aug}, 6 CTC heads), per-GPU batch {B}, "
                                    f"64000 audio samples + {101 if args.model == 'AV' else 100}x88x88 video",
                        "global_batch": world * B, "parallelism": f"dp{world}", "bn": "local batch statistics", "loss": args.loss, "cuda_graph": bool(use_graph),
                        "l2": "inputs+activations per step (>1 GB) exceed the 126 MB L2; no flush needed",

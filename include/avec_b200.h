@@ -256,6 +256,44 @@ int avec_zero_upsample(const void* in, void* out, int N, int Ho, int Wo, int Hi,
 int avec_ctc_loss(const float* logits, const long long* labels, const long long* in_len, const long long* lab_len, float* nll,
                   float* grad, float* ws, int B, int T, int V, int Lmax, int blank, int zero_infinity, avec_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Training-step kernels downstream / upstream of the encoder (csrc/train.cu).
+ * Random draws are Philox4x32-10(counter = (row, column >> 3, site, step), key = seed) with rng_state = {seed, step} two
+ * uint64 in DEVICE memory; avec_counter_advance bumps a device uint64 (the RNG step, the optimizer step) from inside a
+ * captured CUDA graph, so every replay draws fresh masks.  oracle/train_oracle.py restates the generator in numpy.
+ * ------------------------------------------------------------------------------------------------------------------ */
+int avec_counter_advance(unsigned long long* counter, avec_stream_t stream);
+
+/* nn.Dropout (nnet/modules.py:281-283,315,380; nnet/networks.py:221,269) fused with the residual add that follows it:
+ * y[r][c] = (res ? res[r][c] : 0) + alpha * keep(r,c) * x[r][c] / (1-p);  element (r,c) is kept iff its 16 random bits
+ * (16-bit lane (c & 7) of the draw of column group c >> 3) are >= round(p * 65536).  The backward calls the same
+ * function on the incoming gradient with the same site (res = NULL): the mask is regenerated, never stored.  x == y ok.
+ * P > 1: x is [B, Tp, C] (one row per patch of P frames), y / res are [B, T, C] with rows = B*T: the dropout that follows
+ * the patch attention's upsampling (nnet/attentions.py:368-372) draws one mask element per FRAME, as the reference does. */
+int avec_dropout(const void* x, const void* res, void* y, long long rows, int C, int dtype, float p, float alpha,
+                 const unsigned long long* rng_state, int site, int T, int Tp, int P, avec_stream_t stream);
+
+/* SpecAugment (nnet/preprocessing.py:87-129 over torchaudio mask_along_axis), in place on mel [B,F,M] fp32 (frame-major):
+ * mF frequency masks of width < Fmax shared by the batch, mT time masks per utterance of width < int(pS * len_b) inside
+ * [0, len_b).  lengths [B] int64 on the device (NULL = F).  intervals (optional) [B][mF+mT][2] int32 receives [lo, hi). */
+int avec_spec_augment(float* mel, const long long* lengths, int B, int F, int M, int mF, int Fmax, int mT, float pS,
+                      const unsigned long long* rng_state, int site, int* intervals, avec_stream_t stream);
+
+/* Greedy CTC decoding (nnet/decoders.py:97-120): argmax (first maximum) -> frames < in_len -> merge repeats -> drop blanks.
+ * logits [B,T,V] fp32, in_len [B] int64 device (NULL = T); align [B,T] int32 frame-level argmax (-1 beyond the length,
+ * may be NULL), tokens [B,T] int32 padded with -1, ntok [B] int32. */
+int avec_ctc_greedy_decode(const float* logits, const long long* in_len, int* align, int* tokens, int* ntok, int B, int T, int V,
+                           int blank, avec_stream_t stream);
+
+/* Fused optimizer over FLAT fp32 buffers of n elements (n % 4 == 0, 16-byte aligned): torch.optim.Adam with L2 weight decay
+ * (nnet/optimizers.py:61-93), learning rate from the device step counter (lr_mode 0: lr_a; 1: Noam, nnet/schedulers.py:
+ * 120-137, lr_a * min(t * lr_b^-1.5, t^-0.5)), optional global-norm clipping (sumsq = device float holding sum g^2, from
+ * avec_sumsq; nnet/model.py:378-380) and optional EMA copy (nnet/model.py:401-404).  lr_out (optional) [2] = {lr, |g|}. */
+int avec_sumsq(const float* g, long long n, float* out, avec_stream_t stream);
+int avec_adam_step(float* p, const float* g, float* m, float* v, float* ema, long long n, float beta1, float beta2, float eps,
+                   float weight_decay, int lr_mode, float lr_a, float lr_b, float max_norm, float ema_tau,
+                   const unsigned long long* step, const float* sumsq, float* lr_out, avec_stream_t stream);
+
 /* dtype conversion / strided copy helper: dst[r][c] = (T)src[r][c] */
 int avec_convert(const void* src, int src_dtype, long long lds, void* dst, int dst_dtype, long long ldd, long long rows,
                  int C, avec_stream_t stream);

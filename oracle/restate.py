@@ -47,12 +47,16 @@ def rel_pos_table(T, D):
     return pe
 
 
-def ffn(x, sd, p):
-    """FeedForwardModule (modules.py:277-284), dropout p = 0."""
+def ffn(x, sd, p, m_in=None, m_out=None):
+    """FeedForwardModule (modules.py:277-284).  m_in / m_out: the two nn.Dropout layers as explicit multipliers
+    keep / (1 - p) (None = dropout off), so a test can feed the masks the kernels drew."""
     h = F.layer_norm(x, (x.shape[-1],), sd[p + "layers.0.weight"], sd[p + "layers.0.bias"], 1e-6)
     h = F.linear(h, sd[p + "layers.1.weight"], sd[p + "layers.1.bias"])
     h = h * torch.sigmoid(h)
-    return F.linear(h, sd[p + "layers.4.weight"], sd[p + "layers.4.bias"])
+    if m_in is not None:
+        h = h * m_in
+    h = F.linear(h, sd[p + "layers.4.weight"], sd[p + "layers.4.bias"])
+    return h * m_out if m_out is not None else h
 
 
 def relpos_attention(x, sd, p, klen, H, P):
@@ -145,21 +149,27 @@ def conv_module(x, sd, p, stride, training, bn_momentum=0.1):
     return h.transpose(1, 2), rm, rv
 
 
-def conformer_block(x, sd, klen, H, P, stride, training=True, prefix="", G=None):
-    """ConformerBlock.forward (blocks.py:289-306).  G: group size when the block uses grouped attention."""
+def conformer_block(x, sd, klen, H, P, stride, training=True, prefix="", G=None, drop=None):
+    """ConformerBlock.forward (blocks.py:289-306).  G: group size when the block uses grouped attention.
+    drop: None (all dropouts off) or the six dropout multipliers of the block in call order
+    (ff1 inner, ff1 out, attention out, conv out, ff2 inner, ff2 out; modules.py:281,283,333,380)."""
     p = prefix
-    x = x + 0.5 * ffn(x, sd, p + "ff_module1.")
+    d = drop if drop is not None else [None] * 6
+    x = x + 0.5 * ffn(x, sd, p + "ff_module1.", d[0], d[1])
     if G is not None:
-        x = x + grouped_attention(x, sd, p + "self_att_module.", klen, H, G)
+        a = grouped_attention(x, sd, p + "self_att_module.", klen, H, G)
     else:
-        x = x + relpos_attention(x, sd, p + "self_att_module.", klen, H, P)
+        a = relpos_attention(x, sd, p + "self_att_module.", klen, H, P)
+    x = x + (a * d[2] if d[2] is not None else a)
     c, rm, rv = conv_module(x, sd, p + "conv_module.", stride, training)
+    if d[3] is not None:
+        c = c * d[3]
     if p + "conv_res.weight" in sd:
         r = F.conv1d(x.transpose(1, 2), sd[p + "conv_res.weight"], sd[p + "conv_res.bias"], stride=stride).transpose(1, 2)
     else:
         r = x
     x = r + c
-    x = x + 0.5 * ffn(x, sd, p + "ff_module2.")
+    x = x + 0.5 * ffn(x, sd, p + "ff_module2.", d[4], d[5])
     De = x.shape[-1]
     return F.layer_norm(x, (De,), sd[p + "norm.weight"], sd[p + "norm.bias"], 1e-6), rm, rv
 

@@ -1,0 +1,248 @@
+"""GPU parity of the training-step kernels (csrc/train.cu), all through the C ABI:
+dropout masks and SpecAugment intervals BIT-EXACT against the numpy Philox restatement, ConformerBlock with dropout on
+against fixtures produced by the unmodified reference fed the same masks, greedy CTC decoding bit-exact, fused Adam against
+3 steps of the reference's optimizer."""
+import numpy as np
+import pytest
+import torch
+
+import avec_b200
+import seeded
+from avec_b200 import nnet, ops, functional as AF
+from common import make_block, check_close, check_grad_fingerprint, rel_err, att_params
+from conftest import load_golden
+from oracle import train_oracle as TO
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+SEED = 0x1234ABCD5678
+
+
+def _set_rng(seed, step):
+    AF.manual_seed(seed)
+    ops.RNG.get(DEV).copy_(torch.tensor([seed, step], dtype=torch.int64))
+    ops.RNG.site = 0
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("rows,C", [(515, 180), (300, 256), (77, 30), (1, 8), (12864, 720)])
+def test_dropout_mask_bit_exact(dtype, rows, C):
+    _set_rng(SEED, 9)
+    x = seeded.randn("drop.x", (rows, C), 1).to(DEV).to(dtype)
+    res = seeded.randn("drop.r", (rows, C), 2).to(DEV).to(dtype)
+    p, site = 0.1, 17
+    keep = torch.from_numpy(TO.dropout_keep(SEED, 9, site, rows, C, p)).to(DEV)
+    y = ops.dropout(x, p, site)
+    assert torch.equal(y != 0, keep & (x != 0))
+    want = torch.where(keep, x.float() * (1.0 / (1.0 - p)), torch.zeros((), device=DEV))
+    check_close("y", y, want.to(dtype), 1e-6 if dtype == torch.float32 else 8e-3, 1e-7)
+    y2 = ops.dropout(x, p, site, res=res, alpha=0.5)
+    check_close("y+res", y2, (res.float() + 0.5 * want).to(dtype), 1e-6 if dtype == torch.float32 else 8e-3, 1e-6)
+    # same (seed, step, site) -> same mask (what the backward relies on); another step -> another mask
+    assert torch.equal(ops.dropout(x, p, site), y)
+    ops.RNG.advance(DEV)
+    keep2 = torch.from_numpy(TO.dropout_keep(SEED, 10, site, rows, C, p)).to(DEV)
+    assert torch.equal(ops.dropout(x, p, site) != 0, keep2 & (x != 0))
+    # in place
+    xi = x.clone()
+    ops.dropout(xi, p, site, out=xi)
+    assert torch.equal(xi != 0, keep2 & (x != 0))
+
+
+def test_dropout_after_patch_upsampling():
+    _set_rng(SEED, 0)
+    B, T, P, C = 3, 20, 3, 180
+    Tp = -(-T // P)
+    x = seeded.randn("dropup.x", (B * Tp, C), 1).to(DEV)
+    res = seeded.randn("dropup.r", (B * T, C), 2).to(DEV)
+    y = ops.dropout(x, 0.1, 5, res=res, up=(T, Tp, P))
+    m = torch.from_numpy(TO.dropout_scale_mask(SEED, 0, 5, B * T, C, 0.1)).to(DEV)
+    up = x.view(B, Tp, C).repeat_interleave(P, dim=1)[:, :T].reshape(B * T, C)
+    check_close("y", y, res + up * m, 1e-6, 1e-6)
+
+
+def test_spec_augment_matches_reference_fixture():
+    fix = load_golden("train_spec_augment.pt")
+    B, M, F = fix["shape"]
+    _set_rng(fix["seed"], fix["step"])
+    mel = seeded.randn("specaug.mel", (B, M, F), fix["mel_seed"]).transpose(1, 2).contiguous().to(DEV)
+    iv = ops.spec_augment_(mel, fix["lengths"].to(DEV), fix["site"], *fix["params"], want_intervals=True)
+    assert torch.equal(mel.cpu(), fix["out"].transpose(1, 2).contiguous())
+    want_iv = TO.spec_augment_intervals(fix["seed"], fix["step"], fix["site"], fix["lengths"].tolist(), F, M, *fix["params"])
+    assert iv.cpu().tolist() == [[list(t) for t in row] for row in want_iv]
+    # module API in the reference's (B, n_mels, T) layout
+    _set_rng(fix["seed"], fix["step"])
+    sa = nnet.SpecAugment(*fix["params"]).train()
+    out = sa(seeded.randn("specaug.mel", (B, M, F), fix["mel_seed"]).to(DEV), fix["lengths"])
+    assert torch.equal(out.cpu(), fix["out"])
+
+
+def test_spec_augment_full_size_properties():
+    """BASELINE shape (64 x 401 x 80): idempotent, only zeroes, at most mF*F bins and mT*int(pS*len) frames per utterance"""
+    _set_rng(3, 1)
+    B, F, M = 64, 401, 80
+    mel = (torch.randn(B, F, M, device=DEV) - 5.0)
+    lengths = torch.randint(200, 402, (B,), device=DEV)
+    ref = mel.clone()
+    ops.spec_augment_(mel, lengths, 1)
+    once = mel.clone()
+    ops.spec_augment_(mel, lengths, 1)
+    assert torch.equal(mel, once)
+    z = mel == 0
+    assert torch.equal(mel[~z], ref[~z])
+    bins = z.all(dim=1).sum(dim=1)
+    assert int(bins.max()) <= 2 * 27 and torch.equal(z.all(dim=1)[0], z.all(dim=1)[-1])          # shared frequency masks
+    frames = z.all(dim=2).sum(dim=1)
+    assert bool((frames <= 5 * (0.05 * lengths.float()).floor()).all())
+
+
+def test_greedy_decode_matches_reference_fixture():
+    fix = load_golden("train_greedy.pt")
+    dec = nnet.CTCGreedySearchDecoder(None, blank_token=0)
+    logits = fix["logits"].to(DEV)
+    assert dec.greedy_search(logits, fix["lengths"]) == fix["tokens"]
+    tokens, ntok, align = dec.greedy_search_device(logits, fix["lengths"], want_align=True)
+    T = logits.shape[1]
+    valid = torch.arange(T)[None, :] < fix["lengths"][:, None]
+    assert torch.equal(align.cpu().long()[valid], fix["align"][valid]) and bool((align.cpu()[~valid] == -1).all())
+
+
+def test_greedy_decode_full_size_against_torch():
+    B, T, V = 64, 51, 256
+    logits = torch.randn(B, T, V, device=DEV)
+    logits[:, :, 0] += 2.5                     # plenty of blanks
+    logits[:, 10:14, 7] += 9.0                 # repeats
+    lengths = torch.randint(1, T + 1, (B,))
+    got = nnet.CTCGreedySearchDecoder(None).greedy_search(logits, lengths)
+    assert got == TO.greedy_decode(logits.cpu().numpy(), lengths.tolist(), 0)
+
+
+def test_fused_adam_matches_reference_fixture():
+    fix = load_golden("train_adam.pt")
+    h = fix["hyper"]
+    param = torch.nn.Parameter(fix["p0"].clone().to(DEV))
+    opt = nnet.optimizers.Adam([param], lr=nnet.schedulers.NoamDecayScheduler(h["warmup_steps"], h["dim_decay"], h["val_factor"]),
+                               betas=h["betas"], eps=h["eps"], weight_decay=h["weight_decay"], grad_max_norm=h["max_norm"],
+                               ema_tau=h["ema_tau"])
+    for i, g in enumerate(fix["grads"]):
+        param.grad = g.clone().to(DEV)
+        opt.step()
+        info = opt.last_info()
+        assert abs(info["lr"] - fix["lr"][i]) <= 1e-5 * fix["lr"][i]
+        assert abs(info["grad_norm"] - fix["gnorm"][i]) <= 1e-5 * fix["gnorm"][i]
+        check_close(f"p[{i}]", param, fix["p"][i], 1e-5, 1e-7)
+        check_close(f"ema[{i}]", opt.ema_parameters()[0], fix["ema"][i], 1e-5, 1e-7)
+    check_close("m", opt.state[param]["exp_avg"], fix["m"], 1e-5, 1e-7)
+    check_close("v", opt.state[param]["exp_avg_sq"], fix["v"], 1e-5, 1e-9)
+    sd = opt.state_dict()
+    assert int(sd["model_step"]) == 3 and set(sd["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"}
+
+
+def test_fused_adam_whole_model_against_torch():
+    """AO model: every parameter becomes a view of the flat buffer; one fused step == torch.optim.Adam on the same gradients"""
+    torch.manual_seed(0)
+    m = nnet.AudioEfficientConformerInterCTC().to(DEV)
+    ref_params = [torch.nn.Parameter(p.detach().clone()) for p in m.parameters()]
+    grads = [torch.randn_like(p) * 0.01 for p in m.parameters()]
+    opt = nnet.optimizers.Adam(m.parameters(), lr=1e-3, betas=(0.9, 0.98), eps=1e-9, weight_decay=1e-6)
+    tref = torch.optim.Adam(ref_params, lr=1e-3, betas=(0.9, 0.98), eps=1e-9, weight_decay=1e-6)
+    before = avec_b200.launch_count()
+    for _ in range(2):
+        for p, rp, g in zip(m.parameters(), ref_params, grads):
+            p.grad, rp.grad = g.clone(), g.clone()
+        opt.step()
+        tref.step()
+    assert avec_b200.launch_count() - before == 4                       # (advance + adam) x 2 for 657 tensors
+    worst = max(float((p.detach() - rp.detach()).abs().max()) for p, rp in zip(m.parameters(), ref_params))
+    assert worst < 2e-6, worst
+    flat = opt.flat()
+    assert all(p.data_ptr() == flat["p"].data_ptr() + 4 * o for p, o in zip(flat["params"], flat["offs"]))
+    # gradients written straight into the flat views need no gather
+    for p, gv, g in zip(m.parameters(), opt.grad_views(), grads):
+        gv.copy_(g)
+        p.grad = gv
+    opt.step()
+
+
+@pytest.mark.parametrize("tag", ["s1_patch_T20", "s2_down_T12", "s1_grouped3_T20"])
+def test_block_with_dropout_matches_reference_fixture(tag):
+    fix = load_golden(f"train_block_dropout_{tag}.pt")
+    cfg, p = fix["cfg"], fix["p"]
+    try:
+        avec_b200.set_compute_dtype(torch.float32)
+        blk, sd = make_block(cfg)
+        for d in blk.modules():
+            if isinstance(d, torch.nn.Dropout):
+                d.p = p
+        blk = blk.to(DEV).train()
+        x = seeded.randn(tag + ".x", (cfg["B"], cfg["T"], cfg["D"]), cfg["seed"]).to(DEV).requires_grad_(True)
+        avec_b200.new_step()
+        _set_rng(fix["rng_seed"], fix["step"])
+        y = blk(x, klen=fix["lengths"].to(DEV).to(torch.int32))
+        assert ops.RNG.site == 6
+        gy = seeded.randn(tag + ".gy", tuple(y.shape), cfg["seed"]).to(DEV)
+        (y * gy).sum().backward()
+        check_close("y", y, fix["y"], 1e-3, 1e-4)
+        check_close("dx", x.grad, fix["dx"], 1e-3, 1e-4)
+        for k, fp in fix["grads"].items():
+            check_grad_fingerprint(k, dict(blk.named_parameters())[k].grad, fp, 1e-3, 2e-4)
+        # bf16 production mode: same masks, within the bf16 envelope of the block tests
+        avec_b200.set_compute_dtype(torch.bfloat16)
+        avec_b200.new_step()
+        _set_rng(fix["rng_seed"], fix["step"])
+        yb = blk(x.detach().to(torch.bfloat16), klen=fix["lengths"].to(DEV).to(torch.int32))
+        assert rel_err(yb, fix["y"]) < 2e-2
+    finally:
+        avec_b200.set_compute_dtype(torch.bfloat16)
+
+
+def test_model_training_graph_fresh_masks_and_determinism():
+    """AO model in train() (dropout 0.1 + SpecAugment): finite loss and gradients, a new step draws new masks, the same
+    (seed, step) reproduces the masks, and a captured CUDA graph draws fresh masks on every replay"""
+    torch.manual_seed(0)
+    m = nnet.AudioEfficientConformerInterCTC().to(DEV).train()
+    m.compile(losses=nnet.CTCLoss(zero_infinity=True, assert_shorter=False))
+    B = 4
+    audio = (0.1 * torch.randn(B, 16000)).to(DEV)
+    alen = torch.tensor([16000, 15000, 12000, 9000], device=DEV)
+    labels = torch.randint(1, 256, (B, 5), device=DEV)
+    lab_len = torch.full((B,), 5, device=DEV)
+
+    def step():
+        out = m((audio, alen))
+        loss = m.compute_loss(out, (labels, lab_len))
+        m.zero_grad(set_to_none=True)
+        loss.backward()
+        return out["outputs"][0].detach().clone(), float(loss)
+
+    AF.manual_seed(77)
+    o1, l1 = step()
+    o2, l2 = step()
+    assert np.isfinite(l1) and np.isfinite(l2) and rel_err(o2, o1) > 0.05          # new step, new masks
+    assert all(torch.isfinite(p.grad).all() for p in m.parameters() if p.grad is not None)
+    AF.manual_seed(77)
+    o1b, l1b = step()
+    # same (seed, step): same masks; what is left is the summation-order noise of the atomically accumulated BatchNorm
+    # statistics seen through bf16 rounding
+    assert rel_err(o1b, o1) < 0.3 * rel_err(o2, o1)
+    m.eval()
+    with torch.no_grad():
+        e1 = m((audio, alen))["outputs"][0].clone()
+        e2 = m((audio, alen))["outputs"][0].clone()
+    assert torch.equal(e1, e2)
+    m.train()
+    # CUDA graph: the RNG step is advanced by a kernel inside the graph
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(2):
+            m((audio, alen))
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        static_out = m((audio, alen))["outputs"][0]
+    g.replay()
+    r1 = static_out.clone()
+    g.replay()
+    r2 = static_out.clone()
+    assert torch.isfinite(r1).all() and rel_err(r2, r1) > 0.05

@@ -53,8 +53,21 @@ def test_length_bookkeeping():
     assert s.tolist() == [201, 200, 3, 1]
 
 
-def test_dropout_guard():
+def test_no_cpu_fallback():
+    """the product path has no CPU / eager fallback: CPU tensors are rejected loudly"""
     m = nnet.AudioEfficientConformerInterCTC()
     m.train()
-    with pytest.raises(RuntimeError, match="dropout"):
+    with pytest.raises(RuntimeError, match="CUDA"):
         m((torch.zeros(1, 3200), torch.tensor([3200])))
+
+
+def test_training_config_matches_reference():
+    """train() runs the reference's training graph: dropout 0.1 at the six sites of every block + the stack input, SpecAugment
+    (2, 27, 5, 0.05) in the audio encoder (networks.py:327,347-353); zero_dropout() gives the deterministic parity graph"""
+    m = nnet.AudioVisualEfficientConformerInterCTC()
+    drops = [d for d in m.modules() if isinstance(d, torch.nn.Dropout)]
+    assert len(drops) == 24 * 6 + 3 and all(d.p == 0.1 for d in drops)
+    sa = m.encoder.audio_encoder.spec_augment
+    assert sa.params() == (2, 27, 5, 0.05) and sa.enabled
+    nnet.zero_dropout(m)
+    assert all(d.p == 0.0 for d in drops) and not sa.enabled
