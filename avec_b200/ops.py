@@ -297,9 +297,31 @@ def gemm_stats_buffer(Cn, device):
     return zeros_f32((L.STATS_REPLICAS * 2 * Cn,), device)
 
 
+# SyncBatchNorm switch (the reference's DDP default, nnet/model.py:59-61): when set, the per-channel sums of every training-mode
+# BatchNorm are all-reduced over the data-parallel group - forward [sum x, sum x^2] (one packed all-reduce of the accumulator
+# the producing kernel filled), backward [sum dy, sum dy*xhat] - so all ranks normalise with the statistics of the GLOBAL batch.
+# Default None = local statistics (the reference's sync_batch_norm=False branch, model.py:62-63; what north_star prescribes).
+SYNC_BN = None
+
+
+def set_sync_batchnorm(enabled, group=None):
+    global SYNC_BN
+    import torch.distributed as dist
+    SYNC_BN = (group if group is not None else dist.group.WORLD) if enabled else None
+
+
+def _sync_world():
+    import torch.distributed as dist
+    return dist.get_world_size(SYNC_BN)
+
+
 def bn_finalize(stats, gamma, beta, count, running_mean=None, running_var=None, eps=1e-5, momentum=0.1):
     Cn = gamma.numel() if gamma is not None else stats.numel() // 2
     replicas = stats.numel() // (2 * Cn)
+    if SYNC_BN is not None:
+        import torch.distributed as dist
+        dist.all_reduce(stats, group=SYNC_BN)
+        count = count * _sync_world()
     buf = torch.empty((4, Cn), device=stats.device, dtype=torch.float32)  # scale, shift, mean, rstd
     L.check(L.load().avec_bn_finalize(stats.data_ptr(), _p(gamma), _p(beta), buf[0].data_ptr(), buf[1].data_ptr(),
                                       buf[2].data_ptr(), buf[3].data_ptr(), _p(running_mean), _p(running_var), count, Cn,
@@ -334,8 +356,16 @@ def bn_bwd(dy2d, u2d, bnbuf, gamma, act, res=None, want_dres=False):
                                    _stream()), "avec_bn_bwd_reduce")
     du = torch.empty_like(u2d)
     dres = torch.empty_like(u2d) if want_dres else None
+    gsums = sums
+    if SYNC_BN is not None:
+        # the kernel divides by the local row count: hand it the MEAN over ranks of the sums (= global sums / global count);
+        # dgamma / dbeta stay the local sums, the gradient all-reduce averages them like every other parameter gradient
+        import torch.distributed as dist
+        gsums = sums.clone()
+        dist.all_reduce(gsums, group=SYNC_BN)
+        gsums.div_(_sync_world())
     L.check(lib.avec_bn_bwd_apply(dy2d.data_ptr(), u2d.data_ptr(), bnbuf[0].data_ptr(), bnbuf[1].data_ptr(), _p(res),
-                                  bnbuf[2].data_ptr(), bnbuf[3].data_ptr(), _p(gamma), sums.data_ptr(), du.data_ptr(),
+                                  bnbuf[2].data_ptr(), bnbuf[3].data_ptr(), _p(gamma), gsums.data_ptr(), du.data_ptr(),
                                   _p(dres), rows, Cn, act, _dt(u2d), _stream()), "avec_bn_bwd_apply")
     return du, dres, sums[Cn:], sums[:Cn]
 
