@@ -19,38 +19,44 @@ __device__ __forceinline__ float fetch_qkv(const T* __restrict__ qkv_b, int tok,
 
 constexpr int ATT_THREADS = 256;
 constexpr int ATT_WARPS = ATT_THREADS / 32;
-constexpr int MAX_KPL = 10;  // keys per lane  -> T <= 320
+constexpr int MAX_KPL = 13;  // keys per lane  -> T <= 416
 constexpr int MAX_CPL = 5;   // head channels per lane -> d <= 160
+
+// Row stride (elements) of the K / V / E / Q / dO tiles in shared memory.  The tiles are kept in the tensor dtype (bf16 tiles
+// are a lossless copy of bf16 tensors and halve the footprint: T = 400 keys of a 64-channel head fit in 227 KB); lanes read
+// different rows at the same column, so the stride in 32-bit words must be odd.
+template <typename T> __host__ __device__ constexpr int att_ds(int d) { return d + 1; }
+template <> __host__ __device__ constexpr int att_ds<bf16>(int d) { return (((d + 1) / 2) % 2 == 1) ? (d + 1) / 2 * 2 : (d + 1) / 2 * 2 + 2; }
 
 template <typename T>
 __global__ void __launch_bounds__(ATT_THREADS) relpos_attn_fwd_kernel(
     const T* __restrict__ qkv, const T* __restrict__ e, const int* __restrict__ klen, int qlen, T* __restrict__ o,
     float* __restrict__ probs, int Tn, int H, int d, int G, int D1, int Tf, const float* __restrict__ ub, const float* __restrict__ vb) {
-    extern __shared__ float sm[];
-    const int ds = d + 1;
-    float* Ks = sm;                       // [Tn][ds]
-    float* Vs = Ks + (size_t)Tn * ds;     // [Tn][ds]
-    float* Es = Vs + (size_t)Tn * ds;     // [2Tn-1][ds]
-    float* qs = Es + (size_t)(2 * Tn - 1) * ds;  // [ATT_WARPS][2][ds]  (q + u | q + v)
-    float* ps = qs + ATT_WARPS * 2 * ds;  // [ATT_WARPS][Tn]
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    const int ds = att_ds<T>(d), qds = d + 1;
+    T* Ks = reinterpret_cast<T*>(sm_raw);  // [Tn][ds]
+    T* Vs = Ks + (size_t)Tn * ds;          // [Tn][ds]
+    T* Es = Vs + (size_t)Tn * ds;          // [2Tn-1][ds]
+    float* qs = reinterpret_cast<float*>(Es + (size_t)(2 * Tn - 1) * ds);  // [ATT_WARPS][2][qds]  (q + u | q + v), fp32
+    float* ps = qs + ATT_WARPS * 2 * qds;  // [ATT_WARPS][Tn]
     const int b = blockIdx.x / H, h = blockIdx.x % H;
     const int D = H * d;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const T* qkv_b = qkv + (size_t)b * Tf * 3 * D1;
     for (int idx = tid; idx < Tn * d; idx += ATT_THREADS) {
         int j = idx / d, c = idx % d;
-        Ks[j * ds + c] = fetch_qkv(qkv_b, j, h * d + c, 1, G, D1, Tf);
-        Vs[j * ds + c] = fetch_qkv(qkv_b, j, h * d + c, 2, G, D1, Tf);
+        stf(Ks + j * ds + c, fetch_qkv(qkv_b, j, h * d + c, 1, G, D1, Tf));
+        stf(Vs + j * ds + c, fetch_qkv(qkv_b, j, h * d + c, 2, G, D1, Tf));
     }
     for (int idx = tid; idx < (2 * Tn - 1) * d; idx += ATT_THREADS) {
         int r = idx / d, c = idx % d;
-        Es[r * ds + c] = ldf(e + (size_t)r * D + h * d + c);
+        Es[r * ds + c] = e[(size_t)r * D + h * d + c];
     }
     __syncthreads();
     const int kl = klen ? klen[b] : Tn;
     const float scale = rsqrtf((float)d);
-    float* q = qs + warp * 2 * ds;   // q + u (content term)
-    float* qv = q + ds;              // q + v (position term)
+    float* q = qs + warp * 2 * qds;  // q + u (content term)
+    float* qv = q + qds;             // q + v (position term)
     float* p = ps + warp * Tn;
     for (int i = warp; i < Tn; i += ATT_WARPS) {
         for (int c = lane; c < d; c += 32) {
@@ -66,10 +72,10 @@ __global__ void __launch_bounds__(ATT_THREADS) relpos_attn_fwd_kernel(
             int j = lane + u * 32;
             s[u] = -INFINITY;
             if (j < Tn) {
-                const float* kr = Ks + j * ds;
-                const float* er = Es + (Tn - 1 + j - i) * ds;
+                const T* kr = Ks + j * ds;
+                const T* er = Es + (Tn - 1 + j - i) * ds;
                 float acc = 0.0f;
-                for (int c = 0; c < d; ++c) acc = fmaf(q[c], kr[c], fmaf(qv[c], er[c], acc));
+                for (int c = 0; c < d; ++c) acc = fmaf(q[c], ldf(kr + c), fmaf(qv[c], ldf(er + c), acc));
                 acc *= scale;
                 if (j >= kl || i >= qlen) acc += -1e9f;
                 s[u] = acc;
@@ -97,9 +103,9 @@ __global__ void __launch_bounds__(ATT_THREADS) relpos_attn_fwd_kernel(
         for (int u = 0; u < MAX_CPL; ++u) acc[u] = 0.0f;
         for (int j = 0; j < Tn; ++j) {
             float pj = p[j];
-            const float* vr = Vs + j * ds;
+            const T* vr = Vs + j * ds;
 #pragma unroll
-            for (int u = 0; u < MAX_CPL; ++u) { int c = lane + u * 32; if (c < d) acc[u] = fmaf(pj, vr[c], acc[u]); }
+            for (int u = 0; u < MAX_CPL; ++u) { int c = lane + u * 32; if (c < d) acc[u] = fmaf(pj, ldf(vr + c), acc[u]); }
         }
 #pragma unroll
         for (int u = 0; u < MAX_CPL; ++u) {
@@ -119,13 +125,13 @@ __global__ void __launch_bounds__(ATT_THREADS) relpos_attn_bwd_kernel(
     const T* __restrict__ d_o, const T* __restrict__ qkv, const T* __restrict__ e, const float* __restrict__ probs,
     float* __restrict__ ds_ws, T* __restrict__ dqkv, float* __restrict__ de, int Tn, int H, int d, int G, int D1, int Tf,
     const float* __restrict__ ub, const float* __restrict__ vb, float* __restrict__ dub, float* __restrict__ dvb) {
-    extern __shared__ float sm[];
-    const int ds = d + 1;
-    float* Qs = sm;
-    float* Ks = Qs + (size_t)Tn * ds;
-    float* Vs = Ks + (size_t)Tn * ds;
-    float* Os = Vs + (size_t)Tn * ds;  // dO
-    float* ps = Os + (size_t)Tn * ds;  // [ATT_WARPS][Tn] scratch row
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    const int ds = att_ds<T>(d);
+    T* Qs = reinterpret_cast<T*>(sm_raw);
+    T* Ks = Qs + (size_t)Tn * ds;
+    T* Vs = Ks + (size_t)Tn * ds;
+    T* Os = Vs + (size_t)Tn * ds;  // dO
+    float* ps = reinterpret_cast<float*>(Os + (size_t)Tn * ds);  // [ATT_WARPS][Tn] scratch row
     const int b = blockIdx.x / H, h = blockIdx.x % H;
     const int D = H * d;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -134,10 +140,10 @@ __global__ void __launch_bounds__(ATT_THREADS) relpos_attn_bwd_kernel(
     for (int idx = tid; idx < Tn * d; idx += ATT_THREADS) {
         int j = idx / d, c = idx % d;
         const int ee = h * d + c, fi = ee / D1, frame = j * G + fi;
-        Qs[j * ds + c] = fetch_qkv(qkv_b, j, ee, 0, G, D1, Tf);
-        Ks[j * ds + c] = fetch_qkv(qkv_b, j, ee, 1, G, D1, Tf);
-        Vs[j * ds + c] = fetch_qkv(qkv_b, j, ee, 2, G, D1, Tf);
-        Os[j * ds + c] = frame < Tf ? ldf(d_o + ((size_t)b * Tf + frame) * D1 + (ee - fi * D1)) : 0.0f;
+        stf(Qs + j * ds + c, fetch_qkv(qkv_b, j, ee, 0, G, D1, Tf));
+        stf(Ks + j * ds + c, fetch_qkv(qkv_b, j, ee, 1, G, D1, Tf));
+        stf(Vs + j * ds + c, fetch_qkv(qkv_b, j, ee, 2, G, D1, Tf));
+        stf(Os + j * ds + c, frame < Tf ? ldf(d_o + ((size_t)b * Tf + frame) * D1 + (ee - fi * D1)) : 0.0f);
     }
     // gradient element (token, channel c of this head) -> [frames, 3 * D1] matrix; padded frames are dropped
     auto store_grad = [&](int tok, int c, int which, float val) {
@@ -161,9 +167,9 @@ __global__ void __launch_bounds__(ATT_THREADS) relpos_attn_bwd_kernel(
             int cnt = min(32, Tn - i0);
             for (int ii = 0; ii < cnt; ++ii) {
                 float pv = __shfl_sync(0xffffffffu, pij, ii);
-                const float* orow = Os + (i0 + ii) * ds;
+                const T* orow = Os + (i0 + ii) * ds;
 #pragma unroll
-                for (int u = 0; u < MAX_CPL; ++u) { int c = lane + u * 32; if (c < d) acc[u] = fmaf(pv, orow[c], acc[u]); }
+                for (int u = 0; u < MAX_CPL; ++u) { int c = lane + u * 32; if (c < d) acc[u] = fmaf(pv, ldf(orow + c), acc[u]); }
             }
         }
 #pragma unroll
@@ -182,7 +188,7 @@ __global__ void __launch_bounds__(ATT_THREADS) relpos_attn_bwd_kernel(
 
     // ---- phase A: per query row i: dP_ij = dO_i.V_j, delta, dS_ij, dQ_i
     for (int i = warp; i < Tn; i += ATT_WARPS) {
-        const float* orow = Os + i * ds;
+        const T* orow = Os + i * ds;
         float dp[MAX_KPL], pr[MAX_KPL];
         float delta = 0.0f;
 #pragma unroll
@@ -190,9 +196,9 @@ __global__ void __launch_bounds__(ATT_THREADS) relpos_attn_bwd_kernel(
             int j = lane + u * 32;
             dp[u] = 0.0f; pr[u] = 0.0f;
             if (j < Tn) {
-                const float* vr = Vs + j * ds;
+                const T* vr = Vs + j * ds;
                 float acc = 0.0f;
-                for (int c = 0; c < d; ++c) acc = fmaf(orow[c], vr[c], acc);
+                for (int c = 0; c < d; ++c) acc = fmaf(ldf(orow + c), ldf(vr + c), acc);
                 dp[u] = acc;
                 pr[u] = P[(size_t)i * Tn + j];
                 delta = fmaf(pr[u], acc, delta);
@@ -210,12 +216,12 @@ __global__ void __launch_bounds__(ATT_THREADS) relpos_attn_bwd_kernel(
         for (int u = 0; u < MAX_CPL; ++u) { acc[u] = 0.0f; acce[u] = 0.0f; }
         for (int j = 0; j < Tn; ++j) {
             float sv = p[j];
-            const float* kr = Ks + j * ds;
+            const T* kr = Ks + j * ds;
             const T* er = e + (size_t)(Tn - 1 + j - i) * D + h * d;
 #pragma unroll
             for (int u = 0; u < MAX_CPL; ++u) {
                 int c = lane + u * 32;
-                if (c < d) { acc[u] = fmaf(sv, kr[c], acc[u]); acce[u] = fmaf(sv, ldf(er + c), acce[u]); }
+                if (c < d) { acc[u] = fmaf(sv, ldf(kr + c), acc[u]); acce[u] = fmaf(sv, ldf(er + c), acce[u]); }
             }
         }
 #pragma unroll
@@ -251,9 +257,9 @@ __global__ void __launch_bounds__(ATT_THREADS) relpos_attn_bwd_kernel(
             int cnt = min(32, Tn - i0);
             for (int ii = 0; ii < cnt; ++ii) {
                 float sv = __shfl_sync(0xffffffffu, sij, ii);
-                const float* qrow = Qs + (i0 + ii) * ds;
+                const T* qrow = Qs + (i0 + ii) * ds;
 #pragma unroll
-                for (int u = 0; u < MAX_CPL; ++u) { int c = lane + u * 32; if (c < d) acc[u] = fmaf(sv, qrow[c] + ubv[u], acc[u]); }
+                for (int u = 0; u < MAX_CPL; ++u) { int c = lane + u * 32; if (c < d) acc[u] = fmaf(sv, ldf(qrow + c) + ubv[u], acc[u]); }
             }
         }
 #pragma unroll
@@ -271,9 +277,9 @@ __global__ void __launch_bounds__(ATT_THREADS) relpos_attn_bwd_kernel(
             int cnt = min(32, ihi - i0 + 1);
             for (int ii = 0; ii < cnt; ++ii) {
                 float sv = __shfl_sync(0xffffffffu, sij, ii);
-                const float* qrow = Qs + (i0 + ii) * ds;
+                const T* qrow = Qs + (i0 + ii) * ds;
 #pragma unroll
-                for (int u = 0; u < MAX_CPL; ++u) { int c = lane + u * 32; if (c < d) acc[u] = fmaf(sv, qrow[c] + vbv[u], acc[u]); }
+                for (int u = 0; u < MAX_CPL; ++u) { int c = lane + u * 32; if (c < d) acc[u] = fmaf(sv, ldf(qrow + c) + vbv[u], acc[u]); }
             }
         }
 #pragma unroll
@@ -281,8 +287,12 @@ __global__ void __launch_bounds__(ATT_THREADS) relpos_attn_bwd_kernel(
     }
 }
 
-size_t fwd_smem(int T, int d) { return ((size_t)(4 * T - 1) * (d + 1) + ATT_WARPS * 2 * (d + 1) + ATT_WARPS * T) * sizeof(float); }
-size_t bwd_smem(int T, int d) { return ((size_t)4 * T * (d + 1) + ATT_WARPS * T) * sizeof(float); }
+template <typename T> size_t fwd_smem(int Tn, int d) {
+    return (size_t)(4 * Tn - 1) * att_ds<T>(d) * sizeof(T) + ((size_t)ATT_WARPS * 2 * (d + 1) + (size_t)ATT_WARPS * Tn) * sizeof(float);
+}
+template <typename T> size_t bwd_smem(int Tn, int d) {
+    return (size_t)4 * Tn * att_ds<T>(d) * sizeof(T) + (size_t)ATT_WARPS * Tn * sizeof(float);
+}
 
 }  // namespace
 
@@ -300,9 +310,9 @@ extern "C" int avec_relpos_attn_fwd(const void* qkv, const void* e, const int* k
         if (rc != AVEC_ERR_UNSUPPORTED) return rc;
     }
     const int D1 = H * d / G;
-    size_t smem = fwd_smem(T, d);
-    if (smem > 227 * 1024) return AVEC_ERR_UNSUPPORTED;
     AVEC_DISPATCH_DTYPE(dtype, Tt, {
+        const size_t smem = fwd_smem<Tt>(T, d);
+        if (smem > 227 * 1024) return AVEC_ERR_UNSUPPORTED;
         auto kfn = relpos_attn_fwd_kernel<Tt>;
         if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return AVEC_ERR_LAUNCH;
         kfn<<<B * H, ATT_THREADS, smem, as_stream(stream)>>>((const Tt*)qkv, (const Tt*)e, klen, qlen, (Tt*)o, probs, T, H, d, G, D1, Tf, u, v);
@@ -321,9 +331,9 @@ extern "C" int avec_relpos_attn_bwd(const void* d_o, const void* qkv, const void
         if (rc != AVEC_ERR_UNSUPPORTED) return rc;
     }
     const int D1 = H * d / G;
-    size_t smem = bwd_smem(T, d);
-    if (smem > 227 * 1024) return AVEC_ERR_UNSUPPORTED;
     AVEC_DISPATCH_DTYPE(dtype, Tt, {
+        const size_t smem = bwd_smem<Tt>(T, d);
+        if (smem > 227 * 1024) return AVEC_ERR_UNSUPPORTED;
         auto kfn = relpos_attn_bwd_kernel<Tt>;
         if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return AVEC_ERR_LAUNCH;
         kfn<<<B * H, ATT_THREADS, smem, as_stream(stream)>>>((const Tt*)d_o, (const Tt*)qkv, (const Tt*)e, probs, ds_ws, (Tt*)dqkv, de, T, H, d,

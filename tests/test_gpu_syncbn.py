@@ -70,7 +70,8 @@ def _worker(rank, world, port, out):
             for g in gs:
                 dist.all_reduce(g)
             err = {"y": float((ys - yf[sl]).abs().max()), "dx": float((dxs - dxf[sl]).abs().max()),
-                   "grads": max(float((a - b).abs().max() / (b.abs().max() + 1e-6)) for a, b in zip(gs, gf)),
+                   # (+1e-3: the bias gradients in front of a BatchNorm are exactly 0 in exact arithmetic and pure rounding noise here)
+                   "grads": max(float((a - b).abs().max() / (b.abs().max() + 1e-3)) for a, b in zip(gs, gf)),
                    "buffers": max(float((v.float() - bufs_full[k].float()).abs().max()) for k, v in blk.named_buffers()),
                    "scale": float(yf.abs().max())}
             res[kind] = err
