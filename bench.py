@@ -40,6 +40,8 @@ def parse():
     ap.add_argument("--cpu-baseline", type=int, default=1, help="time the CPU restatement on a bounded sample (rank 0, N=1)")
     ap.add_argument("--cpu-sample", type=int, default=8, help="utterances in the CPU baseline sample")
     ap.add_argument("--loss", default="ctc", choices=["ctc", "sum"])
+    ap.add_argument("--optimizer", default="none", choices=["none", "adam"], help="adam: add the fused optimizer step (Adam + Noam LR + "
+                    "global-norm clip, avec_b200.nnet.optimizers.Adam) to every step; the headline metric is forward + backward (none)")
     ap.add_argument("--dropout", type=float, default=0.1, help="0.1 = the reference's training graph (dropout at every site + "
                     "SpecAugment, networks.py:327,347-353); 0 = the deterministic parity graph (dropout off, SpecAugment bypassed)")
     ap.add_argument("--graph", type=int, default=1, help="capture forward+backward in one CUDA graph (falls back to eager if capture fails)")
@@ -204,6 +206,11 @@ def main():
     host = synth_inputs(args.model, B, None, seed=1234 + rank, pinned=True)
     resident = {k: v.to(dev) for k, v in host.items()}
     params = [p for p in model.parameters()]
+    opt = None
+    if args.optimizer == "adam":
+        opt = nnet.optimizers.Adam(model.parameters(), lr=nnet.schedulers.NoamDecayScheduler(10000, 360, 2), betas=(0.9, 0.98), eps=1e-9,
+                                   weight_decay=1e-6, grad_max_norm=5.0)
+        opt.flat()   # parameters become views of the flat buffer BEFORE anything is captured
 
     def fwd_bwd(d):
         """forward + 6 CTC losses + backward; leaves the gradients in p.grad"""
@@ -233,6 +240,8 @@ def main():
         else:
             loss = fwd_bwd(d)
         allreduce_grads()
+        if opt is not None:
+            opt.step(grads=static_grads if (graph is not None and d is resident and world == 1) else None)
         return loss
 
     def sync():
@@ -332,7 +341,7 @@ def main():
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": f"{args.model} EffConfInterCTC fwd+bwd (train mode, {aug}, 6 CTC heads), per-GPU batch {B}, "
                                    f"64000 audio samples + {101 if args.model == 'AV' else 100}x88x88 video",
-                       "global_batch": world * B, "parallelism": f"dp{world}", "bn": "local batch statistics", "loss": args.loss, "cuda_graph": bool(use_graph),
+                       "global_batch": world * B, "parallelism": f"dp{world}", "bn": "local batch statistics", "optimizer": args.optimizer, "loss": args.loss, "cuda_graph": bool(use_graph),
                        "l2": "inputs+activations per step (>1 GB) exceed the 126 MB L2; no flush needed",
                        "achieved_tflops_whole_step": value / world * AV_GFLOP_PER_UTT / 1000.0 if args.model == "AV" else None,
                        "frac_of_tensor_peak_whole_step": (value / world * AV_GFLOP_PER_UTT / 1000.0) / peak_tf if args.model == "AV" else None},
