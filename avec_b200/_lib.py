@@ -54,6 +54,7 @@ PROTOTYPES = {
     "avec_layernorm_bwd": ([_P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P], _I),
     "avec_upsample_add": ([_P, _P, _P, _I, _I, _I, _I, _I, _I, _P], _I),
     "avec_pool_sum": ([_P, _P, _I, _I, _I, _I, _I, _I, _P], _I),
+    "avec_set_attention_long": ([_I], None),
     "avec_relpos_attn_fwd": ([_P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P], _I),
     "avec_relpos_attn_bwd": ([_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P], _I),
     "avec_softmax_fwd": ([_P, _I, _P, _I, _L, _I, _P], _I),

@@ -3,30 +3,9 @@
 //   S[i,j] = (q_i.k_j + q_i.e_{T-1+j-i}) / sqrt(d) + (masked ? -1e9 : 0),  P = softmax_j S,  o_i = sum_j P_ij v_j
 // K, V, (Q, dO) and E tiles of one head are staged in shared memory as fp32; scores never leave the SM in the forward
 // except for the saved probabilities the backward consumes.
-#include "common.cuh"
+#include "attention_common.cuh"
 
 namespace {
-
-// Grouped attention (GroupedRelPosMultiHeadSelfAttention.forwardQKV, reference nnet/attentions.py:579-650): a token is G
-// consecutive frames concatenated (G * D1 wide, split into H heads of d = G * D1 / H channels); frames past the real
-// length Tf are zero rows.  Element e = h * d + c of token `tok` therefore lives in frame tok * G + e / D1, column e % D1.
-// G = 1 is the plain layout.  `which` selects q (0), k (1) or v (2) inside the [frames, 3 * D1] matrix.
-template <typename T>
-__device__ __forceinline__ float fetch_qkv(const T* __restrict__ qkv_b, int tok, int e, int which, int G, int D1, int Tf) {
-    const int i = e / D1, col = e - i * D1, frame = tok * G + i;
-    return frame < Tf ? ldf(qkv_b + (size_t)frame * 3 * D1 + which * D1 + col) : 0.0f;
-}
-
-constexpr int ATT_THREADS = 256;
-constexpr int ATT_WARPS = ATT_THREADS / 32;
-constexpr int MAX_KPL = 13;  // keys per lane  -> T <= 416
-constexpr int MAX_CPL = 5;   // head channels per lane -> d <= 160
-
-// Row stride (elements) of the K / V / E / Q / dO tiles in shared memory.  The tiles are kept in the tensor dtype (bf16 tiles
-// are a lossless copy of bf16 tensors and halve the footprint: T = 400 keys of a 64-channel head fit in 227 KB); lanes read
-// different rows at the same column, so the stride in 32-bit words must be odd.
-template <typename T> __host__ __device__ constexpr int att_ds(int d) { return d + 1; }
-template <> __host__ __device__ constexpr int att_ds<bf16>(int d) { return (((d + 1) / 2) % 2 == 1) ? (d + 1) / 2 * 2 : (d + 1) / 2 * 2 + 2; }
 
 template <typename T>
 __global__ void __launch_bounds__(ATT_THREADS) relpos_attn_fwd_kernel(
@@ -301,18 +280,28 @@ int avec_attn_mma_fwd(const void* qkv, const void* e, const int* klen, int qlen,
 int avec_attn_mma_bwd(const void* d_o, const void* qkv, const void* e, const float* probs, void* dqkv, float* de, int B, int T, int H, int d,
                       cudaStream_t st);
 
+// key-tiled kernels for sequences beyond the whole-head envelope (attention_long.cu)
+int avec_attn_long_fwd(const void* qkv, const void* e, const int* klen, int qlen, void* o, float* probs, int B, int T, int H, int d, int G,
+                       int Tf, const float* u, const float* v, int dtype, cudaStream_t st);
+int avec_attn_long_bwd(const void* d_o, const void* qkv, const void* e, const float* probs, float* ds_ws, void* dqkv, float* de, int B, int T,
+                       int H, int d, int G, int Tf, const float* u, const float* v, float* du, float* dv, int dtype, cudaStream_t st);
+
+static int g_force_long = 0;
+extern "C" void avec_set_attention_long(int force) { g_force_long = force; }
+
 extern "C" int avec_relpos_attn_fwd(const void* qkv, const void* e, const int* klen, int qlen, void* o, float* probs, int B,
                                     int T, int H, int d, int G, int Tf, const float* u, const float* v, int dtype, avec_stream_t stream) {
     AVEC_CHECK_ARG(qkv && e && o && probs && B > 0 && T > 0 && H > 0 && d > 0 && G >= 1 && (H * d) % G == 0);
-    AVEC_CHECK_ARG(T <= 32 * MAX_KPL && d <= 32 * MAX_CPL && Tf > (T - 1) * G && Tf <= T * G);
-    if (dtype == AVEC_BF16 && G == 1 && !u && !v && Tf == T) {
+    AVEC_CHECK_ARG(d <= 32 * MAX_CPL && Tf > (T - 1) * G && Tf <= T * G);
+    if (dtype == AVEC_BF16 && G == 1 && !u && !v && Tf == T && !g_force_long) {
         const int rc = avec_attn_mma_fwd(qkv, e, klen, qlen, o, probs, B, T, H, d, as_stream(stream));
         if (rc != AVEC_ERR_UNSUPPORTED) return rc;
     }
     const int D1 = H * d / G;
     AVEC_DISPATCH_DTYPE(dtype, Tt, {
         const size_t smem = fwd_smem<Tt>(T, d);
-        if (smem > 227 * 1024) return AVEC_ERR_UNSUPPORTED;
+        if (g_force_long || T > 32 * MAX_KPL || smem > 227 * 1024)
+            return avec_attn_long_fwd(qkv, e, klen, qlen, o, probs, B, T, H, d, G, Tf, u, v, dtype, as_stream(stream));
         auto kfn = relpos_attn_fwd_kernel<Tt>;
         if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return AVEC_ERR_LAUNCH;
         kfn<<<B * H, ATT_THREADS, smem, as_stream(stream)>>>((const Tt*)qkv, (const Tt*)e, klen, qlen, (Tt*)o, probs, T, H, d, G, D1, Tf, u, v);
@@ -325,15 +314,16 @@ extern "C" int avec_relpos_attn_bwd(const void* d_o, const void* qkv, const void
                                     void* dqkv, float* de, int B, int T, int H, int d, int G, int Tf, const float* u, const float* v,
                                     float* du, float* dv, int dtype, avec_stream_t stream) {
     AVEC_CHECK_ARG(d_o && qkv && e && probs && ds_ws && dqkv && de && B > 0 && T > 0 && G >= 1 && (H * d) % G == 0);
-    AVEC_CHECK_ARG(T <= 32 * MAX_KPL && d <= 32 * MAX_CPL && Tf > (T - 1) * G && Tf <= T * G);
-    if (dtype == AVEC_BF16 && G == 1 && !u && !v && !du && !dv && Tf == T) {
+    AVEC_CHECK_ARG(d <= 32 * MAX_CPL && Tf > (T - 1) * G && Tf <= T * G);
+    if (dtype == AVEC_BF16 && G == 1 && !u && !v && !du && !dv && Tf == T && !g_force_long) {
         const int rc = avec_attn_mma_bwd(d_o, qkv, e, probs, dqkv, de, B, T, H, d, as_stream(stream));
         if (rc != AVEC_ERR_UNSUPPORTED) return rc;
     }
     const int D1 = H * d / G;
     AVEC_DISPATCH_DTYPE(dtype, Tt, {
         const size_t smem = bwd_smem<Tt>(T, d);
-        if (smem > 227 * 1024) return AVEC_ERR_UNSUPPORTED;
+        if (g_force_long || T > 32 * MAX_KPL || smem > 227 * 1024)
+            return avec_attn_long_bwd(d_o, qkv, e, probs, ds_ws, dqkv, de, B, T, H, d, G, Tf, u, v, du, dv, dtype, as_stream(stream));
         auto kfn = relpos_attn_bwd_kernel<Tt>;
         if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return AVEC_ERR_LAUNCH;
         kfn<<<B * H, ATT_THREADS, smem, as_stream(stream)>>>((const Tt*)d_o, (const Tt*)qkv, (const Tt*)e, probs, ds_ws, (Tt*)dqkv, de, T, H, d,

@@ -5,7 +5,7 @@ set -e
 cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 OUT=${OUT:-../libavec_b200.so}
-SRCS="api.cu gemm_simt.cu gemm_tc.cu attention.cu attention_mma.cu norm.cu convmod.cu frontend.cu ctc.cu train.cu"
+SRCS="api.cu gemm_simt.cu gemm_tc.cu attention.cu attention_long.cu attention_mma.cu norm.cu convmod.cu frontend.cu ctc.cu train.cu"
 $NVCC -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 --use_fast_math -Xcompiler -fPIC -shared \
   -Xptxas -v "$@" $SRCS -o $OUT 2> ${LOG:-build.log} || { cat ${LOG:-build.log}; exit 1; }
 grep -E "error|warning : .*spill|bytes spill" ${LOG:-build.log} | grep -v "0 bytes spill" | head -20 || true

@@ -145,6 +145,9 @@ int avec_pool_sum(const void* dy, void* dout, int B, int T, int Tp, int C, int P
  * o is [B*Tf, D1]; probs [B,H,T,T] fp32 is saved for the backward.
  * bwd: dqkv [B*Tf, 3*D1]; de [2T-1, G*D1], du, dv [D1] fp32, accumulated atomically; ds_ws: [B,H,T,T] fp32 scratch (dS).
  * ------------------------------------------------------------------------------------------------------------------ */
+/* Kernel selection is automatic: tensor-core kernels (bf16, T <= 128 / 112), whole-head SIMT kernels (T <= 416 keys and tiles <=
+ * 227 KB), key-tiled SIMT kernels beyond that (T <= ~1500).  avec_set_attention_long(1) forces the key-tiled kernels (tests). */
+void avec_set_attention_long(int force);
 int avec_relpos_attn_fwd(const void* qkv, const void* e, const int* klen, int qlen, void* o, float* probs, int B, int T,
                          int H, int d, int G, int Tf, const float* u, const float* v, int dtype, avec_stream_t stream);
 int avec_relpos_attn_bwd(const void* d_o, const void* qkv, const void* e, const float* probs, float* ds_ws, void* dqkv,
