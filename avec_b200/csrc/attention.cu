@@ -287,6 +287,9 @@ int avec_attn_long_bwd(const void* d_o, const void* qkv, const void* e, const fl
                        int H, int d, int G, int Tf, const float* u, const float* v, float* du, float* dv, int dtype, cudaStream_t st);
 
 static int g_force_long = 0;
+// whole-head kernels run ONE CTA per (item, head) (8 warps on an SM); from ~256 keys on the key-tiled kernels' T/32 x B x H grid wins
+// (AO regular attention, 800 mel frames, B = 32: 58.8 vs 70.6 ms per training step, profiles/r01_ablation_sweep.md)
+constexpr int LONG_FROM_T = 256;
 extern "C" void avec_set_attention_long(int force) { g_force_long = force; }
 
 extern "C" int avec_relpos_attn_fwd(const void* qkv, const void* e, const int* klen, int qlen, void* o, float* probs, int B,
@@ -300,7 +303,7 @@ extern "C" int avec_relpos_attn_fwd(const void* qkv, const void* e, const int* k
     const int D1 = H * d / G;
     AVEC_DISPATCH_DTYPE(dtype, Tt, {
         const size_t smem = fwd_smem<Tt>(T, d);
-        if (g_force_long || T > 32 * MAX_KPL || smem > 227 * 1024)
+        if (g_force_long || T > LONG_FROM_T || smem > 227 * 1024)
             return avec_attn_long_fwd(qkv, e, klen, qlen, o, probs, B, T, H, d, G, Tf, u, v, dtype, as_stream(stream));
         auto kfn = relpos_attn_fwd_kernel<Tt>;
         if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return AVEC_ERR_LAUNCH;
@@ -322,7 +325,7 @@ extern "C" int avec_relpos_attn_bwd(const void* d_o, const void* qkv, const void
     const int D1 = H * d / G;
     AVEC_DISPATCH_DTYPE(dtype, Tt, {
         const size_t smem = bwd_smem<Tt>(T, d);
-        if (g_force_long || T > 32 * MAX_KPL || smem > 227 * 1024)
+        if (g_force_long || T > LONG_FROM_T || smem > 227 * 1024)
             return avec_attn_long_bwd(d_o, qkv, e, probs, ds_ws, dqkv, de, B, T, H, d, G, Tf, u, v, du, dv, dtype, as_stream(stream));
         auto kfn = relpos_attn_bwd_kernel<Tt>;
         if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return AVEC_ERR_LAUNCH;

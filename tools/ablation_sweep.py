@@ -14,13 +14,18 @@ from avec_b200 import nnet
 
 dev = torch.device("cuda", 0)
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+FORCE_LONG = os.environ.get("AVEC_ATTN_LONG") == "1"      # diagnostics: key-tiled attention kernels for every length
+if FORCE_LONG:
+    from avec_b200 import _lib
+    _lib.load().avec_set_attention_long(1)
+FRAMES = [int(f) for f in os.environ.get("FRAMES", "100,200,400,800,1600").split(",")]
 avec_b200.set_compute_dtype(torch.bfloat16)
 ctc = nnet.CTCLoss(zero_infinity=True, assert_shorter=False)
 rows = []
 for att in ("patch", "grouped", "regular"):  # noqa: C901
     torch.manual_seed(0)
     model = nnet.AudioEfficientConformerInterCTC(att_type=att).to(dev).train()
-    for frames in (100, 200, 400, 800, 1600):
+    for frames in FRAMES:
         L = (frames - 1) * 160
         audio = 0.1 * torch.randn(B, L, device=dev)
         alen = torch.full((B,), L, device=dev)
