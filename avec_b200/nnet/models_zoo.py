@@ -18,11 +18,34 @@ class Model(nn.Module):
         self.losses = None
         self.loss_weights = None
 
-    def compile(self, losses=None, loss_weights=None, optimizer=None, metrics=None, decoders=None):
+    # the zoo's default loss weights, mapped to the outputs by position (lists) or key (dicts): models_zoo.py:81,131,166
+    default_loss_weights = None
+
+    def compile(self, losses=None, loss_weights=None, optimizer=None, metrics=None, decoders=None, grad_max_norm=None, ema_tau=None):
+        """same arguments as the zoo models' compile (models_zoo.py:78-99,128-149,163-184): optimizer="Adam" builds the reference's
+        default (Noam schedule 10000 / 360 / 2, betas (0.9, 0.98), eps 1e-9, L2 weight decay 1e-6) as the fused flat-buffer
+        optimizer; grad_max_norm / ema_tau (Model arguments in the reference, model.py:378-404) are folded into the same launch."""
+        from . import optimizers, schedulers
         self.losses = losses if losses is not None else CTCLoss()
-        self.loss_weights = loss_weights
+        self.loss_weights = loss_weights if loss_weights is not None else self.default_loss_weights
+        if optimizer == "Adam":
+            lr = schedulers.NoamDecayScheduler(warmup_steps=10000, dim_decay=360, val_factor=2)
+            optimizer = optimizers.Adam(params=self.parameters(), lr=lr, betas=(0.9, 0.98), eps=1e-9, weight_decay=1e-6,
+                                        grad_max_norm=grad_max_norm, ema_tau=ema_tau)
         self.optimizer, self.metrics, self.decoders = optimizer, metrics, decoders
         self.compiled = True
+
+    def train_step(self, inputs, targets):
+        """forward + weighted CTC losses + backward + optimizer step (the arithmetic of Model.train_step, model.py:342-407,
+        without grad scaler / accumulation / logging).  Returns the detached total loss (no host sync)."""
+        assert self.compiled and self.optimizer is not None, "compile(optimizer=...) first"
+        outputs = self(inputs)
+        loss = self.compute_loss(outputs, targets)
+        for p in self.parameters():
+            p.grad = None
+        loss.backward()
+        self.optimizer.step()
+        return loss.detach()
 
     def num_params(self):
         return sum(p.numel() for p in self.parameters())
@@ -50,6 +73,8 @@ class Model(nn.Module):
 
 
 class AudioEfficientConformerInterCTC(Model):
+    default_loss_weights = [0.5 / 4, 0.5 / 4, 0.5 / 4, 0.5 / 4, 0.5]
+
     def __init__(self, vocab_size=256, att_type="patch", interctc_blocks=[3, 6, 10, 13]):
         super().__init__(name="Audio Efficient Conformer Inter CTC")
         self.encoder = networks.AudioEfficientConformerEncoder(vocab_size=vocab_size, att_type=att_type, interctc_blocks=interctc_blocks)
@@ -64,6 +89,8 @@ class AudioEfficientConformerInterCTC(Model):
 
 
 class VisualEfficientConformerInterCTC(Model):
+    default_loss_weights = [0.5 / 3, 0.5 / 3, 0.5 / 3, 0.5]
+
     def __init__(self, vocab_size=256, interctc_blocks=[3, 6, 9], test_augments=None):
         super().__init__(name="Visual Efficient Conformer Inter CTC")
         self.encoder = networks.VisualEfficientConformerEncoder(vocab_size=vocab_size, interctc_blocks=interctc_blocks)
@@ -79,6 +106,8 @@ class VisualEfficientConformerInterCTC(Model):
 
 
 class AudioVisualEfficientConformerInterCTC(Model):
+    default_loss_weights = {"v_ctc_2": 0.5 / 3, "v_ctc_5": 0.5 / 3, "a_ctc_7": 0.5 / 3, "a_ctc_10": 0.5 / 3, "f_ctc_1": 0.5 / 3, "outputs": 0.5}
+
     def __init__(self, vocab_size=256, v_interctc_blocks=[3, 6], a_interctc_blocks=[8, 11], f_interctc_blocks=[2]):
         super().__init__(name="Audio-Visual Efficient Conformer Inter CTC")
         self.encoder = networks.AudioVisualEfficientConformerEncoder(

@@ -230,9 +230,34 @@ class AudioVisualEfficientConformerEncoder(nn.Module):
             ff_ratio=4, drop_rate=0.1, conv_stride=2, batch_norm=True, loss_prefix="f_ctc")
         self.head = Linear(dim_model, vocab_size) if include_head else nn.Identity()
 
+    # The two encoders are independent until the fusion module: the audio branch (~600 small, latency-bound launches) is issued
+    # on a second CUDA stream so that it fills the SMs the video front-end's kernels leave idle.  Autograd runs every backward
+    # node on its forward's stream, so the two backward passes overlap the same way; under CUDA-graph capture the fork / join
+    # becomes two parallel branches of the graph.  Set to False for a single-stream schedule.
+    overlap_branches = True
+    _side_streams = {}
+
+    def _side_stream(self, device):
+        s = self._side_streams.get(device)
+        if s is None:
+            s = torch.cuda.Stream(device=device)
+            self._side_streams[device] = s
+        return s
+
     def forward(self, video, video_len, audio, audio_len):
-        video, video_len, video_interctc_outputs = self.video_encoder(video, video_len)
-        audio, audio_len, audio_interctc_outputs = self.audio_encoder(audio, audio_len)
+        if self.overlap_branches and video.is_cuda:
+            cur = torch.cuda.current_stream(video.device)
+            side = self._side_stream(video.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                audio, audio_len, audio_interctc_outputs = self.audio_encoder(audio, audio_len)
+            video, video_len, video_interctc_outputs = self.video_encoder(video, video_len)
+            cur.wait_stream(side)
+            for t in [audio] + [v[0] for v in audio_interctc_outputs.values()]:
+                t.record_stream(cur)      # produced on the side stream, consumed (fusion, losses) on the caller's stream
+        else:
+            video, video_len, video_interctc_outputs = self.video_encoder(video, video_len)
+            audio, audio_len, audio_interctc_outputs = self.audio_encoder(audio, audio_len)
         x = self.fusion_module(audio, video)
         lengths = audio_len
         x, lengths, interctc_outputs = self.audio_visual_encoder(x, lengths)

@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--loss", default="ctc", choices=["ctc", "sum"])
     ap.add_argument("--optimizer", default="none", choices=["none", "adam"], help="adam: add the fused optimizer step (Adam + Noam LR + "
                     "global-norm clip, avec_b200.nnet.optimizers.Adam) to every step; the headline metric is forward + backward (none)")
+    ap.add_argument("--overlap", type=int, default=1, help="AV model: audio encoder on a second stream, concurrent with the video encoder")
     ap.add_argument("--dropout", type=float, default=0.1, help="0.1 = the reference's training graph (dropout at every site + "
                     "SpecAugment, networks.py:327,347-353); 0 = the deterministic parity graph (dropout off, SpecAugment bypassed)")
     ap.add_argument("--graph", type=int, default=1, help="capture forward+backward in one CUDA graph (falls back to eager if capture fails)")
@@ -199,6 +200,8 @@ def main():
             if isinstance(mod, torch.nn.Dropout):
                 mod.p = args.dropout
     model = model.to(dev).train()
+    if args.model == "AV":
+        model.encoder.overlap_branches = bool(args.overlap)
     if world > 1:  # identical replicas
         parallel.broadcast_parameters(model)
     ctc = nnet.CTCLoss(zero_infinity=True, assert_shorter=False)
@@ -341,7 +344,7 @@ def main():
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": f"{args.model} EffConfInterCTC fwd+bwd (train mode, {aug}, 6 CTC heads), per-GPU batch {B}, "
                                    f"64000 audio samples + {101 if args.model == 'AV' else 100}x88x88 video",
-                       "global_batch": world * B, "parallelism": f"dp{world}", "bn": "local batch statistics", "optimizer": args.optimizer, "loss": args.loss, "cuda_graph": bool(use_graph),
+                       "global_batch": world * B, "parallelism": f"dp{world}", "bn": "local batch statistics", "optimizer": args.optimizer, "streams": (2 if (args.model == "AV" and args.overlap) else 1), "loss": args.loss, "cuda_graph": bool(use_graph),
                        "l2": "inputs+activations per step (>1 GB) exceed the 126 MB L2; no flush needed",
                        "achieved_tflops_whole_step": value / world * AV_GFLOP_PER_UTT / 1000.0 if args.model == "AV" else None,
                        "frac_of_tensor_peak_whole_step": (value / world * AV_GFLOP_PER_UTT / 1000.0) / peak_tf if args.model == "AV" else None},

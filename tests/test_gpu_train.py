@@ -246,3 +246,27 @@ def test_model_training_graph_fresh_masks_and_determinism():
     g.replay()
     r2 = static_out.clone()
     assert torch.isfinite(r1).all() and rel_err(r2, r1) > 0.05
+
+
+def test_train_step_reduces_the_loss():
+    """Model.compile(optimizer=...) + Model.train_step: forward + weighted CTC losses + backward + fused Adam on a fixed batch;
+    the loss falls, parameters stay views of the flat buffer, compile("Adam") builds the reference's default optimizer"""
+    torch.manual_seed(0)
+    m = nnet.zero_dropout(nnet.AudioEfficientConformerInterCTC()).to(DEV).train()
+    m.compile(losses=nnet.CTCLoss(zero_infinity=True, assert_shorter=False),
+              optimizer=nnet.optimizers.Adam(m.parameters(), lr=2e-4, betas=(0.9, 0.98), eps=1e-9, weight_decay=1e-6, grad_max_norm=5.0))
+    assert m.loss_weights == [0.125, 0.125, 0.125, 0.125, 0.5]
+    B = 4
+    audio = (0.1 * torch.randn(B, 16000)).to(DEV)
+    alen = torch.full((B,), 16000, device=DEV)
+    targets = (torch.randint(1, 256, (B, 5), device=DEV), torch.full((B,), 5, device=DEV))
+    losses = [float(m.train_step((audio, alen), targets)) for _ in range(8)]
+    assert all(np.isfinite(losses)) and losses[-1] < 0.8 * losses[0], losses
+    flat = m.optimizer.flat()
+    assert all(p.data_ptr() == flat["p"].data_ptr() + 4 * o for p, o in zip(flat["params"], flat["offs"]))
+    assert int(flat["step"]) == 8 and m.optimizer.last_info()["grad_norm"] > 0
+    m2 = nnet.AudioVisualEfficientConformerInterCTC()
+    m2.compile(optimizer="Adam")
+    o = m2.optimizer
+    assert isinstance(o, nnet.optimizers.Adam) and o.scheduler.device_params() == (2 * 360 ** -0.5, 10000.0)
+    assert o.param_groups[0]["betas"] == (0.9, 0.98) and o.param_groups[0]["weight_decay"] == 1e-6
