@@ -15,6 +15,14 @@ def _drop_p(m, training):
     return float(m.p) if (training and isinstance(m, nn.Dropout)) else 0.0
 
 
+def _publish(t):
+    """a cached table is built once on whichever stream asked first and then read from every stream (the audio and video
+    encoders of the AV model run on two streams and share (T, D) keys): make it globally visible before it is cached"""
+    if t.is_cuda and not torch.cuda.is_current_stream_capturing():
+        torch.cuda.current_stream(t.device).synchronize()
+    return t
+
+
 def rel_pos_table(T, D, device, dtype):
     """rows r = 0..2T-2 hold the sinusoid of relative position T-1-r (even channels sin, odd cos); the slice
     pos_encoding[max_len-T : max_len-1+T] of RelativeSinusoidalPositionalEncoding (embeddings.py:117-152)."""
@@ -26,7 +34,7 @@ def rel_pos_table(T, D, device, dtype):
         pe = torch.zeros(2 * T - 1, D)
         pe[:, 0::2] = angles.sin()
         pe[:, 1::2] = angles.cos()
-        t = pe.to(device=device, dtype=dtype).contiguous()
+        t = _publish(pe.to(device=device, dtype=dtype).contiguous())
         _pe_cache[key] = t
     return t
 
@@ -44,7 +52,7 @@ def grouped_rel_pos_table(Tp, D, G, device, dtype):
         pe = torch.zeros(2 * Tp - G, D)
         pe[:, 0::2] = angles.sin()
         pe[:, 1::2] = angles.cos()
-        t = pe.to(device=device, dtype=dtype).contiguous()
+        t = _publish(pe.to(device=device, dtype=dtype).contiguous())
         _pe_cache[key] = t
     return t
 
