@@ -83,3 +83,24 @@ def test_greedy_restatement_matches_reference():
     fix = load_golden("train_greedy.pt")
     assert TO.greedy_decode(fix["logits"].numpy(), fix["lengths"].tolist(), 0) == fix["tokens"]
     assert fix["tokens"][1] == [] and fix["tokens"][4] == []
+
+
+def test_schedulers_match_reference_formulas():
+    """avec_b200.nnet.schedulers (host side of the on-device learning-rate schedule) against the reference's classes when the
+    reference tree is importable (authoring container), and against the closed form otherwise"""
+    from avec_b200.nnet import schedulers as S
+    mine = S.NoamDecayScheduler(warmup_steps=10000, dim_decay=360, val_factor=2)
+    steps = [1, 2, 17, 9999, 10000, 10001, 250000]
+    want = [2 * 360 ** -0.5 * min(s * 10000 ** -1.5, s ** -0.5) for s in steps]
+    from oracle import ref_import
+    if ref_import.available():
+        ref = ref_import.import_reference()
+        r = ref.schedulers.NoamDecayScheduler(warmup_steps=10000, dim_decay=360, val_factor=2)
+        want = [float(r.get_val_step(s)) for s in steps]
+        assert float(ref.schedulers.ConstantScheduler(val=3e-4).get_val_step(5)) == S.ConstantScheduler(3e-4).get_val_step(5)
+    for s, w in zip(steps, want):
+        assert abs(mine.get_val_step(s) - w) <= 1e-12 + 1e-9 * w
+        assert abs(TO.noam_lr(s) - w) <= 1e-12 + 1e-9 * w
+    a, b = mine.device_params()                      # lr = a * min(t * b^-1.5, t^-0.5) evaluated by adam_kernel
+    assert abs(a * min(17 * b ** -1.5, 17 ** -0.5) - mine.get_val_step(17)) < 1e-15
+    assert mine.step() == mine.get_val_step(1) and int(mine.model_step) == 1
