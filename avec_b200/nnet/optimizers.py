@@ -74,6 +74,8 @@ class Adam(torch.optim.Optimizer):
         """grads: optional list (one per parameter) used instead of p.grad, e.g. the static outputs of a captured backward"""
         assert closure is None
         f = self.flat()
+        if grads is not None and len(grads) != len(f["params"]):
+            raise ValueError(f"grads has {len(grads)} entries for {len(f['params'])} trainable parameters")
         src, dst = [], []
         for i, (p, gv) in enumerate(zip(f["params"], f["gviews"])):
             g = grads[i] if grads is not None else p.grad
