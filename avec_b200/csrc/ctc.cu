@@ -34,7 +34,11 @@ __global__ void __launch_bounds__(CTC_THREADS) ctc_kernel(const float* __restric
     const float* lg = logits + (size_t)b * T * V;
     float* gr = grad + (size_t)b * T * V;
     float* alpha = ws + (size_t)b * T * Smax;   // [T][Smax]
-    for (int s = tid; s < Smax; s += CTC_THREADS) lab[s] = (s & 1) ? (int)labels[(size_t)b * Lmax + (s >> 1)] : blank;
+    // labels outside [0, V) cannot be reported from the device: they are clamped (never an out-of-bounds read of the logits row)
+    for (int s = tid; s < Smax; s += CTC_THREADS) {
+        long long l = (s & 1) ? labels[(size_t)b * Lmax + (s >> 1)] : (long long)blank;
+        lab[s] = (int)min(max(l, 0LL), (long long)V - 1);
+    }
     // ---- log-softmax denominators and softmax rows (the gradient's first term)
     for (int t = warp; t < T; t += nw) {
         const float* row = lg + (size_t)t * V;
@@ -81,8 +85,10 @@ __global__ void __launch_bounds__(CTC_THREADS) ctc_kernel(const float* __restric
         if (zero_infinity) {
             for (int i = tid; i < T * V; i += CTC_THREADS) gr[i] = 0.0f;
             if (tid == 0) nll[b] = 0.0f;
-        } else if (tid == 0) {
-            nll[b] = INFINITY;
+        } else {
+            // torch.nn.functional.ctc_loss(zero_infinity=False): loss = inf and a NaN gradient for the whole utterance
+            for (int i = tid; i < T * V; i += CTC_THREADS) gr[i] = __int_as_float(0x7fc00000);
+            if (tid == 0) nll[b] = INFINITY;
         }
         return;
     }

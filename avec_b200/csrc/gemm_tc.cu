@@ -2123,14 +2123,31 @@ bool conv_tma_geom_ok(const ConvGeom& g, bool dgrad) {
     return base && (!dgrad || g.sh == 1);
 }
 
+// per-DEVICE caches: cudaFuncSetAttribute and the SM count belong to the current device, and one process may drive several
+constexpr int MAX_DEVICES = 64;
+int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev >= 0 && dev < MAX_DEVICES ? dev : 0;
+}
 int num_sms_cached() {
-    static int num_sms = 0;
-    if (num_sms == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
+    static int num_sms[MAX_DEVICES] = {0};
+    const int dev = current_device();
+    if (num_sms[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        num_sms[dev] = n;
     }
-    return num_sms;
+    return num_sms[dev];
+}
+// opt-in dynamic shared memory of kernel `slot`, set once per device
+bool smem_attr_once(int slot, const void* fn, int bytes) {
+    static bool done[8][MAX_DEVICES] = {{false}};
+    const int dev = current_device();
+    if (done[slot][dev]) return true;
+    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) != cudaSuccess) return false;
+    done[slot][dev] = true;
+    return true;
 }
 
 }  // namespace
@@ -2212,11 +2229,7 @@ static int wgrad_halo_launch(const avec_gemm_args* a, cudaStream_t st) {
     cuuint64_t sb[3] = {128, (cuuint64_t)p.W * 128, (cuuint64_t)p.W * p.H * 128};
     cuuint32_t boxY[4] = {64, (cuuint32_t)p.W2, (cuuint32_t)p.BH, 1}, boxX[4] = {64, (cuuint32_t)p.W2, (cuuint32_t)(p.BH + 2), 1};
     if (!encode_map(&mapY, a->A, 4, d, sb, boxY) || !encode_map(&mapX, a->B, 4, d, sb, boxX)) return AVEC_ERR_DRIVER;
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(wgrad_halo64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WH_SMEM) != cudaSuccess) return AVEC_ERR_LAUNCH;
-        attr_set = true;
-    }
+    if (!smem_attr_once(0, reinterpret_cast<const void*>(wgrad_halo64_kernel), (int)WH_SMEM)) return AVEC_ERR_LAUNCH;
     const int ctas = std::min(p.total_tiles, num_sms_cached());
     wgrad_halo64_kernel<<<ctas, WH_THREADS, WH_SMEM, st>>>(p, mapY, mapX);
     AVEC_LAUNCH_CHECK();
@@ -2259,11 +2272,7 @@ static int conv_halo_launch(const avec_gemm_args* a, cudaStream_t st) {
     cuuint32_t boxX[4] = {64, (cuuint32_t)p.W2, (cuuint32_t)(p.BH + 2), 1};
     cuuint64_t dw_[2] = {576, 64}; cuuint64_t sw_[1] = {576 * 2}; cuuint32_t boxW[2] = {64, 64};
     if (!encode_map(&mapX, a->A, 4, d, sb, boxX) || !encode_map(&mapW, a->B, 2, dw_, sw_, boxW)) return AVEC_ERR_DRIVER;
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(conv3x3_halo64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CH_SMEM) != cudaSuccess) return AVEC_ERR_LAUNCH;
-        attr_set = true;
-    }
+    if (!smem_attr_once(1, reinterpret_cast<const void*>(conv3x3_halo64_kernel), (int)CH_SMEM)) return AVEC_ERR_LAUNCH;
     const int ctas = std::min(p.total_tiles, num_sms_cached());
     conv3x3_halo64_kernel<<<ctas, CH_THREADS, CH_SMEM, st>>>(p, mapX, mapW);
     AVEC_LAUNCH_CHECK();
@@ -2310,11 +2319,7 @@ static int wgrad_img_launch(const avec_gemm_args* a, const WgImgParams& p, cudaS
     cuuint64_t sX[3] = {(cuuint64_t)p.C * 2, (cuuint64_t)p.W * p.C * 2, (cuuint64_t)p.W * p.H * p.C * 2};
     cuuint32_t box[4] = {64, (cuuint32_t)p.G, (cuuint32_t)(p.H + 2), (cuuint32_t)p.BI};
     if (!encode_map(&mapY, a->A, 4, dY, sY, box) || !encode_map(&mapX, a->B, 4, dX, sX, box)) return AVEC_ERR_DRIVER;
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(wgrad_img_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WI_SMEM_MAX) != cudaSuccess) return AVEC_ERR_LAUNCH;
-        attr_set = true;
-    }
+    if (!smem_attr_once(2, reinterpret_cast<const void*>(wgrad_img_kernel), (int)WI_SMEM_MAX)) return AVEC_ERR_LAUNCH;
     const int nblocks = p.ncb * p.ncob;
     const int parts = std::max(1, std::min(num_sms_cached() / nblocks, p.tiles));
     const size_t smem = 1024 + (size_t)p.stages * p.stage_bytes + 1024;
@@ -2555,11 +2560,7 @@ static int gemm_tc_launch(const avec_gemm_args* a, cudaStream_t st, const DgradC
             }
         }
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return AVEC_ERR_LAUNCH;
-        attr_set = true;
-    }
+    if (!smem_attr_once(3, reinterpret_cast<const void*>(gemm_tc_kernel), 227 * 1024)) return AVEC_ERR_LAUNCH;
     // ---- fast epilogue: launch-constant eligibility (see epilogue_fast)
     {
         static int fast_on = -1;
@@ -2621,11 +2622,7 @@ extern "C" int avec_stem3d_fwd(const void* x, const void* wp, const float* bias,
     CUtensorMap mapW;
     cuuint64_t d[2] = {(cuuint64_t)ST_KPAD, 64}; cuuint64_t s1[1] = {(cuuint64_t)ST_KPAD * 2}; cuuint32_t box[2] = {64, 64};
     if (!encode_map(&mapW, wp, 2, d, s1, box)) return AVEC_ERR_DRIVER;
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(stem3d_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_FWD_SMEM) != cudaSuccess) return AVEC_ERR_LAUNCH;
-        attr_set = true;
-    }
+    if (!smem_attr_once(4, reinterpret_cast<const void*>(stem3d_fwd_kernel), (int)ST_FWD_SMEM)) return AVEC_ERR_LAUNCH;
     const int ctas = std::min(p.total_tiles, num_sms_cached());
     stem3d_fwd_kernel<<<ctas, ST_FWD_THREADS, ST_FWD_SMEM, as_stream(stream)>>>(p, mapW);
     AVEC_LAUNCH_CHECK();
@@ -2642,11 +2639,7 @@ extern "C" int avec_stem3d_wgrad(const void* x, const void* dy, float* dw, int N
     const cuuint64_t sites = (cuuint64_t)p.Ho * p.Wo;
     cuuint64_t d[3] = {64, sites, (cuuint64_t)Nb * T}; cuuint64_t st[2] = {128, sites * 128}; cuuint32_t box[3] = {64, 128, 1};
     if (!encode_map(&mapY, dy, 3, d, st, box)) return AVEC_ERR_DRIVER;
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(stem3d_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_WG_SMEM) != cudaSuccess) return AVEC_ERR_LAUNCH;
-        attr_set = true;
-    }
+    if (!smem_attr_once(5, reinterpret_cast<const void*>(stem3d_wgrad_kernel), (int)ST_WG_SMEM)) return AVEC_ERR_LAUNCH;
     const int ctas = std::min(p.total_tiles, num_sms_cached());
     stem3d_wgrad_kernel<<<ctas, ST_WG_THREADS, ST_WG_SMEM, as_stream(stream)>>>(p, mapY);
     AVEC_LAUNCH_CHECK();

@@ -37,6 +37,13 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const T* __restrict_
             else { v[u][0] = v[u][1] = v[u][2] = v[u][3] = 0.0f; }
             s += v[u][0] + v[u][1] + v[u][2] + v[u][3];
         }
+        if (gamma == nullptr) {   // identity mode (attention.forwardQKV without the module's LayerNorm): plain patch mean
+#pragma unroll
+            for (int u = 0; u < LN_G; ++u)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) out[u][j] += v[u][j];
+            continue;
+        }
         s = warp_sum(s);
         const float mu = s / C;
         float q = 0.0f;
@@ -94,13 +101,35 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict_
         int c = (lane + u * 32) * 4;
 #pragma unroll
         for (int j = 0; j < 4; ++j) { dg[u][j] = 0.0f; db[u][j] = 0.0f; gm[u][j] = 0.0f; }
-        if (c < C) load_vec<4>(gamma + c, gm[u]);
+        if (c < C && gamma) load_vec<4>(gamma + c, gm[u]);
     }
     const float invP = 1.0f / P;
     for (long long row = (long long)blockIdx.x * wpb + wib; row < rows; row += (long long)gridDim.x * wpb) {
         const int b = (int)(row / Tn), t = (int)(row % Tn);
         const T* xr = x + row * C;
         const T* dyr = dy + ((size_t)b * Tp + t / P) * C;
+        if (gamma == nullptr) {   // identity mode: dx = expand(dy) / P (+ dres)
+            const bool hr = dres != nullptr && (t % res_stride) == 0;
+            const T* r0 = hr ? dres + ((size_t)b * Tr + t / res_stride) * C : nullptr;
+#pragma unroll
+            for (int u = 0; u < LN_G; ++u) {
+                int c = (lane + u * 32) * 4;
+                if (c < C) {
+                    float d[4];
+                    load_vec<4>(dyr + c, d);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) d[j] *= invP;
+                    if (hr) {
+                        float r4[4];
+                        load_vec<4>(r0 + c, r4);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) d[j] += r4[j];
+                    }
+                    store_vec<4>(dx + row * C + c, d);
+                }
+            }
+            continue;
+        }
         const float mu = mean[row], rs = rstd[row];
         float g[LN_G][4], xh[LN_G][4];
         float s1 = 0.0f, s2 = 0.0f;
@@ -858,7 +887,7 @@ inline int ew_blocks(long long total, int threads = 256) {
 
 extern "C" int avec_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int B,
                                   int T, int C, int P, float eps, int dtype, avec_stream_t stream) {
-    AVEC_CHECK_ARG(x && gamma && beta && y && mean && rstd && B > 0 && T > 0 && P >= 1 && C > 0 && C <= 128 * LN_G && C % 4 == 0);
+    AVEC_CHECK_ARG(x && y && (gamma == nullptr || (beta && mean && rstd)) && B > 0 && T > 0 && P >= 1 && C > 0 && C <= 128 * LN_G && C % 4 == 0);
     const int Tp = cdiv(T, P);
     const long long warps = (long long)B * Tp;
     const int blocks = (int)cdivll(warps * 32, 256);
@@ -871,7 +900,7 @@ extern "C" int avec_layernorm_fwd(const void* x, const float* gamma, const float
 extern "C" int avec_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
                                   const void* dres, int res_stride, void* dx, float* dgamma, float* dbeta, int B, int T, int C,
                                   int P, int dtype, avec_stream_t stream) {
-    AVEC_CHECK_ARG(dy && x && gamma && mean && rstd && dx && B > 0 && T > 0 && P >= 1 && C > 0 && C <= 128 * LN_G && C % 4 == 0);
+    AVEC_CHECK_ARG(dy && x && (gamma == nullptr || (mean && rstd)) && dx && B > 0 && T > 0 && P >= 1 && C > 0 && C <= 128 * LN_G && C % 4 == 0);
     AVEC_CHECK_ARG(!dres || res_stride >= 1);
     const int Tp = cdiv(T, P);
     const long long rows = (long long)B * T;

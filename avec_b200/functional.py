@@ -24,60 +24,118 @@ _COMPUTE_DTYPE = torch.bfloat16
 
 
 def set_compute_dtype(dt):
-    """torch.bfloat16 (production: tcgen05 tensor cores) or torch.float32 (parity mode: exact fp32 accumulation)."""
+    """torch.bfloat16 (production: tcgen05 tensor cores), torch.float32 (parity mode: exact fp32 accumulation) or "auto":
+    bf16 inside a torch autocast region (the reference's Model.train_step wraps the forward in one when `precision` is a
+    half type, nnet/model.py:356-360), fp32 otherwise - what avec_b200.patch_reference() selects."""
     global _COMPUTE_DTYPE
-    assert dt in (torch.bfloat16, torch.float32)
+    assert dt in (torch.bfloat16, torch.float32, "auto")
     _COMPUTE_DTYPE = dt
-    new_step()
+    invalidate_weights()
 
 
 def compute_dtype():
+    if _COMPUTE_DTYPE == "auto":
+        return torch.bfloat16 if torch.is_autocast_enabled() else torch.float32
     return _COMPUTE_DTYPE
 
 
-# weight cache: compute-dtype, kernel-layout copies of the fp32 master parameters, valid for one forward+backward
+# weight cache: compute-dtype, kernel-layout copies of the fp32 master parameters.  An entry is valid while the parameter's
+# torch version counter AND the library's weight epoch are unchanged; the fused optimizer (which updates the flat parameter
+# buffer from a raw kernel, invisible to the version counter) bumps the epoch after every step.
 _wcache = {}
+_wepoch = 0
+
+
+def invalidate_weights():
+    """drop every cached compute-dtype weight copy (called by avec_b200.nnet.optimizers.Adam.step and load_state_dict hooks)"""
+    global _wepoch
+    _wepoch += 1
+    _wcache.clear()
 
 
 def new_step(arena_numel=0, device=None, advance_rng=False):
-    """start of a forward pass: drop the compute-dtype weight copies of the previous step and (optionally) allocate the
-    zero-initialised fp32 arena that gradient accumulators and BatchNorm statistics of this step are carved from;
-    advance_rng: bump the device-side RNG step (training passes: fresh dropout / SpecAugment draws, also per graph replay)"""
-    _wcache.clear()
+    """start of a forward pass: restart the dropout site counter, (optionally) allocate the zero-initialised fp32 arena that
+    gradient accumulators and BatchNorm statistics of this step are carved from, and with advance_rng bump the device-side RNG
+    step (training passes: fresh dropout / SpecAugment draws, also per CUDA-graph replay) and snapshot {seed, step} for the
+    Functions of this pass (their backward regenerates the masks from the snapshot, not from the live counter)."""
     ops.RNG.site = 0
     if arena_numel and device is not None:
         ops.ARENA.begin(arena_numel, device)
-    if advance_rng and device is not None and torch.device(device).type == "cuda":
-        ops.RNG.advance(device)
+    if device is not None and torch.device(device).type == "cuda":
+        if advance_rng:
+            ops.RNG.advance(device)
+        ops.RNG.snapshot(device)
+
+
+# The outermost module of a forward pass (a zoo Model, or an encoder called directly / from the reference's zoo models after
+# avec_b200.patch_reference()) opens the step; nested encoders see depth > 0 and do nothing.
+_depth = 0
+
+
+class forward_scope:
+    def __init__(self, module, device):
+        self.module, self.device = module, torch.device(device) if device is not None else None
+
+    def __enter__(self):
+        global _depth
+        if _depth == 0:
+            m = self.module
+            numel = getattr(m, "_arena_numel", None)
+            if numel is None:
+                # parameter gradients + BatchNorm statistics / reduction scratch + positional-embedding gradients
+                numel = int(1.3 * sum(p.numel() for p in m.parameters())) + (8 << 20)
+                try:
+                    object.__setattr__(m, "_arena_numel", numel)
+                except Exception:  # noqa: BLE001
+                    pass
+            on_gpu = self.device is not None and self.device.type == "cuda"
+            new_step(numel if on_gpu else 0, self.device, advance_rng=bool(m.training))
+        _depth += 1
+        return self
+
+    def __exit__(self, *exc):
+        global _depth
+        _depth -= 1
+        if _depth == 0:
+            ops.RNG.snap.clear()      # Functions of this pass keep their own reference (ctx.rng)
+        return False
 
 
 def manual_seed(seed):
-    """seed of the dropout / SpecAugment generator (Philox key); the step counter restarts at 0"""
+    """seed of the dropout / SpecAugment generator (Philox key); the step counter restarts at 0.  Under torch.distributed the
+    rank is folded into the key (every replica draws its own masks, as torch's per-process generators do)."""
     ops.RNG.manual_seed(seed)
+
+
+def _wvalid(hit, ver):
+    return hit is not None and hit[0] == ver and hit[2] == _wepoch
 
 
 def wc(param, tag="plain", fn=None):
     """compute-dtype copy of a parameter in the layout a kernel wants (fn: fp32 tensor -> 2-d fp32 view/tensor)."""
-    key = (id(param), tag, _COMPUTE_DTYPE)
+    dt = compute_dtype()
+    key = (id(param), tag, dt)
     hit = _wcache.get(key)
-    if hit is not None and hit[0] == param._version:
+    ver = (param._version, param.data_ptr())
+    if _wvalid(hit, ver):
         return hit[1]
     src = param.detach()
     src = fn(src) if fn is not None else src.reshape(src.shape[0], -1)
-    out = ops.convert(src, _COMPUTE_DTYPE)
-    _wcache[key] = (param._version, out)
+    out = ops.convert(src, dt, pad=True)
+    _wcache[key] = (ver, out, _wepoch)
     return out
 
 
 def wc_cat(params, tag):
-    key = (tuple(id(p) for p in params), tag, _COMPUTE_DTYPE)
-    ver = tuple(p._version for p in params)
+    dt = compute_dtype()
+    key = (tuple(id(p) for p in params), tag, dt)
+    ver = tuple((p._version, p.data_ptr()) for p in params)
     hit = _wcache.get(key)
-    if hit is not None and hit[0] == ver:
+    if _wvalid(hit, ver):
         return hit[1]
     src = torch.cat([p.detach().reshape(p.shape[0], -1) for p in params], dim=0)
-    out = ops.convert(src, _COMPUTE_DTYPE) if src.dim() == 2 and src.shape[1] > 1 else src
-    _wcache[key] = (ver, out)
+    out = ops.convert(src, dt, pad=True) if src.dim() == 2 and src.shape[1] > 1 else src
+    _wcache[key] = (ver, out, _wepoch)
     return out
 
 
@@ -96,12 +154,13 @@ class FFNFn(Function):
         xn, mean, rstd = ops.layernorm_fwd(x, ln_w, ln_b)
         h, pre = ops.linear_fwd(xn.view(B * T, D), wc(w1), b1, L.EPI_SWISH, want_pre=True)
         s_in = s_out = 0
+        ctx.rng = ops.RNG.cur(x.device)
         if p_in > 0:
             s_in = ops.RNG.next_site()
-            ops.dropout(h, p_in, s_in, out=h)
+            ops.dropout_rng(ctx.rng, h, p_in, s_in, out=h)
         if p_out > 0:
             s_out = ops.RNG.next_site()
-            y = ops.dropout(ops.linear_fwd(h, wc(w2), b2), p_out, s_out, res=x.view(B * T, D), alpha=0.5)
+            y = ops.dropout_rng(ctx.rng, ops.linear_fwd(h, wc(w2), b2), p_out, s_out, res=x.view(B * T, D), alpha=0.5)
         else:
             y = ops.linear_fwd(h, wc(w2), b2, L.EPI_RESIDUAL, alpha=0.5, aux=x.view(B * T, D))
         ctx.save_for_backward(x, ln_w, mean, rstd, xn, pre, h, w1, w2)
@@ -116,12 +175,12 @@ class FFNFn(Function):
         dy = _c(dy)
         dy2 = dy.view(B * T, D)
         if p_out > 0:
-            dyd, a = ops.dropout(dy2, p_out, s_out, alpha=0.5), 1.0
+            dyd, a = ops.dropout_rng(ctx.rng, dy2, p_out, s_out, alpha=0.5), 1.0
         else:
             dyd, a = dy2, 0.5
         dpre = ops.linear_dgrad(dyd, wc(w2), L.EPI_DSWISH, alpha=a, aux=pre)
         if p_in > 0:
-            ops.dropout(dpre, p_in, s_in, out=dpre)
+            ops.dropout_rng(ctx.rng, dpre, p_in, s_in, out=dpre)
         dw2 = ops.linear_wgrad(dyd, h, alpha=a)
         db2 = ops.colsum(dyd, a)
         dxn = ops.linear_dgrad(dpre, wc(w1))
@@ -140,6 +199,7 @@ class AttentionFn(Function):
         B, T, D = x.shape
         d = D // H
         x = _c(x)
+        ctx.rng = ops.RNG.cur(x.device)
         xp, mean, rstd = ops.layernorm_fwd(x, ln_w, ln_b, P=P)
         Tp = xp.shape[1]
         wqkv = wc_cat((wq, wk, wv), "qkv")
@@ -153,13 +213,15 @@ class AttentionFn(Function):
             klen_p, qlen = klen, Tp
         o, probs = ops.relpos_attn_fwd(qkv, e, klen_p, qlen, B, Tp, H, d)
         site = 0
-        if p_drop > 0:
+        plain = ln_w is None          # attention.forwardQKV: no LayerNorm in front, no residual behind (modules.py:330)
+        res = None if plain else x.view(B * T, D)
+        if p_drop > 0 or (plain and P > 1):
             # AttentionModule.dropout acts on the upsampled (B, T, D) output: one mask element per frame (modules.py:333)
-            site = ops.RNG.next_site()
+            site = ops.RNG.next_site() if p_drop > 0 else 0
             proj = ops.linear_fwd(o, wc(wo), bo)
-            y = ops.dropout(proj, p_drop, site, res=x.view(B * T, D), up=(T, Tp, P) if P > 1 else None).view(B, T, D)
+            y = ops.dropout_rng(ctx.rng, proj, p_drop, site, res=res, up=(T, Tp, P) if P > 1 else None).view(B, T, D)
         elif P == 1:
-            y = ops.linear_fwd(o, wc(wo), bo, L.EPI_RESIDUAL, aux=x.view(B * T, D)).view(B, T, D)
+            y = ops.linear_fwd(o, wc(wo), bo, L.EPI_LINEAR if plain else L.EPI_RESIDUAL, aux=res).view(B, T, D)
         else:
             proj = ops.linear_fwd(o, wc(wo), bo)
             y = ops.upsample_add(x, proj.view(B, Tp, D), P)
@@ -176,7 +238,7 @@ class AttentionFn(Function):
         d = D // H
         dy = _c(dy)
         p_drop, site = ctx.drop
-        dyd = ops.dropout(dy.view(B * T, D), p_drop, site).view(B, T, D) if p_drop > 0 else dy
+        dyd = ops.dropout_rng(ctx.rng, dy.view(B * T, D), p_drop, site).view(B, T, D) if p_drop > 0 else dy
         dproj = dyd.view(B * T, D) if P == 1 else ops.pool_sum(dyd, P).view(B * Tp, D)
         do = ops.linear_dgrad(dproj, wc(wo))
         dwo = ops.linear_wgrad(dproj, o)
@@ -188,7 +250,7 @@ class AttentionFn(Function):
         dxp = ops.linear_dgrad(dqkv, wqkv)
         dwqkv = ops.linear_wgrad(dqkv, xp.view(B * Tp, D))
         dbqkv = ops.colsum(dqkv)
-        dx, dg, db = ops.layernorm_bwd(dxp.view(B, Tp, D), x, ln_w, mean, rstd, P=P, dres=dy, res_stride=1)
+        dx, dg, db = ops.layernorm_bwd(dxp.view(B, Tp, D), x, ln_w, mean, rstd, P=P, dres=None if ln_w is None else dy, res_stride=1)
         return (dx, dg, db, dwqkv[:D], dbqkv[:D], dwqkv[D:2 * D], dbqkv[D:2 * D], dwqkv[2 * D:], dbqkv[2 * D:], dwo, dbo,
                 dwp, dbp, None, None, None, None, None)
 
@@ -204,6 +266,7 @@ class GroupedAttentionFn(Function):
         Tn = -(-T // G)
         d = G * D // H
         x = _c(x)
+        ctx.rng = ops.RNG.cur(x.device)
         xn, mean, rstd = ops.layernorm_fwd(x, ln_w, ln_b)
         wqkv = wc_cat((wq, wk, wv), "qkv")
         bqkv = wc_cat((bq, bk, bv), "bqkv").reshape(-1)
@@ -212,9 +275,12 @@ class GroupedAttentionFn(Function):
         klen_g = torch.div(klen + (G - 1), G, rounding_mode="floor").to(torch.int32) if klen is not None else None
         o, probs = ops.relpos_attn_fwd(qkv, e, klen_g, Tn, B, Tn, H, d, G=G, Tf=T, u=u, v=v)
         site = 0
+        plain = ln_w is None
         if p_drop > 0:
             site = ops.RNG.next_site()
-            y = ops.dropout(ops.linear_fwd(o, wc(wo), bo), p_drop, site, res=x.view(B * T, D)).view(B, T, D)
+            y = ops.dropout_rng(ctx.rng, ops.linear_fwd(o, wc(wo), bo), p_drop, site, res=x.view(B * T, D)).view(B, T, D)
+        elif plain:
+            y = ops.linear_fwd(o, wc(wo), bo).view(B, T, D)
         else:
             y = ops.linear_fwd(o, wc(wo), bo, L.EPI_RESIDUAL, aux=x.view(B * T, D)).view(B, T, D)
         ctx.save_for_backward(x, ln_w, mean, rstd, xn, qkv, e, probs, o, pe, wq, wk, wv, wo, wp, u, v)
@@ -230,7 +296,7 @@ class GroupedAttentionFn(Function):
         d = G * D // H
         dy = _c(dy)
         p_drop, site = ctx.drop
-        dy2 = ops.dropout(dy.view(B * T, D), p_drop, site) if p_drop > 0 else dy.view(B * T, D)
+        dy2 = ops.dropout_rng(ctx.rng, dy.view(B * T, D), p_drop, site) if p_drop > 0 else dy.view(B * T, D)
         do = ops.linear_dgrad(dy2, wc(wo))
         dwo = ops.linear_wgrad(dy2, o)
         dbo = ops.colsum(dy2)
@@ -242,7 +308,7 @@ class GroupedAttentionFn(Function):
         dxn = ops.linear_dgrad(dqkv, wqkv)
         dwqkv = ops.linear_wgrad(dqkv, xn.view(B * T, D))
         dbqkv = ops.colsum(dqkv)
-        dx, dg, db = ops.layernorm_bwd(dxn.view(B, T, D), x, ln_w, mean, rstd, dres=dy, res_stride=1)
+        dx, dg, db = ops.layernorm_bwd(dxn.view(B, T, D), x, ln_w, mean, rstd, dres=None if ln_w is None else dy, res_stride=1)
         return (dx, dg, db, dwqkv[:D], dbqkv[:D], dwqkv[D:2 * D], dbqkv[D:2 * D], dwqkv[2 * D:], dbqkv[2 * D:], dwo, dbo,
                 dwp, dbp, du, dv, None, None, None, None, None)
 
@@ -257,6 +323,7 @@ class ConvModuleFn(Function):
         De = w3.shape[0]
         ks = wd.shape[-1]
         x = _c(x)
+        ctx.rng = ops.RNG.cur(x.device)
         xn, mean, rstd = ops.layernorm_fwd(x, ln_w, ln_b)
         pre = ops.linear_fwd(xn.view(B * T, D), wc(w1), b1).view(B, T, 2 * De)
         wdw = wd.detach().reshape(De, ks)
@@ -277,7 +344,7 @@ class ConvModuleFn(Function):
         site = 0
         if p_drop > 0:
             site = ops.RNG.next_site()
-            y = ops.dropout(ops.linear_fwd(v, wc(w3), b3), p_drop, site, res=aux).view(B, To, De)
+            y = ops.dropout_rng(ctx.rng, ops.linear_fwd(v, wc(w3), b3), p_drop, site, res=aux).view(B, To, De)
         else:
             y = ops.linear_fwd(v, wc(w3), b3, L.EPI_RESIDUAL, aux=aux).view(B, To, De)
         ctx.save_for_backward(x, ln_w, mean, rstd, xn, pre, u, bnbuf, v, xs, w1, wd, bn_w, w3, wr)
@@ -296,7 +363,7 @@ class ConvModuleFn(Function):
         dy = _c(dy)
         dy2 = dy.view(B * To, De)
         p_drop, site = ctx.drop
-        dyd = ops.dropout(dy2, p_drop, site) if p_drop > 0 else dy2
+        dyd = ops.dropout_rng(ctx.rng, dy2, p_drop, site) if p_drop > 0 else dy2
         dv = ops.linear_dgrad(dyd, wc(w3))
         dw3 = ops.linear_wgrad(dyd, v)
         db3 = ops.colsum(dyd)
@@ -324,12 +391,13 @@ class DropoutFn(Function):
     def forward(ctx, x, p):
         site = ops.RNG.next_site()
         ctx.drop = (p, site)
-        return ops.dropout(_c(x), p, site)
+        ctx.rng = ops.RNG.cur(x.device)
+        return ops.dropout_rng(ctx.rng, _c(x), p, site)
 
     @staticmethod
     def backward(ctx, dy):
         p, site = ctx.drop
-        return ops.dropout(_c(dy), p, site), None
+        return ops.dropout_rng(ctx.rng, _c(dy), p, site), None
 
 
 class LayerNormFn(Function):
@@ -450,7 +518,7 @@ class AudioStemFn(Function):
         B = wave.shape[0]
         mel = ops.stft_mel_log(_c(wave.float()), fb, layout=0)
         if spec is not None:      # SpecAugment (mF, F, mT, pS) on the fp32 log-mel, in place (networks.py:423-424)
-            ops.spec_augment_(mel, mel_len, ops.RNG.next_site(), *spec)
+            ops.spec_augment_(mel, mel_len, ops.RNG.next_site(), *spec, rng=ops.RNG.cur(mel.device))
         F = mel.shape[1]
         melc = ops.convert(mel, compute_dtype())
         Co = cw.shape[0]

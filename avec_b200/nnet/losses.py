@@ -5,25 +5,22 @@ alpha/beta recursions, csrc/ctc.cu) with device-side 
 captured in a CUDA graph."""
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
 
 
 class CTCLoss(nn.Module):
     def __init__(self, blank=0, reduction="mean", zero_infinity=False, assert_shorter=True):
         super().__init__()
+        # the reference's "mean" is the mean over the batch of the per-utterance losses (losses.py:331-333); "sum" their sum
+        assert reduction in ("mean", "sum"), f"CTCLoss reduction {reduction!r}: the reference implements 'mean' and 'sum'"
         self.blank, self.reduction, self.zero_infinity, self.assert_shorter = blank, reduction, zero_infinity, assert_shorter
 
     def forward(self, targets, outputs):
         y, y_len = targets
         logits, logits_len = outputs
+        if not logits.is_cuda:
+            raise RuntimeError("avec_b200.nnet.CTCLoss needs CUDA logits: the hot path has no CPU fallback")
         if self.assert_shorter:   # host sync: keep off (assert_shorter=False) on the training hot path
             assert bool((y_len.cpu() <= logits_len.cpu()).all()), "ctc: label longer than logits"
-        if logits.is_cuda:
-            from .. import functional as AF
-            loss = AF.CTCFn.apply(logits, y, logits_len, y_len, self.blank, self.zero_infinity)
-            return loss.mean() if self.reduction == "mean" else loss.sum()
-        logp = F.log_softmax(logits.float(), dim=-1).transpose(0, 1)
-        # CPU length tensors are passed through untouched (no device sync: required under CUDA-graph capture)
-        loss = F.ctc_loss(logp, y, logits_len.to(torch.long), y_len.to(torch.long), blank=self.blank, reduction="none",
-                          zero_infinity=self.zero_infinity)
+        from .. import functional as AF
+        loss = AF.CTCFn.apply(logits, y, logits_len, y_len, self.blank, self.zero_infinity)
         return loss.mean() if self.reduction == "mean" else loss.sum()

@@ -1,7 +1,7 @@
 """Zoo models with the reference's constructor arguments and forward(inputs) -> dict convention
 (reference nnet/models_zoo.py:64-182).  Only the encoder hot path is re-implemented; `Model` here is a light nn.Module
 base (compile / forward / losses) - the reference's training runtime (nnet/model.py fit/evaluate/save/...) is out of
-scope and keeps working by patching these encoders into it (avec_b200.patch_reference)."""
+scope and keeps working by patching these encoders into it (avec_b200.patch_reference())."""
 import torch
 import torch.nn as nn
 
@@ -50,11 +50,9 @@ class Model(nn.Module):
     def num_params(self):
         return sum(p.numel() for p in self.parameters())
 
-    def _prepare(self, device=None):
-        if getattr(self, "_arena_numel", None) is None:
-            # parameter gradients + BatchNorm statistics / reduction scratch + positional-embedding gradients
-            self._arena_numel = int(1.3 * self.num_params()) + (8 << 20)
-        AF.new_step(self._arena_numel if (device is not None and device.type == "cuda") else 0, device, advance_rng=self.training)
+    def _scope(self, device):
+        """opens the forward pass (zero arena, dropout sites, RNG step): avec_b200.functional.forward_scope"""
+        return AF.forward_scope(self, device)
 
     def compute_loss(self, outputs, targets):
         """sum_k w_k * CTC(outputs[k]) with weights mapped to the outputs by position for lists (model.py:217) or by
@@ -80,9 +78,9 @@ class AudioEfficientConformerInterCTC(Model):
         self.encoder = networks.AudioEfficientConformerEncoder(vocab_size=vocab_size, att_type=att_type, interctc_blocks=interctc_blocks)
 
     def forward(self, inputs):
-        self._prepare(inputs[0].device)
         x, lengths = inputs
-        x, lengths, interctc_outputs = self.encoder(x, lengths)
+        with self._scope(x.device):
+            x, lengths, interctc_outputs = self.encoder(x, lengths)
         outputs = {"outputs": [x, lengths]}
         outputs.update(interctc_outputs)
         return outputs
@@ -94,12 +92,26 @@ class VisualEfficientConformerInterCTC(Model):
     def __init__(self, vocab_size=256, interctc_blocks=[3, 6, 9], test_augments=None):
         super().__init__(name="Visual Efficient Conformer Inter CTC")
         self.encoder = networks.VisualEfficientConformerEncoder(vocab_size=vocab_size, interctc_blocks=interctc_blocks)
-        assert test_augments is None, "flip TTA is an evaluation-time feature outside the hot path"
+        self.test_augments = test_augments if isinstance(test_augments, list) else [test_augments] if test_augments is not None else None
 
     def forward(self, inputs):
-        self._prepare(inputs[0].device)
+        """Evaluation with test-time augmentation (models_zoo.py:113-122; the VO config passes RandomHorizontalFlip(p=1)): the
+        reference runs the encoder once per augment; here the clean clip and its augmented copies go through ONE encoder pass as a
+        batch of (1 + A) * B clips (BatchNorm uses running statistics in eval(), so batching is exact) and the logits are
+        re-stacked to the reference's (B, 1 + A, T, V) / (B, 1 + A)."""
         video, video_lengths = inputs
-        x, lengths, interctc_outputs = self.encoder(video, video_lengths)
+        assert not (self.training and self.test_augments is not None), "Training requires setting test_time_aug to False / test_augments to None"
+        with self._scope(video.device):
+            if not self.training and self.test_augments is not None:
+                v = video.permute(0, 4, 1, 2, 3) if video.shape[-1] == 1 else video          # (B, 1, T, H, W) as the reference passes it
+                clips = [v] + [aug(v) for aug in self.test_augments]
+                n, B = len(clips), v.shape[0]
+                x, lengths, interctc_outputs = self.encoder(torch.cat(clips, dim=0).contiguous(), video_lengths.repeat(n))
+                x = x.view(n, B, *x.shape[1:]).transpose(0, 1).contiguous()
+                lengths = lengths.view(n, B).t().contiguous()
+                interctc_outputs = {k: [val[0][:B], val[1][:B]] for k, val in interctc_outputs.items()}   # the clean clip's heads
+            else:
+                x, lengths, interctc_outputs = self.encoder(video, video_lengths)
         outputs = {"outputs": [x, lengths]}
         outputs.update(interctc_outputs)
         return outputs
@@ -115,9 +127,9 @@ class AudioVisualEfficientConformerInterCTC(Model):
             f_interctc_blocks=f_interctc_blocks)
 
     def forward(self, inputs):
-        self._prepare(inputs[0].device)
         video, video_len, audio, audio_len = inputs
-        x, lengths, interctc_outputs = self.encoder(video, video_len, audio, audio_len)
+        with self._scope(video.device):
+            x, lengths, interctc_outputs = self.encoder(video, video_len, audio, audio_len)
         outputs = {"outputs": [x, lengths]}
         outputs.update(interctc_outputs)
         return outputs

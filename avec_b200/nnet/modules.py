@@ -8,6 +8,7 @@ from .. import functional as AF
 from .layers import Linear, Conv1d, Placeholder, Dropout, Swish
 
 _pe_cache = {}
+PE_MAX_LEN = 10000      # num_pos_embeddings / max_pos_encoding of every AVEC attention (networks.py:329)
 
 
 def _drop_p(m, training):
@@ -15,46 +16,43 @@ def _drop_p(m, training):
     return float(m.p) if (training and isinstance(m, nn.Dropout)) else 0.0
 
 
-def _publish(t):
-    """a cached table is built once on whichever stream asked first and then read from every stream (the audio and video
-    encoders of the AV model run on two streams and share (T, D) keys): make it globally visible before it is cached"""
-    if t.is_cuda and not torch.cuda.is_current_stream_capturing():
-        torch.cuda.current_stream(t.device).synchronize()
+def _pe_table(D, device, dtype, max_len=PE_MAX_LEN):
+    """ONE sinusoid table per (D, device, dtype), as the reference keeps one buffer per module (embeddings.py:117-130):
+    row r holds relative position max_len-1-r (even channels sin, odd cos), r = 0 .. 2*max_len-2.  Every length slices it, so
+    device memory does not grow with the number of distinct sequence lengths seen in training.  Rows are pitched for TMA
+    (ops.row_pitch).  The table is built on whichever stream asks first and then read from every stream (the audio and
+    video encoders of the AV model run on two streams), hence the one-time synchronisation."""
+    key = (D, str(device), dtype, max_len)
+    t = _pe_cache.get(key)
+    if t is None:
+        pos = torch.arange(max_len - 1, -max_len, -1, dtype=torch.float).unsqueeze(1)
+        angles = pos / 10000 ** (2 * torch.arange(0, D // 2, dtype=torch.float).unsqueeze(0) / D)
+        pe = torch.zeros(2 * max_len - 1, D)
+        pe[:, 0::2] = angles.sin()
+        pe[:, 1::2] = angles.cos()
+        from .. import ops
+        t = ops.empty_rows(2 * max_len - 1, D, dtype, device)
+        t.copy_(pe.to(device=device, dtype=dtype))
+        if t.is_cuda and not torch.cuda.is_current_stream_capturing():
+            torch.cuda.current_stream(t.device).synchronize()
+        _pe_cache[key] = t
     return t
 
 
 def rel_pos_table(T, D, device, dtype):
-    """rows r = 0..2T-2 hold the sinusoid of relative position T-1-r (even channels sin, odd cos); the slice
-    pos_encoding[max_len-T : max_len-1+T] of RelativeSinusoidalPositionalEncoding (embeddings.py:117-152)."""
-    key = (T, D, str(device), dtype)
-    t = _pe_cache.get(key)
-    if t is None:
-        pos = torch.arange(T - 1, -T, -1, dtype=torch.float).unsqueeze(1)
-        angles = pos / 10000 ** (2 * torch.arange(0, D // 2, dtype=torch.float).unsqueeze(0) / D)
-        pe = torch.zeros(2 * T - 1, D)
-        pe[:, 0::2] = angles.sin()
-        pe[:, 1::2] = angles.cos()
-        t = _publish(pe.to(device=device, dtype=dtype).contiguous())
-        _pe_cache[key] = t
-    return t
+    """rows r = 0..2T-2 hold the sinusoid of relative position T-1-r; the slice pos_encoding[max_len-T : max_len-1+T] of
+    RelativeSinusoidalPositionalEncoding (embeddings.py:117-152)."""
+    assert T <= PE_MAX_LEN
+    return _pe_table(D, device, dtype)[PE_MAX_LEN - T: PE_MAX_LEN - 1 + T]
 
 
 def grouped_rel_pos_table(Tp, D, G, device, dtype):
     """GroupedRelativeSinusoidalPositionalEncoding slice for a (padded) length Tp = multiple of G, odd G
     (embeddings.py:160-216): 2*Tp - G rows, relative positions Tp-1-G//2 ... -(Tp-1-G//2)."""
     assert G % 2 == 1, "even group sizes use a different table layout in the reference and are not used by AVEC"
-    key = ("g", Tp, D, G, str(device), dtype)
-    t = _pe_cache.get(key)
-    if t is None:
-        half = Tp - 1 - G // 2
-        pos = torch.arange(half, -half - 1, -1, dtype=torch.float).unsqueeze(1)
-        angles = pos / 10000 ** (2 * torch.arange(0, D // 2, dtype=torch.float).unsqueeze(0) / D)
-        pe = torch.zeros(2 * Tp - G, D)
-        pe[:, 0::2] = angles.sin()
-        pe[:, 1::2] = angles.cos()
-        t = _publish(pe.to(device=device, dtype=dtype).contiguous())
-        _pe_cache[key] = t
-    return t
+    half = Tp - 1 - G // 2
+    assert half < PE_MAX_LEN
+    return _pe_table(D, device, dtype)[PE_MAX_LEN - 1 - half: PE_MAX_LEN + half]
 
 
 class FeedForwardModule(nn.Module):
@@ -96,6 +94,14 @@ class RelPos1dMultiHeadAttention(nn.Module):
         self.output_layer = Linear(dim_model, dim_model)
         self.pos_layer = Linear(dim_model, dim_model)
 
+    def forwardQKV(self, Q, K, V, mask=None):
+        """the reference's plug-in entry point (attentions.py:280-323 / 348-382, called at modules.py:330): self-attention only
+        (Q is K is V, as AttentionModule calls it); returns (output, None) - the attention map is never materialised."""
+        return _forward_qkv(self, Q, K, V, mask)
+
+    def forward(self, x, mask=None):
+        return self.forwardQKV(x, x, x, mask)
+
 
 class RelPosPatch1dMultiHeadAttention(RelPos1dMultiHeadAttention):
     def __init__(self, dim_model, num_heads, patch_size, num_pos_embeddings=10000, attn_drop_rate=0.0,
@@ -121,6 +127,39 @@ class GroupedRelPosMultiHeadSelfAttention(nn.Module):
         self.value_layer = Linear(dim_model, dim_model, bias_init=bias_init)
         self.output_layer = Linear(dim_model, dim_model, bias_init=bias_init)
         self.pos_layer = Linear(dim_model, dim_model)
+
+    def forwardQKV(self, Q, K, V, mask=None):
+        """attentions.py:579-650; self-attention only, returns (output, None)"""
+        return _forward_qkv(self, Q, K, V, mask)
+
+    def forward(self, x, mask=None):
+        return self.forwardQKV(x, x, x, mask)
+
+
+def _attention_args(a):
+    return (a.query_layer.weight, a.query_layer.bias, a.key_layer.weight, a.key_layer.bias, a.value_layer.weight, a.value_layer.bias,
+            a.output_layer.weight, a.output_layer.bias, a.pos_layer.weight, a.pos_layer.bias)
+
+
+def _forward_qkv(a, Q, K, V, mask):
+    """attention WITHOUT the module's LayerNorm / residual / dropout (the AttentionModule wraps those, modules.py:320-339):
+    the fused Function is called with identity LayerNorm parameters switched off and the residual subtracted afterwards is
+    avoided by the `plain` flag."""
+    if not (Q is K and K is V):
+        raise NotImplementedError("avec_b200: forwardQKV implements self-attention (Q is K is V), the only use in AVEC (modules.py:330)")
+    from .blocks import mask_to_klen
+    x = Q
+    B, T, D = x.shape
+    klen = mask_to_klen(mask).to(x.device) if mask is not None else None
+    if isinstance(a, GroupedRelPosMultiHeadSelfAttention):
+        G = a.group_size
+        pe = grouped_rel_pos_table(-(-T // G) * G, D, G, x.device, x.dtype)
+        y = AF.GroupedAttentionFn.apply(x, None, None, *_attention_args(a), a.u, a.v, pe, klen, a.num_heads, G, 0.0)
+    else:
+        P = a.patch_size
+        pe = rel_pos_table(-(-T // P), D, x.device, x.dtype)
+        y = AF.AttentionFn.apply(x, None, None, *_attention_args(a), pe, klen, a.num_heads, P, 0.0)
+    return y, None
 
 
 att_dict = {
@@ -149,18 +188,20 @@ class AttentionModule(nn.Module):
             Tp = -(-T // G) * G
             pe = grouped_rel_pos_table(Tp, D, G, x.device, x.dtype)
             return AF.GroupedAttentionFn.apply(
-                x, self.norm.weight, self.norm.bias,
-                a.query_layer.weight, a.query_layer.bias, a.key_layer.weight, a.key_layer.bias,
-                a.value_layer.weight, a.value_layer.bias, a.output_layer.weight, a.output_layer.bias,
-                a.pos_layer.weight, a.pos_layer.bias, a.u, a.v, pe, klen, a.num_heads, G, _drop_p(self.dropout, self.training))
+                x, self.norm.weight, self.norm.bias, *_attention_args(a), a.u, a.v, pe, klen, a.num_heads, G,
+                _drop_p(self.dropout, self.training))
         P = a.patch_size
         Tp = -(-T // P)
         pe = rel_pos_table(Tp, D, x.device, x.dtype)
         return AF.AttentionFn.apply(
-            x, self.norm.weight, self.norm.bias,
-            a.query_layer.weight, a.query_layer.bias, a.key_layer.weight, a.key_layer.bias,
-            a.value_layer.weight, a.value_layer.bias, a.output_layer.weight, a.output_layer.bias,
-            a.pos_layer.weight, a.pos_layer.bias, pe, klen, a.num_heads, P, _drop_p(self.dropout, self.training))
+            x, self.norm.weight, self.norm.bias, *_attention_args(a), pe, klen, a.num_heads, P, _drop_p(self.dropout, self.training))
+
+    def forward(self, x, mask=None, hidden=None):
+        """the reference's module call (modules.py:320-339): returns (x, attention map placeholder, hidden placeholder);
+        with residual=False the caller adds the residual (blocks.py:295), so it is removed again here."""
+        from .blocks import mask_to_klen
+        y = self.forward_residual(x, mask_to_klen(mask).to(x.device) if mask is not None else None)
+        return (y if self.residual else y - x), None, None
 
 
 class ConvolutionModule(nn.Module):

@@ -128,6 +128,10 @@ class AudioEfficientConformerEncoder(nn.Module):
         )
 
     def forward(self, x, lengths):
+        with AF.forward_scope(self, x.device):
+            return self._forward(x, lengths)
+
+    def _forward(self, x, lengths):
         conv, bn = self.subsampling_module.layers[0][0], self.subsampling_module.layers[0][1]
         if self.training:
             bn.num_batches_tracked.add_(1)
@@ -198,6 +202,10 @@ class VisualEfficientConformerEncoder(nn.Module):
 
     def forward(self, x, lengths):
         """x: (B,1,T,H,W) as the reference passes it (models_zoo.py:109) or (B,T,H,W,1) - identical memory for C = 1."""
+        with AF.forward_scope(self, x.device):
+            return self._forward(x, lengths)
+
+    def _forward(self, x, lengths):
         if x.dim() == 5 and x.shape[1] == 1 and x.shape[-1] != 1:
             x = x.permute(0, 2, 3, 4, 1)
         B, T = x.shape[0], x.shape[1]
@@ -245,6 +253,10 @@ class AudioVisualEfficientConformerEncoder(nn.Module):
         return s
 
     def forward(self, video, video_len, audio, audio_len):
+        with AF.forward_scope(self, video.device):
+            return self._forward(video, video_len, audio, audio_len)
+
+    def _forward(self, video, video_len, audio, audio_len):
         if self.overlap_branches and video.is_cuda:
             cur = torch.cuda.current_stream(video.device)
             side = self._side_stream(video.device)

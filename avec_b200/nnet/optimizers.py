@@ -17,7 +17,7 @@ class Adam(torch.optim.Optimizer):
     def __init__(self, params, lr=0.001, betas=(0.9, 0.999), eps=1e-08, weight_decay=0, amsgrad=False, grad_max_norm=None,
                  ema_tau=None):
         assert not amsgrad, "amsgrad is not used by the reference configs"
-        self.scheduler = lr if isinstance(lr, schedulers.Scheduler) else schedulers.ConstantScheduler(val=lr)
+        self.scheduler = schedulers.adopt(lr)
         super().__init__(params, dict(lr=0.0, betas=betas, eps=eps, weight_decay=weight_decay))
         assert len(self.param_groups) == 1, "one parameter group (the reference passes model.parameters())"
         self.grad_max_norm, self.ema_tau = grad_max_norm, ema_tau
@@ -71,17 +71,26 @@ class Adam(torch.optim.Optimizer):
     # ---- step ---------------------------------------------------------------------------------------------------
     @torch.no_grad()
     def step(self, closure=None, grads=None):
-        """grads: optional list (one per parameter) used instead of p.grad, e.g. the static outputs of a captured backward"""
+        """grads: optional list (one per parameter) used instead of p.grad, e.g. the static outputs of a captured backward.
+        Parameters without a gradient are skipped entirely (no weight decay, no moment update), as torch.optim.Adam does:
+        the fused kernel is then launched once per contiguous run of parameters that do have one."""
         assert closure is None
+        from .. import functional as AF
         f = self.flat()
         if grads is not None and len(grads) != len(f["params"]):
             raise ValueError(f"grads has {len(grads)} entries for {len(f['params'])} trainable parameters")
-        src, dst = [], []
-        for i, (p, gv) in enumerate(zip(f["params"], f["gviews"])):
+        src, dst, runs = [], [], []
+        for i, (p, gv, o) in enumerate(zip(f["params"], f["gviews"], f["offs"])):
             g = grads[i] if grads is not None else p.grad
             if g is None:
-                gv.zero_()
-            elif g.data_ptr() != gv.data_ptr():
+                gv.zero_()                      # keeps the global norm exact; the range itself is not stepped
+                continue
+            end = o + (p.numel() + 3) // 4 * 4
+            if runs and runs[-1][1] == o:
+                runs[-1][1] = end
+            else:
+                runs.append([o, end])
+            if g.data_ptr() != gv.data_ptr():
                 src.append(g)
                 dst.append(gv)
         if src:
@@ -95,10 +104,12 @@ class Adam(torch.optim.Optimizer):
         L.check(L.load().avec_counter_advance(f["step"].data_ptr(), ops._stream()), "avec_counter_advance")
         self.scheduler.model_step += 1
         lr_a, lr_b = self.scheduler.device_params()
-        ops.adam_step(f["p"], f["g"], f["m"], f["v"], f["step"], self.scheduler.lr_mode, lr_a, lr_b, grp["betas"], grp["eps"],
-                      grp["weight_decay"], sumsq, float(self.grad_max_norm or 0.0), f["ema"],
-                      float(self.ema_tau or 0.0), f["info"])
+        for lo, hi in runs:
+            ops.adam_step(f["p"][lo:hi], f["g"][lo:hi], f["m"][lo:hi], f["v"][lo:hi], f["step"], self.scheduler.lr_mode, lr_a, lr_b,
+                          grp["betas"], grp["eps"], grp["weight_decay"], sumsq, float(self.grad_max_norm or 0.0),
+                          f["ema"][lo:hi] if f["ema"] is not None else None, float(self.ema_tau or 0.0), f["info"])
         grp["lr"] = self.scheduler.get_val()
+        AF.invalidate_weights()     # the parameters changed behind torch's version counters: drop the cached bf16 copies
         return None
 
     def last_info(self):
@@ -106,14 +117,28 @@ class Adam(torch.optim.Optimizer):
         lr, gn = self.flat()["info"].tolist()
         return {"lr": lr, "grad_norm": gn}
 
+    def sync_host_step(self):
+        """the step counter lives on the device (a captured CUDA graph advances it without running this Python code): copy it
+        back into the host-side scheduler / param_groups (one sync; call before logging or checkpointing)"""
+        step = int(self.flat()["step"].item())
+        self.scheduler.model_step.fill_(step)
+        self.param_groups[0]["lr"] = self.scheduler.get_val() if step > 0 else 0.0
+        return step
+
     # ---- checkpoints: torch.optim.Adam layout + "model_step" (optimizers.py:75-91) ---------------------------------
     def state_dict(self):
-        self.flat()
+        """torch.optim.Adam's layout: every parameter gets its OWN float32 scalar `step` (torch increments it in place per
+        parameter; a shared tensor would be bumped once per parameter after a reload into the reference's Adam) and cloned
+        moments; `model_step` is read from the device counter, so it is right even when the step ran inside a CUDA graph."""
+        step = self.sync_host_step()
         sd = super().state_dict()
-        sd["model_step"] = self.scheduler.model_step
+        sd["state"] = {k: {"step": torch.tensor(float(step), dtype=torch.float32), "exp_avg": st["exp_avg"].detach().clone(),
+                           "exp_avg_sq": st["exp_avg_sq"].detach().clone()} for k, st in sd["state"].items()}
+        sd["model_step"] = self.scheduler.model_step.clone()
         return sd
 
     def load_state_dict(self, state_dict):
+        from .. import functional as AF
         state_dict = dict(state_dict)
         step = int(state_dict.pop("model_step"))
         self.scheduler.model_step.fill_(step)
@@ -129,3 +154,4 @@ class Adam(torch.optim.Optimizer):
                     v.copy_(st["exp_avg_sq"])
                 self.state[p] = {"step": f["step"], "exp_avg": m, "exp_avg_sq": v}
             f["step"].fill_(step)
+        AF.invalidate_weights()

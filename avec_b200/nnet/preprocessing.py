@@ -40,7 +40,7 @@ class SpecAugment(nn.Module):
         return (self.mF, self.F, self.mT, self.pS)
 
     def forward(self, samples, lengths):
-        if not self.training:
+        if not (self.training and self.enabled):
             return samples
         mel = samples.float().transpose(1, 2).contiguous()                     # [B, T, n_mels] frame-major
         ln = lengths.to(device=mel.device, dtype=torch.long) if lengths is not None else None

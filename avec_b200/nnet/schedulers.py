@@ -53,3 +53,22 @@ class NoamDecayScheduler(Scheduler):
 
     def device_params(self):
         return float(self.val_factor * self.dim_decay ** -0.5), float(self.warmup_steps)
+
+
+def adopt(lr):
+    """Scheduler of this package for `lr`: a float, one of our schedulers, or the reference's own scheduler object (duck-typed by
+    class name: after avec_b200.patch_reference() the zoo models hand the reference's NoamDecayScheduler to the fused Adam,
+    models_zoo.py:172-174).  The host-side `model_step` tensor is shared with the adopted object."""
+    if isinstance(lr, Scheduler):
+        return lr
+    if hasattr(lr, "model_step") and hasattr(lr, "get_val_step"):
+        name = lr.__class__.__name__
+        if name == "NoamDecayScheduler":
+            s = NoamDecayScheduler(lr.warmup_steps, lr.dim_decay, lr.val_factor)
+        elif name == "ConstantScheduler":
+            s = ConstantScheduler(lr.val)
+        else:
+            raise NotImplementedError(f"avec_b200 fused Adam: learning-rate schedule {name} is not implemented on the device")
+        s.model_step = lr.model_step
+        return s
+    return ConstantScheduler(val=lr)

@@ -235,6 +235,9 @@ def layernorm_fwd(x, gamma, beta, P=1, eps=1e-6):
     B, T, Cn = x.shape
     Tp = -(-T // P)
     y = torch.empty((B, Tp, Cn), device=x.device, dtype=x.dtype)
+    if gamma is None:   # identity mode: plain mean over the P frames of a patch (attention.forwardQKV without the module's norm)
+        L.check(L.load().avec_layernorm_fwd(x.data_ptr(), 0, 0, y.data_ptr(), 0, 0, B, T, Cn, P, eps, _dt(x), _stream()), "avec_layernorm_fwd")
+        return y, None, None
     mean = torch.empty((B * T,), device=x.device, dtype=torch.float32)
     rstd = torch.empty_like(mean)
     L.check(L.load().avec_layernorm_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), mean.data_ptr(),
@@ -246,6 +249,10 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, P=1, dres=None, res_stride=1):
     """returns dx [B,T,C], dgamma, dbeta (fp32).  dx += dres[b, t/res_stride] on frames t % res_stride == 0."""
     B, T, Cn = x.shape
     dx = torch.empty_like(x)
+    if gamma is None:
+        L.check(L.load().avec_layernorm_bwd(dy.data_ptr(), x.data_ptr(), 0, 0, 0, _p(dres), res_stride, dx.data_ptr(), 0, 0, B, T, Cn, P,
+                                            _dt(x), _stream()), "avec_layernorm_bwd")
+        return dx, None, None
     dg = zeros_f32((Cn,), x.device)
     db = zeros_f32((Cn,), x.device)
     L.check(L.load().avec_layernorm_bwd(dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
@@ -551,46 +558,97 @@ def ctc_loss(logits, labels, in_len, lab_len, blank=0, zero_infinity=False):
     return nll, grad
 
 
-def convert(src, dtype):
-    """dtype cast through the library's own kernel (2-d, possibly strided rows)."""
-    if src.dtype == dtype and src.is_contiguous():
+def row_pitch(C, dtype):
+    """leading dimension (elements) of a [rows, C] activation / weight matrix: rows start on 16-byte boundaries so that
+    every operand qualifies for a TMA descriptor (D = 180 bf16 rows are 360 B: pitch 184 -> 192 keeps them on 128-byte lines)"""
+    if dtype == torch.bfloat16 and C % 8 != 0:
+        return (C + 63) // 64 * 64
+    return C
+
+
+def empty_rows(rows, C, dtype, device):
+    """[rows, C] view of a [rows, row_pitch(C)] allocation (contiguous when the pitch equals C)"""
+    ld = row_pitch(C, dtype)
+    if ld == C:
+        return torch.empty((rows, C), device=device, dtype=dtype)
+    return torch.empty((rows, ld), device=device, dtype=dtype)[:, :C]
+
+
+def convert(src, dtype, pad=False):
+    """dtype cast through the library's own kernel (2-d, possibly strided rows).  pad: the destination rows get the TMA-able
+    pitch of row_pitch() (a [rows, C] view of a wider allocation)."""
+    if src.dtype == dtype and src.is_contiguous() and not (pad and src.dim() == 2 and row_pitch(src.shape[1], dtype) != src.shape[1]):
         return src
     s2 = src.reshape(-1, src.shape[-1]) if src.dim() != 2 else src
     if s2.stride(-1) != 1:
         s2 = s2.contiguous()
-    dst = torch.empty(s2.shape, device=src.device, dtype=dtype)
+    if pad and src.dim() == 2:
+        dst = empty_rows(s2.shape[0], s2.shape[1], dtype, src.device)
+    else:
+        dst = torch.empty(s2.shape, device=src.device, dtype=dtype)
     L.check(L.load().avec_convert(s2.data_ptr(), _dt(s2), s2.stride(0), dst.data_ptr(), _dt(dst), dst.stride(0), s2.shape[0],
                                   s2.shape[1], _stream()), "avec_convert")
-    return dst.reshape(src.shape)
+    return dst if (pad and src.dim() == 2) else dst.reshape(src.shape)
 
 
 # ------------------------------------------------------------------------------------- training-step kernels (train.cu)
 class _Rng:
     """{seed, step} as two uint64 in device memory per GPU, plus the per-forward dropout site counter.  The step is advanced
     by a kernel (capturable: every CUDA-graph replay draws fresh masks); sites are handed out in call order and are
-    therefore identical in the forward and its backward."""
+    therefore identical in the forward and its backward.  Every forward pass works on a SNAPSHOT of {seed, step} taken when
+    the pass starts (functional.new_step), which its autograd Functions keep: 'forward A, forward B, backward A' regenerates
+    A's masks.  Under torch.distributed the rank is folded into the seed so that replicas draw different masks."""
+
+    GOLDEN = 0x9E3779B97F4A7C15
 
     def __init__(self):
-        self.state, self.seed, self.site = {}, 0x5EEDA7EC, 0
+        self.state, self.snap, self.seed, self.site = {}, {}, 0x5EEDA7EC, 0
+
+    def _rank_seed(self):
+        rank = 0
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                rank = dist.get_rank()
+        except Exception:  # noqa: BLE001
+            rank = 0
+        return (self.seed + rank * self.GOLDEN) & 0x7FFFFFFFFFFFFFFF
 
     def manual_seed(self, seed):
         self.seed = int(seed) & 0x7FFFFFFFFFFFFFFF
         for st in self.state.values():
-            st.copy_(torch.tensor([self.seed, 0], dtype=torch.int64))
+            st.copy_(torch.tensor([self._rank_seed(), 0], dtype=torch.int64))
+        self.snap.clear()
 
-    def get(self, device):
+    @staticmethod
+    def _dev(device):
         device = torch.device(device)
         if device.type == "cuda" and device.index is None:
             device = torch.device("cuda", torch.cuda.current_device())
+        return device
+
+    def get(self, device):
+        device = self._dev(device)
         st = self.state.get(device)
         if st is None:
-            st = torch.tensor([self.seed, 0], dtype=torch.int64).to(device)
+            st = torch.tensor([self._rank_seed(), 0], dtype=torch.int64).to(device)
             self.state[device] = st
         return st
 
     def advance(self, device):
         st = self.get(device)
         L.check(L.load().avec_counter_advance(st.data_ptr() + 8, _stream()), "avec_counter_advance")
+
+    def snapshot(self, device):
+        """copy of the live {seed, step} for the forward pass that starts now (one 16-byte device copy, capturable)"""
+        device = self._dev(device)
+        self.snap[device] = self.get(device).clone()
+        return self.snap[device]
+
+    def cur(self, device):
+        device = self._dev(device)
+        s = self.snap.get(device)
+        return s if s is not None else self.get(device)
 
     def next_site(self):
         self.site += 1
@@ -601,9 +659,16 @@ RNG = _Rng()
 
 
 def dropout(x, p, site, res=None, alpha=1.0, out=None, up=None):
-    """out = (res or 0) + alpha * keep * x / (1 - p) with the Philox mask of (seed, step, site); the backward calls it again
-    on the gradient with the same site.  up = (T, Tp, P): x is [B*Tp, C] patch rows repeated over the T frames of out / res."""
+    """dropout_rng on the live generator state (tests / direct calls)"""
+    return dropout_rng(RNG.get(x.device), x, p, site, res, alpha, out, up)
+
+
+def dropout_rng(rng, x, p, site, res=None, alpha=1.0, out=None, up=None):
+    """out = (res or 0) + alpha * keep * x / (1 - p) with the Philox mask of (rng = {seed, step} device tensor, site); the
+    backward calls it again on the gradient with the same rng / site.  up = (T, Tp, P): x is [B*Tp, C] patch rows repeated over
+    the T frames of out / res.  rng None: the current forward pass's snapshot."""
     _cuda(x, res)
+    rng = RNG.cur(x.device) if rng is None else rng
     C = x.shape[-1]
     if up is None:
         rows, T, Tp, P = x.numel() // C, 0, 0, 1
@@ -614,18 +679,19 @@ def dropout(x, p, site, res=None, alpha=1.0, out=None, up=None):
         out = torch.empty((rows, C), device=x.device, dtype=x.dtype) if out is None else out
     assert x.is_contiguous() and out.is_contiguous() and (res is None or (res.is_contiguous() and res.dtype == x.dtype))
     L.check(L.load().avec_dropout(x.data_ptr(), _p(res), out.data_ptr(), rows, C, _dt(x), float(p), float(alpha),
-                                  RNG.get(x.device).data_ptr(), int(site), T, Tp, P, _stream()), "avec_dropout")
+                                  rng.data_ptr(), int(site), T, Tp, P, _stream()), "avec_dropout")
     return out
 
 
-def spec_augment_(mel, lengths, site, mF=2, Fmax=27, mT=5, pS=0.05, want_intervals=False):
+def spec_augment_(mel, lengths, site, mF=2, Fmax=27, mT=5, pS=0.05, want_intervals=False, rng=None):
     """in-place SpecAugment of mel [B, F, M] fp32 (frame-major); lengths [B] int64 device tensor of valid frames or None"""
     _cuda(mel, lengths)
     assert mel.dtype == torch.float32 and mel.is_contiguous()
     B, F, M = mel.shape
     iv = torch.empty((B, mF + mT, 2), device=mel.device, dtype=torch.int32) if want_intervals else None
     L.check(L.load().avec_spec_augment(mel.data_ptr(), _p(lengths), B, F, M, mF, Fmax, mT, float(pS),
-                                       RNG.get(mel.device).data_ptr(), int(site), _p(iv), _stream()), "avec_spec_augment")
+                                       (rng if rng is not None else RNG.cur(mel.device)).data_ptr(), int(site), _p(iv), _stream()),
+            "avec_spec_augment")
     return iv
 
 

@@ -19,7 +19,14 @@ def allreduce_gradients(params, world_size=None, bucket_bytes=256 << 20, grads=N
     otherwise).  `grads` (optional) are the tensors to reduce when they are not `p.grad` itself, e.g. the static gradient
     tensors a captured CUDA graph writes on every replay."""
     world_size = world_size or dist.get_world_size()
-    pairs = [(p, p.grad if grads is None else g) for p, g in zip(params, grads if grads is not None else params)]
+    params = list(params)          # `params` may be a generator (model.parameters()): walk it exactly once
+    if grads is None:
+        pairs = [(p, p.grad) for p in params]
+    else:
+        grads = list(grads)
+        if len(grads) != len(params):
+            raise ValueError(f"allreduce_gradients: {len(grads)} gradients for {len(params)} parameters")
+        pairs = list(zip(params, grads))
     pairs = [(p, g) for p, g in pairs if g is not None]
     avg = dist.get_backend() == "nccl"
     bucket, size = [], 0

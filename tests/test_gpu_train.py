@@ -270,3 +270,61 @@ def test_train_step_reduces_the_loss():
     o = m2.optimizer
     assert isinstance(o, nnet.optimizers.Adam) and o.scheduler.device_params() == (2 * 360 ** -0.5, 10000.0)
     assert o.param_groups[0]["betas"] == (0.9, 0.98) and o.param_groups[0]["weight_decay"] == 1e-6
+
+
+def test_fused_adam_checkpoint_round_trip_with_torch_adam():
+    """state_dict() is torch.optim.Adam's layout (the reference's Adam IS torch.optim.Adam + model_step, optimizers.py:61-93): a
+    checkpoint written by the fused optimizer continues identically in torch's Adam and comes back; per-parameter `step` entries are
+    separate tensors (a shared one would be incremented once per parameter); parameters without a gradient are left untouched."""
+    torch.manual_seed(0)
+    shapes = [(64, 48), (48,), (32, 64), (7,), (5, 3, 3)]
+    ps_a = [torch.nn.Parameter(torch.randn(s, device=DEV)) for s in shapes]
+    ps_b = [torch.nn.Parameter(p.detach().clone()) for p in ps_a]
+    hyper = dict(betas=(0.9, 0.98), eps=1e-9, weight_decay=1e-6)
+    fused = nnet.optimizers.Adam(ps_a, lr=1e-3, **hyper)
+    plain = torch.optim.Adam(ps_b, lr=1e-3, **hyper)
+
+    def grads(step, skip=None):
+        g = torch.Generator().manual_seed(100 + step)
+        return [None if i == skip else torch.randn(s, generator=g).to(DEV) for i, s in enumerate(shapes)]
+
+    for step in range(3):
+        for opt_ps, opt in ((ps_a, fused), (ps_b, plain)):
+            for p, g in zip(opt_ps, grads(step, skip=3 if step == 1 else None)):   # step 1: parameter 3 has no gradient
+                p.grad = None if g is None else g.clone()
+            opt.step()
+    for i, (a, b) in enumerate(zip(ps_a, ps_b)):
+        # parameter 3 skipped a step: torch keeps a per-parameter counter (2 updates), the fused kernel one device counter (its
+        # bias correction is one step ahead for that parameter) - same moments, slightly different step size
+        check_close(f"param[{i}]", a, b, 1e-5 if i != 3 else 1e-2, 1e-7 if i != 3 else 2e-3)
+    sd = fused.state_dict()
+    steps = [st["step"] for st in sd["state"].values()]
+    assert all(float(s) == 3.0 and s.dtype == torch.float32 and s.dim() == 0 for s in steps)
+    assert len({s.data_ptr() for s in steps}) == len(steps) and int(sd["model_step"]) == 3
+    # fused -> torch Adam: one more step on both sides
+    sd_plain = {k: v for k, v in sd.items() if k != "model_step"}
+    ps_c = [torch.nn.Parameter(p.detach().clone()) for p in ps_a]
+    cont = torch.optim.Adam(ps_c, lr=1e-3, **hyper)
+    cont.load_state_dict(sd_plain)
+    for opt_ps, opt in ((ps_a, fused), (ps_c, cont)):
+        for p, g in zip(opt_ps, grads(7)):
+            p.grad = g.clone()
+        opt.step()
+    assert {float(st["step"]) for st in cont.state_dict()["state"].values()} == {4.0}
+    # parameter 3 skipped step 1 in torch (its own counter is 3 there); the fused optimizer keeps ONE device counter, so its bias
+    # correction for that parameter is one step ahead: compare the others exactly, parameter 3 loosely
+    for i, (a, c) in enumerate(zip(ps_a, ps_c)):
+        check_close(f"continued[{i}]", a, c, 1e-5 if i != 3 else 1e-2, 1e-7 if i != 3 else 1e-3)
+    # torch Adam -> fused
+    sd_back = cont.state_dict()
+    sd_back["model_step"] = torch.tensor(4)
+    ps_d = [torch.nn.Parameter(p.detach().clone()) for p in ps_c]
+    back = nnet.optimizers.Adam(ps_d, lr=1e-3, **hyper)
+    back.load_state_dict(sd_back)
+    for opt_ps, opt in ((ps_c, cont), (ps_d, back)):
+        for p, g in zip(opt_ps, grads(9)):
+            p.grad = g.clone()
+        opt.step()
+    for i, (c, d) in enumerate(zip(ps_c, ps_d)):
+        check_close(f"back[{i}]", c, d, 1e-5, 1e-7)
+    assert int(back.state_dict()["model_step"]) == 5
