@@ -111,8 +111,10 @@ def _wvalid(hit, ver):
     return hit is not None and hit[0] == ver and hit[2] == _wepoch
 
 
-def wc(param, tag="plain", fn=None):
-    """compute-dtype copy of a parameter in the layout a kernel wants (fn: fp32 tensor -> 2-d fp32 view/tensor)."""
+def wc(param, tag="plain", fn=None, pad=True):
+    """compute-dtype copy of a parameter in the layout a kernel wants (fn: fp32 tensor -> 2-d fp32 view/tensor).  pad: GEMM
+    operands get the TMA-able row pitch of ops.row_pitch (a [N, K] view of a wider allocation); kernels that index the weight
+    as a dense array pass pad=False."""
     dt = compute_dtype()
     key = (id(param), tag, dt)
     hit = _wcache.get(key)
@@ -121,7 +123,7 @@ def wc(param, tag="plain", fn=None):
         return hit[1]
     src = param.detach()
     src = fn(src) if fn is not None else src.reshape(src.shape[0], -1)
-    out = ops.convert(src, dt, pad=True)
+    out = ops.convert(src, dt, pad=pad)
     _wcache[key] = (ver, out, _wepoch)
     return out
 
@@ -523,7 +525,7 @@ class AudioStemFn(Function):
         melc = ops.convert(mel, compute_dtype())
         Co = cw.shape[0]
         g = ops.make_geom(B, 1, F, 80, 1, Co, (1, 3, 3), (1, 2, 2), (0, 1, 1))
-        wp = wc(cw, "stem2d", lambda w: w[:, 0].transpose(1, 2).reshape(w.shape[0], 9))
+        wp = wc(cw, "stem2d", lambda w: w[:, 0].transpose(1, 2).reshape(w.shape[0], 9), pad=False)
         sites = ops.geom_sites(g)
         stats = ops.gemm_stats_buffer(Co, wave.device) if training else None
         direct = Co % 4 == 0 and Co <= 256   # SIMT stem kernel (K = 9 is far below a tensor-core tile; output-write bound)

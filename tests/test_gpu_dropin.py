@@ -40,6 +40,11 @@ def _to(dev, xs):
     return [x.to(dev) for x in xs]
 
 
+class _NoAug(torch.nn.Module):
+    def forward(self, x, lengths=None):
+        return x
+
+
 def _zoo_model(ref, seed=3):
     m = ref.AudioVisualEfficientConformerInterCTC(vocab_size=256)
     m.compile(losses=ref.CTCLoss(zero_infinity=True, assert_shorter=False))
@@ -57,7 +62,7 @@ def test_reference_model_runtime_on_patched_encoders(tmp_path):
     plain = _zoo_model(ref)
     sd = {k: v.clone() for k, v in plain.state_dict().items()}
     ref_import.zero_dropout(plain)
-    plain.encoder.audio_encoder.spec_augment = torch.nn.Identity()
+    plain.encoder.audio_encoder.spec_augment = _NoAug()
     plain = plain.to(DEV).train()
     want, _, _, _ = plain.forward_model(_to(DEV, inputs), _to(DEV, targets), compute_metrics=False)
     want = {k: float(v) for k, v in want.items()}
