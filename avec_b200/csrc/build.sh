@@ -9,7 +9,7 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 OUT=${OUT:-../libavec_b200.so}
 OBJ=${OBJ:-build}
 LOG=${LOG:-$OBJ/build.log}
-SRCS="api.cu gemm_simt.cu gemm_tc.cu attention.cu attention_long.cu attention_mma.cu attention_flash.cu norm.cu convmod.cu frontend.cu ctc.cu train.cu"
+SRCS="api.cu gemm_simt.cu gemm_tc.cu attention.cu attention_long.cu attention_mma.cu attention_tc.cu norm.cu convmod.cu frontend.cu ctc.cu train.cu"
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 --use_fast_math -Xcompiler -fPIC -Xptxas -v $*"
 mkdir -p $OBJ
 # a change of flags rebuilds everything

@@ -141,8 +141,37 @@ def wc_cat(params, tag):
     return out
 
 
+def wc_fn(params, tag, fn, convert=True):
+    """cached fn(*params) (an fp32 2-d / 1-d tensor in kernel layout), converted to the compute dtype when `convert`"""
+    dt = compute_dtype() if convert else torch.float32
+    key = (tuple(id(p) for p in params), tag, dt)
+    ver = tuple((p._version, p.data_ptr()) for p in params)
+    hit = _wcache.get(key)
+    if _wvalid(hit, ver):
+        return hit[1]
+    src = fn(*[p.detach() for p in params])
+    out = ops.convert(src, dt, pad=True) if convert else src.contiguous()
+    _wcache[key] = (ver, out, _wepoch)
+    return out
+
+
 def _c(t):
     return t if t.is_contiguous() else t.contiguous()
+
+
+# ---- padded-heads layout of the tcgen05 attention kernel: head h owns columns [h*dp, h*dp + d) of a dp-wide block
+def _pad_rows(w, H, d, dp):
+    """[H*d, ...] -> [H*dp, ...] (zero rows appended to every head)"""
+    rest = w.shape[1:]
+    out = torch.zeros((H, dp) + tuple(rest), device=w.device, dtype=w.dtype)
+    out[:, :d] = w.reshape((H, d) + tuple(rest))
+    return out.reshape((H * dp,) + tuple(rest))
+
+
+def _unpad_rows(w, H, d, dp):
+    """[n*H*dp, ...] -> [n*H*d, ...]"""
+    rest = w.shape[1:]
+    return w.reshape((-1, H, dp) + tuple(rest))[:, :, :d].reshape((-1,) + tuple(rest))
 
 
 # --------------------------------------------------------------------------------------------------------------- FFN
@@ -194,7 +223,11 @@ class FFNFn(Function):
 
 # --------------------------------------------------------------------------------------------------------- attention
 class AttentionFn(Function):
-    """y = x + upsample_P( Wo attn( pool_P(LN(x)) ) + bo )   with relative-position scores (P = 1: regular RelPos1d)."""
+    """y = x + upsample_P( Wo attn( pool_P(LN(x)) ) + bo )   with relative-position scores (P = 1: regular RelPos1d).
+    bf16: the tcgen05 / TMEM / TMA flash kernel (csrc/attention_tc.cu) on the padded-heads layout - the Q/K/V/position
+    projections write each head into its own 64- or 128-column block (zero-padded weight rows), the output projection reads
+    it back through zero-padded weight columns; nothing of size T x T is stored.  fp32 parity mode / AVEC_ATTN_TC=0: the
+    round-1 kernels with saved probabilities."""
 
     @staticmethod
     def forward(ctx, x, ln_w, ln_b, wq, bq, wk, bk, wv, bv, wo, bo, wp, bp, pe, klen, H, P, p_drop=0.0):
@@ -204,37 +237,50 @@ class AttentionFn(Function):
         ctx.rng = ops.RNG.cur(x.device)
         xp, mean, rstd = ops.layernorm_fwd(x, ln_w, ln_b, P=P)
         Tp = xp.shape[1]
-        wqkv = wc_cat((wq, wk, wv), "qkv")
-        bqkv = wc_cat((bq, bk, bv), "bqkv").reshape(-1)
-        qkv = ops.linear_fwd(xp.view(B * Tp, D), wqkv, bqkv)
-        e = ops.linear_fwd(pe, wc(wp), bp)
+        dp = ops.attn_head_pad(d)
+        tc = ops.ATTN_TC and x.dtype == torch.bfloat16 and dp is not None and ops.GEMM_IMPL != L.IMPL_SIMT
         if P > 1:
             klen_p = torch.div(klen, P, rounding_mode="floor").to(torch.int32) if klen is not None else None
             qlen = T // P
         else:
             klen_p, qlen = klen, Tp
-        o, probs = ops.relpos_attn_fwd(qkv, e, klen_p, qlen, B, Tp, H, d)
+        if tc:
+            wqkv = wc_fn((wq, wk, wv), "qkv_tc", lambda a, b, c: torch.cat([_pad_rows(t, H, d, dp) for t in (a, b, c)], dim=0))
+            bqkv = wc_fn((bq, bk, bv), "bqkv_tc", lambda a, b, c: torch.cat([_pad_rows(t, H, d, dp) for t in (a, b, c)], dim=0), convert=False)
+            wpp = wc_fn((wp,), "pos_tc", lambda a: _pad_rows(a, H, d, dp))
+            bpp = wc_fn((bp,), "bpos_tc", lambda a: _pad_rows(a, H, d, dp), convert=False)
+            wop = wc_fn((wo,), "out_tc", lambda a: _pad_rows(a.t(), H, d, dp).t())
+            qkv = ops.linear_fwd(xp.view(B * Tp, D), wqkv, bqkv)
+            e = ops.linear_fwd(pe, wpp, bpp)
+            o, aux = ops.relpos_attn_tc_fwd(qkv, e, klen_p, qlen, B, Tp, H, d, dp)
+        else:
+            wqkv = wc_cat((wq, wk, wv), "qkv")
+            bqkv = wc_cat((bq, bk, bv), "bqkv").reshape(-1)
+            wop = wc(wo)
+            qkv = ops.linear_fwd(xp.view(B * Tp, D), wqkv, bqkv)
+            e = ops.linear_fwd(pe, wc(wp), bp)
+            o, aux = ops.relpos_attn_fwd(qkv, e, klen_p, qlen, B, Tp, H, d)
         site = 0
         plain = ln_w is None          # attention.forwardQKV: no LayerNorm in front, no residual behind (modules.py:330)
         res = None if plain else x.view(B * T, D)
         if p_drop > 0 or (plain and P > 1):
             # AttentionModule.dropout acts on the upsampled (B, T, D) output: one mask element per frame (modules.py:333)
             site = ops.RNG.next_site() if p_drop > 0 else 0
-            proj = ops.linear_fwd(o, wc(wo), bo)
+            proj = ops.linear_fwd(o, wop, bo)
             y = ops.dropout_rng(ctx.rng, proj, p_drop, site, res=res, up=(T, Tp, P) if P > 1 else None).view(B, T, D)
         elif P == 1:
-            y = ops.linear_fwd(o, wc(wo), bo, L.EPI_LINEAR if plain else L.EPI_RESIDUAL, aux=res).view(B, T, D)
+            y = ops.linear_fwd(o, wop, bo, L.EPI_LINEAR if plain else L.EPI_RESIDUAL, aux=res).view(B, T, D)
         else:
-            proj = ops.linear_fwd(o, wc(wo), bo)
+            proj = ops.linear_fwd(o, wop, bo)
             y = ops.upsample_add(x, proj.view(B, Tp, D), P)
-        ctx.save_for_backward(x, ln_w, mean, rstd, xp, qkv, e, probs, o, pe, wq, wk, wv, wo, wp)
-        ctx.H, ctx.P, ctx.drop = H, P, (p_drop, site)
+        ctx.save_for_backward(x, ln_w, mean, rstd, xp, qkv, e, aux, o, pe, wq, wk, wv, wo, wp, klen_p)
+        ctx.H, ctx.P, ctx.drop, ctx.tc, ctx.qlen = H, P, (p_drop, site), tc, qlen
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, ln_w, mean, rstd, xp, qkv, e, probs, o, pe, wq, wk, wv, wo, wp = ctx.saved_tensors
-        H, P = ctx.H, ctx.P
+        x, ln_w, mean, rstd, xp, qkv, e, aux, o, pe, wq, wk, wv, wo, wp, klen_p = ctx.saved_tensors
+        H, P, tc = ctx.H, ctx.P, ctx.tc
         B, T, D = x.shape
         Tp = xp.shape[1]
         d = D // H
@@ -242,16 +288,29 @@ class AttentionFn(Function):
         p_drop, site = ctx.drop
         dyd = ops.dropout_rng(ctx.rng, dy.view(B * T, D), p_drop, site).view(B, T, D) if p_drop > 0 else dy
         dproj = dyd.view(B * T, D) if P == 1 else ops.pool_sum(dyd, P).view(B * Tp, D)
-        do = ops.linear_dgrad(dproj, wc(wo))
-        dwo = ops.linear_wgrad(dproj, o)
         dbo = ops.colsum(dproj)
-        dqkv, de, _, _ = ops.relpos_attn_bwd(do, qkv, e, probs, B, Tp, H, d)
-        dwp = ops.linear_wgrad(ops.convert(de, x.dtype), pe)
-        dbp = ops.colsum(de)
-        wqkv = wc_cat((wq, wk, wv), "qkv")
-        dxp = ops.linear_dgrad(dqkv, wqkv)
-        dwqkv = ops.linear_wgrad(dqkv, xp.view(B * Tp, D))
-        dbqkv = ops.colsum(dqkv)
+        if tc:
+            dp = ops.attn_head_pad(d)
+            wqkv = wc_fn((wq, wk, wv), "qkv_tc", lambda a, b, c: torch.cat([_pad_rows(t, H, d, dp) for t in (a, b, c)], dim=0))
+            wop = wc_fn((wo,), "out_tc", lambda a: _pad_rows(a.t(), H, d, dp).t())
+            do = ops.linear_dgrad(dproj, wop)
+            dwo = _unpad_rows(ops.linear_wgrad(dproj, o).t(), H, d, dp).t()
+            dqkv, de = ops.relpos_attn_tc_bwd(do, qkv, e, o, aux, klen_p, ctx.qlen, B, Tp, H, d, dp)
+            dwp = _unpad_rows(ops.linear_wgrad(ops.convert(de, x.dtype), pe), H, d, dp)
+            dbp = _unpad_rows(ops.colsum(de), H, d, dp)
+            dxp = ops.linear_dgrad(dqkv, wqkv)
+            dwqkv = _unpad_rows(ops.linear_wgrad(dqkv, xp.view(B * Tp, D)), H, d, dp)
+            dbqkv = _unpad_rows(ops.colsum(dqkv), H, d, dp)
+        else:
+            do = ops.linear_dgrad(dproj, wc(wo))
+            dwo = ops.linear_wgrad(dproj, o)
+            dqkv, de, _, _ = ops.relpos_attn_bwd(do, qkv, e, aux, B, Tp, H, d)
+            dwp = ops.linear_wgrad(ops.convert(de, x.dtype), pe)
+            dbp = ops.colsum(de)
+            wqkv = wc_cat((wq, wk, wv), "qkv")
+            dxp = ops.linear_dgrad(dqkv, wqkv)
+            dwqkv = ops.linear_wgrad(dqkv, xp.view(B * Tp, D))
+            dbqkv = ops.colsum(dqkv)
         dx, dg, db = ops.layernorm_bwd(dxp.view(B, Tp, D), x, ln_w, mean, rstd, P=P, dres=None if ln_w is None else dy, res_stride=1)
         return (dx, dg, db, dwqkv[:D], dbqkv[:D], dwqkv[D:2 * D], dbqkv[D:2 * D], dwqkv[2 * D:], dbqkv[2 * D:], dwo, dbo,
                 dwp, dbp, None, None, None, None, None)

@@ -415,6 +415,45 @@ def relpos_attn_bwd(do, qkv, e, probs, B, T, H, d, G=1, Tf=None, u=None, v=None)
     return dqkv, de, du, dv
 
 
+# tcgen05 / TMEM / TMA attention (csrc/attention_tc.cu): bf16, regular + patch attention, any sequence length, flash-style
+ATTN_TC = os.environ.get("AVEC_ATTN_TC", "1") != "0"
+
+
+def set_attention_tc(enabled):
+    """False: the round-1 kernels (mma.sync up to 128 keys, SIMT beyond) - kept for grouped attention, fp32 and A/B tests"""
+    global ATTN_TC
+    ATTN_TC = bool(enabled)
+
+
+def attn_head_pad(d):
+    """column block of one head in the padded-heads layout (one or two 64-wide TMA boxes), None if unsupported"""
+    return 64 if d <= 64 else (128 if d <= 128 else None)
+
+
+def relpos_attn_tc_fwd(qkv, e, klen, qlen, B, T, H, d, dp):
+    """qkv [B*T, 3*H*dp], e [2T-1, H*dp] (padded heads) -> o [B*T, H*dp] bf16, lse [B,H,T] fp32"""
+    _cuda(qkv, e)
+    o = torch.empty((B * T, H * dp), device=qkv.device, dtype=qkv.dtype)
+    lse = torch.empty((B, H, T), device=qkv.device, dtype=torch.float32)
+    L.check(L.load().avec_relpos_attn_tc_fwd(qkv.data_ptr(), qkv.stride(0), e.data_ptr(), e.stride(0), _p(klen), int(qlen), o.data_ptr(),
+                                             o.stride(0), lse.data_ptr(), B, T, H, d, dp, _stream()), "avec_relpos_attn_tc_fwd")
+    return o, lse
+
+
+def relpos_attn_tc_bwd(do, qkv, e, o, lse, klen, qlen, B, T, H, d, dp):
+    """-> dqkv [B*T, 3*H*dp] bf16, de [2T-1, H*dp] fp32"""
+    _cuda(do, qkv, e, o)
+    dqkv = torch.empty((B * T, 3 * H * dp), device=qkv.device, dtype=qkv.dtype)
+    ws = None if T <= 128 else zeros_f32((B * T, 3 * H * dp), qkv.device)
+    de = zeros_f32((2 * T - 1, H * dp), qkv.device)
+    L.check(L.load().avec_relpos_attn_tc_bwd(do.data_ptr(), do.stride(0), qkv.data_ptr(), qkv.stride(0), e.data_ptr(), e.stride(0),
+                                             o.data_ptr(), o.stride(0), lse.data_ptr(), _p(klen), int(qlen), dqkv.data_ptr(), dqkv.stride(0),
+                                             _p(ws), de.data_ptr(), de.stride(0), B, T, H, d, dp, _stream()), "avec_relpos_attn_tc_bwd")
+    if ws is not None:
+        dqkv = convert(ws, qkv.dtype)
+    return dqkv, de
+
+
 # --------------------------------------------------------------------------------------------------------- conv module
 def glu_dwconv_fwd(pre, w, bias, stride, ksize=15, want_stats=True):
     B, T, C2 = pre.shape

@@ -154,6 +154,23 @@ int avec_relpos_attn_bwd(const void* d_o, const void* qkv, const void* e, const 
                          float* de, int B, int T, int H, int d, int G, int Tf, const float* u, const float* v, float* du,
                          float* dv, int dtype, avec_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * The same attention as a Blackwell tile kernel (csrc/attention_tc.cu): tcgen05.mma with score / band / output accumulators in
+ * TMEM, operands by TMA, flash-style for ANY sequence length (no [B,H,T,T] tensor: the forward saves lse [B,H,T] fp32, the
+ * backward recomputes the probabilities).  bf16, G = 1 (regular and - on pooled tokens - patch attention).
+ * "Padded heads" layout: every head owns a dp = 64 or 128 wide column block (dp >= d; pad columns are zeros, produced by
+ * zero-padded projection weights): qkv [B*T, >= 3*H*dp] with head h of part s (0 q, 1 k, 2 v) at columns (s*H + h)*dp,
+ * e [2T-1, >= H*dp], o / d_o [B*T, >= H*dp]; ld_* are row pitches in elements (multiples of 8), bases 16-byte aligned.
+ * bwd: dqkv (bf16, qkv's layout) is written directly when T <= 128; for longer sequences the partial sums of the 128 x 128
+ * tiles are accumulated atomically into dqkv_ws (fp32, same shape and pitch, zero-initialised by the caller) instead.
+ * de [2T-1, >= H*dp] fp32 is accumulated atomically (zero-initialised by the caller).
+ * ------------------------------------------------------------------------------------------------------------------ */
+int avec_relpos_attn_tc_fwd(const void* qkv, long long ld_qkv, const void* e, long long ld_e, const int* klen, int qlen, void* o,
+                            long long ld_o, float* lse, int B, int T, int H, int d, int dp, avec_stream_t stream);
+int avec_relpos_attn_tc_bwd(const void* d_o, long long ld_do, const void* qkv, long long ld_qkv, const void* e, long long ld_e,
+                            const void* o, long long ld_o, const float* lse, const int* klen, int qlen, void* dqkv, long long ld_dqkv,
+                            float* dqkv_ws, float* de, long long ld_de, int B, int T, int H, int d, int dp, avec_stream_t stream);
+
 /* row softmax / its backward (InterCTCResModule, nnet/modules.py:397-398).  dadd (optional, fp32) is added to dx. */
 int avec_softmax_fwd(const void* x, int x_dtype, void* y, int y_dtype, long long rows, int C, avec_stream_t stream);
 int avec_softmax_bwd(const void* dy, const void* y, int dtype, const float* dadd, void* dx, int dx_dtype, long long rows,
