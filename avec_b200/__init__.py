@@ -6,6 +6,7 @@
   avec_b200.patch_reference()   swap these encoders (+ CTC loss, fused Adam) under the unmodified reference launcher
 """
 from . import _lib  # noqa: F401
+from . import data  # noqa: F401
 from .functional import set_compute_dtype, compute_dtype, new_step, invalidate_weights, manual_seed  # noqa: F401
 from .ops import set_gemm_impl, launch_count, reset_launch_count  # noqa: F401
 from .dropin import patch_reference, unpatch_reference  # noqa: F401

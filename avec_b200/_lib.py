@@ -85,6 +85,7 @@ PROTOTYPES = {
     "avec_counter_advance": ([_P, _P], _I),
     "avec_dropout": ([_P, _P, _P, _L, _I, _I, _F, _F, _P, _I, _I, _I, _I, _P], _I),
     "avec_spec_augment": ([_P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _I, _P, _P], _I),
+    "avec_video_augment": ([_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _F, _F, _P, _I, _P, _P], _I),
     "avec_ctc_greedy_decode": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _P], _I),
     "avec_sumsq": ([_P, _L, _P, _P], _I),
     "avec_adam_step": ([_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _F, _F, _F, _F, _P, _P, _P, _P], _I),

@@ -151,6 +151,116 @@ extern "C" int avec_spec_augment(float* mel, const long long* lengths, int B, in
     return AVEC_OK;
 }
 
+// ------------------------------------------------------------------------------------------- video augmentation
+// The training_video_transform of the reference's LRS2/3 configs (configs/LRS23/AV/EffConfInterCTC.py:82-88), per sample, on the
+// device and on the whole padded batch at once:  torchvision RandomCrop(Ho, Wo) -> RandomHorizontalFlip(p) -> nnet.TimeMaskSecond
+// (nnet/transforms.py:108-126: int(T_b / fps * num_mask_second) masks over time, each torchaudio mask_along_axis(mask_param =
+// int(T_second * fps), mask_value = mean of the CURRENT clip): value = rand * mask_param, min = rand * (T_b - value), frames
+// [int(min), int(min) + int(value)) replaced).  Draws: Philox(ctr = (b, k, site, step)): k = 0 -> crop row (word 0), crop column
+// (word 1), flip (word 2);  k = 1 + m -> mask m (words 0, 1).  Frames beyond the sample's length are written as zeros (the
+// collate padding of nnet/collate_fn.py).
+#define AVEC_VIDEO_MAX_MASKS 32
+struct VideoDraw { int oy, ox, flip; };
+__device__ __forceinline__ VideoDraw video_draw(const unsigned long long* rng, uint32_t site, uint32_t b, int Hi, int Wi, int Ho, int Wo, float flip_p) {
+    const unsigned long long seed = rng[0], step = rng[1];
+    const uint4 r = philox4x32_10(make_uint4(b, 0u, site, (uint32_t)step), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    VideoDraw d;
+    d.oy = min((int)__fmul_rn(u01(r.x), (float)(Hi - Ho + 1)), Hi - Ho);
+    d.ox = min((int)__fmul_rn(u01(r.y), (float)(Wi - Wo + 1)), Wi - Wo);
+    d.flip = u01(r.z) < flip_p ? 1 : 0;
+    return d;
+}
+
+// fsum[b][t] = sum over the crop window of frame t (a horizontal flip does not change it); one CTA per (b, t)
+__global__ void __launch_bounds__(256) video_frame_sum_kernel(const float* __restrict__ in, const long long* __restrict__ lengths, float* __restrict__ fsum,
+                                                              int T, int Hi, int Wi, int Ho, int Wo, float flip_p,
+                                                              const unsigned long long* __restrict__ rng, uint32_t site) {
+    __shared__ float red[8];
+    const int t = blockIdx.x, b = blockIdx.y;
+    const int len = lengths ? (int)min((long long)T, lengths[b]) : T;
+    float s = 0.0f;
+    if (t < len) {
+        const VideoDraw d = video_draw(rng, site, (uint32_t)b, Hi, Wi, Ho, Wo, flip_p);
+        const float* fr = in + ((size_t)b * T + t) * Hi * Wi;
+        for (int i = threadIdx.x; i < Ho * Wo; i += blockDim.x) s += fr[(size_t)(d.oy + i / Wo) * Wi + d.ox + i % Wo];
+    }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tot = 0.0f;
+        for (int w = 0; w < 8; ++w) tot += red[w];
+        fsum[(size_t)b * T + t] = tot;
+    }
+}
+
+__global__ void __launch_bounds__(256) video_augment_kernel(const float* __restrict__ in, const long long* __restrict__ lengths, const float* __restrict__ fsum,
+                                                            float* __restrict__ out, int T, int Hi, int Wi, int Ho, int Wo, float flip_p, int mask_T,
+                                                            float fps, float num_mask_second, const unsigned long long* __restrict__ rng, uint32_t site,
+                                                            int* __restrict__ draws) {
+    __shared__ float s_val;
+    __shared__ int s_masked;
+    const int t = blockIdx.x, b = blockIdx.y;
+    const int len = lengths ? (int)min((long long)T, lengths[b]) : T;
+    float* dst = out + ((size_t)b * T + t) * Ho * Wo;
+    if (t >= len) {
+        for (int i = threadIdx.x; i < Ho * Wo; i += blockDim.x) dst[i] = 0.0f;
+        return;
+    }
+    const VideoDraw d = video_draw(rng, site, (uint32_t)b, Hi, Wi, Ho, Wo, flip_p);
+    if (threadIdx.x == 0) {
+        // the masks are sequential (each fills with the mean of the clip as the previous masks left it): replay them on the
+        // per-frame sums; this CTA only needs the value its own frame ends up with
+        const int nmask = min((int)((float)len / fps * num_mask_second), AVEC_VIDEO_MAX_MASKS);
+        const float hw = (float)(Ho * Wo);
+        const float* fs = fsum + (size_t)b * T;
+        int lo[AVEC_VIDEO_MAX_MASKS], hi[AVEC_VIDEO_MAX_MASKS];
+        float val[AVEC_VIDEO_MAX_MASKS];
+        int masked = 0;
+        float mine = 0.0f;
+        for (int m = 0; m < nmask; ++m) {
+            mask_interval(rng, site, (uint32_t)b, (uint32_t)(1 + m), (float)mask_T, (float)len, &lo[m], &hi[m]);
+            double tot = 0.0;
+            for (int f = 0; f < len; ++f) {
+                float v = fs[f];
+                for (int q = m - 1; q >= 0; --q) if (f >= lo[q] && f < hi[q]) { v = val[q] * hw; break; }
+                tot += (double)v;
+            }
+            val[m] = (float)(tot / ((double)hw * (double)len));
+            if (t >= lo[m] && t < hi[m]) { masked = 1; mine = val[m]; }
+            if (draws && t == 0) { draws[((size_t)b * (3 + 2 * AVEC_VIDEO_MAX_MASKS)) + 3 + 2 * m] = lo[m]; draws[((size_t)b * (3 + 2 * AVEC_VIDEO_MAX_MASKS)) + 4 + 2 * m] = hi[m]; }
+        }
+        if (draws && t == 0) {
+            int* dr = draws + (size_t)b * (3 + 2 * AVEC_VIDEO_MAX_MASKS);
+            dr[0] = d.oy; dr[1] = d.ox; dr[2] = d.flip;
+            for (int m = nmask; m < AVEC_VIDEO_MAX_MASKS; ++m) { dr[3 + 2 * m] = 0; dr[4 + 2 * m] = 0; }
+        }
+        s_masked = masked; s_val = mine;
+    }
+    __syncthreads();
+    const float* fr = in + ((size_t)b * T + t) * Hi * Wi;
+    const bool masked = s_masked != 0;
+    const float mv = s_val;
+    for (int i = threadIdx.x; i < Ho * Wo; i += blockDim.x) {
+        const int y = i / Wo, x = i - y * Wo;
+        dst[i] = masked ? mv : fr[(size_t)(d.oy + y) * Wi + d.ox + (d.flip ? Wo - 1 - x : x)];
+    }
+}
+
+extern "C" int avec_video_augment(const float* in, const long long* lengths, float* out, float* frame_sums, int B, int T, int Hi, int Wi, int Ho,
+                                  int Wo, float flip_p, int mask_T, float fps, float num_mask_second, const unsigned long long* rng_state,
+                                  int site, int* draws, avec_stream_t stream) {
+    AVEC_CHECK_ARG(in && out && frame_sums && rng_state && B > 0 && T > 0 && Ho > 0 && Wo > 0 && Hi >= Ho && Wi >= Wo && fps > 0.0f && mask_T >= 0);
+    AVEC_CHECK_ARG(B <= 65535 && (int)((float)T / fps * num_mask_second) <= AVEC_VIDEO_MAX_MASKS);
+    dim3 grid((unsigned)T, (unsigned)B);
+    video_frame_sum_kernel<<<grid, 256, 0, as_stream(stream)>>>(in, lengths, frame_sums, T, Hi, Wi, Ho, Wo, flip_p, rng_state, (uint32_t)site);
+    AVEC_LAUNCH_CHECK();
+    video_augment_kernel<<<grid, 256, 0, as_stream(stream)>>>(in, lengths, frame_sums, out, T, Hi, Wi, Ho, Wo, flip_p, mask_T, fps, num_mask_second,
+                                                             rng_state, (uint32_t)site, draws);
+    AVEC_LAUNCH_CHECK();
+    return AVEC_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ greedy CTC decode
 // nnet/decoders.py:97-120: argmax over the vocabulary (first maximum, as torch.argmax), frames beyond the utterance
 // length dropped, consecutive repeats merged, blanks removed.  One CTA per utterance: warps take frames round-robin,

@@ -7,6 +7,7 @@ from .blocks import *          # noqa: F401,F403
 from .networks import *        # noqa: F401,F403
 from .models_zoo import *      # noqa: F401,F403
 from .preprocessing import AudioPreprocessing, SpecAugment  # noqa: F401
+from .transforms import VideoAugment, align_video_to_audio  # noqa: F401
 from .losses import CTCLoss    # noqa: F401
 from .decoders import CTCGreedySearchDecoder  # noqa: F401
 from . import optimizers, schedulers  # noqa: F401

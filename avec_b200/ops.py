@@ -734,6 +734,25 @@ def spec_augment_(mel, lengths, site, mF=2, Fmax=27, mT=5, pS=0.05, want_interva
     return iv
 
 
+VIDEO_MAX_MASKS = 32
+
+
+def video_augment(video, lengths, site, crop=(88, 88), flip_p=0.5, mask_T=10, fps=25.0, num_mask_second=1.0, want_draws=False, rng=None):
+    """video [B,T,Hi,Wi] fp32 -> [B,T,Ho,Wo] fp32: RandomCrop + RandomHorizontalFlip + TimeMaskSecond per sample (see
+    include/avec_b200.h); lengths [B] int64 device tensor of valid frames or None"""
+    _cuda(video, lengths)
+    assert video.dtype == torch.float32 and video.is_contiguous() and video.dim() == 4
+    B, T, Hi, Wi = video.shape
+    out = torch.empty((B, T, crop[0], crop[1]), device=video.device, dtype=torch.float32)
+    fsum = torch.empty((B * T,), device=video.device, dtype=torch.float32)
+    draws = torch.zeros((B, 3 + 2 * VIDEO_MAX_MASKS), device=video.device, dtype=torch.int32) if want_draws else None
+    L.check(L.load().avec_video_augment(video.data_ptr(), _p(lengths), out.data_ptr(), fsum.data_ptr(), B, T, Hi, Wi, crop[0], crop[1],
+                                        float(flip_p), int(mask_T), float(fps), float(num_mask_second),
+                                        (rng if rng is not None else RNG.cur(video.device)).data_ptr(), int(site), _p(draws), _stream()),
+            "avec_video_augment")
+    return (out, draws) if want_draws else out
+
+
 def ctc_greedy_decode(logits, in_len=None, blank=0, want_align=False):
     """logits [B,T,V] fp32 -> (tokens [B,T] int32 padded with -1, ntok [B] int32[, align [B,T] int32])"""
     _cuda(logits, in_len)

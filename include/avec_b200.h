@@ -299,6 +299,15 @@ int avec_dropout(const void* x, const void* res, void* y, long long rows, int C,
 int avec_spec_augment(float* mel, const long long* lengths, int B, int F, int M, int mF, int Fmax, int mT, float pS,
                       const unsigned long long* rng_state, int site, int* intervals, avec_stream_t stream);
 
+/* Video augmentation of the reference's training configs (configs/LRS23/AV/EffConfInterCTC.py:82-88), on the padded batch:
+ * RandomCrop(Ho, Wo) -> RandomHorizontalFlip(flip_p) -> nnet.TimeMaskSecond (nnet/transforms.py:108-126: int(len_b / fps *
+ * num_mask_second) time masks of width < mask_T frames, filled with the running mean of the clip).  in [B,T,Hi,Wi] fp32 ->
+ * out [B,T,Ho,Wo] fp32, frames >= lengths[b] zero; frame_sums: [B*T] float scratch; draws (optional) [B][3 + 2*32] int32 receives
+ * {crop row, crop column, flip, (lo, hi) per mask}.  Same counter-based generator as avec_dropout (site selects the stream). */
+int avec_video_augment(const float* in, const long long* lengths, float* out, float* frame_sums, int B, int T, int Hi, int Wi, int Ho,
+                       int Wo, float flip_p, int mask_T, float fps, float num_mask_second, const unsigned long long* rng_state,
+                       int site, int* draws, avec_stream_t stream);
+
 /* Greedy CTC decoding (nnet/decoders.py:97-120): argmax (first maximum) -> frames < in_len -> merge repeats -> drop blanks.
  * logits [B,T,V] fp32, in_len [B] int64 device (NULL = T); align [B,T] int32 frame-level argmax (-1 beyond the length,
  * may be NULL), tokens [B,T] int32 padded with -1, ntok [B] int32. */

@@ -94,6 +94,35 @@ def spec_augment(mel, lengths, seed, step, site, mF=2, Fmax=27, mT=5, pS=0.05):
     return out
 
 
+def video_draws(seed, step, site, b, length, Hi, Wi, Ho, Wo, flip_p=0.5, mask_T=10, fps=25.0, num_mask_second=1.0):
+    """(crop row, crop column, flip, [(lo, hi) per time mask]) of sample b: csrc/train.cu video_draw / mask_interval"""
+    k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+    w = philox4x32_10(np.uint64(b), np.uint64(0), np.uint64(site), np.uint64(step & 0xFFFFFFFF), k0, k1)
+    oy = min(int(_u01(w[0]) * np.float32(Hi - Ho + 1)), Hi - Ho)
+    ox = min(int(_u01(w[1]) * np.float32(Wi - Wo + 1)), Wi - Wo)
+    flip = bool(_u01(w[2]) < np.float32(flip_p))
+    nmask = int(np.float32(length) / np.float32(fps) * np.float32(num_mask_second))
+    return oy, ox, flip, [_interval(seed, step, site, b, 1 + m, mask_T, length) for m in range(nmask)]
+
+
+def video_augment(video, lengths, seed, step, site, crop=(88, 88), flip_p=0.5, mask_T=10, fps=25.0, num_mask_second=1.0):
+    """video [B,T,Hi,Wi] float32 numpy -> [B,T,Ho,Wo]: torchvision RandomCrop -> RandomHorizontalFlip -> nnet.TimeMaskSecond
+    (transforms.py:108-126, mean_frame=True) per sample on its first lengths[b] frames, zeros beyond (collate padding)."""
+    B, T, Hi, Wi = video.shape
+    Ho, Wo = crop
+    out = np.zeros((B, T, Ho, Wo), dtype=np.float32)
+    for b in range(B):
+        ln = min(int(lengths[b]), T)
+        oy, ox, flip, masks = video_draws(seed, step, site, b, ln, Hi, Wi, Ho, Wo, flip_p, mask_T, fps, num_mask_second)
+        clip = video[b, :ln, oy:oy + Ho, ox:ox + Wo].copy()
+        if flip:
+            clip = clip[:, :, ::-1].copy()
+        for lo, hi in masks:
+            clip[lo:min(hi, ln)] = np.float32(clip.astype(np.float64).mean())
+        out[b, :ln] = clip
+    return out
+
+
 def greedy_decode(logits, lengths, blank=0):
     """CTCGreedySearchDecoder.greedy_search: list of token lists; logits [B,T,V] numpy, lengths [B]."""
     preds = logits.argmax(axis=-1)

@@ -33,11 +33,11 @@ def _batch(B=4, Ls=5120, seed=5):
         video[b, int(vlen[b]):] = 0.0
     g = torch.Generator().manual_seed(seed)
     labels = torch.randint(1, 256, (B, 6), generator=g)
-    return [video, vlen, audio, alen], [labels, torch.full((B,), 6)]
+    return [video, vlen, audio, alen], (labels, torch.full((B,), 6))
 
 
 def _to(dev, xs):
-    return [x.to(dev) for x in xs]
+    return type(xs)(x.to(dev) for x in xs)     # targets stay a TUPLE: a list would be mapped output by output (model.py:212-216)
 
 
 class _NoAug(torch.nn.Module):

@@ -328,3 +328,27 @@ def test_fused_adam_checkpoint_round_trip_with_torch_adam():
     for i, (c, d) in enumerate(zip(ps_c, ps_d)):
         check_close(f"back[{i}]", c, d, 1e-5, 1e-7)
     assert int(back.state_dict()["model_step"]) == 5
+
+
+def test_video_augment_matches_reference_fixture():
+    """RandomCrop + RandomHorizontalFlip + TimeMaskSecond on the device: the draws bit-exact, the clip equal to the fixture the
+    reference's / torchvision's own modules produced from the same draws (mean fill values to fp32 summation order)"""
+    fix = load_golden("train_video_augment.pt")
+    B, T, Hi, Wi = fix["shape"]
+    video = seeded.randn("videoaug.x", fix["shape"], fix["video_seed"]).clamp(-1, 1)
+    _set_rng(fix["seed"], fix["step"])
+    out, draws = ops.video_augment(video.to(DEV), fix["lengths"].to(DEV), fix["site"], want_draws=True, rng=ops.RNG.get(DEV))
+    draws = draws.cpu()
+    for b in range(B):
+        oy, ox, flip, masks = fix["draws"][b]
+        assert draws[b, :3].tolist() == [oy, ox, int(flip)]
+        assert [tuple(draws[b, 3 + 2 * m: 5 + 2 * m].tolist()) for m in range(len(masks))] == [tuple(iv) for iv in masks]
+    want = TO.video_augment(video.numpy(), fix["lengths"].tolist(), fix["seed"], fix["step"], fix["site"])
+    assert float((out.cpu() - torch.from_numpy(want)).abs().max()) <= 1e-6
+    assert float((out.cpu()[:, ::3, ::4, ::4] - fix["out_sub"]).abs().max()) <= 1e-6
+    # module interface: train() augments, eval() is the configs' CenterCrop; frames past the length are zero
+    aug = nnet.VideoAugment().to(DEV).train()
+    y = aug(video.to(DEV).unsqueeze(-1), fix["lengths"].to(DEV))
+    assert y.shape == (B, T, 88, 88, 1) and float(y[2, int(fix["lengths"][2]):].abs().max()) == 0.0
+    ye = aug.eval()(video.to(DEV), None)
+    assert torch.equal(ye, video.to(DEV)[:, :, 4:92, 4:92])

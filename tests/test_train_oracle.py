@@ -104,3 +104,17 @@ def test_schedulers_match_reference_formulas():
     a, b = mine.device_params()                      # lr = a * min(t * b^-1.5, t^-0.5) evaluated by adam_kernel
     assert abs(a * min(17 * b ** -1.5, 17 ** -0.5) - mine.get_val_step(17)) < 1e-15
     assert mine.step() == mine.get_val_step(1) and int(mine.model_step) == 1
+
+
+def test_video_augment_restatement_matches_reference():
+    """oracle/train_oracle.video_augment == torchvision RandomCrop + RandomHorizontalFlip + the reference's TimeMaskSecond fed with the
+    same draws (fixture generated by those modules themselves, oracle/make_golden_train.py video_augment_case)"""
+    fix = load_golden("train_video_augment.pt")
+    video = seeded.randn("videoaug.x", fix["shape"], fix["video_seed"]).clamp(-1, 1).numpy()
+    out = TO.video_augment(video, fix["lengths"].tolist(), fix["seed"], fix["step"], fix["site"])
+    assert np.abs(out[:, ::3, ::4, ::4] - fix["out_sub"].numpy()).max() <= 1e-6
+    assert abs(float(out.astype(np.float64).sum()) - fix["out_sum"]) <= 1e-3
+    B, T, Hi, Wi = fix["shape"]
+    for b in range(B):
+        got = TO.video_draws(fix["seed"], fix["step"], fix["site"], b, int(fix["lengths"][b]), Hi, Wi, 88, 88)
+        assert got == fix["draws"][b]
