@@ -651,18 +651,21 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, float (&v)[64]) {
     for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
 }
 // 8 consecutive bf16 (aligned to 16 bytes when AL16, else to 8 bytes) <-> packed words
+// `half`: only the first 4 of the 8 columns exist (last column group of a matrix whose width is 4 mod 8, e.g. N = 180)
 template <bool AL16>
-__device__ __forceinline__ uint4 ldg_bf16x8(const bf16* q) {
+__device__ __forceinline__ uint4 ldg_bf16x8(const bf16* q, bool half = false) {
+    if (half) { const uint2 a = __ldg(reinterpret_cast<const uint2*>(q)); return make_uint4(a.x, a.y, 0u, 0u); }
     if (AL16) return __ldg(reinterpret_cast<const uint4*>(q));
     const uint2 a = __ldg(reinterpret_cast<const uint2*>(q)), b = __ldg(reinterpret_cast<const uint2*>(q) + 1);
     return make_uint4(a.x, a.y, b.x, b.y);
 }
 template <bool AL16>
-__device__ __forceinline__ void stg_bf16x8(bf16* q, const float (&v)[8]) {
+__device__ __forceinline__ void stg_bf16x8(bf16* q, const float (&v)[8], bool half = false) {
     uint32_t w[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) { __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]); w[i] = *reinterpret_cast<uint32_t*>(&t); }
-    if (AL16) *reinterpret_cast<uint4*>(q) = make_uint4(w[0], w[1], w[2], w[3]);
+    if (half) reinterpret_cast<uint2*>(q)[0] = make_uint2(w[0], w[1]);
+    else if (AL16) *reinterpret_cast<uint4*>(q) = make_uint4(w[0], w[1], w[2], w[3]);
     else { reinterpret_cast<uint2*>(q)[0] = make_uint2(w[0], w[1]); reinterpret_cast<uint2*>(q)[1] = make_uint2(w[2], w[3]); }
 }
 __device__ __forceinline__ void unpack_bf16x8(const uint4& t, float (&v)[8]) {
@@ -699,6 +702,7 @@ __device__ __forceinline__ void epilogue_fast(const TcParams& p, const EpiParams
         const int ncol = min(64, BN - c0);   // multiple of 16
         const int gc = ti.n0 + c0 + lc;
         const bool col_ok = lc < ncol && gc < p.N;
+        const bool half = gc + 8 > p.N;     // N % 8 == 4: the last column group holds 4 columns (8-byte accesses only)
         // ---- auxiliary operand of the first four passes: does not depend on the accumulator, so it is requested first
         uint4 xa[4];
         constexpr bool HAS_AUX = KIND == AVEC_EPI_RESIDUAL || KIND == AVEC_EPI_DSWISH || KIND == AVEC_EPI_RELU;
@@ -709,7 +713,7 @@ __device__ __forceinline__ void epilogue_fast(const TcParams& p, const EpiParams
             for (int u = 0; u < 4; ++u) {
                 const int rr = u * 4 + rs;
                 xa[u] = make_uint4(0u, 0u, 0u, 0u);
-                if (aux_on && col_ok && rr < rows_left) { const long long ro = out_row(rr); if (ro >= 0) xa[u] = ldg_bf16x8<AL16>(auxp + (size_t)ro * ep.ldaux + gc); }
+                if (aux_on && col_ok && rr < rows_left) { const long long ro = out_row(rr); if (ro >= 0) xa[u] = ldg_bf16x8<AL16>(auxp + (size_t)ro * ep.ldaux + gc, half); }
             }
         }
         // ---- row domain: TMEM -> registers -> staging
@@ -732,7 +736,7 @@ __device__ __forceinline__ void epilogue_fast(const TcParams& p, const EpiParams
             for (int u = 0; u < 4; ++u) {
                 const int rr = (4 + u) * 4 + rs;
                 xb[u] = make_uint4(0u, 0u, 0u, 0u);
-                if (aux_on && col_ok && rr < rows_left) { const long long ro = out_row(rr); if (ro >= 0) xb[u] = ldg_bf16x8<AL16>(auxp + (size_t)ro * ep.ldaux + gc); }
+                if (aux_on && col_ok && rr < rows_left) { const long long ro = out_row(rr); if (ro >= 0) xb[u] = ldg_bf16x8<AL16>(auxp + (size_t)ro * ep.ldaux + gc, half); }
             }
         }
         __syncwarp();
@@ -777,11 +781,11 @@ __device__ __forceinline__ void epilogue_fast(const TcParams& p, const EpiParams
                 if (KIND == AVEC_EPI_ACCUM) {
                     float* dst = reinterpret_cast<float*>(ep.out) + oi;
                     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(sa_[0]), "f"(sa_[1]), "f"(sa_[2]), "f"(sa_[3]) : "memory");
-                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(sa_[4]), "f"(sa_[5]), "f"(sa_[6]), "f"(sa_[7]) : "memory");
+                    if (!half) asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(sa_[4]), "f"(sa_[5]), "f"(sa_[6]), "f"(sa_[7]) : "memory");
                 } else {
                     float o[8], x[8];
                     if (HAS_AUX) unpack_bf16x8(g == 0 ? xa[u] : xb[u], x);
-                    if (KIND == AVEC_EPI_SWISH && ep.out2) stg_bf16x8<AL16>(reinterpret_cast<bf16*>(ep.out2) + row * ep.ldo2 + gc, a);
+                    if (KIND == AVEC_EPI_SWISH && ep.out2) stg_bf16x8<AL16>(reinterpret_cast<bf16*>(ep.out2) + row * ep.ldo2 + gc, a, half);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         if (KIND == AVEC_EPI_LINEAR) o[j] = sa_[j];
@@ -790,7 +794,7 @@ __device__ __forceinline__ void epilogue_fast(const TcParams& p, const EpiParams
                         else if (KIND == AVEC_EPI_DSWISH) o[j] = sa_[j] * dswishf_(x[j]);
                         else o[j] = fmaxf(sa_[j] + x[j], 0.0f);
                     }
-                    stg_bf16x8<AL16>(reinterpret_cast<bf16*>(ep.out) + oi, o);
+                    stg_bf16x8<AL16>(reinterpret_cast<bf16*>(ep.out) + oi, o, half);
                 }
                 if (STATS) {
 #pragma unroll
@@ -2567,7 +2571,8 @@ static int gemm_tc_launch(const avec_gemm_args* a, cudaStream_t st, const DgradC
         if (fast_on < 0) { const char* e = getenv("AVEC_EPI_FAST"); fast_on = e ? atoi(e) : 1; }
         const EpiParams& ep = p.ep;
         int al = 16;
-        bool ok = fast_on && !halo && a->N % 8 == 0 && !p.out_transposed;
+        // widths of 4 mod 8 (D = 180) take the fast path too: their last column group is handled with 8-byte accesses
+        bool ok = fast_on && !halo && a->N % 4 == 0 && !p.out_transposed;
         if (ep.kind == AVEC_EPI_ACCUM) {
             ok = ok && ep.out_dtype == AVEC_F32 && (reinterpret_cast<uintptr_t>(ep.out) % 16) == 0 && ep.ldo % 4 == 0 && !ep.colstats;
         } else {
@@ -2575,7 +2580,7 @@ static int gemm_tc_launch(const avec_gemm_args* a, cudaStream_t st, const DgradC
             al = std::min(al, ptr_align(ep.out, ep.ldo));
             if (ep.aux) { ok = ok && ep.aux_dtype == AVEC_BF16; al = std::min(al, ptr_align(ep.aux, ep.ldaux)); }
             if (ep.out2) { ok = ok && ep.out2_dtype == AVEC_BF16 && ep.kind == AVEC_EPI_SWISH; al = std::min(al, ptr_align(ep.out2, ep.ldo2)); }
-            if (ep.colstats) ok = ok && ep.kind == AVEC_EPI_LINEAR && (reinterpret_cast<uintptr_t>(ep.colstats) % 16) == 0;
+            if (ep.colstats) ok = ok && a->N % 8 == 0 && ep.kind == AVEC_EPI_LINEAR && (reinterpret_cast<uintptr_t>(ep.colstats) % 16) == 0;
             if ((ep.kind == AVEC_EPI_RESIDUAL || ep.kind == AVEC_EPI_DSWISH) && !ep.aux) ok = false;
         }
         p.epi_fast = ok && al >= 8 ? (al >= 16 ? 2 : 1) : 0;

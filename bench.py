@@ -563,7 +563,7 @@ def profile_gemm(step_fn, ops):
         ops._gemm = hooked
         ops.stem3d_fwd, ops.stem3d_wgrad = timed_stem(stem_orig[0], "stem3d fwd"), timed_stem(stem_orig[1], "stem3d wgrad")
         try:
-            torch.cuda._sleep(int(0.05 * 1.9e9))
+            torch.cuda._sleep(int(0.4 * 1.9e9))      # ~0.4 s head start: the eager step's host work (~0.15 s) never catches up with the GPU
             step_fn()
             torch.cuda.synchronize()
         finally:
