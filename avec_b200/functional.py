@@ -33,7 +33,25 @@ def set_compute_dtype(dt):
     invalidate_weights()
 
 
+_FORCED_DTYPE = None      # set while a Function.backward runs: the dtype its forward computed in
+
+
+def _bwd(fn):
+    """backward of a Function whose forward recorded ctx.cdt: weight copies are looked up in the FORWARD's compute dtype (with
+    set_compute_dtype("auto") the ambient autocast state is gone by the time autograd runs the backward, model.py:356-367)"""
+    def wrapper(ctx, *grads):
+        global _FORCED_DTYPE
+        prev, _FORCED_DTYPE = _FORCED_DTYPE, getattr(ctx, "cdt", None)
+        try:
+            return fn(ctx, *grads)
+        finally:
+            _FORCED_DTYPE = prev
+    return wrapper
+
+
 def compute_dtype():
+    if _FORCED_DTYPE is not None:
+        return _FORCED_DTYPE
     if _COMPUTE_DTYPE == "auto":
         return torch.bfloat16 if torch.is_autocast_enabled() else torch.float32
     return _COMPUTE_DTYPE
@@ -180,6 +198,7 @@ class FFNFn(Function):
 
     @staticmethod
     def forward(ctx, x, ln_w, ln_b, w1, b1, w2, b2, p_in=0.0, p_out=0.0):
+        ctx.cdt = compute_dtype()
         B, T, D = x.shape
         x = _c(x)
         xn, mean, rstd = ops.layernorm_fwd(x, ln_w, ln_b)
@@ -199,6 +218,7 @@ class FFNFn(Function):
         return y.view(B, T, D)
 
     @staticmethod
+    @_bwd
     def backward(ctx, dy):
         x, ln_w, mean, rstd, xn, pre, h, w1, w2 = ctx.saved_tensors
         p_in, s_in, p_out, s_out = ctx.drop
@@ -231,6 +251,7 @@ class AttentionFn(Function):
 
     @staticmethod
     def forward(ctx, x, ln_w, ln_b, wq, bq, wk, bk, wv, bv, wo, bo, wp, bp, pe, klen, H, P, p_drop=0.0):
+        ctx.cdt = compute_dtype()
         B, T, D = x.shape
         d = D // H
         x = _c(x)
@@ -278,6 +299,7 @@ class AttentionFn(Function):
         return y
 
     @staticmethod
+    @_bwd
     def backward(ctx, dy):
         x, ln_w, mean, rstd, xp, qkv, e, aux, o, pe, wq, wk, wv, wo, wp, klen_p = ctx.saved_tensors
         H, P, tc = ctx.H, ctx.P, ctx.tc
@@ -323,6 +345,7 @@ class GroupedAttentionFn(Function):
 
     @staticmethod
     def forward(ctx, x, ln_w, ln_b, wq, bq, wk, bk, wv, bv, wo, bo, wp, bp, u, v, pe, klen, H, G, p_drop=0.0):
+        ctx.cdt = compute_dtype()
         B, T, D = x.shape
         Tn = -(-T // G)
         d = G * D // H
@@ -349,6 +372,7 @@ class GroupedAttentionFn(Function):
         return y
 
     @staticmethod
+    @_bwd
     def backward(ctx, dy):
         x, ln_w, mean, rstd, xn, qkv, e, probs, o, pe, wq, wk, wv, wo, wp, u, v = ctx.saved_tensors
         H, G = ctx.H, ctx.G
@@ -380,6 +404,7 @@ class ConvModuleFn(Function):
 
     @staticmethod
     def forward(ctx, x, ln_w, ln_b, w1, b1, wd, bd, bn_w, bn_b, rm, rv, w3, b3, wr, br, stride, training, momentum, p_drop=0.0):
+        ctx.cdt = compute_dtype()
         B, T, D = x.shape
         De = w3.shape[0]
         ks = wd.shape[-1]
@@ -413,6 +438,7 @@ class ConvModuleFn(Function):
         return y
 
     @staticmethod
+    @_bwd
     def backward(ctx, dy):
         x, ln_w, mean, rstd, xn, pre, u, bnbuf, v, xs, w1, wd, bn_w, w3, wr = ctx.saved_tensors
         if not ctx.training:
@@ -450,12 +476,14 @@ class DropoutFn(Function):
 
     @staticmethod
     def forward(ctx, x, p):
+        ctx.cdt = compute_dtype()
         site = ops.RNG.next_site()
         ctx.drop = (p, site)
         ctx.rng = ops.RNG.cur(x.device)
         return ops.dropout_rng(ctx.rng, _c(x), p, site)
 
     @staticmethod
+    @_bwd
     def backward(ctx, dy):
         p, site = ctx.drop
         return ops.dropout_rng(ctx.rng, _c(dy), p, site), None
@@ -464,12 +492,14 @@ class DropoutFn(Function):
 class LayerNormFn(Function):
     @staticmethod
     def forward(ctx, x, w, b):
+        ctx.cdt = compute_dtype()
         x = _c(x)
         y, mean, rstd = ops.layernorm_fwd(x, w, b)
         ctx.save_for_backward(x, w, mean, rstd)
         return y
 
     @staticmethod
+    @_bwd
     def backward(ctx, dy):
         x, w, mean, rstd = ctx.saved_tensors
         dx, dg, db = ops.layernorm_bwd(_c(dy), x, w, mean, rstd)
@@ -482,6 +512,7 @@ class InterCTCFn(Function):
 
     @staticmethod
     def forward(ctx, x, w1, b1, w2, b2):
+        ctx.cdt = compute_dtype()
         B, T, D = x.shape
         x = _c(x)
         x2 = x.view(B * T, D)
@@ -492,6 +523,7 @@ class InterCTCFn(Function):
         return y.view(B, T, D), logits.view(B, T, -1)
 
     @staticmethod
+    @_bwd
     def backward(ctx, dy, dlogits):
         x, p, w1, w2 = ctx.saved_tensors
         B, T, D = x.shape
@@ -514,6 +546,7 @@ class LinearFn(Function):
 
     @staticmethod
     def forward(ctx, x, w, b, out_fp32, wl):
+        ctx.cdt = compute_dtype()
         shp = x.shape
         x2 = _c(x).view(-1, shp[-1])
         wk = wc(w, wl[0], wl[1]) if wl is not None else wc(w)
@@ -523,6 +556,7 @@ class LinearFn(Function):
         return y.view(*shp[:-1], w.shape[0])
 
     @staticmethod
+    @_bwd
     def backward(ctx, dy):
         x2, w = ctx.saved_tensors
         wl = ctx.wl
@@ -543,6 +577,7 @@ class MLPFn(Function):
 
     @staticmethod
     def forward(ctx, x, w1, b1, w2, b2):
+        ctx.cdt = compute_dtype()
         shp = x.shape
         x2 = _c(x).view(-1, shp[-1])
         h, pre = ops.linear_fwd(x2, wc(w1), b1, L.EPI_SWISH, want_pre=True)
@@ -552,6 +587,7 @@ class MLPFn(Function):
         return y.view(*shp[:-1], w2.shape[0])
 
     @staticmethod
+    @_bwd
     def backward(ctx, dy):
         x2, pre, h, w1, w2 = ctx.saved_tensors
         dy2 = _c(dy).view(-1, w2.shape[0])
@@ -576,6 +612,7 @@ class AudioStemFn(Function):
 
     @staticmethod
     def forward(ctx, wave, fb, cw, cb, bn_w, bn_b, rm, rv, training, momentum, spec=None, mel_len=None):
+        ctx.cdt = compute_dtype()
         B = wave.shape[0]
         mel = ops.stft_mel_log(_c(wave.float()), fb, layout=0)
         if spec is not None:      # SpecAugment (mF, F, mT, pS) on the fp32 log-mel, in place (networks.py:423-424)
@@ -596,6 +633,7 @@ class AudioStemFn(Function):
         return v.view(B, g.Ho, g.Wo * Co)
 
     @staticmethod
+    @_bwd
     def backward(ctx, dv):
         melc, u, bnbuf, bn_w, cw = ctx.saved_tensors
         if not ctx.training:
@@ -615,6 +653,7 @@ class VideoStemFn(Function):
 
     @staticmethod
     def forward(ctx, video, cw, cb, bn_w, bn_b, rm, rv, training, momentum):
+        ctx.cdt = compute_dtype()
         B, T, H, W = video.shape[0], video.shape[1], video.shape[2], video.shape[3]
         xc = ops.convert(_c(video.float()).view(B * T * H, W), compute_dtype()).view(B, T, H, W, 1)
         Co = cw.shape[0]
@@ -641,6 +680,7 @@ class VideoStemFn(Function):
         return y
 
     @staticmethod
+    @_bwd
     def backward(ctx, dy):
         col, u, bnbuf, bn_w, cw, idx = ctx.saved_tensors
         if not ctx.training:
@@ -678,6 +718,7 @@ class ResBlockFn(Function):
 
     @staticmethod
     def forward(ctx, x, w1, g1w, g1b, rm1, rv1, w2, g2w, g2b, rm2, rv2, wr, grw, grb, rmr, rvr, stride, training, momentum):
+        ctx.cdt = compute_dtype()
         N, H, W, Ci = x.shape
         Co = w1.shape[0]
         x = _c(x)
@@ -711,6 +752,7 @@ class ResBlockFn(Function):
         return y.view(N, ga.Ho, ga.Wo, Co)
 
     @staticmethod
+    @_bwd
     def backward(ctx, dy):
         x, u1, bn1, a1, u2, bn2, ur, bnr, r, w1, g1w, w2, g2w, wr, grw = ctx.saved_tensors
         if not ctx.training:
@@ -739,11 +781,13 @@ class AvgPoolFn(Function):
 
     @staticmethod
     def forward(ctx, x):
+        ctx.cdt = compute_dtype()
         N, H, W, Cn = x.shape
         ctx.shp = x.shape
         return ops.avgpool_fwd(_c(x), N, H * W, Cn)
 
     @staticmethod
+    @_bwd
     def backward(ctx, dy):
         N, H, W, Cn = ctx.shp
         return ops.avgpool_bwd(_c(dy), N, H * W, Cn).view(ctx.shp)
@@ -754,6 +798,7 @@ class CTCFn(Function):
 
     @staticmethod
     def forward(ctx, logits, labels, in_len, lab_len, blank, zero_infinity):
+        ctx.cdt = compute_dtype()
         lg = _c(logits.float())
         dev = lg.device
         lab = _c(labels.to(device=dev, dtype=torch.long))
@@ -764,6 +809,7 @@ class CTCFn(Function):
         return nll
 
     @staticmethod
+    @_bwd
     def backward(ctx, gout):
         (grad,) = ctx.saved_tensors
         return grad * gout.view(-1, 1, 1), None, None, None, None, None

@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--dropout", type=float, default=0.1, help="0.1 = the reference's training graph (dropout at every site + "
                     "SpecAugment, networks.py:327,347-353); 0 = the deterministic parity graph (dropout off, SpecAugment bypassed)")
     ap.add_argument("--graph", type=int, default=1, help="capture forward+backward in one CUDA graph (falls back to eager if capture fails)")
+    ap.add_argument("--sync-bn", type=int, default=0, help="N > 1: the reference's SyncBatchNorm default (model.py:59-61) instead of local statistics")
+    ap.add_argument("--bucket-mb", type=int, default=32, help="N > 1: gradient all-reduce bucket size (overlapped with the backward)")
     ap.add_argument("--parity-check", type=int, default=1, help="compare the benchmarked model / batch with the fp32 oracle on the same GPU (rank 0)")
     ap.add_argument("--incumbent", type=int, default=1, help="time the reference graph as eager bf16-autocast PyTorch on the same GPU (N=1)")
     ap.add_argument("--shape-table", default="", help="write the per-shape tcgen05 launch table (ms, TFLOP/s) to this JSON file")
@@ -339,8 +341,16 @@ def main():
                                    weight_decay=1e-6, grad_max_norm=5.0)
         opt.flat()   # parameters become views of the flat buffer BEFORE anything is captured
 
+    # N > 1: gradients are all-reduced bucket by bucket from inside the backward (hooks), on a communication stream
+    buckets = None
+    if world > 1:
+        if args.sync_bn:
+            ops.set_sync_batchnorm(True)
+        f = opt.flat() if opt is not None else None
+        buckets = parallel.GradientBuckets(params, bucket_bytes=args.bucket_mb << 20, flat=f["g"] if f else None, offsets=f["offs"] if f else None)
+
     def fwd_bwd(d):
-        """forward + 6 CTC losses + backward; leaves the gradients in p.grad"""
+        """forward + 6 CTC losses + backward (+ the overlapped gradient all-reduce); leaves the gradients in p.grad"""
         for p in params:
             p.grad = None
         # every training step starts from weights the optimizer has just changed: the compute-dtype (bf16, kernel-layout) copies are
@@ -353,13 +363,14 @@ def main():
         else:
             loss = sum(v[0].float().mean() for v in outputs.values())
         loss.backward()
+        if buckets is not None:
+            buckets.finish()
         return loss.detach()
 
     static_grads = None   # gradient tensors the captured graph writes on every replay
 
     def allreduce_grads():
-        if world > 1:
-            parallel.allreduce_gradients(params, world, grads=static_grads if graph is not None else None)
+        pass   # done inside fwd_bwd (GradientBuckets)
 
     graph, static_loss = None, None
 
@@ -371,7 +382,7 @@ def main():
             loss = fwd_bwd(d)
         allreduce_grads()
         if opt is not None:
-            opt.step(grads=static_grads if (graph is not None and d is resident and world == 1) else None)
+            opt.step(grads=static_grads if (graph is not None and d is resident) else None)
         return loss
 
     def sync():
@@ -482,7 +493,8 @@ def main():
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": f"{args.model} EffConfInterCTC fwd+bwd (train mode, {aug}, 6 CTC heads), per-GPU batch {B}, "
                                    f"64000 audio samples + {101 if args.model == 'AV' else 100}x88x88 video",
-                       "global_batch": world * B, "parallelism": f"dp{world}", "bn": "local batch statistics", "optimizer": args.optimizer,
+                       "global_batch": world * B, "parallelism": f"dp{world}", "bn": "SyncBatchNorm (all-reduced statistics)" if (world > 1 and args.sync_bn) else "local batch statistics", "optimizer": args.optimizer,
+                       "allreduce": (f"{len(buckets.buckets)} fp32 buckets of <= {args.bucket_mb} MB, launched from backward hooks on a communication stream" if buckets is not None else None),
                        "streams": (2 if (args.model == "AV" and args.overlap) else 1), "loss": args.loss, "cuda_graph": bool(use_graph),
                        "weights": "fp32 masters converted to bf16 kernel layout inside every timed step",
                        "l2": "inputs+activations per step (>1 GB) exceed the 126 MB L2; no flush needed",

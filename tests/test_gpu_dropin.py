@@ -95,6 +95,7 @@ def test_reference_model_runtime_on_patched_encoders(tmp_path):
         assert int(fast.model_step) == 2 and site_counts[0] == site_counts[1] > 100     # sites restart every forward
         assert int(ops.RNG.get(DEV)[1]) >= 2                                            # the RNG step advanced per forward
         assert not torch.equal(w0, fast.encoder.head.weight)
+        assert all(bool(torch.isfinite(q).all()) for q in fast.parameters()), "non-finite parameter after the fused optimizer steps"
         # checkpoint round trip through the reference's save / load
         path = str(tmp_path / "checkpoints_epoch_1_step_2.ckpt")
         fast.save(path, save_optimizer=True)

@@ -38,8 +38,19 @@ def _worker(rank, world, port, out):
         y.square().mean().backward()
         params = [v for v in sd.values() if v.requires_grad]
         local = [p.grad.clone() for p in params]
-        n = parallel.allreduce_gradients(params, world, bucket_bytes=1 << 20)   # several buckets
-        torch.save({"w0": w0, "local": local, "reduced": [p.grad.clone() for p in params], "n": n}, os.path.join(out, f"r{rank}.pt"))
+        n = parallel.allreduce_gradients((p for p in params), world, bucket_bytes=1 << 20)   # a generator, several buckets
+        reduced = [p.grad.clone() for p in params]
+        # the overlapped reducer: hooks fire during backward, buckets are all-reduced as they fill up; one parameter gets no gradient
+        for p in params:
+            p.grad = None
+        extra = torch.zeros(11, requires_grad=True)
+        gb = parallel.GradientBuckets(params + [extra], bucket_bytes=1 << 20)
+        y2, _, _ = restate.conformer_block(x, sd, torch.tensor([7, 5]), 4, 3, 1, True)
+        y2.square().mean().backward()
+        views = gb.finish()
+        assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(params + [extra], views))
+        torch.save({"w0": w0, "local": local, "reduced": reduced, "n": n, "overlapped": [p.grad.clone() for p in params],
+                    "extra": extra.grad.clone(), "nbuckets": len(gb.buckets)}, os.path.join(out, f"r{rank}.pt"))
     finally:
         dist.destroy_process_group()
 
@@ -54,3 +65,6 @@ def test_gradient_allreduce_and_broadcast_world2(tmp_path):
     for l0, l1, g0, g1 in zip(r[0]["local"], r[1]["local"], r[0]["reduced"], r[1]["reduced"]):
         mean = (l0 + l1) / 2
         assert torch.allclose(g0, mean, rtol=1e-6, atol=1e-7) and torch.equal(g0, g1)
+    assert r[0]["nbuckets"] > 2 and float(r[0]["extra"].abs().max()) == 0.0
+    for g0, o0, o1 in zip(r[0]["reduced"], r[0]["overlapped"], r[1]["overlapped"]):
+        assert torch.allclose(o0, g0, rtol=1e-6, atol=1e-7) and torch.equal(o0, o1)
