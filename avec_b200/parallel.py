@@ -61,7 +61,10 @@ class GradientBuckets:
     while the backward keeps running on the compute stream(s).  `finish()` joins the communication stream and re-points every
     `p.grad` at its (averaged) bucket view - the fused optimizer can take the flat buffer as is.  Everything (hooks, event waits,
     NCCL calls) is capturable in a CUDA graph: under capture the buckets become parallel branches of the graph.
-    With `flat` (a preallocated fp32 buffer, e.g. the fused Adam's gradient buffer, and `offsets`) the buckets are slices of it."""
+    With `flat` (a preallocated fp32 buffer, e.g. the fused Adam's gradient buffer, and `offsets`) the buckets are slices of it.
+    Measured on 2 x B200 (AV, per-GPU batch 64, profiles/r02_multigpu.md): ONE bucket reduced right after the backward costs
+    +0.8 ms per step (47.1 vs 46.3 ms on one GPU); 32 MB buckets overlapped with the backward cost +4.0 ms, because the NCCL
+    kernels occupy SMs that the persistent one-CTA-per-SM conv / GEMM kernels are sized for - bench.py therefore uses one bucket."""
 
     def __init__(self, params, bucket_bytes=32 << 20, group=None, flat=None, offsets=None):
         self.params = [p for p in params if p.requires_grad]

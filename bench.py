@@ -46,7 +46,9 @@ def parse():
                     "SpecAugment, networks.py:327,347-353); 0 = the deterministic parity graph (dropout off, SpecAugment bypassed)")
     ap.add_argument("--graph", type=int, default=1, help="capture forward+backward in one CUDA graph (falls back to eager if capture fails)")
     ap.add_argument("--sync-bn", type=int, default=0, help="N > 1: the reference's SyncBatchNorm default (model.py:59-61) instead of local statistics")
-    ap.add_argument("--bucket-mb", type=int, default=32, help="N > 1: gradient all-reduce bucket size (overlapped with the backward)")
+    ap.add_argument("--bucket-mb", type=int, default=4096, help="N > 1: gradient all-reduce bucket size.  Default = ONE bucket, reduced right after the "
+                    "backward inside the captured graph (2 x B200: 47.1 ms / step); 32 MB buckets overlapped with the backward measured SLOWER "
+                    "(50.3 ms): the NCCL kernels take SMs away from the persistent one-CTA-per-SM conv / GEMM kernels (profiles/r02_multigpu.md)")
     ap.add_argument("--parity-check", type=int, default=1, help="compare the benchmarked model / batch with the fp32 oracle on the same GPU (rank 0)")
     ap.add_argument("--incumbent", type=int, default=1, help="time the reference graph as eager bf16-autocast PyTorch on the same GPU (N=1)")
     ap.add_argument("--shape-table", default="", help="write the per-shape tcgen05 launch table (ms, TFLOP/s) to this JSON file")
@@ -346,6 +348,8 @@ def main():
     if world > 1:
         if args.sync_bn:
             ops.set_sync_batchnorm(True)
+            if args.model == "AV":
+                model.encoder.overlap_branches = False   # the statistics all-reduces of both branches share one communicator: single stream
         f = opt.flat() if opt is not None else None
         buckets = parallel.GradientBuckets(params, bucket_bytes=args.bucket_mb << 20, flat=f["g"] if f else None, offsets=f["offs"] if f else None)
 
@@ -494,7 +498,7 @@ def main():
             "config": {"workload": f"{args.model} EffConfInterCTC fwd+bwd (train mode, {aug}, 6 CTC heads), per-GPU batch {B}, "
                                    f"64000 audio samples + {101 if args.model == 'AV' else 100}x88x88 video",
                        "global_batch": world * B, "parallelism": f"dp{world}", "bn": "SyncBatchNorm (all-reduced statistics)" if (world > 1 and args.sync_bn) else "local batch statistics", "optimizer": args.optimizer,
-                       "allreduce": (f"{len(buckets.buckets)} fp32 buckets of <= {args.bucket_mb} MB, launched from backward hooks on a communication stream" if buckets is not None else None),
+                       "allreduce": (f"{len(buckets.buckets)} fp32 bucket(s), NCCL all-reduce (AVG) launched from backward hooks on a communication stream, captured in the CUDA graph" if buckets is not None else None),
                        "streams": (2 if (args.model == "AV" and args.overlap) else 1), "loss": args.loss, "cuda_graph": bool(use_graph),
                        "weights": "fp32 masters converted to bf16 kernel layout inside every timed step",
                        "l2": "inputs+activations per step (>1 GB) exceed the 126 MB L2; no flush needed",

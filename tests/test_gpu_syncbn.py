@@ -90,5 +90,7 @@ def test_sync_batchnorm_two_ranks_equal_full_batch(tmp_path):
     for kind, e in res.items():
         assert e["y"] < 2e-4 * max(1.0, e["scale"]), (kind, e)
         assert e["dx"] < 2e-4 * max(1.0, e["scale"]), (kind, e)
-        assert e["grads"] < 1e-3, (kind, e)
+        # parameter gradients are fp32 atomic sums over the batch (order varies run to run): the analytically-zero ones (key / position
+        # biases, biases in front of a BatchNorm) sit at the 1e-6 noise floor, which the +1e-3 denominator turns into a few 1e-3
+        assert e["grads"] < 5e-3, (kind, e)
         assert e["buffers"] < 1e-5, (kind, e)
