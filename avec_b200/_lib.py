@@ -37,6 +37,11 @@ class GemmArgs(C.Structure):
     ]
 
 
+class CopyJob(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("start", C.c_longlong), ("ss", C.c_longlong * 4), ("ds", C.c_longlong * 4),
+                ("n", C.c_int * 4), ("src_dtype", C.c_int), ("dst_dtype", C.c_int)]
+
+
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 
 # name -> argtypes (every symbol include/avec_b200.h declares; tests/test_abi.py checks the two lists agree)
@@ -89,6 +94,8 @@ PROTOTYPES = {
     "avec_ctc_greedy_decode": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _P], _I),
     "avec_sumsq": ([_P, _L, _P, _P], _I),
     "avec_adam_step": ([_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _F, _F, _F, _F, _P, _P, _P, _P], _I),
+    "avec_convert_multi": ([_P, _I, _L, _P], _I),
+    "avec_unpad_heads": ([_P, _P, _L, _I, _I, _L, _P], _I),
     "avec_convert": ([_P, _I, _L, _P, _I, _L, _L, _I, _P], _I),
 }
 

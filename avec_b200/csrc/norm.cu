@@ -1092,6 +1092,52 @@ extern "C" int avec_zero_upsample(const void* in, void* out, int N, int Ho, int 
     return AVEC_OK;
 }
 
+// ---- multi-tensor strided copy / conversion: every per-step weight re-layout of a model in ONE launch ----------------------
+// job j copies a logical 4-d index space (n0, n1, n2, n3) from src (fp32 or bf16, element strides ss) to dst (fp32 or bf16,
+// element strides ds); `start` is the running element count (exclusive prefix sum), so a thread finds its job by binary search.
+__global__ void __launch_bounds__(256) convert_multi_kernel(const avec_copy_job* __restrict__ jobs, int njobs, long long total) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int lo = 0, hi = njobs - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (jobs[mid].start <= i) lo = mid; else hi = mid - 1;
+        }
+        const avec_copy_job& j = jobs[lo];
+        long long r = i - j.start;
+        const int i3 = (int)(r % j.n[3]); r /= j.n[3];
+        const int i2 = (int)(r % j.n[2]); r /= j.n[2];
+        const int i1 = (int)(r % j.n[1]);
+        const int i0 = (int)(r / j.n[1]);
+        const long long so = i0 * j.ss[0] + i1 * j.ss[1] + i2 * j.ss[2] + i3 * j.ss[3];
+        const long long d_o = i0 * j.ds[0] + i1 * j.ds[1] + i2 * j.ds[2] + i3 * j.ds[3];
+        const float v = j.src_dtype == AVEC_F32 ? reinterpret_cast<const float*>(j.src)[so] : __bfloat162float(reinterpret_cast<const bf16*>(j.src)[so]);
+        if (j.dst_dtype == AVEC_F32) reinterpret_cast<float*>(j.dst)[d_o] = v;
+        else reinterpret_cast<bf16*>(j.dst)[d_o] = __float2bfloat16_rn(v);
+    }
+}
+
+extern "C" int avec_convert_multi(const avec_copy_job* jobs_dev, int njobs, long long total, avec_stream_t stream) {
+    AVEC_CHECK_ARG(jobs_dev && njobs > 0 && total > 0);
+    convert_multi_kernel<<<ew_blocks(total), 256, 0, as_stream(stream)>>>(jobs_dev, njobs, total);
+    AVEC_LAUNCH_CHECK();
+    return AVEC_OK;
+}
+
+__global__ void __launch_bounds__(256) unpad_heads_kernel(const float* __restrict__ src, float* __restrict__ dst, int d, int dp, long long K, long long total) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long c = i % K, row = i / K;
+        const long long g = row / d, r = row - g * d;
+        dst[i] = src[(g * dp + r) * K + c];
+    }
+}
+extern "C" int avec_unpad_heads(const float* src, float* dst, long long groups, int d, int dp, long long K, avec_stream_t stream) {
+    AVEC_CHECK_ARG(src && dst && groups > 0 && d > 0 && dp >= d && K > 0);
+    const long long total = groups * d * K;
+    unpad_heads_kernel<<<ew_blocks(total), 256, 0, as_stream(stream)>>>(src, dst, d, dp, K, total);
+    AVEC_LAUNCH_CHECK();
+    return AVEC_OK;
+}
+
 extern "C" int avec_convert(const void* src, int src_dtype, long long lds, void* dst, int dst_dtype, long long ldd, long long rows,
                             int C, avec_stream_t stream) {
     AVEC_CHECK_ARG(src && dst && rows > 0 && C > 0);

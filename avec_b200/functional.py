@@ -18,6 +18,7 @@ from torch.autograd import Function
 
 from . import _lib as L
 from . import ops
+from . import weights as W
 
 # ------------------------------------------------------------------------------------------------------------- config
 _COMPUTE_DTYPE = torch.bfloat16
@@ -57,18 +58,13 @@ def compute_dtype():
     return _COMPUTE_DTYPE
 
 
-# weight cache: compute-dtype, kernel-layout copies of the fp32 master parameters.  An entry is valid while the parameter's
-# torch version counter AND the library's weight epoch are unchanged; the fused optimizer (which updates the flat parameter
-# buffer from a raw kernel, invisible to the version counter) bumps the epoch after every step.
-_wcache = {}
-_wepoch = 0
-
-
+# Compute-dtype, kernel-layout copies of the fp32 master parameters live in avec_b200.weights.PLAN: persistent buffers refreshed
+# by ONE multi-tensor launch per step.  They are stale after invalidate_weights() - called by the fused optimizer (which updates
+# the flat parameter buffer from a raw kernel, invisible to torch's version counters), by set_compute_dtype and by bench.py at
+# the start of every timed step; parameters changed through torch are detected by version counter / storage pointer.
 def invalidate_weights():
-    """drop every cached compute-dtype weight copy (called by avec_b200.nnet.optimizers.Adam.step and load_state_dict hooks)"""
-    global _wepoch
-    _wepoch += 1
-    _wcache.clear()
+    """mark every cached compute-dtype weight copy stale (avec_b200.nnet.optimizers.Adam.step, checkpoint loads, ...)"""
+    W.PLAN.invalidate()
 
 
 def new_step(arena_numel=0, device=None, advance_rng=False):
@@ -108,6 +104,8 @@ class forward_scope:
                     pass
             on_gpu = self.device is not None and self.device.type == "cuda"
             new_step(numel if on_gpu else 0, self.device, advance_rng=bool(m.training))
+            if on_gpu and W.PLAN.stale():
+                W.PLAN.refresh_all()      # all weight layouts in one launch, on the caller's stream, before any branch forks off
         _depth += 1
         return self
 
@@ -125,71 +123,46 @@ def manual_seed(seed):
     ops.RNG.manual_seed(seed)
 
 
-def _wvalid(hit, ver):
-    return hit is not None and hit[0] == ver and hit[2] == _wepoch
-
-
 def wc(param, tag="plain", fn=None, pad=True):
-    """compute-dtype copy of a parameter in the layout a kernel wants (fn: fp32 tensor -> 2-d fp32 view/tensor).  pad: GEMM
-    operands get the TMA-able row pitch of ops.row_pitch (a [N, K] view of a wider allocation); kernels that index the weight
-    as a dense array pass pad=False."""
-    dt = compute_dtype()
-    key = (id(param), tag, dt)
-    hit = _wcache.get(key)
-    ver = (param._version, param.data_ptr())
-    if _wvalid(hit, ver):
-        return hit[1]
-    src = param.detach()
-    src = fn(src) if fn is not None else src.reshape(src.shape[0], -1)
-    out = ops.convert(src, dt, pad=pad)
-    _wcache[key] = (ver, out, _wepoch)
-    return out
+    """compute-dtype copy of a parameter in the layout a kernel wants; fn: parameter -> VIEW of it (<= 4-d) whose row-major
+    order is the [N, K] layout (default: reshape to [N, -1]).  pad: GEMM operands get the TMA-able row pitch of ops.row_pitch;
+    kernels that index the weight as a dense array pass pad=False."""
+    return W.PLAN.layout((param,), (tag, pad), W.b_plain(fn, pad), compute_dtype())
 
 
 def wc_cat(params, tag):
-    dt = compute_dtype()
-    key = (tuple(id(p) for p in params), tag, dt)
-    ver = tuple((p._version, p.data_ptr()) for p in params)
-    hit = _wcache.get(key)
-    if _wvalid(hit, ver):
-        return hit[1]
-    src = torch.cat([p.detach().reshape(p.shape[0], -1) for p in params], dim=0)
-    out = ops.convert(src, dt, pad=True) if src.dim() == 2 and src.shape[1] > 1 else src
-    _wcache[key] = (ver, out, _wepoch)
-    return out
+    """parameters stacked along rows ([sum N_i, K] in the compute dtype; 1-d parameters: fp32 [sum N_i])"""
+    if params[0].dim() == 1:
+        return W.PLAN.layout(tuple(params), tag, W.b_cat(pad=False), torch.float32).reshape(-1)
+    return W.PLAN.layout(tuple(params), tag, W.b_cat(), compute_dtype())
 
 
-def wc_fn(params, tag, fn, convert=True):
-    """cached fn(*params) (an fp32 2-d / 1-d tensor in kernel layout), converted to the compute dtype when `convert`"""
-    dt = compute_dtype() if convert else torch.float32
-    key = (tuple(id(p) for p in params), tag, dt)
-    ver = tuple((p._version, p.data_ptr()) for p in params)
-    hit = _wcache.get(key)
-    if _wvalid(hit, ver):
-        return hit[1]
-    src = fn(*[p.detach() for p in params])
-    out = ops.convert(src, dt, pad=True) if convert else src.contiguous()
-    _wcache[key] = (ver, out, _wepoch)
-    return out
+def wc_heads(params, tag, H, d, dp, cols=False):
+    """padded-heads layout of the tcgen05 attention kernel: [H*d, K] weights (or [H*d] biases) stacked along rows with every head
+    zero-padded to dp rows; cols=True: an [N, H*d] weight with every head zero-padded to dp COLUMNS (the output projection)"""
+    if cols:
+        return W.PLAN.layout(tuple(params), (tag, dp), W.b_heads_cols(H, d, dp), compute_dtype())
+    if params[0].dim() == 1:
+        return W.PLAN.layout(tuple(params), (tag, dp), W.b_heads_rows(H, d, dp, pad=False), torch.float32).reshape(-1)
+    return W.PLAN.layout(tuple(params), (tag, dp), W.b_heads_rows(H, d, dp), compute_dtype())
 
 
 def _c(t):
     return t if t.is_contiguous() else t.contiguous()
 
 
-# ---- padded-heads layout of the tcgen05 attention kernel: head h owns columns [h*dp, h*dp + d) of a dp-wide block
-def _pad_rows(w, H, d, dp):
-    """[H*d, ...] -> [H*dp, ...] (zero rows appended to every head)"""
-    rest = w.shape[1:]
-    out = torch.zeros((H, dp) + tuple(rest), device=w.device, dtype=w.dtype)
-    out[:, :d] = w.reshape((H, d) + tuple(rest))
-    return out.reshape((H * dp,) + tuple(rest))
-
-
 def _unpad_rows(w, H, d, dp):
-    """[n*H*dp, ...] -> [n*H*d, ...]"""
-    rest = w.shape[1:]
-    return w.reshape((-1, H, dp) + tuple(rest))[:, :, :d].reshape((-1,) + tuple(rest))
+    """[n*H*dp, ...] fp32 gradient in the padded-heads layout -> [n*H*d, ...] (one launch; a view when dp == d)"""
+    if dp == d:
+        return w
+    return ops.unpad_heads(w, H, d, dp, cols=False)
+
+
+def _unpad_cols(w, H, d, dp):
+    """[N, H*dp] -> [N, H*d]"""
+    if dp == d:
+        return w
+    return ops.unpad_heads(w, H, d, dp, cols=True)
 
 
 # --------------------------------------------------------------------------------------------------------------- FFN
@@ -266,17 +239,17 @@ class AttentionFn(Function):
         else:
             klen_p, qlen = klen, Tp
         if tc:
-            wqkv = wc_fn((wq, wk, wv), "qkv_tc", lambda a, b, c: torch.cat([_pad_rows(t, H, d, dp) for t in (a, b, c)], dim=0))
-            bqkv = wc_fn((bq, bk, bv), "bqkv_tc", lambda a, b, c: torch.cat([_pad_rows(t, H, d, dp) for t in (a, b, c)], dim=0), convert=False)
-            wpp = wc_fn((wp,), "pos_tc", lambda a: _pad_rows(a, H, d, dp))
-            bpp = wc_fn((bp,), "bpos_tc", lambda a: _pad_rows(a, H, d, dp), convert=False)
-            wop = wc_fn((wo,), "out_tc", lambda a: _pad_rows(a.t(), H, d, dp).t())
+            wqkv = wc_heads((wq, wk, wv), "qkv_tc", H, d, dp)
+            bqkv = wc_heads((bq, bk, bv), "bqkv_tc", H, d, dp)
+            wpp = wc_heads((wp,), "pos_tc", H, d, dp)
+            bpp = wc_heads((bp,), "bpos_tc", H, d, dp)
+            wop = wc_heads((wo,), "out_tc", H, d, dp, cols=True)
             qkv = ops.linear_fwd(xp.view(B * Tp, D), wqkv, bqkv)
             e = ops.linear_fwd(pe, wpp, bpp)
             o, aux = ops.relpos_attn_tc_fwd(qkv, e, klen_p, qlen, B, Tp, H, d, dp)
         else:
             wqkv = wc_cat((wq, wk, wv), "qkv")
-            bqkv = wc_cat((bq, bk, bv), "bqkv").reshape(-1)
+            bqkv = wc_cat((bq, bk, bv), "bqkv")
             wop = wc(wo)
             qkv = ops.linear_fwd(xp.view(B * Tp, D), wqkv, bqkv)
             e = ops.linear_fwd(pe, wc(wp), bp)
@@ -313,10 +286,10 @@ class AttentionFn(Function):
         dbo = ops.colsum(dproj)
         if tc:
             dp = ops.attn_head_pad(d)
-            wqkv = wc_fn((wq, wk, wv), "qkv_tc", lambda a, b, c: torch.cat([_pad_rows(t, H, d, dp) for t in (a, b, c)], dim=0))
-            wop = wc_fn((wo,), "out_tc", lambda a: _pad_rows(a.t(), H, d, dp).t())
+            wqkv = wc_heads((wq, wk, wv), "qkv_tc", H, d, dp)
+            wop = wc_heads((wo,), "out_tc", H, d, dp, cols=True)
             do = ops.linear_dgrad(dproj, wop)
-            dwo = _unpad_rows(ops.linear_wgrad(dproj, o).t(), H, d, dp).t()
+            dwo = _unpad_cols(ops.linear_wgrad(dproj, o), H, d, dp)
             dqkv, de = ops.relpos_attn_tc_bwd(do, qkv, e, o, aux, klen_p, ctx.qlen, B, Tp, H, d, dp)
             dwp = _unpad_rows(ops.linear_wgrad(ops.convert(de, x.dtype), pe), H, d, dp)
             dbp = _unpad_rows(ops.colsum(de), H, d, dp)
@@ -353,7 +326,7 @@ class GroupedAttentionFn(Function):
         ctx.rng = ops.RNG.cur(x.device)
         xn, mean, rstd = ops.layernorm_fwd(x, ln_w, ln_b)
         wqkv = wc_cat((wq, wk, wv), "qkv")
-        bqkv = wc_cat((bq, bk, bv), "bqkv").reshape(-1)
+        bqkv = wc_cat((bq, bk, bv), "bqkv")
         qkv = ops.linear_fwd(xn.view(B * T, D), wqkv, bqkv)
         e = ops.linear_fwd(pe, wc(wp), bp)                      # [2*Tp-G, D] == [2*Tn-1, G*D]
         klen_g = torch.div(klen + (G - 1), G, rounding_mode="floor").to(torch.int32) if klen is not None else None
@@ -621,7 +594,7 @@ class AudioStemFn(Function):
         melc = ops.convert(mel, compute_dtype())
         Co = cw.shape[0]
         g = ops.make_geom(B, 1, F, 80, 1, Co, (1, 3, 3), (1, 2, 2), (0, 1, 1))
-        wp = wc(cw, "stem2d", lambda w: w[:, 0].transpose(1, 2).reshape(w.shape[0], 9), pad=False)
+        wp = wc(cw, "stem2d", lambda w: w[:, 0].transpose(1, 2), pad=False)
         sites = ops.geom_sites(g)
         stats = ops.gemm_stats_buffer(Co, wave.device) if training else None
         direct = Co % 4 == 0 and Co <= 256   # SIMT stem kernel (K = 9 is far below a tensor-core tile; output-write bound)
@@ -665,12 +638,12 @@ class VideoStemFn(Function):
         direct = ops.stem3d_supported(xc, Co, kt, kh, kw)
         if direct:
             # direct tcgen05 implicit GEMM: the im2col tile only ever exists in shared memory
-            u = ops.stem3d_fwd(xc, wc(cw, "stem3d_direct", ops.stem3d_pack_weight), cb, colstats=stats)
+            u = ops.stem3d_fwd(xc, ops.stem3d_weight_layout(cw), cb, colstats=stats)
             col = xc
         else:
             # fallback (fp32 parity mode / other geometries): im2col + plain GEMMs (fwd and wgrad share the [sites, Kpad] matrix)
             Kpad = (taps + 63) // 64 * 64
-            wp = wc(cw, "stem3d", lambda w: torch.nn.functional.pad(w.reshape(w.shape[0], -1), (0, Kpad - taps)))
+            wp = W.PLAN.layout((cw,), ("stem3d", Kpad), W.b_custom(lambda w: w.reshape(w.shape[0], -1), Co, Kpad, (Kpad, 1)), compute_dtype())
             col = ops.im2col_c1(xc, g, Kpad)
             u = ops.linear_fwd(col, wp, cb, colstats=stats)
         bnbuf = _bn_buf(stats, bn_w, bn_b, rm, rv, sites, training, momentum)
@@ -700,12 +673,12 @@ class VideoStemFn(Function):
         return None, dcw, dcb, dgamma, dbeta, None, None, None, None
 
 
-def _pack_fwd(w):   # (Co, Ci, kh, kw) -> [Co, taps*Ci]
-    return w.permute(0, 2, 3, 1).reshape(w.shape[0], -1)
+def _pack_fwd(w):   # (Co, Ci, kh, kw) -> view (Co, kh, kw, Ci) = rows of the [Co, taps*Ci] forward operand
+    return w.permute(0, 2, 3, 1)
 
 
-def _pack_dgrad(w):  # (Co, Ci, kh, kw) -> [Ci, taps*Co]
-    return w.permute(1, 2, 3, 0).reshape(w.shape[1], -1)
+def _pack_dgrad(w):  # (Co, Ci, kh, kw) -> view (Ci, kh, kw, Co) = rows of the [Ci, taps*Co] dgrad operand
+    return w.permute(1, 2, 3, 0)
 
 
 def _unpack_wgrad(dw, w):  # [Co, taps*Ci] -> (Co, Ci, kh, kw)

@@ -123,7 +123,7 @@ class AudioEfficientConformerEncoder(nn.Module):
         C, Fq = filters, n_mels // 2
         self._proj_layout = (
             "stem_proj",
-            lambda w: w.view(w.shape[0], C, Fq).permute(0, 2, 1).reshape(w.shape[0], C * Fq),
+            lambda w: w.view(w.shape[0], C, Fq).permute(0, 2, 1),          # a VIEW: rows of the [N, Fq*C] operand (avec_b200.weights)
             lambda dw: dw.view(dw.shape[0], Fq, C).permute(0, 2, 1).reshape(dw.shape[0], C * Fq),
         )
 

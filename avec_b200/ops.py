@@ -430,6 +430,22 @@ def attn_head_pad(d):
     return 64 if d <= 64 else (128 if d <= 128 else None)
 
 
+def unpad_heads(w, H, d, dp, cols=False):
+    """fp32 gradient in the padded-heads layout -> dense: rows [n*H*dp, K] -> [n*H*d, K] (or 1-d), cols [N, H*dp] -> [N, H*d]"""
+    _cuda(w)
+    assert w.dtype == torch.float32 and w.is_contiguous()
+    if cols:
+        N = w.shape[0]
+        out = torch.empty((N, H * d), device=w.device, dtype=torch.float32)
+        L.check(L.load().avec_unpad_heads(w.data_ptr(), out.data_ptr(), N * H, d, dp, 1, _stream()), "avec_unpad_heads")
+        return out
+    K = w.numel() // w.shape[0]
+    groups = w.shape[0] // dp
+    out = torch.empty((groups * d,) + tuple(w.shape[1:]), device=w.device, dtype=torch.float32)
+    L.check(L.load().avec_unpad_heads(w.data_ptr(), out.data_ptr(), groups, d, dp, K, _stream()), "avec_unpad_heads")
+    return out
+
+
 def relpos_attn_tc_fwd(qkv, e, klen, qlen, B, T, H, d, dp):
     """qkv [B*T, 3*H*dp], e [2T-1, H*dp] (padded heads) -> o [B*T, H*dp] bf16, lse [B,H,T] fp32"""
     _cuda(qkv, e)
@@ -527,6 +543,13 @@ def stem3d_supported(x, Co, kt, kh, kw):
     B, T, H, W = x.shape[0], x.shape[1], x.shape[2], x.shape[3]
     return (x.dtype == torch.bfloat16 and Co == 64 and (kt, kh, kw) == (5, 7, 7) and W == 88 and H % 2 == 0 and H >= 8
             and GEMM_IMPL != L.IMPL_SIMT)
+
+
+def stem3d_weight_layout(cw):
+    """kernel layout of the visual stem filter: (64, 1, 5, 7, 7) -> bf16 [64, 320] with k = (kt*7+kh)*8 + kw (kw = 7 and k >= 280 zero)"""
+    from . import weights as W
+    return W.PLAN.layout((cw,), "stem3d_direct", W.b_custom(lambda w: w[:, 0].reshape(w.shape[0], 35, 7), cw.shape[0], STEM_KPAD, (STEM_KPAD, 8, 1)),
+                         torch.bfloat16)
 
 
 def stem3d_pack_weight(w):

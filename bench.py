@@ -115,10 +115,11 @@ class ClockSampler:
 
 def gemm_traffic():
     """DRAM bytes (read + write) of all tcgen05 GEMM / conv launches of one step, from the committed ncu pass
-    (profiles/r01_gemm_traffic.json: `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` over tools/one_step.py)"""
-    p = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
-    if os.path.exists(p):
-        return json.load(open(p)).get("dram_bytes_per_step")
+    (profiles/r02_gemm_traffic.json: `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` over tools/one_step.py, tools/gemm_traffic.py)"""
+    for name in ("r02_gemm_traffic.json", "r01_gemm_traffic.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            return json.load(open(p)).get("dram_bytes_per_step")
     return None
 
 

@@ -323,6 +323,22 @@ int avec_adam_step(float* p, const float* g, float* m, float* v, float* ema, lon
                    float weight_decay, int lr_mode, float lr_a, float lr_b, float max_norm, float ema_tau,
                    const unsigned long long* step, const float* sumsq, float* lr_out, avec_stream_t stream);
 
+/* Multi-tensor strided copy / conversion: ONE launch re-lays out every parameter of a model for the kernels (fp32 masters ->
+ * bf16 [N, K] GEMM operands with TMA-able pitch, conv filters permuted to [Co][tap][Ci] / [Ci][tap][Co], Q/K/V stacked with every
+ * head zero-padded to its column block, ...).  Job j copies the 4-d index space n from src (element strides ss) to dst (element
+ * strides ds); start = number of elements of the jobs before it; jobs_dev is the table in DEVICE memory, total = all elements. */
+typedef struct avec_copy_job {
+    const void* src;
+    void* dst;
+    long long start;
+    long long ss[4], ds[4];
+    int n[4];
+    int src_dtype, dst_dtype;
+} avec_copy_job;
+int avec_convert_multi(const avec_copy_job* jobs_dev, int njobs, long long total, avec_stream_t stream);
+/* padded-heads gradient -> dense (fp32): dst[(g*d + r)*K + c] = src[(g*dp + r)*K + c], g < groups, r < d, c < K */
+int avec_unpad_heads(const float* src, float* dst, long long groups, int d, int dp, long long K, avec_stream_t stream);
+
 /* dtype conversion / strided copy helper: dst[r][c] = (T)src[r][c] */
 int avec_convert(const void* src, int src_dtype, long long lds, void* dst, int dst_dtype, long long ldd, long long rows,
                  int C, avec_stream_t stream);
