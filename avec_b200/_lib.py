@@ -62,8 +62,11 @@ PROTOTYPES = {
     "avec_set_attention_long": ([_I], None),
     "avec_relpos_attn_fwd": ([_P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P], _I),
     "avec_relpos_attn_bwd": ([_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P], _I),
-    "avec_relpos_attn_tc_fwd": ([_P, _L, _P, _L, _P, _I, _P, _L, _P, _I, _I, _I, _I, _I, _P], _I),
-    "avec_relpos_attn_tc_bwd": ([_P, _L, _P, _L, _P, _L, _P, _L, _P, _P, _I, _P, _L, _P, _P, _L, _I, _I, _I, _I, _I, _P], _I),
+    "avec_relpos_attn_tc_fwd": ([_P, _L, _P, _L, _P, _I, _P, _L, _P, _I, _I, _I, _I, _I, _I, _P], _I),
+    "avec_relpos_attn_tc_bwd": ([_P, _L, _P, _L, _P, _L, _P, _L, _P, _P, _I, _P, _L, _P, _P, _L, _I, _I, _I, _I, _I, _I, _P], _I),
+    "avec_attn_group_pack": ([_P, _I, _L, _P, _P, _P, _L, _I, _I, _I, _I, _I, _I, _I, _I, _P], _I),
+    "avec_attn_group_unpack": ([_P, _I, _L, _P, _I, _L, _I, _I, _I, _I, _I, _I, _I, _P], _I),
+    "avec_attn_group_unpack_dqkv": ([_P, _L, _P, _L, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P], _I),
     "avec_softmax_fwd": ([_P, _I, _P, _I, _L, _I, _P], _I),
     "avec_softmax_bwd": ([_P, _P, _I, _P, _P, _I, _L, _I, _P], _I),
     "avec_glu_dwconv_fwd": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P], _I),

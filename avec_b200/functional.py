@@ -18,7 +18,7 @@ from torch.autograd import Function
 
 from . import _lib as L
 from . import ops
-from . import weights as W
+from . import weights as WL
 
 # ------------------------------------------------------------------------------------------------------------- config
 _COMPUTE_DTYPE = torch.bfloat16
@@ -64,7 +64,7 @@ def compute_dtype():
 # the start of every timed step; parameters changed through torch are detected by version counter / storage pointer.
 def invalidate_weights():
     """mark every cached compute-dtype weight copy stale (avec_b200.nnet.optimizers.Adam.step, checkpoint loads, ...)"""
-    W.PLAN.invalidate()
+    WL.PLAN.invalidate()
 
 
 def new_step(arena_numel=0, device=None, advance_rng=False):
@@ -104,8 +104,8 @@ class forward_scope:
                     pass
             on_gpu = self.device is not None and self.device.type == "cuda"
             new_step(numel if on_gpu else 0, self.device, advance_rng=bool(m.training))
-            if on_gpu and W.PLAN.stale():
-                W.PLAN.refresh_all()      # all weight layouts in one launch, on the caller's stream, before any branch forks off
+            if on_gpu and WL.PLAN.stale():
+                WL.PLAN.refresh_all()      # all weight layouts in one launch, on the caller's stream, before any branch forks off
         _depth += 1
         return self
 
@@ -127,24 +127,24 @@ def wc(param, tag="plain", fn=None, pad=True):
     """compute-dtype copy of a parameter in the layout a kernel wants; fn: parameter -> VIEW of it (<= 4-d) whose row-major
     order is the [N, K] layout (default: reshape to [N, -1]).  pad: GEMM operands get the TMA-able row pitch of ops.row_pitch;
     kernels that index the weight as a dense array pass pad=False."""
-    return W.PLAN.layout((param,), (tag, pad), W.b_plain(fn, pad), compute_dtype())
+    return WL.PLAN.layout((param,), (tag, pad), WL.b_plain(fn, pad), compute_dtype())
 
 
 def wc_cat(params, tag):
     """parameters stacked along rows ([sum N_i, K] in the compute dtype; 1-d parameters: fp32 [sum N_i])"""
     if params[0].dim() == 1:
-        return W.PLAN.layout(tuple(params), tag, W.b_cat(pad=False), torch.float32).reshape(-1)
-    return W.PLAN.layout(tuple(params), tag, W.b_cat(), compute_dtype())
+        return WL.PLAN.layout(tuple(params), tag, WL.b_cat(pad=False), torch.float32).reshape(-1)
+    return WL.PLAN.layout(tuple(params), tag, WL.b_cat(), compute_dtype())
 
 
 def wc_heads(params, tag, H, d, dp, cols=False):
     """padded-heads layout of the tcgen05 attention kernel: [H*d, K] weights (or [H*d] biases) stacked along rows with every head
     zero-padded to dp rows; cols=True: an [N, H*d] weight with every head zero-padded to dp COLUMNS (the output projection)"""
     if cols:
-        return W.PLAN.layout(tuple(params), (tag, dp), W.b_heads_cols(H, d, dp), compute_dtype())
+        return WL.PLAN.layout(tuple(params), (tag, dp), WL.b_heads_cols(H, d, dp), compute_dtype())
     if params[0].dim() == 1:
-        return W.PLAN.layout(tuple(params), (tag, dp), W.b_heads_rows(H, d, dp, pad=False), torch.float32).reshape(-1)
-    return W.PLAN.layout(tuple(params), (tag, dp), W.b_heads_rows(H, d, dp), compute_dtype())
+        return WL.PLAN.layout(tuple(params), (tag, dp), WL.b_heads_rows(H, d, dp, pad=False), torch.float32).reshape(-1)
+    return WL.PLAN.layout(tuple(params), (tag, dp), WL.b_heads_rows(H, d, dp), compute_dtype())
 
 
 def _c(t):
@@ -314,7 +314,9 @@ class AttentionFn(Function):
 class GroupedAttentionFn(Function):
     """y = x + Wo attn_G(LN(x)) + bo: Transformer-XL style relative attention with content / position biases u, v over
     tokens made of G consecutive frames (GroupedRelPosMultiHeadSelfAttention, reference nnet/attentions.py:579-650;
-    G = 1 is RelPosMultiHeadSelfAttention).  Projections run at full frame rate, grouping is pure addressing."""
+    G = 1 is RelPosMultiHeadSelfAttention).  Projections run at full frame rate.  bf16: the frame-rate q / k / v are regrouped
+    into the padded-heads token layout (4 parts: q + u | k | v | q + v, one kernel) and the tcgen05 flash kernel of
+    csrc/attention_tc.cu does the rest; fp32 parity mode: the round-1 SIMT kernels, grouping as pure addressing."""
 
     @staticmethod
     def forward(ctx, x, ln_w, ln_b, wq, bq, wk, bk, wv, bv, wo, bo, wp, bp, u, v, pe, klen, H, G, p_drop=0.0):
@@ -330,7 +332,17 @@ class GroupedAttentionFn(Function):
         qkv = ops.linear_fwd(xn.view(B * T, D), wqkv, bqkv)
         e = ops.linear_fwd(pe, wc(wp), bp)                      # [2*Tp-G, D] == [2*Tn-1, G*D]
         klen_g = torch.div(klen + (G - 1), G, rounding_mode="floor").to(torch.int32) if klen is not None else None
-        o, probs = ops.relpos_attn_fwd(qkv, e, klen_g, Tn, B, Tn, H, d, G=G, Tf=T, u=u, v=v)
+        dp = ops.attn_head_pad(d)
+        tc = ops.ATTN_TC and x.dtype == torch.bfloat16 and dp is not None and ops.GEMM_IMPL != L.IMPL_SIMT
+        if tc:
+            tok = ops.attn_group_pack(qkv, u, v, B, T, Tn, G, H, D, dp, 4)
+            e_tok = ops.attn_group_pack(e, None, None, 1, e.shape[0], 2 * Tn - 1, G, H, D, dp, 1)
+            o_tok, aux = ops.relpos_attn_tc_fwd(tok, e_tok, klen_g, Tn, B, Tn, H, d, dp, qp_part=3)
+            o = ops.attn_group_unpack(o_tok, B, T, Tn, G, H, D, dp)
+            saved_qkv, saved_e = tok, e_tok
+        else:
+            o, aux = ops.relpos_attn_fwd(qkv, e, klen_g, Tn, B, Tn, H, d, G=G, Tf=T, u=u, v=v)
+            o_tok, saved_qkv, saved_e = None, qkv, e
         site = 0
         plain = ln_w is None
         if p_drop > 0:
@@ -340,14 +352,14 @@ class GroupedAttentionFn(Function):
             y = ops.linear_fwd(o, wc(wo), bo).view(B, T, D)
         else:
             y = ops.linear_fwd(o, wc(wo), bo, L.EPI_RESIDUAL, aux=x.view(B * T, D)).view(B, T, D)
-        ctx.save_for_backward(x, ln_w, mean, rstd, xn, qkv, e, probs, o, pe, wq, wk, wv, wo, wp, u, v)
-        ctx.H, ctx.G, ctx.drop = H, G, (p_drop, site)
+        ctx.save_for_backward(x, ln_w, mean, rstd, xn, saved_qkv, saved_e, aux, o, o_tok, pe, wq, wk, wv, wo, wp, u, v, klen_g)
+        ctx.H, ctx.G, ctx.drop, ctx.tc = H, G, (p_drop, site), tc
         return y
 
     @staticmethod
     @_bwd
     def backward(ctx, dy):
-        x, ln_w, mean, rstd, xn, qkv, e, probs, o, pe, wq, wk, wv, wo, wp, u, v = ctx.saved_tensors
+        x, ln_w, mean, rstd, xn, qkv, e, aux, o, o_tok, pe, wq, wk, wv, wo, wp, u, v, klen_g = ctx.saved_tensors
         H, G = ctx.H, ctx.G
         B, T, D = x.shape
         Tn = -(-T // G)
@@ -358,8 +370,15 @@ class GroupedAttentionFn(Function):
         do = ops.linear_dgrad(dy2, wc(wo))
         dwo = ops.linear_wgrad(dy2, o)
         dbo = ops.colsum(dy2)
-        dqkv, de, du, dv = ops.relpos_attn_bwd(do, qkv, e, probs, B, Tn, H, d, G=G, Tf=T, u=u, v=v)
-        de2 = de.view(-1, D)
+        if ctx.tc:
+            dp = ops.attn_head_pad(d)
+            do_tok = ops.attn_group_pack(do, None, None, B, T, Tn, G, H, D, dp, 1)
+            dqkv_tok, de_tok = ops.relpos_attn_tc_bwd(do_tok, qkv, e, o_tok, aux, klen_g, Tn, B, Tn, H, d, dp, qp_part=3)
+            dqkv, du, dv = ops.attn_group_unpack_dqkv(dqkv_tok, B, T, Tn, G, H, D, dp)
+            de2 = ops.attn_group_unpack(de_tok, 1, pe.shape[0], 2 * Tn - 1, G, H, D, dp)
+        else:
+            dqkv, de, du, dv = ops.relpos_attn_bwd(do, qkv, e, aux, B, Tn, H, d, G=G, Tf=T, u=u, v=v)
+            de2 = de.view(-1, D)
         dwp = ops.linear_wgrad(ops.convert(de2, x.dtype), pe)
         dbp = ops.colsum(de2)
         wqkv = wc_cat((wq, wk, wv), "qkv")
@@ -643,7 +662,7 @@ class VideoStemFn(Function):
         else:
             # fallback (fp32 parity mode / other geometries): im2col + plain GEMMs (fwd and wgrad share the [sites, Kpad] matrix)
             Kpad = (taps + 63) // 64 * 64
-            wp = W.PLAN.layout((cw,), ("stem3d", Kpad), W.b_custom(lambda w: w.reshape(w.shape[0], -1), Co, Kpad, (Kpad, 1)), compute_dtype())
+            wp = WL.PLAN.layout((cw,), ("stem3d", Kpad), WL.b_custom(lambda w: w.reshape(w.shape[0], -1), Co, Kpad, (Kpad, 1)), compute_dtype())
             col = ops.im2col_c1(xc, g, Kpad)
             u = ops.linear_fwd(col, wp, cb, colstats=stats)
         bnbuf = _bn_buf(stats, bn_w, bn_b, rm, rv, sites, training, momentum)

@@ -427,7 +427,36 @@ def set_attention_tc(enabled):
 
 def attn_head_pad(d):
     """column block of one head in the padded-heads layout (one or two 64-wide TMA boxes), None if unsupported"""
-    return 64 if d <= 64 else (128 if d <= 128 else None)
+    return 64 if d <= 64 else (128 if d <= 128 else (192 if d <= 192 else (256 if d <= 256 else None)))
+
+
+def attn_group_pack(src, u, v, B, Tf, Tn, G, H, D1, dp, parts):
+    """frame-rate [B*Tf, (3*)D1] -> padded-heads tokens [B*Tn, parts*H*dp] bf16 (parts 4: q+u | k | v | q+v; 1: plain regroup)"""
+    _cuda(src)
+    dst = torch.empty((B * Tn, parts * H * dp), device=src.device, dtype=torch.bfloat16)
+    L.check(L.load().avec_attn_group_pack(src.data_ptr(), _dt(src), src.stride(0), _p(u), _p(v), dst.data_ptr(), dst.stride(0), B, Tf, Tn, G, H,
+                                          D1, dp, parts, _stream()), "avec_attn_group_pack")
+    return dst
+
+
+def attn_group_unpack(src, B, Tf, Tn, G, H, D1, dp):
+    """padded-heads tokens [B*Tn, H*dp] -> frames [B*Tf, D1] (same dtype: bf16 o, fp32 de)"""
+    _cuda(src)
+    dst = torch.empty((B * Tf, D1), device=src.device, dtype=src.dtype)
+    L.check(L.load().avec_attn_group_unpack(src.data_ptr(), _dt(src), src.stride(0), dst.data_ptr(), _dt(dst), dst.stride(0), B, Tf, Tn, G, H, D1,
+                                            dp, _stream()), "avec_attn_group_unpack")
+    return dst
+
+
+def attn_group_unpack_dqkv(dqkv_tok, B, Tf, Tn, G, H, D1, dp, want_bias=True):
+    """[B*Tn, 4*H*dp] -> dqkv frames [B*Tf, 3*D1] bf16, du, dv [D1] fp32"""
+    _cuda(dqkv_tok)
+    dst = torch.empty((B * Tf, 3 * D1), device=dqkv_tok.device, dtype=dqkv_tok.dtype)
+    du = zeros_f32((D1,), dqkv_tok.device) if want_bias else None
+    dv = zeros_f32((D1,), dqkv_tok.device) if want_bias else None
+    L.check(L.load().avec_attn_group_unpack_dqkv(dqkv_tok.data_ptr(), dqkv_tok.stride(0), dst.data_ptr(), dst.stride(0), _p(du), _p(dv), B, Tf, Tn,
+                                                 G, H, D1, dp, _stream()), "avec_attn_group_unpack_dqkv")
+    return dst, du, dv
 
 
 def unpad_heads(w, H, d, dp, cols=False):
@@ -446,25 +475,26 @@ def unpad_heads(w, H, d, dp, cols=False):
     return out
 
 
-def relpos_attn_tc_fwd(qkv, e, klen, qlen, B, T, H, d, dp):
-    """qkv [B*T, 3*H*dp], e [2T-1, H*dp] (padded heads) -> o [B*T, H*dp] bf16, lse [B,H,T] fp32"""
+def relpos_attn_tc_fwd(qkv, e, klen, qlen, B, T, H, d, dp, qp_part=0):
+    """qkv [B*T, 3*H*dp] (qp_part = 3: [B*T, 4*H*dp] = q+u | k | v | q+v), e [2T-1, H*dp] (padded heads) -> o [B*T, H*dp] bf16, lse [B,H,T]"""
     _cuda(qkv, e)
     o = torch.empty((B * T, H * dp), device=qkv.device, dtype=qkv.dtype)
     lse = torch.empty((B, H, T), device=qkv.device, dtype=torch.float32)
     L.check(L.load().avec_relpos_attn_tc_fwd(qkv.data_ptr(), qkv.stride(0), e.data_ptr(), e.stride(0), _p(klen), int(qlen), o.data_ptr(),
-                                             o.stride(0), lse.data_ptr(), B, T, H, d, dp, _stream()), "avec_relpos_attn_tc_fwd")
+                                             o.stride(0), lse.data_ptr(), B, T, H, d, dp, int(qp_part), _stream()), "avec_relpos_attn_tc_fwd")
     return o, lse
 
 
-def relpos_attn_tc_bwd(do, qkv, e, o, lse, klen, qlen, B, T, H, d, dp):
-    """-> dqkv [B*T, 3*H*dp] bf16, de [2T-1, H*dp] fp32"""
+def relpos_attn_tc_bwd(do, qkv, e, o, lse, klen, qlen, B, T, H, d, dp, qp_part=0):
+    """-> dqkv (qkv's layout) bf16, de [2T-1, H*dp] fp32"""
     _cuda(do, qkv, e, o)
-    dqkv = torch.empty((B * T, 3 * H * dp), device=qkv.device, dtype=qkv.dtype)
-    ws = None if T <= 128 else zeros_f32((B * T, 3 * H * dp), qkv.device)
+    nparts = 4 if qp_part else 3
+    dqkv = torch.empty((B * T, nparts * H * dp), device=qkv.device, dtype=qkv.dtype)
+    ws = None if T <= 128 else zeros_f32((B * T, nparts * H * dp), qkv.device)
     de = zeros_f32((2 * T - 1, H * dp), qkv.device)
     L.check(L.load().avec_relpos_attn_tc_bwd(do.data_ptr(), do.stride(0), qkv.data_ptr(), qkv.stride(0), e.data_ptr(), e.stride(0),
                                              o.data_ptr(), o.stride(0), lse.data_ptr(), _p(klen), int(qlen), dqkv.data_ptr(), dqkv.stride(0),
-                                             _p(ws), de.data_ptr(), de.stride(0), B, T, H, d, dp, _stream()), "avec_relpos_attn_tc_bwd")
+                                             _p(ws), de.data_ptr(), de.stride(0), B, T, H, d, dp, int(qp_part), _stream()), "avec_relpos_attn_tc_bwd")
     if ws is not None:
         dqkv = convert(ws, qkv.dtype)
     return dqkv, de

@@ -158,7 +158,7 @@ int avec_relpos_attn_bwd(const void* d_o, const void* qkv, const void* e, const 
  * The same attention as a Blackwell tile kernel (csrc/attention_tc.cu): tcgen05.mma with score / band / output accumulators in
  * TMEM, operands by TMA, flash-style for ANY sequence length (no [B,H,T,T] tensor: the forward saves lse [B,H,T] fp32, the
  * backward recomputes the probabilities).  bf16, G = 1 (regular and - on pooled tokens - patch attention).
- * "Padded heads" layout: every head owns a dp = 64 or 128 wide column block (dp >= d; pad columns are zeros, produced by
+ * "Padded heads" layout: every head owns a dp = 64, 128, 192 or 256 wide column block (dp >= d; pad columns are zeros, produced by
  * zero-padded projection weights): qkv [B*T, >= 3*H*dp] with head h of part s (0 q, 1 k, 2 v) at columns (s*H + h)*dp,
  * e [2T-1, >= H*dp], o / d_o [B*T, >= H*dp]; ld_* are row pitches in elements (multiples of 8), bases 16-byte aligned.
  * bwd: dqkv (bf16, qkv's layout) is written directly when T <= 128; for longer sequences the partial sums of the 128 x 128
@@ -166,10 +166,23 @@ int avec_relpos_attn_bwd(const void* d_o, const void* qkv, const void* e, const 
  * de [2T-1, >= H*dp] fp32 is accumulated atomically (zero-initialised by the caller).
  * ------------------------------------------------------------------------------------------------------------------ */
 int avec_relpos_attn_tc_fwd(const void* qkv, long long ld_qkv, const void* e, long long ld_e, const int* klen, int qlen, void* o,
-                            long long ld_o, float* lse, int B, int T, int H, int d, int dp, avec_stream_t stream);
+                            long long ld_o, float* lse, int B, int T, int H, int d, int dp, int qp_part, avec_stream_t stream);
 int avec_relpos_attn_tc_bwd(const void* d_o, long long ld_do, const void* qkv, long long ld_qkv, const void* e, long long ld_e,
                             const void* o, long long ld_o, const float* lse, const int* klen, int qlen, void* dqkv, long long ld_dqkv,
-                            float* dqkv_ws, float* de, long long ld_de, int B, int T, int H, int d, int dp, avec_stream_t stream);
+                            float* dqkv_ws, float* de, long long ld_de, int B, int T, int H, int d, int dp, int qp_part, avec_stream_t stream);
+/* Grouped / Transformer-XL attention (GroupedRelPosMultiHeadSelfAttention, nnet/attentions.py:579-650) on the same tile kernel:
+ * qp_part = 3 selects a 4-part layout [q + u | k | v | q + v] (scores use q + u against the keys, q + v against the position rows;
+ * dqkv then carries d(q+u) in part 0 and d(q+v) in part 3); dp up to 256 (d = G*D1/H = 135 -> 192).  The projections run at FRAME
+ * rate ([B*Tf, 3*D1], e [G*(2Tn-1), D1]); a token is G consecutive frames concatenated and split into H heads.
+ * avec_attn_group_pack: frames -> padded-heads tokens (dst_parts 4: qkv with u / v added after the zero padding; 1: plain regroup of a
+ * one-part matrix such as e or d_o);  avec_attn_group_unpack: tokens -> frames for a one-part matrix (o, fp32 de);
+ * avec_attn_group_unpack_dqkv: dqkv tokens -> [B*Tf, 3*D1] (dq = d(q+u) + d(q+v)) and du, dv [D1] (fp32, atomic). */
+int avec_attn_group_pack(const void* src, int src_dtype, long long lds, const float* u, const float* v, void* dst, long long ldd, int B,
+                         int Tf, int Tn, int G, int H, int D1, int dp, int dst_parts, avec_stream_t stream);
+int avec_attn_group_unpack(const void* src, int src_dtype, long long lds, void* dst, int dst_dtype, long long ldd, int B, int Tf, int Tn, int G,
+                           int H, int D1, int dp, avec_stream_t stream);
+int avec_attn_group_unpack_dqkv(const void* src, long long lds, void* dst, long long ldd, float* du, float* dv, int B, int Tf, int Tn, int G,
+                                int H, int D1, int dp, avec_stream_t stream);
 
 /* row softmax / its backward (InterCTCResModule, nnet/modules.py:397-398).  dadd (optional, fp32) is added to dx. */
 int avec_softmax_fwd(const void* x, int x_dtype, void* y, int y_dtype, long long rows, int C, avec_stream_t stream);

@@ -89,3 +89,42 @@ def test_attention_tc_matches_torch(B, T, H, d, ragged, qlen_cut):
         assert _rel(got, want) < 2e-2, f"{name} rel L2 {_rel(got, want)} (T={T}, d={d})"
     if dp > d:
         assert float(dqkv_p.view(B * T, 3 * H, dp)[:, :, d:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("G,T,D", [(3, 20, 180), (3, 401, 180), (1, 13, 256), (1, 200, 360)])
+def test_grouped_attention_tc_matches_simt_kernels(G, T, D):
+    """GroupedRelPosMultiHeadSelfAttention (Transformer-XL biases u, v; tokens of G frames, T not a multiple of G) through the tile
+    kernel (frames regrouped into the 4-part padded-heads layout) against the round-1 SIMT kernels on the same bf16 module:
+    output, input gradient and every parameter gradient incl. du / dv"""
+    import avec_b200
+    from avec_b200 import nnet
+    avec_b200.set_compute_dtype(torch.bfloat16)
+    torch.manual_seed(G * 100 + T)
+    att = {"class": "GroupedRelPosMultiHeadSelfAttention", "params": {"num_heads": 4, "group_size": G, "attn_drop_rate": 0.0, "max_pos_encoding": 10000,
+                                                                         "causal": False}}
+    mod = nnet.AttentionModule(D, att, 0.0).to(DEV).train()
+    with torch.no_grad():
+        mod.attention.u.normal_(0, 0.3)
+        mod.attention.v.normal_(0, 0.3)
+        for lin in (mod.attention.query_layer, mod.attention.key_layer, mod.attention.pos_layer):
+            lin.weight.mul_(3.0)
+    B = 2
+    x = torch.randn(B, T, D, device=DEV).to(torch.bfloat16)
+    klen = torch.tensor([T, max(1, T - 7)], dtype=torch.int32, device=DEV)
+    gy = torch.randn(B, T, D, device=DEV)
+    res = {}
+    for tc in (True, False):
+        ops.set_attention_tc(tc)
+        try:
+            xi = x.clone().requires_grad_(True)
+            mod.zero_grad(set_to_none=True)
+            y = mod.forward_residual(xi, klen)
+            (y.float() * gy).sum().backward()
+            res[tc] = (y.detach(), xi.grad.detach(), {k: p.grad.detach().clone() for k, p in mod.named_parameters()})
+        finally:
+            ops.set_attention_tc(True)
+    assert _rel(res[True][0], res[False][0]) < 1e-2 and _rel(res[True][1], res[False][1]) < 2e-2
+    for k, g in res[False][2].items():
+        if k.endswith("key_layer.bias") or k.endswith("pos_layer.bias"):
+            continue        # analytically zero (softmax is invariant to a per-row constant): rounding noise on both sides
+        assert _rel(res[True][2][k], g) < 3e-2, f"{k}: {_rel(res[True][2][k], g)}"
