@@ -55,10 +55,10 @@ PROTOTYPES = {
     "avec_set_tma": ([_I], None),
     "avec_set_debug_timestamps": ([_P], None),
     "avec_colsum": ([_P, _I, _L, _I, _L, _F, _P, _I, _P], _I),
-    "avec_layernorm_fwd": ([_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _P], _I),
+    "avec_layernorm_fwd": ([_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _L, _P], _I),
     "avec_layernorm_bwd": ([_P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _I, _I, _I, _I, _I, _P], _I),
     "avec_upsample_add": ([_P, _P, _P, _I, _I, _I, _I, _I, _I, _P], _I),
-    "avec_pool_sum": ([_P, _P, _I, _I, _I, _I, _I, _I, _P], _I),
+    "avec_pool_sum": ([_P, _P, _I, _I, _I, _I, _I, _I, _L, _P], _I),
     "avec_set_attention_long": ([_I], None),
     "avec_relpos_attn_fwd": ([_P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P], _I),
     "avec_relpos_attn_bwd": ([_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P], _I),
@@ -74,7 +74,7 @@ PROTOTYPES = {
     "avec_bn_finalize": ([_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _F, _F, _I, _P], _I),
     "avec_bn_eval_affine": ([_P, _P, _P, _P, _P, _P, _I, _F, _P], _I),
     "avec_bn_stats": ([_P, _I, _L, _I, _P, _P], _I),
-    "avec_bn_apply": ([_P, _P, _P, _P, _P, _L, _I, _I, _I, _P], _I),
+    "avec_bn_apply": ([_P, _P, _P, _P, _P, _L, _I, _I, _I, _L, _P], _I),
     "avec_bn_bwd_reduce": ([_P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _P], _I),
     "avec_bn_bwd_apply": ([_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _I, _I, _P], _I),
     "avec_stft_mel_log": ([_P, _P, _P, _I, _I, _I, _I, _P], _I),
@@ -91,7 +91,7 @@ PROTOTYPES = {
     "avec_zero_upsample": ([_P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _P], _I),
     "avec_ctc_loss": ([_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P], _I),
     "avec_counter_advance": ([_P, _P], _I),
-    "avec_dropout": ([_P, _P, _P, _L, _I, _I, _F, _F, _P, _I, _I, _I, _I, _P], _I),
+    "avec_dropout": ([_P, _P, _P, _L, _I, _I, _F, _F, _P, _I, _I, _I, _I, _L, _P], _I),
     "avec_spec_augment": ([_P, _P, _I, _I, _I, _I, _I, _I, _F, _P, _I, _P, _P], _I),
     "avec_video_augment": ([_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _F, _I, _F, _F, _P, _I, _P, _P], _I),
     "avec_ctc_greedy_decode": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _P], _I),

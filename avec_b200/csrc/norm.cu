@@ -15,7 +15,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, T* __restrict__ y,
                                                             float* __restrict__ mean, float* __restrict__ rstd, int B,
-                                                            int Tn, int Tp, int C, int P, float eps) {
+                                                            int Tn, int Tp, int C, int P, float eps, long long ldy) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= B * Tp) return;
     const int b = warp / Tp, tp = warp % Tp;
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const T* __restrict_
         }
     }
     const float invP = 1.0f / P;
-    T* yr = y + ((size_t)b * Tp + tp) * C;
+    T* yr = y + ((size_t)b * Tp + tp) * ldy;
 #pragma unroll
     for (int u = 0; u < LN_G; ++u) {
         int c = (lane + u * 32) * 4;
@@ -213,7 +213,7 @@ __global__ void upsample_add_kernel(const T* __restrict__ x, const T* __restrict
 }
 
 template <typename T, int V>
-__global__ void pool_sum_kernel(const T* __restrict__ dy, T* __restrict__ dout, int Tn, int Tp, int C, int P, long long total) {
+__global__ void pool_sum_kernel(const T* __restrict__ dy, T* __restrict__ dout, int Tn, int Tp, int C, int P, long long total, long long ldo) {
     const int Cv = C / V;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         int c = (int)(i % Cv) * V;
@@ -232,7 +232,7 @@ __global__ void pool_sum_kernel(const T* __restrict__ dy, T* __restrict__ dout, 
                 for (int j = 0; j < V; ++j) s[j] += a[j];
             }
         }
-        store_vec<V>(dout + row * C + c, s);
+        store_vec<V>(dout + row * ldo + c, s);
     }
 }
 
@@ -631,8 +631,10 @@ __global__ void bn_eval_affine_kernel(const float* __restrict__ gamma, const flo
 
 template <typename T, int V>
 __global__ void bn_apply_kernel(const T* __restrict__ u, const float* __restrict__ scale, const float* __restrict__ shift,
-                                const T* __restrict__ res, T* __restrict__ y, long long totalv, int C, int act) {
+                                const T* __restrict__ res, T* __restrict__ y, long long totalv, int C, int act, long long ldy) {
     const int Cv = C / V;
+    // output element offset of flat (dense) element e: rows of y may be pitched (GEMM operands with TMA-able rows)
+    auto yoff = [&](size_t e) -> size_t { return ldy == C ? e : (e / C) * (size_t)ldy + e % C; };
     const long long stride = (long long)gridDim.x * blockDim.x;
     const bool fixed_c = (stride % Cv) == 0;   // every iteration of this thread hits the same channel group
     float sc[V], sh[V];
@@ -651,8 +653,8 @@ __global__ void bn_apply_kernel(const T* __restrict__ u, const float* __restrict
                 if (res) { z0 += r0[j]; z1 += r1[j]; }
                 u0[j] = act_fwd(z0, act); u1[j] = act_fwd(z1, act);
             }
-            store_vec<V>(y + e0, u0);
-            store_vec<V>(y + e1, u1);
+            store_vec<V>(y + yoff(e0), u0);
+            store_vec<V>(y + yoff(e1), u1);
         }
     }
     for (; i < totalv; i += stride) {
@@ -668,7 +670,7 @@ __global__ void bn_apply_kernel(const T* __restrict__ u, const float* __restrict
             if (res) z += rr[j];
             uu[j] = act_fwd(z, act);
         }
-        store_vec<V>(y + e, uu);
+        store_vec<V>(y + yoff(e), uu);
     }
 }
 
@@ -886,13 +888,15 @@ inline int ew_blocks(long long total, int threads = 256) {
 }  // namespace
 
 extern "C" int avec_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int B,
-                                  int T, int C, int P, float eps, int dtype, avec_stream_t stream) {
+                                  int T, int C, int P, float eps, int dtype, long long ldy, avec_stream_t stream) {
+    if (ldy <= 0) ldy = C;
+    AVEC_CHECK_ARG(ldy >= C && ldy % 4 == 0);
     AVEC_CHECK_ARG(x && y && (gamma == nullptr || (beta && mean && rstd)) && B > 0 && T > 0 && P >= 1 && C > 0 && C <= 128 * LN_G && C % 4 == 0);
     const int Tp = cdiv(T, P);
     const long long warps = (long long)B * Tp;
     const int blocks = (int)cdivll(warps * 32, 256);
     AVEC_DISPATCH_DTYPE(dtype, Tt, (layernorm_fwd_kernel<Tt><<<blocks, 256, 0, as_stream(stream)>>>(
-        (const Tt*)x, gamma, beta, (Tt*)y, mean, rstd, B, T, Tp, C, P, eps)));
+        (const Tt*)x, gamma, beta, (Tt*)y, mean, rstd, B, T, Tp, C, P, eps, ldy)));
     AVEC_LAUNCH_CHECK();
     return AVEC_OK;
 }
@@ -904,7 +908,9 @@ extern "C" int avec_layernorm_bwd(const void* dy, const void* x, const float* ga
     AVEC_CHECK_ARG(!dres || res_stride >= 1);
     const int Tp = cdiv(T, P);
     const long long rows = (long long)B * T;
-    int blocks = (int)std::min<long long>(cdivll(rows, 8), 148LL * 4);
+    // >= 4 rows per warp: every CTA ends with 2*C atomics onto the same dgamma / dbeta addresses, so few, longer CTAs
+    // (Conformer sizes are 3-13 k rows: ~100-300 CTAs) beat one row per warp (profiles/r02_ncu_norm_kernels.md)
+    int blocks = (int)std::min<long long>(std::max<long long>(cdivll(rows, 32), 1), 148LL * 2);
     size_t smem = 2 * (size_t)C * sizeof(float);
     AVEC_DISPATCH_DTYPE(dtype, Tt, (layernorm_bwd_kernel<Tt><<<blocks, 256, smem, as_stream(stream)>>>(
         (const Tt*)dy, (const Tt*)x, gamma, mean, rstd, (const Tt*)dres, dres ? res_stride : 0, (Tt*)dx, dgamma, dbeta, B, T, Tp, C, P)));
@@ -922,11 +928,12 @@ extern "C" int avec_upsample_add(const void* x, const void* o, void* y, int B, i
     return AVEC_OK;
 }
 
-extern "C" int avec_pool_sum(const void* dy, void* dout, int B, int T, int Tp, int C, int P, int dtype, avec_stream_t stream) {
-    AVEC_CHECK_ARG(dy && dout && B > 0 && T > 0 && P >= 1 && Tp == cdiv(T, P));
+extern "C" int avec_pool_sum(const void* dy, void* dout, int B, int T, int Tp, int C, int P, int dtype, long long ldo, avec_stream_t stream) {
+    if (ldo <= 0) ldo = C;
+    AVEC_CHECK_ARG(dy && dout && B > 0 && T > 0 && P >= 1 && Tp == cdiv(T, P) && ldo >= C && ldo % 4 == 0);
     long long total = (long long)B * Tp * C;
     AVEC_DISPATCH_DTYPE_VEC(dtype, C, Tt, V, (pool_sum_kernel<Tt, V><<<ew_blocks(total / V), 256, 0, as_stream(stream)>>>(
-        (const Tt*)dy, (Tt*)dout, T, Tp, C, P, total / V)));
+        (const Tt*)dy, (Tt*)dout, T, Tp, C, P, total / V, ldo)));
     AVEC_LAUNCH_CHECK();
     return AVEC_OK;
 }
@@ -998,11 +1005,12 @@ extern "C" int avec_bn_eval_affine(const float* gamma, const float* beta, const 
 }
 
 extern "C" int avec_bn_apply(const void* u, const float* scale, const float* shift, const void* res, void* y, long long rows, int C,
-                             int act, int dtype, avec_stream_t stream) {
-    AVEC_CHECK_ARG(u && scale && shift && y && rows > 0 && C > 0);
+                             int act, int dtype, long long ldy, avec_stream_t stream) {
+    if (ldy <= 0) ldy = C;
+    AVEC_CHECK_ARG(u && scale && shift && y && rows > 0 && C > 0 && ldy >= C && ldy % 4 == 0);
     long long total = rows * C;
     AVEC_DISPATCH_DTYPE_VEC(dtype, C, Tt, V, (bn_apply_kernel<Tt, V><<<ew_blocks(total / V), 256, 0, as_stream(stream)>>>(
-        (const Tt*)u, scale, shift, (const Tt*)res, (Tt*)y, total / V, C, act)));
+        (const Tt*)u, scale, shift, (const Tt*)res, (Tt*)y, total / V, C, act, ldy)));
     AVEC_LAUNCH_CHECK();
     return AVEC_OK;
 }

@@ -42,7 +42,7 @@ template <typename T, int V>
 __global__ void __launch_bounds__(256) dropout_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __restrict__ y,
                                                       long long rows, int C, uint32_t thresh, float scale,
                                                       const unsigned long long* __restrict__ rng, uint32_t site, int Tf, int Tp,
-                                                      int P) {
+                                                      int P, long long ldy) {
     const int per_row = (C + V - 1) / V;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows * per_row) return;
@@ -52,10 +52,11 @@ __global__ void __launch_bounds__(256) dropout_kernel(const T* __restrict__ x, c
     const size_t o = (size_t)row * C + c0;
     // P > 1: x holds one row per patch of P frames ([B, Tp, C]) and is repeated over the frames of y ([B, T, C])
     const size_t ox = P > 1 ? (size_t)((row / Tf) * Tp + (row % Tf) / P) * C + c0 : o;
+    const size_t oy = (size_t)row * ldy + c0;     // y rows may be pitched (GEMM operand with TMA-able rows); x / res are dense
     if constexpr (V == 1) {
         float v = bits16(r, c0 & 7) >= thresh ? ldf(x + ox) * scale : 0.0f;
         if (res) v += ldf(res + o);
-        stf(y + o, v);
+        stf(y + oy, v);
     } else {
         float xv[V], rv[V];
         load_vec<V>(x + ox, xv);
@@ -65,13 +66,14 @@ __global__ void __launch_bounds__(256) dropout_kernel(const T* __restrict__ x, c
             const float v = bits16(r, (c0 + j) & 7) >= thresh ? xv[j] * scale : 0.0f;
             xv[j] = res ? rv[j] + v : v;
         }
-        store_vec<V>(y + o, xv);
+        store_vec<V>(y + oy, xv);
     }
 }
 
 extern "C" int avec_dropout(const void* x, const void* res, void* y, long long rows, int C, int dtype, float p, float alpha,
-                            const unsigned long long* rng_state, int site, int Tf, int Tp, int P, avec_stream_t stream) {
-    AVEC_CHECK_ARG(x && y && rng_state && rows > 0 && C > 0 && p >= 0.0f && p < 1.0f);
+                            const unsigned long long* rng_state, int site, int Tf, int Tp, int P, long long ldy, avec_stream_t stream) {
+    if (ldy <= 0) ldy = C;
+    AVEC_CHECK_ARG(x && y && rng_state && rows > 0 && C > 0 && p >= 0.0f && p < 1.0f && ldy >= C && (ldy == C || ldy % 4 == 0));
     AVEC_CHECK_ARG(P <= 1 || (Tf > 0 && Tp > 0 && rows % Tf == 0 && (Tf + P - 1) / P <= Tp && x != y));
     const uint32_t thresh = (uint32_t)(p * 65536.0f + 0.5f);
     const float scale = alpha / (1.0f - p);
@@ -80,7 +82,7 @@ extern "C" int avec_dropout(const void* x, const void* res, void* y, long long r
     do {                                                                                                               \
         const long long n = rows * ((C + V - 1) / V);                                                                  \
         dropout_kernel<T, V><<<(unsigned)cdivll(n, 256), 256, 0, st>>>((const T*)x, (const T*)res, (T*)y, rows, C, thresh, \
-                                                                       scale, rng_state, (uint32_t)site, Tf, Tp, P);    \
+                                                                       scale, rng_state, (uint32_t)site, Tf, Tp, P, ldy); \
     } while (0)
     AVEC_DISPATCH_DTYPE(dtype, T, {
         if (C % 8 == 0) AVEC_DROP_LAUNCH(T, 8);

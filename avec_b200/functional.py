@@ -199,7 +199,7 @@ class FFNFn(Function):
         dy = _c(dy)
         dy2 = dy.view(B * T, D)
         if p_out > 0:
-            dyd, a = ops.dropout_rng(ctx.rng, dy2, p_out, s_out, alpha=0.5), 1.0
+            dyd, a = ops.dropout_rng(ctx.rng, dy2, p_out, s_out, alpha=0.5, pad_out=True), 1.0
         else:
             dyd, a = dy2, 0.5
         dpre = ops.linear_dgrad(dyd, wc(w2), L.EPI_DSWISH, alpha=a, aux=pre)
@@ -281,7 +281,7 @@ class AttentionFn(Function):
         d = D // H
         dy = _c(dy)
         p_drop, site = ctx.drop
-        dyd = ops.dropout_rng(ctx.rng, dy.view(B * T, D), p_drop, site).view(B, T, D) if p_drop > 0 else dy
+        dyd = ops.dropout_rng(ctx.rng, dy.view(B * T, D), p_drop, site, pad_out=(P == 1)).view(B, T, D) if p_drop > 0 else dy
         dproj = dyd.view(B * T, D) if P == 1 else ops.pool_sum(dyd, P).view(B * Tp, D)
         dbo = ops.colsum(dproj)
         if tc:
@@ -366,7 +366,7 @@ class GroupedAttentionFn(Function):
         d = G * D // H
         dy = _c(dy)
         p_drop, site = ctx.drop
-        dy2 = ops.dropout_rng(ctx.rng, dy.view(B * T, D), p_drop, site) if p_drop > 0 else dy.view(B * T, D)
+        dy2 = ops.dropout_rng(ctx.rng, dy.view(B * T, D), p_drop, site, pad_out=True) if p_drop > 0 else dy.view(B * T, D)
         do = ops.linear_dgrad(dy2, wc(wo))
         dwo = ops.linear_wgrad(dy2, o)
         dbo = ops.colsum(dy2)
@@ -412,7 +412,7 @@ class ConvModuleFn(Function):
             bnbuf = ops.bn_finalize(stats, bn_w, bn_b, B * To, rm, rv, 1e-5, momentum)
         else:
             bnbuf = ops.bn_eval_affine(bn_w, bn_b, rm, rv, 1e-5)
-        v = ops.bn_apply(u2, bnbuf[0], bnbuf[1], L.ACT_SWISH)
+        v = ops.bn_apply(u2, bnbuf[0], bnbuf[1], L.ACT_SWISH, pad_out=True)     # operand of the pointwise conv and of its wgrad
         if wr is None:
             xs = None
             aux = x.view(B * T, D)
@@ -442,7 +442,7 @@ class ConvModuleFn(Function):
         dy = _c(dy)
         dy2 = dy.view(B * To, De)
         p_drop, site = ctx.drop
-        dyd = ops.dropout_rng(ctx.rng, dy2, p_drop, site) if p_drop > 0 else dy2
+        dyd = ops.dropout_rng(ctx.rng, dy2, p_drop, site, pad_out=True) if p_drop > 0 else dy2
         dv = ops.linear_dgrad(dyd, wc(w3))
         dw3 = ops.linear_wgrad(dyd, v)
         db3 = ops.colsum(dyd)
@@ -486,7 +486,7 @@ class LayerNormFn(Function):
     def forward(ctx, x, w, b):
         ctx.cdt = compute_dtype()
         x = _c(x)
-        y, mean, rstd = ops.layernorm_fwd(x, w, b)
+        y, mean, rstd = ops.layernorm_fwd(x, w, b, pad_out=False)     # the block output: read by row kernels, dense rows
         ctx.save_for_backward(x, w, mean, rstd)
         return y
 

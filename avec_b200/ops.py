@@ -229,20 +229,23 @@ def conv_wgrad(dy, x, g):
 
 
 # ------------------------------------------------------------------------------------------------------ normalisations
-def layernorm_fwd(x, gamma, beta, P=1, eps=1e-6):
-    """x [B,T,C] -> y [B,ceil(T/P),C] (mean over P consecutive LayerNorm'ed frames), mean/rstd [B*T] fp32."""
+def layernorm_fwd(x, gamma, beta, P=1, eps=1e-6, pad_out=True):
+    """x [B,T,C] -> y [B,ceil(T/P),C] (mean over P consecutive LayerNorm'ed frames), mean/rstd [B*T] fp32.  y feeds GEMMs as an
+    operand: its rows get the TMA-able pitch of row_pitch() (a [B,Tp,C] view of a wider allocation when C % 8 != 0)."""
     _cuda(x)
     B, T, Cn = x.shape
     Tp = -(-T // P)
-    y = torch.empty((B, Tp, Cn), device=x.device, dtype=x.dtype)
+    y = empty_rows(B * Tp, Cn, x.dtype, x.device) if pad_out else torch.empty((B * Tp, Cn), device=x.device, dtype=x.dtype)
+    ldy = y.stride(0)
+    y3 = y.view(B, Tp, Cn)
     if gamma is None:   # identity mode: plain mean over the P frames of a patch (attention.forwardQKV without the module's norm)
-        L.check(L.load().avec_layernorm_fwd(x.data_ptr(), 0, 0, y.data_ptr(), 0, 0, B, T, Cn, P, eps, _dt(x), _stream()), "avec_layernorm_fwd")
-        return y, None, None
+        L.check(L.load().avec_layernorm_fwd(x.data_ptr(), 0, 0, y.data_ptr(), 0, 0, B, T, Cn, P, eps, _dt(x), ldy, _stream()), "avec_layernorm_fwd")
+        return y3, None, None
     mean = torch.empty((B * T,), device=x.device, dtype=torch.float32)
     rstd = torch.empty_like(mean)
     L.check(L.load().avec_layernorm_fwd(x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), mean.data_ptr(),
-                                        rstd.data_ptr(), B, T, Cn, P, eps, _dt(x), _stream()), "avec_layernorm_fwd")
-    return y, mean, rstd
+                                        rstd.data_ptr(), B, T, Cn, P, eps, _dt(x), ldy, _stream()), "avec_layernorm_fwd")
+    return y3, mean, rstd
 
 
 def layernorm_bwd(dy, x, gamma, mean, rstd, P=1, dres=None, res_stride=1):
@@ -272,9 +275,9 @@ def upsample_add(x, o, P):
 def pool_sum(dy, P):
     B, T, Cn = dy.shape
     Tp = -(-T // P)
-    out = torch.empty((B, Tp, Cn), device=dy.device, dtype=dy.dtype)
-    L.check(L.load().avec_pool_sum(dy.data_ptr(), out.data_ptr(), B, T, Tp, Cn, P, _dt(dy), _stream()), "avec_pool_sum")
-    return out
+    out = empty_rows(B * Tp, Cn, dy.dtype, dy.device)      # a GEMM operand of the backward: TMA-able row pitch
+    L.check(L.load().avec_pool_sum(dy.data_ptr(), out.data_ptr(), B, T, Tp, Cn, P, _dt(dy), out.stride(0), _stream()), "avec_pool_sum")
+    return out.view(B, Tp, Cn)
 
 
 def softmax_fwd(x, out_dtype):
@@ -344,11 +347,12 @@ def bn_eval_affine(gamma, beta, running_mean, running_var, eps=1e-5):
     return buf
 
 
-def bn_apply(u2d, scale, shift, act, res=None):
+def bn_apply(u2d, scale, shift, act, res=None, pad_out=False):
+    """pad_out: y feeds a GEMM as an operand (ConvModule: the pointwise conv after BatchNorm + Swish): TMA-able row pitch"""
     rows, Cn = u2d.shape
-    y = torch.empty_like(u2d)
+    y = empty_rows(rows, Cn, u2d.dtype, u2d.device) if pad_out else torch.empty_like(u2d)
     L.check(L.load().avec_bn_apply(u2d.data_ptr(), scale.data_ptr(), shift.data_ptr(), _p(res), y.data_ptr(), rows, Cn, act,
-                                   _dt(u2d), _stream()), "avec_bn_apply")
+                                   _dt(u2d), y.stride(0), _stream()), "avec_bn_apply")
     return y
 
 
@@ -750,12 +754,12 @@ class _Rng:
 RNG = _Rng()
 
 
-def dropout(x, p, site, res=None, alpha=1.0, out=None, up=None):
+def dropout(x, p, site, res=None, alpha=1.0, out=None, up=None, pad_out=False):
     """dropout_rng on the live generator state (tests / direct calls)"""
-    return dropout_rng(RNG.get(x.device), x, p, site, res, alpha, out, up)
+    return dropout_rng(RNG.get(x.device), x, p, site, res, alpha, out, up, pad_out)
 
 
-def dropout_rng(rng, x, p, site, res=None, alpha=1.0, out=None, up=None):
+def dropout_rng(rng, x, p, site, res=None, alpha=1.0, out=None, up=None, pad_out=False):
     """out = (res or 0) + alpha * keep * x / (1 - p) with the Philox mask of (rng = {seed, step} device tensor, site); the
     backward calls it again on the gradient with the same rng / site.  up = (T, Tp, P): x is [B*Tp, C] patch rows repeated over
     the T frames of out / res.  rng None: the current forward pass's snapshot."""
@@ -764,14 +768,15 @@ def dropout_rng(rng, x, p, site, res=None, alpha=1.0, out=None, up=None):
     C = x.shape[-1]
     if up is None:
         rows, T, Tp, P = x.numel() // C, 0, 0, 1
-        out = torch.empty_like(x) if out is None else out
     else:
         T, Tp, P = up
         rows = (x.numel() // C // Tp) * T
-        out = torch.empty((rows, C), device=x.device, dtype=x.dtype) if out is None else out
-    assert x.is_contiguous() and out.is_contiguous() and (res is None or (res.is_contiguous() and res.dtype == x.dtype))
+    if out is None:     # pad_out (backward: the masked gradient is a GEMM operand): [rows, C] view with the TMA-able row pitch
+        out = empty_rows(rows, C, x.dtype, x.device) if pad_out else (torch.empty_like(x) if up is None else torch.empty((rows, C), device=x.device, dtype=x.dtype))
+    ldy = out.stride(-2) if out.dim() >= 2 else C
+    assert x.is_contiguous() and (out.is_contiguous() or (out.dim() == 2 and out.stride(1) == 1)) and (res is None or (res.is_contiguous() and res.dtype == x.dtype))
     L.check(L.load().avec_dropout(x.data_ptr(), _p(res), out.data_ptr(), rows, C, _dt(x), float(p), float(alpha),
-                                  rng.data_ptr(), int(site), T, Tp, P, _stream()), "avec_dropout")
+                                  rng.data_ptr(), int(site), T, Tp, P, ldy, _stream()), "avec_dropout")
     return out
 
 

@@ -120,9 +120,12 @@ int avec_colsum(const void* x, int dtype, long long rows, int C, long long ldx, 
  * Replaces nn.LayerNorm (nnet/modules.py:278,302,373; nnet/blocks.py:267,304) + MultiHeadAttention.pad +
  * AvgPool1d of RelPosPatch1dMultiHeadAttention.forwardQKV (nnet/attentions.py:351-371).
  * bwd: dx = LNbwd(expand(dy)/P) + (dres ? gather(dres, res_stride) : 0);  dgamma/dbeta accumulate (atomic) into fp32.
+ * gamma == NULL: identity (no normalisation: plain patch mean / its backward).  ldy (here and in avec_pool_sum, avec_bn_apply,
+ * avec_dropout): row pitch of the OUTPUT in elements, 0 = dense; the tensors that feed a GEMM as an operand are written with a
+ * 16-byte-aligned pitch (D = 180: 192) so that the tcgen05 kernel can fetch them by TMA instead of its gather producers.
  * ------------------------------------------------------------------------------------------------------------------ */
 int avec_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int B,
-                       int T, int C, int P, float eps, int dtype, avec_stream_t stream);
+                       int T, int C, int P, float eps, int dtype, long long ldy, avec_stream_t stream);
 int avec_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
                        const void* dres, int res_stride, void* dx, float* dgamma, float* dbeta, int B, int T, int C,
                        int P, int dtype, avec_stream_t stream);
@@ -131,7 +134,7 @@ int avec_layernorm_bwd(const void* dy, const void* x, const float* gamma, const 
 int avec_upsample_add(const void* x, const void* o, void* y, int B, int T, int Tp, int C, int P, int dtype,
                       avec_stream_t stream);
 /* do[b,t'] = sum_{p<P, t'P+p<T} dy[b, t'P+p]   (its backward) */
-int avec_pool_sum(const void* dy, void* dout, int B, int T, int Tp, int C, int P, int dtype, avec_stream_t stream);
+int avec_pool_sum(const void* dy, void* dout, int B, int T, int Tp, int C, int P, int dtype, long long ld_out, avec_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Relative-position multi-head self-attention core (nnet/attentions.py:280-323 incl. rel_to_abs 258-276; grouped /
@@ -216,7 +219,7 @@ int avec_bn_eval_affine(const float* gamma, const float* beta, const float* runn
                         float* scale, float* shift, int C, float eps, avec_stream_t stream);
 int avec_bn_stats(const void* u, int dtype, long long rows, int C, float* stats, avec_stream_t stream);
 int avec_bn_apply(const void* u, const float* scale, const float* shift, const void* res, void* y, long long rows, int C,
-                  int act, int dtype, avec_stream_t stream);
+                  int act, int dtype, long long ldy, avec_stream_t stream);
 int avec_bn_bwd_reduce(const void* dy, const void* u, const float* scale, const float* shift, const void* res,
                        const float* mean, const float* rstd, float* sums, long long rows, int C, int act, int dtype,
                        avec_stream_t stream);
@@ -304,7 +307,7 @@ int avec_counter_advance(unsigned long long* counter, avec_stream_t stream);
  * P > 1: x is [B, Tp, C] (one row per patch of P frames), y / res are [B, T, C] with rows = B*T: the dropout that follows
  * the patch attention's upsampling (nnet/attentions.py:368-372) draws one mask element per FRAME, as the reference does. */
 int avec_dropout(const void* x, const void* res, void* y, long long rows, int C, int dtype, float p, float alpha,
-                 const unsigned long long* rng_state, int site, int T, int Tp, int P, avec_stream_t stream);
+                 const unsigned long long* rng_state, int site, int T, int Tp, int P, long long ldy, avec_stream_t stream);
 
 /* SpecAugment (nnet/preprocessing.py:87-129 over torchaudio mask_along_axis), in place on mel [B,F,M] fp32 (frame-major):
  * mF frequency masks of width < Fmax shared by the batch, mT time masks per utterance of width < int(pS * len_b) inside
