@@ -1120,7 +1120,8 @@ __global__ void __launch_bounds__(TC_THREADS_WIDE, 1) gemm_tc_kernel(const __gri
                 const int esz = p.ep.aux_dtype == AVEC_F32 ? 4 : 2;
                 const char* a0 = reinterpret_cast<const char*>(p.ep.aux) + ((size_t)row * p.ep.ldaux + n0) * esz;
                 const int nbytes = min(BN, p.N - n0) * esz;
-                for (int o = 0; o < nbytes; o += 128) asm volatile("prefetch.global.L1 [%0];" ::"l"(a0 + o));
+                // (L2, not L1: with ~220 KB of the SM's array carved out as shared memory there is next to no L1 to prefetch into)
+                for (int o = 0; o < nbytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(a0 + o));
             }
             if (tid == 0) AVEC_TSJ(j, 0);
             if (AVEC_DBG_MODE(4)) mbar_wait_sleep(&accum_full[buf], (uint32_t)((j >> 1) & 1));
