@@ -529,9 +529,18 @@ def main():
         if world == 1 and args.cpu_baseline:
             cb = cpu_baseline(args, steps=2, warmup=1)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # All ranks leave together and WITHOUT tearing NCCL down: rank 0 arrives here seconds after the others (it alone runs the
+        # parity check), and destroying communicators whose kernels live inside captured CUDA graphs while peers are already gone
+        # hung the 8-GPU run of this round until its time limit.  A hard exit after a final barrier cannot hang; a timer backs it up.
+        sys.stdout.flush()
+        sys.stderr.flush()
+        threading.Timer(120.0, os._exit, args=(0,)).start()
+        try:
+            dist.barrier()
+        finally:
+            os._exit(0)
 
 
 def profile_gemm(step_fn, ops):
