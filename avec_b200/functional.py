@@ -81,6 +81,18 @@ def new_step(arena_numel=0, device=None, advance_rng=False):
         ops.RNG.snapshot(device)
 
 
+# BatchNorm.num_batches_tracked of every training-mode BatchNorm touched by a forward pass: bumped by ONE multi-tensor launch when
+# the pass closes (45 one-element add kernels per AV step otherwise)
+_nbt = []
+
+
+def count_batch(bn):
+    if _depth > 0:
+        _nbt.append(bn.num_batches_tracked)
+    else:
+        bn.num_batches_tracked.add_(1)
+
+
 # The outermost module of a forward pass (a zoo Model, or an encoder called directly / from the reference's zoo models after
 # avec_b200.patch_reference()) opens the step; nested encoders see depth > 0 and do nothing.
 _depth = 0
@@ -114,6 +126,10 @@ class forward_scope:
         _depth -= 1
         if _depth == 0:
             ops.RNG.snap.clear()      # Functions of this pass keep their own reference (ctx.rng)
+            if _nbt:
+                if exc[0] is None:
+                    torch._foreach_add_(list(_nbt), 1)
+                _nbt.clear()
         return False
 
 

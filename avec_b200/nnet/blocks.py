@@ -77,10 +77,10 @@ class ResNetBlock(nn.Module):
         has_res = not isinstance(self.residual, nn.Identity)
         training = self.training
         if training:
-            bn1.num_batches_tracked.add_(1)
-            bn2.num_batches_tracked.add_(1)
+            AF.count_batch(bn1)
+            AF.count_batch(bn2)
             if has_res:
-                self.residual[1].num_batches_tracked.add_(1)
+                AF.count_batch(self.residual[1])
         if has_res:
             cr, br = self.residual[0], self.residual[1]
             res = (cr.weight, br.weight, br.bias, br.running_mean, br.running_var)

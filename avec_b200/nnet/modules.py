@@ -229,7 +229,7 @@ class ConvolutionModule(nn.Module):
         bn = l[4]
         training = self.training
         if training and bn.track_running_stats:
-            bn.num_batches_tracked.add_(1)
+            AF.count_batch(bn)
         has_res = not isinstance(conv_res, nn.Identity)
         return AF.ConvModuleFn.apply(
             x, l[0].weight, l[0].bias, l[1].weight, l[1].bias, l[3].weight, l[3].bias,

@@ -134,7 +134,7 @@ class AudioEfficientConformerEncoder(nn.Module):
     def _forward(self, x, lengths):
         conv, bn = self.subsampling_module.layers[0][0], self.subsampling_module.layers[0][1]
         if self.training:
-            bn.num_batches_tracked.add_(1)
+            AF.count_batch(bn)
         lengths = torch.div(lengths, 160, rounding_mode="floor") + 1      # preprocessing.py:76-77
         spec = self.spec_augment.params() if (self.training and self.spec_augment.enabled) else None
         mel_len = lengths.to(device=x.device, dtype=torch.long) if spec is not None else None
@@ -211,7 +211,7 @@ class VisualEfficientConformerEncoder(nn.Module):
         B, T = x.shape[0], x.shape[1]
         conv, bn = self.front_end[0].layers[0][0], self.front_end[0].layers[0][1]
         if self.training:
-            bn.num_batches_tracked.add_(1)
+            AF.count_batch(bn)
         x = AF.VideoStemFn.apply(x, conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var,
                                  self.training, bn.momentum)
         x = self.front_end[3](x)                 # (B*T, 256)
