@@ -15,6 +15,7 @@ GEMM_PLAIN, GEMM_CONV_FWD, GEMM_CONV_DGRAD, GEMM_CONV_WGRAD = 0, 1, 2, 3
 EPI_LINEAR, EPI_SWISH, EPI_RESIDUAL, EPI_DSWISH, EPI_ACCUM, EPI_RELU = 0, 1, 2, 3, 4, 5
 IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_SWISH = 0, 1, 2
+COPY_CHUNK = 4096      # AVEC_COPY_CHUNK
 STATS_REPLICAS = 32   # copies of the GEMM-epilogue BatchNorm statistics accumulator (AVEC_STATS_REPLICAS in common.cuh)
 
 
@@ -97,7 +98,7 @@ PROTOTYPES = {
     "avec_ctc_greedy_decode": ([_P, _P, _P, _P, _P, _I, _I, _I, _I, _P], _I),
     "avec_sumsq": ([_P, _L, _P, _P], _I),
     "avec_adam_step": ([_P, _P, _P, _P, _P, _L, _F, _F, _F, _F, _I, _F, _F, _F, _F, _P, _P, _P, _P], _I),
-    "avec_convert_multi": ([_P, _I, _L, _P], _I),
+    "avec_convert_multi": ([_P, _P, _I, _P], _I),
     "avec_unpad_heads": ([_P, _P, _L, _I, _I, _L, _P], _I),
     "avec_convert": ([_P, _I, _L, _P, _I, _L, _L, _I, _P], _I),
 }

@@ -1102,20 +1102,42 @@ extern "C" int avec_zero_upsample(const void* in, void* out, int N, int Ho, int 
 
 // ---- multi-tensor strided copy / conversion: every per-step weight re-layout of a model in ONE launch ----------------------
 // job j copies a logical 4-d index space (n0, n1, n2, n3) from src (fp32 or bf16, element strides ss) to dst (fp32 or bf16,
-// element strides ds); `start` is the running element count (exclusive prefix sum), so a thread finds its job by binary search.
-__global__ void __launch_bounds__(256) convert_multi_kernel(const avec_copy_job* __restrict__ jobs, int njobs, long long total) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        int lo = 0, hi = njobs - 1;
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (jobs[mid].start <= i) lo = mid; else hi = mid - 1;
+// element strides ds).  `chunks` maps every CTA to (job, chunk of AVEC_COPY_CHUNK elements of that job): no per-element search,
+// 32-bit index arithmetic, and 4 elements per thread when the innermost dimension is contiguous on both sides.
+constexpr int COPY_CHUNK = 4096;
+__global__ void __launch_bounds__(256) convert_multi_kernel(const avec_copy_job* __restrict__ jobs, const int2* __restrict__ chunks) {
+    const int2 bc = chunks[blockIdx.x];
+    const avec_copy_job j = jobs[bc.x];
+    const unsigned n1 = j.n[1], n2 = j.n[2], n3 = j.n[3];
+    const unsigned numel = (unsigned)j.n[0] * n1 * n2 * n3;
+    const unsigned base = (unsigned)bc.y * COPY_CHUNK, end = min(base + COPY_CHUNK, numel);
+    const bool vec = j.ss[3] == 1 && j.ds[3] == 1 && (n3 & 3u) == 0 && j.src_dtype == AVEC_F32 &&
+                     ((j.ss[0] | j.ss[1] | j.ss[2] | j.ds[0] | j.ds[1] | j.ds[2]) & 3) == 0 &&
+                     (reinterpret_cast<uintptr_t>(j.src) & 15) == 0 && (reinterpret_cast<uintptr_t>(j.dst) & (j.dst_dtype == AVEC_F32 ? 15 : 7)) == 0;
+    if (vec) {
+        for (unsigned e = base + threadIdx.x * 4; e < end; e += 256 * 4) {
+            unsigned r = e;
+            const unsigned i3 = r % n3; r /= n3;
+            const unsigned i2 = r % n2; r /= n2;
+            const unsigned i1 = r % n1;
+            const unsigned i0 = r / n1;
+            const long long so = i0 * j.ss[0] + i1 * j.ss[1] + i2 * j.ss[2] + i3;
+            const long long d_o = i0 * j.ds[0] + i1 * j.ds[1] + i2 * j.ds[2] + i3;
+            const float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(j.src) + so);
+            if (j.dst_dtype == AVEC_F32) *reinterpret_cast<float4*>(reinterpret_cast<float*>(j.dst) + d_o) = v;
+            else {
+                __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+                *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(j.dst) + d_o) = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+            }
         }
-        const avec_copy_job& j = jobs[lo];
-        long long r = i - j.start;
-        const int i3 = (int)(r % j.n[3]); r /= j.n[3];
-        const int i2 = (int)(r % j.n[2]); r /= j.n[2];
-        const int i1 = (int)(r % j.n[1]);
-        const int i0 = (int)(r / j.n[1]);
+        return;
+    }
+    for (unsigned e = base + threadIdx.x; e < end; e += 256) {
+        unsigned r = e;
+        const unsigned i3 = r % n3; r /= n3;
+        const unsigned i2 = r % n2; r /= n2;
+        const unsigned i1 = r % n1;
+        const unsigned i0 = r / n1;
         const long long so = i0 * j.ss[0] + i1 * j.ss[1] + i2 * j.ss[2] + i3 * j.ss[3];
         const long long d_o = i0 * j.ds[0] + i1 * j.ds[1] + i2 * j.ds[2] + i3 * j.ds[3];
         const float v = j.src_dtype == AVEC_F32 ? reinterpret_cast<const float*>(j.src)[so] : __bfloat162float(reinterpret_cast<const bf16*>(j.src)[so]);
@@ -1124,9 +1146,9 @@ __global__ void __launch_bounds__(256) convert_multi_kernel(const avec_copy_job*
     }
 }
 
-extern "C" int avec_convert_multi(const avec_copy_job* jobs_dev, int njobs, long long total, avec_stream_t stream) {
-    AVEC_CHECK_ARG(jobs_dev && njobs > 0 && total > 0);
-    convert_multi_kernel<<<ew_blocks(total), 256, 0, as_stream(stream)>>>(jobs_dev, njobs, total);
+extern "C" int avec_convert_multi(const avec_copy_job* jobs_dev, const int* chunks_dev, int nchunks, avec_stream_t stream) {
+    AVEC_CHECK_ARG(jobs_dev && chunks_dev && nchunks > 0);
+    convert_multi_kernel<<<nchunks, 256, 0, as_stream(stream)>>>(jobs_dev, reinterpret_cast<const int2*>(chunks_dev));
     AVEC_LAUNCH_CHECK();
     return AVEC_OK;
 }

@@ -89,7 +89,7 @@ class WeightPlan:
             raise RuntimeError("avec_b200.weights: a new weight layout was requested during CUDA-graph capture; run one eager step first")
         njobs = sum(len(e.jobs) for e in entries)
         arr = (L.CopyJob * njobs)()
-        k, start = 0, 0
+        k, start, chunks = 0, 0, []
         for e in entries:
             esz = e.dst.element_size()
             for view, dst_off, n, ss, ds in e.jobs:
@@ -98,14 +98,18 @@ class WeightPlan:
                 for q in range(4):
                     j.n[q], j.ss[q], j.ds[q] = n[q], ss[q], ds[q]
                 j.src_dtype, j.dst_dtype = _DT[view.dtype], _DT[e.dst.dtype]
-                start += n[0] * n[1] * n[2] * n[3]
+                numel = n[0] * n[1] * n[2] * n[3]
+                assert numel < 2 ** 31
+                chunks += [(k, c) for c in range(-(-numel // L.COPY_CHUNK))]
+                start += numel
                 k += 1
         dev = entries[0].dst.device
         table = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(dev)
-        return table, njobs, start
+        chunk_t = torch.tensor(chunks, dtype=torch.int32).to(dev)
+        return (table, chunk_t), njobs, len(chunks)
 
-    def _run(self, table, njobs, total):
-        L.check(L.load().avec_convert_multi(table.data_ptr(), njobs, total, ops._stream()), "avec_convert_multi")
+    def _run(self, table, njobs, nchunks):
+        L.check(L.load().avec_convert_multi(table[0].data_ptr(), table[1].data_ptr(), nchunks, ops._stream()), "avec_convert_multi")
 
     def refresh_all(self):
         self._purge()

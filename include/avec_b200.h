@@ -342,7 +342,9 @@ int avec_adam_step(float* p, const float* g, float* m, float* v, float* ema, lon
 /* Multi-tensor strided copy / conversion: ONE launch re-lays out every parameter of a model for the kernels (fp32 masters ->
  * bf16 [N, K] GEMM operands with TMA-able pitch, conv filters permuted to [Co][tap][Ci] / [Ci][tap][Co], Q/K/V stacked with every
  * head zero-padded to its column block, ...).  Job j copies the 4-d index space n from src (element strides ss) to dst (element
- * strides ds); start = number of elements of the jobs before it; jobs_dev is the table in DEVICE memory, total = all elements. */
+ * strides ds); every job holds < 2^31 elements.  jobs_dev is the table in DEVICE memory; chunks_dev [nchunks][2] int32 maps CTA c to
+ * (job index, chunk index): the CTA copies elements [chunk * 4096, (chunk + 1) * 4096) of that job (AVEC_COPY_CHUNK). */
+#define AVEC_COPY_CHUNK 4096
 typedef struct avec_copy_job {
     const void* src;
     void* dst;
@@ -351,7 +353,7 @@ typedef struct avec_copy_job {
     int n[4];
     int src_dtype, dst_dtype;
 } avec_copy_job;
-int avec_convert_multi(const avec_copy_job* jobs_dev, int njobs, long long total, avec_stream_t stream);
+int avec_convert_multi(const avec_copy_job* jobs_dev, const int* chunks_dev, int nchunks, avec_stream_t stream);
 /* padded-heads gradient -> dense (fp32): dst[(g*d + r)*K + c] = src[(g*dp + r)*K + c], g < groups, r < d, c < K */
 int avec_unpad_heads(const float* src, float* dst, long long groups, int d, int dp, long long K, avec_stream_t stream);
 
