@@ -18,7 +18,7 @@ pids=()
 for s in $SRCS; do
   [ -f $s ] || continue
   o=$OBJ/${s%.cu}.o
-  newest=$(ls -t $s *.cuh 2>/dev/null | head -1)
+  newest=$(ls -t $s *.cuh ../../include/avec_b200.h 2>/dev/null | head -1)
   if [ ! -f $o ] || [ $newest -nt $o ]; then
     ( $NVCC $FLAGS -c $s -o $o > $OBJ/${s%.cu}.log 2>&1 || { cat $OBJ/${s%.cu}.log; rm -f $o; exit 1; } ) &
     pids+=($!)

@@ -2,15 +2,20 @@
 """bench.py - utterances/s of the Audio-Visual Efficient Conformer (AVEC) encoder forward+backward on B200.
 
     python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path (one rank per GPU under torchrun)
-    python bench.py --impl reference --gpus N ...              # CPU baseline: the pinned restatement of the reference
+    python bench.py --impl reference --gpus N ...              # the reference's own CPU implementation on the host cores
 
 Workload (BASELINE.json metric / configs[3]): AV EffConfInterCTC, per-GPU batch 64, 4 s of 16 kHz audio (64000
 samples) + 101 frames of 88x88 video (Tv = Ta // 640 + 1, SURVEY section 0 item 4), synthetic data, random-init weights,
 train-mode forward (batch-stat BatchNorm; dropout 0.1 + SpecAugment as in the reference's training graph, --dropout 0 = the
-deterministic parity configuration) + CTC losses on the 6 heads + backward.
+deterministic parity configuration) + CTC losses on the 6 heads + backward; the bf16 kernel-layout weight copies are rebuilt
+from the fp32 masters inside every step.
 One step = one batch.  `value` times steps with inputs resident in HBM; `e2e` times the public API call
 model((video, vlen, audio, alen)) fed from pinned host memory, H2D copies and the D2H read of the loss inside the timed
-region.  Under torchrun (N > 1) gradients are all-reduced over NCCL every step (pure data parallel, local BN).
+region.  Under torchrun (N > 1) the gradients are all-reduced over NCCL inside the captured step (pure data parallel, local BN).
+Beside the number (rank 0): `roofline` (algorithmic FLOPs of the step / CUDA-event time inside the tcgen05 kernels, per family),
+`parity` (the timed model and batch through the dropout-free graph against the fp32 oracle on the same GPU), `incumbent` (the
+reference's graph as eager bf16-autocast PyTorch on the same GPU: the unmodified reference when its tree is present) and
+`cpu_baseline` (the reference's CPU path on a bounded sample).
 """
 import argparse
 import json
