@@ -13,6 +13,8 @@ Reference modules mirrored (file:line in /root/reference):
   ResBlockFn   ResNetBlock                                       nnet/blocks.py:29-91
   AvgPoolFn    GlobalAvgPool2d                                   nnet/networks.py:129-132
 """
+import os
+
 import torch
 from torch.autograd import Function
 
@@ -115,6 +117,8 @@ class forward_scope:
                 except Exception:  # noqa: BLE001
                     pass
             on_gpu = self.device is not None and self.device.type == "cuda"
+            if on_gpu:
+                join_side_streams(self.device)      # (only matters when a trunk input did not require a gradient)
             new_step(numel if on_gpu else 0, self.device, advance_rng=bool(m.training))
             if on_gpu and WL.PLAN.stale():
                 WL.PLAN.refresh_all()      # all weight layouts in one launch, on the caller's stream, before any branch forks off
@@ -768,20 +772,93 @@ class ResBlockFn(Function):
         ga, gb, gr = ctx.geoms
         Co = w1.shape[0]
         dy2 = _c(dy).view(-1, Co)
+        # Weight gradients are off the critical path (nothing in the backward waits for them): they go to a side stream, enqueued
+        # AFTER the input-gradient convolution that shares their operand, so that they run under the BatchNorm backward passes
+        # that follow (tensor-pipe work under HBM-bound work; JoinSideFn at the trunk input joins the stream again).
         du2, dres, dg2, db2 = ops.bn_bwd(dy2, u2, bn2, g2w, L.ACT_RELU, res=r, want_dres=True)
         da1 = ops.conv_dgrad(du2, wc(w2, "cd", _pack_dgrad), gb)
-        dw2 = _unpack_wgrad(ops.conv_wgrad(du2, a1, gb), w2)
+        dw2 = _wgrad_side(du2, a1, gb, w2)
         du1, _, dg1, db1 = ops.bn_bwd(da1, u1, bn1, g1w, L.ACT_RELU)
-        dw1 = _unpack_wgrad(ops.conv_wgrad(du1, x, ga), w1)
         if wr is not None:
             dur, _, dgr, dbr = ops.bn_bwd(dres, ur, bnr, grw, L.ACT_NONE)
             dxr = ops.conv_dgrad(dur, wc(wr, "cd", _pack_dgrad), gr)
-            dwr = _unpack_wgrad(ops.conv_wgrad(dur, x, gr), wr)
             dx = ops.conv_dgrad(du1, wc(w1, "cd", _pack_dgrad), ga, epi=L.EPI_RESIDUAL, aux=dxr)
+            dwr = _wgrad_side(dur, x, gr, wr)
         else:
             dwr = dgr = dbr = None
             dx = ops.conv_dgrad(du1, wc(w1, "cd", _pack_dgrad), ga, epi=L.EPI_RESIDUAL, aux=dres)
+        dw1 = _wgrad_side(du1, x, ga, w1)
         return (dx.view(x.shape), dw1, dg1, db1, None, None, dw2, dg2, db2, None, None, dwr, dgr, dbr, None, None, None, None, None)
+
+
+# ---- weight gradients of the ResNet trunk on a side stream -----------------------------------------------------------------
+WGRAD_OVERLAP = os.environ.get("AVEC_WGRAD_OVERLAP", "1") != "0"
+_wg_streams = {}
+
+
+def _wg_stream(device):
+    s = _wg_streams.get(device)
+    if s is None:
+        s = torch.cuda.Stream(device=device)
+        _wg_streams[device] = s
+    return s
+
+
+def _wgrad_side(dyt, xt, g, w):
+    """dW of one convolution, (Co, Ci, kh, kw) fp32, computed on the weight-gradient stream after everything enqueued so far"""
+    if not (WGRAD_OVERLAP and dyt.is_cuda):
+        return _unpack_wgrad(ops.conv_wgrad(dyt, xt, g), w)
+    cur = torch.cuda.current_stream(dyt.device)
+    side = _wg_stream(dyt.device)
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        dw = _unpack_wgrad(ops.conv_wgrad(dyt, xt, g), w)
+    dyt.record_stream(side)
+    xt.record_stream(side)
+    dw.record_stream(cur)
+    return dw
+
+
+def join_side_streams(device=None):
+    """make the current stream wait for the weight-gradient stream (end of a backward pass)"""
+    for dev, s in _wg_streams.items():
+        if device is None or torch.device(device) == dev:
+            torch.cuda.current_stream(dev).wait_stream(s)
+
+
+_trunk_depth = 0     # > 0 while a ResNet trunk (which joins once, at its input) is running its blocks
+
+
+class trunk_scope:
+    def __enter__(self):
+        global _trunk_depth
+        _trunk_depth += 1
+
+    def __exit__(self, *exc):
+        global _trunk_depth
+        _trunk_depth -= 1
+        return False
+
+
+def in_trunk():
+    return _trunk_depth > 0
+
+
+class JoinSideFn(Function):
+    """identity placed at the input of the ResNet trunk: its backward runs after every block's backward and joins the
+    weight-gradient stream back onto the stream autograd runs the trunk on"""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.cdt = compute_dtype()
+        return x.view_as(x)
+
+    @staticmethod
+    @_bwd
+    def backward(ctx, g):
+        if g.is_cuda:
+            join_side_streams(g.device)
+        return g
 
 
 class AvgPoolFn(Function):

@@ -86,6 +86,8 @@ class ResNetBlock(nn.Module):
             res = (cr.weight, br.weight, br.bias, br.running_mean, br.running_var)
         else:
             res = (None, None, None, None, None)
+        if not AF.in_trunk():
+            x = AF.JoinSideFn.apply(x)      # a block used on its own joins its weight-gradient stream itself
         return AF.ResBlockFn.apply(
             x, l[0].weight, bn1.weight, bn1.bias, bn1.running_mean, bn1.running_var,
             l[3].weight, bn2.weight, bn2.bias, bn2.running_mean, bn2.running_var,

@@ -169,8 +169,10 @@ class ResNet(nn.Module):
                                   Linear(dim_blocks[-1], dim_output, weight_init="he_normal", bias_init="zeros"))
 
     def forward(self, x):
-        for block in self.blocks:
-            x = block(x)
+        x = AF.JoinSideFn.apply(x)       # its backward joins the weight-gradient side stream of the blocks below
+        with AF.trunk_scope():
+            for block in self.blocks:
+                x = block(x)
         x = AF.AvgPoolFn.apply(x)
         return AF.LinearFn.apply(x, self.head[1].weight, self.head[1].bias, False, None)
 

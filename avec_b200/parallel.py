@@ -127,6 +127,8 @@ class GradientBuckets:
         lo, hi = self.spans[b]
         buf = self.flat[lo:hi]
         if self.cuda:
+            from . import functional as AF
+            AF.join_side_streams(self.flat.device)       # weight gradients computed on the side stream
             cur = torch.cuda.current_stream(self.flat.device)
             for s in self.streams[b]:
                 if s != cur:
@@ -151,6 +153,9 @@ class GradientBuckets:
         """end of backward: joins the communication stream and hands the averaged views back as p.grad.  A bucket that never
         filled up (a parameter without a gradient this step) is flushed here with zeros for the missing gradients, so every rank
         issues the same sequence of collectives."""
+        if self.cuda:
+            from . import functional as AF
+            AF.join_side_streams(self.flat.device)
         for b in range(len(self.buckets)):
             if not self.done[b]:
                 for i in self.buckets[b]:
