@@ -804,26 +804,33 @@ def _wg_stream(device):
     return s
 
 
+_wg_pending = {}      # device -> tensors the side stream may still be reading (kept alive until the join)
+
+
 def _wgrad_side(dyt, xt, g, w):
-    """dW of one convolution, (Co, Ci, kh, kw) fp32, computed on the weight-gradient stream after everything enqueued so far"""
+    """dW of one convolution, (Co, Ci, kh, kw) fp32, computed on the weight-gradient stream after everything enqueued so far.
+    The operands stay referenced until join_side_streams(): no record_stream (with 400 MB operands it makes the caching
+    allocator hold every freed block back and the reserved pool balloons)."""
     if not (WGRAD_OVERLAP and dyt.is_cuda):
         return _unpack_wgrad(ops.conv_wgrad(dyt, xt, g), w)
-    cur = torch.cuda.current_stream(dyt.device)
-    side = _wg_stream(dyt.device)
+    dev = dyt.device
+    cur = torch.cuda.current_stream(dev)
+    side = _wg_stream(dev)
     side.wait_stream(cur)
     with torch.cuda.stream(side):
         dw = _unpack_wgrad(ops.conv_wgrad(dyt, xt, g), w)
-    dyt.record_stream(side)
-    xt.record_stream(side)
-    dw.record_stream(cur)
+    _wg_pending.setdefault(dev, []).extend((dyt, xt))
     return dw
 
 
 def join_side_streams(device=None):
-    """make the current stream wait for the weight-gradient stream (end of a backward pass)"""
-    for dev, s in _wg_streams.items():
-        if device is None or torch.device(device) == dev:
-            torch.cuda.current_stream(dev).wait_stream(s)
+    """make the current stream wait for the weight-gradient stream (end of a backward pass); a no-op when nothing is pending"""
+    for dev in list(_wg_pending.keys()):
+        if device is not None and torch.device(device) != dev:
+            continue
+        if _wg_pending[dev]:
+            torch.cuda.current_stream(dev).wait_stream(_wg_streams[dev])
+            _wg_pending[dev] = []
 
 
 _trunk_depth = 0     # > 0 while a ResNet trunk (which joins once, at its input) is running its blocks
