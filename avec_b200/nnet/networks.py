@@ -265,7 +265,8 @@ class AudioVisualEfficientConformerEncoder(nn.Module):
             side.wait_stream(cur)
             with torch.cuda.stream(side):
                 audio, audio_len, audio_interctc_outputs = self.audio_encoder(audio, audio_len)
-            video, video_len, video_interctc_outputs = self.video_encoder(video, video_len)
+            with AF.no_wgrad_overlap():      # the audio branch already fills the gaps of the video branch
+                video, video_len, video_interctc_outputs = self.video_encoder(video, video_len)
             cur.wait_stream(side)
             for t in [audio] + [v[0] for v in audio_interctc_outputs.values()]:
                 t.record_stream(cur)      # produced on the side stream, consumed (fusion, losses) on the caller's stream
