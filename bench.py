@@ -477,7 +477,9 @@ def main():
     # single-stream step (the two-stream schedule would fold the other branch's kernels into each window)
     if args.model == "AV":
         model.encoder.overlap_branches = False
+    wg_overlap, AF.WGRAD_OVERLAP = AF.WGRAD_OVERLAP, False      # (weight gradients on the main stream too: one kernel at a time)
     prof = profile_gemm(lambda: fwd_bwd(resident), ops)
+    AF.WGRAD_OVERLAP = wg_overlap
     if args.model == "AV":
         model.encoder.overlap_branches = bool(args.overlap)
     ops.reset_launch_count()
