@@ -35,6 +35,7 @@ class GemmArgs(C.Structure):
         ("out2", C.c_void_p), ("out2_dtype", C.c_int), ("ldo2", C.c_longlong),
         ("aux", C.c_void_p), ("aux_dtype", C.c_int), ("ldaux", C.c_longlong),
         ("colstats", C.c_void_p), ("split_k", C.c_int),
+        ("drop_p", C.c_float), ("drop_site", C.c_int), ("drop_rng", C.c_void_p),
     ]
 
 
@@ -54,6 +55,8 @@ PROTOTYPES = {
     "avec_reset_launch_count": ([], None),
     "avec_gemm": ([C.POINTER(GemmArgs), _P], _I),
     "avec_set_tma": ([_I], None),
+    "avec_set_pdl": ([_I], None),
+    "avec_pdl_exclude_stream": ([_P, _I], None),
     "avec_set_debug_timestamps": ([_P], None),
     "avec_colsum": ([_P, _I, _L, _I, _L, _F, _P, _I, _P], _I),
     "avec_layernorm_fwd": ([_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _L, _P], _I),

@@ -34,6 +34,9 @@ extern "C" int avec_gemm(const avec_gemm_args* a, avec_stream_t stream) {
     AVEC_CHECK_ARG(a->epi != AVEC_EPI_ACCUM || a->out_dtype == AVEC_F32);
     AVEC_CHECK_ARG((a->epi != AVEC_EPI_RESIDUAL && a->epi != AVEC_EPI_DSWISH) || a->aux);
     cudaStream_t st = as_stream(stream);
+    const bool drop = a->drop_p > 0.0f;
+    AVEC_CHECK_ARG(!drop || (a->drop_rng && a->drop_p < 1.0f && a->epi != AVEC_EPI_ACCUM && a->epi != AVEC_EPI_RELU && !a->colstats));
+    if (drop && (a->impl == AVEC_IMPL_SIMT || !avec_gemm_tc_supported(a))) return AVEC_ERR_UNSUPPORTED;   // caller: separate avec_dropout
     if (a->impl == AVEC_IMPL_SIMT) return avec_gemm_simt(a, st);
     if (a->impl == AVEC_IMPL_TCGEN05) {
         if (!avec_gemm_tc_supported(a)) return AVEC_ERR_UNSUPPORTED;

@@ -107,6 +107,7 @@ __device__ __forceinline__ void mma_scores(uint32_t tmem, uint32_t q_s, uint32_t
 // ================================================================ forward
 __global__ void __launch_bounds__(AT_THREADS, 1) relpos_attn_tc_fwd_kernel(const __grid_constant__ AttnTcParams p, const __grid_constant__ CUtensorMap mapQKV,
                                                                           const __grid_constant__ CUtensorMap mapE) {
+    pdl_trigger();   // programmatic dependent launch: a tcgen05 GEMM behind this kernel may start its prologue now
     extern __shared__ uint8_t smem_raw[];
     uint8_t* sm = align1024(smem_raw);
     uint8_t* ring = sm;
@@ -260,6 +261,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) relpos_attn_tc_fwd_kernel(const
 // ================================================================ backward
 __global__ void __launch_bounds__(AT_THREADS, 1) relpos_attn_tc_bwd_kernel(const __grid_constant__ AttnTcParams p, const __grid_constant__ CUtensorMap mapQKV,
                                                                           const __grid_constant__ CUtensorMap mapE, const __grid_constant__ CUtensorMap mapDO) {
+    pdl_trigger();   // programmatic dependent launch: a tcgen05 GEMM behind this kernel may start its prologue now
     extern __shared__ uint8_t smem_raw[];
     uint8_t* sm = align1024(smem_raw);
     uint8_t* ring = sm;

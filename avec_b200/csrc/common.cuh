@@ -95,6 +95,35 @@ template <int V> __device__ __forceinline__ void store_vec(bf16* p, const float 
         else return AVEC_ERR_INVALID;                                       \
     } while (0)
 
+// ---- counter-based random bits (Philox4x32-10, Salmon et al. SC'11): dropout masks, SpecAugment / video-augmentation draws ----
+// ---- programmatic dependent launch (sm_90+) ------------------------------------------------------------------------------
+// pdl_trigger(): the next kernel of the stream, IF it was launched with cudaLaunchAttributeProgrammaticStreamSerialization, may be
+// scheduled once every CTA of this grid has got here (its CTAs then run their prologue and park in pdl_wait()).  Without that
+// attribute on the next launch the instruction does nothing.  pdl_wait(): returns once the preceding grid has completed and its
+// memory operations are visible (immediately, when the kernel was launched the ordinary way).
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+// 16 random bits of element (row, col): 16-bit lane (col & 7) of Philox(ctr = (row, col >> 3, site, step), key = seed)
+__device__ __forceinline__ uint4 dropout_bits(const unsigned long long* rng, uint32_t site, uint32_t row, uint32_t grp) {
+    const unsigned long long seed = rng[0], step = rng[1];
+    return philox4x32_10(make_uint4(row, grp, site, (uint32_t)step), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+}
+__device__ __forceinline__ uint32_t bits16(const uint4& r, int j) {   // j = 0..7
+    const uint32_t w = (j >> 1) == 0 ? r.x : (j >> 1) == 1 ? r.y : (j >> 1) == 2 ? r.z : r.w;
+    return (j & 1) ? (w >> 16) : (w & 0xFFFFu);
+}
+
 // ---- GEMM epilogue shared by the SIMT kernel and the tcgen05 kernel ------------------------------
 struct EpiParams {
     int M, N;
@@ -105,6 +134,9 @@ struct EpiParams {
     void* out2; int out2_dtype; long long ldo2;
     const void* aux; int aux_dtype; long long ldaux;
     float* colstats;
+    // nn.Dropout fused behind the GEMM (tcgen05 fast epilogue only): the value the epilogue kind produces BEFORE the residual
+    // add is multiplied by keep(row, col) * drop_scale, with exactly the mask avec_dropout draws for (rng, site)
+    const unsigned long long* drop_rng; uint32_t drop_site, drop_thresh; float drop_scale;
 };
 
 static inline EpiParams make_epi(const avec_gemm_args* a) {
@@ -114,6 +146,10 @@ static inline EpiParams make_epi(const avec_gemm_args* a) {
     p.out2 = a->out2; p.out2_dtype = a->out2_dtype; p.ldo2 = a->ldo2;
     p.aux = a->aux; p.aux_dtype = a->aux_dtype; p.ldaux = a->ldaux;
     p.colstats = a->colstats;
+    p.drop_rng = (a->drop_p > 0.0f) ? a->drop_rng : nullptr;
+    p.drop_site = (uint32_t)a->drop_site;
+    p.drop_thresh = (uint32_t)(a->drop_p * 65536.0f + 0.5f);
+    p.drop_scale = a->drop_p > 0.0f ? 1.0f / (1.0f - a->drop_p) : 1.0f;
     return p;
 }
 

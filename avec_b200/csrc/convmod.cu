@@ -19,6 +19,7 @@ __global__ void __launch_bounds__(DW_CH) glu_dwconv_fwd_kernel(const T* __restri
                                                                const float* __restrict__ bias, T* __restrict__ u,
                                                                float* __restrict__ stats, int Tn, int To, int C, int ksize,
                                                                int stride, int pad) {
+    pdl_trigger();   // programmatic dependent launch: a tcgen05 GEMM behind this kernel may start its prologue now
     extern __shared__ float gs[];  // [rows][DW_CH]
     const int b = blockIdx.z, c = blockIdx.y * DW_CH + threadIdx.x;
     const int to0 = blockIdx.x * DW_TO;
@@ -59,6 +60,7 @@ __global__ void __launch_bounds__(DW_CH) glu_dwconv_bwd_kernel(const T* __restri
                                                                const float* __restrict__ w, T* __restrict__ dpre,
                                                                float* __restrict__ dw, float* __restrict__ db, int Tn, int To,
                                                                int C, int ksize, int stride_rt, int pad) {
+    pdl_trigger();   // programmatic dependent launch: a tcgen05 GEMM behind this kernel may start its prologue now
     const int stride = STRIDE > 0 ? STRIDE : stride_rt;   // compile-time stride (1 / 2): no division in the tap loops
     extern __shared__ float sm[];
     const int b = blockIdx.z, c = blockIdx.y * DW_CH + threadIdx.x;

@@ -678,15 +678,16 @@ __device__ __forceinline__ void unpack_bf16x8(const uint4& t, float (&v)[8]) {
 // rows aligned to 8 or 16 bytes, N % 8 == 0, fp32 reductions for ACCUM) compiled per epilogue kind, so the transposed-domain
 // loop is branch-free: four row passes at a time with all their shared-memory and auxiliary loads issued before the first
 // use, bias kept in registers (a lane owns the same 8 columns in every pass).
-template <int KIND, bool STATS, bool AL16>
+template <int KIND, bool STATS, bool AL16, bool DROP = false>
 __device__ __forceinline__ void epilogue_fast(const TcParams& p, const EpiParams& ep, const TileInfo& ti, uint32_t lane_addr, uint32_t stg_s,
                                               uint32_t bias_sa, float* stats_dst, int warp, int lane, bool bias_on, uint32_t rowrel_sa = 0u,
-                                              int slab0 = 0, int slab_step = 64) {
+                                              int slab0 = 0, int slab_step = 64, const uint32_t* kbits = nullptr) {
     const int BN = p.BN;
     const int q = lane & 7, rs = lane >> 3;
     const int lc = q * 8;
     const float alpha = ep.alpha;
     const bool scale_on = alpha != 1.0f;   // kernel-uniform: the common alpha == 1 / no-bias launches skip 16 FP32 ops per row segment
+    constexpr bool drop_on = DROP;   // nn.Dropout fused behind this GEMM: its own instantiation, so the plain epilogues keep their register budget
     const int rows_left = ti.rows_valid - warp * 32;   // valid rows of this warp's quarter (may be <= 0 or >= 32)
     // output row of tile row r: contiguous, or scattered through the row table (parity classes of strided dgrads)
     auto out_row = [&](int rr) -> long long {   // < 0: the tile row holds no output (halo-grid columns past the image)
@@ -698,8 +699,15 @@ __device__ __forceinline__ void epilogue_fast(const TcParams& p, const EpiParams
         }
         return ti.row_base + r;
     };
-    for (int c0 = slab0; c0 < BN; c0 += slab_step) {   // with two epilogue warpgroups each takes every other 64-column slab
+    int si = 0;
+    for (int c0 = slab0; c0 < BN; c0 += slab_step, ++si) {   // with two epilogue warpgroups each takes every other 64-column slab
         const int ncol = min(64, BN - c0);   // multiple of 16
+        // keep bits of this slab (drawn by the caller while the MMAs were still running): bit (u * 8 + j) of word g
+        uint32_t kw0 = 0u, kw1 = 0u;
+        if (drop_on) {
+            kw0 = si == 0 ? kbits[0] : si == 1 ? kbits[2] : si == 2 ? kbits[4] : kbits[6];
+            kw1 = si == 0 ? kbits[1] : si == 1 ? kbits[3] : si == 2 ? kbits[5] : kbits[7];
+        }
         const int gc = ti.n0 + c0 + lc;
         const bool col_ok = lc < ncol && gc < p.N;
         const bool half = gc + 8 > p.N;     // N % 8 == 4: the last column group holds 4 columns (8-byte accesses only)
@@ -783,15 +791,22 @@ __device__ __forceinline__ void epilogue_fast(const TcParams& p, const EpiParams
                     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(sa_[0]), "f"(sa_[1]), "f"(sa_[2]), "f"(sa_[3]) : "memory");
                     if (!half) asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4), "f"(sa_[4]), "f"(sa_[5]), "f"(sa_[6]), "f"(sa_[7]) : "memory");
                 } else {
-                    float o[8], x[8];
+                    float o[8], x[8], kp[8];
                     if (HAS_AUX) unpack_bf16x8(g == 0 ? xa[u] : xb[u], x);
                     if (KIND == AVEC_EPI_SWISH && ep.out2) stg_bf16x8<AL16>(reinterpret_cast<bf16*>(ep.out2) + row * ep.ldo2 + gc, a, half);
 #pragma unroll
+                    for (int j = 0; j < 8; ++j) kp[j] = 1.0f;
+                    if (drop_on) {   // the mask avec_dropout draws for this (row, column group)
+                        const uint32_t kb = (g == 0 ? kw0 : kw1) >> (u * 8);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) kp[j] = ((kb >> j) & 1u) ? ep.drop_scale : 0.0f;
+                    }
+#pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        if (KIND == AVEC_EPI_LINEAR) o[j] = sa_[j];
-                        else if (KIND == AVEC_EPI_SWISH) o[j] = swishf_(a[j]);
-                        else if (KIND == AVEC_EPI_RESIDUAL) o[j] = x[j] + sa_[j];
-                        else if (KIND == AVEC_EPI_DSWISH) o[j] = sa_[j] * dswishf_(x[j]);
+                        if (KIND == AVEC_EPI_LINEAR) o[j] = sa_[j] * kp[j];
+                        else if (KIND == AVEC_EPI_SWISH) o[j] = swishf_(a[j]) * kp[j];
+                        else if (KIND == AVEC_EPI_RESIDUAL) o[j] = x[j] + sa_[j] * kp[j];
+                        else if (KIND == AVEC_EPI_DSWISH) o[j] = sa_[j] * dswishf_(x[j]) * kp[j];
                         else o[j] = fmaxf(sa_[j] + x[j], 0.0f);
                     }
                     stg_bf16x8<AL16>(reinterpret_cast<bf16*>(ep.out) + oi, o, half);
@@ -952,7 +967,17 @@ __device__ __forceinline__ void epilogue_warp(const TcParams& p, const EpiParams
 
 template <bool AL16>
 __device__ __forceinline__ void epilogue_fast_dispatch(const TcParams& p, const EpiParams& ep, const TileInfo& ti, uint32_t lane_addr, uint32_t stg_s,
-                                                       uint32_t bias_sa, float* stats_dst, int warp, int lane, bool bias_on, uint32_t rowrel_sa, int slab0, int slab_step) {
+                                                       uint32_t bias_sa, float* stats_dst, int warp, int lane, bool bias_on, uint32_t rowrel_sa, int slab0, int slab_step,
+                                                       const uint32_t* kbits) {
+    if (ep.drop_rng) {
+        switch (ep.kind) {
+        case AVEC_EPI_LINEAR: epilogue_fast<AVEC_EPI_LINEAR, false, AL16, true>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane, bias_on, rowrel_sa, slab0, slab_step, kbits); break;
+        case AVEC_EPI_SWISH: epilogue_fast<AVEC_EPI_SWISH, false, AL16, true>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane, bias_on, rowrel_sa, slab0, slab_step, kbits); break;
+        case AVEC_EPI_RESIDUAL: epilogue_fast<AVEC_EPI_RESIDUAL, false, AL16, true>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane, bias_on, rowrel_sa, slab0, slab_step, kbits); break;
+        default: epilogue_fast<AVEC_EPI_DSWISH, false, AL16, true>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane, bias_on, rowrel_sa, slab0, slab_step, kbits); break;
+        }
+        return;
+    }
     switch (ep.kind) {
     case AVEC_EPI_LINEAR:
         if (ep.colstats) epilogue_fast<AVEC_EPI_LINEAR, true, AL16>(p, ep, ti, lane_addr, stg_s, bias_sa, stats_dst, warp, lane, bias_on, rowrel_sa, slab0, slab_step);
@@ -971,6 +996,7 @@ __device__ __forceinline__ void epilogue_fast_dispatch(const TcParams& p, const 
 // of tile j overlaps the TMA + MMA main loop of tile j + 1.
 __global__ void __launch_bounds__(TC_THREADS_WIDE, 1) gemm_tc_kernel(const __grid_constant__ TcParams p, const __grid_constant__ CUtensorMap mapA,
                                                                const __grid_constant__ CUtensorMap mapB) {
+    pdl_trigger();   // programmatic dependent launch: a tcgen05 GEMM behind this kernel may start its prologue now
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem_al = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* halo = smem_al;                                   // [2 slots][cpb][halo_bytes] (halo mode only)
@@ -1034,6 +1060,9 @@ __global__ void __launch_bounds__(TC_THREADS_WIDE, 1) gemm_tc_kernel(const __gri
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // everything above touched only this CTA's shared memory / TMEM and the kernel parameters: with a programmatic dependent
+    // launch it overlapped the tail of the preceding kernel.  From here on global memory is read and written.
+    pdl_wait();
     if (tid == 0) AVEC_TS(1);   // setup done (barriers, TMEM alloc)
 
     if (warp < 4 || warp >= 6) {
@@ -1123,6 +1152,30 @@ __global__ void __launch_bounds__(TC_THREADS_WIDE, 1) gemm_tc_kernel(const __gri
                 // (L2, not L1: with ~220 KB of the SM's array carved out as shared memory there is next to no L1 to prefetch into)
                 for (int o = 0; o < nbytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(a0 + o));
             }
+            const int slab0 = grp * 64, slab_step = 64 * epi_groups;
+            // fused nn.Dropout: draw this thread's keep bits (one Philox call per row x 8 columns, <= 4 slabs x 8 rows) now, while
+            // the tile's MMAs are still in flight - the epilogue proper then only shifts bits.  Word [2 * slab + g], bit u * 8 + j.
+            uint32_t kbits[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+            if (p.ep.drop_rng) {
+                const unsigned long long seed = p.ep.drop_rng[0], step = p.ep.drop_rng[1];
+                const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+#pragma unroll
+                for (int si = 0; si < 4; ++si) {
+                    const int c0 = slab0 + si * slab_step;
+                    if (c0 < BN) {
+                        const uint32_t cg = (uint32_t)((n0 + c0 + (lane & 7) * 8) >> 3);
+#pragma unroll
+                        for (int gu = 0; gu < 8; ++gu) {
+                            const uint32_t drow = (uint32_t)(ti.row_base + qw * 32 + gu * 4 + (lane >> 3));
+                            const uint4 rb = philox4x32_10(make_uint4(drow, cg, p.ep.drop_site, (uint32_t)step), key);
+                            uint32_t m = 0u;
+#pragma unroll
+                            for (int jj = 0; jj < 8; ++jj) m |= (bits16(rb, jj) >= p.ep.drop_thresh ? 1u : 0u) << jj;
+                            kbits[si * 2 + (gu >> 2)] |= m << ((gu & 3) * 8);
+                        }
+                    }
+                }
+            }
             if (tid == 0) AVEC_TSJ(j, 0);
             if (AVEC_DBG_MODE(4)) mbar_wait_sleep(&accum_full[buf], (uint32_t)((j >> 1) & 1));
             else mbar_wait(&accum_full[buf], (uint32_t)((j >> 1) & 1));
@@ -1133,13 +1186,12 @@ __global__ void __launch_bounds__(TC_THREADS_WIDE, 1) gemm_tc_kernel(const __gri
             EpiParams ep = p.ep;
             ep.bias = nullptr;   // the bias slice lives in shared memory (bias_s)
             float* stg = (p.stg_dedicated ? reinterpret_cast<float*>(smem + (size_t)p.stages * stage_bytes) : reinterpret_cast<float*>(smem)) + grp * (STG_BYTES / 4) + qw * STG_WARP;
-            const int slab0 = grp * 64, slab_step = 64 * epi_groups;
             // BatchNorm statistics go to one of AVEC_STATS_REPLICAS copies of the accumulator (by tile index): 32x fewer
             // same-address L2 reductions
             float* stats_dst = ep.colstats ? ep.colstats + (size_t)(ti.mtile % AVEC_STATS_REPLICAS) * 2 * p.N : nullptr;
             const bool bias_on = p.ep.bias != nullptr && ti.z == 0;
-            if (p.epi_fast == 2) epilogue_fast_dispatch<true>(p, ep, ti, lane_addr, smem_u32(stg), smem_u32(bias_s), stats_dst, qw, lane, bias_on, smem_u32(rinfo), slab0, slab_step);
-            else if (p.epi_fast == 1) epilogue_fast_dispatch<false>(p, ep, ti, lane_addr, smem_u32(stg), smem_u32(bias_s), stats_dst, qw, lane, bias_on, smem_u32(rinfo), slab0, slab_step);
+            if (p.epi_fast == 2) epilogue_fast_dispatch<true>(p, ep, ti, lane_addr, smem_u32(stg), smem_u32(bias_s), stats_dst, qw, lane, bias_on, smem_u32(rinfo), slab0, slab_step, kbits);
+            else if (p.epi_fast == 1) epilogue_fast_dispatch<false>(p, ep, ti, lane_addr, smem_u32(stg), smem_u32(bias_s), stats_dst, qw, lane, bias_on, smem_u32(rinfo), slab0, slab_step, kbits);
             else epilogue_warp(p, ep, ti, lane_addr, stg, bias_s, stats_dst, qw, lane, slab0, slab_step);
             // all TMEM reads of this buffer are complete: hand it back to the MMA warp
             tc_fence_before();
@@ -2161,6 +2213,23 @@ static int g_tma_enabled = 1;
 static bool g_tma_enabled_flag() { return g_tma_enabled != 0; }
 static unsigned long long* g_dbg_ts = nullptr;
 extern "C" void avec_set_tma(int enabled) { g_tma_enabled = enabled; }
+static int g_pdl_enabled = 1;
+static cudaStream_t g_pdl_excluded[8];
+static int g_pdl_nexcluded = 0;
+extern "C" void avec_set_pdl(int enabled) { g_pdl_enabled = enabled; }
+extern "C" void avec_pdl_exclude_stream(avec_stream_t stream, int enabled) {
+    if (!enabled) { g_pdl_nexcluded = 0; return; }
+    cudaStream_t st = as_stream(stream);
+    for (int i = 0; i < g_pdl_nexcluded; ++i) if (g_pdl_excluded[i] == st) return;
+    if (g_pdl_nexcluded < 8) g_pdl_excluded[g_pdl_nexcluded++] = st;
+}
+static bool pdl_for_stream(cudaStream_t st) {
+    static int env = -1;
+    if (env < 0) { const char* e = getenv("AVEC_PDL"); env = e ? atoi(e) : 1; }
+    if (!env || !g_pdl_enabled) return false;
+    for (int i = 0; i < g_pdl_nexcluded; ++i) if (g_pdl_excluded[i] == st) return false;
+    return true;
+}
 extern "C" void avec_set_debug_timestamps(void* dev_buf_8_u64) { g_dbg_ts = reinterpret_cast<unsigned long long*>(dev_buf_8_u64); }
 
 bool avec_gemm_tc_supported(const avec_gemm_args* a) {
@@ -2587,6 +2656,7 @@ static int gemm_tc_launch(const avec_gemm_args* a, cudaStream_t st, const DgradC
         p.epi_fast = ok && al >= 8 ? (al >= 16 ? 2 : 1) : 0;
     }
     if (dc && (!p.epi_fast || p.b_kind != OP_TMA_K)) return AVEC_ERR_UNSUPPORTED;
+    if (p.ep.drop_rng && (!p.epi_fast || p.rm_on)) return AVEC_ERR_UNSUPPORTED;   // fused dropout lives in the fast epilogue only
     p.grid_m = grid_m; p.grid_n = cdiv(a->N, p.BN); p.splits = split;
     const long long tiles = (long long)p.grid_m * p.grid_n * p.splits;
     if (tiles > 0x7fffffffLL) return AVEC_ERR_INVALID;
@@ -2594,6 +2664,24 @@ static int gemm_tc_launch(const avec_gemm_args* a, cudaStream_t st, const DgradC
     // persistent launch when both operands are TMA-fed (the gather producers double as epilogue warps, so gather kinds keep
     // one tile per CTA); two CTAs per SM when shared memory and TMEM (2 x BN columns each) allow it
     long long ctas = any_gather ? tiles : std::min<long long>(tiles, (long long)num_sms * ctas_per_sm);
+    if (pdl_for_stream(st)) {
+        // programmatic dependent launch: this grid may be scheduled while the preceding kernel of the stream drains (after all its
+        // CTAs passed pdl_trigger() or exited); its CTAs set up barriers / TMEM / descriptors and then wait in pdl_wait()
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3((unsigned)ctas, 1, 1);
+        cfg.blockDim = dim3(epi_groups == 2 ? TC_THREADS_WIDE : TC_THREADS, 1, 1);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, gemm_tc_kernel, p, mapA, mapB);
+        AVEC_LAUNCH_CHECK();
+        return AVEC_OK;
+    }
     gemm_tc_kernel<<<(unsigned)ctas, epi_groups == 2 ? TC_THREADS_WIDE : TC_THREADS, smem, st>>>(p, mapA, mapB);
     AVEC_LAUNCH_CHECK();
     return AVEC_OK;

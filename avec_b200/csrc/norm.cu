@@ -16,6 +16,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const T* __restrict_
                                                             const float* __restrict__ beta, T* __restrict__ y,
                                                             float* __restrict__ mean, float* __restrict__ rstd, int B,
                                                             int Tn, int Tp, int C, int P, float eps, long long ldy) {
+    pdl_trigger();   // programmatic dependent launch: a tcgen05 GEMM behind this kernel may start its prologue now
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= B * Tp) return;
     const int b = warp / Tp, tp = warp % Tp;
@@ -91,6 +92,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict_
                                                             const float* __restrict__ rstd, const T* __restrict__ dres,
                                                             int res_stride, T* __restrict__ dx, float* __restrict__ dgamma,
                                                             float* __restrict__ dbeta, int B, int Tn, int Tp, int C, int P) {
+    pdl_trigger();   // programmatic dependent launch: a tcgen05 GEMM behind this kernel may start its prologue now
     extern __shared__ float red[];  // [2][C]
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const long long rows = (long long)B * Tn;
@@ -197,6 +199,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict_
 template <typename T, int V>
 __global__ void upsample_add_kernel(const T* __restrict__ x, const T* __restrict__ o, T* __restrict__ y, int Tn, int Tp, int C,
                                     int P, long long total) {
+    pdl_trigger();   // programmatic dependent launch: a tcgen05 GEMM behind this kernel may start its prologue now
     const int Cv = C / V;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         int c = (int)(i % Cv) * V;
@@ -214,6 +217,7 @@ __global__ void upsample_add_kernel(const T* __restrict__ x, const T* __restrict
 
 template <typename T, int V>
 __global__ void pool_sum_kernel(const T* __restrict__ dy, T* __restrict__ dout, int Tn, int Tp, int C, int P, long long total, long long ldo) {
+    pdl_trigger();   // programmatic dependent launch: a tcgen05 GEMM behind this kernel may start its prologue now
     const int Cv = C / V;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         int c = (int)(i % Cv) * V;
@@ -297,6 +301,7 @@ constexpr int CR_THREADS = 512;
 template <typename F, int V>
 __global__ void __launch_bounds__(CR_THREADS) colreduce_kernel(F f_in, long long rows, int C, long long rows_per_block,
                                                                float* __restrict__ out0, float* __restrict__ out1, float alpha) {
+    pdl_trigger();   // programmatic dependent launch: a tcgen05 GEMM behind this kernel may start its prologue now
     __shared__ float s0[CR_THREADS * V];
     __shared__ float s1[CR_THREADS * V];
     F f = f_in;
@@ -603,6 +608,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, const float*
                                    float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean,
                                    float* __restrict__ rstd, float* __restrict__ rmean, float* __restrict__ rvar,
                                    float inv_count, float unbias, int C, float eps, float momentum, int replicas) {
+    pdl_trigger();   // programmatic dependent launch: a tcgen05 GEMM behind this kernel may start its prologue now
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     float s1 = 0.0f, s2 = 0.0f;
@@ -864,6 +870,7 @@ __global__ void zero_upsample_kernel(const T* __restrict__ in, T* __restrict__ o
 
 template <typename TI, typename TO>
 __global__ void convert_kernel(const TI* __restrict__ src, long long lds, TO* __restrict__ dst, long long ldd, int C, long long total) {
+    pdl_trigger();   // programmatic dependent launch: a tcgen05 GEMM behind this kernel may start its prologue now
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         int c = (int)(i % C);
         long long r = i / C;
@@ -872,6 +879,7 @@ __global__ void convert_kernel(const TI* __restrict__ src, long long lds, TO* __
 }
 // contiguous fp32 -> bf16, 8 elements per thread
 __global__ void convert_f32_bf16_vec_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long totalv) {
+    pdl_trigger();   // programmatic dependent launch: a tcgen05 GEMM behind this kernel may start its prologue now
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < totalv; i += (long long)gridDim.x * blockDim.x) {
         float v[8];
         load_vec<8>(src + i * 8, v);
@@ -1154,6 +1162,7 @@ extern "C" int avec_convert_multi(const avec_copy_job* jobs_dev, const int* chun
 }
 
 __global__ void __launch_bounds__(256) unpad_heads_kernel(const float* __restrict__ src, float* __restrict__ dst, int d, int dp, long long K, long long total) {
+    pdl_trigger();   // programmatic dependent launch: a tcgen05 GEMM behind this kernel may start its prologue now
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long c = i % K, row = i / K;
         const long long g = row / d, r = row - g * d;

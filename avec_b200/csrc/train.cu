@@ -5,27 +5,7 @@
 // CUDA graph draws fresh masks on every replay (the step counter is advanced by a kernel inside the graph).
 #include "common.cuh"
 
-// ---------------------------------------------------------------------------------------------------- Philox4x32-10
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
-        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
-        k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
-    }
-    return c;
-}
-
-// 16 random bits of element (row, col): word (col & 7) >> 1 of Philox(ctr = (row, col >> 3, site, step), key = seed)
-__device__ __forceinline__ uint4 dropout_bits(const unsigned long long* rng, uint32_t site, uint32_t row, uint32_t grp) {
-    const unsigned long long seed = rng[0], step = rng[1];
-    return philox4x32_10(make_uint4(row, grp, site, (uint32_t)step), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-}
-__device__ __forceinline__ uint32_t bits16(const uint4& r, int j) {   // j = 0..7
-    const uint32_t w = (j >> 1) == 0 ? r.x : (j >> 1) == 1 ? r.y : (j >> 1) == 2 ? r.z : r.w;
-    return (j & 1) ? (w >> 16) : (w & 0xFFFFu);
-}
+// (Philox4x32-10, dropout_bits and bits16 live in common.cuh: the tcgen05 GEMM epilogue draws the same masks)
 
 __global__ void counter_advance_kernel(unsigned long long* ctr) { ctr[0] += 1ull; }
 
@@ -43,6 +23,7 @@ __global__ void __launch_bounds__(256) dropout_kernel(const T* __restrict__ x, c
                                                       long long rows, int C, uint32_t thresh, float scale,
                                                       const unsigned long long* __restrict__ rng, uint32_t site, int Tf, int Tp,
                                                       int P, long long ldy) {
+    pdl_trigger();   // programmatic dependent launch: a tcgen05 GEMM behind this kernel may start its prologue now
     const int per_row = (C + V - 1) / V;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows * per_row) return;

@@ -195,17 +195,12 @@ class FFNFn(Function):
         B, T, D = x.shape
         x = _c(x)
         xn, mean, rstd = ops.layernorm_fwd(x, ln_w, ln_b)
-        h, pre = ops.linear_fwd(xn.view(B * T, D), wc(w1), b1, L.EPI_SWISH, want_pre=True)
-        s_in = s_out = 0
         ctx.rng = ops.RNG.cur(x.device)
-        if p_in > 0:
-            s_in = ops.RNG.next_site()
-            ops.dropout_rng(ctx.rng, h, p_in, s_in, out=h)
-        if p_out > 0:
-            s_out = ops.RNG.next_site()
-            y = ops.dropout_rng(ctx.rng, ops.linear_fwd(h, wc(w2), b2), p_out, s_out, res=x.view(B * T, D), alpha=0.5)
-        else:
-            y = ops.linear_fwd(h, wc(w2), b2, L.EPI_RESIDUAL, alpha=0.5, aux=x.view(B * T, D))
+        # both nn.Dropout layers ride in the epilogue of the GEMM in front of them (same Philox mask as avec_dropout)
+        s_in = ops.RNG.next_site() if p_in > 0 else 0
+        s_out = ops.RNG.next_site() if p_out > 0 else 0
+        h, pre = ops.linear_fwd(xn.view(B * T, D), wc(w1), b1, L.EPI_SWISH, want_pre=True, drop=(ctx.rng, p_in, s_in))
+        y = ops.linear_fwd(h, wc(w2), b2, L.EPI_RESIDUAL, alpha=0.5, aux=x.view(B * T, D), drop=(ctx.rng, p_out, s_out))
         ctx.save_for_backward(x, ln_w, mean, rstd, xn, pre, h, w1, w2)
         ctx.drop = (p_in, s_in, p_out, s_out)
         return y.view(B, T, D)
@@ -222,9 +217,7 @@ class FFNFn(Function):
             dyd, a = ops.dropout_rng(ctx.rng, dy2, p_out, s_out, alpha=0.5, pad_out=True), 1.0
         else:
             dyd, a = dy2, 0.5
-        dpre = ops.linear_dgrad(dyd, wc(w2), L.EPI_DSWISH, alpha=a, aux=pre)
-        if p_in > 0:
-            ops.dropout_rng(ctx.rng, dpre, p_in, s_in, out=dpre)
+        dpre = ops.linear_dgrad(dyd, wc(w2), L.EPI_DSWISH, alpha=a, aux=pre, drop=(ctx.rng, p_in, s_in))
         dw2 = ops.linear_wgrad(dyd, h, alpha=a)
         db2 = ops.colsum(dyd, a)
         dxn = ops.linear_dgrad(dpre, wc(w1))
@@ -277,7 +270,10 @@ class AttentionFn(Function):
         site = 0
         plain = ln_w is None          # attention.forwardQKV: no LayerNorm in front, no residual behind (modules.py:330)
         res = None if plain else x.view(B * T, D)
-        if p_drop > 0 or (plain and P > 1):
+        if p_drop > 0 and P == 1:
+            site = ops.RNG.next_site()
+            y = ops.linear_fwd(o, wop, bo, L.EPI_LINEAR if plain else L.EPI_RESIDUAL, aux=res, drop=(ctx.rng, p_drop, site)).view(B, T, D)
+        elif p_drop > 0 or (plain and P > 1):
             # AttentionModule.dropout acts on the upsampled (B, T, D) output: one mask element per frame (modules.py:333)
             site = ops.RNG.next_site() if p_drop > 0 else 0
             proj = ops.linear_fwd(o, wop, bo)
@@ -367,7 +363,8 @@ class GroupedAttentionFn(Function):
         plain = ln_w is None
         if p_drop > 0:
             site = ops.RNG.next_site()
-            y = ops.dropout_rng(ctx.rng, ops.linear_fwd(o, wc(wo), bo), p_drop, site, res=x.view(B * T, D)).view(B, T, D)
+            y = ops.linear_fwd(o, wc(wo), bo, L.EPI_LINEAR if plain else L.EPI_RESIDUAL, aux=None if plain else x.view(B * T, D),
+                               drop=(ctx.rng, p_drop, site)).view(B, T, D)
         elif plain:
             y = ops.linear_fwd(o, wc(wo), bo).view(B, T, D)
         else:
@@ -442,7 +439,7 @@ class ConvModuleFn(Function):
         site = 0
         if p_drop > 0:
             site = ops.RNG.next_site()
-            y = ops.dropout_rng(ctx.rng, ops.linear_fwd(v, wc(w3), b3), p_drop, site, res=aux).view(B, To, De)
+            y = ops.linear_fwd(v, wc(w3), b3, L.EPI_RESIDUAL, aux=aux, drop=(ctx.rng, p_drop, site)).view(B, To, De)
         else:
             y = ops.linear_fwd(v, wc(w3), b3, L.EPI_RESIDUAL, aux=aux).view(B, To, De)
         ctx.save_for_backward(x, ln_w, mean, rstd, xn, pre, u, bnbuf, v, xs, w1, wd, bn_w, w3, wr)

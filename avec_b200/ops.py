@@ -71,13 +71,46 @@ def launch_count():
     return L.load().avec_launch_count()
 
 
+def set_pdl(enabled):
+    """programmatic dependent launch of the tcgen05 GEMM kernel (on by default)"""
+    L.load().avec_set_pdl(int(bool(enabled)))
+
+
+def pdl_exclude_stream(stream, enabled=True):
+    """GEMMs launched on `stream` (torch.cuda.Stream) are serialised the ordinary way: for a secondary stream whose early-scheduled
+    CTAs would take shared memory from the critical-path stream"""
+    L.load().avec_pdl_exclude_stream(stream.cuda_stream if stream is not None else None, int(bool(enabled)))
+
+
 def reset_launch_count():
     L.load().avec_reset_launch_count()
 
 
 # --------------------------------------------------------------------------------------------------------------- GEMM
-def _gemm(args):
-    L.check(L.load().avec_gemm(args, _stream()), "avec_gemm")
+def _gemm(args, may_decline=False):
+    """may_decline: AVEC_ERR_UNSUPPORTED is an answer (False), not an error - nothing was launched"""
+    rc = L.load().avec_gemm(args, _stream())
+    if may_decline and rc == ERR_UNSUPPORTED:
+        return False
+    L.check(rc, "avec_gemm")
+    return True
+
+
+ERR_UNSUPPORTED = -3
+FUSE_DROPOUT = os.environ.get("AVEC_FUSE_DROPOUT", "1") != "0"
+
+
+def _gemm_drop(args, drop):
+    """launch with nn.Dropout fused into the epilogue (drop = (rng, p, site)); False: this operand / epilogue combination has no
+    fused form (fp32 parity mode, SIMT implementation, unaligned rows) and the caller runs GEMM + avec_dropout instead."""
+    if not FUSE_DROPOUT:
+        return False
+    rng, p, site = drop
+    args.drop_p, args.drop_site, args.drop_rng = float(p), int(site), rng.data_ptr()
+    if not _gemm(args, True):
+        args.drop_p, args.drop_rng = 0.0, None
+        return False
+    return True
 
 
 def _epi(args, epi, alpha, bias, out, out2=None, aux=None, colstats=None):
@@ -101,8 +134,10 @@ def _split_for(M, N, K):
     return max(1, min(kb // 8 if kb >= 16 else 1, max(1, 160 // max(1, tiles)), 512))
 
 
-def linear_fwd(x, w, bias=None, epi=L.EPI_LINEAR, alpha=1.0, aux=None, out_dtype=None, want_pre=False, colstats=None):
-    """out[M,N] = epi(x[M,K] @ w[N,K]^T + bias).  x, w same dtype, row-major (w may have a padded leading dim)."""
+def linear_fwd(x, w, bias=None, epi=L.EPI_LINEAR, alpha=1.0, aux=None, out_dtype=None, want_pre=False, colstats=None, drop=None):
+    """out[M,N] = epi(x[M,K] @ w[N,K]^T + bias).  x, w same dtype, row-major (w may have a padded leading dim).
+    drop = (rng, p, site): nn.Dropout behind the GEMM with the mask avec_dropout draws for (rng, site) -
+    LINEAR: drop(acc), SWISH: drop(swish(acc)) (the pre-activation copy stays whole), RESIDUAL: aux + alpha * drop(acc)."""
     _cuda(x, w)
     M, K = x.shape
     N = w.shape[0]
@@ -113,13 +148,28 @@ def linear_fwd(x, w, bias=None, epi=L.EPI_LINEAR, alpha=1.0, aux=None, out_dtype
     a.A, a.sam, a.sak = x.data_ptr(), x.stride(0), 1
     a.B, a.sbn, a.sbk = w.data_ptr(), w.stride(0), 1
     a.ab_dtype = _dt(x)
+    if drop is not None and drop[1] > 0:
+        _epi(a, epi, alpha, bias, out, pre, aux, colstats)
+        if not _gemm_drop(a, drop):
+            if epi == L.EPI_RESIDUAL:      # aux + alpha * drop(acc): plain GEMM, then the dropout kernel adds the residual
+                _epi(a, L.EPI_LINEAR, 1.0, bias, out, pre, None, colstats)
+                a.aux = None
+                _gemm(a)
+                assert aux.is_contiguous() and aux.dtype == out.dtype
+                dropout_rng(drop[0], out, drop[1], drop[2], res=aux, alpha=alpha, out=out)
+            else:
+                assert epi in (L.EPI_LINEAR, L.EPI_SWISH)
+                _gemm(a)
+                dropout_rng(drop[0], out, drop[1], drop[2], out=out)
+        return (out, pre) if want_pre else out
     _epi(a, epi, alpha, bias, out, pre, aux, colstats)
     _gemm(a)
     return (out, pre) if want_pre else out
 
 
-def linear_dgrad(dy, w, epi=L.EPI_LINEAR, alpha=1.0, aux=None, out_dtype=None):
-    """dx[M,K] = epi(dy[M,N] @ w[N,K])  (B operand read transposed in place: MN-major descriptor, no copy)."""
+def linear_dgrad(dy, w, epi=L.EPI_LINEAR, alpha=1.0, aux=None, out_dtype=None, drop=None):
+    """dx[M,K] = epi(dy[M,N] @ w[N,K])  (B operand read transposed in place: MN-major descriptor, no copy).
+    drop = (rng, p, site): the gradient of an nn.Dropout in front of this layer's input, i.e. drop(epi(..)) with the forward's mask."""
     _cuda(dy, w)
     M, N = dy.shape
     K = w.shape[1]
@@ -130,6 +180,11 @@ def linear_dgrad(dy, w, epi=L.EPI_LINEAR, alpha=1.0, aux=None, out_dtype=None):
     a.B, a.sbn, a.sbk = w.data_ptr(), 1, w.stride(0)
     a.ab_dtype = _dt(dy)
     _epi(a, epi, alpha, None, out, None, aux)
+    if drop is not None and drop[1] > 0:
+        if not _gemm_drop(a, drop):
+            _gemm(a)
+            dropout_rng(drop[0], out, drop[1], drop[2], out=out)
+        return out
     _gemm(a)
     return out
 

@@ -575,12 +575,14 @@ def profile_gemm(step_fn, ops):
     for _ in range(3):
         recs = []
 
-        def hooked(a, recs=recs):
+        def hooked(a, may_decline=False, recs=recs):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            orig(a)
+            launched = orig(a, may_decline)
             e1.record()
-            recs.append((e0, e1) + describe(a))
+            if launched is not False:      # (a GEMM with a fused dropout may decline: the un-fused pair follows and is recorded)
+                recs.append((e0, e1) + describe(a))
+            return launched
 
         def timed_stem(fn, name, recs=recs):
             def wrapper(x, *a, **k):

@@ -99,11 +99,24 @@ typedef struct avec_gemm_args {
     float* colstats; /* optional [32][2*N] (32 replicas selected by CTA index, summed by avec_bn_finalize):
                         += sum_m v, += sum_m v^2 of v = acc + bias (BatchNorm batch statistics) */
     int split_k;     /* ACCUM epilogue: number of K slices (0/1 = none) */
+    /* nn.Dropout fused behind the GEMM (drop_p > 0; tcgen05 path with bf16 output, else AVEC_ERR_UNSUPPORTED and the caller runs
+     * avec_dropout): the epilogue's value BEFORE the residual add is multiplied by keep / (1 - p) with the mask avec_dropout draws
+     * for (rng_state, site) - LINEAR alpha*drop(acc+bias), SWISH drop(swish(.)), RESIDUAL aux + alpha*drop(acc+bias),
+     * DSWISH drop(alpha*acc*swish'(aux)) */
+    float drop_p;
+    int drop_site;
+    const unsigned long long* drop_rng;
 } avec_gemm_args;
 
 int avec_gemm(const avec_gemm_args* args, avec_stream_t stream);
 /* diagnostics: 0 forces the cp.async gather producers even where a TMA descriptor is possible (default 1) */
 void avec_set_tma(int enabled);
+/* Programmatic dependent launch of the tcgen05 GEMM kernel (default on; AVEC_PDL=0 in the environment disables it for the process):
+ * the grid may be scheduled while the preceding kernel of its stream drains and overlaps its prologue (barriers, TMEM allocation,
+ * descriptor prefetch) with that tail.  avec_pdl_exclude_stream: launches on this stream keep the ordinary full serialisation - for a
+ * secondary stream whose parked CTAs would take shared memory from the critical-path stream (<= 8 streams; enabled = 0 clears the list) */
+void avec_set_pdl(int enabled);
+void avec_pdl_exclude_stream(avec_stream_t stream, int enabled);
 /* diagnostics: device buffer of 232 uint64; CTA (0,0,0) of every tcgen05 GEMM launch records %globaltimer (ns) at
  * [0] start, [1] setup done, [2] first k-block in smem, [3] last MMA issued, [4] accumulator complete, [5] epilogue
  * done, [6] TMEM released; [8 + 5 j + k], j < 32: per-tile timeline of that CTA (k = 0 epilogue starts waiting,

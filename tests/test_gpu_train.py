@@ -49,6 +49,63 @@ def test_dropout_mask_bit_exact(dtype, rows, C):
     assert torch.equal(xi != 0, keep2 & (x != 0))
 
 
+@pytest.mark.parametrize("M,N,K", [(515, 180, 720), (300, 720, 180), (1000, 256, 256), (70, 360, 1440)])
+def test_dropout_fused_into_gemm_epilogue(M, N, K):
+    """nn.Dropout riding in the tcgen05 GEMM's epilogue (LINEAR / SWISH / RESIDUAL forward, DSWISH backward): exactly the keep mask
+    of the oracle (oracle/train_oracle.py dropout_keep) for (seed, step, site), values = mask * the undropped GEMM, and the pitched
+    D = 180 rows included; the un-fused fallback (AVEC_FUSE_DROPOUT=0) agrees to bf16 rounding."""
+    from avec_b200 import _lib as L
+    _set_rng(SEED, 4)
+    rng = ops.RNG.get(DEV)
+    p, site = 0.1, 23
+    x = ops.convert(seeded.randn("fdrop.x", (M, K), 1).to(DEV), torch.bfloat16, pad=True)
+    w = ops.convert(0.05 * seeded.randn("fdrop.w", (N, K), 2).to(DEV), torch.bfloat16, pad=True)
+    b = 0.1 * seeded.randn("fdrop.b", (N,), 3).to(DEV)
+    aux = seeded.randn("fdrop.a", (M, N), 4).to(DEV).to(torch.bfloat16)
+    keep = torch.from_numpy(TO.dropout_keep(SEED, 4, site, M, N, p)).to(DEV)
+    scale = 1.0 / (1.0 - p)
+    acc = x.float() @ w.float().t() + b
+    cases = {
+        "linear": (dict(epi=L.EPI_LINEAR), acc * scale, None),
+        "swish": (dict(epi=L.EPI_SWISH, want_pre=True), acc * torch.sigmoid(acc) * scale, None),
+        "residual": (dict(epi=L.EPI_RESIDUAL, alpha=0.5, aux=aux), 0.5 * acc * scale, aux.float()),
+    }
+    for name, (kw, val, res) in cases.items():
+        want = torch.where(keep, val, torch.zeros((), device=DEV)) + (res if res is not None else 0.0)
+        got = {}
+        for fused in (True, False):
+            ops.FUSE_DROPOUT = fused
+            try:
+                n0 = avec_b200.launch_count()
+                out = ops.linear_fwd(x, w, b, drop=(rng, p, site), **kw)
+                got[fused] = (out, avec_b200.launch_count() - n0)
+            finally:
+                ops.FUSE_DROPOUT = True
+        assert got[True][1] == 1 and got[False][1] == 2, f"{name}: launches {got[True][1]} / {got[False][1]}"
+        y = got[True][0][0] if name == "swish" else got[True][0]
+        y0 = got[False][0][0] if name == "swish" else got[False][0]
+        assert rel_err(y, want) < 4e-3, f"{name}: {rel_err(y, want)}"
+        assert rel_err(y, y0) < 6e-3, f"{name} fused vs separate: {rel_err(y, y0)}"
+        if res is None:
+            nz = val.abs() > 1e-3                 # values that survive the bf16 rounding
+            assert torch.equal((y != 0) & nz, keep & nz), name
+        if name == "swish":
+            assert rel_err(got[True][0][1], acc) < 4e-3       # the saved pre-activation is NOT masked
+    # backward of FFN's inner dropout: drop(dswish(pre) * (dy @ W))
+    dy = ops.convert(seeded.randn("fdrop.dy", (M, N), 5).to(DEV), torch.bfloat16, pad=True)
+    pre = seeded.randn("fdrop.pre", (M, K), 6).to(DEV).to(torch.bfloat16)
+    keep_k = torch.from_numpy(TO.dropout_keep(SEED, 4, site, M, K, p)).to(DEV)
+    sg = torch.sigmoid(pre.float())
+    val = (dy.float() @ w.float()) * (sg * (1 + pre.float() * (1 - sg))) * scale
+    want = torch.where(keep_k, val, torch.zeros((), device=DEV))
+    n0 = avec_b200.launch_count()
+    dpre = ops.linear_dgrad(dy, w, L.EPI_DSWISH, aux=pre, drop=(rng, p, site))
+    assert avec_b200.launch_count() - n0 == 1
+    assert rel_err(dpre, want) < 4e-3, rel_err(dpre, want)
+    nz = val.abs() > 1e-3
+    assert torch.equal((dpre != 0) & nz, keep_k & nz)
+
+
 def test_dropout_after_patch_upsampling():
     _set_rng(SEED, 0)
     B, T, P, C = 3, 20, 3, 180
