@@ -1,6 +1,7 @@
 // Library-level entry points: status strings, diagnostics and the avec_gemm dispatcher.
 #include "common.cuh"
 #include <atomic>
+#include <cstdlib>
 
 static thread_local int g_last_cuda_error = 0;
 // process-wide: the autograd backward of the host mirror runs on PyTorch's backward thread, the forward on the caller's
@@ -8,6 +9,31 @@ static std::atomic<long long> g_launches{0};
 
 void avec_set_last_cuda_error(int e) { g_last_cuda_error = e; }
 void avec_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// ---- programmatic dependent launch policy (see common.cuh avec_launch_pdl) ---------------------------------------------------
+static int g_pdl_enabled = 1;
+static cudaStream_t g_pdl_excluded[8];
+static int g_pdl_nexcluded = 0;
+extern "C" void avec_set_pdl(int enabled) { g_pdl_enabled = enabled; }
+extern "C" void avec_pdl_exclude_stream(avec_stream_t stream, int enabled) {
+    if (!enabled) { g_pdl_nexcluded = 0; return; }
+    cudaStream_t st = as_stream(stream);
+    for (int i = 0; i < g_pdl_nexcluded; ++i) if (g_pdl_excluded[i] == st) return;
+    if (g_pdl_nexcluded < 8) g_pdl_excluded[g_pdl_nexcluded++] = st;
+}
+bool avec_pdl_for_stream(cudaStream_t st) {
+    static int env = -1;
+    if (env < 0) { const char* e = getenv("AVEC_PDL"); env = e ? atoi(e) : 1; }
+    if (!env || !g_pdl_enabled) return false;
+    for (int i = 0; i < g_pdl_nexcluded; ++i) if (g_pdl_excluded[i] == st) return false;
+    return true;
+}
+// AVEC_PDL=1: the tcgen05 GEMM only; 2 (default): also the small latency-bound kernels around it
+bool avec_pdl_small_kernels() {
+    static int env = -1;
+    if (env < 0) { const char* e = getenv("AVEC_PDL"); env = e ? atoi(e) : 2; }
+    return env >= 2;
+}
 
 int avec_gemm_simt(const avec_gemm_args* a, cudaStream_t st);
 int avec_gemm_tc(const avec_gemm_args* a, cudaStream_t st);       // gemm_tc.cu

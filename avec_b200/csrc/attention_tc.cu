@@ -121,6 +121,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) relpos_attn_tc_fwd_kernel(const
     const int h = idx % p.H, b = idx / p.H;
     const int i0 = qb * 128, T = p.T, H = p.H, dp = p.dp, ndb = p.ndb;
     setup(bars, tid, warp, &mapQKV, &mapE, nullptr);
+    pdl_wait();      // barriers / TMEM / descriptor prefetch above overlapped the kernel in front; global memory from here on
     const uint32_t tmem = bars->tmem;
     const uint32_t ring_s = smem_u32(ring), p_s = smem_u32(ptile);
 
@@ -276,6 +277,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1) relpos_attn_tc_bwd_kernel(const
     const int h = idx % p.H, b = idx / p.H;
     const int i0 = qb * 128, T = p.T, H = p.H, dp = p.dp, ndb = p.ndb;
     setup(bars, tid, warp, &mapQKV, &mapE, &mapDO);
+    pdl_wait();      // (as in the forward kernel)
     const uint32_t tmem = bars->tmem;
     const uint32_t ring_s = smem_u32(ring), p_s = smem_u32(ptile), ds_s = smem_u32(dstile), dsb_s = smem_u32(dsb);
     const bool single = p.nqb == 1 && p.nkb == 1;
@@ -627,7 +629,7 @@ extern "C" int avec_relpos_attn_tc_fwd(const void* qkv, long long ld_qkv, const 
     if (!attr_once(0, reinterpret_cast<const void*>(relpos_attn_tc_fwd_kernel), 227 * 1024)) return AVEC_ERR_LAUNCH;
     const long long ctas = (long long)B * H * p.nqb;
     if (ctas > 0x7fffffffLL) return AVEC_ERR_INVALID;
-    relpos_attn_tc_fwd_kernel<<<(unsigned)ctas, AT_THREADS, smem, as_stream(stream)>>>(p, mq, me);
+    avec_launch_pdl(relpos_attn_tc_fwd_kernel, dim3((unsigned)ctas), dim3(AT_THREADS), smem, as_stream(stream), false, p, mq, me);
     AVEC_LAUNCH_CHECK();
     return AVEC_OK;
 }
@@ -663,7 +665,7 @@ extern "C" int avec_relpos_attn_tc_bwd(const void* d_o, long long ld_do, const v
     if (!attr_once(1, reinterpret_cast<const void*>(relpos_attn_tc_bwd_kernel), 227 * 1024)) return AVEC_ERR_LAUNCH;
     const long long ctas = (long long)B * H * p.nqb;
     if (ctas > 0x7fffffffLL) return AVEC_ERR_INVALID;
-    relpos_attn_tc_bwd_kernel<<<(unsigned)ctas, AT_THREADS, smem, as_stream(stream)>>>(p, mq, me, mdo);
+    avec_launch_pdl(relpos_attn_tc_bwd_kernel, dim3((unsigned)ctas), dim3(AT_THREADS), smem, as_stream(stream), false, p, mq, me, mdo);
     AVEC_LAUNCH_CHECK();
     return AVEC_OK;
 }

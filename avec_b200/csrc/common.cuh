@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <string.h>
 #include "../../include/avec_b200.h"
 
 #define AVEC_CHECK_ARG(cond) do { if (!(cond)) return AVEC_ERR_INVALID; } while (0)
@@ -11,11 +12,39 @@
 void avec_set_last_cuda_error(int e);
 void avec_count_launch();
 
+bool avec_pdl_for_stream(cudaStream_t st);     // api.cu
+bool avec_pdl_small_kernels();                  // api.cu
+
 static inline cudaStream_t as_stream(avec_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline long long cdivll(long long a, long long b) { return (a + b - 1) / b; }
 
 typedef __nv_bfloat16 bf16;
+
+// Launch `kernel` as a programmatic dependent of the kernel in front of it on the stream when the policy allows (`force`, or a
+// grid of at most two waves of threads: parked CTAs of a large grid would take registers and thread slots
+// from kernels of other streams), else the ordinary way.  EVERY kernel launched through this helper executes pdl_wait() before its
+// first global-memory access - that is what keeps the stream's ordering intact.
+template <typename... KArgs, typename... Args>
+static inline void avec_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool force, Args&&... args) {
+    const unsigned long long threads = (unsigned long long)grid.x * grid.y * grid.z * block.x * block.y * block.z;
+    if (avec_pdl_for_stream(st) && (force || (avec_pdl_small_kernels() && threads <= 148ull * 4096ull))) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = grid;
+        cfg.blockDim = block;
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+    } else {
+        kernel<<<grid, block, smem, st>>>(static_cast<KArgs>(args)...);
+    }
+}
 
 // BatchNorm column statistics are accumulated into one of AVEC_STATS_REPLICAS copies (selected by CTA index) to spread the
 // same-address L2 atomics; avec_bn_finalize sums the copies.

@@ -19,7 +19,8 @@ __global__ void __launch_bounds__(DW_CH) glu_dwconv_fwd_kernel(const T* __restri
                                                                const float* __restrict__ bias, T* __restrict__ u,
                                                                float* __restrict__ stats, int Tn, int To, int C, int ksize,
                                                                int stride, int pad) {
-    pdl_trigger();   // programmatic dependent launch: a tcgen05 GEMM behind this kernel may start its prologue now
+    pdl_wait();      // (launched through avec_launch_pdl: nothing before this line touches global memory)
+    pdl_trigger();   // the kernel behind this one may be scheduled now
     extern __shared__ float gs[];  // [rows][DW_CH]
     const int b = blockIdx.z, c = blockIdx.y * DW_CH + threadIdx.x;
     const int to0 = blockIdx.x * DW_TO;
@@ -60,7 +61,8 @@ __global__ void __launch_bounds__(DW_CH) glu_dwconv_bwd_kernel(const T* __restri
                                                                const float* __restrict__ w, T* __restrict__ dpre,
                                                                float* __restrict__ dw, float* __restrict__ db, int Tn, int To,
                                                                int C, int ksize, int stride_rt, int pad) {
-    pdl_trigger();   // programmatic dependent launch: a tcgen05 GEMM behind this kernel may start its prologue now
+    pdl_wait();      // (launched through avec_launch_pdl: nothing before this line touches global memory)
+    pdl_trigger();   // the kernel behind this one may be scheduled now
     const int stride = STRIDE > 0 ? STRIDE : stride_rt;   // compile-time stride (1 / 2): no division in the tap loops
     extern __shared__ float sm[];
     const int b = blockIdx.z, c = blockIdx.y * DW_CH + threadIdx.x;
@@ -154,7 +156,7 @@ extern "C" int avec_glu_dwconv_fwd(const void* pre, const float* w, const float*
     AVEC_DISPATCH_DTYPE(dtype, Tt, {
         auto kfn = glu_dwconv_fwd_kernel<Tt>;
         if (smem > 48 * 1024 && cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return AVEC_ERR_LAUNCH;
-        kfn<<<grid, DW_CH, smem, as_stream(stream)>>>((const Tt*)pre, w, bias, (Tt*)u, stats, T, To, C, ksize, stride, pad);
+        avec_launch_pdl(kfn, grid, dim3(DW_CH), smem, as_stream(stream), false, (const Tt*)pre, w, bias, (Tt*)u, stats, T, To, C, ksize, stride, pad);
     });
     AVEC_LAUNCH_CHECK();
     return AVEC_OK;
@@ -171,7 +173,7 @@ extern "C" int avec_glu_dwconv_bwd(const void* du, const void* pre, const float*
     AVEC_DISPATCH_DTYPE(dtype, Tt, {
         auto kfn = stride == 1 ? glu_dwconv_bwd_kernel<Tt, 1> : (stride == 2 ? glu_dwconv_bwd_kernel<Tt, 2> : glu_dwconv_bwd_kernel<Tt, 0>);
         if (smem > 48 * 1024 && cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return AVEC_ERR_LAUNCH;
-        kfn<<<grid, DW_CH, smem, as_stream(stream)>>>((const Tt*)du, (const Tt*)pre, w, (Tt*)dpre, dw, db, T, To, C, ksize, stride, pad);
+        avec_launch_pdl(kfn, grid, dim3(DW_CH), smem, as_stream(stream), false, (const Tt*)du, (const Tt*)pre, w, (Tt*)dpre, dw, db, T, To, C, ksize, stride, pad);
     });
     AVEC_LAUNCH_CHECK();
     return AVEC_OK;

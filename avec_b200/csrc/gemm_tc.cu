@@ -2213,23 +2213,6 @@ static int g_tma_enabled = 1;
 static bool g_tma_enabled_flag() { return g_tma_enabled != 0; }
 static unsigned long long* g_dbg_ts = nullptr;
 extern "C" void avec_set_tma(int enabled) { g_tma_enabled = enabled; }
-static int g_pdl_enabled = 1;
-static cudaStream_t g_pdl_excluded[8];
-static int g_pdl_nexcluded = 0;
-extern "C" void avec_set_pdl(int enabled) { g_pdl_enabled = enabled; }
-extern "C" void avec_pdl_exclude_stream(avec_stream_t stream, int enabled) {
-    if (!enabled) { g_pdl_nexcluded = 0; return; }
-    cudaStream_t st = as_stream(stream);
-    for (int i = 0; i < g_pdl_nexcluded; ++i) if (g_pdl_excluded[i] == st) return;
-    if (g_pdl_nexcluded < 8) g_pdl_excluded[g_pdl_nexcluded++] = st;
-}
-static bool pdl_for_stream(cudaStream_t st) {
-    static int env = -1;
-    if (env < 0) { const char* e = getenv("AVEC_PDL"); env = e ? atoi(e) : 1; }
-    if (!env || !g_pdl_enabled) return false;
-    for (int i = 0; i < g_pdl_nexcluded; ++i) if (g_pdl_excluded[i] == st) return false;
-    return true;
-}
 extern "C" void avec_set_debug_timestamps(void* dev_buf_8_u64) { g_dbg_ts = reinterpret_cast<unsigned long long*>(dev_buf_8_u64); }
 
 bool avec_gemm_tc_supported(const avec_gemm_args* a) {
@@ -2664,21 +2647,10 @@ static int gemm_tc_launch(const avec_gemm_args* a, cudaStream_t st, const DgradC
     // persistent launch when both operands are TMA-fed (the gather producers double as epilogue warps, so gather kinds keep
     // one tile per CTA); two CTAs per SM when shared memory and TMEM (2 x BN columns each) allow it
     long long ctas = any_gather ? tiles : std::min<long long>(tiles, (long long)num_sms * ctas_per_sm);
-    if (pdl_for_stream(st)) {
-        // programmatic dependent launch: this grid may be scheduled while the preceding kernel of the stream drains (after all its
-        // CTAs passed pdl_trigger() or exited); its CTAs set up barriers / TMEM / descriptors and then wait in pdl_wait()
-        cudaLaunchConfig_t cfg;
-        memset(&cfg, 0, sizeof(cfg));
-        cfg.gridDim = dim3((unsigned)ctas, 1, 1);
-        cfg.blockDim = dim3(epi_groups == 2 ? TC_THREADS_WIDE : TC_THREADS, 1, 1);
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        cudaLaunchKernelEx(&cfg, gemm_tc_kernel, p, mapA, mapB);
+    // programmatic dependent launch (AVEC_PDL_SMALL_ONLY does not apply: a parked GEMM grid is one CTA per SM): this grid may be
+    // scheduled while the preceding kernel of the stream drains; its CTAs set up barriers / TMEM / descriptors, then pdl_wait()
+    if (avec_pdl_for_stream(st)) {
+        avec_launch_pdl(gemm_tc_kernel, dim3((unsigned)ctas), dim3(epi_groups == 2 ? TC_THREADS_WIDE : TC_THREADS), smem, st, true, p, mapA, mapB);
         AVEC_LAUNCH_CHECK();
         return AVEC_OK;
     }

@@ -16,7 +16,8 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const T* __restrict_
                                                             const float* __restrict__ beta, T* __restrict__ y,
                                                             float* __restrict__ mean, float* __restrict__ rstd, int B,
                                                             int Tn, int Tp, int C, int P, float eps, long long ldy) {
-    pdl_trigger();   // programmatic dependent launch: a tcgen05 GEMM behind this kernel may start its prologue now
+    pdl_wait();      // (launched through avec_launch_pdl: nothing before this line touches global memory)
+    pdl_trigger();   // the kernel behind this one may be scheduled now
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= B * Tp) return;
     const int b = warp / Tp, tp = warp % Tp;
@@ -92,7 +93,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict_
                                                             const float* __restrict__ rstd, const T* __restrict__ dres,
                                                             int res_stride, T* __restrict__ dx, float* __restrict__ dgamma,
                                                             float* __restrict__ dbeta, int B, int Tn, int Tp, int C, int P) {
-    pdl_trigger();   // programmatic dependent launch: a tcgen05 GEMM behind this kernel may start its prologue now
+    pdl_wait();      // (launched through avec_launch_pdl: nothing before this line touches global memory)
+    pdl_trigger();   // the kernel behind this one may be scheduled now
     extern __shared__ float red[];  // [2][C]
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const long long rows = (long long)B * Tn;
@@ -199,7 +201,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict_
 template <typename T, int V>
 __global__ void upsample_add_kernel(const T* __restrict__ x, const T* __restrict__ o, T* __restrict__ y, int Tn, int Tp, int C,
                                     int P, long long total) {
-    pdl_trigger();   // programmatic dependent launch: a tcgen05 GEMM behind this kernel may start its prologue now
+    pdl_wait();      // (launched through avec_launch_pdl: nothing before this line touches global memory)
+    pdl_trigger();   // the kernel behind this one may be scheduled now
     const int Cv = C / V;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         int c = (int)(i % Cv) * V;
@@ -217,7 +220,8 @@ __global__ void upsample_add_kernel(const T* __restrict__ x, const T* __restrict
 
 template <typename T, int V>
 __global__ void pool_sum_kernel(const T* __restrict__ dy, T* __restrict__ dout, int Tn, int Tp, int C, int P, long long total, long long ldo) {
-    pdl_trigger();   // programmatic dependent launch: a tcgen05 GEMM behind this kernel may start its prologue now
+    pdl_wait();      // (launched through avec_launch_pdl: nothing before this line touches global memory)
+    pdl_trigger();   // the kernel behind this one may be scheduled now
     const int Cv = C / V;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         int c = (int)(i % Cv) * V;
@@ -301,7 +305,8 @@ constexpr int CR_THREADS = 512;
 template <typename F, int V>
 __global__ void __launch_bounds__(CR_THREADS) colreduce_kernel(F f_in, long long rows, int C, long long rows_per_block,
                                                                float* __restrict__ out0, float* __restrict__ out1, float alpha) {
-    pdl_trigger();   // programmatic dependent launch: a tcgen05 GEMM behind this kernel may start its prologue now
+    pdl_wait();      // (launched through avec_launch_pdl: nothing before this line touches global memory)
+    pdl_trigger();   // the kernel behind this one may be scheduled now
     __shared__ float s0[CR_THREADS * V];
     __shared__ float s1[CR_THREADS * V];
     F f = f_in;
@@ -364,7 +369,7 @@ int launch_colreduce(const F& f, long long rows, int C, float* out0, float* out1
     long long rpb = cdivll(rows, nchunk);
     nchunk = cdivll(rows, rpb);
     dim3 grid(gx, (unsigned)nchunk), block(X, Y);
-    colreduce_kernel<F, V><<<grid, block, 0, st>>>(f, rows, C, rpb, out0, out1, alpha);
+    avec_launch_pdl(colreduce_kernel<F, V>, dim3(grid), dim3(block), 0, st, false, f, rows, C, rpb, out0, out1, alpha);
     return 0;
 }
 
@@ -518,6 +523,7 @@ __global__ void __launch_bounds__(CR_THREADS) bn_bwd_reduce_kernel(const T* __re
                                                                    const float* __restrict__ scale, const float* __restrict__ shift,
                                                                    const float* __restrict__ mean, const float* __restrict__ rstd, long long rows, int C,
                                                                    long long rows_per_block, int act, float* __restrict__ out0, float* __restrict__ out1) {
+    pdl_wait();      // (launched through avec_launch_pdl: nothing before this line touches global memory)
     __shared__ float s0[CR_THREADS * V];
     __shared__ float s1[CR_THREADS * V];
     const int X = blockDim.x, Y = blockDim.y;
@@ -597,8 +603,8 @@ int launch_bn_bwd_reduce(const T* dy, const T* u, const T* res, const float* sca
     const long long rpb = cdivll(rows, nchunk);
     nchunk = cdivll(rows, rpb);
     dim3 grid(gx, (unsigned)nchunk), block(X, Y);
-    if (res) bn_bwd_reduce_kernel<T, V, RR, true><<<grid, block, 0, st>>>(dy, u, res, scale, shift, mean, rstd, rows, C, rpb, act, sums, sums + C);
-    else bn_bwd_reduce_kernel<T, V, RN, false><<<grid, block, 0, st>>>(dy, u, res, scale, shift, mean, rstd, rows, C, rpb, act, sums, sums + C);
+    if (res) avec_launch_pdl(bn_bwd_reduce_kernel<T, V, RR, true>, dim3(grid), dim3(block), 0, st, false, dy, u, res, scale, shift, mean, rstd, rows, C, rpb, act, sums, sums + C);
+    else avec_launch_pdl(bn_bwd_reduce_kernel<T, V, RN, false>, dim3(grid), dim3(block), 0, st, false, dy, u, res, scale, shift, mean, rstd, rows, C, rpb, act, sums, sums + C);
     return 0;
 }
 
@@ -608,7 +614,8 @@ __global__ void bn_finalize_kernel(const float* __restrict__ stats, const float*
                                    float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean,
                                    float* __restrict__ rstd, float* __restrict__ rmean, float* __restrict__ rvar,
                                    float inv_count, float unbias, int C, float eps, float momentum, int replicas) {
-    pdl_trigger();   // programmatic dependent launch: a tcgen05 GEMM behind this kernel may start its prologue now
+    pdl_wait();      // (launched through avec_launch_pdl: nothing before this line touches global memory)
+    pdl_trigger();   // the kernel behind this one may be scheduled now
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     float s1 = 0.0f, s2 = 0.0f;
@@ -638,6 +645,7 @@ __global__ void bn_eval_affine_kernel(const float* __restrict__ gamma, const flo
 template <typename T, int V>
 __global__ void bn_apply_kernel(const T* __restrict__ u, const float* __restrict__ scale, const float* __restrict__ shift,
                                 const T* __restrict__ res, T* __restrict__ y, long long totalv, int C, int act, long long ldy) {
+    pdl_wait();      // (launched through avec_launch_pdl: nothing before this line touches global memory)
     const int Cv = C / V;
     // output element offset of flat (dense) element e: rows of y may be pitched (GEMM operands with TMA-able rows)
     auto yoff = [&](size_t e) -> size_t { return ldy == C ? e : (e / C) * (size_t)ldy + e % C; };
@@ -685,6 +693,7 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restric
                                     const float* __restrict__ shift, const T* __restrict__ res, const float* __restrict__ mean,
                                     const float* __restrict__ rstd, const float* __restrict__ gamma, const float* __restrict__ sums,
                                     T* __restrict__ du, T* __restrict__ dres, long long totalv, int C, int act, float inv_count) {
+    pdl_wait();      // (launched through avec_launch_pdl: nothing before this line touches global memory)
     const int Cv = C / V;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const bool fixed_c = (stride % Cv) == 0;
@@ -870,7 +879,8 @@ __global__ void zero_upsample_kernel(const T* __restrict__ in, T* __restrict__ o
 
 template <typename TI, typename TO>
 __global__ void convert_kernel(const TI* __restrict__ src, long long lds, TO* __restrict__ dst, long long ldd, int C, long long total) {
-    pdl_trigger();   // programmatic dependent launch: a tcgen05 GEMM behind this kernel may start its prologue now
+    pdl_wait();      // (launched through avec_launch_pdl: nothing before this line touches global memory)
+    pdl_trigger();   // the kernel behind this one may be scheduled now
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         int c = (int)(i % C);
         long long r = i / C;
@@ -879,7 +889,8 @@ __global__ void convert_kernel(const TI* __restrict__ src, long long lds, TO* __
 }
 // contiguous fp32 -> bf16, 8 elements per thread
 __global__ void convert_f32_bf16_vec_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long totalv) {
-    pdl_trigger();   // programmatic dependent launch: a tcgen05 GEMM behind this kernel may start its prologue now
+    pdl_wait();      // (launched through avec_launch_pdl: nothing before this line touches global memory)
+    pdl_trigger();   // the kernel behind this one may be scheduled now
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < totalv; i += (long long)gridDim.x * blockDim.x) {
         float v[8];
         load_vec<8>(src + i * 8, v);
@@ -903,7 +914,7 @@ extern "C" int avec_layernorm_fwd(const void* x, const float* gamma, const float
     const int Tp = cdiv(T, P);
     const long long warps = (long long)B * Tp;
     const int blocks = (int)cdivll(warps * 32, 256);
-    AVEC_DISPATCH_DTYPE(dtype, Tt, (layernorm_fwd_kernel<Tt><<<blocks, 256, 0, as_stream(stream)>>>(
+    AVEC_DISPATCH_DTYPE(dtype, Tt, (avec_launch_pdl(layernorm_fwd_kernel<Tt>, dim3(blocks), dim3(256), 0, as_stream(stream), false, 
         (const Tt*)x, gamma, beta, (Tt*)y, mean, rstd, B, T, Tp, C, P, eps, ldy)));
     AVEC_LAUNCH_CHECK();
     return AVEC_OK;
@@ -920,7 +931,7 @@ extern "C" int avec_layernorm_bwd(const void* dy, const void* x, const float* ga
     // (Conformer sizes are 3-13 k rows: ~100-300 CTAs) beat one row per warp (profiles/r02_ncu_norm_kernels.md)
     int blocks = (int)std::min<long long>(std::max<long long>(cdivll(rows, 32), 1), 148LL * 2);
     size_t smem = 2 * (size_t)C * sizeof(float);
-    AVEC_DISPATCH_DTYPE(dtype, Tt, (layernorm_bwd_kernel<Tt><<<blocks, 256, smem, as_stream(stream)>>>(
+    AVEC_DISPATCH_DTYPE(dtype, Tt, (avec_launch_pdl(layernorm_bwd_kernel<Tt>, dim3(blocks), dim3(256), smem, as_stream(stream), false, 
         (const Tt*)dy, (const Tt*)x, gamma, mean, rstd, (const Tt*)dres, dres ? res_stride : 0, (Tt*)dx, dgamma, dbeta, B, T, Tp, C, P)));
     AVEC_LAUNCH_CHECK();
     return AVEC_OK;
@@ -930,7 +941,7 @@ extern "C" int avec_upsample_add(const void* x, const void* o, void* y, int B, i
                                  avec_stream_t stream) {
     AVEC_CHECK_ARG(x && o && y && B > 0 && T > 0 && P >= 1 && Tp == cdiv(T, P));
     long long total = (long long)B * T * C;
-    AVEC_DISPATCH_DTYPE_VEC(dtype, C, Tt, V, (upsample_add_kernel<Tt, V><<<ew_blocks(total / V), 256, 0, as_stream(stream)>>>(
+    AVEC_DISPATCH_DTYPE_VEC(dtype, C, Tt, V, (avec_launch_pdl(upsample_add_kernel<Tt, V>, dim3(ew_blocks(total / V)), dim3(256), 0, as_stream(stream), false, 
         (const Tt*)x, (const Tt*)o, (Tt*)y, T, Tp, C, P, total / V)));
     AVEC_LAUNCH_CHECK();
     return AVEC_OK;
@@ -940,7 +951,7 @@ extern "C" int avec_pool_sum(const void* dy, void* dout, int B, int T, int Tp, i
     if (ldo <= 0) ldo = C;
     AVEC_CHECK_ARG(dy && dout && B > 0 && T > 0 && P >= 1 && Tp == cdiv(T, P) && ldo >= C && ldo % 4 == 0);
     long long total = (long long)B * Tp * C;
-    AVEC_DISPATCH_DTYPE_VEC(dtype, C, Tt, V, (pool_sum_kernel<Tt, V><<<ew_blocks(total / V), 256, 0, as_stream(stream)>>>(
+    AVEC_DISPATCH_DTYPE_VEC(dtype, C, Tt, V, (avec_launch_pdl(pool_sum_kernel<Tt, V>, dim3(ew_blocks(total / V)), dim3(256), 0, as_stream(stream), false, 
         (const Tt*)dy, (Tt*)dout, T, Tp, C, P, total / V, ldo)));
     AVEC_LAUNCH_CHECK();
     return AVEC_OK;
@@ -998,7 +1009,7 @@ extern "C" int avec_bn_finalize(const float* stats, const float* gamma, const fl
                                 float momentum, int replicas, avec_stream_t stream) {
     AVEC_CHECK_ARG(stats && scale && shift && count > 0 && C > 0 && replicas >= 1);
     float unbias = count > 1 ? (float)((double)count / (double)(count - 1)) : 1.0f;
-    bn_finalize_kernel<<<cdiv(C, 128), 128, 0, as_stream(stream)>>>(stats, gamma, beta, scale, shift, mean, rstd, running_mean,
+    avec_launch_pdl(bn_finalize_kernel, dim3(cdiv(C, 128)), dim3(128), 0, as_stream(stream), false, stats, gamma, beta, scale, shift, mean, rstd, running_mean,
                                                                    running_var, (float)(1.0 / (double)count), unbias, C, eps, momentum, replicas);
     AVEC_LAUNCH_CHECK();
     return AVEC_OK;
@@ -1017,7 +1028,7 @@ extern "C" int avec_bn_apply(const void* u, const float* scale, const float* shi
     if (ldy <= 0) ldy = C;
     AVEC_CHECK_ARG(u && scale && shift && y && rows > 0 && C > 0 && ldy >= C && ldy % 4 == 0);
     long long total = rows * C;
-    AVEC_DISPATCH_DTYPE_VEC(dtype, C, Tt, V, (bn_apply_kernel<Tt, V><<<ew_blocks(total / V), 256, 0, as_stream(stream)>>>(
+    AVEC_DISPATCH_DTYPE_VEC(dtype, C, Tt, V, (avec_launch_pdl(bn_apply_kernel<Tt, V>, dim3(ew_blocks(total / V)), dim3(256), 0, as_stream(stream), false, 
         (const Tt*)u, scale, shift, (const Tt*)res, (Tt*)y, total / V, C, act, ldy)));
     AVEC_LAUNCH_CHECK();
     return AVEC_OK;
@@ -1040,7 +1051,7 @@ extern "C" int avec_bn_bwd_apply(const void* dy, const void* u, const float* sca
                                  long long rows, int C, int act, int dtype, avec_stream_t stream) {
     AVEC_CHECK_ARG(dy && u && scale && shift && mean && rstd && sums && du && rows > 0 && C > 0);
     long long total = rows * C;
-    AVEC_DISPATCH_DTYPE_VEC(dtype, C, Tt, V, (bn_bwd_apply_kernel<Tt, V><<<ew_blocks(total / V), 256, 0, as_stream(stream)>>>(
+    AVEC_DISPATCH_DTYPE_VEC(dtype, C, Tt, V, (avec_launch_pdl(bn_bwd_apply_kernel<Tt, V>, dim3(ew_blocks(total / V)), dim3(256), 0, as_stream(stream), false, 
         (const Tt*)dy, (const Tt*)u, scale, shift, (const Tt*)res, mean, rstd, gamma, sums, (Tt*)du, (Tt*)dres, total / V, C, act,
         (float)(1.0 / (double)rows))));
     AVEC_LAUNCH_CHECK();
@@ -1162,7 +1173,8 @@ extern "C" int avec_convert_multi(const avec_copy_job* jobs_dev, const int* chun
 }
 
 __global__ void __launch_bounds__(256) unpad_heads_kernel(const float* __restrict__ src, float* __restrict__ dst, int d, int dp, long long K, long long total) {
-    pdl_trigger();   // programmatic dependent launch: a tcgen05 GEMM behind this kernel may start its prologue now
+    pdl_wait();      // (launched through avec_launch_pdl: nothing before this line touches global memory)
+    pdl_trigger();   // the kernel behind this one may be scheduled now
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long c = i % K, row = i / K;
         const long long g = row / d, r = row - g * d;
@@ -1172,7 +1184,7 @@ __global__ void __launch_bounds__(256) unpad_heads_kernel(const float* __restric
 extern "C" int avec_unpad_heads(const float* src, float* dst, long long groups, int d, int dp, long long K, avec_stream_t stream) {
     AVEC_CHECK_ARG(src && dst && groups > 0 && d > 0 && dp >= d && K > 0);
     const long long total = groups * d * K;
-    unpad_heads_kernel<<<ew_blocks(total), 256, 0, as_stream(stream)>>>(src, dst, d, dp, K, total);
+    avec_launch_pdl(unpad_heads_kernel, dim3(ew_blocks(total)), dim3(256), 0, as_stream(stream), false, src, dst, d, dp, K, total);
     AVEC_LAUNCH_CHECK();
     return AVEC_OK;
 }
@@ -1185,11 +1197,11 @@ extern "C" int avec_convert(const void* src, int src_dtype, long long lds, void*
     int blocks = ew_blocks(total);
     if (src_dtype == AVEC_F32 && dst_dtype == AVEC_BF16 && lds == C && ldd == C && total % 8 == 0 &&
         ((uintptr_t)src & 31) == 0 && ((uintptr_t)dst & 15) == 0)
-        convert_f32_bf16_vec_kernel<<<ew_blocks(total / 8), 256, 0, st>>>((const float*)src, (bf16*)dst, total / 8);
-    else if (src_dtype == AVEC_F32 && dst_dtype == AVEC_BF16) convert_kernel<float, bf16><<<blocks, 256, 0, st>>>((const float*)src, lds, (bf16*)dst, ldd, C, total);
-    else if (src_dtype == AVEC_BF16 && dst_dtype == AVEC_F32) convert_kernel<bf16, float><<<blocks, 256, 0, st>>>((const bf16*)src, lds, (float*)dst, ldd, C, total);
-    else if (src_dtype == AVEC_F32 && dst_dtype == AVEC_F32) convert_kernel<float, float><<<blocks, 256, 0, st>>>((const float*)src, lds, (float*)dst, ldd, C, total);
-    else if (src_dtype == AVEC_BF16 && dst_dtype == AVEC_BF16) convert_kernel<bf16, bf16><<<blocks, 256, 0, st>>>((const bf16*)src, lds, (bf16*)dst, ldd, C, total);
+        avec_launch_pdl(convert_f32_bf16_vec_kernel, dim3(ew_blocks(total / 8)), dim3(256), 0, st, false, (const float*)src, (bf16*)dst, total / 8);
+    else if (src_dtype == AVEC_F32 && dst_dtype == AVEC_BF16) avec_launch_pdl(convert_kernel<float, bf16>, dim3(blocks), dim3(256), 0, st, false, (const float*)src, lds, (bf16*)dst, ldd, C, total);
+    else if (src_dtype == AVEC_BF16 && dst_dtype == AVEC_F32) avec_launch_pdl(convert_kernel<bf16, float>, dim3(blocks), dim3(256), 0, st, false, (const bf16*)src, lds, (float*)dst, ldd, C, total);
+    else if (src_dtype == AVEC_F32 && dst_dtype == AVEC_F32) avec_launch_pdl(convert_kernel<float, float>, dim3(blocks), dim3(256), 0, st, false, (const float*)src, lds, (float*)dst, ldd, C, total);
+    else if (src_dtype == AVEC_BF16 && dst_dtype == AVEC_BF16) avec_launch_pdl(convert_kernel<bf16, bf16>, dim3(blocks), dim3(256), 0, st, false, (const bf16*)src, lds, (bf16*)dst, ldd, C, total);
     else return AVEC_ERR_INVALID;
     AVEC_LAUNCH_CHECK();
     return AVEC_OK;

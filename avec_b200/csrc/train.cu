@@ -23,7 +23,8 @@ __global__ void __launch_bounds__(256) dropout_kernel(const T* __restrict__ x, c
                                                       long long rows, int C, uint32_t thresh, float scale,
                                                       const unsigned long long* __restrict__ rng, uint32_t site, int Tf, int Tp,
                                                       int P, long long ldy) {
-    pdl_trigger();   // programmatic dependent launch: a tcgen05 GEMM behind this kernel may start its prologue now
+    pdl_wait();      // (launched through avec_launch_pdl: nothing before this line touches global memory)
+    pdl_trigger();   // the kernel behind this one may be scheduled now
     const int per_row = (C + V - 1) / V;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows * per_row) return;
@@ -62,7 +63,7 @@ extern "C" int avec_dropout(const void* x, const void* res, void* y, long long r
 #define AVEC_DROP_LAUNCH(T, V)                                                                                         \
     do {                                                                                                               \
         const long long n = rows * ((C + V - 1) / V);                                                                  \
-        dropout_kernel<T, V><<<(unsigned)cdivll(n, 256), 256, 0, st>>>((const T*)x, (const T*)res, (T*)y, rows, C, thresh, \
+        avec_launch_pdl(dropout_kernel<T, V>, dim3((unsigned)cdivll(n, 256)), dim3(256), 0, st, false, (const T*)x, (const T*)res, (T*)y, rows, C, thresh, \
                                                                        scale, rng_state, (uint32_t)site, Tf, Tp, P, ldy); \
     } while (0)
     AVEC_DISPATCH_DTYPE(dtype, T, {
