@@ -97,13 +97,17 @@ def _gemm(args, may_decline=False):
 
 
 ERR_UNSUPPORTED = -3
-FUSE_DROPOUT = os.environ.get("AVEC_FUSE_DROPOUT", "1") != "0"
+# nn.Dropout inside the GEMM epilogue - 0: never, 1: wherever the kernel can, 2 (default): only behind GEMMs whose output is not wider
+# than twice their contraction (FFN second Linear, attention output projection, ConvModule's last pointwise conv).  The wide, short
+# ones (FFN first Linear: 4D outputs from D inputs) are bound by their 4-8 epilogue warps, where the Philox draws cost more than the
+# separate full-occupancy dropout kernel they replace (profiles/r02_launches_train_graph.md).
+FUSE_DROPOUT = int(os.environ.get("AVEC_FUSE_DROPOUT", "2"))
 
 
 def _gemm_drop(args, drop):
     """launch with nn.Dropout fused into the epilogue (drop = (rng, p, site)); False: this operand / epilogue combination has no
     fused form (fp32 parity mode, SIMT implementation, unaligned rows) and the caller runs GEMM + avec_dropout instead."""
-    if not FUSE_DROPOUT:
+    if not FUSE_DROPOUT or (int(FUSE_DROPOUT) == 2 and args.N > 2 * args.K):
         return False
     rng, p, site = drop
     args.drop_p, args.drop_site, args.drop_rng = float(p), int(site), rng.data_ptr()
