@@ -507,7 +507,8 @@ def main():
                                    f"64000 audio samples + {101 if args.model == 'AV' else 100}x88x88 video",
                        "global_batch": world * B, "parallelism": f"dp{world}", "bn": "SyncBatchNorm (all-reduced statistics)" if (world > 1 and args.sync_bn) else "local batch statistics", "optimizer": args.optimizer,
                        "allreduce": (f"{len(buckets.buckets)} fp32 bucket(s), NCCL all-reduce (AVG) launched from backward hooks on a communication stream, captured in the CUDA graph" if buckets is not None else None),
-                       "streams": (2 if (args.model == "AV" and args.overlap and not (world > 1 and args.sync_bn)) else 1), "loss": args.loss, "cuda_graph": bool(use_graph),
+                       "streams": (3 if (args.model == "AV" and args.overlap and not (world > 1 and args.sync_bn)) else 1),   # caller + audio branch + video branch
+                       "launch": "programmatic dependent launch (GEMM / attention / small kernels)" + (" on the caller's stream only" if args.model == "AV" and args.overlap else ""), "loss": args.loss, "cuda_graph": bool(use_graph),
                        "weights": "fp32 masters converted to bf16 kernel layout inside every timed step",
                        "l2": "inputs+activations per step (>1 GB) exceed the 126 MB L2; no flush needed",
                        "algorithmic_tflop_per_step": algo_tf, "achieved_tflops_whole_step": whole,
