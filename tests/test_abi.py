@@ -28,11 +28,39 @@ def test_library_exports_every_declared_symbol():
     assert lib.avec_strerror(-3) == b"combination not implemented"
 
 
-def test_struct_layout_matches_c():
-    # sizeof(avec_gemm_args) as laid out by the C compiler: 5 ints, ptr, 2 ll, ptr, 2 ll, int, geom(18 ints), ...
+def test_struct_layout_matches_c(tmp_path):
+    """the header is plain C: gcc lays the argument structs out, and the ctypes mirrors must agree on size and on every field offset
+    (a field added on one side only would shift everything behind it without any error at the call)"""
     import ctypes
+    import shutil
+    import subprocess
     assert ctypes.sizeof(L.ConvGeom) == 18 * 4
-    assert ctypes.sizeof(L.GemmArgs) % 8 == 0
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    structs = {"avec_conv_geom": L.ConvGeom, "avec_gemm_args": L.GemmArgs, "avec_copy_job": L.CopyJob}
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "avec_b200.h"', "int main(void) {"]
+    for cname, cls in structs.items():
+        lines.append(f'    printf("{cname} sizeof %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'    printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["    return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines) + "\n")
+    exe = tmp_path / "layout"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    seen = 0
+    for ln in out:
+        if not ln:
+            continue
+        cname, field, value = ln.split()
+        cls = structs[cname]
+        want = ctypes.sizeof(cls) if field == "sizeof" else getattr(cls, field).offset
+        assert int(value) == want, f"{cname}.{field}: C {value}, ctypes {want}"
+        seen += 1
+    assert seen == sum(len(c._fields_) + 1 for c in structs.values())
+    assert L.COPY_CHUNK == 4096        # AVEC_COPY_CHUNK of the header (chunk table granularity of avec_convert_multi)
 
 
 def test_ops_refuse_cpu_tensors():
