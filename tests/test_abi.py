@@ -66,3 +66,21 @@ def test_struct_layout_matches_c(tmp_path):
 def test_ops_refuse_cpu_tensors():
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         ops.linear_fwd(torch.zeros(4, 8), torch.zeros(4, 8))
+
+
+def test_fused_dropout_policy_declines_before_any_launch():
+    """ops.FUSE_DROPOUT: 0 never fuses, 2 (default) leaves GEMMs whose output is wider than twice the contraction to the separate
+    dropout kernel - both decided on the host, before the library is called"""
+    a = L.GemmArgs()
+    prev = ops.FUSE_DROPOUT
+    try:
+        ops.FUSE_DROPOUT = 2
+        a.N, a.K = 720, 180            # FFN first Linear: epilogue-bound
+        assert ops._gemm_drop(a, (None, 0.1, 3)) is False
+        ops.FUSE_DROPOUT = 0
+        a.N, a.K = 180, 720
+        assert ops._gemm_drop(a, (None, 0.1, 3)) is False
+        assert a.drop_p == 0.0 and not a.drop_rng
+    finally:
+        ops.FUSE_DROPOUT = prev
+    assert prev == int(os.environ.get("AVEC_FUSE_DROPOUT", "2"))
